@@ -1,0 +1,46 @@
+"""gradus_b200 -- B200-native geodesic hot path behind Gradus.jl's tracing API.
+
+Host-side mirror (Python, because no Julia toolchain exists in this image) of the slice
+of the reference's public API that sits on the per-ray integration path:
+
+    tracegeodesics   (src/tracing/tracing.jl:66-80)
+    rendergeodesics  (src/rendering/rendering.jl:28-54)
+    lineprofile      (src/line-profiles.jl:152-198, BinningMethod)
+
+with the same argument meaning, defaults and error behaviour, and a new ensemble type
+`EnsembleB200` next to `EnsembleEndpointThreads` (src/Gradus.jl:412).  All compute goes
+through the C ABI of include/gradus_b200.h (libgradus_b200.so, hand-written sm_100a CUDA);
+there is no CPU fallback."""
+from .api import (  # noqa: F401
+    BinningMethod,
+    ConstPointFunctions,
+    DatumPlane,
+    EnsembleB200,
+    EnsembleEndpointThreads,
+    GeodesicPoints,
+    GeometricGrid,
+    InverseGrid,
+    JohannsenPsaltisMetric,
+    KerrMetric,
+    LinearGrid,
+    PolarChart,
+    PolarPlane,
+    PowerLawEmissivity,
+    ShakuraSunyaev,
+    StatusCodes,
+    TabulatedEmissivity,
+    ThinDisc,
+    TracingConfiguration,
+    chart_for_metric,
+    domain_upper_hemisphere,
+    impact_axes,
+    inner_radius,
+    isco,
+    lineprofile,
+    rendergeodesics,
+    tracegeodesics,
+    tracing_configuration,
+)
+from ._cabi import GradusB200Error  # noqa: F401
+
+__version__ = "0.1.0"

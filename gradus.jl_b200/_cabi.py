@@ -1,0 +1,181 @@
+"""ctypes mirror of include/gradus_b200.h and loader for libgradus_b200.so.
+
+This is the same binding surface a Julia maintainer reaches with ``ccall`` (see
+INTEGRATION.md).  There is no CPU fallback: if the CUDA library is missing or no
+device is usable, every compute call raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libgradus_b200.so")
+
+# ---- constants (include/gradus_b200.h) -------------------------------------
+OK = 0
+ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = -1, -2, -3, -4, -5
+STATUS_OUT_OF_DOMAIN, STATUS_WITHIN_INNER_BOUNDARY, STATUS_INTERSECTED, STATUS_NO_STATUS = 0, 1, 2, 3
+METRIC_KERR, METRIC_JP = 0, 1
+GEOMETRY_NONE, GEOMETRY_THIN_DISC, GEOMETRY_SHAKURA_SUNYAEV, GEOMETRY_DATUM_PLANE = 0, 1, 2, 3
+CALLBACK_NONE, CALLBACK_UPPER_HEMISPHERE = 0, 1
+POW_EXACT, POW_FAST32 = 0, 1
+IC_RENDER_GRID, IC_POLAR_PLANE, IC_EXPLICIT = 0, 1, 2
+GRID_LINEAR, GRID_GEOMETRIC, GRID_INVERSE = 0, 1, 2
+PF_SHADOW, PF_REDSHIFT, PF_DISC_RADIUS, PF_COORDINATE_TIME, PF_STATUS, PF_AFFINE_TIME = 0, 1, 2, 3, 4, 5
+EMISSIVITY_POWERLAW, EMISSIVITY_TABLE = 0, 1
+FLAG_MAXITERS, FLAG_DT_MIN, FLAG_UNSTABLE = 1, 2, 4
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class Problem(C.Structure):
+    _fields_ = [
+        ("metric_kind", C.c_int32), ("geometry_kind", C.c_int32), ("callback_kind", C.c_int32), ("pow_mode", C.c_int32),
+        ("metric_params", C.c_double * 4), ("observer", C.c_double * 4), ("geometry_params", C.c_double * 4),
+        ("gtol", C.c_double), ("chart_inner", C.c_double), ("chart_outer", C.c_double), ("callback_delta", C.c_double),
+        ("lambda_min", C.c_double), ("lambda_max", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double),
+        ("dtmax", C.c_double), ("mu", C.c_double), ("maxiters", C.c_int64),
+    ]
+
+
+class IC(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("grid_kind", C.c_int32), ("width", C.c_int64), ("height", C.c_int64),
+        ("lo0", C.c_double), ("hi0", C.c_double), ("lo1", C.c_double), ("hi1", C.c_double),
+        ("x", _dp * 4), ("v", _dp * 4), ("n", C.c_int64),
+    ]
+
+
+class Range(C.Structure):
+    _fields_ = [("first", C.c_int64), ("count", C.c_int64), ("stride", C.c_int64)]
+
+
+class Endpoints(C.Structure):
+    _fields_ = [
+        ("status", _ip), ("lambda_max", _dp), ("x", _dp * 4), ("v", _dp * 4), ("x_init", _dp * 4), ("v_init", _dp * 4),
+        ("naccept", _ip), ("nreject", _ip), ("flags", _ip),
+    ]
+
+
+class Emissivity(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n", C.c_int32), ("index", C.c_double), ("r", _dp), ("eps", _dp)]
+
+
+class PlungingTable(C.Structure):
+    _fields_ = [("n", C.c_int32), ("r", _dp), ("ut", _dp), ("ur", _dp), ("uphi", _dp)]
+
+
+class LineProfileOpts(C.Structure):
+    _fields_ = [("min_re", C.c_double), ("max_re", C.c_double), ("normalise", C.c_int32), ("bin_right_closed", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("kernel_ms", C.c_double), ("total_ms", C.c_double), ("rays", C.c_int64), ("steps_accepted", C.c_int64),
+        ("steps_rejected", C.c_int64), ("launches", C.c_int64), ("flagged", C.c_int64),
+    ]
+
+
+#: every symbol include/gradus_b200.h declares
+EXPORTED_SYMBOLS = (
+    "gb200_version", "gb200_init", "gb200_destroy", "gb200_last_error", "gb200_get_stats", "gb200_validate",
+    "gb200_isco", "gb200_radiative_efficiency", "gb200_trace", "gb200_render", "gb200_lineprofile",
+    "gb200_render_device", "gb200_lineprofile_device", "gb200_fp64_peak",
+)
+
+
+def dptr(a):
+    """double* of a C-contiguous float64 numpy array (None -> NULL)."""
+    if a is None:
+        return C.cast(None, _dp)
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_dp)
+
+
+def iptr(a):
+    if a is None:
+        return C.cast(None, _ip)
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_ip)
+
+
+class EndpointArrays:
+    """Caller-owned host SoA for `count` rays plus the ctypes view handed to the library."""
+
+    def __init__(self, count, init=True, stats=True):
+        n = int(count)
+        self.status = np.full(n, -1, np.int32)
+        self.lambda_max = np.zeros(n)
+        self.x = np.zeros((4, n))
+        self.v = np.zeros((4, n))
+        self.x_init = np.zeros((4, n)) if init else None
+        self.v_init = np.zeros((4, n)) if init else None
+        self.naccept = np.zeros(n, np.int32) if stats else None
+        self.nreject = np.zeros(n, np.int32) if stats else None
+        self.flags = np.zeros(n, np.int32) if stats else None
+        e = Endpoints()
+        e.status = iptr(self.status)
+        e.lambda_max = dptr(self.lambda_max)
+        for k in range(4):
+            e.x[k] = dptr(self.x[k])
+            e.v[k] = dptr(self.v[k])
+            e.x_init[k] = dptr(self.x_init[k]) if init else C.cast(None, _dp)
+            e.v_init[k] = dptr(self.v_init[k]) if init else C.cast(None, _dp)
+        e.naccept = iptr(self.naccept)
+        e.nreject = iptr(self.nreject)
+        e.flags = iptr(self.flags)
+        self.c = e
+
+
+_lib = None
+
+
+class GradusB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libgradus_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load():
+    """dlopen libgradus_b200.so and set prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GradusB200Error(ERR_NO_DEVICE, f"{LIB_PATH} not built; run __graft_entry__.build() (no CPU fallback exists)")
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.gb200_version.restype = C.c_int
+    lib.gb200_init.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.gb200_destroy.argtypes = [vp]
+    lib.gb200_destroy.restype = None
+    lib.gb200_last_error.argtypes = [vp]
+    lib.gb200_last_error.restype = C.c_char_p
+    lib.gb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.gb200_validate.argtypes = [C.POINTER(Problem), C.POINTER(IC)]
+    lib.gb200_isco.argtypes = [C.c_int32, _dp, _dp]
+    lib.gb200_radiative_efficiency.argtypes = [C.c_int32, _dp, _dp]
+    lib.gb200_trace.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range), C.POINTER(Endpoints)]
+    lib.gb200_render.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range), _ip, C.c_int32,
+                                 C.POINTER(PlungingTable), C.POINTER(_dp)]
+    lib.gb200_lineprofile.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range), C.POINTER(Emissivity),
+                                      C.POINTER(PlungingTable), _dp, C.c_int32, C.POINTER(LineProfileOpts), _dp]
+    lib.gb200_render_device.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range), _ip, C.c_int32,
+                                        C.POINTER(PlungingTable), C.POINTER(vp), vp, C.c_int]
+    lib.gb200_lineprofile_device.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range),
+                                             C.POINTER(Emissivity), C.POINTER(PlungingTable), _dp, C.c_int32,
+                                             C.POINTER(LineProfileOpts), vp, vp, C.c_int]
+    lib.gb200_fp64_peak.argtypes = [vp, _dp]
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(lib, name)
+        if name not in ("gb200_destroy", "gb200_last_error", "gb200_version"):
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(code, ctx=None):
+    if code != OK:
+        msg = load().gb200_last_error(ctx)
+        raise GradusB200Error(code, msg.decode() if msg else "?")

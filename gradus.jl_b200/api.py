@@ -1,0 +1,639 @@
+"""Host-side mirror of the reference's tracing front-end for the in-scope path.
+
+Everything here is argument plumbing: it flattens the reference's configuration objects
+(`TracingConfiguration`, src/tracing/configuration.jl:3-125) into the POD structs of
+include/gradus_b200.h and calls the C ABI.  The Julia extension described in
+INTEGRATION.md does exactly the same with `ccall`."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import threading
+from dataclasses import dataclass, field
+from typing import Any, Callable, Optional, Sequence
+
+import numpy as np
+
+from . import _cabi as cabi
+
+DEFAULT_TOLERANCE = 1e-9  # src/tracing/configuration.jl:1
+
+
+class StatusCodes:
+    """src/Gradus.jl:59-64 (declaration order = integer value)."""
+
+    OutOfDomain = 0
+    WithinInnerBoundary = 1
+    IntersectedWithGeometry = 2
+    NoStatus = 3
+
+
+# --------------------------------------------------------------------------- metrics
+@dataclass(frozen=True)
+class KerrMetric:
+    """src/metrics/kerr-metric.jl:62-68"""
+
+    M: float = 1.0
+    a: float = 0.0
+    kind = cabi.METRIC_KERR
+
+    def params(self):
+        return (float(self.M), float(self.a), 0.0, 0.0)
+
+
+@dataclass(frozen=True)
+class JohannsenPsaltisMetric:
+    """src/metrics/johannsen-psaltis-ad.jl:38-46 (`eps3` is the reference's `ϵ3`)."""
+
+    M: float = 1.0
+    a: float = 0.0
+    eps3: float = 0.0
+    kind = cabi.METRIC_JP
+
+    def params(self):
+        return (float(self.M), float(self.a), float(self.eps3), 0.0)
+
+
+_SUPPORTED_METRICS = (KerrMetric, JohannsenPsaltisMetric)
+
+
+def _check_metric(m):
+    if not isinstance(m, _SUPPORTED_METRICS):
+        raise ValueError(f"EnsembleB200 supports KerrMetric and JohannsenPsaltisMetric only, got {type(m).__name__} (no CPU fallback)")
+
+
+def inner_radius(m) -> float:
+    """kerr-metric.jl:72 / johannsen-psaltis-ad.jl:50"""
+    _check_metric(m)
+    return m.M + math.sqrt(m.M**2 - m.a**2)
+
+
+def _metric_params_array(m):
+    return (C.c_double * 4)(*m.params())
+
+
+def isco(m) -> float:
+    """Innermost stable circular orbit (kerr-metric.jl:91; src/special-radii.jl:14-60). Host arithmetic in the library."""
+    _check_metric(m)
+    out = C.c_double()
+    cabi.check(cabi.load().gb200_isco(m.kind, _metric_params_array(m), C.byref(out)))
+    return out.value
+
+
+# --------------------------------------------------------------------------- geometry
+@dataclass(frozen=True)
+class ThinDisc:
+    """src/geometry/discs/thin-disc.jl:9-14"""
+
+    inner_radius: float = 0.0
+    outer_radius: float = 500.0
+
+    def to_c(self):
+        return cabi.GEOMETRY_THIN_DISC, (float(self.inner_radius), float(self.outer_radius), 0.0, 0.0)
+
+
+@dataclass(frozen=True)
+class DatumPlane:
+    """src/geometry/discs/datum-plane.jl:1-10"""
+
+    height: float = 0.0
+
+    def to_c(self):
+        return cabi.GEOMETRY_DATUM_PLANE, (float(self.height), 0.0, 0.0, 0.0)
+
+
+class ShakuraSunyaev:
+    """src/geometry/discs/shakura-sunyaev.jl:22-52.  `ShakuraSunyaev(m; eddington_ratio, η)`."""
+
+    def __init__(self, m, eddington_ratio=0.3, eta=None):
+        _check_metric(m)
+        self.inner_radius = isco(m)
+        if eta is None:
+            out = C.c_double()
+            cabi.check(cabi.load().gb200_radiative_efficiency(m.kind, _metric_params_array(m), C.byref(out)))
+            eta = out.value
+        self.Mdot_Medd = float(eddington_ratio)
+        self.inv_eta = 1.0 / eta
+
+    def to_c(self):
+        return cabi.GEOMETRY_SHAKURA_SUNYAEV, (self.Mdot_Medd, self.inv_eta, self.inner_radius, 0.0)
+
+
+_SUPPORTED_GEOMETRY = (ThinDisc, ShakuraSunyaev, DatumPlane)
+
+
+# --------------------------------------------------------------------------- charts and callbacks
+@dataclass(frozen=True)
+class PolarChart:
+    """src/tracing/charts.jl:3-6"""
+
+    inner_radius: float
+    outer_radius: float
+
+
+def chart_for_metric(m, outer_radius=12000.0, closest_approach=1.01):
+    """src/tracing/charts.jl:51-58"""
+    return PolarChart(inner_radius(m) * closest_approach, float(outer_radius))
+
+
+@dataclass(frozen=True)
+class UpperHemisphereCallback:
+    delta: float = 1e-4
+
+
+def domain_upper_hemisphere(delta=1e-4):
+    """src/tracing/callbacks.jl:31-39"""
+    return UpperHemisphereCallback(float(delta))
+
+
+# --------------------------------------------------------------------------- image planes
+@dataclass(frozen=True)
+class LinearGrid:
+    kind = cabi.GRID_LINEAR
+
+
+@dataclass(frozen=True)
+class GeometricGrid:
+    kind = cabi.GRID_GEOMETRIC
+
+
+@dataclass(frozen=True)
+class InverseGrid:
+    kind = cabi.GRID_INVERSE
+
+
+@dataclass(frozen=True)
+class PolarPlane:
+    """src/image-planes/planes.jl:70-91"""
+
+    grid: Any = field(default_factory=GeometricGrid)
+    Nr: int = 400
+    Ntheta: int = 100
+    r_min: float = 1.0
+    r_max: float = 250.0
+    theta_min: float = 0.0
+    theta_max: float = 2 * math.pi
+
+    def trajectory_count(self):
+        return self.Nr * self.Ntheta
+
+
+@dataclass(frozen=True)
+class RenderGrid:
+    """The closure returned by `_render_velocity_function` (src/rendering/rendering.jl:140-163) as data."""
+
+    image_width: int
+    image_height: int
+    alpha_lims: tuple
+    beta_lims: tuple
+
+    def trajectory_count(self):
+        return self.image_width * self.image_height
+
+
+# --------------------------------------------------------------------------- ensembles
+class EnsembleB200:
+    """New ensemble type (next to `EnsembleEndpointThreads`, src/Gradus.jl:412): rays are
+    integrated on the listed CUDA devices by libgradus_b200.  One context per device."""
+
+    def __init__(self, devices: Sequence[int] = (0,)):
+        self.devices = tuple(int(d) for d in devices)
+        if not self.devices:
+            raise ValueError("EnsembleB200 needs at least one device")
+        self._ctx = {}
+
+    def ctx(self, device):
+        if device not in self._ctx:
+            h = C.c_void_p()
+            cabi.check(cabi.load().gb200_init(device, C.byref(h)))
+            self._ctx[device] = h
+        return self._ctx[device]
+
+    def close(self):
+        for h in self._ctx.values():
+            cabi.load().gb200_destroy(h)
+        self._ctx = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self, device=None):
+        s = cabi.Stats()
+        cabi.check(cabi.load().gb200_get_stats(self.ctx(self.devices[0] if device is None else device), C.byref(s)))
+        return s
+
+
+class EnsembleEndpointThreads:
+    """The reference's CPU ensemble.  Not available here by design: there is no CPU fallback."""
+
+
+class BinningMethod:
+    """src/Gradus.jl:447"""
+
+
+# --------------------------------------------------------------------------- configuration
+@dataclass
+class TracingConfiguration:
+    """src/tracing/configuration.jl:3-88, restricted to what the device path supports."""
+
+    metric: Any
+    position: Any
+    velocity: Any
+    geometry: Any
+    chart: PolarChart
+    callback: Any
+    solver: str
+    ensemble: Any
+    trajectories: Optional[int]
+    lambda_domain: tuple
+    abstol: float
+    reltol: float
+    gtol: float = 1e-2
+    mu: float = 0.0
+    pow_mode: int = cabi.POW_EXACT
+    maxiters: int = 0
+    dtmax: float = 0.0
+    _keep: list = field(default_factory=list, repr=False)
+
+    def to_c(self):
+        """-> (gb200_problem, gb200_ic).  Raises ValueError for anything outside the hot-path scope."""
+        m = self.metric
+        _check_metric(m)
+        p = cabi.Problem()
+        p.metric_kind = m.kind
+        p.metric_params[:] = m.params()
+        if self.geometry is None:
+            p.geometry_kind = cabi.GEOMETRY_NONE
+        elif isinstance(self.geometry, _SUPPORTED_GEOMETRY):
+            p.geometry_kind, gp = self.geometry.to_c()
+            p.geometry_params[:] = gp
+        else:
+            raise ValueError(f"geometry {type(self.geometry).__name__} is outside the EnsembleB200 scope")
+        if self.callback is None:
+            p.callback_kind = cabi.CALLBACK_NONE
+        elif isinstance(self.callback, UpperHemisphereCallback):
+            p.callback_kind = cabi.CALLBACK_UPPER_HEMISPHERE
+            p.callback_delta = self.callback.delta
+        else:
+            raise ValueError("only `domain_upper_hemisphere` user callbacks can run on the device")
+        if not isinstance(self.chart, PolarChart):
+            raise ValueError("only PolarChart is supported")
+        if self.solver != "Tsit5":
+            raise ValueError("EnsembleB200 integrates with Tsit5 only")
+        p.pow_mode = self.pow_mode
+        p.gtol = self.gtol
+        p.chart_inner, p.chart_outer = self.chart.inner_radius, self.chart.outer_radius
+        p.lambda_min, p.lambda_max = float(self.lambda_domain[0]), float(self.lambda_domain[1])
+        p.abstol, p.reltol = float(self.abstol), float(self.reltol)
+        p.dtmax = float(self.dtmax)
+        p.mu = float(self.mu)
+        p.maxiters = int(self.maxiters)
+
+        ic = cabi.IC()
+        v = self.velocity
+        pos = np.asarray(self.position, np.float64)
+        if isinstance(v, RenderGrid):
+            if not (v.alpha_lims[0] <= v.alpha_lims[1] and v.beta_lims[0] <= v.beta_lims[1]):
+                raise AssertionError("α/β limits must be sorted")  # rendering.jl:148-149
+            p.observer[:] = pos
+            ic.kind = cabi.IC_RENDER_GRID
+            ic.width, ic.height = v.image_width, v.image_height
+            ic.lo0, ic.hi0 = map(float, v.alpha_lims)
+            ic.lo1, ic.hi1 = map(float, v.beta_lims)
+            ic.n = v.trajectory_count()
+        elif isinstance(v, PolarPlane):
+            p.observer[:] = pos
+            ic.kind = cabi.IC_POLAR_PLANE
+            ic.grid_kind = v.grid.kind
+            ic.width, ic.height = v.Nr, v.Ntheta
+            ic.lo0, ic.hi0 = float(v.r_min), float(v.r_max)
+            ic.lo1, ic.hi1 = float(v.theta_min), float(v.theta_max)
+            ic.n = v.trajectory_count()
+        else:
+            # explicit SoA: what the Julia shim builds by evaluating prob_func on host threads
+            if callable(v):
+                if self.trajectories is None:
+                    raise ValueError("When velocity is a function, trajectories must be defined.")  # configuration.jl:47-49
+                vs = np.array([np.asarray(v(i + 1), np.float64) for i in range(self.trajectories)])
+            else:
+                vs = np.atleast_2d(np.asarray(v, np.float64))
+                if self.trajectories is not None and vs.shape[0] == 1 and pos.ndim == 1:
+                    raise ValueError("Trajectories should be `nothing` when solving only a single geodesic problem.")
+            n = vs.shape[0]
+            xs = np.broadcast_to(pos, (n, 4)) if pos.ndim == 1 else pos
+            if xs.shape != (n, 4) or vs.shape != (n, 4):
+                raise ValueError("positions and velocities must be (n, 4)")
+            xs_soa = np.ascontiguousarray(xs.T)
+            vs_soa = np.ascontiguousarray(vs.T)
+            self._keep = [xs_soa, vs_soa]
+            p.observer[:] = xs[0]
+            ic.kind = cabi.IC_EXPLICIT
+            for k in range(4):
+                ic.x[k] = cabi.dptr(xs_soa[k])
+                ic.v[k] = cabi.dptr(vs_soa[k])
+            ic.n = n
+        cabi.check(cabi.load().gb200_validate(C.byref(p), C.byref(ic)))
+        return p, ic
+
+
+_CONFIG_KWARGS = {"chart", "callback", "solver", "ensemble", "trajectories", "abstol", "reltol", "gtol", "mu", "μ",
+                  "pow_mode", "maxiters", "dtmax", "save_on", "verbose", "progress_bar", "integrator_verbose"}
+
+
+def tracing_configuration(m, position, velocity, *args, **kwargs):
+    """`tracing_configuration` (src/geometry/bootstrap.jl:1-22, src/tracing/configuration.jl:90-138).
+
+    args = ([geometry], λ) with λ a number (λ_max) or a (λ_min, λ_max) pair."""
+    if len(args) == 1:
+        geometry, lam = None, args[0]
+    elif len(args) == 2:
+        geometry, lam = args
+    else:
+        raise TypeError("expected tracing_configuration(m, x, v, [geometry], λ)")
+    unknown = set(kwargs) - _CONFIG_KWARGS
+    if unknown:
+        # solver_opts reach `solve` with kwargshandle = KeywordArgError (tracing.jl:106,146,215); the device
+        # integrator has no further options, so every unknown keyword is an error.
+        raise TypeError(f"unrecognised keyword arguments for the B200 integrator: {sorted(unknown)}")
+    if kwargs.get("save_on", False):
+        raise ValueError("Cannot use `EnsembleB200` with `save_on`")  # tracing.jl:159-161
+    lam_dom = (0.0, float(lam)) if np.isscalar(lam) else (float(lam[0]), float(lam[1]))
+    ensemble = kwargs.get("ensemble", None)
+    if ensemble is None:
+        ensemble = EnsembleB200()
+    if not isinstance(ensemble, EnsembleB200):
+        raise ValueError("this build integrates on the GPU only: pass ensemble=EnsembleB200(...) (no CPU fallback)")
+    return TracingConfiguration(
+        metric=m,
+        position=position,
+        velocity=velocity,
+        geometry=geometry,
+        chart=kwargs.get("chart") or chart_for_metric(m),
+        callback=kwargs.get("callback"),
+        solver=kwargs.get("solver", "Tsit5"),
+        ensemble=ensemble,
+        trajectories=kwargs.get("trajectories"),
+        lambda_domain=lam_dom,
+        abstol=kwargs.get("abstol", DEFAULT_TOLERANCE),
+        reltol=kwargs.get("reltol", DEFAULT_TOLERANCE),
+        gtol=kwargs.get("gtol", 1e-2),
+        mu=kwargs.get("mu", kwargs.get("μ", 0.0)),
+        pow_mode=kwargs.get("pow_mode", cabi.POW_EXACT),
+        maxiters=kwargs.get("maxiters", 0),
+        dtmax=kwargs.get("dtmax", 0.0),
+    )
+
+
+# --------------------------------------------------------------------------- results
+class GeodesicPoints:
+    """SoA of `GeodesicPoint`s (src/solution-processing.jl:15-32); `gps[i]` gives one point."""
+
+    def __init__(self, arrays: cabi.EndpointArrays, lambda_min: float):
+        self.status = arrays.status
+        self.lambda_min = lambda_min
+        self.lambda_max = arrays.lambda_max
+        self.x_init, self.v_init = arrays.x_init, arrays.v_init
+        self.x, self.v = arrays.x, arrays.v
+        self.naccept, self.nreject, self.flags = arrays.naccept, arrays.nreject, arrays.flags
+
+    def __len__(self):
+        return len(self.status)
+
+    def __getitem__(self, i):
+        return dict(status=int(self.status[i]), lambda_min=self.lambda_min, lambda_max=float(self.lambda_max[i]),
+                    x_init=self.x_init[:, i].copy(), x=self.x[:, i].copy(), v_init=self.v_init[:, i].copy(),
+                    v=self.v[:, i].copy(), aux=None)
+
+
+def _shards(n, ndev):
+    """Contiguous ray blocks, one per device."""
+    base, rem = divmod(n, ndev)
+    out, first = [], 0
+    for d in range(ndev):
+        cnt = base + (1 if d < rem else 0)
+        out.append((first, cnt))
+        first += cnt
+    return out
+
+
+def _run_sharded(ensemble, n, fn):
+    """Call fn(ctx, first, count, slot) for each device concurrently (ctypes drops the GIL)."""
+    shards = [(d, f, c) for d, (f, c) in zip(ensemble.devices, _shards(n, len(ensemble.devices))) if c > 0]
+    errs = []
+
+    def work(slot, dev, first, count):
+        try:
+            fn(ensemble.ctx(dev), first, count, slot)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    if len(shards) == 1:
+        work(0, *shards[0])
+    else:
+        ths = [threading.Thread(target=work, args=(s,) + sh) for s, sh in enumerate(shards)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+    if errs:
+        raise errs[0]
+    return shards
+
+
+def solve_tracing_problem(config: TracingConfiguration) -> GeodesicPoints:
+    """`ensemble_solve_tracing_problem(::EnsembleB200, ...)`: the seam of src/tracing/tracing.jl:151-196."""
+    p, ic = config.to_c()
+    n = ic.n
+    out = cabi.EndpointArrays(n)
+    lib = cabi.load()
+
+    def fn(ctx, first, count, slot):
+        view = cabi.Endpoints()
+        off = first
+        view.status = C.cast(C.addressof(out.c.status.contents) + 4 * off, cabi._ip)
+        view.lambda_max = C.cast(C.addressof(out.c.lambda_max.contents) + 8 * off, cabi._dp)
+        for k in range(4):
+            for name in ("x", "v", "x_init", "v_init"):
+                src = getattr(out.c, name)[k]
+                getattr(view, name)[k] = C.cast(C.addressof(src.contents) + 8 * off, cabi._dp)
+        for name in ("naccept", "nreject", "flags"):
+            setattr(view, name, C.cast(C.addressof(getattr(out.c, name).contents) + 4 * off, cabi._ip))
+        rng = cabi.Range(first, count, 1)
+        cabi.check(lib.gb200_trace(ctx, C.byref(p), C.byref(ic), C.byref(rng), C.byref(view)), ctx)
+
+    _run_sharded(config.ensemble, n, fn)
+    return GeodesicPoints(out, config.lambda_domain[0])
+
+
+def tracegeodesics(m, position, velocity, *args, **kwargs) -> GeodesicPoints:
+    """`tracegeodesics(m, x, v | plane | velfunc, [geometry], λ; kwargs...)` (src/tracing/tracing.jl:66-80)."""
+    config = tracing_configuration(m, position, velocity, *args, **kwargs)
+    return solve_tracing_problem(config)
+
+
+# --------------------------------------------------------------------------- point functions
+@dataclass(frozen=True)
+class PointFunction:
+    """A point function the device can evaluate at the ray endpoint (src/point-functions.jl:81-125)."""
+
+    name: str
+    filter: Optional[str] = None
+
+    def __matmul__(self, other):  # pf ∘ filter
+        if not isinstance(other, FilterPointFunction):
+            raise TypeError("only composition with a FilterPointFunction is supported")
+        return PointFunction(self.name, other.name)
+
+    def kind(self):
+        table = {
+            ("affine_time", "early_term"): cabi.PF_SHADOW,
+            ("redshift", "intersected"): cabi.PF_REDSHIFT,
+            ("radius", "intersected"): cabi.PF_DISC_RADIUS,
+            ("coordinate_time", "intersected"): cabi.PF_COORDINATE_TIME,
+            ("status", None): cabi.PF_STATUS,
+            ("affine_time", None): cabi.PF_AFFINE_TIME,
+        }
+        key = (self.name, self.filter)
+        if key not in table:
+            raise ValueError(f"point function {key} has no device implementation")
+        return table[key]
+
+
+@dataclass(frozen=True)
+class FilterPointFunction:
+    name: str
+
+
+class ConstPointFunctions:
+    """src/const-point-functions.jl"""
+
+    @staticmethod
+    def filter_early_term():
+        return FilterPointFunction("early_term")
+
+    @staticmethod
+    def filter_intersected():
+        return FilterPointFunction("intersected")
+
+    @staticmethod
+    def affine_time():
+        return PointFunction("affine_time")
+
+    @staticmethod
+    def shadow():
+        return PointFunction("affine_time") @ FilterPointFunction("early_term")
+
+    @staticmethod
+    def redshift(m=None, u=None):
+        return PointFunction("redshift")
+
+    @staticmethod
+    def radius():
+        return PointFunction("radius")
+
+    @staticmethod
+    def coordinate_time():
+        return PointFunction("coordinate_time")
+
+
+def impact_axes(width, height, alpha_lims, beta_lims):
+    """src/rendering/utility.jl:43-47"""
+    return np.linspace(alpha_lims[0], alpha_lims[1], width), np.linspace(beta_lims[0], beta_lims[1], height)
+
+
+def _pop_alias(kwargs, names, default):
+    for nme in names:
+        if nme in kwargs:
+            return kwargs.pop(nme)
+    return default
+
+
+def rendergeodesics(m, position, *args, pf=None, image_width=375, image_height=250, ensemble=None, **kwargs):
+    """`rendergeodesics(m, x, [d], λ_max; pf, image_width, image_height, αlims, βlims, ensemble, ...)`
+    (src/rendering/rendering.jl:28-54).  Returns (α, β, image) with image of shape (H, W).
+
+    `pf` may also be a sequence of point functions: one fused trace, several images."""
+    alpha_lims = _pop_alias(kwargs, ("αlims", "alpha_lims"), (-60, 60))
+    beta_lims = _pop_alias(kwargs, ("βlims", "beta_lims"), (-40, 40))
+    velocity = RenderGrid(int(image_width), int(image_height), tuple(alpha_lims), tuple(beta_lims))
+    config = tracing_configuration(m, position, velocity, *args, ensemble=ensemble,
+                                   trajectories=image_width * image_height, **kwargs)
+    pfs = [ConstPointFunctions.shadow()] if pf is None else (list(pf) if isinstance(pf, (list, tuple)) else [pf])
+    kinds = np.array([f.kind() for f in pfs], np.int32)
+    p, ic = config.to_c()
+    n = ic.n
+    images = np.zeros((len(pfs), n))
+    lib = cabi.load()
+
+    def fn(ctx, first, count, slot):
+        ptrs = (cabi._dp * len(pfs))(*[C.cast(images[k].ctypes.data + 8 * first, cabi._dp) for k in range(len(pfs))])
+        rng = cabi.Range(first, count, 1)
+        cabi.check(lib.gb200_render(ctx, C.byref(p), C.byref(ic), C.byref(rng), cabi.iptr(kinds), len(pfs), None, ptrs), ctx)
+
+    _run_sharded(config.ensemble, n, fn)
+    alpha, beta = impact_axes(image_width, image_height, alpha_lims, beta_lims)
+    imgs = [images[k].reshape(image_width, image_height).T for k in range(len(pfs))]  # column-major (H, W)
+    return (alpha, beta, imgs[0]) if not isinstance(pf, (list, tuple)) else (alpha, beta, imgs)
+
+
+# --------------------------------------------------------------------------- line profiles
+@dataclass(frozen=True)
+class PowerLawEmissivity:
+    """ε(r) = r^-index"""
+
+    index: float = 3.0
+
+
+@dataclass(frozen=True)
+class TabulatedEmissivity:
+    r: Any
+    eps: Any
+
+
+def lineprofile(bins, emissivity, m, position, d, method=None, *, lambda_max=None, min_re=None, max_re=50.0,
+                plane=None, callback="default", ensemble=None, bin_right_closed=True, **solver_args):
+    """`lineprofile(bins, ε, m, u, d, ::BinningMethod; λ_max, minrₑ, maxrₑ, plane, callback, ...)`
+    (src/line-profiles.jl:152-198).  Returns (bins, flux ./ sum(flux))."""
+    if method is not None and not isinstance(method, BinningMethod):
+        raise ValueError("only BinningMethod() runs on the device (TransferFunctionMethod is a later row)")
+    lambda_max = _pop_alias(solver_args, ("λ_max",), lambda_max)
+    min_re = _pop_alias(solver_args, ("minrₑ",), min_re)
+    max_re = _pop_alias(solver_args, ("maxrₑ",), max_re)
+    bins = np.ascontiguousarray(bins, np.float64)
+    if lambda_max is None:
+        lambda_max = 2 * position[1]
+    if min_re is None:
+        min_re = isco(m)
+    if plane is None:
+        plane = PolarPlane(GeometricGrid(), Nr=450, Ntheta=1300, r_max=5 * max_re)
+    if callback == "default":
+        callback = domain_upper_hemisphere()
+    config = tracing_configuration(m, position, plane, d, (0.0, lambda_max), callback=callback, ensemble=ensemble,
+                                   **solver_args)
+    p, ic = config.to_c()
+    n = ic.n
+    lib = cabi.load()
+    emis = cabi.Emissivity()
+    keep = []
+    if isinstance(emissivity, PowerLawEmissivity):
+        emis.kind, emis.index = cabi.EMISSIVITY_POWERLAW, float(emissivity.index)
+    elif isinstance(emissivity, TabulatedEmissivity):
+        r = np.ascontiguousarray(emissivity.r, np.float64)
+        e = np.ascontiguousarray(emissivity.eps, np.float64)
+        keep += [r, e]
+        emis.kind, emis.n, emis.r, emis.eps = cabi.EMISSIVITY_TABLE, len(r), cabi.dptr(r), cabi.dptr(e)
+    else:
+        raise ValueError("emissivity must be PowerLawEmissivity or TabulatedEmissivity (a closure cannot cross the C ABI)")
+    opts = cabi.LineProfileOpts(float(min_re), float(max_re), 0, 1 if bin_right_closed else 0)
+    ndev = len(config.ensemble.devices)
+    partial = np.zeros((ndev, len(bins)))
+
+    def fn(ctx, first, count, slot):
+        rng = cabi.Range(first, count, 1)
+        cabi.check(lib.gb200_lineprofile(ctx, C.byref(p), C.byref(ic), C.byref(rng), C.byref(emis), None,
+                                         cabi.dptr(bins), len(bins), C.byref(opts), cabi.dptr(partial[slot])), ctx)
+
+    _run_sharded(config.ensemble, n, fn)
+    flux = partial.sum(axis=0)  # fixed device order: deterministic
+    return bins, flux / flux.sum()

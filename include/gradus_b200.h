@@ -1,0 +1,258 @@
+/*
+ * gradus_b200.h -- C ABI of libgradus_b200.so: the B200-native (sm_100a, FP64)
+ * implementation of Gradus.jl's per-ray geodesic integration hot path.
+ *
+ * This is the drop-in boundary for the reference's ensemble seam
+ *     Gradus.ensemble_solve_tracing_problem(ensemble, problem, config; ...)
+ *         reference: src/tracing/tracing.jl:113-196
+ *         (GPU specialisation it replaces: ext/GradusDiffEqGPUExt/GradusDiffEqGPUExt.jl:10-31)
+ * A Julia extension adds `struct EnsembleB200` plus one method of that function
+ * which fills the POD structs below from `TracingConfiguration` fields
+ * (src/tracing/configuration.jl:16-29) and `ccall`s into this library; see
+ * INTEGRATION.md for the binding.  Plain C only: pointers, sizes, PODs.
+ *
+ * Ownership: the caller owns every host buffer passed in; the library owns all
+ * device memory, streams and events inside `gb200_ctx`.  All calls are blocking.
+ * A context may be used from one thread at a time.  Every entry point returns
+ * GB200_OK (0) or a negative error code; the message is available through
+ * gb200_last_error().  Nothing here ever falls back to a CPU implementation:
+ * without a usable CUDA device gb200_init fails with GB200_ERR_NO_DEVICE.
+ */
+#ifndef GRADUS_B200_H
+#define GRADUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB200_VERSION 100 /* 0.1.0 */
+
+/* ---- error codes ------------------------------------------------------- */
+#define GB200_OK 0
+#define GB200_ERR_INVALID_ARGUMENT (-1) /* mirrors Julia ArgumentError / KeywordArgError */
+#define GB200_ERR_NO_DEVICE (-2)        /* no CUDA device: there is no CPU fallback */
+#define GB200_ERR_CUDA (-3)
+#define GB200_ERR_UNSUPPORTED (-4) /* configuration outside the hot-path scope */
+#define GB200_ERR_NOMEM (-5)
+
+/* ---- StatusCodes.T, declaration order of src/Gradus.jl:59-64 ----------- */
+#define GB200_STATUS_OUT_OF_DOMAIN 0
+#define GB200_STATUS_WITHIN_INNER_BOUNDARY 1
+#define GB200_STATUS_INTERSECTED_WITH_GEOMETRY 2
+#define GB200_STATUS_NO_STATUS 3
+
+/* ---- metrics: src/metrics/kerr-metric.jl:62-68, johannsen-psaltis-ad.jl:38-46 */
+#define GB200_METRIC_KERR 0              /* params: M, a          */
+#define GB200_METRIC_JOHANNSEN_PSALTIS 1 /* params: M, a, eps3    */
+
+/* ---- accretion geometry: src/geometry/discs/ --------------------------- */
+#define GB200_GEOMETRY_NONE 0
+#define GB200_GEOMETRY_THIN_DISC 1       /* thin-disc.jl:9-26       params: inner_radius, outer_radius */
+#define GB200_GEOMETRY_SHAKURA_SUNYAEV 2 /* shakura-sunyaev.jl:22-33 params: Mdot/Mdot_edd, inv_eta, inner_radius(isco) */
+#define GB200_GEOMETRY_DATUM_PLANE 3     /* datum-plane.jl:1-10     params: height */
+
+/* ---- user discrete callback: src/tracing/callbacks.jl:31-39 ------------ */
+#define GB200_CALLBACK_NONE 0
+#define GB200_CALLBACK_UPPER_HEMISPHERE 1 /* r cos(theta) < delta -> OutOfDomain */
+
+/* ---- step-controller pow(): DiffEqBase.fastpow is version dependent ---- */
+#define GB200_POW_EXACT 0 /* IEEE double pow */
+#define GB200_POW_FAST32 1 /* Float32 exp2(y*log2(x)) a la FastPower.jl */
+
+/* ---- integrator failure flags (SciML retcodes are invisible in GeodesicPoint) */
+#define GB200_FLAG_MAXITERS 1
+#define GB200_FLAG_DT_MIN 2
+#define GB200_FLAG_UNSTABLE 4
+
+/*
+ * Everything `TracingConfiguration` (src/tracing/configuration.jl:3-88) carries
+ * for the in-scope path, flattened.  Integrator: Tsit5 with OrdinaryDiffEq's
+ * default PI controller; only the fields below are configurable, anything else
+ * the reference would accept as `solver_opts` is rejected by the host shim.
+ */
+typedef struct gb200_problem {
+    int32_t metric_kind;
+    int32_t geometry_kind;
+    int32_t callback_kind;
+    int32_t pow_mode;
+    double metric_params[4];
+    double observer[4]; /* x = (t, r, theta, phi) shared by all rays unless the IC is explicit */
+    double geometry_params[4];
+    double gtol;           /* src/geometry/bootstrap.jl:8, default 1e-2 */
+    double chart_inner;    /* PolarChart.inner_radius, src/tracing/charts.jl:3-6 */
+    double chart_outer;    /* PolarChart.outer_radius */
+    double callback_delta; /* domain_upper_hemisphere(delta) */
+    double lambda_min;
+    double lambda_max;
+    double abstol;
+    double reltol;
+    double dtmax; /* <= 0 -> lambda_max - lambda_min (OrdinaryDiffEq default) */
+    double mu;    /* geodesic mass, 0 for photons (constrain_time, auto-diff.jl:161-173) */
+    int64_t maxiters; /* <= 0 -> 1000000 */
+} gb200_problem;
+
+/* ---- initial conditions ------------------------------------------------ */
+#define GB200_IC_RENDER_GRID 0 /* _render_velocity_function, src/rendering/rendering.jl:140-163 */
+#define GB200_IC_POLAR_PLANE 1 /* PolarPlane + promote_velfunc, src/image-planes/planes.jl:70-115,180-184 */
+#define GB200_IC_EXPLICIT 2    /* prob_func evaluated on the host into SoA (corona ensembles) */
+
+#define GB200_GRID_LINEAR 0    /* src/image-planes/grids.jl:32-36 */
+#define GB200_GRID_GEOMETRIC 1 /* grids.jl:11-20 */
+#define GB200_GRID_INVERSE 2   /* grids.jl:22-30 */
+
+typedef struct gb200_ic {
+    int32_t kind;
+    int32_t grid_kind; /* polar plane only */
+    /* render grid: ray i (0-based) -> col = i / height, row = i % height;
+       alpha = range(alpha_lo, alpha_hi, width)[col] + 1e-6, beta likewise */
+    int64_t width;  /* render: image_width ; polar: Nr */
+    int64_t height; /* render: image_height; polar: Ntheta */
+    double lo0, hi0; /* render: alpha limits; polar: r_min, r_max */
+    double lo1, hi1; /* render: beta  limits; polar: theta_min, theta_max */
+    /* explicit: host SoA, each pointer addresses n doubles; v[0] (v^t) is
+       ignored and re-constrained exactly like wrap_constraint does */
+    const double* x[4];
+    const double* v[4];
+    int64_t n; /* total number of rays described by this IC */
+} gb200_ic;
+
+/* Sub-range of rays handled by one call: indices first, first+stride, ...
+   (count of them).  Rays shard trivially across GPUs / ranks. */
+typedef struct gb200_range {
+    int64_t first;
+    int64_t count;
+    int64_t stride; /* >= 1 */
+} gb200_range;
+
+/* Caller-allocated host SoA, `count` entries each; any pointer may be NULL.
+   Field meaning: GeodesicPoint, src/solution-processing.jl:15-32. */
+typedef struct gb200_endpoints {
+    int32_t* status;
+    double* lambda_max;
+    double* x[4];
+    double* v[4];
+    double* x_init[4];
+    double* v_init[4];
+    int32_t* naccept; /* per-ray integrator statistics */
+    int32_t* nreject;
+    int32_t* flags;
+} gb200_endpoints;
+
+/* ---- point functions: src/const-point-functions.jl --------------------- */
+#define GB200_PF_SHADOW 0          /* affine_time o filter_early_term (default pf of render_into_image!, rendering.jl:93-95) */
+#define GB200_PF_REDSHIFT 1        /* redshift o filter_intersected (src/redshift.jl:192-220) */
+#define GB200_PF_DISC_RADIUS 2     /* r sin(theta) o filter_intersected */
+#define GB200_PF_COORDINATE_TIME 3 /* x[1] o filter_intersected */
+#define GB200_PF_STATUS 4          /* status as double, no filter */
+#define GB200_PF_AFFINE_TIME 5     /* lambda_max, no filter */
+
+/* ---- emissivity for the binned line profile ---------------------------- */
+#define GB200_EMISSIVITY_POWERLAW 0 /* eps(r) = r^(-index) */
+#define GB200_EMISSIVITY_TABLE 1    /* linear interpolation in (r, eps), clamped */
+
+typedef struct gb200_emissivity {
+    int32_t kind;
+    int32_t n;       /* table length */
+    double index;    /* power-law index */
+    const double* r; /* host, ascending */
+    const double* eps;
+} gb200_emissivity;
+
+/* Optional plunging-region velocity table for non-Kerr redshift
+   (interpolate_redshift, src/redshift.jl:246-276): columns r (ascending), u^t, u^r, u^phi. */
+typedef struct gb200_plunging_table {
+    int32_t n;
+    const double* r;
+    const double* ut;
+    const double* ur;
+    const double* uphi;
+} gb200_plunging_table;
+
+typedef struct gb200_lineprofile_opts {
+    double min_re;  /* minr_e, default isco(m)  (src/line-profiles.jl:163) */
+    double max_re;  /* maxr_e, default 50 */
+    int32_t normalise; /* 1: flux ./ sum(flux) (line-profiles.jl:197); 0: raw partial sums (multi-rank) */
+    int32_t bin_right_closed; /* 1: index = searchsortedfirst(bins, g) clamped (default); 0: searchsortedlast */
+} gb200_lineprofile_opts;
+
+/* Timing / counters of the last call on a context. */
+typedef struct gb200_stats {
+    double kernel_ms;      /* CUDA-event time of the trace kernel(s) */
+    double total_ms;       /* including H2D/D2H */
+    int64_t rays;
+    int64_t steps_accepted;
+    int64_t steps_rejected;
+    int64_t launches;      /* kernels launched by the call */
+    int64_t flagged;       /* rays with a non-zero failure flag */
+} gb200_stats;
+
+typedef struct gb200_ctx gb200_ctx;
+
+int gb200_version(void);
+
+/* Create a context on CUDA device `device` (ordinal).  One context per GPU;
+   multi-GPU callers create one per device (or one per rank). */
+int gb200_init(int device, gb200_ctx** out);
+void gb200_destroy(gb200_ctx* ctx);
+const char* gb200_last_error(gb200_ctx* ctx); /* ctx may be NULL: last global error */
+int gb200_get_stats(gb200_ctx* ctx, gb200_stats* out);
+
+/* Validate a configuration without running it (what the Julia shim calls first
+   so that unsupported set-ups raise ArgumentError before any work). */
+int gb200_validate(const gb200_problem* p, const gb200_ic* ic);
+
+/* Special radii needed to build configurations on the host.
+   isco: Kerr analytic (kerr-metric-first-order.jl:336-337); otherwise the root of
+   dE/dr (src/special-radii.jl:14-60).  Pure host arithmetic. */
+int gb200_isco(int32_t metric_kind, const double* metric_params, double* out);
+/* 1 - E_isco, i.e. the default eta of ShakuraSunyaev (shakura-sunyaev.jl:41-50). */
+int gb200_radiative_efficiency(int32_t metric_kind, const double* metric_params, double* out);
+
+/* ensemble_solve_tracing_problem(::EnsembleB200, ...) -> endpoints (tracing.jl:151-196). */
+int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic,
+                const gb200_range* range, gb200_endpoints* out);
+
+/* rendergeodesics fused path (rendering.jl:28-54,89-107): trace + point
+   function(s); writes `npf` images of `range->count` doubles each, image k at
+   images[k], ray order (for the full range this is the (H,W) column-major image). */
+int gb200_render(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic,
+                 const gb200_range* range, const int32_t* pointfns, int32_t npf,
+                 const gb200_plunging_table* plunging, double* const* images);
+
+/* lineprofile(::BinningMethod) fused path (src/line-profiles.jl:152-198):
+   trace + redshift + eps(r) g^3 area + bucket.  flux_out has nbins doubles. */
+int gb200_lineprofile(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic,
+                      const gb200_range* range, const gb200_emissivity* emis,
+                      const gb200_plunging_table* plunging,
+                      const double* bins, int32_t nbins,
+                      const gb200_lineprofile_opts* opts, double* flux_out);
+
+/* ---- device-resident variants (inputs/outputs stay in HBM) ------------- */
+/* Same as gb200_render but `d_images[k]` are DEVICE pointers on ctx's device and no
+   host copy is made; work is enqueued on `cuda_stream` (a cudaStream_t cast to
+   void*, NULL = the context's own stream) and the call returns without
+   synchronising when `async` != 0. */
+int gb200_render_device(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic,
+                        const gb200_range* range, const int32_t* pointfns, int32_t npf,
+                        const gb200_plunging_table* plunging, double* const* d_images,
+                        void* cuda_stream, int async);
+
+/* Raw (un-normalised) line-profile partial sums into a DEVICE buffer of nbins
+   doubles, ready for an NCCL all-reduce issued by the caller on the same stream. */
+int gb200_lineprofile_device(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic,
+                             const gb200_range* range, const gb200_emissivity* emis,
+                             const gb200_plunging_table* plunging,
+                             const double* bins, int32_t nbins,
+                             const gb200_lineprofile_opts* opts, double* d_flux,
+                             void* cuda_stream, int async);
+
+/* Dependent-free DFMA micro-benchmark: measured FP64 FMA throughput of the
+   device in TFLOP/s (2 flop per FMA); the roofline denominator. */
+int gb200_fp64_peak(gb200_ctx* ctx, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRADUS_B200_H */

@@ -1,0 +1,132 @@
+"""ctypes wrapper of the CPU oracle (oracle/gradus_oracle.cpp).  TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
+may import this module.  It reuses the POD struct layouts of include/gradus_b200.h (via the
+package's ctypes mirror) so the very same problem description can be handed to the
+oracle and to the CUDA library."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import gradus_b200._cabi as cabi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "gradus_oracle.cpp")
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        _lib = C.CDLL(LIB)
+    return _lib
+
+
+def max_threads():
+    return int(lib().oracle_max_threads())
+
+
+def _range(ic, rng):
+    if rng is None:
+        return cabi.Range(0, ic.n, 1)
+    return rng
+
+
+def trace(problem, ic, rng=None, nthreads=0, precision=0):
+    rng = _range(ic, rng)
+    out = cabi.EndpointArrays(rng.count)
+    rc = lib().oracle_trace(C.byref(problem), C.byref(ic), C.byref(rng), nthreads, precision, C.byref(out.c))
+    assert rc == 0
+    return out
+
+
+def render(problem, ic, pointfns, rng=None, nthreads=0, precision=0, plunging=None, endpoints=False):
+    rng = _range(ic, rng)
+    pfs = np.asarray(pointfns, np.int32)
+    imgs = np.zeros((len(pfs), rng.count))
+    ptrs = (cabi._dp * len(pfs))(*[cabi.dptr(imgs[k]) for k in range(len(pfs))])
+    out = cabi.EndpointArrays(rng.count) if endpoints else None
+    rc = lib().oracle_render(C.byref(problem), C.byref(ic), C.byref(rng), nthreads, precision, cabi.iptr(pfs), len(pfs),
+                             C.byref(plunging) if plunging is not None else None, ptrs,
+                             C.byref(out.c) if out is not None else None)
+    assert rc == 0
+    return (imgs, out) if endpoints else imgs
+
+
+def lineprofile(problem, ic, emis, bins, opts, rng=None, nthreads=0, precision=0, plunging=None, endpoints=False):
+    rng = _range(ic, rng)
+    bins = np.ascontiguousarray(bins, np.float64)
+    flux = np.zeros(len(bins))
+    out = cabi.EndpointArrays(rng.count) if endpoints else None
+    rc = lib().oracle_lineprofile(C.byref(problem), C.byref(ic), C.byref(rng), nthreads, precision, C.byref(emis),
+                                  C.byref(plunging) if plunging is not None else None, cabi.dptr(bins), len(bins),
+                                  C.byref(opts), cabi.dptr(flux), C.byref(out.c) if out is not None else None)
+    assert rc == 0
+    return (flux, out) if endpoints else flux
+
+
+def _mp(params):
+    a = np.zeros(4)
+    a[: len(params)] = params
+    return a
+
+
+def isco(kind, params, generic=False):
+    out = C.c_double()
+    mp = _mp(params)
+    fn = lib().oracle_generic_isco if generic else lib().oracle_isco
+    fn(kind, cabi.dptr(mp), C.byref(out))
+    return out.value
+
+
+def circular_energy(kind, params, r):
+    out = C.c_double()
+    mp = _mp(params)
+    lib().oracle_circular_energy(kind, cabi.dptr(mp), C.c_double(r), C.byref(out))
+    return out.value
+
+
+def circular_fourvelocity(kind, params, r):
+    v = np.zeros(4)
+    mp = _mp(params)
+    lib().oracle_circular_fourvelocity(kind, cabi.dptr(mp), C.c_double(r), cabi.dptr(v))
+    return v
+
+
+def metric(kind, params, r, th):
+    g, dr, dth = np.zeros(5), np.zeros(5), np.zeros(5)
+    mp = _mp(params)
+    lib().oracle_metric(kind, cabi.dptr(mp), C.c_double(r), C.c_double(th), cabi.dptr(g), cabi.dptr(dr), cabi.dptr(dth))
+    return g, dr, dth
+
+
+def rhs(kind, params, u):
+    u = np.ascontiguousarray(u, np.float64)
+    du = np.zeros(8)
+    mp = _mp(params)
+    lib().oracle_rhs(kind, cabi.dptr(mp), cabi.dptr(u), cabi.dptr(du))
+    return du
+
+
+def lnrbasis(kind, params, r, th):
+    b, f = np.zeros(16), np.zeros(16)
+    mp = _mp(params)
+    lib().oracle_lnrbasis(kind, cabi.dptr(mp), C.c_double(r), C.c_double(th), cabi.dptr(b), cabi.dptr(f))
+    return b.reshape(4, 4), f.reshape(4, 4)
+
+
+def initial_state(problem, alpha, beta):
+    u = np.zeros(8)
+    lib().oracle_initial_velocity(C.byref(problem), C.c_double(alpha), C.c_double(beta), cabi.dptr(u))
+    return u
