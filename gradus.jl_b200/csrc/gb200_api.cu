@@ -1,0 +1,552 @@
+// gb200_api.cu -- the C ABI of include/gradus_b200.h: context, validation, host-side problem
+// set-up (observer LNRF constants, special radii), device buffer management and launches.
+// No CPU implementation of the path exists in this library: every compute entry point runs
+// the sm_100a kernels of gb200_trace.cu or fails.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "gb200_device.cuh"
+#include "gb200_internal.h"
+
+// ---------------------------------------------------------------- errors
+static thread_local std::string g_last_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct gb200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    std::string err;
+    gb200_stats stats{};
+    std::vector<DevBuf> pool;
+    unsigned long long* d_queue = nullptr; // [0] queue, [1..3] counters
+    double fp64_peak = 0.0;
+};
+
+static int fail(gb200_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (ctx) ctx->err = buf;
+    return code;
+}
+#define CU(ctx, call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess) return fail(ctx, GB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+// ---------------------------------------------------------------- host-only dual number (d/dr), for the ISCO root find
+struct D1 {
+    double v, d;
+    GB_HD D1(double v_ = 0.0, double d_ = 0.0) : v(v_), d(d_) {}
+    GB_HD friend D1 operator+(const D1& a, const D1& b) { return D1(a.v + b.v, a.d + b.d); }
+    GB_HD friend D1 operator-(const D1& a, const D1& b) { return D1(a.v - b.v, a.d - b.d); }
+    GB_HD friend D1 operator-(const D1& a) { return D1(-a.v, -a.d); }
+    GB_HD friend D1 operator*(const D1& a, const D1& b) { return D1(a.v * b.v, a.d * b.v + a.v * b.d); }
+    GB_HD friend D1 operator/(const D1& a, const D1& b) { double q = a.v / b.v; return D1(q, (a.d - q * b.d) / b.v); }
+};
+static inline D1 dsqrt(const D1& a) { double s = std::sqrt(a.v); return D1(s, a.d / (2.0 * s)); }
+static inline double dsqrt(double a) { return std::sqrt(a); }
+static inline double val(const D1& a) { return a.v; }
+static inline double val(double a) { return a; }
+
+// E = -u_t of the equatorial circular orbit at radius r (CircularOrbits.energy, src/orbits/circular-orbits.jl:11-52)
+template <class S>
+static S circular_energy_host(int kind, const double* mp, S r) {
+    S g[5], dr[5], dth[5];
+    if (kind == GB200_METRIC_KERR) kerr_metric_jacobian<S>(mp[0], mp[1], r, S(1.0), S(0.0), g, dr, dth);
+    else jp_metric_jacobian<S>(mp[0], mp[1], mp[2], r, S(1.0), S(0.0), g, dr, dth);
+    const S D = g[0] * g[3] - g[4] * g[4];
+    const S gitt = g[3] / D, giphph = g[0] / D, gitph = -g[4] / D;
+    const S Om = -(dr[4] - dsqrt(dr[4] * dr[4] - dr[0] * dr[3])) / dr[3];
+    const S A = -(Om * gitt - gitph);
+    const S B = (Om * gitph - giphph);
+    const S denom = B * B * gitt + 2.0 * A * B * gitph + A * A * giphph;
+    const double sg = val(denom) > 0 ? 1.0 : (val(denom) < 0 ? -1.0 : 0.0);
+    const S ad = val(denom) < 0 ? -denom : denom;
+    const S d = -sg * dsqrt(S(1.0) / ad);
+    return -(B * d);
+}
+
+static double kerr_isco_host(double M, double a) { // Bardeen et al. (1972), kerr-metric-first-order.jl:297-337
+    const double x = a / M;
+    const double Z1 = 1 + std::cbrt(1 - x * x) * (std::cbrt(1 + x) + std::cbrt(1 - x));
+    const double Z2 = std::sqrt(3 * x * x + Z1 * Z1);
+    const double s = std::sqrt((3 - Z1) * (3 + Z1 + 2 * Z2));
+    return a > 0.0 ? M * (3 + Z2 - s) : M * (3 + Z2 + s);
+}
+
+// isco(::AbstractStaticAxisSymmetric): bracket from find_isco_bounds, then the root of dE/dr (special-radii.jl:14-60)
+static int generic_isco_host(int kind, const double* mp, double* out) {
+    double lower = 0, upper = 0;
+    for (long n = 0;; ++n) {
+        const double r = 100.0 - 0.005 * (double)n;
+        if (r < 1.0) break;
+        const double en = circular_energy_host<double>(kind, mp, r);
+        if (std::fabs(en) > 1.0) { lower = r; upper = 100.0; break; }
+    }
+    if (lower == upper) return GB200_ERR_INVALID_ARGUMENT;
+    auto dE = [&](double r) { return circular_energy_host<D1>(kind, mp, D1(r, 1.0)).d; };
+    double lo = lower, hi = upper, flo = dE(lo);
+    for (int it = 0; it < 200; ++it) {
+        const double mid = lo + (hi - lo) / 2;
+        if (!(mid > lo && mid < hi)) break;
+        const double fm = dE(mid);
+        if (fm == 0) { lo = hi = mid; break; }
+        if ((fm > 0) == (flo > 0)) { lo = mid; flo = fm; } else hi = mid;
+    }
+    *out = lo + (hi - lo) / 2;
+    return GB200_OK;
+}
+
+// ---------------------------------------------------------------- validation
+static int validate(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic) {
+    if (!p || !ic) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null problem or ic");
+    if (p->metric_kind != GB200_METRIC_KERR && p->metric_kind != GB200_METRIC_JOHANNSEN_PSALTIS)
+        return fail(ctx, GB200_ERR_UNSUPPORTED, "metric kind %d is outside the hot-path scope (Kerr, JohannsenPsaltis)", p->metric_kind);
+    const double M = p->metric_params[0], a = p->metric_params[1];
+    if (!(M > 0) || !(std::fabs(a) <= M)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "need M > 0 and |a| <= M (M=%g a=%g)", M, a);
+    if (p->geometry_kind < GB200_GEOMETRY_NONE || p->geometry_kind > GB200_GEOMETRY_DATUM_PLANE)
+        return fail(ctx, GB200_ERR_UNSUPPORTED, "geometry kind %d is outside the hot-path scope", p->geometry_kind);
+    if (p->geometry_kind == GB200_GEOMETRY_THIN_DISC && !(p->geometry_params[0] <= p->geometry_params[1]))
+        return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "ThinDisc needs inner_radius <= outer_radius");
+    if (p->callback_kind != GB200_CALLBACK_NONE && p->callback_kind != GB200_CALLBACK_UPPER_HEMISPHERE)
+        return fail(ctx, GB200_ERR_UNSUPPORTED, "callback kind %d cannot run on the device", p->callback_kind);
+    if (p->pow_mode != GB200_POW_EXACT && p->pow_mode != GB200_POW_FAST32) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad pow_mode");
+    if (!(p->lambda_max > p->lambda_min)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "need lambda_max > lambda_min");
+    if (!(p->abstol > 0) || !(p->reltol > 0)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "abstol and reltol must be positive");
+    if (!(p->chart_outer > p->chart_inner)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "chart outer radius must exceed inner radius");
+    if (ic->kind == GB200_IC_RENDER_GRID) {
+        if (ic->width < 1 || ic->height < 1) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "image size must be positive");
+        if (!(ic->lo0 <= ic->hi0) || !(ic->lo1 <= ic->hi1)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "alpha / beta limits must be sorted");
+        if (ic->n != ic->width * ic->height) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "ic.n != width*height");
+    } else if (ic->kind == GB200_IC_POLAR_PLANE) {
+        if (ic->width < 2 || ic->height < 1) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "PolarPlane needs Nr >= 2, Ntheta >= 1");
+        if (ic->grid_kind < GB200_GRID_LINEAR || ic->grid_kind > GB200_GRID_INVERSE) return fail(ctx, GB200_ERR_UNSUPPORTED, "grid kind %d", ic->grid_kind);
+        if (!(ic->lo0 > 0) || !(ic->hi0 > ic->lo0)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "PolarPlane needs 0 < r_min < r_max");
+        if (ic->n != ic->width * ic->height) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "ic.n != Nr*Ntheta");
+    } else if (ic->kind == GB200_IC_EXPLICIT) {
+        if (ic->n < 1) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "explicit IC needs n >= 1");
+        for (int k = 0; k < 4; ++k)
+            if (!ic->x[k] || !ic->v[k]) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "explicit IC pointers must be non-null");
+    } else return fail(ctx, GB200_ERR_UNSUPPORTED, "ic kind %d", ic->kind);
+    return GB200_OK;
+}
+
+static int validate_range(gb200_ctx* ctx, const gb200_ic* ic, const gb200_range* rg) {
+    if (!rg) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null range");
+    if (rg->count < 0 || rg->first < 0 || rg->stride < 1) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad range");
+    if (rg->count > 0 && rg->first + (rg->count - 1) * rg->stride >= ic->n) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "range exceeds the %lld rays of the IC", (long long)ic->n);
+    return GB200_OK;
+}
+
+// ---------------------------------------------------------------- problem -> kernel parameters (host arithmetic)
+static void dd_step(double lo, double hi, int64_t n, double* shi, double* slo) { // (hi-lo)/(n-1) as double-double
+    if (n <= 1) { *shi = 0; *slo = 0; return; }
+    const long double s = ((long double)hi - (long double)lo) / (long double)(n - 1);
+    *shi = (double)s;
+    *slo = (double)(s - (long double)*shi);
+}
+
+static void fill_params(const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, GbParams& P) {
+    memset(&P, 0, sizeof P);
+    P.metric_kind = p->metric_kind;
+    P.M = p->metric_params[0]; P.a = p->metric_params[1]; P.eps3 = p->metric_params[2];
+    P.lam0 = p->lambda_min; P.lam1 = p->lambda_max; P.abstol = p->abstol; P.reltol = p->reltol;
+    P.dtmax = p->dtmax > 0 ? p->dtmax : (p->lambda_max - p->lambda_min);
+    P.mu = p->mu;
+    P.maxiters = p->maxiters > 0 ? p->maxiters : 1000000;
+    P.pow_mode = p->pow_mode;
+    P.geometry_kind = p->geometry_kind;
+    P.gp0 = p->geometry_params[0]; P.gp1 = p->geometry_params[1]; P.gp2 = p->geometry_params[2];
+    P.gtol = p->gtol;
+    P.chart_inner = p->chart_inner; P.chart_outer = p->chart_outer;
+    P.callback_kind = p->callback_kind; P.callback_delta = p->callback_delta;
+    P.ic_kind = ic->kind; P.grid_kind = ic->grid_kind;
+    P.width = ic->width; P.height = ic->height;
+    for (int k = 0; k < 4; ++k) P.xo[k] = p->observer[k];
+    if (ic->kind == GB200_IC_RENDER_GRID) {
+        P.lo0 = ic->lo0; dd_step(ic->lo0, ic->hi0, ic->width, &P.step0_hi, &P.step0_lo);
+        P.lo1 = ic->lo1; dd_step(ic->lo1, ic->hi1, ic->height, &P.step1_hi, &P.step1_lo);
+    } else if (ic->kind == GB200_IC_POLAR_PLANE) {
+        P.lo0 = ic->lo0; dd_step(ic->lo0, ic->hi0, ic->width, &P.step0_hi, &P.step0_lo);
+        P.geoK = std::pow(ic->hi0 / ic->lo0, 1.0 / (double)(ic->width - 1));
+        P.inv_lo_hi = 1.0 / ic->hi0; dd_step(1.0 / ic->hi0, 1.0 / ic->lo0, ic->width, &P.inv_step_hi, &P.inv_step_lo);
+        const double dth = (ic->hi1 - ic->lo1) / (double)ic->height; // planes.jl:95-96
+        P.lo1 = ic->lo1; dd_step(ic->lo1, ic->hi1 - dth, ic->height, &P.step1_hi, &P.step1_lo);
+    }
+    if (ic->kind != GB200_IC_EXPLICIT) {
+        // closed-form LNRF (ZAMO) co-basis at the observer, generic for static axisymmetric g:
+        //   e^(t) = N dt, e^(r) = sqrt(g_rr) dr, e^(th) = sqrt(g_thth) dth, e^(ph) = sqrt(g_phph)(dph - w dt)
+        double g[5];
+        metric_components_rt(P, P.xo[1], P.xo[2], g);
+        for (int k = 0; k < 5; ++k) P.go[k] = g[k];
+        const double D = g[0] * g[3] - g[4] * g[4];
+        const double gitt = g[3] / D, giphph = g[0] / D, gitph = -g[4] / D;
+        const double N = std::sqrt(-1.0 / gitt);
+        const double om = -g[4] / g[3];
+        const double sph = std::sqrt(g[3]);
+        P.c_r = 1.0 / std::sqrt(g[1]);
+        P.c_th = 1.0 / std::sqrt(g[2]);
+        P.c_ph0 = gitph * N;
+        P.c_ph1 = (giphph - gitph * om) * sph;
+    }
+    P.first = rg->first; P.count = rg->count; P.stride = rg->stride;
+}
+
+// ---------------------------------------------------------------- device memory
+static int pool_get(gb200_ctx* ctx, size_t slot, size_t bytes, void** out) {
+    if (ctx->pool.size() <= slot) ctx->pool.resize(slot + 1);
+    DevBuf& b = ctx->pool[slot];
+    if (b.cap < bytes) {
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr; b.cap = 0;
+        cudaError_t e = cudaMalloc(&b.p, bytes);
+        if (e != cudaSuccess) return fail(ctx, GB200_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+        b.cap = bytes;
+    }
+    *out = b.p;
+    return GB200_OK;
+}
+// pool slots
+enum { SL_STATUS = 0, SL_LAMBDA, SL_X0, SL_V0 = SL_X0 + 4, SL_XI0 = SL_V0 + 4, SL_VI0 = SL_XI0 + 4, SL_NACC = SL_VI0 + 4, SL_NREJ, SL_FLAGS,
+       SL_IMG0, SL_G = SL_IMG0 + GB_MAX_PF, SL_F, SL_EX0, SL_EV0 = SL_EX0 + 4, SL_BINS = SL_EV0 + 4, SL_PARTIAL, SL_FLUX, SL_EMR, SL_EME,
+       SL_PL0, SL_SCRATCH = SL_PL0 + 4, SL_COUNT };
+
+static int upload(gb200_ctx* ctx, size_t slot, const void* host, size_t bytes, const void** dev) {
+    void* d = nullptr;
+    int rc = pool_get(ctx, slot, bytes, &d);
+    if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = d;
+    return GB200_OK;
+}
+
+static int upload_ic_and_tables(gb200_ctx* ctx, const gb200_ic* ic, const gb200_plunging_table* pl, const gb200_emissivity* em, GbParams& P) {
+    if (ic->kind == GB200_IC_EXPLICIT) {
+        for (int k = 0; k < 4; ++k) {
+            const void* d;
+            int rc = upload(ctx, SL_EX0 + k, ic->x[k], sizeof(double) * ic->n, &d); if (rc) return rc;
+            P.ex[k] = (const double*)d;
+            rc = upload(ctx, SL_EV0 + k, ic->v[k], sizeof(double) * ic->n, &d); if (rc) return rc;
+            P.ev[k] = (const double*)d;
+        }
+    }
+    if (pl && pl->n >= 2) {
+        const double* src[4] = {pl->r, pl->ut, pl->ur, pl->uphi};
+        const double* dst[4];
+        for (int k = 0; k < 4; ++k) {
+            const void* d;
+            int rc = upload(ctx, SL_PL0 + k, src[k], sizeof(double) * pl->n, &d); if (rc) return rc;
+            dst[k] = (const double*)d;
+        }
+        P.pl_n = pl->n; P.pl_r = dst[0]; P.pl_ut = dst[1]; P.pl_ur = dst[2]; P.pl_uphi = dst[3];
+    }
+    if (em) {
+        P.emis_kind = em->kind; P.emis_index = em->index; P.emis_n = em->n;
+        if (em->kind == GB200_EMISSIVITY_TABLE) {
+            if (em->n < 2 || !em->r || !em->eps) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "emissivity table needs n >= 2");
+            const void* d;
+            int rc = upload(ctx, SL_EMR, em->r, sizeof(double) * em->n, &d); if (rc) return rc;
+            P.emis_r = (const double*)d;
+            rc = upload(ctx, SL_EME, em->eps, sizeof(double) * em->n, &d); if (rc) return rc;
+            P.emis_eps = (const double*)d;
+        } else if (em->kind != GB200_EMISSIVITY_POWERLAW) return fail(ctx, GB200_ERR_UNSUPPORTED, "emissivity kind %d", em->kind);
+    }
+    return GB200_OK;
+}
+
+static bool needs_isco(const int32_t* pfs, int npf, bool lineprofile) {
+    if (lineprofile) return true;
+    for (int k = 0; k < npf; ++k) if (pfs[k] == GB200_PF_REDSHIFT) return true;
+    return false;
+}
+
+static int set_isco(gb200_ctx* ctx, const gb200_problem* p, GbParams& P) {
+    double r = 0;
+    int rc = gb200_isco(p->metric_kind, p->metric_params, &r);
+    if (rc) return fail(ctx, rc, "no ISCO found for this metric (is it a naked singularity?)");
+    P.r_isco = r;
+    return GB200_OK;
+}
+
+// run the trace kernel on `stream` (queue reset + launch), timing it with events when `timed`
+static int run_trace(gb200_ctx* ctx, GbParams& P, cudaStream_t stream, bool timed) {
+    P.queue = ctx->d_queue;
+    P.counters = ctx->d_queue + 1;
+    CU(ctx, cudaMemsetAsync(ctx->d_queue, 0, 4 * sizeof(unsigned long long), stream));
+    if (timed) CU(ctx, cudaEventRecord(ctx->ev1, stream));
+    int blocks = 0;
+    if (P.count > 0) CU(ctx, gb200_launch_trace(P, ctx->sm_count, stream, &blocks));
+    if (timed) CU(ctx, cudaEventRecord(ctx->ev2, stream));
+    ctx->stats.launches += (P.count > 0) ? 1 : 0;
+    return GB200_OK;
+}
+
+static int finish_stats(gb200_ctx* ctx, int64_t rays) {
+    unsigned long long c[4];
+    CU(ctx, cudaMemcpyAsync(c, ctx->d_queue, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    float k = 0, tot = 0;
+    cudaEventElapsedTime(&k, ctx->ev1, ctx->ev2);
+    cudaEventElapsedTime(&tot, ctx->ev0, ctx->ev3);
+    ctx->stats.kernel_ms = k; ctx->stats.total_ms = tot; ctx->stats.rays = rays;
+    ctx->stats.steps_accepted = (int64_t)c[1]; ctx->stats.steps_rejected = (int64_t)c[2]; ctx->stats.flagged = (int64_t)c[3];
+    return GB200_OK;
+}
+
+// ---------------------------------------------------------------- C ABI
+extern "C" {
+
+int gb200_version(void) { return GB200_VERSION; }
+
+const char* gb200_last_error(gb200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int gb200_init(int device, gb200_ctx** out) {
+    if (!out) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null out pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, GB200_ERR_NO_DEVICE, "no CUDA device available (%s); libgradus_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "device %d out of range [0, %d)", device, ndev);
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(nullptr, GB200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    gb200_ctx* ctx = new gb200_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    CU(nullptr, cudaSetDevice(device));
+    CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(nullptr, cudaEventCreate(&ctx->ev0)); CU(nullptr, cudaEventCreate(&ctx->ev1));
+    CU(nullptr, cudaEventCreate(&ctx->ev2)); CU(nullptr, cudaEventCreate(&ctx->ev3));
+    CU(nullptr, cudaMalloc(&ctx->d_queue, 4 * sizeof(unsigned long long)));
+    *out = ctx;
+    return GB200_OK;
+}
+
+void gb200_destroy(gb200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto& b : ctx->pool) if (b.p) cudaFree(b.p);
+    if (ctx->d_queue) cudaFree(ctx->d_queue);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int gb200_get_stats(gb200_ctx* ctx, gb200_stats* out) {
+    if (!ctx || !out) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null argument");
+    *out = ctx->stats;
+    return GB200_OK;
+}
+
+int gb200_validate(const gb200_problem* p, const gb200_ic* ic) { return validate(nullptr, p, ic); }
+
+int gb200_isco(int32_t metric_kind, const double* mp, double* out) {
+    if (!mp || !out) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null argument");
+    if (metric_kind == GB200_METRIC_KERR) { *out = kerr_isco_host(mp[0], mp[1]); return GB200_OK; }
+    if (metric_kind == GB200_METRIC_JOHANNSEN_PSALTIS) {
+        int rc = generic_isco_host(metric_kind, mp, out);
+        if (rc) return fail(nullptr, rc, "No boundaries for minimization could be determined. It is likely this configuration does not have an ISCO solution.");
+        return GB200_OK;
+    }
+    return fail(nullptr, GB200_ERR_UNSUPPORTED, "metric kind %d", metric_kind);
+}
+
+int gb200_radiative_efficiency(int32_t metric_kind, const double* mp, double* out) {
+    double r = 0;
+    int rc = gb200_isco(metric_kind, mp, &r);
+    if (rc) return rc;
+    *out = 1.0 - circular_energy_host<double>(metric_kind, mp, r);
+    return GB200_OK;
+}
+
+int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, gb200_endpoints* out) {
+    if (!ctx) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null context");
+    int rc = validate(ctx, p, ic); if (rc) return rc;
+    rc = validate_range(ctx, ic, rg); if (rc) return rc;
+    if (!out) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null endpoints");
+    CU(ctx, cudaSetDevice(ctx->device));
+    ctx->stats = gb200_stats{};
+    CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    GbParams P;
+    fill_params(p, ic, rg, P);
+    rc = upload_ic_and_tables(ctx, ic, nullptr, nullptr, P); if (rc) return rc;
+    const size_t n = (size_t)rg->count;
+    void* d;
+#define WANT(ptr, slot, type, field)                                               \
+    if (ptr) { rc = pool_get(ctx, slot, n * sizeof(type) + 8, &d); if (rc) return rc; field = (type*)d; }
+    WANT(out->status, SL_STATUS, int32_t, P.o_status)
+    WANT(out->lambda_max, SL_LAMBDA, double, P.o_lambda)
+    for (int k = 0; k < 4; ++k) {
+        WANT(out->x[k], SL_X0 + k, double, P.o_x[k])
+        WANT(out->v[k], SL_V0 + k, double, P.o_v[k])
+        WANT(out->x_init[k], SL_XI0 + k, double, P.o_x0[k])
+        WANT(out->v_init[k], SL_VI0 + k, double, P.o_v0[k])
+    }
+    WANT(out->naccept, SL_NACC, int32_t, P.o_naccept)
+    WANT(out->nreject, SL_NREJ, int32_t, P.o_nreject)
+    WANT(out->flags, SL_FLAGS, int32_t, P.o_flags)
+#undef WANT
+    // x_init / v_init are written together with point functions; request at least x0[0] consistently
+    rc = run_trace(ctx, P, ctx->stream, true); if (rc) return rc;
+#define BACK(ptr, field, type) \
+    if (ptr && n) CU(ctx, cudaMemcpyAsync(ptr, field, n * sizeof(type), cudaMemcpyDeviceToHost, ctx->stream));
+    BACK(out->status, P.o_status, int32_t)
+    BACK(out->lambda_max, P.o_lambda, double)
+    for (int k = 0; k < 4; ++k) {
+        BACK(out->x[k], P.o_x[k], double)
+        BACK(out->v[k], P.o_v[k], double)
+        BACK(out->x_init[k], P.o_x0[k], double)
+        BACK(out->v_init[k], P.o_v0[k], double)
+    }
+    BACK(out->naccept, P.o_naccept, int32_t)
+    BACK(out->nreject, P.o_nreject, int32_t)
+    BACK(out->flags, P.o_flags, int32_t)
+#undef BACK
+    return finish_stats(ctx, rg->count);
+}
+
+static int render_common(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, const int32_t* pfs, int32_t npf,
+                         const gb200_plunging_table* pl, double* const* images, bool device_out, cudaStream_t stream, int async) {
+    if (!ctx) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null context");
+    int rc = validate(ctx, p, ic); if (rc) return rc;
+    rc = validate_range(ctx, ic, rg); if (rc) return rc;
+    if (npf < 1 || npf > GB_MAX_PF || !pfs || !images) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "need 1..%d point functions", GB_MAX_PF);
+    for (int k = 0; k < npf; ++k) {
+        if (pfs[k] < GB200_PF_SHADOW || pfs[k] > GB200_PF_AFFINE_TIME) return fail(ctx, GB200_ERR_UNSUPPORTED, "point function %d", pfs[k]);
+        if (!images[k]) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null image pointer");
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    ctx->stats = gb200_stats{};
+    CU(ctx, cudaEventRecord(ctx->ev0, stream));
+    GbParams P;
+    fill_params(p, ic, rg, P);
+    if (needs_isco(pfs, npf, false)) { rc = set_isco(ctx, p, P); if (rc) return rc; }
+    rc = upload_ic_and_tables(ctx, ic, pl, nullptr, P); if (rc) return rc;
+    const size_t n = (size_t)rg->count;
+    P.npf = npf;
+    for (int k = 0; k < npf; ++k) {
+        P.pf[k] = pfs[k];
+        if (device_out) P.o_img[k] = images[k];
+        else { void* d; rc = pool_get(ctx, SL_IMG0 + k, n * sizeof(double) + 8, &d); if (rc) return rc; P.o_img[k] = (double*)d; }
+    }
+    rc = run_trace(ctx, P, stream, true); if (rc) return rc;
+    if (!device_out)
+        for (int k = 0; k < npf; ++k)
+            if (n) CU(ctx, cudaMemcpyAsync(images[k], P.o_img[k], n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (async) { ctx->stats.rays = rg->count; return GB200_OK; }
+    if (stream != ctx->stream) { CU(ctx, cudaStreamSynchronize(stream)); }
+    return finish_stats(ctx, rg->count);
+}
+
+int gb200_render(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, const int32_t* pfs, int32_t npf,
+                 const gb200_plunging_table* pl, double* const* images) {
+    return render_common(ctx, p, ic, rg, pfs, npf, pl, images, false, ctx ? ctx->stream : nullptr, 0);
+}
+
+int gb200_render_device(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, const int32_t* pfs, int32_t npf,
+                        const gb200_plunging_table* pl, double* const* d_images, void* cuda_stream, int async) {
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : (ctx ? ctx->stream : nullptr);
+    return render_common(ctx, p, ic, rg, pfs, npf, pl, d_images, true, s, async);
+}
+
+static int lineprofile_common(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, const gb200_emissivity* em,
+                              const gb200_plunging_table* pl, const double* bins, int32_t nbins, const gb200_lineprofile_opts* opts,
+                              double* flux, bool device_out, cudaStream_t stream, int async) {
+    if (!ctx) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null context");
+    int rc = validate(ctx, p, ic); if (rc) return rc;
+    rc = validate_range(ctx, ic, rg); if (rc) return rc;
+    if (!em || !bins || !opts || !flux || nbins < 1 || nbins > 8192) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad line-profile arguments (1 <= nbins <= 8192)");
+    for (int b = 1; b < nbins; ++b) if (!(bins[b] > bins[b - 1])) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bins must be strictly increasing");
+    CU(ctx, cudaSetDevice(ctx->device));
+    ctx->stats = gb200_stats{};
+    CU(ctx, cudaEventRecord(ctx->ev0, stream));
+    GbParams P;
+    fill_params(p, ic, rg, P);
+    rc = set_isco(ctx, p, P); if (rc) return rc;
+    rc = upload_ic_and_tables(ctx, ic, pl, em, P); if (rc) return rc;
+    P.min_re = opts->min_re; P.max_re = opts->max_re;
+    const size_t n = (size_t)rg->count;
+    void* d;
+    rc = pool_get(ctx, SL_G, n * sizeof(double) + 8, &d); if (rc) return rc; P.o_g = (double*)d;
+    rc = pool_get(ctx, SL_F, n * sizeof(double) + 8, &d); if (rc) return rc; P.o_f = (double*)d;
+    const void* dbins;
+    rc = upload(ctx, SL_BINS, bins, sizeof(double) * nbins, &dbins); if (rc) return rc;
+    const int nblocks = ctx->sm_count * 4;
+    rc = pool_get(ctx, SL_PARTIAL, sizeof(double) * (size_t)nblocks * nbins, &d); if (rc) return rc;
+    double* dpartial = (double*)d;
+    double* dflux = flux;
+    if (!device_out) { rc = pool_get(ctx, SL_FLUX, sizeof(double) * nbins, &d); if (rc) return rc; dflux = (double*)d; }
+    rc = run_trace(ctx, P, stream, true); if (rc) return rc;
+    CU(ctx, gb200_launch_hist(P.o_g, P.o_f, rg->count, (const double*)dbins, nbins, opts->bin_right_closed, dpartial, nblocks, dflux, stream));
+    ctx->stats.launches += 2;
+    if (!device_out) {
+        std::vector<double> h((size_t)nbins);
+        CU(ctx, cudaMemcpyAsync(h.data(), dflux, sizeof(double) * nbins, cudaMemcpyDeviceToHost, stream));
+        CU(ctx, cudaStreamSynchronize(stream));
+        double tot = 0;
+        for (int b = 0; b < nbins; ++b) tot += h[(size_t)b];
+        for (int b = 0; b < nbins; ++b) flux[b] = opts->normalise ? h[(size_t)b] / tot : h[(size_t)b]; // flux ./ sum(flux), line-profiles.jl:197
+    }
+    if (async) { ctx->stats.rays = rg->count; return GB200_OK; }
+    if (stream != ctx->stream) { CU(ctx, cudaStreamSynchronize(stream)); }
+    return finish_stats(ctx, rg->count);
+}
+
+int gb200_lineprofile(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, const gb200_emissivity* em,
+                      const gb200_plunging_table* pl, const double* bins, int32_t nbins, const gb200_lineprofile_opts* opts, double* flux_out) {
+    return lineprofile_common(ctx, p, ic, rg, em, pl, bins, nbins, opts, flux_out, false, ctx ? ctx->stream : nullptr, 0);
+}
+
+int gb200_lineprofile_device(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, const gb200_emissivity* em,
+                             const gb200_plunging_table* pl, const double* bins, int32_t nbins, const gb200_lineprofile_opts* opts,
+                             double* d_flux, void* cuda_stream, int async) {
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : (ctx ? ctx->stream : nullptr);
+    return lineprofile_common(ctx, p, ic, rg, em, pl, bins, nbins, opts, d_flux, true, s, async);
+}
+
+int gb200_fp64_peak(gb200_ctx* ctx, double* tflops_out) {
+    if (!ctx || !tflops_out) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    void* d;
+    int rc = pool_get(ctx, SL_SCRATCH, 64, &d); if (rc) return rc;
+    const int blocks = ctx->sm_count * 8, iters = 20000;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(ctx, gb200_launch_dfma((double*)d, blocks, iters, ctx->stream));
+        CU(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev2);
+        const double flop = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks; // 64 FMAs per iteration per thread
+        const double tf = flop / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    ctx->fp64_peak = best;
+    *tflops_out = best;
+    return GB200_OK;
+}
+
+} // extern "C"

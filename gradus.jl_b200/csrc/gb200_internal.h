@@ -1,0 +1,9 @@
+// gb200_internal.h -- launchers shared between gb200_trace.cu (kernels) and gb200_api.cu (C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+struct GbParams;
+cudaError_t gb200_launch_trace(const GbParams& P, int sm_count, cudaStream_t stream, int* blocks_out);
+cudaError_t gb200_launch_hist(const double* g, const double* f, int64_t n, const double* bins, int nbins, int right_closed,
+                              double* partial, int nblocks, double* out, cudaStream_t stream);
+cudaError_t gb200_launch_dfma(double* d_out, int blocks, int iters, cudaStream_t stream);

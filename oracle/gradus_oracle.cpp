@@ -464,6 +464,10 @@ template <class T>
 struct RayResult {
     int status; T lambda; T x[4], v[4], x0[4], v0[4];
     int naccept, nreject, flags;
+    // Smallest distance of any discrete decision taken for this ray from its threshold (accept test EEst <= 1,
+    // sign tests of the disc condition at the step ends and the 7 interior samples, chart and hemisphere tests),
+    // each scaled to be dimensionless.  Rays with a tiny margin form the "grazing band" of DESIGN.md.
+    double margin;
 };
 
 // Dense output, OrdinaryDiffEq Tsit5 interpolant (order-4), Theta in [0,1]
@@ -483,8 +487,12 @@ void interpolant(T Th, T dt, const T y0[8], const T k[7][8], T out[8], int ncomp
 
 // One ray: SciMLBase.init / reinit! / auto_dt_reset! / solve! with the callback set of
 // create_callback_set (callbacks.jl:25-28): continuous disc event, then discrete user, then chart.
+// optional per-step record (save_on = true path of the reference: every accepted step), used for debugging and
+// for the plunging-velocity table (orbit-solving.jl:137-167)
+struct StepRecord { std::vector<double> t, dt, eest; std::vector<double> u; };
+
 template <class T>
-void trace_ray(const gb200_problem& p, const Metric& m, const T u_init[8], RayResult<T>& res) {
+void trace_ray(const gb200_problem& p, const Metric& m, const T u_init[8], RayResult<T>& res, StepRecord* rec = nullptr) {
     const T abstol = T(p.abstol), reltol = T(p.reltol);
     const T t0 = T(p.lambda_min), tstop = T(p.lambda_max);
     const T dtmax = (p.dtmax > 0) ? T(p.dtmax) : (tstop - t0);
@@ -497,6 +505,19 @@ void trace_ray(const gb200_problem& p, const Metric& m, const T u_init[8], RayRe
     for (int i = 0; i < 8; ++i) { u[i] = u_init[i]; uprev[i] = u_init[i]; }
     for (int i = 0; i < 4; ++i) { res.x0[i] = u_init[i]; res.v0[i] = u_init[4 + i]; }
     res.status = GB200_STATUS_NO_STATUS; res.naccept = 0; res.nreject = 0; res.flags = 0;
+    res.margin = 1e300;
+    auto note = [&](T dist) { double d = (double)rabs(dist); if (d < res.margin) res.margin = d; };
+    auto note_cond = [&](T c, T r_, T th_) { // disc condition margins, incl. the radial-range discontinuity of ThinDisc
+        note(c / std::max(T(1), rabs(r_)));
+        if (p.geometry_kind == GB200_GEOMETRY_THIN_DISC) {
+            T rho = r_ * rabs(rsin(th_));
+            if (p.geometry_params[0] > 0) note((rho - T(p.geometry_params[0])) / T(p.geometry_params[0]));
+            note((rho - T(p.geometry_params[1])) / T(p.geometry_params[1]));
+        } else if (p.geometry_kind == GB200_GEOMETRY_SHAKURA_SUNYAEV) {
+            T rho = r_ * rabs(rsin(th_));
+            note((rho - T(p.geometry_params[2])) / T(p.geometry_params[2]));
+        }
+    };
     T t = t0, tprev = t0;
 
     // ---- initial dt (ode_determine_initdt, out-of-place form) and FSAL initialisation
@@ -579,8 +600,10 @@ void trace_ray(const gb200_problem& p, const Metric& m, const T u_init[8], RayRe
             q = std::max(T(1) / qmax, std::min(T(1) / qmin, q / gamma));
         }
         accept = (EEst <= T(1));
+        note(EEst - T(1));
         if (!accept) { ++res.nreject; continue; }
         ++res.naccept;
+        if (rec) { rec->t.push_back((double)(t + dt)); rec->dt.push_back((double)dt); rec->eest.push_back((double)EEst); for (int i = 0; i < 8; ++i) rec->u.push_back((double)u[i]); }
         T dtnew = dt / q; // step_accept_controller!
         qold = std::max(EEst, qoldinit);
         tprev = t;
@@ -597,6 +620,7 @@ void trace_ray(const gb200_problem& p, const Metric& m, const T u_init[8], RayRe
             T cprev = disc_condition<T>(p, uprev[1], uprev[2]);
             T cnext = disc_condition<T>(p, u[1], u[2]);
             int sprev = (cprev > 0) - (cprev < 0), snext = (cnext > 0) - (cnext < 0);
+            note_cond(cnext, u[1], u[2]);
             bool event = false;
             T bottom = tprev, top = t;
             if (sprev != 0 && sprev * snext <= 0) event = true;
@@ -606,7 +630,7 @@ void trace_ray(const gb200_problem& p, const Metric& m, const T u_init[8], RayRe
                     T abst = (i == 8) ? t : tprev + (T(i - 1) * (t - tprev)) / T(7);
                     T cnew;
                     if (i == 8) cnew = cnext;
-                    else { T ui[8]; interpolant<T>((abst - tprev) / dt, dt, uprev, k, ui, 3); cnew = disc_condition<T>(p, ui[1], ui[2]); }
+                    else { T ui[8]; interpolant<T>((abst - tprev) / dt, dt, uprev, k, ui, 3); cnew = disc_condition<T>(p, ui[1], ui[2]); note_cond(cnew, ui[1], ui[2]); }
                     if (T(sprev) * cnew < T(0)) { event = true; bottom = last; top = abst; break; }
                     last = abst;
                 }
@@ -643,8 +667,11 @@ void trace_ray(const gb200_problem& p, const Metric& m, const T u_init[8], RayRe
         }
         // (2) DiscreteCallbacks in CallbackSet order: user (domain_upper_hemisphere), then chart
         if (p.callback_kind == GB200_CALLBACK_UPPER_HEMISPHERE) {
+            note((u[1] * rcos(u[2]) - T(p.callback_delta)) / std::max(T(1), rabs(u[1])));
             if (u[1] * rcos(u[2]) < T(p.callback_delta)) { res.status = GB200_STATUS_OUT_OF_DOMAIN; terminated = true; }
         }
+        note((u[1] - T(p.chart_inner)) / T(p.chart_inner));
+        note((u[1] - T(p.chart_outer)) / T(p.chart_outer));
         if (u[1] <= T(p.chart_inner) || u[1] > T(p.chart_outer)) { // charts.jl:8-24
             res.status = (u[1] <= T(p.chart_inner)) ? GB200_STATUS_WITHIN_INNER_BOUNDARY : GB200_STATUS_OUT_OF_DOMAIN;
             terminated = true;
@@ -804,7 +831,7 @@ static int bin_index(const double* bins, int nbins, double g, int right_closed) 
 
 template <class T>
 int run(const gb200_problem& p, const gb200_ic& ic, const gb200_range& rg, int nthreads,
-        gb200_endpoints* out, const int32_t* pfs, int npf, const gb200_plunging_table* pl, double* const* images,
+        gb200_endpoints* out, double* margin, const int32_t* pfs, int npf, const gb200_plunging_table* pl, double* const* images,
         const gb200_emissivity* emis, const double* bins, int nbins, const gb200_lineprofile_opts* lo, double* flux) {
     Metric m{p.metric_kind, p.metric_params[0], p.metric_params[1], p.metric_params[2]};
     LnrTransform<T> xfm;
@@ -846,6 +873,7 @@ int run(const gb200_problem& p, const gb200_ic& ic, const gb200_range& rg, int n
             if (out->nreject) out->nreject[n] = res.nreject;
             if (out->flags) out->flags[n] = res.flags;
         }
+        if (margin) margin[n] = res.margin;
         for (int kpf = 0; kpf < npf; ++kpf) images[kpf][n] = (double)point_function<T>(pfs[kpf], p, m, r_isco, pl, res);
         if (flux && res.status == GB200_STATUS_INTERSECTED_WITH_GEOMETRY) { // line-profiles.jl:186-194
             double rho = (double)(res.x[1] * rabs(rsin(res.x[2])));
@@ -875,20 +903,20 @@ int run(const gb200_problem& p, const gb200_ic& ic, const gb200_range& rg, int n
 extern "C" {
 
 // precision: 0 = double, 1 = long double (x87 80-bit) -- the latter defines the rounding-robust reference
-int oracle_trace(const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, int nthreads, int precision, gb200_endpoints* out) {
-    if (precision == 1) return orc::run<long double>(*p, *ic, *rg, nthreads, out, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
-    return orc::run<double>(*p, *ic, *rg, nthreads, out, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+int oracle_trace(const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, int nthreads, int precision, gb200_endpoints* out, double* margin) {
+    if (precision == 1) return orc::run<long double>(*p, *ic, *rg, nthreads, out, margin, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+    return orc::run<double>(*p, *ic, *rg, nthreads, out, margin, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
 }
 int oracle_render(const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, int nthreads, int precision,
                   const int32_t* pfs, int npf, const gb200_plunging_table* pl, double* const* images, gb200_endpoints* out) {
-    if (precision == 1) return orc::run<long double>(*p, *ic, *rg, nthreads, out, pfs, npf, pl, images, nullptr, nullptr, 0, nullptr, nullptr);
-    return orc::run<double>(*p, *ic, *rg, nthreads, out, pfs, npf, pl, images, nullptr, nullptr, 0, nullptr, nullptr);
+    if (precision == 1) return orc::run<long double>(*p, *ic, *rg, nthreads, out, nullptr, pfs, npf, pl, images, nullptr, nullptr, 0, nullptr, nullptr);
+    return orc::run<double>(*p, *ic, *rg, nthreads, out, nullptr, pfs, npf, pl, images, nullptr, nullptr, 0, nullptr, nullptr);
 }
 int oracle_lineprofile(const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, int nthreads, int precision,
                        const gb200_emissivity* emis, const gb200_plunging_table* pl, const double* bins, int nbins,
                        const gb200_lineprofile_opts* lo, double* flux, gb200_endpoints* out) {
-    if (precision == 1) return orc::run<long double>(*p, *ic, *rg, nthreads, out, nullptr, 0, pl, nullptr, emis, bins, nbins, lo, flux);
-    return orc::run<double>(*p, *ic, *rg, nthreads, out, nullptr, 0, pl, nullptr, emis, bins, nbins, lo, flux);
+    if (precision == 1) return orc::run<long double>(*p, *ic, *rg, nthreads, out, nullptr, nullptr, 0, pl, nullptr, emis, bins, nbins, lo, flux);
+    return orc::run<double>(*p, *ic, *rg, nthreads, out, nullptr, nullptr, 0, pl, nullptr, emis, bins, nbins, lo, flux);
 }
 int oracle_isco(int kind, const double* mp, double* out) {
     orc::Metric m{kind, mp[0], mp[1], mp[2]};
@@ -941,6 +969,20 @@ int oracle_initial_velocity(const gb200_problem* p, double alpha, double beta, d
     ric.alpha = alpha; ric.beta = beta; ric.explicit_v = false; ric.area = 1;
     orc::initial_state<double>(*p, m, ric, &xfm, u8);
     return 0;
+}
+// single ray with every accepted step recorded; returns the number of steps written (<= cap)
+int oracle_trace_path(const gb200_problem* p, const double* u0, int precision, int cap, double* t, double* dt, double* eest, double* u8) {
+    orc::Metric m{p->metric_kind, p->metric_params[0], p->metric_params[1], p->metric_params[2]};
+    orc::StepRecord rec;
+    if (precision == 1) {
+        long double ul[8]; for (int i = 0; i < 8; ++i) ul[i] = u0[i];
+        orc::RayResult<long double> res; orc::trace_ray<long double>(*p, m, ul, res, &rec);
+    } else {
+        orc::RayResult<double> res; orc::trace_ray<double>(*p, m, u0, res, &rec);
+    }
+    int n = (int)std::min<size_t>(rec.t.size(), (size_t)cap);
+    for (int i = 0; i < n; ++i) { t[i] = rec.t[i]; dt[i] = rec.dt[i]; eest[i] = rec.eest[i]; for (int k = 0; k < 8; ++k) u8[8 * i + k] = rec.u[8 * i + k]; }
+    return (int)rec.t.size();
 }
 int oracle_max_threads(void) {
 #ifdef _OPENMP

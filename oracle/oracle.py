@@ -46,7 +46,9 @@ def _range(ic, rng):
 def trace(problem, ic, rng=None, nthreads=0, precision=0):
     rng = _range(ic, rng)
     out = cabi.EndpointArrays(rng.count)
-    rc = lib().oracle_trace(C.byref(problem), C.byref(ic), C.byref(rng), nthreads, precision, C.byref(out.c))
+    out.margin = np.zeros(rng.count)  # oracle-only: distance of the closest discrete decision from its threshold
+    rc = lib().oracle_trace(C.byref(problem), C.byref(ic), C.byref(rng), nthreads, precision, C.byref(out.c),
+                            cabi.dptr(out.margin))
     assert rc == 0
     return out
 
@@ -130,3 +132,13 @@ def initial_state(problem, alpha, beta):
     u = np.zeros(8)
     lib().oracle_initial_velocity(C.byref(problem), C.c_double(alpha), C.c_double(beta), cabi.dptr(u))
     return u
+
+
+def trace_path(problem, u0, precision=0, cap=100000):
+    """One ray, every accepted step: returns (t, dt, EEst, u[n,8])."""
+    u0 = np.ascontiguousarray(u0, np.float64)
+    t, dt, ee, u = np.zeros(cap), np.zeros(cap), np.zeros(cap), np.zeros((cap, 8))
+    n = lib().oracle_trace_path(C.byref(problem), cabi.dptr(u0), precision, cap, cabi.dptr(t), cabi.dptr(dt), cabi.dptr(ee),
+                                cabi.dptr(u.reshape(-1)))
+    n = min(n, cap)
+    return t[:n], dt[:n], ee[:n], u[:n]
