@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- geodesics/sec of the B200 hot path on BASELINE.json's headline configuration.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     (the reference algorithm on the host cores: CPU oracle)
+
+A "step" is one full render of the workload: Kerr a=0.998, observer r=1000 theta=60deg, ThinDisc(0,50),
+2048 x 2048 image plane per GPU, two fused point functions (redshift + disc radius), Tsit5 abstol=reltol=1e-9
+(BASELINE.json configs[1]).  Rays shard across ranks with no data-path collective (weak scaling: the
+image is 2048 x (2048*N) over the same field of view and rank r integrates rays r, r+N, ...).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H_IMG = 2048
+W_IMG_PER_GPU = 2048
+F_RHS = {0: 118.0, 1: 222.0}  # algorithmic flops per RHS evaluation (Kerr: SURVEY 8d; JP: 151 (sympy CSE) + 71 contraction)
+F_STAGE, F_EVENT, F_IC, F_END = 566.0, 280.0, 60.0, 150.0
+
+
+def flops_per_attempt(metric_kind, has_disc):
+    return 6.0 * F_RHS[metric_kind] + F_STAGE + (F_EVENT if has_disc else 0.0)
+
+
+def build_workload(world, ensemble=None):
+    import gradus_b200 as gb
+    from gradus_b200.api import RenderGrid, tracing_configuration
+
+    m = gb.KerrMetric(M=1.0, a=0.998)
+    x = [0.0, 1000.0, math.radians(60.0), 0.0]
+    d = gb.ThinDisc(0.0, 50.0)
+    w, h = W_IMG_PER_GPU * world, H_IMG
+    cfg = tracing_configuration(m, x, RenderGrid(w, h, (-60, 60), (-40, 40)), d, 2000.0, ensemble=ensemble, trajectories=w * h)
+    return cfg, w, h
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU algorithm (EnsembleEndpointThreads work decomposition) on this box's host cores.
+    Julia cannot run here, so this is the C++ oracle port (kind = "port"), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from gradus_b200 import _cabi as cabi
+    from oracle import oracle
+
+    cfg, w, h = build_workload(world)
+    p, ic = cfg.to_c()
+    stride = args.ref_stride
+    rng = cabi.Range(0, (ic.n + stride - 1) // stride, stride)
+    pfs = [cabi.PF_REDSHIFT, cabi.PF_DISC_RADIUS]
+    threads = oracle.max_threads()
+    for _ in range(args.warmup):
+        oracle.render(p, ic, pfs, rng=rng)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.render(p, ic, pfs, rng=rng)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = rng.count / dt
+    sample = f"every {stride}th ray of the {w}x{h} image ({rng.count} rays per step)"
+    out = {
+        "impl": "reference", "metric": "geodesics/sec", "value": val, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(world, w, h),
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(world, w, h):
+    return {"workload": f"C2: KerrMetric a=0.998, observer r=1000 theta=60deg, ThinDisc(0,50), {w}x{h} image plane "
+                        f"({W_IMG_PER_GPU}x{H_IMG} per GPU), redshift + disc-radius point functions, Tsit5 abstol=reltol=1e-9, lambda_max=2000",
+            "rays_per_gpu": W_IMG_PER_GPU * H_IMG, "parallelism": f"ray-sharded x{world} (interleaved, no collective)",
+            "l2": "flushed between timed steps (256 MiB write); the kernel reads no input arrays"}
+
+
+def run_ours(args, rank, world, local):
+    import torch
+
+    import gradus_b200 as gb
+    from gradus_b200 import _cabi as cabi
+    from gradus_b200 import distributed as gd
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the host baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = cabi.load()
+    ens = gb.EnsembleB200(devices=(local,))
+    ctx = ens.ctx(local)
+    cfg, w, h = build_workload(world, ensemble=ens)
+    p, ic = cfg.to_c()
+    rng = gd.interleaved_range(ic.n, rank, world)
+    n_local = rng.count
+    pfs = np.array([cabi.PF_REDSHIFT, cabi.PF_DISC_RADIUS], np.int32)
+    stream = torch.cuda.Stream(device=dev)  # explicit non-default stream: the library launches on it, the events time it
+    torch.cuda.set_stream(stream)
+    sptr = C.c_void_p(stream.cuda_stream)
+
+    # ---- device-resident arm: outputs stay in HBM
+    d_imgs = [torch.empty(n_local, dtype=torch.float64, device=dev) for _ in pfs]
+    d_ptrs = (C.c_void_p * len(pfs))(*[C.c_void_p(t.data_ptr()) for t in d_imgs])
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def step_device(async_=1):
+        cabi.check(lib.gb200_render_device(ctx, C.byref(p), C.byref(ic), C.byref(rng), cabi.iptr(pfs), len(pfs), None, d_ptrs, sptr, async_), ctx)
+
+    peak = C.c_double()
+    cabi.check(lib.gb200_fp64_peak(ctx, C.byref(peak)), ctx)
+    step_device(0)  # synchronous once: per-call counters for the algorithmic flop count
+    st = ens.stats(local)
+    attempts = st.steps_accepted + st.steps_rejected
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    gd.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for a, b in evs:
+        flush.fill_(1.0)  # L2 flush, outside the event pair
+        a.record(stream)
+        step_device()
+        b.record(stream)
+    torch.cuda.synchronize()
+    gd.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_local = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    ms = gd.max_over_ranks(ms_local, dev)
+    total_rays = gd.sum_over_ranks(float(n_local), dev)
+    total_attempts = gd.sum_over_ranks(float(attempts), dev)
+    value = total_rays / (ms * 1e-3)
+
+    # ---- end-to-end arm: the reference-facing C-ABI call with HOST buffers (D2H inside the timed region)
+    h_imgs = [torch.empty(n_local, dtype=torch.float64, pin_memory=True) for _ in pfs]
+    h_ptrs = (cabi._dp * len(pfs))(*[C.cast(t.data_ptr(), cabi._dp) for t in h_imgs])
+
+    def step_e2e():
+        cabi.check(lib.gb200_render(ctx, C.byref(p), C.byref(ic), C.byref(rng), cabi.iptr(pfs), len(pfs), None, h_ptrs), ctx)
+
+    for _ in range(args.warmup):
+        step_e2e()
+    torch.cuda.synchronize()
+    gd.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_local = (time.perf_counter() - t0) / args.steps
+    gd.barrier()
+    e2e_s = gd.max_over_ranks(e2e_local, dev)
+    e2e_value = total_rays / e2e_s
+    checksum = float(np.nansum(h_imgs[0].numpy()))
+
+    # ---- secondary: binned line profile with the histogram all-reduced over NCCL (BASELINE.json configs[2])
+    lp = None
+    if not args.no_lineprofile:
+        lp = run_lineprofile(args, rank, world, local, ens, dev, stream, sptr)
+
+    if rank != 0:
+        return
+    # ---- roofline (FP64 CUDA-core pipe; DESIGN.md states the per-attempt algorithmic flop count)
+    fpa = flops_per_attempt(p.metric_kind, p.geometry_kind != 0)
+    flops_per_launch_local = attempts * fpa + n_local * (F_IC + F_END)
+    achieved = flops_per_launch_local / (ms_local * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    nominal_fp64 = 148 * 64 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
+    roofline = {
+        "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None,
+        "traffic": None,
+        "peak_source": "measured in this run: dependent-free DFMA micro-benchmark (gb200_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+        "peak_nominal": nominal_fp64,
+        "flops_per_step_attempt": fpa, "step_attempts_per_ray": attempts / max(n_local, 1),
+        "hbm": {"algorithmic_bytes_per_ray": 16, "achieved_GBs": 16.0 * n_local / (ms_local * 1e-3) / 1e9, "peak_GBs": peaks.get("hbm_gbs")},
+    }
+    # ---- CPU baseline: the oracle port on a bounded sample of the same workload (rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+
+        stride = args.cpu_stride
+        crng = cabi.Range(0, (ic.n + stride - 1) // stride, stride)
+        t0 = time.perf_counter()
+        oracle.render(p, ic, [cabi.PF_REDSHIFT, cabi.PF_DISC_RADIUS], rng=crng)
+        cdt = time.perf_counter() - t0
+        cpu = {"value": crng.count / cdt, "unit": "rays/s", "cores": oracle.max_threads(), "kind": "port",
+               "sample": f"every {stride}th ray of the {w}x{h} image ({crng.count} rays, {cdt:.1f} s)",
+               "note": "C++ restatement of the reference algorithm (closed toolchain: no Julia in this image); optimistic stand-in for Gradus.jl"}
+    out = {
+        "metric": "geodesics/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(world, w, h),
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": C.sizeof(cabi.Problem) + C.sizeof(cabi.IC) + C.sizeof(cabi.Range),
+                "d2h_bytes_per_step": 8 * len(pfs) * n_local, "ms_per_step": e2e_s * 1e3, "timing": "wall clock around the blocking C-ABI call, max over ranks"},
+        "gpu_launches": int(args.steps * 1),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "total_rays_per_step": total_rays, "step_attempts_per_step": total_attempts, "image_checksum": checksum,
+    }
+    if lp is not None:
+        out["lineprofile"] = lp
+    print(json.dumps(out), flush=True)
+
+
+def run_lineprofile(args, rank, world, local, ens, dev, stream, sptr):
+    """C3: lineprofile(BinningMethod) for Kerr a=0.998 theta=40deg, PolarPlane 4096 x 4096 per GPU, eps(r) = r^-3,
+    histogram partial sums all-reduced with NCCL, then normalised."""
+    import torch
+
+    import gradus_b200 as gb
+    from gradus_b200 import _cabi as cabi
+    from gradus_b200 import distributed as gd
+    from gradus_b200.api import tracing_configuration
+
+    lib = cabi.load()
+    ctx = ens.ctx(local)
+    m = gb.KerrMetric(1.0, 0.998)
+    x = [0.0, 1000.0, math.radians(40.0), 0.0]
+    plane = gb.PolarPlane(gb.GeometricGrid(), Nr=args.lp_n, Ntheta=args.lp_n * world, r_min=1.0, r_max=250.0)
+    cfg = tracing_configuration(m, x, plane, gb.ThinDisc(0.0, 400.0), (0.0, 2000.0), callback=gb.domain_upper_hemisphere(), ensemble=ens)
+    p, ic = cfg.to_c()
+    rng = gd.interleaved_range(ic.n, rank, world)
+    bins = np.ascontiguousarray(np.linspace(0.1, 1.5, 180))
+    emis = cabi.Emissivity(cabi.EMISSIVITY_POWERLAW, 0, 3.0, None, None)
+    opts = cabi.LineProfileOpts(gb.isco(m), 50.0, 0, 1)
+    d_flux = torch.zeros(len(bins), dtype=torch.float64, device=dev)
+
+    def step():
+        cabi.check(lib.gb200_lineprofile_device(ctx, C.byref(p), C.byref(ic), C.byref(rng), C.byref(emis), None, cabi.dptr(bins), len(bins),
+                                                C.byref(opts), C.c_void_p(d_flux.data_ptr()), sptr, 1), ctx)
+        return gd.allreduce_histogram(d_flux)
+
+    step()
+    torch.cuda.synchronize()
+    gd.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(args.lp_steps):
+        flux = step()
+    b.record(stream)
+    torch.cuda.synchronize()
+    gd.barrier()
+    ms = gd.max_over_ranks(a.elapsed_time(b) / args.lp_steps, dev)
+    total = gd.sum_over_ranks(float(rng.count), dev)
+    fl = flux.cpu().numpy()
+    return {"metric": "geodesics/sec (binned line profile, NCCL-reduced histogram)", "value": total / (ms * 1e-3), "unit": "rays/s",
+            "ms_per_step": ms, "rays_per_step": total, "plane": f"PolarPlane geometric {args.lp_n}x{args.lp_n * world}", "nbins": 180,
+            "flux_sum": float(fl.sum()), "flux_argmax_g": float(bins[int(np.argmax(fl))])}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-stride", type=int, default=16, help="cpu_baseline sample: every n-th ray")
+    ap.add_argument("--ref-stride", type=int, default=64, help="--impl reference sample per step: every n-th ray")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lineprofile", action="store_true")
+    ap.add_argument("--lp-n", type=int, default=4096)
+    ap.add_argument("--lp-steps", type=int, default=2)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        from gradus_b200 import distributed as gd
+
+        gd.init_from_env("nccl")
+    run_ours(args, rank, world, local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -25,7 +25,8 @@ struct DevBuf {
 struct gb200_ctx {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr; // the context's own stream
+    cudaStream_t cur = nullptr;    // stream of the call in flight (own stream unless the caller passed one)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     std::string err;
     gb200_stats stats{};
@@ -60,6 +61,7 @@ struct D1 {
     GB_HD friend D1 operator*(const D1& a, const D1& b) { return D1(a.v * b.v, a.d * b.v + a.v * b.d); }
     GB_HD friend D1 operator/(const D1& a, const D1& b) { double q = a.v / b.v; return D1(q, (a.d - q * b.d) / b.v); }
 };
+GB_HD static inline D1 gb_rcp(const D1& a) { return D1(1.0) / a; }
 static inline D1 dsqrt(const D1& a) { double s = std::sqrt(a.v); return D1(s, a.d / (2.0 * s)); }
 static inline double dsqrt(double a) { return std::sqrt(a); }
 static inline double val(const D1& a) { return a.v; }
@@ -232,7 +234,7 @@ static int upload(gb200_ctx* ctx, size_t slot, const void* host, size_t bytes, c
     void* d = nullptr;
     int rc = pool_get(ctx, slot, bytes, &d);
     if (rc) return rc;
-    CU(ctx, cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->cur));
     *dev = d;
     return GB200_OK;
 }
@@ -300,9 +302,9 @@ static int run_trace(gb200_ctx* ctx, GbParams& P, cudaStream_t stream, bool time
 
 static int finish_stats(gb200_ctx* ctx, int64_t rays) {
     unsigned long long c[4];
-    CU(ctx, cudaMemcpyAsync(c, ctx->d_queue, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaMemcpyAsync(c, ctx->d_queue, sizeof c, cudaMemcpyDeviceToHost, ctx->cur));
+    CU(ctx, cudaEventRecord(ctx->ev3, ctx->cur));
+    CU(ctx, cudaStreamSynchronize(ctx->cur));
     float k = 0, tot = 0;
     cudaEventElapsedTime(&k, ctx->ev1, ctx->ev2);
     cudaEventElapsedTime(&tot, ctx->ev0, ctx->ev3);
@@ -388,6 +390,7 @@ int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, cons
     if (!out) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null endpoints");
     CU(ctx, cudaSetDevice(ctx->device));
     ctx->stats = gb200_stats{};
+    ctx->cur = ctx->stream;
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     GbParams P;
     fill_params(p, ic, rg, P);
@@ -439,6 +442,7 @@ static int render_common(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic*
     }
     CU(ctx, cudaSetDevice(ctx->device));
     ctx->stats = gb200_stats{};
+    ctx->cur = stream;
     CU(ctx, cudaEventRecord(ctx->ev0, stream));
     GbParams P;
     fill_params(p, ic, rg, P);
@@ -456,7 +460,6 @@ static int render_common(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic*
         for (int k = 0; k < npf; ++k)
             if (n) CU(ctx, cudaMemcpyAsync(images[k], P.o_img[k], n * sizeof(double), cudaMemcpyDeviceToHost, stream));
     if (async) { ctx->stats.rays = rg->count; return GB200_OK; }
-    if (stream != ctx->stream) { CU(ctx, cudaStreamSynchronize(stream)); }
     return finish_stats(ctx, rg->count);
 }
 
@@ -481,6 +484,7 @@ static int lineprofile_common(gb200_ctx* ctx, const gb200_problem* p, const gb20
     for (int b = 1; b < nbins; ++b) if (!(bins[b] > bins[b - 1])) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bins must be strictly increasing");
     CU(ctx, cudaSetDevice(ctx->device));
     ctx->stats = gb200_stats{};
+    ctx->cur = stream;
     CU(ctx, cudaEventRecord(ctx->ev0, stream));
     GbParams P;
     fill_params(p, ic, rg, P);
@@ -510,7 +514,6 @@ static int lineprofile_common(gb200_ctx* ctx, const gb200_problem* p, const gb20
         for (int b = 0; b < nbins; ++b) flux[b] = opts->normalise ? h[(size_t)b] / tot : h[(size_t)b]; // flux ./ sum(flux), line-profiles.jl:197
     }
     if (async) { ctx->stats.rays = rg->count; return GB200_OK; }
-    if (stream != ctx->stream) { CU(ctx, cudaStreamSynchronize(stream)); }
     return finish_stats(ctx, rg->count);
 }
 

@@ -24,6 +24,22 @@
 #define GB_D inline
 #endif
 
+// Branch-free FP64 reciprocal: hardware seed (rcp.approx, >= 20 good bits) + two Newton steps -> <= 1-2 ulp.
+// Used for the well-conditioned denominators of the hot loop (Sigma, Delta, sin^2, error scales); an IEEE
+// division costs ~25 instructions including a divergent slow-path check, this costs 5.
+GB_HD inline double gb_rcp(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+#else
+    return 1.0 / x;
+#endif
+}
+
 #include "jp_metric_generated.cuh"
 
 #define GB_MAX_PF 4
@@ -92,56 +108,168 @@ struct GbParams {
 };
 
 // ---------------------------------------------------------------- Tsit5 constants (OrdinaryDiffEq Tsit5ConstantCache)
-#define GB_A21 0.161
-#define GB_A31 -0.008480655492356989
-#define GB_A32 0.335480655492357
-#define GB_A41 2.8971530571054935
-#define GB_A42 -6.359448489975075
-#define GB_A43 4.3622954328695815
-#define GB_A51 5.325864828439257
-#define GB_A52 -11.748883564062828
-#define GB_A53 7.4955393428898365
-#define GB_A54 -0.09249506636175525
-#define GB_A61 5.86145544294642
-#define GB_A62 -12.92096931784711
-#define GB_A63 8.159367898576159
-#define GB_A64 -0.071584973281401
-#define GB_A65 -0.028269050394068383
-#define GB_A71 0.09646076681806523
-#define GB_A72 0.01
-#define GB_A73 0.4798896504144996
-#define GB_A74 1.379008574103742
-#define GB_A75 -3.290069515436081
-#define GB_A76 2.324710524099774
-#define GB_BT1 -0.00178001105222577714
-#define GB_BT2 -0.0008164344596567469
-#define GB_BT3 0.007880878010261995
-#define GB_BT4 -0.1447110071732629
-#define GB_BT5 0.5823571654525552
-#define GB_BT6 -0.45808210592918697
-#define GB_BT7 0.015151515151515152
+#ifdef __CUDA_ARCH__
+#define GB_TAB(i) gb_tab[i]
+#else
+#define GB_TAB(i) gb_tab_host[i]
+#endif
+#define GB_A21_V 0.161
+#define GB_A21 GB_TAB(0)
+#define GB_A31_V -0.008480655492356989
+#define GB_A31 GB_TAB(1)
+#define GB_A32_V 0.335480655492357
+#define GB_A32 GB_TAB(2)
+#define GB_A41_V 2.8971530571054935
+#define GB_A41 GB_TAB(3)
+#define GB_A42_V -6.359448489975075
+#define GB_A42 GB_TAB(4)
+#define GB_A43_V 4.3622954328695815
+#define GB_A43 GB_TAB(5)
+#define GB_A51_V 5.325864828439257
+#define GB_A51 GB_TAB(6)
+#define GB_A52_V -11.748883564062828
+#define GB_A52 GB_TAB(7)
+#define GB_A53_V 7.4955393428898365
+#define GB_A53 GB_TAB(8)
+#define GB_A54_V -0.09249506636175525
+#define GB_A54 GB_TAB(9)
+#define GB_A61_V 5.86145544294642
+#define GB_A61 GB_TAB(10)
+#define GB_A62_V -12.92096931784711
+#define GB_A62 GB_TAB(11)
+#define GB_A63_V 8.159367898576159
+#define GB_A63 GB_TAB(12)
+#define GB_A64_V -0.071584973281401
+#define GB_A64 GB_TAB(13)
+#define GB_A65_V -0.028269050394068383
+#define GB_A65 GB_TAB(14)
+#define GB_A71_V 0.09646076681806523
+#define GB_A71 GB_TAB(15)
+#define GB_A72_V 0.01
+#define GB_A72 GB_TAB(16)
+#define GB_A73_V 0.4798896504144996
+#define GB_A73 GB_TAB(17)
+#define GB_A74_V 1.379008574103742
+#define GB_A74 GB_TAB(18)
+#define GB_A75_V -3.290069515436081
+#define GB_A75 GB_TAB(19)
+#define GB_A76_V 2.324710524099774
+#define GB_A76 GB_TAB(20)
+#define GB_BT1_V -0.00178001105222577714
+#define GB_BT1 GB_TAB(21)
+#define GB_BT2_V -0.0008164344596567469
+#define GB_BT2 GB_TAB(22)
+#define GB_BT3_V 0.007880878010261995
+#define GB_BT3 GB_TAB(23)
+#define GB_BT4_V -0.1447110071732629
+#define GB_BT4 GB_TAB(24)
+#define GB_BT5_V 0.5823571654525552
+#define GB_BT5 GB_TAB(25)
+#define GB_BT6_V -0.45808210592918697
+#define GB_BT6 GB_TAB(26)
+#define GB_BT7_V 0.015151515151515152
+#define GB_BT7 GB_TAB(27)
 // dense output: b_1 = Th (1 + Th (R12 + Th (R13 + Th R14))), b_j = Th^2 (Rj2 + Th (Rj3 + Th Rj4))
-#define GB_R12 -2.763706197274826
-#define GB_R13 2.9132554618219126
-#define GB_R14 -1.0530884977290216
-#define GB_R22 0.13169999999999998
-#define GB_R23 -0.2234
-#define GB_R24 0.1017
-#define GB_R32 3.9302962368947516
-#define GB_R33 -5.941033872131505
-#define GB_R34 2.490627285651253
-#define GB_R42 -12.411077166933676
-#define GB_R43 30.33818863028232
-#define GB_R44 -16.548102889244902
-#define GB_R52 37.50931341651104
-#define GB_R53 -88.1789048947664
-#define GB_R54 47.37952196281928
-#define GB_R62 -27.896526289197286
-#define GB_R63 65.09189467479366
-#define GB_R64 -34.87065786149661
-#define GB_R72 1.5
-#define GB_R73 -4.0
-#define GB_R74 2.5
+#define GB_R12_V -2.763706197274826
+#define GB_R12 GB_TAB(28)
+#define GB_R13_V 2.9132554618219126
+#define GB_R13 GB_TAB(29)
+#define GB_R14_V -1.0530884977290216
+#define GB_R14 GB_TAB(30)
+#define GB_R22_V 0.13169999999999998
+#define GB_R22 GB_TAB(31)
+#define GB_R23_V -0.2234
+#define GB_R23 GB_TAB(32)
+#define GB_R24_V 0.1017
+#define GB_R24 GB_TAB(33)
+#define GB_R32_V 3.9302962368947516
+#define GB_R32 GB_TAB(34)
+#define GB_R33_V -5.941033872131505
+#define GB_R33 GB_TAB(35)
+#define GB_R34_V 2.490627285651253
+#define GB_R34 GB_TAB(36)
+#define GB_R42_V -12.411077166933676
+#define GB_R42 GB_TAB(37)
+#define GB_R43_V 30.33818863028232
+#define GB_R43 GB_TAB(38)
+#define GB_R44_V -16.548102889244902
+#define GB_R44 GB_TAB(39)
+#define GB_R52_V 37.50931341651104
+#define GB_R52 GB_TAB(40)
+#define GB_R53_V -88.1789048947664
+#define GB_R53 GB_TAB(41)
+#define GB_R54_V 47.37952196281928
+#define GB_R54 GB_TAB(42)
+#define GB_R62_V -27.896526289197286
+#define GB_R62 GB_TAB(43)
+#define GB_R63_V 65.09189467479366
+#define GB_R63 GB_TAB(44)
+#define GB_R64_V -34.87065786149661
+#define GB_R64 GB_TAB(45)
+#define GB_R72_V 1.5
+#define GB_R72 GB_TAB(46)
+#define GB_R73_V -4.0
+#define GB_R73 GB_TAB(47)
+#define GB_R74_V 2.5
+#define GB_R74 GB_TAB(48)
+
+
+// Tableau constants live in the constant bank so FP64 instructions read them as c[bank][offset] operands
+// (literal doubles are otherwise materialised with two UMOVs per use: 17% of all executed instructions in v1).
+#ifdef __CUDACC__
+__device__ __constant__ double gb_tab[] = {
+    0.161, // 0: GB_A21
+    -0.008480655492356989, // 1: GB_A31
+    0.335480655492357, // 2: GB_A32
+    2.8971530571054935, // 3: GB_A41
+    -6.359448489975075, // 4: GB_A42
+    4.3622954328695815, // 5: GB_A43
+    5.325864828439257, // 6: GB_A51
+    -11.748883564062828, // 7: GB_A52
+    7.4955393428898365, // 8: GB_A53
+    -0.09249506636175525, // 9: GB_A54
+    5.86145544294642, // 10: GB_A61
+    -12.92096931784711, // 11: GB_A62
+    8.159367898576159, // 12: GB_A63
+    -0.071584973281401, // 13: GB_A64
+    -0.028269050394068383, // 14: GB_A65
+    0.09646076681806523, // 15: GB_A71
+    0.01, // 16: GB_A72
+    0.4798896504144996, // 17: GB_A73
+    1.379008574103742, // 18: GB_A74
+    -3.290069515436081, // 19: GB_A75
+    2.324710524099774, // 20: GB_A76
+    -0.00178001105222577714, // 21: GB_BT1
+    -0.0008164344596567469, // 22: GB_BT2
+    0.007880878010261995, // 23: GB_BT3
+    -0.1447110071732629, // 24: GB_BT4
+    0.5823571654525552, // 25: GB_BT5
+    -0.45808210592918697, // 26: GB_BT6
+    0.015151515151515152, // 27: GB_BT7
+    -2.763706197274826, // 28: GB_R12
+    2.9132554618219126, // 29: GB_R13
+    -1.0530884977290216, // 30: GB_R14
+    0.13169999999999998, // 31: GB_R22
+    -0.2234, // 32: GB_R23
+    0.1017, // 33: GB_R24
+    3.9302962368947516, // 34: GB_R32
+    -5.941033872131505, // 35: GB_R33
+    2.490627285651253, // 36: GB_R34
+    -12.411077166933676, // 37: GB_R42
+    30.33818863028232, // 38: GB_R43
+    -16.548102889244902, // 39: GB_R44
+    37.50931341651104, // 40: GB_R52
+    -88.1789048947664, // 41: GB_R53
+    47.37952196281928, // 42: GB_R54
+    -27.896526289197286, // 43: GB_R62
+    65.09189467479366, // 44: GB_R63
+    -34.87065786149661, // 45: GB_R64
+    1.5, // 46: GB_R72
+    -4.0, // 47: GB_R73
+    2.5, // 48: GB_R74
+};
+#endif
+static const double gb_tab_host[] = {0.161, -0.008480655492356989, 0.335480655492357, 2.8971530571054935, -6.359448489975075, 4.3622954328695815, 5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774, -0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629, 0.5823571654525552, -0.45808210592918697, 0.015151515151515152, -2.763706197274826, 2.9132554618219126, -1.0530884977290216, 0.13169999999999998, -0.2234, 0.1017, 3.9302962368947516, -5.941033872131505, 2.490627285651253, -12.411077166933676, 30.33818863028232, -16.548102889244902, 37.50931341651104, -88.1789048947664, 47.37952196281928, -27.896526289197286, 65.09189467479366, -34.87065786149661, 1.5, -4.0, 2.5};
 
 // ---------------------------------------------------------------- metrics
 // Kerr: components and Jacobian from w = 2Mr/Sigma (see DESIGN.md for the derivation).
@@ -152,7 +280,7 @@ GB_HD inline void kerr_metric_jacobian(double M, double a, S r, S s, S c, S g[5]
     const S sin2 = 2.0 * s * c;
     const S Sig = r2 + a2 * c2;
     const S Del = r2 - 2.0 * M * r + a2;
-    const S iSig = 1.0 / Sig, iDel = 1.0 / Del;
+    const S iSig = gb_rcp(Sig), iDel = gb_rcp(Del);
     const S w = 2.0 * M * r * iSig;
     const S w_r = 2.0 * (M - w * r) * iSig;
     const S w_t = w * a2 * sin2 * iSig;
@@ -191,9 +319,9 @@ GB_HD inline void metric_jacobian_rt(const GbParams& P, double r, double s, doub
 GB_HD inline void geodesic_accel(const double g[5], const double dr[5], const double dth[5],
                                  double vt, double vr, double vth, double vph, double acc[4]) {
     const double D = g[0] * g[3] - g[4] * g[4];
-    const double iD = 1.0 / D;
+    const double iD = gb_rcp(D);
     const double gitt = g[3] * iD, giphph = g[0] * iD, gitph = -g[4] * iD;
-    const double girr = 1.0 / g[1], githth = 1.0 / g[2];
+    const double girr = gb_rcp(g[1]), githth = gb_rcp(g[2]);
     const double d0 = vr * dr[0] + vth * dth[0];
     const double d1 = vr * dr[1] + vth * dth[1];
     const double d2 = vr * dr[2] + vth * dth[2];
@@ -211,13 +339,87 @@ GB_HD inline void geodesic_accel(const double g[5], const double dr[5], const do
 }
 
 #ifdef __CUDACC__
+// Branch-free sincos for the polar angle (|x| << 2^20 rad always holds: theta is bounded by the number of polar
+// passages): Cody-Waite reduction by pi/2 in three parts, fdlibm __kernel_sin/__kernel_cos minimax polynomials on
+// [-pi/4, pi/4] (< 1 ulp), quadrant fix-up with selects.  The CUDA library sincos() carries a Payne-Hanek slow
+// path behind a divergent branch; this has none.
+GB_D void gb_sincos(double x, double* sp, double* cp) {
+    const double q = rint(x * 0.63661977236758134308);
+    double rr = fma(-q, 1.57079632673412561417e+00, x);
+    rr = fma(-q, 6.07710050650619224932e-11, rr);
+    rr = fma(-q, 2.02226624879595063154e-21, rr);
+    const double z = rr * rr;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sn = fma(rr * z, ps, rr);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cs = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const int n = __double2int_rn(q);
+    const bool swap = (n & 1) != 0;
+    double so = swap ? cs : sn;
+    double co = swap ? sn : cs;
+    if (n & 2) so = -so;
+    if ((n + 1) & 2) co = -co;
+    *sp = so;
+    *cp = co;
+}
+
+// Kerr right-hand side with everything folded: two reciprocals (1/(Sigma Delta) and 1/sin^2) and the identity
+// g_tt g_phph - g_tph^2 = -Delta sin^2, so  g^tt = -B/Delta, g^tph = -a w/Delta, g^phph = (1 - w)/(Delta sin^2).
+GB_D void kerr_rhs_accel(double M, double a, double r, double s, double c, double vt, double vr, double vth, double vph, double acc[4]) {
+    const double a2 = a * a, r2 = r * r, s2 = s * s, c2 = c * c;
+    const double sin2 = 2.0 * s * c;
+    const double Sig = fma(a2, c2, r2);
+    const double Del = fma(r, r - 2.0 * M, a2);
+    const double R = gb_rcp(Sig * Del), is2 = gb_rcp(s2);
+    const double iSig = R * Del, iDel = R * Sig;
+    const double w = 2.0 * M * r * iSig;
+    const double w_r = 2.0 * (M - w * r) * iSig;
+    const double w_t = w * a2 * sin2 * iSig;
+    const double Sig_t = -a2 * sin2;
+    const double as2 = a2 * s2;
+    const double B = fma(as2, w, r2 + a2);
+    const double q = fma(s2, w_t, sin2 * w);
+    const double grr = Sig * iDel;
+    // Jacobian (d_r, d_theta) of (tt, rr, thth, phph, tph)
+    const double r0 = w_r, t0 = w_t;
+    const double r1 = (2.0 * r - grr * 2.0 * (r - M)) * iDel, t1 = Sig_t * iDel;
+    const double r2_ = 2.0 * r, t2 = Sig_t;
+    const double r3 = s2 * fma(as2, w_r, 2.0 * r), t3 = fma(sin2, B, as2 * q);
+    const double r4 = -a * s2 * w_r, t4 = -a * q;
+    // inverse metric
+    const double gitt = -B * iDel, gitph = -a * w * iDel, giphph = (1.0 - w) * iDel * is2;
+    const double girr = Del * iSig, githth = iSig;
+    const double d0 = fma(vr, r0, vth * t0), d1 = fma(vr, r1, vth * t1), d2 = fma(vr, r2_, vth * t2);
+    const double d3 = fma(vr, r3, vth * t3), d4 = fma(vr, r4, vth * t4);
+    const double Pt = fma(d0, vt, d4 * vph), Pp = fma(d4, vt, d3 * vph);
+    const double vtt = vt * vt, vrr = vr * vr, vthth = vth * vth, vpp = vph * vph, vtp2 = 2.0 * vt * vph;
+    const double Sr = fma(r0, vtt, fma(r1, vrr, fma(r2_, vthth, fma(r3, vpp, r4 * vtp2))));
+    const double St = fma(t0, vtt, fma(t1, vrr, fma(t2, vthth, fma(t3, vpp, t4 * vtp2))));
+    acc[0] = -fma(gitt, Pt, gitph * Pp);
+    acc[1] = -girr * fma(d1, vr, -0.5 * Sr);
+    acc[2] = -githth * fma(d2, vth, -0.5 * St);
+    acc[3] = -fma(gitph, Pt, giphph * Pp);
+}
+
 template <int METRIC>
 GB_D void rhs_accel(const GbParams& P, double r, double th, double vt, double vr, double vth, double vph,
                     double acc[4], double& s, double& c) {
-    sincos(th, &s, &c);
-    double g[5], dr[5], dth[5];
-    metric_jacobian<METRIC>(P, r, s, c, g, dr, dth);
-    geodesic_accel(g, dr, dth, vt, vr, vth, vph, acc);
+    gb_sincos(th, &s, &c);
+    if (METRIC == GB200_METRIC_KERR) {
+        kerr_rhs_accel(P.M, P.a, r, s, c, vt, vr, vth, vph, acc);
+    } else {
+        double g[5], dr[5], dth[5];
+        metric_jacobian<METRIC>(P, r, s, c, g, dr, dth);
+        geodesic_accel(g, dr, dth, vt, vr, vth, vph, acc);
+    }
 }
 #endif
 

@@ -1,7 +1,11 @@
 // gb200_trace.cu -- the hot path: persistent-thread FP64 adaptive Tsit5 ray tracer for sm_100a.
 //
 // One ray per thread, whole integrator state in registers (k1..k7 accelerations, the stage
-// velocities of r and theta for the dense output, previous and proposed state).  Warps stay
+// velocities of r and theta for the dense output, previous and proposed state).  The step
+// is straight-line code (taken branches cost instruction-fetch bubbles that two warps per
+// scheduler cannot hide): reciprocals and sincos are branch-free, the tableau sits in the
+// constant bank, and the 6 interior event samples are skipped when a bound on the dense
+// output proves the disc condition cannot change sign.  Warps stay
 // full through a work queue: a global ticket counter hands out ray slots, and a warp
 // refills its lanes (one warp-aggregated atomicAdd) once GB_REFILL_THRESH of them have
 // terminated.  Terminated lanes keep their last step in registers and are finalised
@@ -36,18 +40,20 @@
 #define LANE_PENDING 2
 #define FULLMASK 0xffffffffu
 
-// stage input  u + dt * sum_{l<S} a_{S+1,l+1} k_l   (S = 1..6 -> stages 2..7), summed left to right like the reference
+// stage input  u + dt * sum_{l<S} a_{S+1,l+1} k_l   (S = 1..6 -> stages 2..7), summed left to right like the reference.
+// k0 is the FSAL slope (k1 of the tableau); k[1..5] are k2..k6.
 template <int S>
-GB_D double comb(double u, double dt, const double* k) {
-    if (S == 1) return fma(dt * GB_A21, k[0], u);
-    if (S == 2) return fma(dt, fma(GB_A32, k[1], GB_A31 * k[0]), u);
-    if (S == 3) return fma(dt, fma(GB_A43, k[2], fma(GB_A42, k[1], GB_A41 * k[0])), u);
-    if (S == 4) return fma(dt, fma(GB_A54, k[3], fma(GB_A53, k[2], fma(GB_A52, k[1], GB_A51 * k[0]))), u);
-    if (S == 5) return fma(dt, fma(GB_A65, k[4], fma(GB_A64, k[3], fma(GB_A63, k[2], fma(GB_A62, k[1], GB_A61 * k[0])))), u);
-    return fma(dt, fma(GB_A76, k[5], fma(GB_A75, k[4], fma(GB_A74, k[3], fma(GB_A73, k[2], fma(GB_A72, k[1], GB_A71 * k[0]))))), u);
+GB_D double comb(double u, double dt, double k0, const double* k) {
+    if (S == 1) return fma(dt * GB_A21, k0, u);
+    if (S == 2) return fma(dt, fma(GB_A32, k[1], GB_A31 * k0), u);
+    if (S == 3) return fma(dt, fma(GB_A43, k[2], fma(GB_A42, k[1], GB_A41 * k0)), u);
+    if (S == 4) return fma(dt, fma(GB_A54, k[3], fma(GB_A53, k[2], fma(GB_A52, k[1], GB_A51 * k0))), u);
+    if (S == 5) return fma(dt, fma(GB_A65, k[4], fma(GB_A64, k[3], fma(GB_A63, k[2], fma(GB_A62, k[1], GB_A61 * k0)))), u);
+    return fma(dt, fma(GB_A76, k[5], fma(GB_A75, k[4], fma(GB_A74, k[3], fma(GB_A73, k[2], fma(GB_A72, k[1], GB_A71 * k0))))), u);
 }
-GB_D double errcomb(const double* k) {
-    return fma(GB_BT7, k[6], fma(GB_BT6, k[5], fma(GB_BT5, k[4], fma(GB_BT4, k[3], fma(GB_BT3, k[2], fma(GB_BT2, k[1], GB_BT1 * k[0]))))));
+// sum_j btilde_j k_j with k_1 = k0, k_7 = k6
+GB_D double errcomb(double k0, const double* k, double k6) {
+    return fma(GB_BT7, k6, fma(GB_BT6, k[5], fma(GB_BT5, k[4], fma(GB_BT4, k[3], fma(GB_BT3, k[2], fma(GB_BT2, k[1], GB_BT1 * k0))))));
 }
 template <int S> GB_D constexpr double a7coef() {
     return S == 0 ? GB_A71 : S == 1 ? GB_A72 : S == 2 ? GB_A73 : S == 3 ? GB_A74 : S == 4 ? GB_A75 : GB_A76;
@@ -56,10 +62,10 @@ template <int S> GB_D constexpr double btcoef() {
     return S == 0 ? GB_BT1 : S == 1 ? GB_BT2 : S == 2 ? GB_BT3 : S == 3 ? GB_BT4 : S == 4 ? GB_BT5 : S == 5 ? GB_BT6 : GB_BT7;
 }
 // dense-output polynomial coefficients  u(Th) = u0 + dt*Th*(k0 + Th*(C2 + Th*(C3 + Th*C4)))
-GB_D void dense_coeffs(const double* k, double& C2, double& C3, double& C4) {
-    C2 = fma(GB_R72, k[6], fma(GB_R62, k[5], fma(GB_R52, k[4], fma(GB_R42, k[3], fma(GB_R32, k[2], fma(GB_R22, k[1], GB_R12 * k[0]))))));
-    C3 = fma(GB_R73, k[6], fma(GB_R63, k[5], fma(GB_R53, k[4], fma(GB_R43, k[3], fma(GB_R33, k[2], fma(GB_R23, k[1], GB_R13 * k[0]))))));
-    C4 = fma(GB_R74, k[6], fma(GB_R64, k[5], fma(GB_R54, k[4], fma(GB_R44, k[3], fma(GB_R34, k[2], fma(GB_R24, k[1], GB_R14 * k[0]))))));
+GB_D void dense_coeffs(double k0, const double* k, double k6, double& C2, double& C3, double& C4) {
+    C2 = fma(GB_R72, k6, fma(GB_R62, k[5], fma(GB_R52, k[4], fma(GB_R42, k[3], fma(GB_R32, k[2], fma(GB_R22, k[1], GB_R12 * k0))))));
+    C3 = fma(GB_R73, k6, fma(GB_R63, k[5], fma(GB_R53, k[4], fma(GB_R43, k[3], fma(GB_R33, k[2], fma(GB_R23, k[1], GB_R13 * k0))))));
+    C4 = fma(GB_R74, k6, fma(GB_R64, k[5], fma(GB_R54, k[4], fma(GB_R44, k[3], fma(GB_R34, k[2], fma(GB_R24, k[1], GB_R14 * k0))))));
 }
 GB_D double dense_eval(double u0, double dt, double Th, double C1, double C2, double C3, double C4) {
     return fma(dt * Th, fma(Th, fma(Th, fma(Th, C4, C3), C2), C1), u0);
@@ -71,6 +77,22 @@ GB_D double ctrl_pow_log(double logx, double x, double y, int mode) {
     if (mode == GB200_POW_FAST32) return (double)exp2f((float)y * log2f((float)x));
     return exp(y * logx);
 }
+
+// Can the disc condition become negative anywhere on this step?  Conservative bound from the dense-output
+// polynomial: |u(Th) - u0| <= |dt| (|C1| + |C2| + |C3| + |C4|) for Th in [0, 1], and |cos| is 1-Lipschitz.
+// Returning false lets the caller skip the 6 interior samples (they would all be positive).
+template <int GEOM>
+GB_D bool scan_needed(const GbParams& P, double r0, double acos0, double cprev, double Bth, double Br) {
+    const double slack = 1.0 + 1e-9;
+    if (GEOM == GB200_GEOMETRY_THIN_DISC) return !(acos0 - Bth > P.gtol * slack + 1e-12);
+    if (GEOM == GB200_GEOMETRY_SHAKURA_SUNYAEV) {
+        const double hmax = 3.0 * P.gp1 * P.gp0;
+        return !((acos0 - Bth) > 0.0 && (acos0 - Bth) * (r0 - Br) > hmax * slack + 1e-12);
+    }
+    if (GEOM == GB200_GEOMETRY_DATUM_PLANE) return !(fabs(cprev) > (Br + (fabs(r0) + Br) * Bth) * slack + 1e-12);
+    return false;
+}
+
 
 template <int METRIC, int GEOM>
 __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(const __grid_constant__ GbParams P) {
@@ -86,9 +108,9 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
     double lam = 0;                                                         // affine parameter at u_prev (integrator.t)
     double ct = 0, r = 0, th = 0, ph = 0, vt = 0, vr = 0, vth = 0, vph = 0; // u_prev (ct = coordinate time x^t)
     double nct = 0, nr = 0, nth = 0, nph = 0, nvt = 0, nvr = 0, nvth = 0, nvph = 0; // u (proposed / final)
-    double kA0[7], kA1[7], kA2[7], kA3[7]; // k_j[5..8]: accelerations
-    double kR[7], kT[7];                   // k_j[2], k_j[3]: stage velocities v^r, v^theta
-    double dt = 0, dt_step = 0, qoldpow = 1, cprev = 1, ev_lo = 0, ev_hi = 0;
+    double kA0[7], kA1[7], kA2[7], kA3[7]; // accelerations: [0] = FSAL k1, [1..5] = k2..k6, [6] = k7
+    double kR[6], kT[6];                   // stage velocities v^r, v^theta of k2..k6 ([0] unused: k1's are vr, vth)
+    double dt = 0, dt_step = 0, qoldpow = 1, cprev = 1, acos_prev = 1, ev_lo = 0, ev_hi = 0;
     double tfinal = 0;
     int state = LANE_EMPTY, pend_status = GB200_STATUS_NO_STATUS;
     bool pend_event = false;
@@ -97,7 +119,9 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
     bool exhausted = false;
     unsigned long long tot_acc = 0, tot_rej = 0, tot_flag = 0;
 #pragma unroll
-    for (int j = 0; j < 7; ++j) { kA0[j] = kA1[j] = kA2[j] = kA3[j] = kR[j] = kT[j] = 0.0; }
+    for (int j = 0; j < 7; ++j) { kA0[j] = kA1[j] = kA2[j] = kA3[j] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { kR[j] = kT[j] = 0.0; }
 
     for (;;) {
         unsigned run_mask = __ballot_sync(FULLMASK, state == LANE_RUN);
@@ -111,23 +135,24 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                 if (GEOM != GB200_GEOMETRY_NONE && pend_event) {
                     // ContinuousCallback root find on the dense output (DiffEqBase find_callback_time, LeftRootFind)
                     double C2r, C3r, C4r, C2t, C3t, C4t;
-                    dense_coeffs(kR, C2r, C3r, C4r);
-                    dense_coeffs(kT, C2t, C3t, C4t);
+                    dense_coeffs(vr, kR, nvr, C2r, C3r, C4r);
+                    dense_coeffs(vth, kT, nvth, C2t, C3t, C4t);
                     const double sprev = sgn(cprev);
                     double lo = ev_lo, hi = ev_hi;
-                    double flo = cprev * 0.0 + sprev, fhi = -sprev; // only signs matter until evaluated
+                    double flo, fhi;
                     {
                         double s_, c_;
                         if (lo > 0.0) {
-                            sincos(dense_eval(th, dt_step, lo, kT[0], C2t, C3t, C4t), &s_, &c_);
-                            flo = disc_condition<GEOM>(P, dense_eval(r, dt_step, lo, kR[0], C2r, C3r, C4r), s_, c_);
+                            sincos(dense_eval(th, dt_step, lo, vth, C2t, C3t, C4t), &s_, &c_);
+                            flo = disc_condition<GEOM>(P, dense_eval(r, dt_step, lo, vr, C2r, C3r, C4r), s_, c_);
                         } else flo = cprev;
-                        sincos(dense_eval(th, dt_step, hi, kT[0], C2t, C3t, C4t), &s_, &c_);
-                        fhi = disc_condition<GEOM>(P, dense_eval(r, dt_step, hi, kR[0], C2r, C3r, C4r), s_, c_);
+                        sincos(dense_eval(th, dt_step, hi, vth, C2t, C3t, C4t), &s_, &c_);
+                        fhi = disc_condition<GEOM>(P, dense_eval(r, dt_step, hi, vr, C2r, C3r, C4r), s_, c_);
                     }
                     if (fhi == 0.0) lo = hi;
                     else {
                         int side = 0;
+#pragma unroll 1
                         for (int it = 0; it < 100; ++it) {
                             const double w = hi - lo;
                             if (w <= 1e-15) break;
@@ -136,8 +161,8 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                             if (!(mid > lo && mid < hi)) mid = 0.5 * (lo + hi);
                             if (!(mid > lo && mid < hi)) break;
                             double s_, c_;
-                            sincos(dense_eval(th, dt_step, mid, kT[0], C2t, C3t, C4t), &s_, &c_);
-                            const double fm = disc_condition<GEOM>(P, dense_eval(r, dt_step, mid, kR[0], C2r, C3r, C4r), s_, c_);
+                            sincos(dense_eval(th, dt_step, mid, vth, C2t, C3t, C4t), &s_, &c_);
+                            const double fm = disc_condition<GEOM>(P, dense_eval(r, dt_step, mid, vr, C2r, C3r, C4r), s_, c_);
                             if (fm != 0.0 && (fm > 0.0) == (sprev > 0.0)) {
                                 lo = mid; flo = fm;
                                 if (side == -1) fhi *= 0.5;
@@ -161,18 +186,20 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                     b[5] = Th2 * fma(Th, fma(Th, GB_R64, GB_R63), GB_R62);
                     b[6] = Th2 * fma(Th, fma(Th, GB_R74, GB_R73), GB_R72);
                     // stage v^t, v^phi are recomputed from the stored accelerations (bitwise the same values)
-                    double W0[7], W3[7];
-                    W0[0] = vt; W3[0] = vph;
-                    W0[1] = comb<1>(vt, dt_step, kA0); W3[1] = comb<1>(vph, dt_step, kA3);
-                    W0[2] = comb<2>(vt, dt_step, kA0); W3[2] = comb<2>(vph, dt_step, kA3);
-                    W0[3] = comb<3>(vt, dt_step, kA0); W3[3] = comb<3>(vph, dt_step, kA3);
-                    W0[4] = comb<4>(vt, dt_step, kA0); W3[4] = comb<4>(vph, dt_step, kA3);
-                    W0[5] = comb<5>(vt, dt_step, kA0); W3[5] = comb<5>(vph, dt_step, kA3);
-                    W0[6] = nvt; W3[6] = nvph;
+                    double W0[7], W3[7], WR[7], WT[7];
+                    W0[0] = vt; W3[0] = vph; WR[0] = vr; WT[0] = vth;
+                    W0[1] = comb<1>(vt, dt_step, kA0[0], kA0); W3[1] = comb<1>(vph, dt_step, kA3[0], kA3);
+                    W0[2] = comb<2>(vt, dt_step, kA0[0], kA0); W3[2] = comb<2>(vph, dt_step, kA3[0], kA3);
+                    W0[3] = comb<3>(vt, dt_step, kA0[0], kA0); W3[3] = comb<3>(vph, dt_step, kA3[0], kA3);
+                    W0[4] = comb<4>(vt, dt_step, kA0[0], kA0); W3[4] = comb<4>(vph, dt_step, kA3[0], kA3);
+                    W0[5] = comb<5>(vt, dt_step, kA0[0], kA0); W3[5] = comb<5>(vph, dt_step, kA3[0], kA3);
+                    W0[6] = nvt; W3[6] = nvph; WR[6] = nvr; WT[6] = nvth;
+#pragma unroll
+                    for (int j = 1; j < 6; ++j) { WR[j] = kR[j]; WT[j] = kT[j]; }
                     double st = 0, sr = 0, sth = 0, sph = 0, s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
                     for (int j = 0; j < 7; ++j) {
-                        st = fma(b[j], W0[j], st); sr = fma(b[j], kR[j], sr); sth = fma(b[j], kT[j], sth); sph = fma(b[j], W3[j], sph);
+                        st = fma(b[j], W0[j], st); sr = fma(b[j], WR[j], sr); sth = fma(b[j], WT[j], sth); sph = fma(b[j], W3[j], sph);
                         s0 = fma(b[j], kA0[j], s0); s1 = fma(b[j], kA1[j], s1); s2 = fma(b[j], kA2[j], s2); s3 = fma(b[j], kA3[j], s3);
                     }
                     nct = fma(dt_step, st, ct); nr = fma(dt_step, sr, r); nth = fma(dt_step, sth, th); nph = fma(dt_step, sph, ph);
@@ -261,10 +288,13 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                         ray_initial_state(P, P.first + s * P.stride, ri);
                         lam = P.lam0; ct = ri.x[0]; r = ri.x[1]; th = ri.x[2]; ph = ri.x[3];
                         vt = ri.v[0]; vr = ri.v[1]; vth = ri.v[2]; vph = ri.v[3];
+                        naccept = 0; nreject = 0; flags = 0; iter = 0;
+                        pend_event = false;
                         // f0 and the Hairer-Wanner initial step (ode_determine_initdt)
                         double acc[4], s_, c_;
                         rhs_accel<METRIC>(P, r, th, vt, vr, vth, vph, acc, s_, c_);
                         if (GEOM != GB200_GEOMETRY_NONE) cprev = disc_condition<GEOM>(P, r, s_, c_);
+                        acos_prev = fabs(c_);
                         const double u0[8] = {ct, r, th, ph, vt, vr, vth, vph};
                         const double f0[8] = {vt, vr, vth, vph, acc[0], acc[1], acc[2], acc[3]};
                         double sk[8], d0 = 0, d1 = 0;
@@ -290,10 +320,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                         const double dt1 = (md <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(md)) / 5.0);
                         dt = fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
                         kA0[0] = acc[0]; kA1[0] = acc[1]; kA2[0] = acc[2]; kA3[0] = acc[3];
-                        kR[0] = vr; kT[0] = vth;
                         qoldpow = ctrl_pow_log(log_qoldinit, 1e-4, beta2, P.pow_mode);
-                        naccept = 0; nreject = 0; flags = 0; iter = 0;
-                        pend_event = false;
                         state = LANE_RUN;
                     }
                 }
@@ -303,7 +330,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
             if (run_mask == 0) break;
         }
 
-        // ================= one Tsit5 step attempt for every running lane =================
+        // ================= one Tsit5 step attempt for every running lane (straight-line: no taken branches) ==========
         if (state == LANE_RUN) {
             ++iter;
             bool stop_now = false;
@@ -317,112 +344,119 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
             if (stop_now) { // integrator failure: the ray keeps NoStatus at its last accepted state
                 nct = ct; nr = r; nth = th; nph = ph; nvt = vt; nvr = vr; nvth = vth; nvph = vph;
                 tfinal = lam; pend_status = GB200_STATUS_NO_STATUS; pend_event = false; state = LANE_PENDING;
-            } else {
-                double acc[4], s_ = 0, c_ = 1;
-                double tsum = GB_A71 * vt, psum = GB_A71 * vph;   // sum_j a7j k_j[1], k_j[4]
-                double terr = GB_BT1 * vt, perr = GB_BT1 * vph;   // sum_j btilde_j k_j[1], k_j[4]
-#define GB_STAGE(S)                                                                                          \
-    {                                                                                                        \
-        const double xr = comb<S>(r, dt, kR), xt = comb<S>(th, dt, kT);                                     \
-        const double w0 = comb<S>(vt, dt, kA0), w1 = comb<S>(vr, dt, kA1), w2 = comb<S>(vth, dt, kA2),      \
-                     w3 = comb<S>(vph, dt, kA3);                                                             \
-        kR[S] = w1; kT[S] = w2;                                                                              \
-        tsum = fma(a7coef<S>(), w0, tsum); psum = fma(a7coef<S>(), w3, psum);                               \
-        terr = fma(btcoef<S>(), w0, terr); perr = fma(btcoef<S>(), w3, perr);                               \
-        rhs_accel<METRIC>(P, xr, xt, w0, w1, w2, w3, acc, s_, c_);                                           \
-        kA0[S] = acc[0]; kA1[S] = acc[1]; kA2[S] = acc[2]; kA3[S] = acc[3];                                  \
+            }
+        }
+        if (state == LANE_RUN) {
+            double acc[4], s_ = 0, c_ = 1;
+            double tsum = GB_A71 * vt, psum = GB_A71 * vph; // sum_j a7j k_j[1], k_j[4]
+            double terr = GB_BT1 * vt, perr = GB_BT1 * vph; // sum_j btilde_j k_j[1], k_j[4]
+#define GB_STAGE(S)                                                                                                     \
+    {                                                                                                                   \
+        const double xr = comb<S>(r, dt, vr, kR), xt = comb<S>(th, dt, vth, kT);                                        \
+        const double w0 = comb<S>(vt, dt, kA0[0], kA0), w1 = comb<S>(vr, dt, kA1[0], kA1),                              \
+                     w2 = comb<S>(vth, dt, kA2[0], kA2), w3 = comb<S>(vph, dt, kA3[0], kA3);                            \
+        kR[S] = w1; kT[S] = w2;                                                                                         \
+        tsum = fma(a7coef<S>(), w0, tsum); psum = fma(a7coef<S>(), w3, psum);                                           \
+        terr = fma(btcoef<S>(), w0, terr); perr = fma(btcoef<S>(), w3, perr);                                           \
+        rhs_accel<METRIC>(P, xr, xt, w0, w1, w2, w3, acc, s_, c_);                                                      \
+        kA0[S] = acc[0]; kA1[S] = acc[1]; kA2[S] = acc[2]; kA3[S] = acc[3];                                             \
     }
-                GB_STAGE(1) GB_STAGE(2) GB_STAGE(3) GB_STAGE(4) GB_STAGE(5)
+            GB_STAGE(1) GB_STAGE(2) GB_STAGE(3) GB_STAGE(4) GB_STAGE(5)
 #undef GB_STAGE
-                // 7th stage = the proposed state (FSAL)
-                nr = comb<6>(r, dt, kR); nth = comb<6>(th, dt, kT);
-                nvt = comb<6>(vt, dt, kA0); nvr = comb<6>(vr, dt, kA1); nvth = comb<6>(vth, dt, kA2); nvph = comb<6>(vph, dt, kA3);
-                nct = fma(dt, tsum, ct); nph = fma(dt, psum, ph);
-                kR[6] = nvr; kT[6] = nvth;
-                terr = fma(GB_BT7, nvt, terr); perr = fma(GB_BT7, nvph, perr);
-                rhs_accel<METRIC>(P, nr, nth, nvt, nvr, nvth, nvph, acc, s_, c_);
-                kA0[6] = acc[0]; kA1[6] = acc[1]; kA2[6] = acc[2]; kA3[6] = acc[3];
-                // error estimate: rms( dt*sum btilde_j k_j / (abstol + max(|u_prev|,|u|) reltol) )
-                double ee = 0;
-                {
-                    const double e0 = dt * terr, e1 = dt * errcomb(kR), e2 = dt * errcomb(kT), e3 = dt * perr;
-                    const double e4 = dt * errcomb(kA0), e5 = dt * errcomb(kA1), e6 = dt * errcomb(kA2), e7 = dt * errcomb(kA3);
-                    double q_;
-                    q_ = e0 / fma(fmax(fabs(ct), fabs(nct)), reltol, abstol); ee = fma(q_, q_, ee);
-                    q_ = e1 / fma(fmax(fabs(r), fabs(nr)), reltol, abstol); ee = fma(q_, q_, ee);
-                    q_ = e2 / fma(fmax(fabs(th), fabs(nth)), reltol, abstol); ee = fma(q_, q_, ee);
-                    q_ = e3 / fma(fmax(fabs(ph), fabs(nph)), reltol, abstol); ee = fma(q_, q_, ee);
-                    q_ = e4 / fma(fmax(fabs(vt), fabs(nvt)), reltol, abstol); ee = fma(q_, q_, ee);
-                    q_ = e5 / fma(fmax(fabs(vr), fabs(nvr)), reltol, abstol); ee = fma(q_, q_, ee);
-                    q_ = e6 / fma(fmax(fabs(vth), fabs(nvth)), reltol, abstol); ee = fma(q_, q_, ee);
-                    q_ = e7 / fma(fmax(fabs(vph), fabs(nvph)), reltol, abstol); ee = fma(q_, q_, ee);
-                }
-                const double EEst = sqrt(ee / 8.0);
-                // PI controller (stepsize_controller!, OrdinaryDiffEq)
-                double q, q11 = 1.0, logE = 0.0;
-                if (EEst == 0.0) q = 1.0 / qmax;
-                else {
-                    logE = log(EEst);
-                    q11 = ctrl_pow_log(logE, EEst, beta1, P.pow_mode);
-                    q = q11 / qoldpow;
-                    q = fmax(1.0 / qmax, fmin(1.0 / qmin, q / gamma));
-                }
-                if (EEst <= 1.0) {
-                    ++naccept;
-                    const double dtnew = dt / q;
-                    const double Eq = fmax(EEst, 1e-4);
-                    qoldpow = ctrl_pow_log(fmax(logE, log_qoldinit), Eq, beta2, P.pow_mode);
-                    if (EEst == 0.0) qoldpow = ctrl_pow_log(log_qoldinit, 1e-4, beta2, P.pow_mode);
-                    const double ttmp = lam + dt;
-                    const double tnew = (fabs(ttmp - tstop) < 100.0 * (fabs(tstop) * 2.220446049250313e-16)) ? tstop : ttmp;
-                    const double dtprop = fmax(fmin(dtmax, dtnew), dtmin);
-                    // ---- callbacks: continuous (disc) first, then discrete (user, chart)
-                    bool event = false;
-                    double cnext = 1.0;
-                    if (GEOM != GB200_GEOMETRY_NONE) {
-                        cnext = disc_condition<GEOM>(P, nr, s_, c_);
-                        const double sprev = sgn(cprev);
-                        if (sprev != 0.0) {
-                            if (sprev * sgn(cnext) <= 0.0) { event = true; ev_lo = 0.0; ev_hi = 1.0; }
-                            else {
-                                double C2r, C3r, C4r, C2t, C3t, C4t;
-                                dense_coeffs(kR, C2r, C3r, C4r);
-                                dense_coeffs(kT, C2t, C3t, C4t);
+            // 7th stage = the proposed state (FSAL)
+            nr = comb<6>(r, dt, vr, kR); nth = comb<6>(th, dt, vth, kT);
+            nvt = comb<6>(vt, dt, kA0[0], kA0); nvr = comb<6>(vr, dt, kA1[0], kA1);
+            nvth = comb<6>(vth, dt, kA2[0], kA2); nvph = comb<6>(vph, dt, kA3[0], kA3);
+            nct = fma(dt, tsum, ct); nph = fma(dt, psum, ph);
+            terr = fma(GB_BT7, nvt, terr); perr = fma(GB_BT7, nvph, perr);
+            rhs_accel<METRIC>(P, nr, nth, nvt, nvr, nvth, nvph, acc, s_, c_);
+            kA0[6] = acc[0]; kA1[6] = acc[1]; kA2[6] = acc[2]; kA3[6] = acc[3];
+            // ---- error estimate: rms( dt*sum btilde_j k_j / (abstol + max(|u_prev|,|u|) reltol) )
+            double ee = 0;
+            {
+                const double e0 = dt * terr, e1 = dt * errcomb(vr, kR, nvr), e2 = dt * errcomb(vth, kT, nvth), e3 = dt * perr;
+                const double e4 = dt * errcomb(kA0[0], kA0, kA0[6]), e5 = dt * errcomb(kA1[0], kA1, kA1[6]);
+                const double e6 = dt * errcomb(kA2[0], kA2, kA2[6]), e7 = dt * errcomb(kA3[0], kA3, kA3[6]);
+                double q_;
+                q_ = e0 * gb_rcp(fma(fmax(fabs(ct), fabs(nct)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e1 * gb_rcp(fma(fmax(fabs(r), fabs(nr)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e2 * gb_rcp(fma(fmax(fabs(th), fabs(nth)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e3 * gb_rcp(fma(fmax(fabs(ph), fabs(nph)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e4 * gb_rcp(fma(fmax(fabs(vt), fabs(nvt)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e5 * gb_rcp(fma(fmax(fabs(vr), fabs(nvr)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e6 * gb_rcp(fma(fmax(fabs(vth), fabs(nvth)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e7 * gb_rcp(fma(fmax(fabs(vph), fabs(nvph)), reltol, abstol)); ee = fma(q_, q_, ee);
+            }
+            const double EEst = sqrt(ee * 0.125);
+            // PI controller (stepsize_controller!, OrdinaryDiffEq)
+            double q, q11 = 1.0, logE = 0.0;
+            if (EEst == 0.0) q = 1.0 / qmax;
+            else {
+                logE = log(EEst);
+                q11 = ctrl_pow_log(logE, EEst, beta1, P.pow_mode);
+                q = q11 * gb_rcp(qoldpow);
+                q = fmax(1.0 / qmax, fmin(1.0 / qmin, q * (1.0 / gamma)));
+            }
+            if (EEst <= 1.0) {
+                ++naccept;
+                const double dtnew = dt * gb_rcp(q);
+                const double Eq = fmax(EEst, 1e-4);
+                qoldpow = ctrl_pow_log(fmax(logE, log_qoldinit), Eq, beta2, P.pow_mode);
+                if (EEst == 0.0) qoldpow = ctrl_pow_log(log_qoldinit, 1e-4, beta2, P.pow_mode);
+                const double ttmp = lam + dt;
+                const double tnew = (fabs(ttmp - tstop) < 100.0 * (fabs(tstop) * 2.220446049250313e-16)) ? tstop : ttmp;
+                const double dtprop = fmax(fmin(dtmax, dtnew), dtmin);
+                // ---- callbacks: continuous (disc) first, then discrete (user, chart)
+                bool event = false;
+                double cnext = 1.0;
+                if (GEOM != GB200_GEOMETRY_NONE) {
+                    cnext = disc_condition<GEOM>(P, nr, s_, c_);
+                    const double sprev = sgn(cprev);
+                    if (sprev != 0.0) {
+                        if (sprev * sgn(cnext) <= 0.0) { event = true; ev_lo = 0.0; ev_hi = 1.0; }
+                        else {
+                            double C2r, C3r, C4r, C2t, C3t, C4t;
+                            dense_coeffs(vth, kT, nvth, C2t, C3t, C4t);
+                            dense_coeffs(vr, kR, nvr, C2r, C3r, C4r);
+                            const double adt = fabs(dt);
+                            const double Bth = adt * (fabs(vth) + fabs(C2t) + fabs(C3t) + fabs(C4t));
+                            const double Br = adt * (fabs(vr) + fabs(C2r) + fabs(C3r) + fabs(C4r));
+                            if (sprev < 0.0 || scan_needed<GEOM>(P, r, acos_prev, cprev, Bth, Br)) {
+#pragma unroll 1
                                 for (int i = 1; i <= 6; ++i) { // interp_points = 8: Theta = 1/7 .. 6/7 (7/7 is u itself)
                                     const double Th = (double)i / 7.0;
                                     double si, ci;
-                                    sincos(dense_eval(th, dt, Th, kT[0], C2t, C3t, C4t), &si, &ci);
-                                    const double cn = disc_condition<GEOM>(P, dense_eval(r, dt, Th, kR[0], C2r, C3r, C4r), si, ci);
+                                    gb_sincos(dense_eval(th, dt, Th, vth, C2t, C3t, C4t), &si, &ci);
+                                    const double cn = disc_condition<GEOM>(P, dense_eval(r, dt, Th, vr, C2r, C3r, C4r), si, ci);
                                     if (sprev * cn < 0.0) { event = true; ev_lo = (double)(i - 1) / 7.0; ev_hi = Th; break; }
                                 }
                             }
                         }
                     }
-                    if (event) {
-                        // keep u_prev, the stage data and dt in registers; root find happens at finalise
-                        dt_step = dt; tfinal = lam; pend_event = true; pend_status = GB200_STATUS_INTERSECTED_WITH_GEOMETRY;
-                        state = LANE_PENDING;
-                    } else {
-                        int status = GB200_STATUS_NO_STATUS;
-                        bool term = false;
-                        if (P.callback_kind == GB200_CALLBACK_UPPER_HEMISPHERE && nr * c_ < P.callback_delta) { status = GB200_STATUS_OUT_OF_DOMAIN; term = true; }
-                        if (nr <= P.chart_inner) { status = GB200_STATUS_WITHIN_INNER_BOUNDARY; term = true; }
-                        else if (nr > P.chart_outer) { status = GB200_STATUS_OUT_OF_DOMAIN; term = true; }
-                        if (!(tnew < tstop)) term = true; // reached lambda_max: NoStatus unless a callback fired
-                        if (term) {
-                            tfinal = tnew; pend_status = status; pend_event = false; state = LANE_PENDING;
-                        } else { // apply_step!: u_prev <- u, FSAL
-                            lam = tnew; ct = nct; r = nr; th = nth; ph = nph; vt = nvt; vr = nvr; vth = nvth; vph = nvph;
-                            kA0[0] = kA0[6]; kA1[0] = kA1[6]; kA2[0] = kA2[6]; kA3[0] = kA3[6];
-                            kR[0] = nvr; kT[0] = nvth;
-                            cprev = cnext;
-                            dt = dtprop;
-                        }
-                    }
-                } else {
-                    ++nreject;
-                    dt = dt / fmin(1.0 / qmin, q11 / gamma); // step_reject_controller!
                 }
+                if (event) {
+                    // keep u_prev, the stage data and dt in registers; the root find happens at finalise
+                    dt_step = dt; tfinal = lam; pend_event = true; pend_status = GB200_STATUS_INTERSECTED_WITH_GEOMETRY;
+                    state = LANE_PENDING;
+                } else {
+                    int status = GB200_STATUS_NO_STATUS;
+                    bool term = false;
+                    if (P.callback_kind == GB200_CALLBACK_UPPER_HEMISPHERE && nr * c_ < P.callback_delta) { status = GB200_STATUS_OUT_OF_DOMAIN; term = true; }
+                    if (nr <= P.chart_inner) { status = GB200_STATUS_WITHIN_INNER_BOUNDARY; term = true; }
+                    else if (nr > P.chart_outer) { status = GB200_STATUS_OUT_OF_DOMAIN; term = true; }
+                    if (!(tnew < tstop)) term = true; // reached lambda_max: NoStatus unless a callback fired
+                    if (term) {
+                        tfinal = tnew; pend_status = status; pend_event = false; state = LANE_PENDING;
+                    } else { // apply_step!: u_prev <- u, FSAL
+                        lam = tnew; ct = nct; r = nr; th = nth; ph = nph; vt = nvt; vr = nvr; vth = nvth; vph = nvph;
+                        kA0[0] = kA0[6]; kA1[0] = kA1[6]; kA2[0] = kA2[6]; kA3[0] = kA3[6];
+                        cprev = cnext; acos_prev = fabs(c_);
+                        dt = dtprop;
+                    }
+                }
+            } else {
+                ++nreject;
+                dt = dt / fmin(1.0 / qmin, q11 / gamma); // step_reject_controller!
             }
         }
     }

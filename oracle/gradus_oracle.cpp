@@ -489,7 +489,11 @@ void interpolant(T Th, T dt, const T y0[8], const T k[7][8], T out[8], int ncomp
 // create_callback_set (callbacks.jl:25-28): continuous disc event, then discrete user, then chart.
 // optional per-step record (save_on = true path of the reference: every accepted step), used for debugging and
 // for the plunging-velocity table (orbit-solving.jl:137-167)
-struct StepRecord { std::vector<double> t, dt, eest; std::vector<double> u; };
+struct StepRecord {
+    std::vector<double> t, dt, eest; std::vector<double> u;
+    bool keep_dense = false;            // also keep u_prev and k1..k7 of every accepted step (band analysis)
+    std::vector<double> uprev, kst;     // 8 and 56 doubles per step
+};
 
 template <class T>
 void trace_ray(const gb200_problem& p, const Metric& m, const T u_init[8], RayResult<T>& res, StepRecord* rec = nullptr) {
@@ -603,7 +607,14 @@ void trace_ray(const gb200_problem& p, const Metric& m, const T u_init[8], RayRe
         note(EEst - T(1));
         if (!accept) { ++res.nreject; continue; }
         ++res.naccept;
-        if (rec) { rec->t.push_back((double)(t + dt)); rec->dt.push_back((double)dt); rec->eest.push_back((double)EEst); for (int i = 0; i < 8; ++i) rec->u.push_back((double)u[i]); }
+        if (rec) {
+            rec->t.push_back((double)(t + dt)); rec->dt.push_back((double)dt); rec->eest.push_back((double)EEst);
+            for (int i = 0; i < 8; ++i) rec->u.push_back((double)u[i]);
+            if (rec->keep_dense) {
+                for (int i = 0; i < 8; ++i) rec->uprev.push_back((double)uprev[i]);
+                for (int j = 0; j < 7; ++j) for (int i = 0; i < 8; ++i) rec->kst.push_back((double)k[j][i]);
+            }
+        }
         T dtnew = dt / q; // step_accept_controller!
         qold = std::max(EEst, qoldinit);
         tprev = t;
@@ -897,6 +908,53 @@ int run(const gb200_problem& p, const gb200_ic& ic, const gb200_range& rg, int n
     return 0;
 }
 
+// ------------------------------------------------------------------ grazing-band analysis
+// The reference detects the disc by sampling the condition at step ends and at 7 interior points of the dense
+// output (DiffEqBase interp_points = 8).  A ray whose path through the region {condition < 0} is shorter than the
+// sample spacing dt/7 is detected or missed depending on where the samples happen to fall, i.e. on the step
+// sequence, which differs between any two correct implementations at rounding level (the first steps' error
+// estimates are rounding-noise dominated).  This routine integrates the ray with a TRANSPARENT disc, finely
+// samples (256 per step) the dense output, finds the first interval with condition < 0 and returns
+//     ratio = (affine length of that interval) / (dt_local / 7),
+// 0 if the condition never goes negative.  0 < ratio < ~1.3 marks the band.
+static double band_ratio(const gb200_problem& p, const Metric& m, const double u0[8]) {
+    gb200_problem q = p;
+    q.geometry_kind = GB200_GEOMETRY_NONE;
+    StepRecord rec;
+    rec.keep_dense = true;
+    RayResult<double> res;
+    trace_ray<double>(q, m, u0, res, &rec);
+    const int nfine = 256;
+    const size_t ns = rec.t.size();
+    bool inside = false;
+    double lam_in = 0, dt_local = 0;
+    for (size_t sidx = 0; sidx < ns; ++sidx) {
+        const double dt = rec.dt[sidx], t1 = rec.t[sidx], t0 = t1 - dt;
+        const double* up = &rec.uprev[8 * sidx];
+        double k[7][8];
+        for (int j = 0; j < 7; ++j) for (int i = 0; i < 8; ++i) k[j][i] = rec.kst[56 * sidx + 8 * j + i];
+        if (!inside && p.geometry_kind == GB200_GEOMETRY_THIN_DISC) { // cheap skip far from the equatorial wedge
+            const double c0 = std::fabs(std::cos(up[2])), c1 = std::fabs(std::cos(rec.u[8 * sidx + 2]));
+            const bool crosses = (std::cos(up[2]) > 0) != (std::cos(rec.u[8 * sidx + 2]) > 0);
+            const double dth = std::fabs(rec.u[8 * sidx + 2] - up[2]);
+            if (!crosses && std::min(c0, c1) - dth > 4.0 * p.gtol) continue;
+        }
+        for (int f = (sidx == 0 ? 0 : 1); f <= nfine; ++f) {
+            const double Th = (double)f / nfine;
+            double ui[8];
+            interpolant<double>(Th, dt, up, k, ui, 3);
+            const bool neg = disc_condition<double>(p, ui[1], ui[2]) < 0.0;
+            if (neg && !inside) { inside = true; lam_in = t0 + Th * dt; dt_local = dt; }
+            else if (inside) {
+                dt_local = std::max(dt_local, dt);
+                if (!neg) return (t0 + Th * dt - lam_in) / (dt_local / 7.0);
+            }
+        }
+    }
+    if (inside) return 1e30; // still inside when the transparent ray terminated: a step end lies inside
+    return 0.0;
+}
+
 } // namespace orc
 
 // ====================================================================== C entry points (ctypes)
@@ -983,6 +1041,23 @@ int oracle_trace_path(const gb200_problem* p, const double* u0, int precision, i
     int n = (int)std::min<size_t>(rec.t.size(), (size_t)cap);
     for (int i = 0; i < n; ++i) { t[i] = rec.t[i]; dt[i] = rec.dt[i]; eest[i] = rec.eest[i]; for (int k = 0; k < 8; ++k) u8[8 * i + k] = rec.u[8 * i + k]; }
     return (int)rec.t.size();
+}
+int oracle_band(const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, int nthreads, double* ratio) {
+    orc::Metric m{p->metric_kind, p->metric_params[0], p->metric_params[1], p->metric_params[2]};
+    orc::LnrTransform<double> xfm;
+    if (ic->kind != GB200_IC_EXPLICIT) xfm.build(m, p->observer);
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t n = 0; n < rg->count; ++n) {
+        orc::RayIC ric;
+        orc::ic_for_ray(*p, *ic, rg->first + n * rg->stride, ric);
+        double u0[8];
+        orc::initial_state<double>(*p, m, ric, &xfm, u0);
+        ratio[n] = (p->geometry_kind == GB200_GEOMETRY_NONE) ? 0.0 : orc::band_ratio(*p, m, u0);
+    }
+    return 0;
 }
 int oracle_max_threads(void) {
 #ifdef _OPENMP

@@ -142,3 +142,13 @@ def trace_path(problem, u0, precision=0, cap=100000):
                                 cabi.dptr(u.reshape(-1)))
     n = min(n, cap)
     return t[:n], dt[:n], ee[:n], u[:n]
+
+
+def band_ratio(problem, ic, rng=None, nthreads=0):
+    """Per ray: affine length of the first passage through {disc condition < 0} of the TRANSPARENT trajectory
+    divided by the event sampler's spacing dt/7 (0: never inside).  0 < ratio < ~1.3 is the grazing band."""
+    rng = _range(ic, rng)
+    out = np.zeros(rng.count)
+    rc = lib().oracle_band(C.byref(problem), C.byref(ic), C.byref(rng), nthreads, cabi.dptr(out))
+    assert rc == 0
+    return out
