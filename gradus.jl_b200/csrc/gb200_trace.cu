@@ -29,10 +29,10 @@
 #define GB_BLOCK 128
 #endif
 #ifndef GB_MIN_BLOCKS
-#define GB_MIN_BLOCKS 2
+#define GB_MIN_BLOCKS 3
 #endif
 #ifndef GB_REFILL_THRESH
-#define GB_REFILL_THRESH 4
+#define GB_REFILL_THRESH 8
 #endif
 
 #define LANE_EMPTY 0
@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
     double kR[6], kT[6];                   // stage velocities v^r, v^theta of k2..k6 ([0] unused: k1's are vr, vth)
     double dt = 0, dt_step = 0, qoldpow = 1, cprev = 1, acos_prev = 1, ev_lo = 0, ev_hi = 0;
     double tfinal = 0;
+    double E_obs = 0, area = 1; // per-ray constants fixed at refill (redshift numerator, image-plane area weight)
     int state = LANE_EMPTY, pend_status = GB200_STATUS_NO_STATUS;
     bool pend_event = false;
     int naccept = 0, nreject = 0, flags = 0;
@@ -143,10 +144,10 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                     {
                         double s_, c_;
                         if (lo > 0.0) {
-                            sincos(dense_eval(th, dt_step, lo, vth, C2t, C3t, C4t), &s_, &c_);
+                            gb_sincos(dense_eval(th, dt_step, lo, vth, C2t, C3t, C4t), &s_, &c_);
                             flo = disc_condition<GEOM>(P, dense_eval(r, dt_step, lo, vr, C2r, C3r, C4r), s_, c_);
                         } else flo = cprev;
-                        sincos(dense_eval(th, dt_step, hi, vth, C2t, C3t, C4t), &s_, &c_);
+                        gb_sincos(dense_eval(th, dt_step, hi, vth, C2t, C3t, C4t), &s_, &c_);
                         fhi = disc_condition<GEOM>(P, dense_eval(r, dt_step, hi, vr, C2r, C3r, C4r), s_, c_);
                     }
                     if (fhi == 0.0) lo = hi;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                             if (!(mid > lo && mid < hi)) mid = 0.5 * (lo + hi);
                             if (!(mid > lo && mid < hi)) break;
                             double s_, c_;
-                            sincos(dense_eval(th, dt_step, mid, vth, C2t, C3t, C4t), &s_, &c_);
+                            gb_sincos(dense_eval(th, dt_step, mid, vth, C2t, C3t, C4t), &s_, &c_);
                             const double fm = disc_condition<GEOM>(P, dense_eval(r, dt_step, mid, vr, C2r, C3r, C4r), s_, c_);
                             if (fm != 0.0 && (fm > 0.0) == (sprev > 0.0)) {
                                 lo = mid; flo = fm;
@@ -226,23 +227,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                 if (P.o_nreject) P.o_nreject[n] = nreject;
                 if (P.o_flags) P.o_flags[n] = flags;
                 tot_acc += (unsigned)naccept; tot_rej += (unsigned)nreject; tot_flag += (flags != 0);
-                bool need_init = (P.npf > 0) || (P.o_g != nullptr);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) need_init = need_init || (P.o_x0[k] != nullptr) || (P.o_v0[k] != nullptr);
-                if (need_init) {
-                    GbRayInit ri;
-                    ray_initial_state(P, P.first + n * P.stride, ri); // deterministic: same values as at start
-                    double go[5];
-                    if (P.ic_kind == GB200_IC_EXPLICIT) metric_components_rt(P, ri.x[1], ri.x[2], go);
-                    else {
-#pragma unroll
-                        for (int k = 0; k < 5; ++k) go[k] = P.go[k];
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (P.o_x0[k]) P.o_x0[k][n] = ri.x[k];
-                        if (P.o_v0[k]) P.o_v0[k][n] = ri.v[k];
-                    }
+                if (P.npf > 0 || P.o_g != nullptr) {
                     const bool hit = (status == GB200_STATUS_INTERSECTED_WITH_GEOMETRY);
                     double g_red = nan("");
                     bool have_g = false;
@@ -251,7 +236,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                         const int pf = P.pf[k];
                         if (pf == GB200_PF_SHADOW) { if (tfinal < P.lam1) val = tfinal; }
                         else if (pf == GB200_PF_REDSHIFT) {
-                            if (hit) { if (!have_g) { g_red = redshift_endpoint(P, xe, ve, ri.v, go); have_g = true; } val = g_red; }
+                            if (hit) { if (!have_g) { g_red = redshift_endpoint<METRIC>(P, xe, ve, E_obs); have_g = true; } val = g_red; }
                         } else if (pf == GB200_PF_DISC_RADIUS) { if (hit) val = nr * fabs(sin(nth)); }
                         else if (pf == GB200_PF_COORDINATE_TIME) { if (hit) val = nct; }
                         else if (pf == GB200_PF_STATUS) val = (double)status;
@@ -263,8 +248,8 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                         if (hit) {
                             const double rho = nr * fabs(sin(nth));
                             if (P.min_re <= rho && rho <= P.max_re) {
-                                gg = have_g ? g_red : redshift_endpoint(P, xe, ve, ri.v, go);
-                                ff = emissivity_eval(P, rho) * gg * gg * gg * ri.area;
+                                gg = have_g ? g_red : redshift_endpoint<METRIC>(P, xe, ve, E_obs);
+                                ff = emissivity_eval(P, rho) * gg * gg * gg * area;
                             }
                         }
                         P.o_g[n] = gg;
@@ -288,6 +273,18 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                         ray_initial_state(P, P.first + s * P.stride, ri);
                         lam = P.lam0; ct = ri.x[0]; r = ri.x[1]; th = ri.x[2]; ph = ri.x[3];
                         vt = ri.v[0]; vr = ri.v[1]; vth = ri.v[2]; vph = ri.v[3];
+                        area = ri.area;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { // GeodesicPoint.x_init / v_init are known now
+                            if (P.o_x0[k]) P.o_x0[k][s] = ri.x[k];
+                            if (P.o_v0[k]) P.o_v0[k][s] = ri.v[k];
+                        }
+                        if (P.ic_kind == GB200_IC_EXPLICIT) {
+                            double go[5], sx, cx;
+                            sincos(th, &sx, &cx);
+                            metric_components_t<METRIC>(P, r, sx, cx, go);
+                            E_obs = go[0] * vt + go[4] * vph;
+                        } else E_obs = P.go[0] * vt + P.go[4] * vph;
                         naccept = 0; nreject = 0; flags = 0; iter = 0;
                         pend_event = false;
                         // f0 and the Hairer-Wanner initial step (ode_determine_initdt)
@@ -300,8 +297,8 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                         double sk[8], d0 = 0, d1 = 0;
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            sk[k] = fma(fabs(u0[k]), reltol, abstol);
-                            const double a0 = u0[k] / sk[k], a1 = f0[k] / sk[k];
+                            sk[k] = gb_rcp(fma(fabs(u0[k]), reltol, abstol)); // 1/sk
+                            const double a0 = u0[k] * sk[k], a1 = f0[k] * sk[k];
                             d0 = fma(a0, a0, d0); d1 = fma(a1, a1, d1);
                         }
                         d0 = sqrt(d0 / 8.0); d1 = sqrt(d1 / 8.0);
@@ -314,10 +311,11 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                                               acc1[0], acc1[1], acc1[2], acc1[3]};
                         double d2 = 0;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) { const double a2 = (f1[k] - f0[k]) / sk[k]; d2 = fma(a2, a2, d2); }
+                        for (int k = 0; k < 8; ++k) { const double a2 = (f1[k] - f0[k]) * sk[k]; d2 = fma(a2, a2, d2); }
                         d2 = sqrt(d2 / 8.0) / dt0;
                         const double md = fmax(d1, d2);
-                        const double dt1 = (md <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(md)) / 5.0);
+                        // 10^(-(2 + log10 md)/5) = (100 md)^(-1/5)
+                        const double dt1 = (md <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : exp(-0.2 * log(100.0 * md));
                         dt = fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
                         kA0[0] = acc[0]; kA1[0] = acc[1]; kA2[0] = acc[2]; kA3[0] = acc[3];
                         qoldpow = ctrl_pow_log(log_qoldinit, 1e-4, beta2, P.pow_mode);
