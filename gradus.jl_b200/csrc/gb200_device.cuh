@@ -409,11 +409,11 @@ GB_D void kerr_rhs_accel(double M, double a, double r, double s, double c, doubl
     acc[3] = -fma(gitph, Pt, giphph * Pp);
 }
 
-// The right-hand side is ONE out-of-line device function shared by the six stages of a step: the hot loop
-// then fits the instruction cache (v4 measured 2.1 issue-slots of instruction-fetch stall per issued instruction
-// with six inlined copies).  Everything travels in registers: scalars in, a small struct out.
+// The right-hand side, inlined at each of the six stages.  (Measured alternatives, profiles/r01_tuning_log.md: one
+// out-of-line copy removes instruction-fetch stalls but pays ~25% more instructions in call marshalling; with the
+// CTA-synchronous stepping of gb200_trace.cu the inlined form is the faster one.)
 struct GbAcc { double a0, a1, a2, a3, s, c; };
-#ifndef GB_RHS_INLINE
+#ifdef GB_RHS_CALL /* tuning variant: one out-of-line copy (smaller code, but ~25% more instructions for call marshalling) */
 #define GB_RHS_ATTR __device__ __noinline__
 #else
 #define GB_RHS_ATTR __device__ __forceinline__

@@ -32,7 +32,10 @@
 #define GB_MIN_BLOCKS 3
 #endif
 #ifndef GB_REFILL_THRESH
-#define GB_REFILL_THRESH 8
+#define GB_REFILL_THRESH 8 /* idle lanes per warp that trigger a service pass (per CTA: x warps per CTA) */
+#endif
+#ifndef GB_BLOCK_SYNC
+#define GB_BLOCK_SYNC 1 /* CTA-synchronous stepping: one barrier per step attempt keeps the warps of a CTA in lockstep */
 #endif
 
 #define LANE_EMPTY 0
@@ -124,11 +127,25 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
 #pragma unroll
     for (int j = 0; j < 6; ++j) { kR[j] = kT[j] = 0.0; }
 
+#if GB_BLOCK_SYNC
+    __shared__ int sh_exhausted;
+    if (threadIdx.x == 0) sh_exhausted = 0;
+    __syncthreads();
+#endif
     for (;;) {
+#if GB_BLOCK_SYNC
+        // One barrier per step attempt: the warps of a CTA walk the (long, straight-line) step code together and
+        // share its instruction-cache lines, and the decision to run the cold service code is CTA-uniform, so that
+        // code is fetched once per CTA instead of once per warp.
+        const int idle_cta = __syncthreads_count(state != LANE_RUN);
+        exhausted = (*(volatile int*)&sh_exhausted) != 0;
+        const bool service = idle_cta >= GB_REFILL_THRESH * (GB_BLOCK / 32) || idle_cta == GB_BLOCK;
+#else
         unsigned run_mask = __ballot_sync(FULLMASK, state == LANE_RUN);
         const unsigned pend_mask = __ballot_sync(FULLMASK, state == LANE_PENDING);
         const int nidle = 32 - __popc(run_mask);
         const bool service = (run_mask == 0) || (nidle >= GB_REFILL_THRESH && (pend_mask != 0 || !exhausted));
+#endif
         if (service) {
             // ================= finalise terminated lanes =================
             if (state == LANE_PENDING) {
@@ -322,10 +339,19 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                         state = LANE_RUN;
                     }
                 }
-                if ((int64_t)base + nfree >= P.count) exhausted = true;
+                if ((int64_t)base + nfree >= P.count) {
+                    exhausted = true;
+#if GB_BLOCK_SYNC
+                    if (lane == 0) *(volatile int*)&sh_exhausted = 1;
+#endif
+                }
             }
+#if GB_BLOCK_SYNC
+            if (__syncthreads_count(state == LANE_RUN) == 0) break; // CTA-uniform: queue drained and every lane finalised
+#else
             run_mask = __ballot_sync(FULLMASK, state == LANE_RUN);
             if (run_mask == 0) break;
+#endif
         }
 
         // ================= one Tsit5 step attempt for every running lane (straight-line: no taken branches) ==========

@@ -1059,6 +1059,29 @@ int oracle_band(const gb200_problem* p, const gb200_ic* ic, const gb200_range* r
     }
     return 0;
 }
+// "Same geodesic" check for rays that end in a DiscreteCallback (chart / hemisphere): their stored endpoint is
+// wherever the last accepted step landed, which depends on the step sequence.  Integrate ray i from its initial
+// state exactly to the affine parameter lam_end[i] (no geometry, no chart, no callback) and return the state.
+int oracle_trace_to(const gb200_problem* p, int64_t n, const double* u0 /* n x 8, row-major */, const double* lam_end,
+                    int nthreads, double* u_out /* n x 8 */) {
+    orc::Metric m{p->metric_kind, p->metric_params[0], p->metric_params[1], p->metric_params[2]};
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = 0; i < n; ++i) {
+        gb200_problem q = *p;
+        q.geometry_kind = GB200_GEOMETRY_NONE;
+        q.callback_kind = GB200_CALLBACK_NONE;
+        q.chart_inner = 0.0;
+        q.chart_outer = 1e300;
+        q.lambda_max = lam_end[i];
+        orc::RayResult<double> res;
+        orc::trace_ray<double>(q, m, u0 + 8 * i, res);
+        for (int k = 0; k < 4; ++k) { u_out[8 * i + k] = res.x[k]; u_out[8 * i + 4 + k] = res.v[k]; }
+    }
+    return 0;
+}
 int oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -152,3 +152,14 @@ def band_ratio(problem, ic, rng=None, nthreads=0):
     rc = lib().oracle_band(C.byref(problem), C.byref(ic), C.byref(rng), nthreads, cabi.dptr(out))
     assert rc == 0
     return out
+
+
+def trace_to(problem, u0, lam_end, nthreads=0):
+    """Integrate each row of u0 (n x 8) exactly to lam_end[i] with no termination conditions; returns n x 8 states."""
+    u0 = np.ascontiguousarray(u0, np.float64)
+    lam_end = np.ascontiguousarray(lam_end, np.float64)
+    out = np.zeros_like(u0)
+    rc = lib().oracle_trace_to(C.byref(problem), C.c_int64(len(lam_end)), cabi.dptr(u0.reshape(-1)), cabi.dptr(lam_end), nthreads,
+                               cabi.dptr(out.reshape(-1)))
+    assert rc == 0
+    return out
