@@ -249,10 +249,11 @@ def test_full_size_trace_conservation_laws(ensemble):
 
     E0, L0, n0 = invariants(gps.x_init, gps.v_init)
     E1, L1, n1 = invariants(gps.x, gps.v)
-    far = gps.status != cabi.STATUS_WITHIN_INNER_BOUNDARY  # v^t diverges at the horizon chart: checked separately, scaled
+    scale = 1.0 + np.abs(gps.v[0])  # v^t diverges towards the horizon: errors are measured against it
+    far = scale < 10.0
+    assert far.mean() > 0.95
     assert np.abs(n0).max() < 1e-12
     assert np.abs(E1 - E0)[far].max() < 1e-6 and np.abs(L1 - L0)[far].max() < 1e-5 and np.abs(n1)[far].max() < 1e-6
-    scale = 1.0 + np.abs(gps.v[0])
     assert (np.abs(E1 - E0) / scale).max() < 1e-6 and (np.abs(n1) / scale**2).max() < 1e-6
     assert np.bincount(gps.status, minlength=4)[cabi.STATUS_OUT_OF_DOMAIN] == 0  # nothing escapes past r=12000 by lambda=2000
 
