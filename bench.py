@@ -331,6 +331,8 @@ def main():
     if world > 1:
         from gradus_b200 import distributed as gd
 
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL prints its version banner there)
         gd.init_from_env("nccl")
     run_ours(args, rank, world, local)
     if world > 1:

@@ -40,6 +40,19 @@ GB_HD inline double gb_rcp(double x) {
 #endif
 }
 
+// One Newton step only (relative error ~2^-40): for the error-norm scales, whose reciprocal feeds an estimate that
+// already carries ~1e-7 of rounding noise.
+GB_HD inline double gb_rcp_lo(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+#else
+    return 1.0 / x;
+#endif
+}
+
 #include "jp_metric_generated.cuh"
 
 #define GB_MAX_PF 4

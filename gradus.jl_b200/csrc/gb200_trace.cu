@@ -37,6 +37,9 @@
 #ifndef GB_BLOCK_SYNC
 #define GB_BLOCK_SYNC 1 /* CTA-synchronous stepping: one barrier per step attempt keeps the warps of a CTA in lockstep */
 #endif
+#ifndef GB_SYNC_EVERY
+#define GB_SYNC_EVERY 4 /* barrier (and service decision) every n-th attempt */
+#endif
 
 #define LANE_EMPTY 0
 #define LANE_RUN 1
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
     for (int j = 0; j < 6; ++j) { kR[j] = kT[j] = 0.0; }
 
 #if GB_BLOCK_SYNC
+    unsigned loop_count = 0;
     __shared__ int sh_exhausted;
     if (threadIdx.x == 0) sh_exhausted = 0;
     __syncthreads();
@@ -137,9 +141,12 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
         // One barrier per step attempt: the warps of a CTA walk the (long, straight-line) step code together and
         // share its instruction-cache lines, and the decision to run the cold service code is CTA-uniform, so that
         // code is fetched once per CTA instead of once per warp.
-        const int idle_cta = __syncthreads_count(state != LANE_RUN);
-        exhausted = (*(volatile int*)&sh_exhausted) != 0;
-        const bool service = idle_cta >= GB_REFILL_THRESH * (GB_BLOCK / 32) || idle_cta == GB_BLOCK;
+        bool service = false;
+        if (GB_SYNC_EVERY == 1 || (loop_count++ % GB_SYNC_EVERY) == 0) {
+            const int idle_cta = __syncthreads_count(state != LANE_RUN);
+            exhausted = (*(volatile int*)&sh_exhausted) != 0;
+            service = idle_cta >= GB_REFILL_THRESH * (GB_BLOCK / 32) || idle_cta == GB_BLOCK;
+        }
 #else
         unsigned run_mask = __ballot_sync(FULLMASK, state == LANE_RUN);
         const unsigned pend_mask = __ballot_sync(FULLMASK, state == LANE_PENDING);
@@ -335,7 +342,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                         const double dt1 = (md <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : exp(-0.2 * log(100.0 * md));
                         dt = fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
                         kA0[0] = acc[0]; kA1[0] = acc[1]; kA2[0] = acc[2]; kA3[0] = acc[3];
-                        qoldpow = ctrl_pow_log(log_qoldinit, 1e-4, beta2, P.pow_mode);
+                        qoldpow = (P.pow_mode == GB200_POW_FAST32) ? ctrl_pow_log(log_qoldinit, 1e-4, beta2, P.pow_mode) : beta2 * log_qoldinit;
                         state = LANE_RUN;
                     }
                 }
@@ -402,31 +409,32 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                 const double e4 = dt * errcomb(kA0[0], kA0, kA0[6]), e5 = dt * errcomb(kA1[0], kA1, kA1[6]);
                 const double e6 = dt * errcomb(kA2[0], kA2, kA2[6]), e7 = dt * errcomb(kA3[0], kA3, kA3[6]);
                 double q_;
-                q_ = e0 * gb_rcp(fma(fmax(fabs(ct), fabs(nct)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e1 * gb_rcp(fma(fmax(fabs(r), fabs(nr)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e2 * gb_rcp(fma(fmax(fabs(th), fabs(nth)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e3 * gb_rcp(fma(fmax(fabs(ph), fabs(nph)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e4 * gb_rcp(fma(fmax(fabs(vt), fabs(nvt)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e5 * gb_rcp(fma(fmax(fabs(vr), fabs(nvr)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e6 * gb_rcp(fma(fmax(fabs(vth), fabs(nvth)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e7 * gb_rcp(fma(fmax(fabs(vph), fabs(nvph)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e0 * gb_rcp_lo(fma(fmax(fabs(ct), fabs(nct)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e1 * gb_rcp_lo(fma(fmax(fabs(r), fabs(nr)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e2 * gb_rcp_lo(fma(fmax(fabs(th), fabs(nth)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e3 * gb_rcp_lo(fma(fmax(fabs(ph), fabs(nph)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e4 * gb_rcp_lo(fma(fmax(fabs(vt), fabs(nvt)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e5 * gb_rcp_lo(fma(fmax(fabs(vr), fabs(nvr)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e6 * gb_rcp_lo(fma(fmax(fabs(vth), fabs(nvth)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e7 * gb_rcp_lo(fma(fmax(fabs(vph), fabs(nvph)), reltol, abstol)); ee = fma(q_, q_, ee);
             }
             const double EEst = sqrt(ee * 0.125);
-            // PI controller (stepsize_controller!, OrdinaryDiffEq)
-            double q, q11 = 1.0, logE = 0.0;
+            // PI controller (stepsize_controller!, OrdinaryDiffEq): q = EEst^beta1 / qold^beta2 / gamma, clamped.
+            // In the default pow mode this is one log and one exp: q = exp(beta1 log EEst - beta2 log qold) / gamma.
+            double q, logE = 0.0;
+            const bool fast32 = (P.pow_mode == GB200_POW_FAST32);
             if (EEst == 0.0) q = 1.0 / qmax;
             else {
                 logE = log(EEst);
-                q11 = ctrl_pow_log(logE, EEst, beta1, P.pow_mode);
-                q = q11 * gb_rcp(qoldpow);
+                if (fast32) q = ctrl_pow_log(logE, EEst, beta1, P.pow_mode) * gb_rcp(qoldpow);
+                else q = exp(fma(beta1, logE, -qoldpow)); // qoldpow holds beta2 * log(qold) in this mode
                 q = fmax(1.0 / qmax, fmin(1.0 / qmin, q * (1.0 / gamma)));
             }
             if (EEst <= 1.0) {
                 ++naccept;
                 const double dtnew = dt * gb_rcp(q);
-                const double Eq = fmax(EEst, 1e-4);
-                qoldpow = ctrl_pow_log(fmax(logE, log_qoldinit), Eq, beta2, P.pow_mode);
-                if (EEst == 0.0) qoldpow = ctrl_pow_log(log_qoldinit, 1e-4, beta2, P.pow_mode);
+                if (fast32) qoldpow = ctrl_pow_log(fmax(logE, log_qoldinit), fmax(EEst, 1e-4), beta2, P.pow_mode);
+                else qoldpow = beta2 * ((EEst == 0.0) ? log_qoldinit : fmax(logE, log_qoldinit));
                 const double ttmp = lam + dt;
                 const double tnew = (fabs(ttmp - tstop) < 100.0 * (fabs(tstop) * 2.220446049250313e-16)) ? tstop : ttmp;
                 const double dtprop = fmax(fmin(dtmax, dtnew), dtmin);
@@ -439,13 +447,21 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                     if (sprev != 0.0) {
                         if (sprev * sgn(cnext) <= 0.0) { event = true; ev_lo = 0.0; ev_hi = 1.0; }
                         else {
-                            double C2r, C3r, C4r, C2t, C3t, C4t;
-                            dense_coeffs(vth, kT, nvth, C2t, C3t, C4t);
-                            dense_coeffs(vr, kR, nvr, C2r, C3r, C4r);
+                            // cheap bound first: |u(Th) - u0| <= |dt| * L * max_j |k_j| with L = max_Th sum_j |b_j(Th)| = 7.5822
+                            // for the Tsit5 dense output; only when it is inconclusive are the polynomial coefficients formed
                             const double adt = fabs(dt);
-                            const double Bth = adt * (fabs(vth) + fabs(C2t) + fabs(C3t) + fabs(C4t));
-                            const double Br = adt * (fabs(vr) + fabs(C2r) + fabs(C3r) + fabs(C4r));
-                            if (sprev < 0.0 || scan_needed<GEOM>(P, r, acos_prev, cprev, Bth, Br)) {
+                            const double mth = fmax(fmax(fmax(fabs(vth), fabs(kT[1])), fmax(fabs(kT[2]), fabs(kT[3]))), fmax(fmax(fabs(kT[4]), fabs(kT[5])), fabs(nvth)));
+                            const double mr = fmax(fmax(fmax(fabs(vr), fabs(kR[1])), fmax(fabs(kR[2]), fabs(kR[3]))), fmax(fmax(fabs(kR[4]), fabs(kR[5])), fabs(nvr)));
+                            bool need = sprev < 0.0 || scan_needed<GEOM>(P, r, acos_prev, cprev, adt * 7.5823 * mth, adt * 7.5823 * mr);
+                            double C2r = 0, C3r = 0, C4r = 0, C2t = 0, C3t = 0, C4t = 0;
+                            if (need) {
+                                dense_coeffs(vth, kT, nvth, C2t, C3t, C4t);
+                                dense_coeffs(vr, kR, nvr, C2r, C3r, C4r);
+                                const double Bth = adt * (fabs(vth) + fabs(C2t) + fabs(C3t) + fabs(C4t));
+                                const double Br = adt * (fabs(vr) + fabs(C2r) + fabs(C3r) + fabs(C4r));
+                                need = sprev < 0.0 || scan_needed<GEOM>(P, r, acos_prev, cprev, Bth, Br);
+                            }
+                            if (need) {
 #pragma unroll 1
                                 for (int i = 1; i <= 6; ++i) { // interp_points = 8: Theta = 1/7 .. 6/7 (7/7 is u itself)
                                     const double Th = (double)i / 7.0;
@@ -480,6 +496,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                 }
             } else {
                 ++nreject;
+                const double q11 = ctrl_pow_log(logE, EEst, beta1, P.pow_mode);
                 dt = dt / fmin(1.0 / qmin, q11 / gamma); // step_reject_controller!
             }
         }
