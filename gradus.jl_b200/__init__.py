@@ -39,6 +39,7 @@ from .api import (  # noqa: F401
     lineprofile,
     rendergeodesics,
     tracegeodesics,
+    tracegeodesics_batch,
     tracing_configuration,
 )
 from ._cabi import GradusB200Error  # noqa: F401

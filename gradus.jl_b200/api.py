@@ -466,6 +466,25 @@ def solve_tracing_problem(config: TracingConfiguration) -> GeodesicPoints:
     return GeodesicPoints(out, config.lambda_domain[0])
 
 
+def tracegeodesics_batch(configs: Sequence[TracingConfiguration]) -> list:
+    """Many (short) ensembles in one call: every configuration is traced on its own stream of the first device's
+    stream pool and the host synchronises once (the reference calls `tracegeodesics` once per corona
+    model, src/corona/models/lamp-post.jl:89-100).  Returns one `GeodesicPoints` per configuration."""
+    if not configs:
+        return []
+    ens = configs[0].ensemble
+    nb = len(configs)
+    pcs = [c.to_c() for c in configs]
+    problems = (cabi.Problem * nb)(*[pc[0] for pc in pcs])
+    ics = (cabi.IC * nb)(*[pc[1] for pc in pcs])
+    ranges = (cabi.Range * nb)(*[cabi.Range(0, pc[1].n, 1) for pc in pcs])
+    arrays = [cabi.EndpointArrays(pc[1].n) for pc in pcs]
+    outs = (cabi.Endpoints * nb)(*[a.c for a in arrays])
+    ctx = ens.ctx(ens.devices[0])
+    cabi.check(cabi.load().gb200_trace_batch(ctx, nb, problems, ics, ranges, outs), ctx)
+    return [GeodesicPoints(a, c.lambda_domain[0]) for a, c in zip(arrays, configs)]
+
+
 def tracegeodesics(m, position, velocity, *args, **kwargs) -> GeodesicPoints:
     """`tracegeodesics(m, x, v | plane | velfunc, [geometry], λ; kwargs...)` (src/tracing/tracing.jl:66-80)."""
     config = tracing_configuration(m, position, velocity, *args, **kwargs)

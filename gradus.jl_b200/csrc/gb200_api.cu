@@ -33,6 +33,9 @@ struct gb200_ctx {
     std::vector<DevBuf> pool;
     unsigned long long* d_queue = nullptr; // [0] queue, [1..3] counters
     double fp64_peak = 0.0;
+    std::vector<cudaStream_t> pool_streams; // gb200_trace_batch
+    void* stage = nullptr;                  // pinned host staging for gb200_trace_batch
+    size_t stage_cap = 0;
 };
 
 static int fail(gb200_ctx* ctx, int code, const char* fmt, ...) {
@@ -228,7 +231,7 @@ static int pool_get(gb200_ctx* ctx, size_t slot, size_t bytes, void** out) {
 // pool slots
 enum { SL_STATUS = 0, SL_LAMBDA, SL_X0, SL_V0 = SL_X0 + 4, SL_XI0 = SL_V0 + 4, SL_VI0 = SL_XI0 + 4, SL_NACC = SL_VI0 + 4, SL_NREJ, SL_FLAGS,
        SL_IMG0, SL_G = SL_IMG0 + GB_MAX_PF, SL_F, SL_EX0, SL_EV0 = SL_EX0 + 4, SL_BINS = SL_EV0 + 4, SL_PARTIAL, SL_FLUX, SL_EMR, SL_EME,
-       SL_PL0, SL_SCRATCH = SL_PL0 + 4, SL_COUNT };
+       SL_PL0, SL_SCRATCH = SL_PL0 + 4, SL_BATCH, SL_BATCH_QUEUE, SL_COUNT };
 
 static int upload(gb200_ctx* ctx, size_t slot, const void* host, size_t bytes, const void** dev) {
     void* d = nullptr;
@@ -348,6 +351,8 @@ void gb200_destroy(gb200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (auto& b : ctx->pool) if (b.p) cudaFree(b.p);
     if (ctx->d_queue) cudaFree(ctx->d_queue);
+    for (auto st : ctx->pool_streams) cudaStreamDestroy(st);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -428,6 +433,126 @@ int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, cons
     BACK(out->flags, P.o_flags, int32_t)
 #undef BACK
     return finish_stats(ctx, rg->count);
+}
+
+int gb200_trace_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* problems, const gb200_ic* ics,
+                      const gb200_range* ranges, gb200_endpoints* outs) {
+    if (!ctx) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null context");
+    if (nbatch < 1 || !problems || !ics || !ranges || !outs) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad batch arguments");
+    for (int b = 0; b < nbatch; ++b) {
+        int rc = validate(ctx, &problems[b], &ics[b]); if (rc) return rc;
+        rc = validate_range(ctx, &ics[b], &ranges[b]); if (rc) return rc;
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    ctx->stats = gb200_stats{};
+    ctx->cur = ctx->stream;
+    const int nstreams = nbatch < 32 ? nbatch : 32;
+    while ((int)ctx->pool_streams.size() < nstreams) {
+        cudaStream_t st;
+        CU(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ctx->pool_streams.push_back(st);
+    }
+    // One device arena: [explicit ICs of every ensemble | outputs of every ensemble], mirrored by one pinned host
+    // staging buffer, so the whole batch costs one H2D and one D2H copy instead of ~20 small ones per ensemble.
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    struct Off { size_t status, lambda, x[4], v[4], x0[4], v0[4], nacc, nrej, flags, ex[4], ev[4]; };
+    std::vector<Off> off((size_t)nbatch);
+    size_t total = 0;
+    for (int b = 0; b < nbatch; ++b)
+        if (ics[b].kind == GB200_IC_EXPLICIT)
+            for (int k = 0; k < 4; ++k) { off[(size_t)b].ex[k] = total; total += al(8 * (size_t)ics[b].n); off[(size_t)b].ev[k] = total; total += al(8 * (size_t)ics[b].n); }
+    const size_t in_bytes = total;
+    for (int b = 0; b < nbatch; ++b) {
+        const size_t n = (size_t)ranges[b].count;
+        Off& o = off[(size_t)b];
+        o.status = total; total += al(4 * n);
+        o.lambda = total; total += al(8 * n);
+        for (int k = 0; k < 4; ++k) { o.x[k] = total; total += al(8 * n); o.v[k] = total; total += al(8 * n);
+                                      o.x0[k] = total; total += al(8 * n); o.v0[k] = total; total += al(8 * n); }
+        o.nacc = total; total += al(4 * n); o.nrej = total; total += al(4 * n); o.flags = total; total += al(4 * n);
+    }
+    void* arena_v = nullptr;
+    int rc = pool_get(ctx, SL_BATCH, total + 256, &arena_v); if (rc) return rc;
+    char* arena = (char*)arena_v;
+    if (ctx->stage_cap < total) {
+        if (ctx->stage) cudaFreeHost(ctx->stage);
+        ctx->stage = nullptr; ctx->stage_cap = 0;
+        CU(ctx, cudaMallocHost(&ctx->stage, total + 256));
+        ctx->stage_cap = total;
+    }
+    char* stage = (char*)ctx->stage;
+    void* qv = nullptr;
+    rc = pool_get(ctx, SL_BATCH_QUEUE, sizeof(unsigned long long) * 4 * (size_t)nbatch, &qv); if (rc) return rc;
+    unsigned long long* queues = (unsigned long long*)qv;
+    for (int b = 0; b < nbatch; ++b)
+        if (ics[b].kind == GB200_IC_EXPLICIT)
+            for (int k = 0; k < 4; ++k) {
+                memcpy(stage + off[(size_t)b].ex[k], ics[b].x[k], 8 * (size_t)ics[b].n);
+                memcpy(stage + off[(size_t)b].ev[k], ics[b].v[k], 8 * (size_t)ics[b].n);
+            }
+    CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(ctx, cudaMemsetAsync(queues, 0, sizeof(unsigned long long) * 4 * (size_t)nbatch, ctx->stream));
+    if (in_bytes) CU(ctx, cudaMemcpyAsync(arena, stage, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    for (int sidx = 0; sidx < nstreams; ++sidx) CU(ctx, cudaStreamWaitEvent(ctx->pool_streams[(size_t)sidx], ctx->ev1, 0));
+    for (int b = 0; b < nbatch; ++b) {
+        cudaStream_t st = ctx->pool_streams[(size_t)(b % nstreams)];
+        const gb200_endpoints& out = outs[b];
+        const Off& o = off[(size_t)b];
+        GbParams P;
+        fill_params(&problems[b], &ics[b], &ranges[b], P);
+        if (ics[b].kind == GB200_IC_EXPLICIT)
+            for (int k = 0; k < 4; ++k) { P.ex[k] = (const double*)(arena + o.ex[k]); P.ev[k] = (const double*)(arena + o.ev[k]); }
+        if (out.status) P.o_status = (int32_t*)(arena + o.status);
+        if (out.lambda_max) P.o_lambda = (double*)(arena + o.lambda);
+        for (int k = 0; k < 4; ++k) {
+            if (out.x[k]) P.o_x[k] = (double*)(arena + o.x[k]);
+            if (out.v[k]) P.o_v[k] = (double*)(arena + o.v[k]);
+            if (out.x_init[k]) P.o_x0[k] = (double*)(arena + o.x0[k]);
+            if (out.v_init[k]) P.o_v0[k] = (double*)(arena + o.v0[k]);
+        }
+        if (out.naccept) P.o_naccept = (int32_t*)(arena + o.nacc);
+        if (out.nreject) P.o_nreject = (int32_t*)(arena + o.nrej);
+        if (out.flags) P.o_flags = (int32_t*)(arena + o.flags);
+        P.queue = queues + 4 * (size_t)b;
+        P.counters = P.queue + 1;
+        int blocks = 0;
+        if (ranges[b].count) { CU(ctx, gb200_launch_trace(P, ctx->sm_count, st, &blocks)); ctx->stats.launches += 1; }
+    }
+    for (int sidx = 0; sidx < nstreams; ++sidx) { // join the pool back into the context stream
+        CU(ctx, cudaEventRecord(ctx->ev2, ctx->pool_streams[(size_t)sidx]));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev2, 0));
+    }
+    std::vector<unsigned long long> c((size_t)nbatch * 4);
+    if (total > in_bytes) CU(ctx, cudaMemcpyAsync(stage + in_bytes, arena + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(c.data(), queues, sizeof(unsigned long long) * c.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < nbatch; ++b) { // scatter the staging buffer into the caller's SoA
+        const gb200_endpoints& out = outs[b];
+        const Off& o = off[(size_t)b];
+        const size_t n = (size_t)ranges[b].count;
+        if (out.status) memcpy(out.status, stage + o.status, 4 * n);
+        if (out.lambda_max) memcpy(out.lambda_max, stage + o.lambda, 8 * n);
+        for (int k = 0; k < 4; ++k) {
+            if (out.x[k]) memcpy(out.x[k], stage + o.x[k], 8 * n);
+            if (out.v[k]) memcpy(out.v[k], stage + o.v[k], 8 * n);
+            if (out.x_init[k]) memcpy(out.x_init[k], stage + o.x0[k], 8 * n);
+            if (out.v_init[k]) memcpy(out.v_init[k], stage + o.v0[k], 8 * n);
+        }
+        if (out.naccept) memcpy(out.naccept, stage + o.nacc, 4 * n);
+        if (out.nreject) memcpy(out.nreject, stage + o.nrej, 4 * n);
+        if (out.flags) memcpy(out.flags, stage + o.flags, 4 * n);
+    }
+    float tot = 0;
+    cudaEventElapsedTime(&tot, ctx->ev0, ctx->ev3);
+    ctx->stats.kernel_ms = tot; ctx->stats.total_ms = tot;
+    for (int b = 0; b < nbatch; ++b) {
+        ctx->stats.rays += ranges[b].count;
+        ctx->stats.steps_accepted += (int64_t)c[(size_t)b * 4 + 1]; ctx->stats.steps_rejected += (int64_t)c[(size_t)b * 4 + 2];
+        ctx->stats.flagged += (int64_t)c[(size_t)b * 4 + 3];
+    }
+    return GB200_OK;
 }
 
 static int render_common(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, const int32_t* pfs, int32_t npf,

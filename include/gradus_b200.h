@@ -214,6 +214,13 @@ int gb200_radiative_efficiency(int32_t metric_kind, const double* metric_params,
 int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic,
                 const gb200_range* range, gb200_endpoints* out);
 
+/* Many short ensembles at once (corona / lamp-post emissivity fans over an (a, h) grid,
+   src/corona/models/lamp-post.jl:89-100 called once per model).  Equivalent to `nbatch` gb200_trace calls, but every
+   ensemble is launched on its own stream of a pool and the host synchronises once, so 1000-ray ensembles overlap
+   instead of each paying a launch + copy round trip. */
+int gb200_trace_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* problems, const gb200_ic* ics,
+                      const gb200_range* ranges, gb200_endpoints* outs);
+
 /* rendergeodesics fused path (rendering.jl:28-54,89-107): trace + point
    function(s); writes `npf` images of `range->count` doubles each, image k at
    images[k], ray order (for the full range this is the (H,W) column-major image). */

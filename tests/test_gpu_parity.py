@@ -295,3 +295,25 @@ def test_invalid_calls_fail_loudly(ensemble):
     p.geometry_kind = 9
     rng = cabi.Range(0, 4, 1)
     assert lib.gb200_trace(ctx, C.byref(p), C.byref(ic), C.byref(rng), C.byref(out.c)) == cabi.ERR_UNSUPPORTED
+
+
+def test_batched_short_ensembles_match_individual_calls(ensemble):
+    """SURVEY 8f-1 / BASELINE configs[3]: lamp-post-like 1000-ray fans over a spin grid, one batched call."""
+    from gradus_b200 import tracegeodesics_batch
+
+    xs = [0.0, 10.0, 0.01, 0.0]
+    delta = np.radians(np.linspace(0.01, 179.99, 1000))
+    vs = np.stack([np.zeros_like(delta), -np.cos(delta), np.sin(delta) / 10.0, np.zeros_like(delta)], axis=1)
+    spins = [0.0, 0.3, 0.6, 0.9, 0.998]
+    cfgs = [tracing_configuration(gb.KerrMetric(1.0, a), xs, vs, gb.ThinDisc(0.0, 1000.0), 10000.0, callback=gb.domain_upper_hemisphere(),
+                                  ensemble=ensemble) for a in spins]
+    cfgs.append(common.c1(40, 40, ensemble=ensemble)[3])  # a structured-IC ensemble mixed into the same batch
+    batch = tracegeodesics_batch(cfgs)
+    st = ensemble.stats()
+    assert st.launches == len(cfgs) and st.rays == 5 * 1000 + 1600
+    for cfg, got in zip(cfgs, batch):
+        want = solve_tracing_problem(cfg)
+        assert np.array_equal(got.status, want.status)
+        assert np.array_equal(got.x, want.x) and np.array_equal(got.v, want.v) and np.array_equal(got.lambda_max, want.lambda_max)
+        assert np.array_equal(got.x_init, want.x_init) and np.array_equal(got.naccept, want.naccept)
+    assert sum(int(g.naccept.sum()) for g in batch) == st.steps_accepted

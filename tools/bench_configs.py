@@ -69,3 +69,11 @@ for k in range(nl):
 wall = time.perf_counter() - t0
 st = ens.stats()
 print(f"C4 lamp-post-like 1000-ray ensembles x {nl} spins: {wall / nl * 1e3:.2f} ms per ensemble wall (last kernel {st.kernel_ms:.3f} ms) -> {1000 * nl / wall / 1e6:.3f} Mrays/s; hits {int((gps.status == 2).sum())}")
+
+from gradus_b200 import tracegeodesics_batch
+from gradus_b200.api import tracing_configuration
+cfgs = [tracing_configuration(gb.KerrMetric(1.0, 0.998 * k / (nl - 1)), xs, vs, gb.ThinDisc(0.0, 1000.0), 10000.0, callback=gb.domain_upper_hemisphere(), ensemble=ens) for k in range(nl)]
+tracegeodesics_batch(cfgs)
+t0 = time.perf_counter(); out = tracegeodesics_batch(cfgs); wall = time.perf_counter() - t0
+st = ens.stats()
+print(f"C4 batched: {nl} ensembles x 1000 rays in one gb200_trace_batch call: {wall * 1e3:.2f} ms wall ({st.total_ms:.2f} ms device span) -> {1000 * nl / wall / 1e6:.3f} Mrays/s")
