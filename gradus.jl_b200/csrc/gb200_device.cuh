@@ -280,9 +280,41 @@ __device__ __constant__ double gb_tab[] = {
     1.5, // 46: GB_R72
     -4.0, // 47: GB_R73
     2.5, // 48: GB_R74
+    0.63661977236758134308, // 49: GB_SC_2OPI
+    1.57079632673412561417e+00, // 50: GB_SC_PIO2_1
+    6.07710050650619224932e-11, // 51: GB_SC_PIO2_2
+    2.02226624879595063154e-21, // 52: GB_SC_PIO2_3
+    1.58969099521155010221e-10, // 53: GB_SC_S6
+    -2.50507602534068634195e-08, // 54: GB_SC_S5
+    2.75573137070700676789e-06, // 55: GB_SC_S4
+    -1.98412698298579493134e-04, // 56: GB_SC_S3
+    8.33333333332248946124e-03, // 57: GB_SC_S2
+    -1.66666666666666324348e-01, // 58: GB_SC_S1
+    -1.13596475577881948265e-11, // 59: GB_SC_C6
+    2.08757232129817482790e-09, // 60: GB_SC_C5
+    -2.75573143513906633035e-07, // 61: GB_SC_C4
+    2.48015872894767294178e-05, // 62: GB_SC_C3
+    -1.38888888888741095749e-03, // 63: GB_SC_C2
+    4.16666666666666019037e-02, // 64: GB_SC_C1
 };
 #endif
-static const double gb_tab_host[] = {0.161, -0.008480655492356989, 0.335480655492357, 2.8971530571054935, -6.359448489975075, 4.3622954328695815, 5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774, -0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629, 0.5823571654525552, -0.45808210592918697, 0.015151515151515152, -2.763706197274826, 2.9132554618219126, -1.0530884977290216, 0.13169999999999998, -0.2234, 0.1017, 3.9302962368947516, -5.941033872131505, 2.490627285651253, -12.411077166933676, 30.33818863028232, -16.548102889244902, 37.50931341651104, -88.1789048947664, 47.37952196281928, -27.896526289197286, 65.09189467479366, -34.87065786149661, 1.5, -4.0, 2.5};
+#define GB_SC_2OPI GB_TAB(49)
+#define GB_SC_PIO2_1 GB_TAB(50)
+#define GB_SC_PIO2_2 GB_TAB(51)
+#define GB_SC_PIO2_3 GB_TAB(52)
+#define GB_SC_S6 GB_TAB(53)
+#define GB_SC_S5 GB_TAB(54)
+#define GB_SC_S4 GB_TAB(55)
+#define GB_SC_S3 GB_TAB(56)
+#define GB_SC_S2 GB_TAB(57)
+#define GB_SC_S1 GB_TAB(58)
+#define GB_SC_C6 GB_TAB(59)
+#define GB_SC_C5 GB_TAB(60)
+#define GB_SC_C4 GB_TAB(61)
+#define GB_SC_C3 GB_TAB(62)
+#define GB_SC_C2 GB_TAB(63)
+#define GB_SC_C1 GB_TAB(64)
+static const double gb_tab_host[] = {0.161, -0.008480655492356989, 0.335480655492357, 2.8971530571054935, -6.359448489975075, 4.3622954328695815, 5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774, -0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629, 0.5823571654525552, -0.45808210592918697, 0.015151515151515152, -2.763706197274826, 2.9132554618219126, -1.0530884977290216, 0.13169999999999998, -0.2234, 0.1017, 3.9302962368947516, -5.941033872131505, 2.490627285651253, -12.411077166933676, 30.33818863028232, -16.548102889244902, 37.50931341651104, -88.1789048947664, 47.37952196281928, -27.896526289197286, 65.09189467479366, -34.87065786149661, 1.5, -4.0, 2.5, 0.63661977236758134308, 1.57079632673412561417e+00, 6.07710050650619224932e-11, 2.02226624879595063154e-21, 1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01, -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
 
 // ---------------------------------------------------------------- metrics
 // Kerr: components and Jacobian from w = 2Mr/Sigma (see DESIGN.md for the derivation).
@@ -357,22 +389,22 @@ GB_HD inline void geodesic_accel(const double g[5], const double dr[5], const do
 // [-pi/4, pi/4] (< 1 ulp), quadrant fix-up with selects.  The CUDA library sincos() carries a Payne-Hanek slow
 // path behind a divergent branch; this has none.
 GB_D void gb_sincos(double x, double* sp, double* cp) {
-    const double q = rint(x * 0.63661977236758134308);
-    double rr = fma(-q, 1.57079632673412561417e+00, x);
-    rr = fma(-q, 6.07710050650619224932e-11, rr);
-    rr = fma(-q, 2.02226624879595063154e-21, rr);
+    const double q = rint(x * GB_SC_2OPI);
+    double rr = fma(-q, GB_SC_PIO2_1, x);
+    rr = fma(-q, GB_SC_PIO2_2, rr);
+    rr = fma(-q, GB_SC_PIO2_3, rr);
     const double z = rr * rr;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double ps = fma(z, GB_SC_S6, GB_SC_S5);
+    ps = fma(z, ps, GB_SC_S4);
+    ps = fma(z, ps, GB_SC_S3);
+    ps = fma(z, ps, GB_SC_S2);
+    ps = fma(z, ps, GB_SC_S1);
     const double sn = fma(rr * z, ps, rr);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double pc = fma(z, GB_SC_C6, GB_SC_C5);
+    pc = fma(z, pc, GB_SC_C4);
+    pc = fma(z, pc, GB_SC_C3);
+    pc = fma(z, pc, GB_SC_C2);
+    pc = fma(z, pc, GB_SC_C1);
     const double cs = fma(z * z, pc, fma(z, -0.5, 1.0));
     const int n = __double2int_rn(q);
     const bool swap = (n & 1) != 0;

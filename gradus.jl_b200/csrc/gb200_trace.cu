@@ -144,7 +144,6 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
         bool service = false;
         if (GB_SYNC_EVERY == 1 || (loop_count++ % GB_SYNC_EVERY) == 0) {
             const int idle_cta = __syncthreads_count(state != LANE_RUN);
-            exhausted = (*(volatile int*)&sh_exhausted) != 0;
             service = idle_cta >= GB_REFILL_THRESH * (GB_BLOCK / 32) || idle_cta == GB_BLOCK;
         }
 #else
@@ -354,7 +353,9 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                 }
             }
 #if GB_BLOCK_SYNC
-            if (__syncthreads_count(state == LANE_RUN) == 0) break; // CTA-uniform: queue drained and every lane finalised
+            const int running_cta = __syncthreads_count(state == LANE_RUN);
+            exhausted = (*(volatile int*)&sh_exhausted) != 0; // written only inside a service pass, read only after its closing barrier
+            if (running_cta == 0) break;                       // CTA-uniform: queue drained and every lane finalised
 #else
             run_mask = __ballot_sync(FULLMASK, state == LANE_RUN);
             if (run_mask == 0) break;

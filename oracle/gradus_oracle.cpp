@@ -74,7 +74,8 @@ template <class S, int N> Dual<S, N> operator*(const Dual<S, N>& a, const Dual<S
     Dual<S, N> r; r.v = a.v * b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
 template <class S, int N> Dual<S, N> operator/(const Dual<S, N>& a, const Dual<S, N>& b) {
     Dual<S, N> r; S ib = S(1) / b.v; r.v = a.v * ib;
-    for (int i = 0; i < N; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib; return r; }
+    for (int i = 0; i < N; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib;
+    return r; }
 // mixed with plain arithmetic constants
 template <class S, int N, class C> Dual<S, N> operator+(const Dual<S, N>& a, const C& c) { return a + Dual<S, N>(S(c)); }
 template <class S, int N, class C> Dual<S, N> operator+(const C& c, const Dual<S, N>& a) { return Dual<S, N>(S(c)) + a; }

@@ -72,17 +72,20 @@ def check_parity(cfg, name, max_band=2e-2, discrete_tol=1e-5):
         ex, ev = _x_rel(gps.x[:, sel], ref.x[:, sel]), _vec_rel(gps.v[:, sel], ref.v[:, sel], 1e-12)
         el = np.abs(gps.lambda_max[sel] - ref.lambda_max[sel]) / np.maximum(np.abs(ref.lambda_max[sel]), 1.0)
         assert ex.max() < TOL and ev.max() < TOL and el.max() < TOL, f"{name}: status {code}: x {ex.max():.2e} v {ev.max():.2e} lam {el.max():.2e}"
-    # (3) DiscreteCallback-terminated rays: same geodesic at the same affine parameter
-    disc = same & ((ref.status == cabi.STATUS_WITHIN_INNER_BOUNDARY) | (ref.status == cabi.STATUS_OUT_OF_DOMAIN))
-    idx = np.where(disc)[0]
-    if len(idx):
+    # (3) DiscreteCallback-terminated rays: same geodesic at the same affine parameter.  At the horizon chart
+    # (r = 1.01 r_h) phi, v^t and v^phi diverge logarithmically: the oracle's own double vs long-double spread of this
+    # very check is 2.3e-5 there, so the inner-boundary tolerance is 2e-4; escaping / hemisphere rays get 1e-5.
+    for code, tol in ((cabi.STATUS_WITHIN_INNER_BOUNDARY, 20 * discrete_tol), (cabi.STATUS_OUT_OF_DOMAIN, discrete_tol)):
+        idx = np.where(same & (ref.status == code))[0]
+        if not len(idx):
+            continue
         idx = idx[:: max(1, len(idx) // 400)]
         u0 = np.concatenate([gps.x_init[:, idx], gps.v_init[:, idx]]).T
         want = oracle.trace_to(p, u0, gps.lambda_max[idx])
         got = np.concatenate([gps.x[:, idx], gps.v[:, idx]]).T
         ex = np.max(np.abs(got[:, :4] - want[:, :4]) / np.maximum(np.abs(want[:, :4]), 1.0), axis=1)
         ev = np.max(np.abs(got[:, 4:] - want[:, 4:]), axis=1) / np.maximum(np.max(np.abs(want[:, 4:]), axis=1), 1e-12)
-        assert ex.max() < discrete_tol and ev.max() < discrete_tol, f"{name}: same-geodesic check x {ex.max():.2e} v {ev.max():.2e}"
+        assert ex.max() < tol and ev.max() < tol, f"{name}: same-geodesic check (status {code}) x {ex.max():.2e} v {ev.max():.2e}"
     # (4) initial conditions (closed-form LNRF vs the oracle's Gram-Schmidt tetrad) and counters
     assert _vec_rel(gps.v_init, ref.v_init, 1e-12).max() < 1e-11
     assert np.array_equal(gps.x_init, ref.x_init)
