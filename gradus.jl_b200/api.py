@@ -202,12 +202,14 @@ class EnsembleB200:
             raise ValueError("EnsembleB200 needs at least one device")
         self._ctx = {}
 
-    def ctx(self, device):
-        if device not in self._ctx:
+    def ctx(self, device, slot=0):
+        """Context for `device`; `slot` distinguishes several contexts on the same device (one per host thread)."""
+        key = (device, slot)
+        if key not in self._ctx:
             h = C.c_void_p()
             cabi.check(cabi.load().gb200_init(device, C.byref(h)))
-            self._ctx[device] = h
-        return self._ctx[device]
+            self._ctx[key] = h
+        return self._ctx[key]
 
     def close(self):
         for h in self._ctx.values():
@@ -421,19 +423,22 @@ def _shards(n, ndev):
 
 def _run_sharded(ensemble, n, fn):
     """Call fn(ctx, first, count, slot) for each device concurrently (ctypes drops the GIL)."""
-    shards = [(d, f, c) for d, (f, c) in zip(ensemble.devices, _shards(n, len(ensemble.devices))) if c > 0]
+    devs = ensemble.devices
+    shards = [(i, d, f, c) for i, (d, (f, c)) in enumerate(zip(devs, _shards(n, len(devs)))) if c > 0]
     errs = []
 
-    def work(slot, dev, first, count):
+    def work(i, dev, first, count):
         try:
-            fn(ensemble.ctx(dev), first, count, slot)
+            # a device listed twice gets two contexts: a context is used by one thread at a time
+            fn(ensemble.ctx(dev, devs[:i].count(dev)), first, count, i)
         except Exception as e:  # noqa: BLE001
             errs.append(e)
 
-    if len(shards) == 1:
-        work(0, *shards[0])
+    if len(shards) <= 1:
+        for sh in shards:
+            work(*sh)
     else:
-        ths = [threading.Thread(target=work, args=(s,) + sh) for s, sh in enumerate(shards)]
+        ths = [threading.Thread(target=work, args=sh) for sh in shards]
         [t.start() for t in ths]
         [t.join() for t in ths]
     if errs:

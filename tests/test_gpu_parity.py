@@ -320,3 +320,90 @@ def test_batched_short_ensembles_match_individual_calls(ensemble):
         assert np.array_equal(got.x, want.x) and np.array_equal(got.v, want.v) and np.array_equal(got.lambda_max, want.lambda_max)
         assert np.array_equal(got.x_init, want.x_init) and np.array_equal(got.naccept, want.naccept)
     assert sum(int(g.naccept.sum()) for g in batch) == st.steps_accepted
+
+
+def test_edge_cases(ensemble):
+    """Empty and single-ray ranges, strided sub-ranges, non-default tolerances and lambda domain, iteration cap."""
+    m, x, d, cfg = common.c1(32, 32, ensemble=ensemble)
+    p, ic = cfg.to_c()
+    lib = cabi.load()
+    ctx = ensemble.ctx(ensemble.devices[0])
+    out = cabi.EndpointArrays(1)
+    assert lib.gb200_trace(ctx, C.byref(p), C.byref(ic), C.byref(cabi.Range(5, 0, 1)), C.byref(out.c)) == cabi.OK  # empty: no launch
+    assert ensemble.stats().launches == 0 and ensemble.stats().rays == 0
+    full = solve_tracing_problem(cfg)
+    for first, count, stride in [(777, 1, 1), (3, 100, 7), (1023, 1, 1), (0, 1024, 1)]:
+        sub = cabi.EndpointArrays(count)
+        cabi.check(lib.gb200_trace(ctx, C.byref(p), C.byref(ic), C.byref(cabi.Range(first, count, stride)), C.byref(sub.c)), ctx)
+        idx = first + stride * np.arange(count)
+        assert np.array_equal(sub.status, full.status[idx]) and np.array_equal(sub.x, full.x[:, idx]) and np.array_equal(sub.v, full.v[:, idx])
+    # looser and tighter tolerances, shifted affine domain: still matches the oracle
+    for tol in (1e-6, 1e-11):
+        c2 = common.render_config(m, x, d, (5.0, 2005.0), 24, 24, ensemble=ensemble, abstol=tol, reltol=tol)
+        p2, ic2 = c2.to_c()
+        ref = oracle.trace(p2, ic2)
+        got = solve_tracing_problem(c2)
+        agree = got.status == ref.status
+        assert agree.mean() > 0.99
+        hit = agree & (ref.status == cabi.STATUS_INTERSECTED)
+        assert _x_rel(got.x[:, hit], ref.x[:, hit]).max() < max(1e-6, 300 * tol)
+        assert got.lambda_max.min() > 5.0 and np.all(got.lambda_max[ref.status == cabi.STATUS_NO_STATUS] == 2005.0)
+    # iteration cap: the ray keeps NoStatus and raises the MAXITERS flag (SciML retcode MaxIters is invisible in GeodesicPoint)
+    c3 = common.render_config(m, x, d, 2000.0, 8, 8, ensemble=ensemble, maxiters=20)
+    got = solve_tracing_problem(c3)
+    assert np.all(got.status == cabi.STATUS_NO_STATUS) and np.all(got.flags == cabi.FLAG_MAXITERS) and np.all(got.naccept + got.nreject == 20)
+    assert ensemble.stats().flagged == 64
+
+
+def test_fast32_controller_and_massive_geodesics(ensemble):
+    m, x, d, _ = common.c1(8, 8, ensemble=ensemble)
+    # Float32 controller power (FastPower.jl-style): same classes and hits as the oracle's fast32 mode
+    cfg = common.render_config(m, x, d, 2000.0, 48, 48, ensemble=ensemble, pow_mode=cabi.POW_FAST32)
+    p, ic = cfg.to_c()
+    ref = oracle.trace(p, ic)
+    got = solve_tracing_problem(cfg)
+    agree = got.status == ref.status
+    assert agree.mean() > 0.995
+    hit = agree & (ref.status == cabi.STATUS_INTERSECTED)
+    assert _x_rel(got.x[:, hit], ref.x[:, hit]).max() < 1e-6
+    # massive particles (mu = 1, explicit ICs): the plunging-orbit set-up of orbit-solving.jl:137-167 uses this path
+    mk = gb.KerrMetric(1.0, 0.5)
+    vs = np.array([[0.0, -0.05 * k, 0.0, 0.02] for k in range(1, 33)])
+    cfg = tracing_configuration(mk, [0.0, 8.0, math.pi / 2 - 0.05, 0.0], vs, 5.0, mu=1.0, ensemble=ensemble)
+    p, ic = cfg.to_c()
+    ref = oracle.trace(p, ic)
+    got = solve_tracing_problem(cfg)
+    assert np.array_equal(got.status, ref.status)
+    assert np.all(got.v_init[0] > 0) and _vec_rel(got.v_init, ref.v_init, 1e-12).max() < 1e-11
+    done = ref.status == cabi.STATUS_NO_STATUS
+    assert done.sum() >= 16 and _x_rel(got.x[:, done], ref.x[:, done]).max() < 1e-6
+    # timelike normalisation g(v, v) = -mu^2 is kept along the orbit
+    r_, th_ = got.x[1, done], got.x[2, done]
+    S = r_**2 + 0.25 * np.cos(th_) ** 2
+    D = r_**2 - 2 * r_ + 0.25
+    s2 = np.sin(th_) ** 2
+    vv = got.v[:, done]
+    norm = (-(1 - 2 * r_ / S) * vv[0] ** 2 + S / D * vv[1] ** 2 + S * vv[2] ** 2 + s2 * (r_**2 + 0.25 + 2 * r_ * 0.25 * s2 / S) * vv[3] ** 2
+            - 2 * (2 * r_ * 0.5 * s2 / S) * vv[0] * vv[3])
+    assert np.abs(norm + 1.0).max() < 1e-6
+
+
+def test_in_process_sharding_over_contexts(ensemble):
+    """EnsembleB200 with several contexts (here: the same GPU listed twice) = the Julia ext's multi-GPU path."""
+    ens2 = gb.EnsembleB200(devices=(ensemble.devices[0], ensemble.devices[0]))
+    try:
+        m, x, d, plane, cfg1 = common.c3(48, 48, ensemble=ensemble)
+        _, _, _, _, cfg2 = common.c3(48, 48, ensemble=ens2)
+        a, b = solve_tracing_problem(cfg1), solve_tracing_problem(cfg2)
+        assert np.array_equal(a.status, b.status) and np.array_equal(a.x, b.x) and np.array_equal(a.naccept, b.naccept)
+        bins = np.linspace(0.1, 1.5, 60)
+        _, f1 = gb.lineprofile(bins, gb.PowerLawEmissivity(3.0), m, x, d, gb.BinningMethod(), plane=plane, lambda_max=2000.0, ensemble=ensemble)
+        _, f2 = gb.lineprofile(bins, gb.PowerLawEmissivity(3.0), m, x, d, gb.BinningMethod(), plane=plane, lambda_max=2000.0, ensemble=ens2)
+        assert np.abs(f1 - f2).max() < 1e-12  # invariant to the device count up to summation order
+        pf = gb.ConstPointFunctions.redshift() @ gb.ConstPointFunctions.filter_intersected()
+        mm, xx, dd, _ = common.c1(8, 8)
+        _, _, i1 = gb.rendergeodesics(mm, xx, dd, 2000.0, pf=pf, image_width=33, image_height=17, ensemble=ensemble)
+        _, _, i2 = gb.rendergeodesics(mm, xx, dd, 2000.0, pf=pf, image_width=33, image_height=17, ensemble=ens2)
+        assert i1.shape == (17, 33) and np.array_equal(i1, i2, equal_nan=True)
+    finally:
+        ens2.close()
