@@ -35,6 +35,7 @@ from .api import (  # noqa: F401
     domain_upper_hemisphere,
     impact_axes,
     inner_radius,
+    interpolate_plunging_velocities,
     isco,
     lineprofile,
     rendergeodesics,

@@ -80,7 +80,7 @@ class Stats(C.Structure):
 #: every symbol include/gradus_b200.h declares
 EXPORTED_SYMBOLS = (
     "gb200_version", "gb200_init", "gb200_destroy", "gb200_last_error", "gb200_get_stats", "gb200_validate",
-    "gb200_isco", "gb200_radiative_efficiency", "gb200_trace", "gb200_trace_batch", "gb200_render", "gb200_lineprofile",
+    "gb200_isco", "gb200_radiative_efficiency", "gb200_trace", "gb200_trace_batch", "gb200_trace_path", "gb200_build_plunging_table", "gb200_render", "gb200_lineprofile",
     "gb200_render_device", "gb200_lineprofile_device", "gb200_fp64_peak",
 )
 
@@ -159,6 +159,8 @@ def load():
     lib.gb200_radiative_efficiency.argtypes = [C.c_int32, _dp, _dp]
     lib.gb200_trace.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range), C.POINTER(Endpoints)]
     lib.gb200_trace_batch.argtypes = [vp, C.c_int32, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range), C.POINTER(Endpoints)]
+    lib.gb200_trace_path.argtypes = [vp, C.POINTER(Problem), _dp, C.c_int32, _dp, _dp, _ip, _ip]
+    lib.gb200_build_plunging_table.argtypes = [vp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, _dp, _ip]
     lib.gb200_render.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range), _ip, C.c_int32,
                                  C.POINTER(PlungingTable), C.POINTER(_dp)]
     lib.gb200_lineprofile.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range), C.POINTER(Emissivity),

@@ -496,6 +496,53 @@ def tracegeodesics(m, position, velocity, *args, **kwargs) -> GeodesicPoints:
     return solve_tracing_problem(config)
 
 
+# --------------------------------------------------------------------------- plunging region (non-Kerr redshift)
+class PlungingInterpolation:
+    """`PlungingInterpolation` (src/orbits/orbit-solving.jl:99-135) as data: r (ascending) -> (u^t, u^r, u^phi)."""
+
+    def __init__(self, r, ut, ur, uphi):
+        self.r, self.ut, self.ur, self.uphi = (np.ascontiguousarray(a, np.float64) for a in (r, ut, ur, uphi))
+        self.c = cabi.PlungingTable(len(self.r), cabi.dptr(self.r), cabi.dptr(self.ut), cabi.dptr(self.ur), cabi.dptr(self.uphi))
+
+    def __call__(self, r):
+        x = np.clip(r, self.r[0], self.r[-1])  # _enforce_interpolation_bounds
+        return np.interp(x, self.r, self.ut), np.interp(x, self.r, self.ur), np.interp(x, self.r, self.uphi)
+
+
+_PLUNGING_CACHE = {}
+
+
+def interpolate_plunging_velocities(m, ensemble=None, cap=1 << 17) -> PlungingInterpolation:
+    """`interpolate_plunging_velocities(m)` (orbit-solving.jl:137-167): the massive plunging geodesic from the ISCO is
+    integrated on the device (gb200_trace_path) and tabulated."""
+    _check_metric(m)
+    key = (type(m).__name__, m.params())
+    if key in _PLUNGING_CACHE:
+        return _PLUNGING_CACHE[key]
+    ens = ensemble or EnsembleB200()
+    ctx = ens.ctx(ens.devices[0])
+    arrs = [np.zeros(cap) for _ in range(4)]
+    n = C.c_int32()
+    cabi.check(cabi.load().gb200_build_plunging_table(ctx, m.kind, _metric_params_array(m), cap, *[cabi.dptr(a) for a in arrs], C.byref(n)), ctx)
+    tab = PlungingInterpolation(*[a[: n.value] for a in arrs])
+    _PLUNGING_CACHE[key] = tab
+    return tab
+
+
+def _auto_plunging(m, geometry, ensemble, want_redshift, plunging):
+    """The reference's `redshift(m::AbstractMetric, u)` builds the plunging interpolation for every non-Kerr metric
+    (const-point-functions.jl:79); here it is only needed when the disc reaches inside the ISCO."""
+    if plunging is not None or not want_redshift or isinstance(m, KerrMetric):
+        return plunging
+    inner = getattr(geometry, "inner_radius", 0.0)
+    try:
+        if inner >= isco(m):
+            return None
+    except cabi.GradusB200Error:
+        return None  # no ISCO (e.g. near-naked-singularity JP): redshift is undefined inside, NaN like a missing table
+    return interpolate_plunging_velocities(m, ensemble)
+
+
 # --------------------------------------------------------------------------- point functions
 @dataclass(frozen=True)
 class PointFunction:
@@ -573,7 +620,7 @@ def _pop_alias(kwargs, names, default):
     return default
 
 
-def rendergeodesics(m, position, *args, pf=None, image_width=375, image_height=250, ensemble=None, **kwargs):
+def rendergeodesics(m, position, *args, pf=None, image_width=375, image_height=250, ensemble=None, plunging=None, **kwargs):
     """`rendergeodesics(m, x, [d], λ_max; pf, image_width, image_height, αlims, βlims, ensemble, ...)`
     (src/rendering/rendering.jl:28-54).  Returns (α, β, image) with image of shape (H, W).
 
@@ -589,11 +636,13 @@ def rendergeodesics(m, position, *args, pf=None, image_width=375, image_height=2
     n = ic.n
     images = np.zeros((len(pfs), n))
     lib = cabi.load()
+    plunging = _auto_plunging(m, config.geometry, config.ensemble, cabi.PF_REDSHIFT in kinds, plunging)
+    pl_ref = C.byref(plunging.c) if plunging is not None else None
 
     def fn(ctx, first, count, slot):
         ptrs = (cabi._dp * len(pfs))(*[C.cast(images[k].ctypes.data + 8 * first, cabi._dp) for k in range(len(pfs))])
         rng = cabi.Range(first, count, 1)
-        cabi.check(lib.gb200_render(ctx, C.byref(p), C.byref(ic), C.byref(rng), cabi.iptr(kinds), len(pfs), None, ptrs), ctx)
+        cabi.check(lib.gb200_render(ctx, C.byref(p), C.byref(ic), C.byref(rng), cabi.iptr(kinds), len(pfs), pl_ref, ptrs), ctx)
 
     _run_sharded(config.ensemble, n, fn)
     alpha, beta = impact_axes(image_width, image_height, alpha_lims, beta_lims)
@@ -616,7 +665,7 @@ class TabulatedEmissivity:
 
 
 def lineprofile(bins, emissivity, m, position, d, method=None, *, lambda_max=None, min_re=None, max_re=50.0,
-                plane=None, callback="default", ensemble=None, bin_right_closed=True, **solver_args):
+                plane=None, callback="default", ensemble=None, bin_right_closed=True, plunging=None, **solver_args):
     """`lineprofile(bins, ε, m, u, d, ::BinningMethod; λ_max, minrₑ, maxrₑ, plane, callback, ...)`
     (src/line-profiles.jl:152-198).  Returns (bins, flux ./ sum(flux))."""
     if method is not None and not isinstance(method, BinningMethod):
@@ -650,12 +699,14 @@ def lineprofile(bins, emissivity, m, position, d, method=None, *, lambda_max=Non
     else:
         raise ValueError("emissivity must be PowerLawEmissivity or TabulatedEmissivity (a closure cannot cross the C ABI)")
     opts = cabi.LineProfileOpts(float(min_re), float(max_re), 0, 1 if bin_right_closed else 0)
+    plunging = _auto_plunging(m, d, config.ensemble, min_re < (isco(m) if not isinstance(m, KerrMetric) else 0.0), plunging)
+    pl_ref = C.byref(plunging.c) if plunging is not None else None
     ndev = len(config.ensemble.devices)
     partial = np.zeros((ndev, len(bins)))
 
     def fn(ctx, first, count, slot):
         rng = cabi.Range(first, count, 1)
-        cabi.check(lib.gb200_lineprofile(ctx, C.byref(p), C.byref(ic), C.byref(rng), C.byref(emis), None,
+        cabi.check(lib.gb200_lineprofile(ctx, C.byref(p), C.byref(ic), C.byref(rng), C.byref(emis), pl_ref,
                                          cabi.dptr(bins), len(bins), C.byref(opts), cabi.dptr(partial[slot])), ctx)
 
     _run_sharded(config.ensemble, n, fn)

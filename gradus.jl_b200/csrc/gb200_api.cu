@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -552,6 +553,88 @@ int gb200_trace_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* probl
         ctx->stats.steps_accepted += (int64_t)c[(size_t)b * 4 + 1]; ctx->stats.steps_rejected += (int64_t)c[(size_t)b * 4 + 2];
         ctx->stats.flagged += (int64_t)c[(size_t)b * 4 + 3];
     }
+    return GB200_OK;
+}
+
+int gb200_trace_path(gb200_ctx* ctx, const gb200_problem* p, const double* u0, int32_t cap, double* lambda, double* u,
+                     int32_t* nrows, int32_t* status) {
+    if (!ctx) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null context");
+    if (!p || !u0 || cap < 1 || !lambda || !u || !nrows || !status) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad path arguments");
+    gb200_ic ic{};
+    ic.kind = GB200_IC_EXPLICIT; ic.n = 1;
+    for (int k = 0; k < 4; ++k) { ic.x[k] = u0 + k; ic.v[k] = u0 + 4 + k; }
+    int rc = validate(ctx, p, &ic); if (rc) return rc;
+    CU(ctx, cudaSetDevice(ctx->device));
+    ctx->stats = gb200_stats{};
+    ctx->cur = ctx->stream;
+    gb200_range rg{0, 1, 1};
+    GbParams P;
+    fill_params(p, &ic, &rg, P);
+    void *d_u0, *d_lam, *d_u, *d_meta;
+    rc = pool_get(ctx, SL_EX0, 64, &d_u0); if (rc) return rc;
+    rc = pool_get(ctx, SL_LAMBDA, sizeof(double) * (size_t)cap, &d_lam); if (rc) return rc;
+    rc = pool_get(ctx, SL_X0, sizeof(double) * 8 * (size_t)cap, &d_u); if (rc) return rc;
+    rc = pool_get(ctx, SL_SCRATCH, 64, &d_meta); if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(d_u0, u0, 64, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, gb200_launch_path(P, (const double*)d_u0, cap, (double*)d_lam, (double*)d_u, (int*)d_meta, ctx->stream));
+    ctx->stats.launches = 1;
+    int meta[2] = {0, 0};
+    CU(ctx, cudaMemcpyAsync(meta, d_meta, sizeof meta, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    const int nw = meta[0] < cap ? meta[0] : cap;
+    CU(ctx, cudaMemcpy(lambda, d_lam, sizeof(double) * (size_t)nw, cudaMemcpyDeviceToHost));
+    CU(ctx, cudaMemcpy(u, d_u, sizeof(double) * 8 * (size_t)nw, cudaMemcpyDeviceToHost));
+    *nrows = meta[0];
+    *status = meta[1];
+    return GB200_OK;
+}
+
+int gb200_build_plunging_table(gb200_ctx* ctx, int32_t metric_kind, const double* mp, int32_t cap, double* r, double* ut, double* ur,
+                         double* uphi, int32_t* n) {
+    if (!ctx) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null context");
+    if (!mp || cap < 2 || !r || !ut || !ur || !uphi || !n) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad plunging-table arguments");
+    double risco = 0;
+    int rc = gb200_isco(metric_kind, mp, &risco);
+    if (rc) return fail(ctx, rc, "no ISCO for this metric");
+    // CircularOrbits.plunging_fourvelocity at the ISCO (circular-orbits.jl:129-150)
+    double g[5], dr[5], dth[5];
+    if (metric_kind == GB200_METRIC_KERR) kerr_metric_jacobian<double>(mp[0], mp[1], risco, 1.0, 0.0, g, dr, dth);
+    else jp_metric_jacobian<double>(mp[0], mp[1], mp[2], risco, 1.0, 0.0, g, dr, dth);
+    const double D = g[0] * g[3] - g[4] * g[4];
+    const double gitt = g[3] / D, giphph = g[0] / D, gitph = -g[4] / D;
+    const double Om = -(dr[4] - std::sqrt(dr[4] * dr[4] - dr[0] * dr[3])) / dr[3];
+    const double A = -(Om * gitt - gitph), B = (Om * gitph - giphph);
+    const double denom = B * B * gitt + 2.0 * A * B * gitph + A * A * giphph;
+    const double dd = -(denom > 0 ? 1.0 : -1.0) * std::sqrt(1.0 / std::fabs(denom));
+    const double ut_ = B * dd, uph_ = A * dd; // covariant u_t, u_phi
+    const double E = -ut_, L = uph_;
+    const double vt = gitt * ut_ + gitph * uph_, vph = gitph * ut_ + giphph * uph_;
+    const double nom = gitt * E * E - 2.0 * gitph * E * L + giphph * L * L + 1.0;
+    const double vr = -std::sqrt(std::fabs(nom / (-g[1])));
+    gb200_problem p{};
+    p.metric_kind = metric_kind;
+    for (int k = 0; k < 4; ++k) p.metric_params[k] = (k < 3) ? mp[k] : 0.0;
+    p.mu = 1.0; p.abstol = 1e-9; p.reltol = 1e-9; p.lambda_min = 0.0; p.lambda_max = 50000.0; p.gtol = 1e-2;
+    const double rh = mp[0] + std::sqrt(mp[0] * mp[0] - mp[1] * mp[1]);
+    p.chart_inner = rh * 1.000001; p.chart_outer = 12000.0;
+    const double u0[8] = {0.0, risco - 1e-8, M_PI / 2, 0.0, vt, vr, 0.0, vph};
+    const int pathcap = 1 << 20;
+    std::vector<double> lam((size_t)pathcap), u((size_t)pathcap * 8);
+    int32_t rows = 0, status = 0;
+    rc = gb200_trace_path(ctx, &p, u0, pathcap, lam.data(), u.data(), &rows, &status);
+    if (rc) return rc;
+    if (rows > pathcap) return fail(ctx, GB200_ERR_NOMEM, "plunging geodesic needs %d rows (> %d)", rows, pathcap);
+    // PlungingInterpolation (orbit-solving.jl:99-135): sort by r, drop the innermost sample
+    std::vector<int> idx((size_t)rows);
+    for (int i = 0; i < rows; ++i) idx[(size_t)i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a_, int b_) { return u[(size_t)a_ * 8 + 1] < u[(size_t)b_ * 8 + 1]; });
+    const int nt = rows - 1;
+    if (nt > cap) return fail(ctx, GB200_ERR_NOMEM, "plunging table needs %d entries (cap %d)", nt, cap);
+    for (int i = 0; i < nt; ++i) {
+        const size_t s = (size_t)idx[(size_t)i + 1] * 8;
+        r[i] = u[s + 1]; ut[i] = u[s + 4]; ur[i] = u[s + 5]; uphi[i] = u[s + 7];
+    }
+    *n = nt;
     return GB200_OK;
 }
 

@@ -210,6 +210,20 @@ int gb200_isco(int32_t metric_kind, const double* metric_params, double* out);
 /* 1 - E_isco, i.e. the default eta of ShakuraSunyaev (shakura-sunyaev.jl:41-50). */
 int gb200_radiative_efficiency(int32_t metric_kind, const double* metric_params, double* out);
 
+/* One geodesic with EVERY accepted step recorded (the `save_on = true` single-ray form of tracegeodesics,
+   src/tracing/tracing.jl:66-108): u0 = (x[4], v[4]) with v^t re-constrained for mass p->mu; no geometry is used.
+   Writes at most `cap` rows: lambda[k], u[8*k .. 8*k+7] (row 0 is the initial state); *nrows receives the number of
+   rows the solve produced (may exceed cap), *status the final StatusCodes value.  One GPU thread; a set-up tool. */
+int gb200_trace_path(gb200_ctx* ctx, const gb200_problem* p, const double* u0, int32_t cap,
+                     double* lambda, double* u, int32_t* nrows, int32_t* status);
+
+/* Plunging-region four-velocity table for the redshift of non-Kerr metrics inside the ISCO
+   (interpolate_plunging_velocities, src/orbits/orbit-solving.jl:99-167): a massive geodesic released at
+   r_isco - 1e-8 with CircularOrbits.plunging_fourvelocity, traced to 1.000001 r_h on the device, sorted by radius
+   with the innermost sample dropped.  Caller provides 4 arrays of `cap` doubles; *n receives the table length. */
+int gb200_build_plunging_table(gb200_ctx* ctx, int32_t metric_kind, const double* metric_params, int32_t cap,
+                         double* r, double* ut, double* ur, double* uphi, int32_t* n);
+
 /* ensemble_solve_tracing_problem(::EnsembleB200, ...) -> endpoints (tracing.jl:151-196). */
 int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic,
                 const gb200_range* range, gb200_endpoints* out);

@@ -407,3 +407,71 @@ def test_in_process_sharding_over_contexts(ensemble):
         assert i1.shape == (17, 33) and np.array_equal(i1, i2, equal_nan=True)
     finally:
         ens2.close()
+
+
+def _oracle_plunging_table(kind, mp):
+    """interpolate_plunging_velocities (src/orbits/orbit-solving.jl:137-167) restated with the oracle's pieces."""
+    risco = oracle.isco(kind, mp)
+    g, dr, _ = oracle.metric(kind, mp, risco, math.pi / 2)
+    D = g[0] * g[3] - g[4] ** 2
+    gitt, giphph, gitph = g[3] / D, g[0] / D, -g[4] / D
+    v = oracle.circular_fourvelocity(kind, mp, risco)
+    E = oracle.circular_energy(kind, mp, risco)
+    ut = -E
+    uph = (v[3] - gitph * ut) / giphph  # v^phi = g^tphi u_t + g^phiphi u_phi
+    nom = gitt * E * E - 2 * gitph * E * uph + giphph * uph * uph + 1
+    vr = -math.sqrt(abs(nom / (-g[1])))
+    p = cabi.Problem()
+    p.metric_kind = kind
+    p.metric_params[:] = list(mp) + [0.0] * (4 - len(mp))
+    p.mu, p.abstol, p.reltol, p.lambda_min, p.lambda_max, p.gtol = 1.0, 1e-9, 1e-9, 0.0, 50000.0, 1e-2
+    p.chart_inner = (mp[0] + math.sqrt(mp[0] ** 2 - mp[1] ** 2)) * 1.000001
+    p.chart_outer = 12000.0
+    u0 = np.array([0.0, risco - 1e-8, math.pi / 2, 0.0, v[0], vr, 0.0, v[3]])
+    g0, _, _ = oracle.metric(kind, mp, u0[1], u0[2])
+    disc = -g0[0] * g0[1] * vr**2 - g0[0] - (g0[0] * g0[3] - g0[4] ** 2) * v[3] ** 2  # constrain_time, mu = 1
+    u0[4] = -(g0[4] * v[3] + math.sqrt(disc)) / g0[0]
+    t, dt, ee, u = oracle.trace_path(p, u0, cap=1 << 20)
+    u = np.vstack([u0, u])
+    order = np.argsort(u[:, 1], kind="stable")[1:]
+    return u[order, 1], u[order, 4], u[order, 5], u[order, 7]
+
+
+def test_plunging_table_and_redshift_inside_isco(ensemble):
+    """Non-Kerr redshift inside the ISCO (src/redshift.jl:246-276): table built on the device vs the oracle's."""
+    m = gb.JohannsenPsaltisMetric(1.0, 0.6, 2.0)
+    mp = (1.0, 0.6, 2.0)
+    tab = gb.interpolate_plunging_velocities(m, ensemble)
+    r_o, ut_o, ur_o, uph_o = _oracle_plunging_table(cabi.METRIC_JP, mp)
+    risco = gb.isco(m)
+    assert tab.r[0] == pytest.approx(r_o[0], rel=2e-2) and tab.r[-1] == pytest.approx(risco, abs=1e-6)
+    # Two correct integrations sample the plunge at different radii, and the reference interpolates LINEARLY between
+    # samples: near the horizon (u^t ~ 9, steep, sparsely sampled) that alone is worth ~3e-3 (u^r -> 0 at the ISCO inflates its relative error there).
+    rr = np.linspace(max(tab.r[0], r_o[0]) * 1.001, risco * 0.9999, 200)
+    for got, want in zip(tab(rr), (np.interp(rr, r_o, ut_o), np.interp(rr, r_o, ur_o), np.interp(rr, r_o, uph_o))):
+        rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-3)
+        assert rel.max() < 1e-2 and np.median(rel) < 1e-4
+    # Kerr limit of the machinery: the table reproduces Cunningham's analytic plunging flow (src/redshift.jl:93-164) to table accuracy
+    mk = gb.JohannsenPsaltisMetric(1.0, 0.6, 0.0)
+    tk = gb.interpolate_plunging_velocities(mk, ensemble)
+    rk = np.linspace(tk.r[0] * 1.05, gb.isco(mk) * 0.98, 50)
+    rms = gb.isco(mk)
+    ur_analytic = -np.sqrt(2.0 / (3.0 * rms)) * (rms / rk - 1.0) ** 1.5
+    assert np.max(np.abs(tk(rk)[1] - ur_analytic)) < 2e-4
+    # end to end: JP disc reaching inside the ISCO, redshift image vs oracle with the oracle's own table
+    x = [0.0, 1000.0, math.radians(60.0), 0.0]
+    d = gb.ThinDisc(0.0, 30.0)
+    pf = gb.ConstPointFunctions.redshift(m, x) @ gb.ConstPointFunctions.filter_intersected()
+    _, _, img = gb.rendergeodesics(m, x, d, 2000.0, pf=pf, image_width=64, image_height=64, αlims=(-30, 30), βlims=(-20, 20), ensemble=ensemble)
+    cfg = common.render_config(m, x, d, 2000.0, 64, 64, (-30, 30), (-20, 20), ensemble=ensemble)
+    p, ic = cfg.to_c()
+    otab = cabi.PlungingTable(len(r_o), cabi.dptr(np.ascontiguousarray(r_o)), cabi.dptr(np.ascontiguousarray(ut_o)),
+                              cabi.dptr(np.ascontiguousarray(ur_o)), cabi.dptr(np.ascontiguousarray(uph_o)))
+    want, ep = oracle.render(p, ic, [cabi.PF_REDSHIFT, cabi.PF_DISC_RADIUS], plunging=otab, endpoints=True)
+    want_g = want[0].reshape(64, 64).T
+    rho = want[1].reshape(64, 64).T
+    both = ~np.isnan(img) & ~np.isnan(want_g)
+    inside = both & (rho < risco)
+    assert inside.sum() > 20 and (both & ~inside).sum() > 500
+    assert np.abs(img[both & ~inside] - want_g[both & ~inside]).max() < 1e-6
+    assert np.abs(img[inside] - want_g[inside]).max() < 2e-3  # two independently integrated tables, linearly interpolated
