@@ -182,6 +182,7 @@ def run_ours(args, rank, world, local):
     clocks = sampler.stop() if rank == 0 else None
     ms_local = sum(a.elapsed_time(b) for a, b in evs) / args.steps
     ms = gd.max_over_ranks(ms_local, dev)
+    ms_ranks = gd.gather_floats(ms_local, dev)
     total_rays = gd.sum_over_ranks(float(n_local), dev)
     total_attempts = gd.sum_over_ranks(float(attempts), dev)
     value = total_rays / (ms * 1e-3)
@@ -262,6 +263,7 @@ def run_ours(args, rank, world, local):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,
+        "ms_per_step_per_rank": ms_ranks,
         "total_rays_per_step": total_rays, "step_attempts_per_step": total_attempts, "image_checksum": checksum,
     }
     if lp is not None:

@@ -71,3 +71,13 @@ def sum_over_ranks(value: float, device=None) -> float:
 def barrier():
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
+
+
+def gather_floats(value: float, device=None):
+    """List of `value` from every rank (on every rank)."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return [value]
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(o.item()) for o in out]
