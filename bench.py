@@ -7,7 +7,7 @@
 A "step" is one full render of the workload: Kerr a=0.998, observer r=1000 theta=60deg, ThinDisc(0,50),
 2048 x 2048 image plane per GPU, two fused point functions (redshift + disc radius), Tsit5 abstol=reltol=1e-9
 (BASELINE.json configs[1]).  Rays shard across ranks with no data-path collective (weak scaling: the
-image is 2048 x (2048*N) over the same field of view and rank r integrates rays r, r+N, ...).
+image is 2048 x (2048*N) over the same field of view and rank r integrates every N-th strip of 4 image columns).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -123,7 +123,7 @@ def run_reference(args, rank, world):
 def workload_config(world, w, h):
     return {"workload": f"C2: KerrMetric a=0.998, observer r=1000 theta=60deg, ThinDisc(0,50), {w}x{h} image plane "
                         f"({W_IMG_PER_GPU}x{H_IMG} per GPU), redshift + disc-radius point functions, Tsit5 abstol=reltol=1e-9, lambda_max=2000",
-            "rays_per_gpu": W_IMG_PER_GPU * H_IMG, "parallelism": f"ray-sharded x{world} (interleaved, no collective)",
+            "rays_per_gpu": W_IMG_PER_GPU * H_IMG, "parallelism": f"ray-sharded x{world} (strips of 4 image columns interleaved over ranks, no collective)",
             "l2": "flushed between timed steps (256 MiB write); the kernel reads no input arrays"}
 
 
@@ -143,7 +143,7 @@ def run_ours(args, rank, world, local):
     ctx = ens.ctx(local)
     cfg, w, h = build_workload(world, ensemble=ens)
     p, ic = cfg.to_c()
-    rng = gd.interleaved_range(ic.n, rank, world)
+    rng = gd.strip_interleaved_range(ic, rank, world)
     n_local = rng.count
     pfs = np.array([cabi.PF_REDSHIFT, cabi.PF_DISC_RADIUS], np.int32)
     stream = torch.cuda.Stream(device=dev)  # explicit non-default stream: the library launches on it, the events time it
@@ -288,7 +288,7 @@ def run_lineprofile(args, rank, world, local, ens, dev, stream, sptr):
     plane = gb.PolarPlane(gb.GeometricGrid(), Nr=args.lp_n, Ntheta=args.lp_n * world, r_min=1.0, r_max=250.0)
     cfg = tracing_configuration(m, x, plane, gb.ThinDisc(0.0, 400.0), (0.0, 2000.0), callback=gb.domain_upper_hemisphere(), ensemble=ens)
     p, ic = cfg.to_c()
-    rng = gd.interleaved_range(ic.n, rank, world)
+    rng = gd.strip_interleaved_range(ic, rank, world)
     bins = np.ascontiguousarray(np.linspace(0.1, 1.5, 180))
     emis = cabi.Emissivity(cabi.EMISSIVITY_POWERLAW, 0, 3.0, None, None)
     opts = cabi.LineProfileOpts(gb.isco(m), 50.0, 0, 1)

@@ -48,7 +48,17 @@ class IC(C.Structure):
 
 
 class Range(C.Structure):
-    _fields_ = [("first", C.c_int64), ("count", C.c_int64), ("stride", C.c_int64)]
+    """Slot n holds ray first + (n // block) * stride * block + n % block (include/gradus_b200.h)."""
+
+    _fields_ = [("first", C.c_int64), ("count", C.c_int64), ("stride", C.c_int64), ("block", C.c_int64)]
+
+    def __init__(self, first=0, count=0, stride=1, block=1):
+        super().__init__(first, count, stride, block)
+
+    def indices(self):
+        n = np.arange(self.count, dtype=np.int64)
+        b = max(self.block, 1)
+        return self.first + (n // b) * (self.stride * b) + n % b
 
 
 class Endpoints(C.Structure):

@@ -156,8 +156,13 @@ static int validate(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic) 
 
 static int validate_range(gb200_ctx* ctx, const gb200_ic* ic, const gb200_range* rg) {
     if (!rg) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null range");
-    if (rg->count < 0 || rg->first < 0 || rg->stride < 1) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad range");
-    if (rg->count > 0 && rg->first + (rg->count - 1) * rg->stride >= ic->n) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "range exceeds the %lld rays of the IC", (long long)ic->n);
+    if (rg->count < 0 || rg->first < 0 || rg->stride < 1 || rg->block < 0) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad range");
+    const int64_t blk = rg->block > 0 ? rg->block : 1;
+    if (rg->count > 0) {
+        const int64_t nlast = rg->count - 1;
+        const int64_t last = rg->first + (nlast / blk) * (rg->stride * blk) + nlast % blk;
+        if (last >= ic->n) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "range exceeds the %lld rays of the IC", (long long)ic->n);
+    }
     return GB200_OK;
 }
 
@@ -213,6 +218,15 @@ static void fill_params(const gb200_problem* p, const gb200_ic* ic, const gb200_
         P.c_ph1 = (giphph - gitph * om) * sph;
     }
     P.first = rg->first; P.count = rg->count; P.stride = rg->stride;
+    P.block = rg->block > 0 ? rg->block : 1;
+    // 2-D tiled work order when the range is made of whole strips of GB_TILE_C image columns (or theta-rows of the plane)
+    P.tile_h = 0;
+    if (ic->kind != GB200_IC_EXPLICIT && !getenv("GB200_NO_TILING")) {
+        const int64_t h = (ic->kind == GB200_IC_RENDER_GRID) ? ic->height : ic->width; // fastest-varying extent of the ray index
+        const int64_t strip = GB_TILE_C * h;
+        const bool contiguous = (P.stride == 1) || (P.block % strip == 0);
+        if (h % GB_TILE_R == 0 && contiguous && P.first % strip == 0 && P.count % strip == 0) P.tile_h = h;
+    }
 }
 
 // ---------------------------------------------------------------- device memory

@@ -85,8 +85,11 @@ struct GbParams {
     double go[5];                   // metric components at the observer (for constrain_time and E_obs)
     const double* ex[4];            // explicit ICs (device SoA), indexed by global ray id
     const double* ev[4];
-    // ray range
-    int64_t first, count, stride;
+    // ray range: slot n <-> ray index first + (n / block) * stride * block + n % block
+    int64_t first, count, stride, block;
+    // work order: tickets are handed out so that a warp starts on a 2-D tile of GB_TILE_R x GB_TILE_C neighbouring
+    // rays (rows x columns of the image / r x theta of the polar plane) instead of 32 consecutive rows; 0 = ticket order
+    int64_t tile_h;
     // outputs, indexed by slot n in [0, count)
     int32_t* o_status;
     double* o_lambda;
@@ -519,6 +522,28 @@ GB_HD inline double disc_condition(const GbParams& P, double r, double s, double
         return r * c - P.gp0;
     }
     return 1.0;
+}
+
+// ---------------------------------------------------------------- ray indexing
+#ifndef GB_TILE_R
+#define GB_TILE_R 8
+#endif
+#ifndef GB_TILE_C
+#define GB_TILE_C 4
+#endif
+GB_HD inline int64_t ray_index_of_slot(const GbParams& P, int64_t n) {
+    return P.first + (n / P.block) * (P.stride * P.block) + n % P.block;
+}
+// ticket (work-queue order) -> slot (output order).  Within every strip of GB_TILE_C columns (= GB_TILE_C * tile_h
+// consecutive slots) tickets walk 8 x 4 tiles; neighbouring rays take similar step counts and reach the disc at the
+// same steps, which keeps a warp's event scans, terminations and refills in phase.
+GB_HD inline int64_t slot_of_ticket(const GbParams& P, int64_t k) {
+    if (P.tile_h == 0) return k;
+    const int64_t strip = GB_TILE_C * P.tile_h;
+    const int64_t sidx = k / strip, w = k - sidx * strip;
+    const int64_t t = w / (GB_TILE_R * GB_TILE_C), l = w - t * (GB_TILE_R * GB_TILE_C);
+    const int64_t dc = l / GB_TILE_R, dr = l - dc * GB_TILE_R;
+    return sidx * strip + dc * P.tile_h + t * GB_TILE_R + dr;
 }
 
 // ---------------------------------------------------------------- image-plane -> initial state

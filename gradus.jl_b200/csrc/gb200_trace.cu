@@ -289,11 +289,12 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                 if (lane == 0) base = atomicAdd(P.queue, (unsigned long long)nfree);
                 base = __shfl_sync(FULLMASK, base, 0);
                 if (state == LANE_EMPTY) {
-                    const int64_t s = (int64_t)base + __popc(emask & ((1u << lane) - 1u));
-                    if (s < P.count) {
+                    const int64_t ticket = (int64_t)base + __popc(emask & ((1u << lane) - 1u));
+                    if (ticket < P.count) {
+                        const int64_t s = slot_of_ticket(P, ticket);
                         slot = s;
                         GbRayInit ri;
-                        ray_initial_state(P, P.first + s * P.stride, ri);
+                        ray_initial_state(P, ray_index_of_slot(P, s), ri);
                         lam = P.lam0; ct = ri.x[0]; r = ri.x[1]; th = ri.x[2]; ph = ri.x[3];
                         vt = ri.v[0]; vr = ri.v[1]; vth = ri.v[2]; vph = ri.v[3];
                         area = ri.area;

@@ -37,6 +37,20 @@ def interleaved_range(n_total, rank, world) -> cabi.Range:
     return cabi.Range(rank, count, world)
 
 
+def strip_interleaved_range(ic, rank, world, columns=4) -> cabi.Range:
+    """Whole strips of `columns` image columns (render grid) / theta-rows (polar plane), strip r, r+world, ... for rank r.
+    Balances like ray interleaving but keeps neighbouring rays on the same GPU and in the same warp, which is worth
+    up to 15 % of kernel time at 8 ranks (profiles/r01_tuning_log.md).  Falls back to ray interleaving when the image
+    does not divide into strips."""
+    h = ic.height if ic.kind == cabi.IC_RENDER_GRID else ic.width
+    strip = columns * h
+    if ic.kind == cabi.IC_EXPLICIT or ic.n % strip != 0:
+        return interleaved_range(ic.n, rank, world)
+    nstrips = ic.n // strip
+    mine = (nstrips - rank + world - 1) // world if nstrips > rank else 0
+    return cabi.Range(rank * strip, mine * strip, world, strip)
+
+
 def block_range(n_total, rank, world) -> cabi.Range:
     """Contiguous slab of rays (for images: a block of columns of the column-major (H, W) array)."""
     base, rem = divmod(n_total, world)

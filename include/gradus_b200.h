@@ -118,12 +118,16 @@ typedef struct gb200_ic {
     int64_t n; /* total number of rays described by this IC */
 } gb200_ic;
 
-/* Sub-range of rays handled by one call: indices first, first+stride, ...
-   (count of them).  Rays shard trivially across GPUs / ranks. */
+/* Sub-range of rays handled by one call.  Output slot n (0 <= n < count) holds ray
+       first + (n / block) * stride * block + n % block,
+   i.e. blocks of `block` consecutive rays, every `stride`-th block (block = 1: rays first, first+stride, ...).
+   Rays shard trivially across GPUs / ranks; interleaving whole blocks of image columns (block = 4 * image_height)
+   keeps neighbouring rays together, which the kernel's warps like ("work order"). */
 typedef struct gb200_range {
     int64_t first;
     int64_t count;
     int64_t stride; /* >= 1 */
+    int64_t block;  /* >= 1; 0 is read as 1 */
 } gb200_range;
 
 /* Caller-allocated host SoA, `count` entries each; any pointer may be NULL.

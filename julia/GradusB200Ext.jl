@@ -42,7 +42,7 @@ struct CIC
     x::NTuple{4,Ptr{Float64}}; v::NTuple{4,Ptr{Float64}}; n::Int64
 end
 struct CRange
-    first::Int64; count::Int64; stride::Int64
+    first::Int64; count::Int64; stride::Int64; block::Int64
 end
 struct CEndpoints
     status::Ptr{Int32}; lambda_max::Ptr{Float64}
@@ -137,7 +137,7 @@ function Gradus.ensemble_solve_tracing_problem(
             off(a) = pointer(a, first + 1)
             out = CEndpoints(off(status), off(λ), Tuple(off.(x)), Tuple(off.(v)), Tuple(off.(x0)), Tuple(off.(v0)), C_NULL, C_NULL, C_NULL)
             rc = ccall((:gb200_trace, libgradus_b200), Cint, (Ptr{Cvoid}, Ref{CProblem}, Ref{CIC}, Ref{CRange}, Ref{CEndpoints}),
-                       ctx[], p, ic, CRange(first, count, 1), out)
+                       ctx[], p, ic, CRange(first, count, 1, 1), out)
             _check(rc, ctx[])
             ccall((:gb200_destroy, libgradus_b200), Cvoid, (Ptr{Cvoid},), ctx[])
         end

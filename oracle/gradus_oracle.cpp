@@ -864,7 +864,8 @@ int run(const gb200_problem& p, const gb200_ic& ic, const gb200_range& rg, int n
 #endif
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t n = 0; n < rg.count; ++n) {
-        int64_t i = rg.first + n * rg.stride;
+        const int64_t blk = rg.block > 0 ? rg.block : 1;
+        int64_t i = rg.first + (n / blk) * (rg.stride * blk) + n % blk;
         RayIC ric;
         ic_for_ray(p, ic, i, ric);
         // (the plane path's map_impact_parameters rebuilds the same transform per ray, utility.jl:84-87: identical values)
@@ -1053,7 +1054,8 @@ int oracle_band(const gb200_problem* p, const gb200_ic* ic, const gb200_range* r
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t n = 0; n < rg->count; ++n) {
         orc::RayIC ric;
-        orc::ic_for_ray(*p, *ic, rg->first + n * rg->stride, ric);
+        const int64_t blk = rg->block > 0 ? rg->block : 1;
+        orc::ic_for_ray(*p, *ic, rg->first + (n / blk) * (rg->stride * blk) + n % blk, ric);
         double u0[8];
         orc::initial_state<double>(*p, m, ric, &xfm, u0);
         ratio[n] = (p->geometry_kind == GB200_GEOMETRY_NONE) ? 0.0 : orc::band_ratio(*p, m, u0);

@@ -82,3 +82,13 @@ def test_range_helpers_partition_the_rays():
                 b = gd.block_range(n, r, world)
                 seen += list(range(b.first, b.first + b.count))
             assert seen == list(range(n))
+    # strips of 4 columns of a 16 x 24 image (H = 16): every ray exactly once, whole strips per rank
+    import gradus_b200 as gb
+    from gradus_b200.api import RenderGrid, tracing_configuration
+
+    cfg = tracing_configuration(gb.KerrMetric(), [0.0, 100.0, 1.0, 0.0], RenderGrid(24, 16, (-5, 5), (-5, 5)), 200.0, trajectories=384)
+    _, ic = cfg.to_c()
+    for world in (1, 2, 3, 4):
+        seen = np.concatenate([gd.strip_interleaved_range(ic, r, world).indices() for r in range(world)])
+        assert sorted(seen.tolist()) == list(range(384))
+        assert all(gd.strip_interleaved_range(ic, r, world).block == 64 for r in range(world))

@@ -210,6 +210,13 @@ def test_full_size_render_properties(ensemble):
     # sharding invariance: an interleaved shard reproduces exactly the same pixels (what the multi-GPU path relies on)
     shard = render(cabi.Range(3, ic.n // 8, 8))
     assert np.array_equal(shard, full[:, 3::8][:, : ic.n // 8], equal_nan=True)
+    # strips of 4 image columns interleaved over 8 ranks (bench.py's decomposition; 2-D tiled work order inside)
+    from gradus_b200 import distributed as gd
+
+    for rank in (0, 5):
+        rng = gd.strip_interleaved_range(ic, rank, 8)
+        assert rng.block == 4 * 2048 and rng.count == ic.n // 8
+        assert np.array_equal(render(rng), full[:, rng.indices()], equal_nan=True)
     # physics: redshift range of a a=0.998 disc seen at 60 degrees, radii inside the disc, NaN masks consistent
     g, rho, status = full
     hit = status == cabi.STATUS_INTERSECTED
@@ -332,10 +339,11 @@ def test_edge_cases(ensemble):
     assert lib.gb200_trace(ctx, C.byref(p), C.byref(ic), C.byref(cabi.Range(5, 0, 1)), C.byref(out.c)) == cabi.OK  # empty: no launch
     assert ensemble.stats().launches == 0 and ensemble.stats().rays == 0
     full = solve_tracing_problem(cfg)
-    for first, count, stride in [(777, 1, 1), (3, 100, 7), (1023, 1, 1), (0, 1024, 1)]:
+    for first, count, stride, block in [(777, 1, 1, 1), (3, 100, 7, 1), (1023, 1, 1, 1), (0, 1024, 1, 1), (32, 96, 3, 32), (128, 256, 2, 128), (5, 70, 4, 10)]:
         sub = cabi.EndpointArrays(count)
-        cabi.check(lib.gb200_trace(ctx, C.byref(p), C.byref(ic), C.byref(cabi.Range(first, count, stride)), C.byref(sub.c)), ctx)
-        idx = first + stride * np.arange(count)
+        rng = cabi.Range(first, count, stride, block)
+        cabi.check(lib.gb200_trace(ctx, C.byref(p), C.byref(ic), C.byref(rng), C.byref(sub.c)), ctx)
+        idx = rng.indices()
         assert np.array_equal(sub.status, full.status[idx]) and np.array_equal(sub.x, full.x[:, idx]) and np.array_equal(sub.v, full.v[:, idx])
     # looser and tighter tolerances, shifted affine domain: still matches the oracle
     for tol in (1e-6, 1e-11):
