@@ -751,6 +751,36 @@ int gb200_lineprofile_device(gb200_ctx* ctx, const gb200_problem* p, const gb200
     return lineprofile_common(ctx, p, ic, rg, em, pl, bins, nbins, opts, d_flux, true, s, async);
 }
 
+int gb200_debug_rhs(gb200_ctx* ctx, int32_t metric_kind, const double* mp, int64_t n, const double* u, double* du) {
+    if (!ctx || !mp || !u || !du || n < 1) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (metric_kind != GB200_METRIC_KERR && metric_kind != GB200_METRIC_JOHANNSEN_PSALTIS) return fail(ctx, GB200_ERR_UNSUPPORTED, "metric kind %d", metric_kind);
+    CU(ctx, cudaSetDevice(ctx->device));
+    GbParams P;
+    memset(&P, 0, sizeof P);
+    P.metric_kind = metric_kind; P.M = mp[0]; P.a = mp[1]; P.eps3 = mp[2];
+    void *d_u, *d_du;
+    int rc = pool_get(ctx, SL_X0, sizeof(double) * 8 * (size_t)n, &d_u); if (rc) return rc;
+    rc = pool_get(ctx, SL_V0, sizeof(double) * 8 * (size_t)n, &d_du); if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(d_u, u, sizeof(double) * 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, gb200_launch_debug_rhs(P, n, (const double*)d_u, (double*)d_du, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(du, d_du, sizeof(double) * 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB200_OK;
+}
+
+int gb200_debug_math(gb200_ctx* ctx, int64_t n, const double* x, double* out3) {
+    if (!ctx || !x || !out3 || n < 1) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad arguments");
+    CU(ctx, cudaSetDevice(ctx->device));
+    void *d_x, *d_o;
+    int rc = pool_get(ctx, SL_X0, sizeof(double) * (size_t)n, &d_x); if (rc) return rc;
+    rc = pool_get(ctx, SL_V0, sizeof(double) * 3 * (size_t)n, &d_o); if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(d_x, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, gb200_launch_debug_math(n, (const double*)d_x, (double*)d_o, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(out3, d_o, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB200_OK;
+}
+
 int gb200_fp64_peak(gb200_ctx* ctx, double* tflops_out) {
     if (!ctx || !tflops_out) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null argument");
     CU(ctx, cudaSetDevice(ctx->device));

@@ -720,6 +720,33 @@ cudaError_t gb200_launch_hist(const double* g, const double* f, int64_t n, const
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- diagnostics
+template <int METRIC>
+__global__ void gb200_debug_rhs_kernel(const GbParams P, long long n, const double* __restrict__ u, double* __restrict__ du) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc[4], s_, c_;
+    rhs_accel<METRIC>(P, u[8 * i + 1], u[8 * i + 2], u[8 * i + 4], u[8 * i + 5], u[8 * i + 6], u[8 * i + 7], acc, s_, c_);
+    for (int k = 0; k < 4; ++k) { du[8 * i + k] = u[8 * i + 4 + k]; du[8 * i + 4 + k] = acc[k]; }
+}
+__global__ void gb200_debug_math_kernel(long long n, const double* __restrict__ x, double* __restrict__ out3) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s_, c_;
+    gb_sincos(x[i], &s_, &c_);
+    out3[3 * i] = s_; out3[3 * i + 1] = c_; out3[3 * i + 2] = gb_rcp(x[i]);
+}
+cudaError_t gb200_launch_debug_rhs(const GbParams& P, long long n, const double* d_u, double* d_du, cudaStream_t stream) {
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (P.metric_kind == GB200_METRIC_KERR) gb200_debug_rhs_kernel<GB200_METRIC_KERR><<<grid, 128, 0, stream>>>(P, n, d_u, d_du);
+    else gb200_debug_rhs_kernel<GB200_METRIC_JOHANNSEN_PSALTIS><<<grid, 128, 0, stream>>>(P, n, d_u, d_du);
+    return cudaGetLastError();
+}
+cudaError_t gb200_launch_debug_math(long long n, const double* d_x, double* d_out3, cudaStream_t stream) {
+    gb200_debug_math_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, d_x, d_out3);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- FP64 peak micro-benchmark (roofline denominator)
 __global__ void __launch_bounds__(256) gb200_dfma_kernel(double* out, int iters, double seed) {
     double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

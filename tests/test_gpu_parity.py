@@ -483,3 +483,33 @@ def test_plunging_table_and_redshift_inside_isco(ensemble):
     assert inside.sum() > 20 and (both & ~inside).sum() > 500
     assert np.abs(img[both & ~inside] - want_g[both & ~inside]).max() < 1e-6
     assert np.abs(img[inside] - want_g[inside]).max() < 2e-3  # two independently integrated tables, linearly interpolated
+
+
+def test_device_math_against_oracle(ensemble):
+    """Function-level check of the closed forms: device RHS vs the oracle's dual-number RHS, sincos and reciprocal."""
+    lib = cabi.load()
+    ctx = ensemble.ctx(ensemble.devices[0])
+    rs = np.random.RandomState(7)
+    n = 4000
+    for kind, mp in [(cabi.METRIC_KERR, (1.0, 0.998)), (cabi.METRIC_KERR, (1.3, -0.4)), (cabi.METRIC_JP, (1.0, 0.6, 2.0)), (cabi.METRIC_JP, (1.0, 0.8831, 0.4))]:
+        rh = mp[0] + math.sqrt(mp[0] ** 2 - mp[1] ** 2)
+        u = np.zeros((n, 8))
+        u[:, 1] = rh * 1.02 * np.exp(rs.uniform(0, 7, n))  # 1.02 r_h .. 1e3 r_h
+        u[:, 2] = rs.uniform(0.05, math.pi - 0.05, n)
+        u[:, 3] = rs.uniform(-3, 3, n)
+        u[:, 4:] = rs.normal(size=(n, 4)) * np.array([1.5, 1.0, 0.3, 0.3])
+        du = np.zeros_like(u)
+        mpa = np.array(list(mp) + [0.0] * (4 - len(mp)))
+        cabi.check(lib.gb200_debug_rhs(ctx, kind, cabi.dptr(mpa), n, cabi.dptr(u.reshape(-1)), cabi.dptr(du.reshape(-1))), ctx)
+        want = np.array([oracle.rhs(kind, mp, u[i]) for i in range(n)])
+        scale = np.max(np.abs(want[:, 4:]), axis=1, keepdims=True)
+        # the oracle's generic inverse g_tt g_phph - g_tph^2 cancels near the horizon (condition number ~1e4): 1e-10 there
+        err = np.abs(du[:, 4:] - want[:, 4:]) / scale
+        assert np.array_equal(du[:, :4], u[:, 4:])
+        assert err.max() < 1e-10 and np.median(err) < 1e-14, (kind, mp, err.max(), np.median(err))
+    x = np.concatenate([rs.uniform(-60, 60, 20000), np.array([0.0, 1e-300, math.pi / 2, math.pi, -math.pi / 4, 40.0, 1e-9])])
+    out = np.zeros((len(x), 3))
+    cabi.check(lib.gb200_debug_math(ctx, len(x), cabi.dptr(x), cabi.dptr(out.reshape(-1))), ctx)
+    assert np.abs(out[:, 0] - np.sin(x)).max() < 2.5e-16 and np.abs(out[:, 1] - np.cos(x)).max() < 2.5e-16
+    nz = x != 0
+    assert np.max(np.abs(out[nz, 2] * x[nz] - 1.0)) < 4.5e-16
