@@ -13,6 +13,7 @@ through the C ABI of include/gradus_b200.h (libgradus_b200.so, hand-written sm_1
 there is no CPU fallback."""
 from .api import (  # noqa: F401
     BinningMethod,
+    CartesianPlane,
     ConstPointFunctions,
     DatumPlane,
     EnsembleB200,

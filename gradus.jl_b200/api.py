@@ -179,6 +179,22 @@ class PolarPlane:
 
 
 @dataclass(frozen=True)
+class CartesianPlane:
+    """src/image-planes/planes.jl:130-163"""
+
+    grid: Any = field(default_factory=LinearGrid)
+    Nx: int = 150
+    Ny: int = 150
+    x_min: float = 0.0
+    x_max: float = 150.0
+    y_min: float = 0.0
+    y_max: float = 150.0
+
+    def trajectory_count(self):
+        return (2 * (self.Ny // 2) - 1) * (2 * (self.Nx // 2) - 1)
+
+
+@dataclass(frozen=True)
 class RenderGrid:
     """The closure returned by `_render_velocity_function` (src/rendering/rendering.jl:140-163) as data."""
 
@@ -313,6 +329,14 @@ class TracingConfiguration:
             ic.width, ic.height = v.Nr, v.Ntheta
             ic.lo0, ic.hi0 = float(v.r_min), float(v.r_max)
             ic.lo1, ic.hi1 = float(v.theta_min), float(v.theta_max)
+            ic.n = v.trajectory_count()
+        elif isinstance(v, CartesianPlane):
+            p.observer[:] = pos
+            ic.kind = cabi.IC_CARTESIAN_PLANE
+            ic.grid_kind = v.grid.kind
+            ic.width, ic.height = v.Nx, v.Ny
+            ic.lo0, ic.hi0 = float(v.x_min), float(v.x_max)
+            ic.lo1, ic.hi1 = float(v.y_min), float(v.y_max)
             ic.n = v.trajectory_count()
         else:
             # explicit SoA: what the Julia shim builds by evaluating prob_func on host threads

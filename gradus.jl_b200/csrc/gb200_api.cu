@@ -146,6 +146,12 @@ static int validate(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic) 
         if (ic->grid_kind < GB200_GRID_LINEAR || ic->grid_kind > GB200_GRID_INVERSE) return fail(ctx, GB200_ERR_UNSUPPORTED, "grid kind %d", ic->grid_kind);
         if (!(ic->lo0 > 0) || !(ic->hi0 > ic->lo0)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "PolarPlane needs 0 < r_min < r_max");
         if (ic->n != ic->width * ic->height) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "ic.n != Nr*Ntheta");
+    } else if (ic->kind == GB200_IC_CARTESIAN_PLANE) {
+        if (ic->width < 4 || ic->height < 4) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "CartesianPlane needs Nx, Ny >= 4");
+        if (ic->grid_kind < GB200_GRID_LINEAR || ic->grid_kind > GB200_GRID_INVERSE) return fail(ctx, GB200_ERR_UNSUPPORTED, "grid kind %d", ic->grid_kind);
+        if (!(ic->hi0 > ic->lo0) || !(ic->hi1 > ic->lo1)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "CartesianPlane needs x_min < x_max, y_min < y_max");
+        if (ic->grid_kind != GB200_GRID_LINEAR && (!(ic->lo0 > 0) || !(ic->lo1 > 0))) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "geometric / inverse grids need positive minima");
+        if (ic->n != (2 * (ic->height / 2) - 1) * (2 * (ic->width / 2) - 1)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "ic.n != (2(Ny/2)-1)(2(Nx/2)-1)");
     } else if (ic->kind == GB200_IC_EXPLICIT) {
         if (ic->n < 1) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "explicit IC needs n >= 1");
         for (int k = 0; k < 4; ++k)
@@ -201,6 +207,17 @@ static void fill_params(const gb200_problem* p, const gb200_ic* ic, const gb200_
         const double dth = (ic->hi1 - ic->lo1) / (double)ic->height; // planes.jl:95-96
         P.lo1 = ic->lo1; dd_step(ic->lo1, ic->hi1 - dth, ic->height, &P.step1_hi, &P.step1_lo);
     }
+    if (ic->kind == GB200_IC_CARTESIAN_PLANE) {
+        P.n0 = ic->width / 2; P.n1 = ic->height / 2;
+        P.lo0 = ic->lo0; dd_step(ic->lo0, ic->hi0, P.n0, &P.step0_hi, &P.step0_lo);
+        P.lo1 = ic->lo1; dd_step(ic->lo1, ic->hi1, P.n1, &P.step1_hi, &P.step1_lo);
+        if (ic->grid_kind != GB200_GRID_LINEAR) {
+            P.geoK = std::pow(ic->hi0 / ic->lo0, 1.0 / (double)(P.n0 - 1));
+            P.geoK1 = std::pow(ic->hi1 / ic->lo1, 1.0 / (double)(P.n1 - 1));
+            P.inv_lo_hi = 1.0 / ic->hi0; dd_step(1.0 / ic->hi0, 1.0 / ic->lo0, P.n0, &P.inv_step_hi, &P.inv_step_lo);
+            P.inv1_lo_hi = 1.0 / ic->hi1; dd_step(1.0 / ic->hi1, 1.0 / ic->lo1, P.n1, &P.inv1_step_hi, &P.inv1_step_lo);
+        }
+    }
     if (ic->kind != GB200_IC_EXPLICIT) {
         // closed-form LNRF (ZAMO) co-basis at the observer, generic for static axisymmetric g:
         //   e^(t) = N dt, e^(r) = sqrt(g_rr) dr, e^(th) = sqrt(g_thth) dth, e^(ph) = sqrt(g_phph)(dph - w dt)
@@ -222,7 +239,8 @@ static void fill_params(const gb200_problem* p, const gb200_ic* ic, const gb200_
     // 2-D tiled work order when the range is made of whole strips of GB_TILE_C image columns (or theta-rows of the plane)
     P.tile_h = 0;
     if (ic->kind != GB200_IC_EXPLICIT && !getenv("GB200_NO_TILING")) {
-        const int64_t h = (ic->kind == GB200_IC_RENDER_GRID) ? ic->height : ic->width; // fastest-varying extent of the ray index
+        const int64_t h = (ic->kind == GB200_IC_RENDER_GRID) ? ic->height
+                        : (ic->kind == GB200_IC_CARTESIAN_PLANE) ? (2 * (ic->height / 2) - 1) : ic->width; // fastest-varying extent of the ray index
         const int64_t strip = GB_TILE_C * h;
         const bool contiguous = (P.stride == 1) || (P.block % strip == 0);
         if (h % GB_TILE_R == 0 && contiguous && P.first % strip == 0 && P.count % strip == 0) P.tile_h = h;

@@ -75,10 +75,12 @@ struct GbParams {
     // initial conditions
     int32_t ic_kind, grid_kind;
     int64_t width, height;
-    double lo0, step0_hi, step0_lo; // alpha (or r) axis: value = lo + i*step, step in double-double
-    double lo1, step1_hi, step1_lo; // beta (or theta) axis
-    double geoK;                    // geometric grid ratio
-    double inv_lo_hi, inv_step_hi, inv_step_lo; // inverse grid: range(1/max, 1/min, N)
+    double lo0, step0_hi, step0_lo; // alpha (or r / x) axis: value = lo + i*step, step in double-double
+    double lo1, step1_hi, step1_lo; // beta (or theta / y) axis
+    double geoK, geoK1;             // geometric grid ratios of axis 0 / axis 1
+    double inv_lo_hi, inv_step_hi, inv_step_lo;    // inverse grid of axis 0: range(1/max, 1/min, N)
+    double inv1_lo_hi, inv1_step_hi, inv1_step_lo; // inverse grid of axis 1 (cartesian plane)
+    int64_t n0, n1;                 // points per axis grid (cartesian plane: Nx/2, Ny/2)
     double xo[4];                   // observer position
     // observer LNRF constants: v^r = c_r p_r, v^th = c_th p_th, v^ph = c_ph0 + c_ph1 p_ph
     double c_r, c_th, c_ph0, c_ph1;
@@ -579,7 +581,20 @@ GB_HD inline void ray_initial_state(const GbParams& P, int64_t i, GbRayInit& o) 
         return;
     }
     double alpha, beta;
-    if (P.ic_kind == GB200_IC_RENDER_GRID) { // rendering.jl:150-159
+    if (P.ic_kind == GB200_IC_CARTESIAN_PLANE) { // planes.jl:152-171: grids mirrored about their first point
+        const int64_t rows = 2 * P.n1 - 1;
+        const int64_t col = i / rows, row = i - col * rows;
+        const int64_t ka = (col < P.n0 - 1) ? (P.n0 - 1 - col) : (col - (P.n0 - 1));
+        const int64_t kb = (row < P.n1 - 1) ? (P.n1 - 1 - row) : (row - (P.n1 - 1));
+        double xa, yb;
+        if (P.grid_kind == GB200_GRID_GEOMETRIC) { xa = P.lo0 * pow(P.geoK, (double)ka); yb = P.lo1 * pow(P.geoK1, (double)kb); }
+        else if (P.grid_kind == GB200_GRID_INVERSE) {
+            xa = 1.0 / dd_axis(P.inv_lo_hi, P.inv_step_hi, P.inv_step_lo, P.n0 - 1 - ka);
+            yb = 1.0 / dd_axis(P.inv1_lo_hi, P.inv1_step_hi, P.inv1_step_lo, P.n1 - 1 - kb);
+        } else { xa = dd_axis(P.lo0, P.step0_hi, P.step0_lo, ka); yb = dd_axis(P.lo1, P.step1_hi, P.step1_lo, kb); }
+        alpha = (col < P.n0 - 1) ? -xa : xa;
+        beta = (row < P.n1 - 1) ? -yb : yb;
+    } else if (P.ic_kind == GB200_IC_RENDER_GRID) { // rendering.jl:150-159
         const int64_t col = i / P.height, row = i - col * P.height;
         alpha = dd_axis(P.lo0, P.step0_hi, P.step0_lo, col) + 1e-6;
         beta = dd_axis(P.lo1, P.step1_hi, P.step1_lo, row) + 1e-6;

@@ -97,6 +97,7 @@ typedef struct gb200_problem {
 #define GB200_IC_RENDER_GRID 0 /* _render_velocity_function, src/rendering/rendering.jl:140-163 */
 #define GB200_IC_POLAR_PLANE 1 /* PolarPlane + promote_velfunc, src/image-planes/planes.jl:70-115,180-184 */
 #define GB200_IC_EXPLICIT 2    /* prob_func evaluated on the host into SoA (corona ensembles) */
+#define GB200_IC_CARTESIAN_PLANE 3 /* CartesianPlane, src/image-planes/planes.jl:130-178 */
 
 #define GB200_GRID_LINEAR 0    /* src/image-planes/grids.jl:32-36 */
 #define GB200_GRID_GEOMETRIC 1 /* grids.jl:11-20 */
@@ -107,10 +108,12 @@ typedef struct gb200_ic {
     int32_t grid_kind; /* polar plane only */
     /* render grid: ray i (0-based) -> col = i / height, row = i % height;
        alpha = range(alpha_lo, alpha_hi, width)[col] + 1e-6, beta likewise */
-    int64_t width;  /* render: image_width ; polar: Nr */
-    int64_t height; /* render: image_height; polar: Ntheta */
-    double lo0, hi0; /* render: alpha limits; polar: r_min, r_max */
-    double lo1, hi1; /* render: beta  limits; polar: theta_min, theta_max */
+    int64_t width;  /* render: image_width ; polar: Nr     ; cartesian: Nx */
+    int64_t height; /* render: image_height; polar: Ntheta ; cartesian: Ny */
+    double lo0, hi0; /* render: alpha limits; polar: r_min, r_max         ; cartesian: x_min, x_max */
+    double lo1, hi1; /* render: beta  limits; polar: theta_min, theta_max ; cartesian: y_min, y_max */
+    /* cartesian plane: the grid (grid_kind) is evaluated on Nx/2 and Ny/2 points and mirrored about the first point;
+       n = (2(Ny/2) - 1)(2(Nx/2) - 1); ray i -> beta index i % (2(Ny/2) - 1), alpha index i / (2(Ny/2) - 1) */
     /* explicit: host SoA, each pointer addresses n doubles; v[0] (v^t) is
        ignored and re-constrained exactly like wrap_constraint does */
     const double* x[4];

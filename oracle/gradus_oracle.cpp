@@ -384,6 +384,17 @@ static void ic_for_ray(const gb200_problem& p, const gb200_ic& ic, int64_t i, Ra
         out.alpha = r * std::cos(th);
         out.beta = r * std::sin(th);
         out.area = r * r;
+    } else if (ic.kind == GB200_IC_CARTESIAN_PLANE) { // planes.jl:152-171
+        int64_t hx = ic.width / 2, hy = ic.height / 2;
+        int64_t rows = 2 * hy - 1; // X_size
+        int64_t col = i / rows, row = i % rows;
+        // alphas = hcat(-reverse(X), xs[1], X): columns -xs[end..2], xs[1], xs[2..end]; betas likewise along rows
+        auto mirrored = [&](int64_t idx, int64_t h, double lo, double hi) {
+            if (idx < h - 1) return -grid_value(ic.grid_kind, lo, hi, h, h - 1 - idx);
+            return grid_value(ic.grid_kind, lo, hi, h, idx - (h - 1));
+        };
+        out.alpha = mirrored(col, hx, ic.lo0, ic.hi0);
+        out.beta = mirrored(row, hy, ic.lo1, ic.hi1);
     } else {
         for (int k = 0; k < 4; ++k) { out.x[k] = ic.x[k][i]; out.v[k] = ic.v[k][i]; }
         out.explicit_v = true;

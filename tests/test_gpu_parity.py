@@ -183,6 +183,10 @@ def test_reference_golden_values_on_gpu(ensemble):
     for grid, count in [(gb.LinearGrid(), 10), (gb.GeometricGrid(), 30), (gb.InverseGrid(), 80)]:  # test-polar-grids.jl:13-21
         gps = gb.tracegeodesics(gb.KerrMetric(), [1.0, 1e3, math.pi / 2, 0.0], gb.PolarPlane(grid, Nr=10, Ntheta=10), (0.0, 2000.0), ensemble=ensemble)
         assert int((gps.status == cabi.STATUS_WITHIN_INNER_BOUNDARY).sum()) == count
+    for grid, count in [(gb.LinearGrid(), 1), (gb.GeometricGrid(), 25), (gb.InverseGrid(), 81)]:  # test-cartesian-grids.jl:13-21
+        plane = gb.CartesianPlane(grid, x_min=0.1, y_min=0.1, Nx=12, Ny=12)
+        gps = gb.tracegeodesics(gb.KerrMetric(), [1.0, 1e3, math.pi / 2, 0.0], plane, (0.0, 2000.0), ensemble=ensemble)
+        assert len(gps) == 121 and int((gps.status == cabi.STATUS_WITHIN_INNER_BOUNDARY).sum()) == count
     m = gb.KerrMetric(1.0, 0.998)  # test/transfer-functions/test-2d.jl:25
     x = [0.0, 1e6, math.radians(30), 0.0]
     gps = gb.tracegeodesics(m, x, gb.PolarPlane(gb.GeometricGrid(), Nr=20, Ntheta=20), gb.ThinDisc(gb.isco(m), 500.0), (0.0, 2e6),

@@ -70,6 +70,16 @@ def test_polar_grid_inner_boundary_counts(grid, name):
     assert int((ep.status == cabi.STATUS_WITHIN_INNER_BOUNDARY).sum()) == GOLD["polar_grid_inner_counts"]["value"][name]
 
 
+@pytest.mark.parametrize("grid,name", [(gb.LinearGrid(), "linear"), (gb.GeometricGrid(), "geometric"), (gb.InverseGrid(), "inverse")])
+def test_cartesian_grid_inner_boundary_counts(grid, name):
+    plane = gb.CartesianPlane(grid, x_min=0.1, y_min=0.1, Nx=12, Ny=12)
+    cfg = tracing_configuration(gb.KerrMetric(), [1.0, 1e3, math.pi / 2, 0.0], plane, (0.0, 2000.0))
+    p, ic = cfg.to_c()
+    assert ic.n == 121
+    ep = oracle.trace(p, ic)
+    assert int((ep.status == cabi.STATUS_WITHIN_INNER_BOUNDARY).sum()) == GOLD["cartesian_grid_inner_counts"]["value"][name]
+
+
 def test_lagtransfer_observer_to_disc_hit_count():
     m = gb.KerrMetric(M=1.0, a=0.998)
     x = [0.0, 1e6, math.radians(30), 0.0]
