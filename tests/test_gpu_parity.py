@@ -194,6 +194,23 @@ def test_reference_golden_values_on_gpu(ensemble):
     assert int((gps.status == cabi.STATUS_INTERSECTED).sum()) == 337
 
 
+@pytest.mark.parametrize("m,g_low_ref", [(gb.KerrMetric(1.0, 0.6), 0.355), (gb.JohannsenPsaltisMetric(1.0, 0.6, 2.0), 0.27)])
+def test_reference_line_profile_edges_on_gpu(ensemble, m, g_low_ref):
+    """test/line-profiles/test-binning.jl:5-57 through the GPU `lineprofile`, and L1 parity with the oracle on the same fixture."""
+    u = [0.0, 1000.0, math.radians(60), 0.0]
+    d = gb.ThinDisc(gb.isco(m), 250.0)
+    plane = gb.PolarPlane(gb.GeometricGrid(), Nr=100, Ntheta=400)
+    bins = np.linspace(0.1, 1.3, 100)
+    x, y = gb.lineprofile(bins, gb.PowerLawEmissivity(3.0), m, u, d, gb.BinningMethod(), plane=plane, callback=gb.domain_upper_hemisphere(), ensemble=ensemble)
+    nzi = np.nonzero(y > 0)[0]
+    assert x[nzi[0]] == pytest.approx(g_low_ref, abs=0.05) and x[nzi[-1] - 1] == pytest.approx(1.2, abs=0.05)
+    assert y.sum() == pytest.approx(1.0, abs=1e-12)
+    cfg = tracing_configuration(m, u, plane, d, (0.0, 2000.0), callback=gb.domain_upper_hemisphere(), ensemble=ensemble)
+    p, ic = cfg.to_c()
+    want = oracle.lineprofile(p, ic, cabi.Emissivity(cabi.EMISSIVITY_POWERLAW, 0, 3.0, None, None), bins, cabi.LineProfileOpts(gb.isco(m), 50.0, 1, 1))
+    assert np.abs(y - want).sum() < 1e-4
+
+
 def test_full_size_render_properties(ensemble):
     """BASELINE configs[1] at full 2048x2048 size: size-independent properties + a strided oracle sample."""
     m, x, d, cfg = common.c1(2048, 2048, ensemble=ensemble)

@@ -146,3 +146,32 @@ def test_lnr_frame_is_orthonormal_for_jp():
         _, frame = oracle.lnrbasis(cabi.METRIC_JP, mp, 7.3, th)
         res = frame @ G @ frame.T
         assert np.allclose(res, np.diag([-1.0, 1, 1, 1]), atol=1e-13)
+
+
+def _binning_fixture(m):
+    """test/line-profiles/test-binning.jl:5-57: the reference's only numeric pin of the redshift point function."""
+    u = [0.0, 1000.0, math.radians(60), 0.0]
+    d = gb.ThinDisc(gb.isco(m), 250.0)
+    plane = gb.PolarPlane(gb.GeometricGrid(), Nr=100, Ntheta=400)
+    bins = np.linspace(0.1, 1.3, 100)
+    return u, d, plane, bins
+
+
+def _edges(bins, y):
+    nzi = np.nonzero(y > 0)[0]
+    g_low = bins[nzi[0]]
+    g_high = bins[len(bins) - 1 - (len(y) - 1 - nzi[-1]) - 1]  # x[end - findfirst(>(0), reverse(y))], 1-based in the reference
+    return g_low, g_high
+
+
+@pytest.mark.parametrize("m,g_low_ref", [(gb.KerrMetric(1.0, 0.6), 0.355), (gb.JohannsenPsaltisMetric(1.0, 0.6, 2.0), 0.27)])
+def test_binned_line_profile_edges(m, g_low_ref):
+    u, d, plane, bins = _binning_fixture(m)
+    cfg = tracing_configuration(m, u, plane, d, (0.0, 2000.0), callback=gb.domain_upper_hemisphere())
+    p, ic = cfg.to_c()
+    emis = cabi.Emissivity(cabi.EMISSIVITY_POWERLAW, 0, 3.0, None, None)
+    y = oracle.lineprofile(p, ic, emis, bins, cabi.LineProfileOpts(gb.isco(m), 50.0, 1, 1))
+    g_low, g_high = _edges(bins, y)
+    assert g_low == pytest.approx(g_low_ref, abs=0.05)   # test-binning.jl:25,50
+    assert g_high == pytest.approx(1.2, abs=0.05)        # :29,54
+    assert y.sum() == pytest.approx(1.0, abs=1e-12)      # :32,57
