@@ -101,3 +101,19 @@ def test_band_ratio_is_consistent_with_statuses():
     hit = ep.status == cabi.STATUS_INTERSECTED
     assert not np.any(hit & (ratio == 0))       # a detected hit implies the transparent ray enters the disc region
     assert not np.any(~hit & (ratio > 1.3) & (ep.status != cabi.STATUS_WITHIN_INNER_BOUNDARY))  # long passages are never missed
+
+
+def test_oracle_matches_frozen_vectors():
+    """tests/golden/oracle_small.npz (made by tests/golden/make_golden.py once the oracle was pinned to the reference)."""
+    import os
+
+    from common import c5
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_small.npz"))
+    for name, cfg in [("c1_24x24", c1(24, 24)[3]), ("c3_20x20", c3(20, 20)[4]), ("c5_20x20", c5(20, 20)[3])]:
+        p, ic = cfg.to_c()
+        imgs, ep = oracle.render(p, ic, [cabi.PF_REDSHIFT, cabi.PF_DISC_RADIUS], endpoints=True, nthreads=2)
+        assert np.array_equal(ep.status, gold[name + "_status"]) and np.array_equal(ep.naccept, gold[name + "_naccept"])
+        assert np.allclose(ep.x, gold[name + "_x"], rtol=1e-12, atol=1e-12) and np.allclose(ep.v, gold[name + "_v"], rtol=1e-12, atol=1e-12)
+        assert np.allclose(imgs[0], gold[name + "_redshift"], rtol=1e-12, atol=0, equal_nan=True)
+        assert np.allclose(imgs[1], gold[name + "_radius"], rtol=1e-12, atol=0, equal_nan=True)
