@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
     double nct = 0, nr = 0, nth = 0, nph = 0, nvt = 0, nvr = 0, nvth = 0, nvph = 0; // u (proposed / final)
     double kA0[7], kA1[7], kA2[7], kA3[7]; // accelerations: [0] = FSAL k1, [1..5] = k2..k6, [6] = k7
     double kR[6], kT[6];                   // stage velocities v^r, v^theta of k2..k6 ([0] unused: k1's are vr, vth)
-    double dt = 0, dt_step = 0, qoldpow = 1, cprev = 1, acos_prev = 1, ev_lo = 0, ev_hi = 0;
+    double dt = 0, dt_step = 0, cprev = 1, acos_prev = 1, ev_lo = 0, ev_hi = 0;
+    double qoldpow = 1; // controller memory: beta2 * log(qold) (POW_EXACT) or qold^beta2 (POW_FAST32)
     double tfinal = 0;
     double E_obs = 0, area = 1; // per-ray constants fixed at refill (redshift numerator, image-plane area weight)
     int state = LANE_EMPTY, pend_status = GB200_STATUS_NO_STATUS;
@@ -138,9 +139,9 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
 #endif
     for (;;) {
 #if GB_BLOCK_SYNC
-        // One barrier per step attempt: the warps of a CTA walk the (long, straight-line) step code together and
-        // share its instruction-cache lines, and the decision to run the cold service code is CTA-uniform, so that
-        // code is fetched once per CTA instead of once per warp.
+        // A barrier every GB_SYNC_EVERY-th step attempt: the warps of a CTA walk the (long, straight-line) step code
+        // together and share its instruction-cache lines, and the decision to run the cold service code is CTA-uniform,
+        // so that code is fetched once per CTA instead of once per warp.
         bool service = false;
         if (GB_SYNC_EVERY == 1 || (loop_count++ % GB_SYNC_EVERY) == 0) {
             const int idle_cta = __syncthreads_count(state != LANE_RUN);
