@@ -19,6 +19,7 @@ from .api import (  # noqa: F401
     EnsembleB200,
     EnsembleEndpointThreads,
     GeodesicPoints,
+    ImpactParameters,
     GeometricGrid,
     InverseGrid,
     JohannsenPsaltisMetric,
@@ -32,6 +33,7 @@ from .api import (  # noqa: F401
     TabulatedEmissivity,
     ThinDisc,
     TracingConfiguration,
+    apply_point_functions,
     chart_for_metric,
     domain_upper_hemisphere,
     impact_axes,
@@ -45,5 +47,14 @@ from .api import (  # noqa: F401
     tracing_configuration,
 )
 from ._cabi import GradusB200Error  # noqa: F401
+from .transfer_functions import (  # noqa: F401
+    CunninghamTransferData,
+    DeviceProber,
+    TransferFunctionSetup,
+    cunningham_transfer_function,
+    cunningham_transfer_functions,
+    find_offset_for_radius,
+    jacobian_ab_gr,
+)
 
 __version__ = "0.1.0"

@@ -194,6 +194,17 @@ class CartesianPlane:
         return (2 * (self.Ny // 2) - 1) * (2 * (self.Nx // 2) - 1)
 
 
+@dataclass(frozen=True, eq=False)
+class ImpactParameters:
+    """`map_impact_parameters(m, x, αs, βs)` (src/tracing/utility.jl:70-87) as data: one ray per (α, β) pair."""
+
+    alpha: Any
+    beta: Any
+
+    def trajectory_count(self):
+        return len(self.alpha)
+
+
 @dataclass(frozen=True)
 class RenderGrid:
     """The closure returned by `_render_velocity_function` (src/rendering/rendering.jl:140-163) as data."""
@@ -330,6 +341,16 @@ class TracingConfiguration:
             ic.lo0, ic.hi0 = float(v.r_min), float(v.r_max)
             ic.lo1, ic.hi1 = float(v.theta_min), float(v.theta_max)
             ic.n = v.trajectory_count()
+        elif isinstance(v, ImpactParameters):
+            al = np.ascontiguousarray(v.alpha, np.float64)
+            be = np.ascontiguousarray(v.beta, np.float64)
+            if al.shape != be.shape or al.ndim != 1:
+                raise ValueError("alpha and beta must be 1-D arrays of equal length")
+            self._keep = [al, be]
+            p.observer[:] = pos
+            ic.kind = cabi.IC_IMPACT_PARAMETERS
+            ic.x[0], ic.x[1] = cabi.dptr(al), cabi.dptr(be)
+            ic.n = len(al)
         elif isinstance(v, CartesianPlane):
             p.observer[:] = pos
             ic.kind = cabi.IC_CARTESIAN_PLANE
@@ -644,6 +665,27 @@ def _pop_alias(kwargs, names, default):
     return default
 
 
+def apply_point_functions(config, pfs, plunging=None):
+    """Trace every ray of `config` and evaluate the point functions `pfs` at its endpoint in the same kernel
+    (the fused form of `apply(pf, rendergeodesics(...))`, src/rendering/rendering.jl:64-107, for any velocity source
+    including `ImpactParameters`).  Returns an array of shape (len(pfs), n_rays)."""
+    kinds = np.array([f.kind() for f in pfs], np.int32)
+    p, ic = config.to_c()
+    n = ic.n
+    images = np.zeros((len(pfs), n))
+    lib = cabi.load()
+    plunging = _auto_plunging(config.metric, config.geometry, config.ensemble, cabi.PF_REDSHIFT in kinds, plunging)
+    pl_ref = C.byref(plunging.c) if plunging is not None else None
+
+    def fn(ctx, first, count, slot):
+        ptrs = (cabi._dp * len(pfs))(*[C.cast(images[k].ctypes.data + 8 * first, cabi._dp) for k in range(len(pfs))])
+        rng = cabi.Range(first, count, 1)
+        cabi.check(lib.gb200_render(ctx, C.byref(p), C.byref(ic), C.byref(rng), cabi.iptr(kinds), len(pfs), pl_ref, ptrs), ctx)
+
+    _run_sharded(config.ensemble, n, fn)
+    return images
+
+
 def rendergeodesics(m, position, *args, pf=None, image_width=375, image_height=250, ensemble=None, plunging=None, **kwargs):
     """`rendergeodesics(m, x, [d], λ_max; pf, image_width, image_height, αlims, βlims, ensemble, ...)`
     (src/rendering/rendering.jl:28-54).  Returns (α, β, image) with image of shape (H, W).
@@ -655,20 +697,7 @@ def rendergeodesics(m, position, *args, pf=None, image_width=375, image_height=2
     config = tracing_configuration(m, position, velocity, *args, ensemble=ensemble,
                                    trajectories=image_width * image_height, **kwargs)
     pfs = [ConstPointFunctions.shadow()] if pf is None else (list(pf) if isinstance(pf, (list, tuple)) else [pf])
-    kinds = np.array([f.kind() for f in pfs], np.int32)
-    p, ic = config.to_c()
-    n = ic.n
-    images = np.zeros((len(pfs), n))
-    lib = cabi.load()
-    plunging = _auto_plunging(m, config.geometry, config.ensemble, cabi.PF_REDSHIFT in kinds, plunging)
-    pl_ref = C.byref(plunging.c) if plunging is not None else None
-
-    def fn(ctx, first, count, slot):
-        ptrs = (cabi._dp * len(pfs))(*[C.cast(images[k].ctypes.data + 8 * first, cabi._dp) for k in range(len(pfs))])
-        rng = cabi.Range(first, count, 1)
-        cabi.check(lib.gb200_render(ctx, C.byref(p), C.byref(ic), C.byref(rng), cabi.iptr(kinds), len(pfs), pl_ref, ptrs), ctx)
-
-    _run_sharded(config.ensemble, n, fn)
+    images = apply_point_functions(config, pfs, plunging=plunging)
     alpha, beta = impact_axes(image_width, image_height, alpha_lims, beta_lims)
     imgs = [images[k].reshape(image_width, image_height).T for k in range(len(pfs))]  # column-major (H, W)
     return (alpha, beta, imgs[0]) if not isinstance(pf, (list, tuple)) else (alpha, beta, imgs)

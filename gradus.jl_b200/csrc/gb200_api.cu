@@ -152,6 +152,8 @@ static int validate(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic) 
         if (!(ic->hi0 > ic->lo0) || !(ic->hi1 > ic->lo1)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "CartesianPlane needs x_min < x_max, y_min < y_max");
         if (ic->grid_kind != GB200_GRID_LINEAR && (!(ic->lo0 > 0) || !(ic->lo1 > 0))) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "geometric / inverse grids need positive minima");
         if (ic->n != (2 * (ic->height / 2) - 1) * (2 * (ic->width / 2) - 1)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "ic.n != (2(Ny/2)-1)(2(Nx/2)-1)");
+    } else if (ic->kind == GB200_IC_IMPACT_PARAMETERS) {
+        if (ic->n < 1 || !ic->x[0] || !ic->x[1]) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "impact-parameter IC needs n >= 1 and alpha / beta arrays");
     } else if (ic->kind == GB200_IC_EXPLICIT) {
         if (ic->n < 1) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "explicit IC needs n >= 1");
         for (int k = 0; k < 4; ++k)
@@ -238,7 +240,7 @@ static void fill_params(const gb200_problem* p, const gb200_ic* ic, const gb200_
     P.block = rg->block > 0 ? rg->block : 1;
     // 2-D tiled work order when the range is made of whole strips of GB_TILE_C image columns (or theta-rows of the plane)
     P.tile_h = 0;
-    if (ic->kind != GB200_IC_EXPLICIT && !getenv("GB200_NO_TILING")) {
+    if (ic->kind != GB200_IC_EXPLICIT && ic->kind != GB200_IC_IMPACT_PARAMETERS && !getenv("GB200_NO_TILING")) {
         const int64_t h = (ic->kind == GB200_IC_RENDER_GRID) ? ic->height
                         : (ic->kind == GB200_IC_CARTESIAN_PLANE) ? (2 * (ic->height / 2) - 1) : ic->width; // fastest-varying extent of the ray index
         const int64_t strip = GB_TILE_C * h;
@@ -276,6 +278,13 @@ static int upload(gb200_ctx* ctx, size_t slot, const void* host, size_t bytes, c
 }
 
 static int upload_ic_and_tables(gb200_ctx* ctx, const gb200_ic* ic, const gb200_plunging_table* pl, const gb200_emissivity* em, GbParams& P) {
+    if (ic->kind == GB200_IC_IMPACT_PARAMETERS) {
+        for (int k = 0; k < 2; ++k) {
+            const void* d;
+            int rc = upload(ctx, SL_EX0 + k, ic->x[k], sizeof(double) * ic->n, &d); if (rc) return rc;
+            P.ex[k] = (const double*)d;
+        }
+    }
     if (ic->kind == GB200_IC_EXPLICIT) {
         for (int k = 0; k < 4; ++k) {
             const void* d;
@@ -475,6 +484,7 @@ int gb200_trace_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* probl
     for (int b = 0; b < nbatch; ++b) {
         int rc = validate(ctx, &problems[b], &ics[b]); if (rc) return rc;
         rc = validate_range(ctx, &ics[b], &ranges[b]); if (rc) return rc;
+        if (ics[b].kind == GB200_IC_IMPACT_PARAMETERS) return fail(ctx, GB200_ERR_UNSUPPORTED, "impact-parameter lists are not batched; use gb200_trace / gb200_render");
     }
     CU(ctx, cudaSetDevice(ctx->device));
     ctx->stats = gb200_stats{};

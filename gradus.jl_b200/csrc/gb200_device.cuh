@@ -581,7 +581,10 @@ GB_HD inline void ray_initial_state(const GbParams& P, int64_t i, GbRayInit& o) 
         return;
     }
     double alpha, beta;
-    if (P.ic_kind == GB200_IC_CARTESIAN_PLANE) { // planes.jl:152-171: grids mirrored about their first point
+    if (P.ic_kind == GB200_IC_IMPACT_PARAMETERS) { // explicit (alpha, beta) lists: ex[0] = alpha, ex[1] = beta
+        alpha = P.ex[0][i];
+        beta = P.ex[1][i];
+    } else if (P.ic_kind == GB200_IC_CARTESIAN_PLANE) { // planes.jl:152-171: grids mirrored about their first point
         const int64_t rows = 2 * P.n1 - 1;
         const int64_t col = i / rows, row = i - col * rows;
         const int64_t ka = (col < P.n0 - 1) ? (P.n0 - 1 - col) : (col - (P.n0 - 1));

@@ -98,6 +98,8 @@ typedef struct gb200_problem {
 #define GB200_IC_POLAR_PLANE 1 /* PolarPlane + promote_velfunc, src/image-planes/planes.jl:70-115,180-184 */
 #define GB200_IC_EXPLICIT 2    /* prob_func evaluated on the host into SoA (corona ensembles) */
 #define GB200_IC_CARTESIAN_PLANE 3 /* CartesianPlane, src/image-planes/planes.jl:130-178 */
+#define GB200_IC_IMPACT_PARAMETERS 4 /* map_impact_parameters(m, x, alphas, betas), src/tracing/utility.jl:70-87:
+                                        x[0] = alpha[n], x[1] = beta[n] (host arrays); observer = problem.observer */
 
 #define GB200_GRID_LINEAR 0    /* src/image-planes/grids.jl:32-36 */
 #define GB200_GRID_GEOMETRIC 1 /* grids.jl:11-20 */

@@ -384,6 +384,9 @@ static void ic_for_ray(const gb200_problem& p, const gb200_ic& ic, int64_t i, Ra
         out.alpha = r * std::cos(th);
         out.beta = r * std::sin(th);
         out.area = r * r;
+    } else if (ic.kind == GB200_IC_IMPACT_PARAMETERS) { // map_impact_parameters over (alpha, beta) lists, utility.jl:70-87
+        out.alpha = ic.x[0][i];
+        out.beta = ic.x[1][i];
     } else if (ic.kind == GB200_IC_CARTESIAN_PLANE) { // planes.jl:152-171
         int64_t hx = ic.width / 2, hy = ic.height / 2;
         int64_t rows = 2 * hy - 1; // X_size

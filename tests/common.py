@@ -40,3 +40,13 @@ def c5(w=64, h=64, a=0.6, eps3=2.0, ensemble=None, inner=None):
 
 def rel_err(a, b):
     return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+class OracleProber(gb.DeviceProber):
+    """The transfer-function orchestration's tracer with the CPU oracle in place of the device (tests only)."""
+
+    def evaluate(self, config):
+        from oracle import oracle
+        p, ic = config.to_c()
+        kinds = [f.kind() for f in self.pfs]
+        return oracle.render(p, ic, kinds, plunging=None)
