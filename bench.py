@@ -291,7 +291,7 @@ def run_lineprofile(args, rank, world, local, ens, dev, stream, sptr):
     rng = gd.strip_interleaved_range(ic, rank, world)
     bins = np.ascontiguousarray(np.linspace(0.1, 1.5, 180))
     emis = cabi.Emissivity(cabi.EMISSIVITY_POWERLAW, 0, 3.0, None, None)
-    opts = cabi.LineProfileOpts(gb.isco(m), 50.0, 0, 1)
+    opts = cabi.LineProfileOpts(gb.isco(m), 50.0, 0, 0)
     d_flux = torch.zeros(len(bins), dtype=torch.float64, device=dev)
 
     def step():

@@ -718,7 +718,7 @@ class TabulatedEmissivity:
 
 
 def lineprofile(bins, emissivity, m, position, d, method=None, *, lambda_max=None, min_re=None, max_re=50.0,
-                plane=None, callback="default", ensemble=None, bin_right_closed=True, plunging=None, **solver_args):
+                plane=None, callback="default", ensemble=None, bin_right_closed=False, plunging=None, **solver_args):
     """`lineprofile(bins, ε, m, u, d, ::BinningMethod; λ_max, minrₑ, maxrₑ, plane, callback, ...)`
     (src/line-profiles.jl:152-198).  Returns (bins, flux ./ sum(flux))."""
     if method is not None and not isinstance(method, BinningMethod):

@@ -1,0 +1,161 @@
+"""Host-side (numpy, vectorised) metric algebra needed by the post-processing around the traced endpoints: metric
+components, tetrads, circular-orbit four-velocities, LNRF velocities.  None of this is the hot path (it is evaluated a
+few hundred times per call, at source positions and disc hits), it only has to agree with the reference's formulas:
+
+    metric components       src/metrics/kerr-metric.jl:4-30, src/metrics/johannsen-psaltis-ad.jl:4-26
+    tetradframe             src/orthonormalization.jl:36-105
+    lnrbasis                src/orthonormalization.jl:116-123
+    CircularOrbits          src/orbits/circular-orbits.jl:10-130
+    local_velocity, lorentz_factor   src/corona/flux-calculations.jl:13-36
+
+All functions accept numpy arrays for r (complex allowed: the radial metric derivative is taken by a complex step,
+which is exact to rounding for these rational metrics)."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import api
+
+
+def metric_components(m, r, theta):
+    """(g_tt, g_rr, g_θθ, g_φφ, g_tφ), each broadcast over r, θ."""
+    r = np.asarray(r)
+    theta = np.asarray(theta, np.float64)
+    M, a = m.M, m.a
+    c2 = np.cos(theta) ** 2
+    s2 = np.sin(theta) ** 2
+    sigma = r * r + a * a * c2
+    delta = r * r - 2 * M * r + a * a
+    if isinstance(m, api.KerrMetric):
+        tt = -(1 - 2 * M * r / sigma)
+        rr = sigma / delta
+        thth = sigma + 0 * r
+        phph = s2 * (r * r + a * a + 2 * M * a * a * r * s2 / sigma)
+        tph = -2 * M * a * r * s2 / sigma
+    elif isinstance(m, api.JohannsenPsaltisMetric):
+        h = m.eps3 * M**3 * r / sigma**2
+        tt = -(1 + h) * (1 - 2 * M * r / sigma)
+        rr = sigma * (1 + h) / (delta + a * a * s2 * h)
+        thth = sigma + 0 * r
+        phph = s2 * (r * r + a * a + 2 * a * a * M * r * s2 / sigma) + h * a * a * (sigma + 2 * M * r) * s2 * s2 / sigma
+        tph = -2 * a * M * r * s2 * (1 + h) / sigma
+    else:
+        raise ValueError(f"metric {type(m).__name__} is outside the B200 scope")
+    return np.stack(np.broadcast_arrays(tt, rr, thth, phph, tph))
+
+
+def metric_dr(m, r, theta, h=1e-30):
+    """∂g/∂r of the five components (complex step)."""
+    r = np.asarray(r, np.float64)
+    return np.imag(metric_components(m, r + 1j * h, theta)) / h
+
+
+def metric_matrix(g):
+    """4×4 matrix (…, 4, 4) from components (5, …)."""
+    g = np.asarray(g)
+    out = np.zeros(g.shape[1:] + (4, 4), g.dtype)
+    out[..., 0, 0], out[..., 1, 1], out[..., 2, 2], out[..., 3, 3] = g[0], g[1], g[2], g[3]
+    out[..., 0, 3] = out[..., 3, 0] = g[4]
+    return out
+
+
+def inverse_metric_components(g):
+    d = g[0] * g[3] - g[4] * g[4]
+    return np.stack([g[3] / d, 1 / g[1], 1 / g[2], g[0] / d, -g[4] / d])
+
+
+def dot(g, u, v):
+    """g_{μν} u^μ v^ν with components g (5, …) and vectors (4, …)."""
+    return (g[0] * u[0] * v[0] + g[1] * u[1] * v[1] + g[2] * u[2] * v[2] + g[3] * u[3] * v[3]
+            + g[4] * (u[0] * v[3] + u[3] * v[0]))
+
+
+def circular_fourvelocity(m, r, contra_rotating=False):
+    """CircularOrbits.fourvelocity(m, r) in the equatorial plane: (u^t, 0, 0, u^φ) (circular-orbits.jl:10-130)."""
+    r = np.asarray(r, np.float64)
+    th = np.pi / 2
+    dg = metric_dr(m, r, th)
+    disc = np.sqrt(dg[4] ** 2 - dg[0] * dg[3])
+    omega = -(dg[4] + disc) / dg[3] if contra_rotating else -(dg[4] - disc) / dg[3]
+    gi = inverse_metric_components(metric_components(m, r, th))
+    A = -(omega * gi[0] - gi[4])
+    B = omega * gi[4] - gi[3]
+    den = B * B * gi[0] + 2 * A * B * gi[4] + A * A * gi[3]
+    d = -np.sign(den) * np.sqrt(1 / np.abs(den))
+    ut_lo, uph_lo = B * d, A * d
+    vt = gi[0] * ut_lo + gi[4] * uph_lo
+    vph = gi[4] * ut_lo + gi[3] * uph_lo
+    z = np.zeros_like(vt)
+    return np.stack([vt, z, z, vph])
+
+
+def _gram_schmidt(start, basis, G):
+    v = start.astype(np.float64)
+    for _ in range(2):  # second pass = re-orthogonalisation (the reference loops until the projection is below 4 eps)
+        for e in basis:
+            v = v - (v @ G @ e) / (e @ G @ e) * e
+    return v / np.sqrt(abs(v @ G @ v))
+
+
+def _searchsortedfirst(v, x):
+    """Julia's binary search, 1-based result, also on the unsorted masks `tetradframe` feeds it."""
+    lo, hi = 0, len(v) + 1
+    while lo < hi - 1:
+        mid = (lo + hi) >> 1
+        if v[mid - 1] < x:
+            lo = mid
+        else:
+            hi = mid
+    return hi
+
+
+def _permute(x):
+    return (x[0], x[3], x[1], x[2])
+
+
+def tetradframe(G, v):
+    """Gram–Schmidt tetrad whose first leg is v/|v|, returned in coordinate order (t, r, θ, φ)
+    (orthonormalization.jl:75-103).  G: 4×4 metric, v: 4-vector.  Like the reference's, the construction needs a
+    velocity with at least one vanishing spatial component (its start vectors are the occupancy masks of v)."""
+    G = np.asarray(G, np.float64)
+    v = np.asarray(v, np.float64)
+    v1 = v / np.sqrt(abs(v @ G @ v))
+    state = tuple(bool(c != 0) for c in v1)
+    if sum(state) == 1:
+        state = (True, False, False, True)
+    permutations = _searchsortedfirst(state[1:], True)
+    v2 = _gram_schmidt(np.array(state, float), (v1,), G)
+    state = tuple(a or b for a, b in zip(state, _permute(state)))
+    v3 = _gram_schmidt(np.array(state, float), (v1, v2), G)
+    state = tuple(a or b for a, b in zip(state, _permute(state)))
+    v4 = _gram_schmidt(np.array(state, float), (v1, v2, v3), G)
+    ret = (v1, v2, v3, v4)
+    for _ in range(2, permutations + 1):
+        ret = _permute(ret)
+    return ret
+
+
+def tetradframe_matrix(m, x, v):
+    """Columns = tetrad legs (t, r, θ, φ)."""
+    G = metric_matrix(metric_components(m, x[1], x[2]))
+    return np.stack(tetradframe(G, v), axis=1)
+
+
+def lnr_velocity_phi(m, r, theta, v):
+    """𝒱^(φ) = v·e^(φ) / v·e^(t) in the locally non-rotating frame (Bardeen+73 3.9; flux-calculations.jl:13-18),
+    closed form of the ZAMO co-basis: e^(t) = N dt, e^(φ) = √g_φφ (dφ − ω dt)."""
+    g = metric_components(m, r, theta)
+    omega = -g[4] / g[3]
+    N = np.sqrt(-(g[0] - g[4] ** 2 / g[3]))  # lapse: −1/g^tt = −(g_tt − g_tφ²/g_φφ)
+    return np.sqrt(g[3]) * (v[3] - omega * v[0]) / (N * v[0])
+
+
+def lorentz_factor(m, r, theta, v):
+    """flux-calculations.jl:32-35"""
+    return 1.0 / np.sqrt(1.0 - lnr_velocity_phi(m, r, theta, v) ** 2)
+
+
+def proper_area(m, r, theta):
+    """`_proper_area`, corona/emissivity.jl:170-174: 2π √(g_rr g_φφ)"""
+    g = metric_components(m, r, theta)
+    return 2 * np.pi * np.sqrt(g[1] * g[3])

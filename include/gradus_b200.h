@@ -183,7 +183,9 @@ typedef struct gb200_lineprofile_opts {
     double min_re;  /* minr_e, default isco(m)  (src/line-profiles.jl:163) */
     double max_re;  /* maxr_e, default 50 */
     int32_t normalise; /* 1: flux ./ sum(flux) (line-profiles.jl:197); 0: raw partial sums (multi-rank) */
-    int32_t bin_right_closed; /* 1: index = searchsortedfirst(bins, g) clamped (default); 0: searchsortedlast */
+    int32_t bin_right_closed; /* 0 (Buckets.Simple): slot i takes bins[i] <= g < bins[i+1], i.e. searchsortedlast, clamped to the
+                                 ends -- the convention that reproduces test/unit/emissivity.jl:31-42 to 1e-11;
+                                 1: bins[i-1] < g <= bins[i] (searchsortedfirst), kept for callers that label bins by their upper edge */
 } gb200_lineprofile_opts;
 
 /* Timing / counters of the last call on a context. */

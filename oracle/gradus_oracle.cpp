@@ -847,7 +847,9 @@ static double emissivity_at(const gb200_emissivity& e, double r) {
     double w = (x - e.r[idx]) / (e.r[idx + 1] - e.r[idx]);
     return (1 - w) * e.eps[idx] + w * e.eps[idx + 1];
 }
-// Buckets.Simple convention (un-vendored; parity unpinned): searchsortedfirst / searchsortedlast, clamped to [1, n]
+// Buckets.Simple convention (un-vendored): slot i takes bins[i] <= g < bins[i+1] (searchsortedlast, clamped to [1, n]),
+// right_closed = 0.  Pinned through the reference's radial-profile literals (test/unit/emissivity.jl:31-42), which use the
+// same `Simple` bucketing and are reproduced to 1e-11 with this convention and off by 2x with the other.
 static int bin_index(const double* bins, int nbins, double g, int right_closed) {
     int idx;
     if (right_closed) idx = (int)(std::lower_bound(bins, bins + nbins, g) - bins);       // searchsortedfirst - 1

@@ -50,3 +50,46 @@ class OracleProber(gb.DeviceProber):
         p, ic = config.to_c()
         kinds = [f.kind() for f in self.pfs]
         return oracle.render(p, ic, kinds, plunging=None)
+
+
+def oracle_plunging_table(kind, mp):
+    """interpolate_plunging_velocities (src/orbits/orbit-solving.jl:137-167) restated with the oracle's pieces."""
+    risco = _oracle().isco(kind, mp)
+    g, dr, _ = _oracle().metric(kind, mp, risco, math.pi / 2)
+    D = g[0] * g[3] - g[4] ** 2
+    gitt, giphph, gitph = g[3] / D, g[0] / D, -g[4] / D
+    v = _oracle().circular_fourvelocity(kind, mp, risco)
+    E = _oracle().circular_energy(kind, mp, risco)
+    ut = -E
+    uph = (v[3] - gitph * ut) / giphph  # v^phi = g^tphi u_t + g^phiphi u_phi
+    nom = gitt * E * E - 2 * gitph * E * uph + giphph * uph * uph + 1
+    vr = -math.sqrt(abs(nom / (-g[1])))
+    p = cabi.Problem()
+    p.metric_kind = kind
+    p.metric_params[:] = list(mp) + [0.0] * (4 - len(mp))
+    p.mu, p.abstol, p.reltol, p.lambda_min, p.lambda_max, p.gtol = 1.0, 1e-9, 1e-9, 0.0, 50000.0, 1e-2
+    p.chart_inner = (mp[0] + math.sqrt(mp[0] ** 2 - mp[1] ** 2)) * 1.000001
+    p.chart_outer = 12000.0
+    u0 = np.array([0.0, risco - 1e-8, math.pi / 2, 0.0, v[0], vr, 0.0, v[3]])
+    g0, _, _ = _oracle().metric(kind, mp, u0[1], u0[2])
+    disc = -g0[0] * g0[1] * vr**2 - g0[0] - (g0[0] * g0[3] - g0[4] ** 2) * v[3] ** 2  # constrain_time, mu = 1
+    u0[4] = -(g0[4] * v[3] + math.sqrt(disc)) / g0[0]
+    t, dt, ee, u = _oracle().trace_path(p, u0, cap=1 << 20)
+    u = np.vstack([u0, u])
+    order = np.argsort(u[:, 1], kind="stable")[1:]
+    return u[order, 1], u[order, 4], u[order, 5], u[order, 7]
+
+
+def _oracle():
+    from oracle import oracle
+    return oracle
+
+
+def oracle_solver(configs):
+    """A list of TracingConfigurations traced by the CPU oracle (tests only): stands in for the device solver."""
+    from gradus_b200 import api
+    out = []
+    for config in configs:
+        p, ic = config.to_c()
+        out.append(api.GeodesicPoints(_oracle().trace(p, ic), config.lambda_domain[0]))
+    return out

@@ -1,0 +1,157 @@
+"""Coronal emissivity profiles: host post-processing pinned on the CPU with the oracle as tracer against
+the reference's literals (test/unit/emissivity.jl:9-42), then the product path (device tracer) against the same literals
+and against the oracle-traced profile.
+
+The second literal set is reproduced to 1e-11 (the reference quotes rtol 1e-2): besides the energy ratio, Lorentz factor
+and proper area this pins the `Buckets.Simple` convention (slot i takes bins[i] ≤ v < bins[i+1]) that the line-profile
+histogram shares — with the other convention the values are off by factors of 1.4–9."""
+import math
+
+import numpy as np
+import pytest
+
+import gradus_b200 as gb
+from gradus_b200 import _cabi as cabi
+from gradus_b200 import api, corona, hostmath
+
+import common
+from oracle import oracle
+
+POINT_SOURCE_LITERALS = np.array([
+    0.0029464479567890534, 0.0014052519492578114, 0.0008963679521766861, 0.0005749351642563003, 0.0003386885861792927,
+    0.0001703542742784169, 6.482839568020104e-5, 1.3029008103481133e-5, 3.432060732289487e-6])
+SAMPLED_SKY_LITERALS = np.array([
+    1.4346387869787864, 3.0822515234888774, 1.7923604648828981, 0.6016959946033558, 0.11910008907351012,
+    0.017392602799041507, 0.0023309504405384547, 0.0003139154565507922, 3.665392374360994e-5, 1.2069687133228597e-6])
+
+
+def fixture():
+    return gb.KerrMetric(1.0, 0.998), gb.ThinDisc(0.0, 500.0), corona.LampPostModel(h=10.0)
+
+
+@pytest.fixture
+def oracle_plunging_kerr():
+    m = gb.KerrMetric(1.0, 0.998)
+    key = (type(m).__name__, m.params())
+    saved = api._PLUNGING_CACHE.get(key)
+    api._PLUNGING_CACHE[key] = api.PlungingInterpolation(*common.oracle_plunging_table(cabi.METRIC_KERR, [1.0, 0.998]))
+    yield
+    if saved is None:
+        api._PLUNGING_CACHE.pop(key, None)
+    else:
+        api._PLUNGING_CACHE[key] = saved
+
+
+# --------------------------------------------------------------------------- host algebra vs the oracle's restatement
+@pytest.mark.parametrize("m", [gb.KerrMetric(1.0, 0.998), gb.KerrMetric(1.0, -0.4), gb.JohannsenPsaltisMetric(1.0, 0.6, 2.0)])
+def test_host_metric_and_circular_orbits_match_the_oracle(m):
+    mp = list(m.params())
+    for r, th in [(3.0, 0.3), (10.0, 1.2), (1.9, math.pi / 2), (400.0, 2.5)]:
+        g, dr, _ = oracle.metric(m.kind, mp, r, th)
+        assert np.allclose(hostmath.metric_components(m, r, th), g, rtol=1e-13, atol=0)
+        assert np.allclose(hostmath.metric_dr(m, r, th), dr, rtol=1e-12, atol=1e-300)
+    for r in (api.isco(m) * 1.0001, 6.0, 57.0):
+        v = oracle.circular_fourvelocity(m.kind, mp, r)
+        assert np.allclose(hostmath.circular_fourvelocity(m, r), v, rtol=1e-12, atol=0)
+
+
+def test_tetrad_is_orthonormal_and_ordered():
+    m = gb.KerrMetric(1.0, 0.9)
+    x = np.array([0.0, 7.0, 0.8, 0.3])
+    g = hostmath.metric_components(m, x[1], x[2])
+    G = hostmath.metric_matrix(g)
+    eta = np.diag([-1.0, 1.0, 1.0, 1.0])
+    for v in ([1.0, 0, 0, 0], [1.0, 0.1, 0.0, 0.0], [1.0, 0.0, 0.0, 0.05], [1.0, 0.0, 0.02, 0.0]):
+        v = np.array(v)
+        v = v / math.sqrt(-hostmath.dot(g, v, v))
+        B = np.stack(hostmath.tetradframe(G, v), axis=1)
+        assert np.allclose(B.T @ G @ B, eta, atol=1e-13)
+        assert np.allclose(B[:, 0], v)
+        # legs point along +r, +θ, +φ
+        assert B[1, 1] > 0 and B[2, 2] > 0 and B[3, 3] > 0
+    # static source: the closed form e_r = ∂_r/√g_rr, e_θ = ∂_θ/√g_θθ, e_φ ∝ (−g_tφ/g_tt, 0, 0, 1)
+    v = np.array([1 / math.sqrt(-g[0]), 0, 0, 0])
+    B = np.stack(hostmath.tetradframe(G, v), axis=1)
+    assert np.allclose(B[:, 1], [0, 1 / math.sqrt(g[1]), 0, 0], atol=1e-14)
+    assert np.allclose(B[:, 2], [0, 0, 1 / math.sqrt(g[2]), 0], atol=1e-14)
+    assert abs(B[0, 3] / B[3, 3] + g[4] / g[0]) < 1e-13
+
+
+def test_sky_velocities_are_null_and_unit_energy():
+    m, _, model = fixture()
+    x, v_src = corona.sample_position_velocity(m, model)
+    elev, azim = corona.EvenSampler("both", "golden").angles(64)
+    vs = corona.sky_angles_to_velocity(m, x, v_src, elev, azim)
+    g = hostmath.metric_components(m, x[1], x[2])
+    assert np.max(np.abs(hostmath.dot(g, vs, vs))) < 1e-12
+    assert np.allclose(hostmath.dot(g, vs, v_src[:, None]), -1.0, atol=1e-13)  # E₀ = 1 in the source frame
+
+
+def test_even_sampler_follows_the_reference_quirks():
+    th, ph = corona.EvenSampler("both", "golden").angles(10)
+    assert np.allclose(th, np.arccos(1 - 2 * np.arange(1, 11) / 10)) and th[-1] == math.pi
+    assert np.allclose(ph, np.mod(math.pi * (1 + math.sqrt(5)) * np.arange(1, 11), 2 * math.pi))
+    th, ph = corona.EvenSampler("lower", "even").angles(10)  # geti = i/N, then sample_elevation(i/N / N)
+    assert np.allclose(th, np.arccos(1 - np.arange(1, 11) / 100)) and np.allclose(ph, np.mod(2 * math.pi * np.arange(1, 11) / 10, 2 * math.pi))
+
+
+# --------------------------------------------------------------------------- reference literals, oracle tracer
+def test_point_source_profile_literals_with_the_oracle_tracer():
+    m, d, model = fixture()
+    prof = corona.emissivity_profile(m, d, model, n_samples=20, solver=common.oracle_solver)
+    assert len(prof.radii) == 9 and np.all(np.diff(prof.radii) > 0)
+    assert np.max(np.abs(prof.eps - POINT_SOURCE_LITERALS)) < 1e-5  # the reference's own tolerance
+    # coordinate arrival time: grows outwards beyond the source height's footprint, Shapiro-delayed close to the hole
+    assert np.all(np.diff(prof.t[prof.radii > 6]) > 0) and prof.t[0] > prof.t[2]
+
+
+def test_sampled_sky_profile_literals_with_the_oracle_tracer(oracle_plunging_kerr):
+    m, d, model = fixture()
+    prof = corona.emissivity_profile(m, d, model, n_samples=1000, sampler=corona.EvenSampler("both", "golden"), N=10,
+                                     solver=common.oracle_solver)
+    # the innermost bin straddles the ISCO: its mean energy ratio uses the tabulated plunging flow (linear table)
+    assert abs(prof.eps[0] / SAMPLED_SKY_LITERALS[0] - 1) < 1e-3
+    assert np.max(np.abs(prof.eps[1:] / SAMPLED_SKY_LITERALS[1:] - 1)) < 1e-9
+
+
+def test_profile_feeds_the_line_profile_emissivity_table():
+    prof = corona.RadialDiscProfile(np.array([1.0, 2.0, 4.0]), np.array([3.0, 1.0, 0.5]), np.array([10.0, 11.0, 13.0]))
+    assert prof.emissivity_at(3.0) == 0.75 and prof.emissivity_at(0.5) == 3.0 and prof.coordtime_at(9.0) == 13.0
+    tab = prof.as_tabulated_emissivity()
+    assert isinstance(tab, gb.TabulatedEmissivity) and np.array_equal(tab.r, prof.radii)
+
+
+# --------------------------------------------------------------------------- device
+@pytest.mark.gpu
+def test_reference_literals_on_the_device():
+    m, d, model = fixture()
+    prof = corona.emissivity_profile(m, d, model, n_samples=20)
+    assert np.max(np.abs(prof.eps - POINT_SOURCE_LITERALS)) < 1e-5
+    prof = corona.emissivity_profile(m, d, model, n_samples=1000, sampler=corona.EvenSampler("both", "golden"), N=10)
+    assert abs(prof.eps[0] / SAMPLED_SKY_LITERALS[0] - 1) < 1e-3
+    assert np.max(np.abs(prof.eps[1:] / SAMPLED_SKY_LITERALS[1:] - 1)) < 1e-7
+
+
+@pytest.mark.gpu
+def test_device_profile_equals_oracle_profile_and_batches_are_independent():
+    models = [(gb.KerrMetric(1.0, a), gb.ThinDisc(0.0, 1000.0), corona.LampPostModel(h=h))
+              for a in (0.0, 0.9, 0.998) for h in (3.0, 10.0, 30.0)]
+    models.append((gb.JohannsenPsaltisMetric(1.0, 0.6, 2.0), gb.ThinDisc(0.0, 1000.0), corona.LampPostModel(h=8.0)))
+    batch = corona.emissivity_profiles(models, n_samples=1000)
+    for k in (0, 4, 8, 9):
+        single = corona.emissivity_profile(*models[k], n_samples=1000)
+        assert np.array_equal(single.radii, batch[k].radii) and np.array_equal(single.eps, batch[k].eps)
+    for k in (2, 5, 9):
+        m, d, model = models[k]
+        key = (type(m).__name__, m.params())
+        dev_table = api._PLUNGING_CACHE.get(key)
+        want = corona.emissivity_profiles([models[k]], n_samples=1000, solver=common.oracle_solver)[0]
+        got = batch[k]
+        # grazing rays may differ in termination class: compare on the common radii
+        assert abs(len(got.radii) - len(want.radii)) <= 2
+        if len(got.radii) == len(want.radii):
+            assert np.max(np.abs(got.radii / want.radii - 1)) < 1e-6
+            inner = slice(2, -2)  # ε_i uses neighbour differences of hit radii 1e-9-close to each other only in ratio
+            assert np.max(np.abs(got.eps[inner] / want.eps[inner] - 1)) < 1e-4
+            assert np.max(np.abs(got.t - want.t)) < 1e-5
+        assert dev_table is None or dev_table is api._PLUNGING_CACHE.get(key)

@@ -28,7 +28,7 @@ def _worker(rank, world, port, mode, q):
     p, ic = cfg.to_c()
     bins = np.linspace(0.1, 1.5, 40)
     emis = cabi.Emissivity(cabi.EMISSIVITY_POWERLAW, 0, 3.0, None, None)
-    opts = cabi.LineProfileOpts(gb.isco(m), 50.0, 0, 1)
+    opts = cabi.LineProfileOpts(gb.isco(m), 50.0, 0, 0)
     rng = gd.interleaved_range(ic.n, rank, world) if mode == "interleaved" else gd.block_range(ic.n, rank, world)
     partial = torch.from_numpy(oracle.lineprofile(p, ic, emis, bins, opts, rng=rng, nthreads=2))
     flux = gd.allreduce_histogram(partial)
@@ -60,7 +60,7 @@ def test_two_rank_line_profile_equals_single_rank(mode):
     p, ic = cfg.to_c()
     bins = np.linspace(0.1, 1.5, 40)
     emis = cabi.Emissivity(cabi.EMISSIVITY_POWERLAW, 0, 3.0, None, None)
-    opts = cabi.LineProfileOpts(gb.isco(m), 50.0, 1, 1)
+    opts = cabi.LineProfileOpts(gb.isco(m), 50.0, 1, 0)
     flux1 = oracle.lineprofile(p, ic, emis, bins, opts)
     assert total == ic.n and mx == 1.0
     assert flux2.sum() == pytest.approx(1.0, abs=1e-12)

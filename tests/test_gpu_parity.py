@@ -120,7 +120,7 @@ def test_c3_line_profile_plane(ensemble):
     bins = np.linspace(0.1, 1.5, 180)
     _, flux = gb.lineprofile(bins, gb.PowerLawEmissivity(3.0), m, x, d, gb.BinningMethod(), plane=plane, lambda_max=2000.0, ensemble=ensemble)
     emis = cabi.Emissivity(cabi.EMISSIVITY_POWERLAW, 0, 3.0, None, None)
-    want = oracle.lineprofile(p, ic, emis, bins, cabi.LineProfileOpts(gb.isco(m), 50.0, 1, 1))
+    want = oracle.lineprofile(p, ic, emis, bins, cabi.LineProfileOpts(gb.isco(m), 50.0, 1, 0))
     assert flux.sum() == pytest.approx(1.0, abs=1e-12)
     assert np.abs(flux - want).sum() < 1e-4  # L1, north_star tolerance
     # coarse features the reference's own test pins (test/line-profiles/test-binning.jl:24-29 analogue)
@@ -207,7 +207,7 @@ def test_reference_line_profile_edges_on_gpu(ensemble, m, g_low_ref):
     assert y.sum() == pytest.approx(1.0, abs=1e-12)
     cfg = tracing_configuration(m, u, plane, d, (0.0, 2000.0), callback=gb.domain_upper_hemisphere(), ensemble=ensemble)
     p, ic = cfg.to_c()
-    want = oracle.lineprofile(p, ic, cabi.Emissivity(cabi.EMISSIVITY_POWERLAW, 0, 3.0, None, None), bins, cabi.LineProfileOpts(gb.isco(m), 50.0, 1, 1))
+    want = oracle.lineprofile(p, ic, cabi.Emissivity(cabi.EMISSIVITY_POWERLAW, 0, 3.0, None, None), bins, cabi.LineProfileOpts(gb.isco(m), 50.0, 1, 0))
     # In this fixture the disc's inner edge IS the ISCO, so the handful of rays that graze that edge (grazing band)
     # carry the largest r^-3 g^3 weights of a 40 000-ray plane: L1 is band-limited here (the band-free C3 test requires 1e-4).
     assert np.abs(y - want).sum() < 5e-3
@@ -440,40 +440,12 @@ def test_in_process_sharding_over_contexts(ensemble):
         ens2.close()
 
 
-def _oracle_plunging_table(kind, mp):
-    """interpolate_plunging_velocities (src/orbits/orbit-solving.jl:137-167) restated with the oracle's pieces."""
-    risco = oracle.isco(kind, mp)
-    g, dr, _ = oracle.metric(kind, mp, risco, math.pi / 2)
-    D = g[0] * g[3] - g[4] ** 2
-    gitt, giphph, gitph = g[3] / D, g[0] / D, -g[4] / D
-    v = oracle.circular_fourvelocity(kind, mp, risco)
-    E = oracle.circular_energy(kind, mp, risco)
-    ut = -E
-    uph = (v[3] - gitph * ut) / giphph  # v^phi = g^tphi u_t + g^phiphi u_phi
-    nom = gitt * E * E - 2 * gitph * E * uph + giphph * uph * uph + 1
-    vr = -math.sqrt(abs(nom / (-g[1])))
-    p = cabi.Problem()
-    p.metric_kind = kind
-    p.metric_params[:] = list(mp) + [0.0] * (4 - len(mp))
-    p.mu, p.abstol, p.reltol, p.lambda_min, p.lambda_max, p.gtol = 1.0, 1e-9, 1e-9, 0.0, 50000.0, 1e-2
-    p.chart_inner = (mp[0] + math.sqrt(mp[0] ** 2 - mp[1] ** 2)) * 1.000001
-    p.chart_outer = 12000.0
-    u0 = np.array([0.0, risco - 1e-8, math.pi / 2, 0.0, v[0], vr, 0.0, v[3]])
-    g0, _, _ = oracle.metric(kind, mp, u0[1], u0[2])
-    disc = -g0[0] * g0[1] * vr**2 - g0[0] - (g0[0] * g0[3] - g0[4] ** 2) * v[3] ** 2  # constrain_time, mu = 1
-    u0[4] = -(g0[4] * v[3] + math.sqrt(disc)) / g0[0]
-    t, dt, ee, u = oracle.trace_path(p, u0, cap=1 << 20)
-    u = np.vstack([u0, u])
-    order = np.argsort(u[:, 1], kind="stable")[1:]
-    return u[order, 1], u[order, 4], u[order, 5], u[order, 7]
-
-
 def test_plunging_table_and_redshift_inside_isco(ensemble):
     """Non-Kerr redshift inside the ISCO (src/redshift.jl:246-276): table built on the device vs the oracle's."""
     m = gb.JohannsenPsaltisMetric(1.0, 0.6, 2.0)
     mp = (1.0, 0.6, 2.0)
     tab = gb.interpolate_plunging_velocities(m, ensemble)
-    r_o, ut_o, ur_o, uph_o = _oracle_plunging_table(cabi.METRIC_JP, mp)
+    r_o, ut_o, ur_o, uph_o = common.oracle_plunging_table(cabi.METRIC_JP, mp)
     risco = gb.isco(m)
     assert tab.r[0] == pytest.approx(r_o[0], rel=2e-2) and tab.r[-1] == pytest.approx(risco, abs=1e-6)
     # Two correct integrations sample the plunge at different radii, and the reference interpolates LINEARLY between

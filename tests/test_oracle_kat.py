@@ -170,7 +170,7 @@ def test_binned_line_profile_edges(m, g_low_ref):
     cfg = tracing_configuration(m, u, plane, d, (0.0, 2000.0), callback=gb.domain_upper_hemisphere())
     p, ic = cfg.to_c()
     emis = cabi.Emissivity(cabi.EMISSIVITY_POWERLAW, 0, 3.0, None, None)
-    y = oracle.lineprofile(p, ic, emis, bins, cabi.LineProfileOpts(gb.isco(m), 50.0, 1, 1))
+    y = oracle.lineprofile(p, ic, emis, bins, cabi.LineProfileOpts(gb.isco(m), 50.0, 1, 0))
     g_low, g_high = _edges(bins, y)
     assert g_low == pytest.approx(g_low_ref, abs=0.05)   # test-binning.jl:25,50
     assert g_high == pytest.approx(1.2, abs=0.05)        # :29,54
