@@ -268,7 +268,40 @@ def run_ours(args, rank, world, local):
     }
     if lp is not None:
         out["lineprofile"] = lp
+    if world == 1 and not args.no_callers:
+        out["callers"] = run_callers(ens)
     print(json.dumps(out), flush=True)
+
+
+def run_callers(ens):
+    """Secondary, N = 1 only: the two callers of the path built on host orchestration + device traces.
+    Wall clock through the public API (host buffers both ways); the device share is launch-latency bound."""
+    import math
+
+    from gradus_b200 import corona
+    from gradus_b200 import transfer_functions as tf
+
+    m = gb.KerrMetric(1.0, 0.998)
+    x = [0.0, 1e5, math.radians(30), 0.0]
+    d = gb.ThinDisc(0.0, float("inf"))
+    pr = gb.DeviceProber(m, x, d, chart=gb.chart_for_metric(m, 2e5, closest_approach=1.005), ensemble=ens)
+    radii = np.geomspace(gb.isco(m) + 1e-2, 1000.0, 150)
+    tf.cunningham_transfer_functions(m, x, d, radii[::10], prober=pr)
+    pr.launches = pr.rays = 0
+    t0 = time.perf_counter()
+    tf.cunningham_transfer_functions(m, x, d, radii, prober=pr)
+    dt = time.perf_counter() - t0
+    out = {"transfer_functions": {"workload": "Kerr a=0.998, observer r=1e5 at 30deg, 150 emission radii x 114 samples (N=80 + 2x17)",
+                                  "seconds": dt, "radii_per_s": len(radii) / dt, "launches": pr.launches, "rays": pr.rays}}
+    disc = gb.ThinDisc(0.0, 1000.0)
+    grid = [(gb.KerrMetric(1.0, a), disc, corona.LampPostModel(h=h)) for a in np.linspace(0.0, 0.998, 10) for h in np.geomspace(2.5, 50.0, 10)]
+    corona.emissivity_profiles(grid[:4], n_samples=1000, ensemble=ens)
+    t0 = time.perf_counter()
+    corona.emissivity_profiles(grid, n_samples=1000, ensemble=ens)
+    dt = time.perf_counter() - t0
+    out["emissivity_profiles"] = {"workload": "lamp post, 10 spins x 10 heights, 1000 rays each, one gb200_trace_batch",
+                                  "seconds": dt, "profiles_per_s": len(grid) / dt, "rays": 1000 * len(grid)}
+    return out
 
 
 def run_lineprofile(args, rank, world, local, ens, dev, stream, sptr):
@@ -327,6 +360,7 @@ def main():
     ap.add_argument("--ref-stride", type=int, default=64, help="--impl reference sample per step: every n-th ray")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lineprofile", action="store_true")
+    ap.add_argument("--no-callers", action="store_true", help="skip the transfer-function / emissivity-profile timings")
     ap.add_argument("--lp-n", type=int, default=4096)
     ap.add_argument("--lp-steps", type=int, default=2)
     args = ap.parse_args()

@@ -46,7 +46,7 @@ from .api import (  # noqa: F401
     tracegeodesics_batch,
     tracing_configuration,
 )
-from . import corona, hostmath  # noqa: F401
+from . import corona, hostmath, tf_integration  # noqa: F401
 from ._cabi import GradusB200Error  # noqa: F401
 from .transfer_functions import (  # noqa: F401
     CunninghamTransferData,
