@@ -278,6 +278,7 @@ def run_callers(ens):
     Wall clock through the public API (host buffers both ways); the device share is launch-latency bound."""
     import math
 
+    import gradus_b200 as gb
     from gradus_b200 import corona
     from gradus_b200 import transfer_functions as tf
 

@@ -22,7 +22,10 @@ from .api import (  # noqa: F401
     ImpactParameters,
     GeometricGrid,
     InverseGrid,
+    BumblebeeMetric,
+    JohannsenMetric,
     JohannsenPsaltisMetric,
+    KerrNewmanMetric,
     KerrMetric,
     LinearGrid,
     PolarChart,

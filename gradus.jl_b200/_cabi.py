@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libgradus_b200.so")
 OK = 0
 ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = -1, -2, -3, -4, -5
 STATUS_OUT_OF_DOMAIN, STATUS_WITHIN_INNER_BOUNDARY, STATUS_INTERSECTED, STATUS_NO_STATUS = 0, 1, 2, 3
-METRIC_KERR, METRIC_JP = 0, 1
+METRIC_KERR, METRIC_JP, METRIC_JOHANNSEN, METRIC_BUMBLEBEE, METRIC_KERR_NEWMAN = 0, 1, 2, 3, 4
 GEOMETRY_NONE, GEOMETRY_THIN_DISC, GEOMETRY_SHAKURA_SUNYAEV, GEOMETRY_DATUM_PLANE = 0, 1, 2, 3
 CALLBACK_NONE, CALLBACK_UPPER_HEMISPHERE = 0, 1
 POW_EXACT, POW_FAST32 = 0, 1
@@ -32,7 +32,7 @@ _ip = C.POINTER(C.c_int32)
 class Problem(C.Structure):
     _fields_ = [
         ("metric_kind", C.c_int32), ("geometry_kind", C.c_int32), ("callback_kind", C.c_int32), ("pow_mode", C.c_int32),
-        ("metric_params", C.c_double * 4), ("observer", C.c_double * 4), ("geometry_params", C.c_double * 4),
+        ("metric_params", C.c_double * 8), ("observer", C.c_double * 4), ("geometry_params", C.c_double * 4),
         ("gtol", C.c_double), ("chart_inner", C.c_double), ("chart_outer", C.c_double), ("callback_delta", C.c_double),
         ("lambda_min", C.c_double), ("lambda_max", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double),
         ("dtmax", C.c_double), ("mu", C.c_double), ("maxiters", C.c_int64),

@@ -38,7 +38,7 @@ class KerrMetric:
     kind = cabi.METRIC_KERR
 
     def params(self):
-        return (float(self.M), float(self.a), 0.0, 0.0)
+        return _pad8(self.M, self.a)
 
 
 @dataclass(frozen=True)
@@ -51,25 +51,83 @@ class JohannsenPsaltisMetric:
     kind = cabi.METRIC_JP
 
     def params(self):
-        return (float(self.M), float(self.a), float(self.eps3), 0.0)
+        return _pad8(self.M, self.a, self.eps3)
 
 
-_SUPPORTED_METRICS = (KerrMetric, JohannsenPsaltisMetric)
+@dataclass(frozen=True)
+class JohannsenMetric:
+    """src/metrics/johannsen-ad.jl:40-62 (`alpha13, alpha22, alpha52, eps3` are the reference's α13, α22, α52, ϵ3)."""
+
+    M: float = 1.0
+    a: float = 0.0
+    alpha13: float = 0.0
+    alpha22: float = 0.0
+    alpha52: float = 0.0
+    eps3: float = 0.0
+    kind = cabi.METRIC_JOHANNSEN
+
+    def params(self):
+        return _pad8(self.M, self.a, self.alpha13, self.alpha22, self.alpha52, self.eps3)
+
+
+@dataclass(frozen=True)
+class BumblebeeMetric:
+    """src/metrics/bumblebee-ad.jl:26-46: slow-rotation metric with Lorentz-symmetry-breaking parameter l."""
+
+    M: float = 1.0
+    a: float = 0.0
+    l: float = 0.0  # noqa: E741
+    kind = cabi.METRIC_BUMBLEBEE
+
+    def __post_init__(self):
+        if self.l <= -1.0:
+            raise ValueError("l must be >-1")
+        if abs(self.a) > 0.3:
+            raise ValueError("This metric is for the slow rotation approximation only, and requires |a| < 0.3.")
+
+    def params(self):
+        return _pad8(self.M, self.a, self.l)
+
+
+@dataclass(frozen=True)
+class KerrNewmanMetric:
+    """src/metrics/kerr-newman-ad.jl:41-58.  Neutral test particles only (the reference's `q = 0` default)."""
+
+    M: float = 1.0
+    a: float = 0.0
+    Q: float = 0.0
+    kind = cabi.METRIC_KERR_NEWMAN
+
+    def __post_init__(self):
+        if self.a**2 + self.Q**2 > self.M**2:
+            raise ValueError("Value error: `a^2 + Q^2` must be `<= M^2`")
+
+    def params(self):
+        return _pad8(self.M, self.a, self.Q)
+
+
+def _pad8(*vals):
+    return tuple(float(v) for v in vals) + (0.0,) * (8 - len(vals))
+
+
+_SUPPORTED_METRICS = (KerrMetric, JohannsenPsaltisMetric, JohannsenMetric, BumblebeeMetric, KerrNewmanMetric)
 
 
 def _check_metric(m):
     if not isinstance(m, _SUPPORTED_METRICS):
-        raise ValueError(f"EnsembleB200 supports KerrMetric and JohannsenPsaltisMetric only, got {type(m).__name__} (no CPU fallback)")
+        raise ValueError("EnsembleB200 supports " + ", ".join(c.__name__ for c in _SUPPORTED_METRICS)
+                         + f" only, got {type(m).__name__} (no CPU fallback)")
 
 
 def inner_radius(m) -> float:
-    """kerr-metric.jl:72 / johannsen-psaltis-ad.jl:50"""
+    """kerr-metric.jl:72, johannsen-psaltis-ad.jl:50, johannsen-ad.jl:66, bumblebee-ad.jl:51, kerr-newman-ad.jl:65"""
     _check_metric(m)
-    return m.M + math.sqrt(m.M**2 - m.a**2)
+    q2 = m.Q**2 if isinstance(m, KerrNewmanMetric) else 0.0
+    return m.M + math.sqrt(m.M**2 - m.a**2 - q2)
 
 
 def _metric_params_array(m):
-    return (C.c_double * 4)(*m.params())
+    return (C.c_double * 8)(*m.params())
 
 
 def isco(m) -> float:

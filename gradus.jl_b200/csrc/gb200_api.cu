@@ -75,8 +75,7 @@ static inline double val(double a) { return a; }
 template <class S>
 static S circular_energy_host(int kind, const double* mp, S r) {
     S g[5], dr[5], dth[5];
-    if (kind == GB200_METRIC_KERR) kerr_metric_jacobian<S>(mp[0], mp[1], r, S(1.0), S(0.0), g, dr, dth);
-    else jp_metric_jacobian<S>(mp[0], mp[1], mp[2], r, S(1.0), S(0.0), g, dr, dth);
+    metric_jacobian_kind<S>(kind, mp, r, S(1.0), S(0.0), g, dr, dth);
     const S D = g[0] * g[3] - g[4] * g[4];
     const S gitt = g[3] / D, giphph = g[0] / D, gitph = -g[4] / D;
     const S Om = -(dr[4] - dsqrt(dr[4] * dr[4] - dr[0] * dr[3])) / dr[3];
@@ -123,10 +122,14 @@ static int generic_isco_host(int kind, const double* mp, double* out) {
 // ---------------------------------------------------------------- validation
 static int validate(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic) {
     if (!p || !ic) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null problem or ic");
-    if (p->metric_kind != GB200_METRIC_KERR && p->metric_kind != GB200_METRIC_JOHANNSEN_PSALTIS)
-        return fail(ctx, GB200_ERR_UNSUPPORTED, "metric kind %d is outside the hot-path scope (Kerr, JohannsenPsaltis)", p->metric_kind);
+    if (p->metric_kind < 0 || p->metric_kind >= GB200_METRIC_COUNT)
+        return fail(ctx, GB200_ERR_UNSUPPORTED, "metric kind %d has no closed-form right-hand side in this library", p->metric_kind);
     const double M = p->metric_params[0], a = p->metric_params[1];
     if (!(M > 0) || !(std::fabs(a) <= M)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "need M > 0 and |a| <= M (M=%g a=%g)", M, a);
+    if (p->metric_kind == GB200_METRIC_BUMBLEBEE && (!(p->metric_params[2] > -1.0) || std::fabs(a) > 0.3))
+        return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "Bumblebee metric needs l > -1 and |a| <= 0.3 (bumblebee-ad.jl:33-40)");
+    if (p->metric_kind == GB200_METRIC_KERR_NEWMAN && a * a + p->metric_params[2] * p->metric_params[2] > M * M)
+        return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "Kerr-Newman metric needs a^2 + Q^2 <= M^2 (kerr-newman-ad.jl:50-52)");
     if (p->geometry_kind < GB200_GEOMETRY_NONE || p->geometry_kind > GB200_GEOMETRY_DATUM_PLANE)
         return fail(ctx, GB200_ERR_UNSUPPORTED, "geometry kind %d is outside the hot-path scope", p->geometry_kind);
     if (p->geometry_kind == GB200_GEOMETRY_THIN_DISC && !(p->geometry_params[0] <= p->geometry_params[1]))
@@ -186,6 +189,7 @@ static void fill_params(const gb200_problem* p, const gb200_ic* ic, const gb200_
     memset(&P, 0, sizeof P);
     P.metric_kind = p->metric_kind;
     P.M = p->metric_params[0]; P.a = p->metric_params[1]; P.eps3 = p->metric_params[2];
+    for (int k = 0; k < 8; ++k) P.mp[k] = p->metric_params[k];
     P.lam0 = p->lambda_min; P.lam1 = p->lambda_max; P.abstol = p->abstol; P.reltol = p->reltol;
     P.dtmax = p->dtmax > 0 ? p->dtmax : (p->lambda_max - p->lambda_min);
     P.mu = p->mu;
@@ -414,7 +418,7 @@ int gb200_validate(const gb200_problem* p, const gb200_ic* ic) { return validate
 int gb200_isco(int32_t metric_kind, const double* mp, double* out) {
     if (!mp || !out) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null argument");
     if (metric_kind == GB200_METRIC_KERR) { *out = kerr_isco_host(mp[0], mp[1]); return GB200_OK; }
-    if (metric_kind == GB200_METRIC_JOHANNSEN_PSALTIS) {
+    if (metric_kind > GB200_METRIC_KERR && metric_kind < GB200_METRIC_COUNT) {
         int rc = generic_isco_host(metric_kind, mp, out);
         if (rc) return fail(nullptr, rc, "No boundaries for minimization could be determined. It is likely this configuration does not have an ISCO solution.");
         return GB200_OK;
@@ -640,8 +644,7 @@ int gb200_build_plunging_table(gb200_ctx* ctx, int32_t metric_kind, const double
     if (rc) return fail(ctx, rc, "no ISCO for this metric");
     // CircularOrbits.plunging_fourvelocity at the ISCO (circular-orbits.jl:129-150)
     double g[5], dr[5], dth[5];
-    if (metric_kind == GB200_METRIC_KERR) kerr_metric_jacobian<double>(mp[0], mp[1], risco, 1.0, 0.0, g, dr, dth);
-    else jp_metric_jacobian<double>(mp[0], mp[1], mp[2], risco, 1.0, 0.0, g, dr, dth);
+    metric_jacobian_kind<double>(metric_kind, mp, risco, 1.0, 0.0, g, dr, dth);
     const double D = g[0] * g[3] - g[4] * g[4];
     const double gitt = g[3] / D, giphph = g[0] / D, gitph = -g[4] / D;
     const double Om = -(dr[4] - std::sqrt(dr[4] * dr[4] - dr[0] * dr[3])) / dr[3];
@@ -655,9 +658,10 @@ int gb200_build_plunging_table(gb200_ctx* ctx, int32_t metric_kind, const double
     const double vr = -std::sqrt(std::fabs(nom / (-g[1])));
     gb200_problem p{};
     p.metric_kind = metric_kind;
-    for (int k = 0; k < 4; ++k) p.metric_params[k] = (k < 3) ? mp[k] : 0.0;
+    for (int k = 0; k < 8; ++k) p.metric_params[k] = mp[k];
     p.mu = 1.0; p.abstol = 1e-9; p.reltol = 1e-9; p.lambda_min = 0.0; p.lambda_max = 50000.0; p.gtol = 1e-2;
-    const double rh = mp[0] + std::sqrt(mp[0] * mp[0] - mp[1] * mp[1]);
+    const double q2 = metric_kind == GB200_METRIC_KERR_NEWMAN ? mp[2] * mp[2] : 0.0;
+    const double rh = mp[0] + std::sqrt(mp[0] * mp[0] - mp[1] * mp[1] - q2);
     p.chart_inner = rh * 1.000001; p.chart_outer = 12000.0;
     const double u0[8] = {0.0, risco - 1e-8, M_PI / 2, 0.0, vt, vr, 0.0, vph};
     const int pathcap = 1 << 20;
@@ -781,11 +785,12 @@ int gb200_lineprofile_device(gb200_ctx* ctx, const gb200_problem* p, const gb200
 
 int gb200_debug_rhs(gb200_ctx* ctx, int32_t metric_kind, const double* mp, int64_t n, const double* u, double* du) {
     if (!ctx || !mp || !u || !du || n < 1) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad arguments");
-    if (metric_kind != GB200_METRIC_KERR && metric_kind != GB200_METRIC_JOHANNSEN_PSALTIS) return fail(ctx, GB200_ERR_UNSUPPORTED, "metric kind %d", metric_kind);
+    if (metric_kind < 0 || metric_kind >= GB200_METRIC_COUNT) return fail(ctx, GB200_ERR_UNSUPPORTED, "metric kind %d", metric_kind);
     CU(ctx, cudaSetDevice(ctx->device));
     GbParams P;
     memset(&P, 0, sizeof P);
     P.metric_kind = metric_kind; P.M = mp[0]; P.a = mp[1]; P.eps3 = mp[2];
+    for (int k = 0; k < 8; ++k) P.mp[k] = mp[k];
     void *d_u, *d_du;
     int rc = pool_get(ctx, SL_X0, sizeof(double) * 8 * (size_t)n, &d_u); if (rc) return rc;
     rc = pool_get(ctx, SL_V0, sizeof(double) * 8 * (size_t)n, &d_du); if (rc) return rc;

@@ -54,6 +54,7 @@ GB_HD inline double gb_rcp_lo(double x) {
 }
 
 #include "jp_metric_generated.cuh"
+#include "metrics_generated.cuh"
 
 #define GB_MAX_PF 4
 
@@ -62,6 +63,7 @@ struct GbParams {
     // metric
     int32_t metric_kind;
     double M, a, eps3;
+    double mp[8]; // all metric parameters in the order of include/gradus_b200.h (M = mp[0], a = mp[1])
     // integrator
     double lam0, lam1, abstol, reltol, dtmax, mu;
     int64_t maxiters;
@@ -354,14 +356,23 @@ GB_HD inline void kerr_metric_jacobian(double M, double a, S r, S s, S c, S g[5]
     dth[4] = -a * q;
 }
 
+// components + Jacobian of metric `kind` with parameters mp[] (s = sin theta, c = cos theta)
+template <class S>
+GB_HD inline void metric_jacobian_kind(int kind, const double* mp, S r, S s, S c, S g[5], S dr[5], S dth[5]) {
+    switch (kind) {
+    case GB200_METRIC_KERR: kerr_metric_jacobian<S>(mp[0], mp[1], r, s, c, g, dr, dth); break;
+    case GB200_METRIC_JOHANNSEN_PSALTIS: jp_metric_jacobian<S>(mp[0], mp[1], mp[2], r, s, c, g, dr, dth); break;
+    case GB200_METRIC_JOHANNSEN: johannsen_metric_jacobian<S>(mp, r, s, c, g, dr, dth); break;
+    case GB200_METRIC_BUMBLEBEE: bumblebee_metric_jacobian<S>(mp, r, s, c, g, dr, dth); break;
+    default: kerr_newman_metric_jacobian<S>(mp, r, s, c, g, dr, dth); break;
+    }
+}
 template <int METRIC>
 GB_HD inline void metric_jacobian(const GbParams& P, double r, double s, double c, double g[5], double dr[5], double dth[5]) {
-    if (METRIC == GB200_METRIC_KERR) kerr_metric_jacobian(P.M, P.a, r, s, c, g, dr, dth);
-    else jp_metric_jacobian(P.M, P.a, P.eps3, r, s, c, g, dr, dth);
+    metric_jacobian_kind<double>(METRIC, P.mp, r, s, c, g, dr, dth); // METRIC is a compile-time constant: the switch folds
 }
 GB_HD inline void metric_jacobian_rt(const GbParams& P, double r, double s, double c, double g[5], double dr[5], double dth[5]) {
-    if (P.metric_kind == GB200_METRIC_KERR) kerr_metric_jacobian(P.M, P.a, r, s, c, g, dr, dth);
-    else jp_metric_jacobian(P.M, P.a, P.eps3, r, s, c, g, dr, dth);
+    metric_jacobian_kind<double>(P.metric_kind, P.mp, r, s, c, g, dr, dth);
 }
 
 // a^mu = -g^{mu m} ( gdot_{mk} v^k - 1/2 S_m ),  gdot = v^r d_r g + v^th d_th g,  S_m = d_m g_{kl} v^k v^l
@@ -469,15 +480,15 @@ struct GbAcc { double a0, a1, a2, a3, s, c; };
 #define GB_RHS_ATTR __device__ __forceinline__
 #endif
 template <int METRIC>
-GB_RHS_ATTR GbAcc rhs_eval(double M, double a, double e3, double r, double th, double vt, double vr, double vth, double vph) {
+GB_RHS_ATTR GbAcc rhs_eval(const GbParams& P, double r, double th, double vt, double vr, double vth, double vph) {
     GbAcc o;
     double acc[4];
     gb_sincos(th, &o.s, &o.c);
     if (METRIC == GB200_METRIC_KERR) {
-        kerr_rhs_accel(M, a, r, o.s, o.c, vt, vr, vth, vph, acc);
+        kerr_rhs_accel(P.M, P.a, r, o.s, o.c, vt, vr, vth, vph, acc);
     } else {
         double g[5], dr[5], dth[5];
-        jp_metric_jacobian<double>(M, a, e3, r, o.s, o.c, g, dr, dth);
+        metric_jacobian<METRIC>(P, r, o.s, o.c, g, dr, dth);
         geodesic_accel(g, dr, dth, vt, vr, vth, vph, acc);
     }
     o.a0 = acc[0]; o.a1 = acc[1]; o.a2 = acc[2]; o.a3 = acc[3];
@@ -486,7 +497,7 @@ GB_RHS_ATTR GbAcc rhs_eval(double M, double a, double e3, double r, double th, d
 template <int METRIC>
 GB_D void rhs_accel(const GbParams& P, double r, double th, double vt, double vr, double vth, double vph,
                     double acc[4], double& s, double& c) {
-    const GbAcc o = rhs_eval<METRIC>(P.M, P.a, P.eps3, r, th, vt, vr, vth, vph);
+    const GbAcc o = rhs_eval<METRIC>(P, r, th, vt, vr, vth, vph);
     acc[0] = o.a0; acc[1] = o.a1; acc[2] = o.a2; acc[3] = o.a3; s = o.s; c = o.c;
 }
 #endif

@@ -545,8 +545,13 @@ static cudaError_t launch_geom(const GbParams& P, int sm_count, cudaStream_t str
 }
 
 cudaError_t gb200_launch_trace(const GbParams& P, int sm_count, cudaStream_t stream, int* blocks_out) {
-    if (P.metric_kind == GB200_METRIC_KERR) return launch_geom<GB200_METRIC_KERR>(P, sm_count, stream, blocks_out);
-    if (P.metric_kind == GB200_METRIC_JOHANNSEN_PSALTIS) return launch_geom<GB200_METRIC_JOHANNSEN_PSALTIS>(P, sm_count, stream, blocks_out);
+    switch (P.metric_kind) {
+    case GB200_METRIC_KERR: return launch_geom<GB200_METRIC_KERR>(P, sm_count, stream, blocks_out);
+    case GB200_METRIC_JOHANNSEN_PSALTIS: return launch_geom<GB200_METRIC_JOHANNSEN_PSALTIS>(P, sm_count, stream, blocks_out);
+    case GB200_METRIC_JOHANNSEN: return launch_geom<GB200_METRIC_JOHANNSEN>(P, sm_count, stream, blocks_out);
+    case GB200_METRIC_BUMBLEBEE: return launch_geom<GB200_METRIC_BUMBLEBEE>(P, sm_count, stream, blocks_out);
+    case GB200_METRIC_KERR_NEWMAN: return launch_geom<GB200_METRIC_KERR_NEWMAN>(P, sm_count, stream, blocks_out);
+    }
     return cudaErrorInvalidValue;
 }
 
@@ -640,8 +645,13 @@ __global__ void gb200_path_kernel(const GbParams P, const double* __restrict__ u
 }
 
 cudaError_t gb200_launch_path(const GbParams& P, const double* d_u0, int cap, double* d_lambda, double* d_u, int* d_meta, cudaStream_t stream) {
-    if (P.metric_kind == GB200_METRIC_KERR) gb200_path_kernel<GB200_METRIC_KERR><<<1, 32, 0, stream>>>(P, d_u0, cap, d_lambda, d_u, d_meta);
-    else gb200_path_kernel<GB200_METRIC_JOHANNSEN_PSALTIS><<<1, 32, 0, stream>>>(P, d_u0, cap, d_lambda, d_u, d_meta);
+    switch (P.metric_kind) {
+    case GB200_METRIC_KERR: gb200_path_kernel<GB200_METRIC_KERR><<<1, 32, 0, stream>>>(P, d_u0, cap, d_lambda, d_u, d_meta); break;
+    case GB200_METRIC_JOHANNSEN_PSALTIS: gb200_path_kernel<GB200_METRIC_JOHANNSEN_PSALTIS><<<1, 32, 0, stream>>>(P, d_u0, cap, d_lambda, d_u, d_meta); break;
+    case GB200_METRIC_JOHANNSEN: gb200_path_kernel<GB200_METRIC_JOHANNSEN><<<1, 32, 0, stream>>>(P, d_u0, cap, d_lambda, d_u, d_meta); break;
+    case GB200_METRIC_BUMBLEBEE: gb200_path_kernel<GB200_METRIC_BUMBLEBEE><<<1, 32, 0, stream>>>(P, d_u0, cap, d_lambda, d_u, d_meta); break;
+    default: gb200_path_kernel<GB200_METRIC_KERR_NEWMAN><<<1, 32, 0, stream>>>(P, d_u0, cap, d_lambda, d_u, d_meta); break;
+    }
     return cudaGetLastError();
 }
 
@@ -739,8 +749,13 @@ __global__ void gb200_debug_math_kernel(long long n, const double* __restrict__ 
 }
 cudaError_t gb200_launch_debug_rhs(const GbParams& P, long long n, const double* d_u, double* d_du, cudaStream_t stream) {
     const unsigned grid = (unsigned)((n + 127) / 128);
-    if (P.metric_kind == GB200_METRIC_KERR) gb200_debug_rhs_kernel<GB200_METRIC_KERR><<<grid, 128, 0, stream>>>(P, n, d_u, d_du);
-    else gb200_debug_rhs_kernel<GB200_METRIC_JOHANNSEN_PSALTIS><<<grid, 128, 0, stream>>>(P, n, d_u, d_du);
+    switch (P.metric_kind) {
+    case GB200_METRIC_KERR: gb200_debug_rhs_kernel<GB200_METRIC_KERR><<<grid, 128, 0, stream>>>(P, n, d_u, d_du); break;
+    case GB200_METRIC_JOHANNSEN_PSALTIS: gb200_debug_rhs_kernel<GB200_METRIC_JOHANNSEN_PSALTIS><<<grid, 128, 0, stream>>>(P, n, d_u, d_du); break;
+    case GB200_METRIC_JOHANNSEN: gb200_debug_rhs_kernel<GB200_METRIC_JOHANNSEN><<<grid, 128, 0, stream>>>(P, n, d_u, d_du); break;
+    case GB200_METRIC_BUMBLEBEE: gb200_debug_rhs_kernel<GB200_METRIC_BUMBLEBEE><<<grid, 128, 0, stream>>>(P, n, d_u, d_du); break;
+    default: gb200_debug_rhs_kernel<GB200_METRIC_KERR_NEWMAN><<<grid, 128, 0, stream>>>(P, n, d_u, d_du); break;
+    }
     return cudaGetLastError();
 }
 cudaError_t gb200_launch_debug_math(long long n, const double* d_x, double* d_out3, cudaStream_t stream) {

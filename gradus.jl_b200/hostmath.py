@@ -39,6 +39,33 @@ def metric_components(m, r, theta):
         thth = sigma + 0 * r
         phph = s2 * (r * r + a * a + 2 * a * a * M * r * s2 / sigma) + h * a * a * (sigma + 2 * M * r) * s2 * s2 / sigma
         tph = -2 * a * M * r * s2 * (1 + h) / sigma
+    elif isinstance(m, api.JohannsenMetric):
+        f = m.eps3 * M**3 / r
+        sigma = r * r + a * a * c2 + f
+        A1 = 1 + m.alpha13 * (M / r) ** 3
+        A2 = 1 + m.alpha22 * (M / r) ** 2
+        A5 = 1 + m.alpha52 * (M / r) ** 2
+        r2a2 = r * r + a * a
+        den = (r2a2 * A1 - a * a * A2 * s2) ** 2
+        tt = -sigma * (delta - a * a * A2**2 * s2) / den
+        rr = sigma / (delta * A5)
+        thth = sigma + 0 * r
+        phph = sigma * s2 * (r2a2**2 * A1**2 - a * a * delta * s2) / den
+        tph = -a * sigma * s2 * (r2a2 * A1 * A2 - delta) / den
+    elif isinstance(m, api.BumblebeeMetric):
+        tt = -(1 - 2 * M / r)
+        rr = r * r / ((r * r - 2 * M * r) / (m.l + 1))
+        thth = r * r + 0 * c2
+        phph = r * r * s2
+        tph = -2 * M * a * s2 / r
+    elif isinstance(m, api.KerrNewmanMetric):
+        delta = delta + m.Q**2
+        r2a2 = r * r + a * a
+        tt = (a * a * s2 - delta) / sigma
+        rr = sigma / delta
+        thth = sigma + 0 * r
+        phph = (s2 / sigma) * (r2a2**2 - a * a * s2 * delta)
+        tph = (a * s2 / sigma) * (delta - r2a2)
     else:
         raise ValueError(f"metric {type(m).__name__} is outside the B200 scope")
     return np.stack(np.broadcast_arrays(tt, rr, thth, phph, tph))

@@ -46,6 +46,10 @@ extern "C" {
 /* ---- metrics: src/metrics/kerr-metric.jl:62-68, johannsen-psaltis-ad.jl:38-46 */
 #define GB200_METRIC_KERR 0              /* params: M, a          */
 #define GB200_METRIC_JOHANNSEN_PSALTIS 1 /* params: M, a, eps3    */
+#define GB200_METRIC_JOHANNSEN 2         /* src/metrics/johannsen-ad.jl:40-62     params: M, a, alpha13, alpha22, alpha52, eps3 */
+#define GB200_METRIC_BUMBLEBEE 3         /* src/metrics/bumblebee-ad.jl:26-46     params: M, a, l  (l > -1, |a| <= 0.3)        */
+#define GB200_METRIC_KERR_NEWMAN 4       /* src/metrics/kerr-newman-ad.jl:41-58   params: M, a, Q  (neutral particles: q = 0)  */
+#define GB200_METRIC_COUNT 5
 
 /* ---- accretion geometry: src/geometry/discs/ --------------------------- */
 #define GB200_GEOMETRY_NONE 0
@@ -77,7 +81,7 @@ typedef struct gb200_problem {
     int32_t geometry_kind;
     int32_t callback_kind;
     int32_t pow_mode;
-    double metric_params[4];
+    double metric_params[8];
     double observer[4]; /* x = (t, r, theta, phi) shared by all rays unless the IC is explicit */
     double geometry_params[4];
     double gtol;           /* src/geometry/bootstrap.jl:8, default 1e-2 */

@@ -31,7 +31,7 @@ Gradus.restrict_ensemble(::Gradus.AbstractMetric, e::EnsembleB200) = e
 # ---- POD mirrors of include/gradus_b200.h ---------------------------------------------------------------------
 struct CProblem
     metric_kind::Int32; geometry_kind::Int32; callback_kind::Int32; pow_mode::Int32
-    metric_params::NTuple{4,Float64}; observer::NTuple{4,Float64}; geometry_params::NTuple{4,Float64}
+    metric_params::NTuple{8,Float64}; observer::NTuple{4,Float64}; geometry_params::NTuple{4,Float64}
     gtol::Float64; chart_inner::Float64; chart_outer::Float64; callback_delta::Float64
     lambda_min::Float64; lambda_max::Float64; abstol::Float64; reltol::Float64
     dtmax::Float64; mu::Float64; maxiters::Int64
@@ -50,9 +50,13 @@ struct CEndpoints
     naccept::Ptr{Int32}; nreject::Ptr{Int32}; flags::Ptr{Int32}
 end
 
-_metric(m::KerrMetric) = (Int32(0), (m.M, m.a, 0.0, 0.0))
-_metric(m::JohannsenPsaltisMetric) = (Int32(1), (m.M, m.a, m.ϵ3, 0.0))
-_metric(m) = throw(ArgumentError("EnsembleB200 supports KerrMetric and JohannsenPsaltisMetric only (got $(typeof(m))); there is no CPU fallback"))
+_mp8(v...) = ntuple(i -> i <= length(v) ? Float64(v[i]) : 0.0, 8)
+_metric(m::KerrMetric) = (Int32(0), _mp8(m.M, m.a))
+_metric(m::JohannsenPsaltisMetric) = (Int32(1), _mp8(m.M, m.a, m.ϵ3))
+_metric(m::JohannsenMetric) = (Int32(2), _mp8(m.M, m.a, m.α13, m.α22, m.α52, m.ϵ3))
+_metric(m::BumblebeeMetric) = (Int32(3), _mp8(m.M, m.a, m.l))
+_metric(m::KerrNewmanMetric) = (Int32(4), _mp8(m.M, m.a, m.Q))   # neutral particles only: trace.q must be 0
+_metric(m) = throw(ArgumentError("EnsembleB200 has no closed-form right-hand side for $(typeof(m)); there is no CPU fallback"))
 _geometry(::Nothing) = (Int32(0), (0.0, 0.0, 0.0, 0.0))
 _geometry(d::ThinDisc) = (Int32(1), (d.inner_radius, d.outer_radius, 0.0, 0.0))
 _geometry(d::ShakuraSunyaev) = (Int32(2), (d.Ṁ_Ṁedd, d.inv_η, d.inner_radius, 0.0))

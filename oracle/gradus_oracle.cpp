@@ -107,7 +107,13 @@ template <class S> S sq(const S& x) { return x * x; }
 struct Metric {
     int kind;
     double M, a, eps3;
+    double p[8]; // all parameters in the order of include/gradus_b200.h
 };
+inline Metric make_metric(int kind, const double* mp) {
+    Metric m{kind, mp[0], mp[1], mp[2], {0, 0, 0, 0, 0, 0, 0, 0}};
+    for (int i = 0; i < 8; ++i) m.p[i] = mp[i];
+    return m;
+}
 
 // (g_tt, g_rr, g_thth, g_phph, g_tph); Kerr: src/metrics/kerr-metric.jl:11-28;
 // Johannsen-Psaltis: src/metrics/johannsen-psaltis-ad.jl:4-26.
@@ -127,6 +133,43 @@ void metric_components(const Metric& m, const S& r, const S& th, S g[5]) {
         g[2] = Sigma;
         g[3] = sinth2 * (sq(r) + sq(a) + (gam * a) * iSigma);
         g[4] = -gam * iSigma;
+    } else if (m.kind == GB200_METRIC_JOHANNSEN) { // src/metrics/johannsen-ad.jl:4-36
+        S M = S(m.M), a = S(m.a), a13 = S(m.p[2]), a22 = S(m.p[3]), a52 = S(m.p[4]), e3 = S(m.p[5]);
+        S Mr = M / r;
+        S A1 = S(1.0) + a13 * (Mr * Mr * Mr);
+        S A2 = S(1.0) + a22 * sq(Mr);
+        S A5 = S(1.0) + a52 * sq(Mr);
+        S Sigma = sq(r) + sq(a) * sq(rcos(th)) + e3 * (M * M * M) / r;
+        S Delta = sq(r) - S(2.0) * M * r + sq(a);
+        S r2a2 = sq(r) + sq(a);
+        S sinth2 = sq(rsin(th));
+        S denom = sq(r2a2 * A1 - sq(a) * A2 * sinth2);
+        g[0] = -Sigma * (Delta - sq(a) * sq(A2) * sinth2) / denom;
+        g[1] = Sigma / (Delta * A5);
+        g[2] = Sigma;
+        g[3] = Sigma * sinth2 * (sq(r2a2) * sq(A1) - sq(a) * Delta * sinth2) / denom;
+        g[4] = -a * Sigma * sinth2 * (r2a2 * A1 * A2 - Delta) / denom;
+    } else if (m.kind == GB200_METRIC_BUMBLEBEE) { // src/metrics/bumblebee-ad.jl:5-22
+        S M = S(m.M), a = S(m.a), l = S(m.p[2]);
+        S sinth2 = sq(rsin(th));
+        S Delta = (sq(r) - S(2.0) * M * r) / (l + S(1.0));
+        g[0] = -(S(1.0) - S(2.0) * M / r);
+        g[1] = sq(r) / Delta;
+        g[2] = sq(r);
+        g[3] = sq(r) * sinth2;
+        g[4] = -S(2.0) * M * a * sinth2 / r;
+    } else if (m.kind == GB200_METRIC_KERR_NEWMAN) { // src/metrics/kerr-newman-ad.jl:5-27
+        S M = S(m.M), a = S(m.a), Q = S(m.p[2]);
+        S R = S(2.0) * M;
+        S Sigma = sq(r) + sq(a * rcos(th));
+        S sinth2 = sq(rsin(th));
+        S Delta = sq(r) - R * r + sq(a) + sq(Q);
+        S r2a2 = sq(r) + sq(a);
+        g[0] = (sq(a) * sinth2 - Delta) / Sigma;
+        g[1] = Sigma / Delta;
+        g[2] = Sigma;
+        g[3] = (sinth2 / Sigma) * (sq(r2a2) - sq(a) * sinth2 * Delta);
+        g[4] = (a * sinth2 / Sigma) * (Delta - r2a2);
     } else {
         S M = S(m.M), a = S(m.a), e3 = S(m.eps3);
         S Sigma = sq(r) + sq(a) * sq(rcos(th));
@@ -144,7 +187,10 @@ void metric_components(const Metric& m, const S& r, const S& th, S g[5]) {
 }
 
 // src/metrics/kerr-metric.jl:72, johannsen-psaltis-ad.jl:50
-inline double inner_radius(const Metric& m) { return m.M + std::sqrt(m.M * m.M - m.a * m.a); }
+inline double inner_radius(const Metric& m) {
+    const double q2 = (m.kind == GB200_METRIC_KERR_NEWMAN) ? m.p[2] * m.p[2] : 0.0; // kerr-newman-ad.jl:65
+    return m.M + std::sqrt(m.M * m.M - m.a * m.a - q2);
+}
 
 // metric_jacobian, auto-diff.jl:206-211: value and d/dr, d/dtheta of the 5 components.
 template <class S>
@@ -861,7 +907,7 @@ template <class T>
 int run(const gb200_problem& p, const gb200_ic& ic, const gb200_range& rg, int nthreads,
         gb200_endpoints* out, double* margin, const int32_t* pfs, int npf, const gb200_plunging_table* pl, double* const* images,
         const gb200_emissivity* emis, const double* bins, int nbins, const gb200_lineprofile_opts* lo, double* flux) {
-    Metric m{p.metric_kind, p.metric_params[0], p.metric_params[1], p.metric_params[2]};
+    Metric m = make_metric(p.metric_kind, p.metric_params);
     LnrTransform<T> xfm;
     if (ic.kind != GB200_IC_EXPLICIT) {
         T xo[4];
@@ -995,38 +1041,38 @@ int oracle_lineprofile(const gb200_problem* p, const gb200_ic* ic, const gb200_r
     return orc::run<double>(*p, *ic, *rg, nthreads, out, nullptr, nullptr, 0, pl, nullptr, emis, bins, nbins, lo, flux);
 }
 int oracle_isco(int kind, const double* mp, double* out) {
-    orc::Metric m{kind, mp[0], mp[1], mp[2]};
+    orc::Metric m = orc::make_metric(kind, mp);
     *out = orc::isco_of(m);
     return 0;
 }
 int oracle_generic_isco(int kind, const double* mp, double* out) { // the root-finding branch even for Kerr (special-radii KAT)
-    orc::Metric m{kind, mp[0], mp[1], mp[2]};
+    orc::Metric m = orc::make_metric(kind, mp);
     *out = orc::generic_isco(m);
     return 0;
 }
 int oracle_circular_energy(int kind, const double* mp, double r, double* out) {
-    orc::Metric m{kind, mp[0], mp[1], mp[2]};
+    orc::Metric m = orc::make_metric(kind, mp);
     *out = orc::circ_energy<double>(m, r);
     return 0;
 }
 int oracle_circular_fourvelocity(int kind, const double* mp, double r, double* v4) {
-    orc::Metric m{kind, mp[0], mp[1], mp[2]};
+    orc::Metric m = orc::make_metric(kind, mp);
     orc::circ_fourvelocity<double>(m, r, v4);
     return 0;
 }
 // unit-test hooks
 int oracle_metric(int kind, const double* mp, double r, double th, double* g5, double* dr5, double* dth5) {
-    orc::Metric m{kind, mp[0], mp[1], mp[2]};
+    orc::Metric m = orc::make_metric(kind, mp);
     orc::metric_jacobian<double>(m, r, th, g5, dr5, dth5);
     return 0;
 }
 int oracle_rhs(int kind, const double* mp, const double* u8, double* du8) {
-    orc::Metric m{kind, mp[0], mp[1], mp[2]};
+    orc::Metric m = orc::make_metric(kind, mp);
     orc::rhs<double>(m, u8, du8);
     return 0;
 }
 int oracle_lnrbasis(int kind, const double* mp, double r, double th, double* basis16, double* frame16) {
-    orc::Metric m{kind, mp[0], mp[1], mp[2]};
+    orc::Metric m = orc::make_metric(kind, mp);
     double gc[5], g[4][4];
     orc::metric_components<double>(m, r, th, gc);
     orc::symmetric_matrix(gc, g);
@@ -1037,7 +1083,7 @@ int oracle_lnrbasis(int kind, const double* mp, double r, double th, double* bas
     return 0;
 }
 int oracle_initial_velocity(const gb200_problem* p, double alpha, double beta, double* u8) {
-    orc::Metric m{p->metric_kind, p->metric_params[0], p->metric_params[1], p->metric_params[2]};
+    orc::Metric m = orc::make_metric(p->metric_kind, p->metric_params);
     orc::LnrTransform<double> xfm;
     xfm.build(m, p->observer);
     orc::RayIC ric;
@@ -1048,7 +1094,7 @@ int oracle_initial_velocity(const gb200_problem* p, double alpha, double beta, d
 }
 // single ray with every accepted step recorded; returns the number of steps written (<= cap)
 int oracle_trace_path(const gb200_problem* p, const double* u0, int precision, int cap, double* t, double* dt, double* eest, double* u8) {
-    orc::Metric m{p->metric_kind, p->metric_params[0], p->metric_params[1], p->metric_params[2]};
+    orc::Metric m = orc::make_metric(p->metric_kind, p->metric_params);
     orc::StepRecord rec;
     if (precision == 1) {
         long double ul[8]; for (int i = 0; i < 8; ++i) ul[i] = u0[i];
@@ -1061,7 +1107,7 @@ int oracle_trace_path(const gb200_problem* p, const double* u0, int precision, i
     return (int)rec.t.size();
 }
 int oracle_band(const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, int nthreads, double* ratio) {
-    orc::Metric m{p->metric_kind, p->metric_params[0], p->metric_params[1], p->metric_params[2]};
+    orc::Metric m = orc::make_metric(p->metric_kind, p->metric_params);
     orc::LnrTransform<double> xfm;
     if (ic->kind != GB200_IC_EXPLICIT) xfm.build(m, p->observer);
 #ifdef _OPENMP
@@ -1083,7 +1129,7 @@ int oracle_band(const gb200_problem* p, const gb200_ic* ic, const gb200_range* r
 // state exactly to the affine parameter lam_end[i] (no geometry, no chart, no callback) and return the state.
 int oracle_trace_to(const gb200_problem* p, int64_t n, const double* u0 /* n x 8, row-major */, const double* lam_end,
                     int nthreads, double* u_out /* n x 8 */) {
-    orc::Metric m{p->metric_kind, p->metric_params[0], p->metric_params[1], p->metric_params[2]};
+    orc::Metric m = orc::make_metric(p->metric_kind, p->metric_params);
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif

@@ -79,7 +79,7 @@ def lineprofile(problem, ic, emis, bins, opts, rng=None, nthreads=0, precision=0
 
 
 def _mp(params):
-    a = np.zeros(4)
+    a = np.zeros(8)
     a[: len(params)] = params
     return a
 

@@ -66,7 +66,7 @@ def oracle_plunging_table(kind, mp):
     vr = -math.sqrt(abs(nom / (-g[1])))
     p = cabi.Problem()
     p.metric_kind = kind
-    p.metric_params[:] = list(mp) + [0.0] * (4 - len(mp))
+    p.metric_params[:] = list(mp) + [0.0] * (8 - len(mp))
     p.mu, p.abstol, p.reltol, p.lambda_min, p.lambda_max, p.gtol = 1.0, 1e-9, 1e-9, 0.0, 50000.0, 1e-2
     p.chart_inner = (mp[0] + math.sqrt(mp[0] ** 2 - mp[1] ** 2)) * 1.000001
     p.chart_outer = 12000.0

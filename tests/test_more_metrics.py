@@ -1,0 +1,119 @@
+"""Further static, axis-symmetric metrics: Johannsen, Bumblebee, Kerr-Newman (neutral particles).
+
+Pins: the reference's `rendergeodesics` smoke matrix (test/smoke-tests/rendergeodesics.jl:32-82 — shadow, thin-disc and
+Shakura-Sunyaev fingerprints per metric, default parameters) for the oracle; GPU vs oracle at non-trivial parameters
+with the same protocol as the main parity tests (identical termination class outside the oracle-defined grazing band,
+disc-hit endpoints to 1e-6, redshift to 1e-6)."""
+import math
+
+import numpy as np
+import pytest
+
+import gradus_b200 as gb
+from gradus_b200 import _cabi as cabi
+from gradus_b200 import api, hostmath
+from oracle import oracle
+
+from common import render_config
+
+ORACLE_GEOMETRY_SS_LEGACY_GTOL = 101
+
+# (metric with the reference's defaults, shadow literal, thin-disc literal, Shakura-Sunyaev literal)
+SMOKE = [
+    (gb.JohannsenMetric(), 9009.448935932085, 38412.08386562321, 34455.344169980635),
+    (gb.BumblebeeMetric(), 9009.452384885506, 38412.0832157869, 34455.3441698318),
+    (gb.KerrNewmanMetric(), 9009.451384824908, 38412.08517225652, 34455.34416971527),
+]
+NONTRIVIAL = [
+    gb.JohannsenMetric(M=1.0, a=0.7, alpha13=0.35, alpha22=-0.2, alpha52=0.5, eps3=0.8),
+    gb.BumblebeeMetric(M=1.0, a=0.25, l=0.4),
+    gb.KerrNewmanMetric(M=1.0, a=0.6, Q=0.5),
+]
+IDS = ["johannsen", "bumblebee", "kerr_newman"]
+
+
+def _smoke_fixture(m, d):
+    return render_config(m, [0.0, 100.0, math.radians(85), 0.0], d, 200.0, 20, 20, (-9.5, 9.5), (-9.5, 9.5))
+
+
+@pytest.mark.parametrize("m, shadow, thin, ss", SMOKE, ids=IDS)
+def test_oracle_reproduces_the_smoke_matrix(m, shadow, thin, ss):
+    p, ic = _smoke_fixture(m, None).to_c()
+    assert np.nansum(oracle.render(p, ic, [cabi.PF_SHADOW])[0]) == pytest.approx(shadow, rel=1e-6)
+    p, ic = _smoke_fixture(m, gb.ThinDisc(0.0, 40.0)).to_c()
+    assert np.nansum(oracle.render(p, ic, [cabi.PF_SHADOW])[0]) == pytest.approx(thin, rel=1e-6)
+    p, ic = _smoke_fixture(m, gb.ShakuraSunyaev(m)).to_c()
+    p.geometry_kind = ORACLE_GEOMETRY_SS_LEGACY_GTOL  # the form the literals were recorded with, see test_oracle_kat.py
+    assert np.nansum(oracle.render(p, ic, [cabi.PF_SHADOW])[0]) == pytest.approx(ss, rel=1e-9)
+
+
+@pytest.mark.parametrize("m", NONTRIVIAL, ids=IDS)
+def test_host_and_oracle_metric_algebra_agree(m):
+    mp = list(m.params())
+    for r, th in [(3.0, 0.4), (9.0, 1.3), (250.0, 2.2)]:
+        g, dr, _ = oracle.metric(m.kind, mp, r, th)
+        assert np.allclose(hostmath.metric_components(m, r, th), g, rtol=1e-13, atol=0)
+        assert np.allclose(hostmath.metric_dr(m, r, th), dr, rtol=1e-11, atol=1e-300)
+    r_isco = api.isco(m)  # library host code (dual-number root find on the generated closed form)
+    assert r_isco == pytest.approx(oracle.isco(m.kind, mp), rel=1e-10)
+    assert 1.0 < r_isco < 9.0
+
+
+def test_kerr_limits_of_the_deformed_metrics():
+    """Zero deformation = Kerr (Johannsen, Kerr-Newman) / Schwarzschild (Bumblebee at a = 0, l = 0)."""
+    k = gb.KerrMetric(1.0, 0.6)
+    for m in (gb.JohannsenMetric(1.0, 0.6), gb.KerrNewmanMetric(1.0, 0.6, 0.0)):
+        for r, th in [(2.5, 0.7), (30.0, 1.5)]:
+            assert np.allclose(hostmath.metric_components(m, r, th), hostmath.metric_components(k, r, th), rtol=1e-13)
+        assert api.isco(m) == pytest.approx(api.isco(k), rel=1e-9)
+    assert api.isco(gb.BumblebeeMetric()) == pytest.approx(6.0, rel=1e-9)
+    assert api.inner_radius(gb.KerrNewmanMetric(1.0, 0.6, 0.5)) == pytest.approx(1.0 + math.sqrt(1 - 0.36 - 0.25))
+
+
+def test_constructor_checks_follow_the_reference():
+    with pytest.raises(ValueError):
+        gb.BumblebeeMetric(1.0, 0.0, -1.0)
+    with pytest.raises(ValueError):
+        gb.BumblebeeMetric(1.0, 0.5, 0.0)
+    with pytest.raises(ValueError):
+        gb.KerrNewmanMetric(1.0, 0.9, 0.9)
+
+
+# --------------------------------------------------------------------------- device
+@pytest.mark.gpu
+@pytest.mark.parametrize("m, shadow, thin, ss", SMOKE, ids=IDS)
+def test_device_reproduces_the_smoke_matrix(m, shadow, thin, ss):
+    x = [0.0, 100.0, math.radians(85), 0.0]
+    kw = dict(image_width=20, image_height=20, alpha_lims=(-9.5, 9.5), beta_lims=(-9.5, 9.5))
+    _, _, img = gb.rendergeodesics(m, x, 200.0, **kw)
+    assert np.nansum(img) == pytest.approx(shadow, rel=1e-6)
+    _, _, img = gb.rendergeodesics(m, x, gb.ThinDisc(0.0, 40.0), 200.0, **kw)
+    assert np.nansum(img) == pytest.approx(thin, rel=1e-6)
+    _, _, img = gb.rendergeodesics(m, x, gb.ShakuraSunyaev(m), 200.0, **kw)
+    assert np.nansum(img) == pytest.approx(ss, rel=0.1)  # current thick-disc source; the literal's legacy form is oracle-only
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m", NONTRIVIAL, ids=IDS)
+def test_device_matches_oracle_at_nontrivial_parameters(m):
+    x = [0.0, 1000.0, math.radians(70), 0.0]
+    d = gb.ThinDisc(api.isco(m), 40.0)
+    cfg = render_config(m, x, d, 2000.0, 96, 96, (-45, 45), (-30, 30))
+    p, ic = cfg.to_c()
+    want, ep = oracle.render(p, ic, [cabi.PF_REDSHIFT, cabi.PF_DISC_RADIUS], endpoints=True)
+    band = oracle.band_ratio(p, ic)
+    ep_l = oracle.trace(p, ic, precision=1)
+    graze = ((band > 0) & (band < 1.3)) | (ep.status != ep_l.status)
+    pfs = [gb.ConstPointFunctions.redshift(m, x) @ gb.ConstPointFunctions.filter_intersected(),
+           gb.ConstPointFunctions.radius() @ gb.ConstPointFunctions.filter_intersected()]
+    _, _, imgs = gb.rendergeodesics(m, x, d, 2000.0, pf=pfs, image_width=96, image_height=96, alpha_lims=(-45, 45), beta_lims=(-30, 30))
+    got = np.stack([im.T.reshape(-1) for im in imgs])
+    gps = api.solve_tracing_problem(cfg)
+    ok = ~graze
+    assert graze.mean() < 0.02
+    assert np.array_equal(np.asarray(gps.status)[ok], ep.status[ok])
+    hit = ok & (ep.status == cabi.STATUS_INTERSECTED)
+    assert hit.sum() > 500
+    assert np.max(np.abs(got[0][hit] - want[0][hit])) < 1e-6
+    assert np.max(np.abs(got[1][hit] / want[1][hit] - 1)) < 1e-6
+    assert np.array_equal(np.isnan(got[0][ok]), np.isnan(want[0][ok]))
