@@ -26,7 +26,9 @@ SMOKE = [
 ]
 NONTRIVIAL = [
     gb.JohannsenMetric(M=1.0, a=0.7, alpha13=0.35, alpha22=-0.2, alpha52=0.5, eps3=0.8),
-    gb.BumblebeeMetric(M=1.0, a=0.25, l=0.4),
+    # a = 0.1: the chart's inner boundary 1.01 (M + sqrt(M^2 - a^2)) = 2.015 stays outside this metric's coordinate
+    # singularity at r = 2M (for larger a the reference's inner_radius, bumblebee-ad.jl:51, lets rays run into it)
+    gb.BumblebeeMetric(M=1.0, a=0.1, l=0.4),
     gb.KerrNewmanMetric(M=1.0, a=0.6, Q=0.5),
 ]
 IDS = ["johannsen", "bumblebee", "kerr_newman"]
