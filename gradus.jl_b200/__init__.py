@@ -49,7 +49,7 @@ from .api import (  # noqa: F401
     tracegeodesics_batch,
     tracing_configuration,
 )
-from . import corona, hostmath, tf_integration  # noqa: F401
+from . import corona, hostmath, reverberation, tf_integration  # noqa: F401
 from ._cabi import GradusB200Error  # noqa: F401
 from .transfer_functions import (  # noqa: F401
     CunninghamTransferData,

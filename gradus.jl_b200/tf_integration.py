@@ -237,3 +237,81 @@ def lineprofile_transfer_functions(bins, emissivity: Callable, m, x, d, *, min_r
     bins = np.asarray(bins, np.float64)
     itb = transferfunctions(m, x, d, min_re=min_re, max_re=max_re, num_re=num_re, **kwargs)
     return bins, integrate_lineprofile(emissivity, itb, bins, h=h, n_radii=n_radii)
+
+
+# --------------------------------------------------------------------------- lag (2-D) transfer functions
+def _time_interpolate(t0, f1, f2, gs, h):
+    """integration.jl:73-84: near the ends of the g✶ range blend the two branches' times."""
+    lo, hi = gs < h, gs > 1 - h
+    if not (lo.any() or hi.any()):
+        return t0
+    w = np.where(lo, gs / h, 1 - (1 - gs) / h)
+    t1 = np.where(lo, f1(np.full_like(gs, h)), f1(np.full_like(gs, 1 - h)))
+    t2 = np.where(lo, f2(np.full_like(gs, h)), f2(np.full_like(gs, 1 - h)))
+    return np.where(lo | hi, t1 * w + (1 - w) * t2, t0)
+
+
+def _time_gstar(br: TransferBranches, gs, h):
+    tl, tu = br.lower_t(gs), br.upper_t(gs)
+    return _time_interpolate(tl, br.lower_t, br.upper_t, gs, h), _time_interpolate(tu, br.upper_t, br.lower_t, gs, h)
+
+
+def geometric_grid(lo, hi, n):
+    """Grids._geometric_grid (src/image-planes/grids.jl:16-19)"""
+    return lo * (hi / lo) ** (np.arange(n) / (n - 1))
+
+
+def integrate_lagtransfer(profile, itb: InterpolatingTransferBranches, g_grid, t_grid, *, rmin=None, rmax=None, g_scale=1.0,
+                          h=1e-8, n_radii=1000, g_grid_upscale=1, quadrature_points=7, t0=0.0):
+    """`integrate_lagtransfer(prof, tfs, g_grid, t_grid; t0, n_radii, rmin, rmax)` (integration.jl:256-279, 359-442):
+    flux[energy bin, time bin]; `profile` gives emissivity_at(r) and coordtime_at(r)."""
+    g_grid = np.asarray(g_grid, np.float64)
+    t_grid = np.asarray(t_grid, np.float64)
+    rmin = itb.inner_radius() if rmin is None else rmin
+    rmax = itb.outer_radius() if rmax is None else rmax
+    rule = _gauss(quadrature_points)
+    out = np.zeros((g_grid.size, t_grid.size))
+    radii = geometric_grid(rmin, rmax, n_radii)
+    r_prev = rmin - (radii[1] - rmin)
+    nt = t_grid.size
+    rows = np.arange(g_grid.size - 1)
+    for r_e in radii:
+        br = itb(r_e)
+        span = br.gmax - br.gmin
+
+        def branch(fn, br=br, span=span):
+            def S(g):
+                gs = (g - br.gmin) / span
+                f = fn(gs)
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    return g * g * np.where(np.isnan(f), 0.0, f) * g / np.sqrt(gs * (1 - gs))
+            return S
+
+        S_lower, S_upper = branch(br.lower_f), branch(br.upper_f)
+        weight = (r_e - r_prev) * r_e * float(profile.emissivity_at(r_e)) * math.pi / span
+        t_sd = float(profile.coordtime_at(r_e)) - t0
+        glo = np.clip(g_grid[:-1] / g_scale, br.gmin, br.gmax)
+        ghi = np.clip(g_grid[1:] / g_scale, br.gmin, br.gmax)
+        live = glo != ghi
+        dg = (ghi - glo) / g_grid_upscale
+        for i in range(g_grid_upscale):
+            flo = glo + i * dg
+            fhi = flo + dg
+            k1 = _integrate_bins(S_lower, flo, fhi, br.gmin, br.gmax, h, rule)
+            k2 = _integrate_bins(S_upper, flo, fhi, br.gmin, br.gmax, h, rule)
+            gs_lo = np.clip((flo - br.gmin) / span, 0, 1)
+            gs_hi = np.clip((fhi - br.gmin) / span, 0, 1)
+            tl1, tu1 = _time_gstar(br, gs_lo, h)
+            tl2, tu2 = _time_gstar(br, gs_hi, h)
+            i1 = np.searchsorted(t_grid, (tl1 + tl2) / 2 + t_sd, side="left")
+            i2 = np.searchsorted(t_grid, (tu1 + tu2) / 2 + t_sd, side="left")
+            ok1, ok2 = live & (i1 < nt), live & (i2 < nt)
+            np.add.at(out, (rows[ok1], i1[ok1]), k1[ok1] * weight)
+            np.add.at(out, (rows[ok2], i2[ok2]), k2[ok2] * weight)
+        r_prev = r_e
+    # _normalize! (matrix form), transfer-functions/utils.jl:135-147 — the caller receives the Σ = 1 array
+    out[:-1] = out[:-1] / (g_grid[1:] + g_grid[:-1])[:, None]
+    total = out[:-1].sum()
+    if total > 0:
+        out = out / total
+    return out

@@ -1,0 +1,95 @@
+"""Lag transfer functions (second half) against the reference's own test, literal for literal
+(test/transfer-functions/test-2d.jl): hit counts of both legs, the binned 2-D transfer function, and the
+semi-analytic path (sampled-sky emissivity profile × Cunningham transfer functions × time-resolved quadrature)."""
+import math
+
+import numpy as np
+import pytest
+
+import gradus_b200 as gb
+from gradus_b200 import _cabi as cabi
+from gradus_b200 import api, corona
+from gradus_b200 import reverberation as rv
+from gradus_b200 import tf_integration as ti
+
+import common
+from oracle import oracle
+
+REF_OBSERVER_TO_DISC = 337          # test-2d.jl:25
+REF_SOURCE_TO_DISC = 58             # test-2d.jl:26
+REF_BINFLUX_SUM = 3.9126785201177956  # test-2d.jl:32, atol 1e-2
+REF_LAG_ROW_40 = 0.021759503160585468  # test-2d.jl:65, atol 1e-4
+
+
+def fixture():
+    m = gb.KerrMetric(1.0, 0.998)
+    x = [0.0, 1e6, math.radians(30), 0.0]
+    plane = gb.PolarPlane(gb.GeometricGrid(), Nr=20, Ntheta=20)
+    d = gb.ThinDisc(gb.isco(m), 500.0)
+    model = corona.LampPostModel(h=10.0, theta=math.radians(0.0001))
+    return m, x, plane, d, model
+
+
+def oracle_evaluator(config, pfs):
+    p, ic = config.to_c()
+    return oracle.render(p, ic, [f.kind() for f in pfs])
+
+
+def run_reference_test(solver=None, evaluator=None, prober_cls=None):
+    m, x, plane, d, model = fixture()
+    sampler = corona.EvenSampler("both", "golden")
+    lt = rv.lagtransfer(m, x, d, model, plane=plane, n_samples=100, sampler=sampler, solver=solver, evaluator=evaluator)
+    t, E, f = rv.binflux(lt, N_t=100, N_E=100)
+    prof = corona.emissivity_profile(m, d, model, n_samples=5000, sampler=sampler, solver=solver)
+    radii = ti.inverse_grid(gb.isco(m), 100.0, 5)
+    d2 = gb.ThinDisc(0.0, 500.0)
+    kw = {} if prober_cls is None else {"prober": prober_cls(m, x, d2)}
+    itb = ti.transferfunctions(m, x, d2, radii=radii, **kw)
+    flux = ti.integrate_lagtransfer(prof, itb, np.linspace(0.0, 1.5, 100), np.linspace(0.0, 150.0, 100), t0=x[1], n_radii=1000,
+                                    rmin=radii.min(), rmax=radii.max())
+    return lt, (t, E, f), flux
+
+
+def check(lt, binned, flux, tol_sum, tol_row):
+    t, E, f = binned
+    assert lt.observer_to_disc_count == REF_OBSERVER_TO_DISC
+    assert lt.coronal_geodesics.geodesic_points["x"].shape[1] == REF_SOURCE_TO_DISC
+    assert f.shape == (100, 100) and 0 < t[0] < 100 and 0 < E[0] < E[-1] < 6.4 * 1.6
+    assert abs(np.nansum(f) - REF_BINFLUX_SUM) < tol_sum
+    assert flux.sum() == pytest.approx(1.0) and np.all(flux[-1] == 0)
+    assert abs(flux[39].sum() - REF_LAG_ROW_40) < tol_row
+
+
+@pytest.fixture
+def oracle_plunging_kerr():
+    m = gb.KerrMetric(1.0, 0.998)
+    key = (type(m).__name__, m.params())
+    saved = api._PLUNGING_CACHE.get(key)
+    api._PLUNGING_CACHE[key] = api.PlungingInterpolation(*common.oracle_plunging_table(cabi.METRIC_KERR, [1.0, 0.998]))
+    yield
+    if saved is None:
+        api._PLUNGING_CACHE.pop(key, None)
+    else:
+        api._PLUNGING_CACHE[key] = saved
+
+
+def test_two_dimensional_simple_bucket():
+    tb, eb, td = rv.bin_transfer_function(np.array([0.0, 0.49, 1.0, 1.0]), np.array([2.0, 2.0, 3.0, 2.5]), np.array([1.0, 2.0, 4.0, 8.0]),
+                                          N_E=3, N_t=3)
+    assert np.allclose(eb, [2.0, 2.5, 3.0]) and np.allclose(tb, [0.0, 0.5, 1.0])
+    want = np.full((3, 3), np.nan)
+    want[0, 0] = 3.0 / 0.25   # (E=2, t=0) and (E=2, t=0.49) share the lower-edge-labelled cell
+    want[2, 2] = 4.0 / 0.25   # values on the last edge go to the last slot
+    want[1, 2] = 8.0 / 0.25
+    assert np.array_equal(np.isnan(td), np.isnan(want)) and np.allclose(td[~np.isnan(td)], want[~np.isnan(want)])
+
+
+def test_reference_reverberation_literals_with_the_oracle_tracer(oracle_plunging_kerr):
+    lt, binned, flux = run_reference_test(solver=common.oracle_solver, evaluator=oracle_evaluator, prober_cls=common.OracleProber)
+    check(lt, binned, flux, tol_sum=1e-4, tol_row=1e-5)  # the reference quotes 1e-2 and 1e-4
+
+
+@pytest.mark.gpu
+def test_reference_reverberation_literals_on_the_device():
+    lt, binned, flux = run_reference_test()
+    check(lt, binned, flux, tol_sum=1e-4, tol_row=1e-5)
