@@ -258,6 +258,7 @@ class ImpactParameters:
 
     alpha: Any
     beta: Any
+    height: Any = None  # optional per-ray datum-plane heights (`datumplane(d, rₑ)` of many radii in one launch)
 
     def trajectory_count(self):
         return len(self.alpha)
@@ -408,6 +409,12 @@ class TracingConfiguration:
             p.observer[:] = pos
             ic.kind = cabi.IC_IMPACT_PARAMETERS
             ic.x[0], ic.x[1] = cabi.dptr(al), cabi.dptr(be)
+            if v.height is not None:
+                hg = np.ascontiguousarray(np.broadcast_to(np.asarray(v.height, np.float64), al.shape))
+                if not isinstance(self.geometry, DatumPlane):
+                    raise ValueError("per-ray heights need a DatumPlane geometry")
+                self._keep.append(hg)
+                ic.x[2] = cabi.dptr(hg)
             ic.n = len(al)
         elif isinstance(v, CartesianPlane):
             p.observer[:] = pos

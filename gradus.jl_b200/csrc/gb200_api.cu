@@ -283,7 +283,9 @@ static int upload(gb200_ctx* ctx, size_t slot, const void* host, size_t bytes, c
 
 static int upload_ic_and_tables(gb200_ctx* ctx, const gb200_ic* ic, const gb200_plunging_table* pl, const gb200_emissivity* em, GbParams& P) {
     if (ic->kind == GB200_IC_IMPACT_PARAMETERS) {
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < 3; ++k) {
+            P.ex[k] = nullptr;
+            if (k == 2 && !ic->x[2]) continue; // optional per-ray datum-plane heights
             const void* d;
             int rc = upload(ctx, SL_EX0 + k, ic->x[k], sizeof(double) * ic->n, &d); if (rc) return rc;
             P.ex[k] = (const double*)d;

@@ -519,8 +519,9 @@ GB_HD inline double constrain_vt(const double g[5], double vr, double vth, doubl
 }
 
 // ---------------------------------------------------------------- disc conditions (distance_to_disc)
+// `hgt` is the datum-plane height of this ray (P.gp0 unless the IC carries per-ray heights); unused otherwise.
 template <int GEOM>
-GB_HD inline double disc_condition(const GbParams& P, double r, double s, double c) {
+GB_HD inline double disc_condition(const GbParams& P, double r, double s, double c, double hgt) {
     if (GEOM == GB200_GEOMETRY_THIN_DISC) { // thin-disc.jl:20-26 with _gtol_error = gtol*|r| (discs.jl:7)
         const double rho = r * fabs(s);
         if (rho < P.gp0 || rho > P.gp1) return 1.0;
@@ -532,7 +533,7 @@ GB_HD inline double disc_condition(const GbParams& P, double r, double s, double
         if (h <= 0.0) return 1.0;
         return r * fabs(c) - h;
     } else if (GEOM == GB200_GEOMETRY_DATUM_PLANE) { // datum-plane.jl:6-10
-        return r * c - P.gp0;
+        return r * c - hgt;
     }
     return 1.0;
 }

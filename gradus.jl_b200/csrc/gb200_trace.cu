@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
     double qoldpow = 1; // controller memory: beta2 * log(qold) (POW_EXACT) or qold^beta2 (POW_FAST32)
     double tfinal = 0;
     double E_obs = 0, area = 1; // per-ray constants fixed at refill (redshift numerator, image-plane area weight)
+    double hgt = P.gp0;         // datum-plane height of this ray (only read when GEOM is the datum plane)
     int state = LANE_EMPTY, pend_status = GB200_STATUS_NO_STATUS;
     bool pend_event = false;
     int naccept = 0, nreject = 0, flags = 0;
@@ -169,10 +170,10 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                         double s_, c_;
                         if (lo > 0.0) {
                             gb_sincos(dense_eval(th, dt_step, lo, vth, C2t, C3t, C4t), &s_, &c_);
-                            flo = disc_condition<GEOM>(P, dense_eval(r, dt_step, lo, vr, C2r, C3r, C4r), s_, c_);
+                            flo = disc_condition<GEOM>(P, dense_eval(r, dt_step, lo, vr, C2r, C3r, C4r), s_, c_, hgt);
                         } else flo = cprev;
                         gb_sincos(dense_eval(th, dt_step, hi, vth, C2t, C3t, C4t), &s_, &c_);
-                        fhi = disc_condition<GEOM>(P, dense_eval(r, dt_step, hi, vr, C2r, C3r, C4r), s_, c_);
+                        fhi = disc_condition<GEOM>(P, dense_eval(r, dt_step, hi, vr, C2r, C3r, C4r), s_, c_, hgt);
                     }
                     if (fhi == 0.0) lo = hi;
                     else {
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                             if (!(mid > lo && mid < hi)) break;
                             double s_, c_;
                             gb_sincos(dense_eval(th, dt_step, mid, vth, C2t, C3t, C4t), &s_, &c_);
-                            const double fm = disc_condition<GEOM>(P, dense_eval(r, dt_step, mid, vr, C2r, C3r, C4r), s_, c_);
+                            const double fm = disc_condition<GEOM>(P, dense_eval(r, dt_step, mid, vr, C2r, C3r, C4r), s_, c_, hgt);
                             if (fm != 0.0 && (fm > 0.0) == (sprev > 0.0)) {
                                 lo = mid; flo = fm;
                                 if (side == -1) fhi *= 0.5;
@@ -299,6 +300,8 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                         lam = P.lam0; ct = ri.x[0]; r = ri.x[1]; th = ri.x[2]; ph = ri.x[3];
                         vt = ri.v[0]; vr = ri.v[1]; vth = ri.v[2]; vph = ri.v[3];
                         area = ri.area;
+                        if (GEOM == GB200_GEOMETRY_DATUM_PLANE && P.ic_kind == GB200_IC_IMPACT_PARAMETERS && P.ex[2])
+                            hgt = P.ex[2][ray_index_of_slot(P, s)];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) { // GeodesicPoint.x_init / v_init are known now
                             if (P.o_x0[k]) P.o_x0[k][s] = ri.x[k];
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                         // f0 and the Hairer-Wanner initial step (ode_determine_initdt)
                         double acc[4], s_, c_;
                         rhs_accel<METRIC>(P, r, th, vt, vr, vth, vph, acc, s_, c_);
-                        if (GEOM != GB200_GEOMETRY_NONE) cprev = disc_condition<GEOM>(P, r, s_, c_);
+                        if (GEOM != GB200_GEOMETRY_NONE) cprev = disc_condition<GEOM>(P, r, s_, c_, hgt);
                         acos_prev = fabs(c_);
                         const double u0[8] = {ct, r, th, ph, vt, vr, vth, vph};
                         const double f0[8] = {vt, vr, vth, vph, acc[0], acc[1], acc[2], acc[3]};
@@ -445,7 +448,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                 bool event = false;
                 double cnext = 1.0;
                 if (GEOM != GB200_GEOMETRY_NONE) {
-                    cnext = disc_condition<GEOM>(P, nr, s_, c_);
+                    cnext = disc_condition<GEOM>(P, nr, s_, c_, hgt);
                     const double sprev = sgn(cprev);
                     if (sprev != 0.0) {
                         if (sprev * sgn(cnext) <= 0.0) { event = true; ev_lo = 0.0; ev_hi = 1.0; }
@@ -470,7 +473,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                                     const double Th = (double)i / 7.0;
                                     double si, ci;
                                     gb_sincos(dense_eval(th, dt, Th, vth, C2t, C3t, C4t), &si, &ci);
-                                    const double cn = disc_condition<GEOM>(P, dense_eval(r, dt, Th, vr, C2r, C3r, C4r), si, ci);
+                                    const double cn = disc_condition<GEOM>(P, dense_eval(r, dt, Th, vr, C2r, C3r, C4r), si, ci, hgt);
                                     if (sprev * cn < 0.0) { event = true; ev_lo = (double)(i - 1) / 7.0; ev_hi = Th; break; }
                                 }
                             }

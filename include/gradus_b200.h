@@ -103,7 +103,10 @@ typedef struct gb200_problem {
 #define GB200_IC_EXPLICIT 2    /* prob_func evaluated on the host into SoA (corona ensembles) */
 #define GB200_IC_CARTESIAN_PLANE 3 /* CartesianPlane, src/image-planes/planes.jl:130-178 */
 #define GB200_IC_IMPACT_PARAMETERS 4 /* map_impact_parameters(m, x, alphas, betas), src/tracing/utility.jl:70-87:
-                                        x[0] = alpha[n], x[1] = beta[n] (host arrays); observer = problem.observer */
+                                        x[0] = alpha[n], x[1] = beta[n] (host arrays); observer = problem.observer;
+                                        x[2] = optional height[n]: with GB200_GEOMETRY_DATUM_PLANE each ray meets its own
+                                        plane z = height[i] (datumplane(d, r_e) of many emission radii in one launch,
+                                        src/geometry/discs/datum-plane.jl:14-19), NULL = geometry_params[0] */
 
 #define GB200_GRID_LINEAR 0    /* src/image-planes/grids.jl:32-36 */
 #define GB200_GRID_GEOMETRIC 1 /* grids.jl:11-20 */

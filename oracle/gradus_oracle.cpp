@@ -411,11 +411,13 @@ static inline double grid_value(int kind, double lo, double hi, int64_t n, int64
     return jl_range(lo, hi, n, i);
 }
 
-struct RayIC { double x[4]; double alpha, beta, area; double v[4]; bool explicit_v; };
+struct RayIC { double x[4]; double alpha, beta, area; double v[4]; bool explicit_v; bool has_height; double height; };
 
 static void ic_for_ray(const gb200_problem& p, const gb200_ic& ic, int64_t i, RayIC& out) {
     for (int k = 0; k < 4; ++k) out.x[k] = p.observer[k];
     out.explicit_v = false;
+    out.has_height = false;
+    out.height = 0.0;
     out.area = 1.0;
     if (ic.kind == GB200_IC_RENDER_GRID) { // rendering.jl:140-163
         int64_t col = i / ic.height, row = i % ic.height;
@@ -433,6 +435,7 @@ static void ic_for_ray(const gb200_problem& p, const gb200_ic& ic, int64_t i, Ra
     } else if (ic.kind == GB200_IC_IMPACT_PARAMETERS) { // map_impact_parameters over (alpha, beta) lists, utility.jl:70-87
         out.alpha = ic.x[0][i];
         out.beta = ic.x[1][i];
+        if (ic.x[2]) { out.has_height = true; out.height = ic.x[2][i]; } // per-ray datum plane
     } else if (ic.kind == GB200_IC_CARTESIAN_PLANE) { // planes.jl:152-171
         int64_t hx = ic.width / 2, hy = ic.height / 2;
         int64_t rows = 2 * hy - 1; // X_size
@@ -933,8 +936,10 @@ int run(const gb200_problem& p, const gb200_ic& ic, const gb200_range& rg, int n
         // (the plane path's map_impact_parameters rebuilds the same transform per ray, utility.jl:84-87: identical values)
         T u0[8];
         initial_state<T>(p, m, ric, &xfm, u0);
+        gb200_problem pray = p; // per-ray datum-plane height (impact-parameter lists)
+        if (ric.has_height) pray.geometry_params[0] = ric.height;
         RayResult<T> res;
-        trace_ray<T>(p, m, u0, res);
+        trace_ray<T>(pray, m, u0, res);
         if (out) {
             if (out->status) out->status[n] = res.status;
             if (out->lambda_max) out->lambda_max[n] = (double)res.lambda;
