@@ -803,15 +803,15 @@ int gb200_debug_rhs(gb200_ctx* ctx, int32_t metric_kind, const double* mp, int64
     return GB200_OK;
 }
 
-int gb200_debug_math(gb200_ctx* ctx, int64_t n, const double* x, double* out3) {
-    if (!ctx || !x || !out3 || n < 1) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad arguments");
+int gb200_debug_math(gb200_ctx* ctx, int64_t n, const double* x, double* out5) {
+    if (!ctx || !x || !out5 || n < 1) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad arguments");
     CU(ctx, cudaSetDevice(ctx->device));
     void *d_x, *d_o;
     int rc = pool_get(ctx, SL_X0, sizeof(double) * (size_t)n, &d_x); if (rc) return rc;
-    rc = pool_get(ctx, SL_V0, sizeof(double) * 3 * (size_t)n, &d_o); if (rc) return rc;
+    rc = pool_get(ctx, SL_V0, sizeof(double) * 5 * (size_t)n, &d_o); if (rc) return rc;
     CU(ctx, cudaMemcpyAsync(d_x, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, gb200_launch_debug_math(n, (const double*)d_x, (double*)d_o, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(out3, d_o, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(out5, d_o, sizeof(double) * 5 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return GB200_OK;
 }

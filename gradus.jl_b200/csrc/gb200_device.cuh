@@ -303,6 +303,27 @@ __device__ __constant__ double gb_tab[] = {
     2.48015872894767294178e-05, // 62: GB_SC_C3
     -1.38888888888741095749e-03, // 63: GB_SC_C2
     4.16666666666666019037e-02, // 64: GB_SC_C1
+    6.93147180369123816490e-01, // 65: GB_LN2_HI
+    1.90821492927058770002e-10, // 66: GB_LN2_LO
+    6.666666666666735130e-01, // 67: GB_LG1
+    3.999999999940941908e-01, // 68: GB_LG2
+    2.857142874366239149e-01, // 69: GB_LG3
+    2.222219843214978396e-01, // 70: GB_LG4
+    1.818357216161805012e-01, // 71: GB_LG5
+    1.531383769920937332e-01, // 72: GB_LG6
+    1.479819860511658591e-01, // 73: GB_LG7
+    1.44269504088896338700e+00, // 74: GB_INVLN2
+    2.08767569878681e-09, // 75: GB_EX12
+    2.505210838544172e-08, // 76: GB_EX11
+    2.755731922398589e-07, // 77: GB_EX10
+    2.7557319223985893e-06, // 78: GB_EX9
+    2.48015873015873e-05, // 79: GB_EX8
+    0.0001984126984126984, // 80: GB_EX7
+    0.001388888888888889, // 81: GB_EX6
+    0.008333333333333333, // 82: GB_EX5
+    0.041666666666666664, // 83: GB_EX4
+    0.16666666666666666, // 84: GB_EX3
+    0.5, // 85: GB_EX2
 };
 #endif
 #define GB_SC_2OPI GB_TAB(49)
@@ -321,7 +342,28 @@ __device__ __constant__ double gb_tab[] = {
 #define GB_SC_C3 GB_TAB(62)
 #define GB_SC_C2 GB_TAB(63)
 #define GB_SC_C1 GB_TAB(64)
-static const double gb_tab_host[] = {0.161, -0.008480655492356989, 0.335480655492357, 2.8971530571054935, -6.359448489975075, 4.3622954328695815, 5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774, -0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629, 0.5823571654525552, -0.45808210592918697, 0.015151515151515152, -2.763706197274826, 2.9132554618219126, -1.0530884977290216, 0.13169999999999998, -0.2234, 0.1017, 3.9302962368947516, -5.941033872131505, 2.490627285651253, -12.411077166933676, 30.33818863028232, -16.548102889244902, 37.50931341651104, -88.1789048947664, 47.37952196281928, -27.896526289197286, 65.09189467479366, -34.87065786149661, 1.5, -4.0, 2.5, 0.63661977236758134308, 1.57079632673412561417e+00, 6.07710050650619224932e-11, 2.02226624879595063154e-21, 1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01, -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+#define GB_LN2_HI GB_TAB(65)
+#define GB_LN2_LO GB_TAB(66)
+#define GB_LG1 GB_TAB(67)
+#define GB_LG2 GB_TAB(68)
+#define GB_LG3 GB_TAB(69)
+#define GB_LG4 GB_TAB(70)
+#define GB_LG5 GB_TAB(71)
+#define GB_LG6 GB_TAB(72)
+#define GB_LG7 GB_TAB(73)
+#define GB_INVLN2 GB_TAB(74)
+#define GB_EX12 GB_TAB(75)
+#define GB_EX11 GB_TAB(76)
+#define GB_EX10 GB_TAB(77)
+#define GB_EX9 GB_TAB(78)
+#define GB_EX8 GB_TAB(79)
+#define GB_EX7 GB_TAB(80)
+#define GB_EX6 GB_TAB(81)
+#define GB_EX5 GB_TAB(82)
+#define GB_EX4 GB_TAB(83)
+#define GB_EX3 GB_TAB(84)
+#define GB_EX2 GB_TAB(85)
+static const double gb_tab_host[] = {0.161, -0.008480655492356989, 0.335480655492357, 2.8971530571054935, -6.359448489975075, 4.3622954328695815, 5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774, -0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629, 0.5823571654525552, -0.45808210592918697, 0.015151515151515152, -2.763706197274826, 2.9132554618219126, -1.0530884977290216, 0.13169999999999998, -0.2234, 0.1017, 3.9302962368947516, -5.941033872131505, 2.490627285651253, -12.411077166933676, 30.33818863028232, -16.548102889244902, 37.50931341651104, -88.1789048947664, 47.37952196281928, -27.896526289197286, 65.09189467479366, -34.87065786149661, 1.5, -4.0, 2.5, 0.63661977236758134308, 1.57079632673412561417e+00, 6.07710050650619224932e-11, 2.02226624879595063154e-21, 1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01, -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02, 6.93147180369123816490e-01, 1.90821492927058770002e-10, 6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01, 1.44269504088896338700e+00, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06, 2.48015873015873e-05, 0.0001984126984126984, 0.001388888888888889, 0.008333333333333333, 0.041666666666666664, 0.16666666666666666, 0.5};
 
 // ---------------------------------------------------------------- metrics
 // Kerr: components and Jacobian from w = 2Mr/Sigma (see DESIGN.md for the derivation).
@@ -399,12 +441,24 @@ GB_HD inline void geodesic_accel(const double g[5], const double dr[5], const do
     acc[3] = -(gitph * Pt + giphph * Pp);
 }
 
+#ifndef GB_OPT_SIGNFLIP
+#define GB_OPT_SIGNFLIP 1 /* quadrant signs of sincos through the integer pipe */
+#endif
+#ifndef GB_OPT_KERR_SQ
+#define GB_OPT_KERR_SQ 1 /* Kerr RHS from sin^2, cos^2, sin 2theta of the reduced argument (signs of sin, cos only where needed) */
+#endif
 #ifdef __CUDACC__
 // Branch-free sincos for the polar angle (|x| << 2^20 rad always holds: theta is bounded by the number of polar
 // passages): Cody-Waite reduction by pi/2 in three parts, fdlibm __kernel_sin/__kernel_cos minimax polynomials on
 // [-pi/4, pi/4] (< 1 ulp), quadrant fix-up with selects.  The CUDA library sincos() carries a Payne-Hanek slow
 // path behind a divergent branch; this has none.
-GB_D void gb_sincos(double x, double* sp, double* cp) {
+// x with its sign flipped when bit 31 of `signbit31` is set (integer pipe; a DADD negate + select costs FP64 issue slots)
+GB_D double gb_flip_sign(double x, int signbit31) {
+    return __hiloint2double(__double2hiint(x) ^ (signbit31 & (int)0x80000000), __double2loint(x));
+}
+// Reduced form: x = n pi/2 + rr, returns sn = sin(rr), cs = cos(rr) and the quadrant n.
+struct GbSinCos { double sn, cs; int n; };
+GB_D GbSinCos gb_sincos_reduced(double x) {
     const double q = rint(x * GB_SC_2OPI);
     double rr = fma(-q, GB_SC_PIO2_1, x);
     rr = fma(-q, GB_SC_PIO2_2, rr);
@@ -422,21 +476,73 @@ GB_D void gb_sincos(double x, double* sp, double* cp) {
     pc = fma(z, pc, GB_SC_C2);
     pc = fma(z, pc, GB_SC_C1);
     const double cs = fma(z * z, pc, fma(z, -0.5, 1.0));
-    const int n = __double2int_rn(q);
-    const bool swap = (n & 1) != 0;
-    double so = swap ? cs : sn;
-    double co = swap ? sn : cs;
-    if (n & 2) so = -so;
-    if ((n + 1) & 2) co = -co;
-    *sp = so;
-    *cp = co;
+    GbSinCos o;
+    o.sn = sn; o.cs = cs; o.n = __double2int_rn(q);
+    return o;
+}
+GB_D void gb_sincos(double x, double* sp, double* cp) {
+    const GbSinCos o = gb_sincos_reduced(x);
+    const bool swap = (o.n & 1) != 0;
+    const double so = swap ? o.cs : o.sn;
+    const double co = swap ? o.sn : o.cs;
+#if GB_OPT_SIGNFLIP
+    *sp = gb_flip_sign(so, o.n << 30);       // n & 2
+    *cp = gb_flip_sign(co, (o.n + 1) << 30); // (n + 1) & 2
+#else
+    *sp = (o.n & 2) ? -so : so;
+    *cp = ((o.n + 1) & 2) ? -co : co;
+#endif
+}
+
+// Branch-free natural logarithm for the step controller (argument: the error estimate, a positive normal double or 0).
+// fdlibm/musl __log: x = 2^k m with m in [sqrt(1/2), sqrt(2)), f = m - 1, s = f/(2+f), log m = f - f^2/2 + s (f^2/2 + R(s^2));
+// < 1 ulp.  x = 0 returns a large negative number (about -745) instead of -inf, which the controller clamps the same way.
+// The library log() carries denormal/inf/nan branches and ~20 literal coefficients that each cost two moves per use.
+GB_D double gb_log_pos(double x) {
+    int hx = __double2hiint(x);
+    const int lx = __double2loint(x);
+    hx += 0x3ff00000 - 0x3fe6a09e;
+    const int k = (hx >> 20) - 0x3ff;
+    hx = (hx & 0x000fffff) + 0x3fe6a09e;
+    const double m = __hiloint2double(hx, lx);
+    const double f = m - 1.0;
+    const double hfsq = 0.5 * f * f;
+    const double sq = f * gb_rcp(2.0 + f);
+    const double z = sq * sq, w = z * z;
+    const double t1 = w * fma(w, fma(w, GB_LG6, GB_LG4), GB_LG2);
+    const double t2 = z * fma(w, fma(w, fma(w, GB_LG7, GB_LG5), GB_LG3), GB_LG1);
+    const double R = t2 + t1;
+    const double dk = (double)k;
+    return fma(dk, GB_LN2_HI, fma(sq, hfsq + R, dk * GB_LN2_LO) - hfsq + f);
+}
+// Branch-free exp for |x| <= 8 (the controller clamps its argument first): x = k ln2 + rr, degree-12 Taylor polynomial on
+// |rr| <= ln2/2 (truncation 1.7e-16 relative), scaled by 2^k through the exponent field.
+GB_D double gb_exp_small(double x) {
+    const double kf = rint(x * GB_INVLN2);
+    double rr = fma(-kf, GB_LN2_HI, x);
+    rr = fma(-kf, GB_LN2_LO, rr);
+    // Estrin-style split into even/odd halves keeps the dependency chain short
+    const double r2 = rr * rr;
+    double pe = fma(r2, GB_EX12, GB_EX10);
+    double po = fma(r2, GB_EX11, GB_EX9);
+    pe = fma(r2, pe, GB_EX8); po = fma(r2, po, GB_EX7);
+    pe = fma(r2, pe, GB_EX6); po = fma(r2, po, GB_EX5);
+    pe = fma(r2, pe, GB_EX4); po = fma(r2, po, GB_EX3);
+    pe = fma(r2, pe, GB_EX2);
+    // exp(rr) = 1 + rr + r2 * (pe + rr * po)
+    const double p = fma(r2, fma(rr, po, pe), rr) + 1.0;
+    const int k = __double2int_rn(kf);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
 // Kerr right-hand side with everything folded: two reciprocals (1/(Sigma Delta) and 1/sin^2) and the identity
 // g_tt g_phph - g_tph^2 = -Delta sin^2, so  g^tt = -B/Delta, g^tph = -a w/Delta, g^phph = (1 - w)/(Delta sin^2).
+GB_D void kerr_rhs_accel_sq(double M, double a, double r, double s2, double c2, double sin2, double vt, double vr, double vth, double vph, double acc[4]);
 GB_D void kerr_rhs_accel(double M, double a, double r, double s, double c, double vt, double vr, double vth, double vph, double acc[4]) {
-    const double a2 = a * a, r2 = r * r, s2 = s * s, c2 = c * c;
-    const double sin2 = 2.0 * s * c;
+    kerr_rhs_accel_sq(M, a, r, s * s, c * c, 2.0 * s * c, vt, vr, vth, vph, acc);
+}
+GB_D void kerr_rhs_accel_sq(double M, double a, double r, double s2, double c2, double sin2, double vt, double vr, double vth, double vph, double acc[4]) {
+    const double a2 = a * a, r2 = r * r;
     const double Sig = fma(a2, c2, r2);
     const double Del = fma(r, r - 2.0 * M, a2);
     const double R = gb_rcp(Sig * Del), is2 = gb_rcp(s2);
@@ -483,6 +589,20 @@ template <int METRIC>
 GB_RHS_ATTR GbAcc rhs_eval(const GbParams& P, double r, double th, double vt, double vr, double vth, double vph) {
     GbAcc o;
     double acc[4];
+#if GB_OPT_KERR_SQ
+    if (METRIC == GB200_METRIC_KERR) {
+        // squares and sin(2 theta) need no quadrant signs beyond the parity of n; the signed sin, cos are formed with
+        // integer operations and are dead code at the stages whose caller ignores them
+        const GbSinCos q = gb_sincos_reduced(th);
+        const bool swap = (q.n & 1) != 0;
+        const double sa = swap ? q.cs : q.sn, ca = swap ? q.sn : q.cs;
+        o.s = gb_flip_sign(sa, q.n << 30);
+        o.c = gb_flip_sign(ca, (q.n + 1) << 30);
+        kerr_rhs_accel_sq(P.M, P.a, r, sa * sa, ca * ca, gb_flip_sign(2.0 * sa * ca, q.n << 31), vt, vr, vth, vph, acc);
+        o.a0 = acc[0]; o.a1 = acc[1]; o.a2 = acc[2]; o.a3 = acc[3];
+        return o;
+    }
+#endif
     gb_sincos(th, &o.s, &o.c);
     if (METRIC == GB200_METRIC_KERR) {
         kerr_rhs_accel(P.M, P.a, r, o.s, o.c, vt, vr, vth, vph, acc);

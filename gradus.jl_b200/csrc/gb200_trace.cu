@@ -41,6 +41,17 @@
 #define GB_SYNC_EVERY 4 /* barrier (and service decision) every n-th attempt */
 #endif
 
+#ifndef GB_OPT_LOGEXP
+#define GB_OPT_LOGEXP 1 /* branch-free log/exp with constant-bank coefficients in the step controller */
+#endif
+
+#ifndef GB_OPT_INTMAX
+#define GB_OPT_INTMAX 1 /* event-scan pre-test bound from integer maxima of the high words */
+#endif
+#ifndef GB_OPT_ERRDT
+#define GB_OPT_ERRDT 1 /* error norm with dt factored out of the eight components */
+#endif
+
 #define LANE_EMPTY 0
 #define LANE_RUN 1
 #define LANE_PENDING 2
@@ -84,6 +95,16 @@ GB_D double ctrl_pow_log(double logx, double x, double y, int mode) {
     return exp(y * logx);
 }
 
+// An upper bound of max_i |a_i| from the high words alone (integer pipe): doubles order like their bit patterns, and
+// (hi + 1, 0) exceeds every double whose high word is hi.  inf/nan inputs give a nan bound, which the caller's
+// comparisons treat as "cannot skip".
+GB_D double absmax7_bound(double a0, double a1, double a2, double a3, double a4, double a5, double a6) {
+    const int m = 0x7fffffff;
+    const int h = max(max(max(__double2hiint(a0) & m, __double2hiint(a1) & m), max(__double2hiint(a2) & m, __double2hiint(a3) & m)),
+                      max(max(__double2hiint(a4) & m, __double2hiint(a5) & m), __double2hiint(a6) & m));
+    return __hiloint2double(h + 1, 0);
+}
+
 // Can the disc condition become negative anywhere on this step?  Conservative bound from the dense-output
 // polynomial: |u(Th) - u0| <= |dt| (|C1| + |C2| + |C3| + |C4|) for Th in [0, 1], and |cos| is 1-Lipschitz.
 // Returning false lets the caller skip the 6 interior samples (they would all be positive).
@@ -116,7 +137,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
     double nct = 0, nr = 0, nth = 0, nph = 0, nvt = 0, nvr = 0, nvth = 0, nvph = 0; // u (proposed / final)
     double kA0[7], kA1[7], kA2[7], kA3[7]; // accelerations: [0] = FSAL k1, [1..5] = k2..k6, [6] = k7
     double kR[6], kT[6];                   // stage velocities v^r, v^theta of k2..k6 ([0] unused: k1's are vr, vth)
-    double dt = 0, dt_step = 0, cprev = 1, acos_prev = 1, ev_lo = 0, ev_hi = 0;
+    double dt = 0, cprev = 1, acos_prev = 1, ev_lo = 0, ev_hi = 0;
     double qoldpow = 1; // controller memory: beta2 * log(qold) (POW_EXACT) or qold^beta2 (POW_FAST32)
     double tfinal = 0;
     double E_obs = 0, area = 1; // per-ray constants fixed at refill (redshift numerator, image-plane area weight)
@@ -169,11 +190,11 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                     {
                         double s_, c_;
                         if (lo > 0.0) {
-                            gb_sincos(dense_eval(th, dt_step, lo, vth, C2t, C3t, C4t), &s_, &c_);
-                            flo = disc_condition<GEOM>(P, dense_eval(r, dt_step, lo, vr, C2r, C3r, C4r), s_, c_, hgt);
+                            gb_sincos(dense_eval(th, dt, lo, vth, C2t, C3t, C4t), &s_, &c_);
+                            flo = disc_condition<GEOM>(P, dense_eval(r, dt, lo, vr, C2r, C3r, C4r), s_, c_, hgt);
                         } else flo = cprev;
-                        gb_sincos(dense_eval(th, dt_step, hi, vth, C2t, C3t, C4t), &s_, &c_);
-                        fhi = disc_condition<GEOM>(P, dense_eval(r, dt_step, hi, vr, C2r, C3r, C4r), s_, c_, hgt);
+                        gb_sincos(dense_eval(th, dt, hi, vth, C2t, C3t, C4t), &s_, &c_);
+                        fhi = disc_condition<GEOM>(P, dense_eval(r, dt, hi, vr, C2r, C3r, C4r), s_, c_, hgt);
                     }
                     if (fhi == 0.0) lo = hi;
                     else {
@@ -187,8 +208,8 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                             if (!(mid > lo && mid < hi)) mid = 0.5 * (lo + hi);
                             if (!(mid > lo && mid < hi)) break;
                             double s_, c_;
-                            gb_sincos(dense_eval(th, dt_step, mid, vth, C2t, C3t, C4t), &s_, &c_);
-                            const double fm = disc_condition<GEOM>(P, dense_eval(r, dt_step, mid, vr, C2r, C3r, C4r), s_, c_, hgt);
+                            gb_sincos(dense_eval(th, dt, mid, vth, C2t, C3t, C4t), &s_, &c_);
+                            const double fm = disc_condition<GEOM>(P, dense_eval(r, dt, mid, vr, C2r, C3r, C4r), s_, c_, hgt);
                             if (fm != 0.0 && (fm > 0.0) == (sprev > 0.0)) {
                                 lo = mid; flo = fm;
                                 if (side == -1) fhi *= 0.5;
@@ -214,11 +235,11 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                     // stage v^t, v^phi are recomputed from the stored accelerations (bitwise the same values)
                     double W0[7], W3[7], WR[7], WT[7];
                     W0[0] = vt; W3[0] = vph; WR[0] = vr; WT[0] = vth;
-                    W0[1] = comb<1>(vt, dt_step, kA0[0], kA0); W3[1] = comb<1>(vph, dt_step, kA3[0], kA3);
-                    W0[2] = comb<2>(vt, dt_step, kA0[0], kA0); W3[2] = comb<2>(vph, dt_step, kA3[0], kA3);
-                    W0[3] = comb<3>(vt, dt_step, kA0[0], kA0); W3[3] = comb<3>(vph, dt_step, kA3[0], kA3);
-                    W0[4] = comb<4>(vt, dt_step, kA0[0], kA0); W3[4] = comb<4>(vph, dt_step, kA3[0], kA3);
-                    W0[5] = comb<5>(vt, dt_step, kA0[0], kA0); W3[5] = comb<5>(vph, dt_step, kA3[0], kA3);
+                    W0[1] = comb<1>(vt, dt, kA0[0], kA0); W3[1] = comb<1>(vph, dt, kA3[0], kA3);
+                    W0[2] = comb<2>(vt, dt, kA0[0], kA0); W3[2] = comb<2>(vph, dt, kA3[0], kA3);
+                    W0[3] = comb<3>(vt, dt, kA0[0], kA0); W3[3] = comb<3>(vph, dt, kA3[0], kA3);
+                    W0[4] = comb<4>(vt, dt, kA0[0], kA0); W3[4] = comb<4>(vph, dt, kA3[0], kA3);
+                    W0[5] = comb<5>(vt, dt, kA0[0], kA0); W3[5] = comb<5>(vph, dt, kA3[0], kA3);
                     W0[6] = nvt; W3[6] = nvph; WR[6] = nvr; WT[6] = nvth;
 #pragma unroll
                     for (int j = 1; j < 6; ++j) { WR[j] = kR[j]; WT[j] = kT[j]; }
@@ -228,9 +249,9 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                         st = fma(b[j], W0[j], st); sr = fma(b[j], WR[j], sr); sth = fma(b[j], WT[j], sth); sph = fma(b[j], W3[j], sph);
                         s0 = fma(b[j], kA0[j], s0); s1 = fma(b[j], kA1[j], s1); s2 = fma(b[j], kA2[j], s2); s3 = fma(b[j], kA3[j], s3);
                     }
-                    nct = fma(dt_step, st, ct); nr = fma(dt_step, sr, r); nth = fma(dt_step, sth, th); nph = fma(dt_step, sph, ph);
-                    nvt = fma(dt_step, s0, vt); nvr = fma(dt_step, s1, vr); nvth = fma(dt_step, s2, vth); nvph = fma(dt_step, s3, vph);
-                    tfinal = fma(Th, dt_step, tfinal); // tfinal held lambda_prev for event lanes
+                    nct = fma(dt, st, ct); nr = fma(dt, sr, r); nth = fma(dt, sth, th); nph = fma(dt, sph, ph);
+                    nvt = fma(dt, s0, vt); nvr = fma(dt, s1, vr); nvth = fma(dt, s2, vth); nvph = fma(dt, s3, vph);
+                    tfinal = fma(Th, dt, tfinal); // tfinal held lambda_prev for event lanes
                     status = GB200_STATUS_INTERSECTED_WITH_GEOMETRY;
                     // DiscreteCallbacks still run on the event state (handle_callbacks!): user, then chart
                     if (P.callback_kind == GB200_CALLBACK_UPPER_HEMISPHERE && nr * cos(nth) < P.callback_delta) status = GB200_STATUS_OUT_OF_DOMAIN;
@@ -411,9 +432,14 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
             // ---- error estimate: rms( dt*sum btilde_j k_j / (abstol + max(|u_prev|,|u|) reltol) )
             double ee = 0;
             {
-                const double e0 = dt * terr, e1 = dt * errcomb(vr, kR, nvr), e2 = dt * errcomb(vth, kT, nvth), e3 = dt * perr;
-                const double e4 = dt * errcomb(kA0[0], kA0, kA0[6]), e5 = dt * errcomb(kA1[0], kA1, kA1[6]);
-                const double e6 = dt * errcomb(kA2[0], kA2, kA2[6]), e7 = dt * errcomb(kA3[0], kA3, kA3[6]);
+#if GB_OPT_ERRDT
+                const double edt = 1.0; // dt multiplies the norm once, below
+#else
+                const double edt = dt;
+#endif
+                const double e0 = edt * terr, e1 = edt * errcomb(vr, kR, nvr), e2 = edt * errcomb(vth, kT, nvth), e3 = edt * perr;
+                const double e4 = edt * errcomb(kA0[0], kA0, kA0[6]), e5 = edt * errcomb(kA1[0], kA1, kA1[6]);
+                const double e6 = edt * errcomb(kA2[0], kA2, kA2[6]), e7 = edt * errcomb(kA3[0], kA3, kA3[6]);
                 double q_;
                 q_ = e0 * gb_rcp_lo(fma(fmax(fabs(ct), fabs(nct)), reltol, abstol)); ee = fma(q_, q_, ee);
                 q_ = e1 * gb_rcp_lo(fma(fmax(fabs(r), fabs(nr)), reltol, abstol)); ee = fma(q_, q_, ee);
@@ -424,87 +450,111 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                 q_ = e6 * gb_rcp_lo(fma(fmax(fabs(vth), fabs(nvth)), reltol, abstol)); ee = fma(q_, q_, ee);
                 q_ = e7 * gb_rcp_lo(fma(fmax(fabs(vph), fabs(nvph)), reltol, abstol)); ee = fma(q_, q_, ee);
             }
+#if GB_OPT_ERRDT
+            const double EEst = fabs(dt) * sqrt(ee * 0.125);
+#else
             const double EEst = sqrt(ee * 0.125);
-            // PI controller (stepsize_controller!, OrdinaryDiffEq): q = EEst^beta1 / qold^beta2 / gamma, clamped.
-            // In the default pow mode this is one log and one exp: q = exp(beta1 log EEst - beta2 log qold) / gamma.
-            double q, logE = 0.0;
+#endif
+            // PI controller (stepsize_controller!, OrdinaryDiffEq): q = EEst^beta1 / qold^beta2 / gamma, clamped; a rejected
+            // attempt uses EEst^beta1 / gamma (step_reject_controller!).  One log and one exp serve both:
+            // exp(beta1 log EEst - [accepted] beta2 log qold).  EEst = 0 gives log = -inf, exp = 0, q = 1/qmax as required.
+            const bool accept = EEst <= 1.0;
             const bool fast32 = (P.pow_mode == GB200_POW_FAST32);
-            if (EEst == 0.0) q = 1.0 / qmax;
-            else {
-                logE = log(EEst);
-                if (fast32) q = ctrl_pow_log(logE, EEst, beta1, P.pow_mode) * gb_rcp(qoldpow);
-                else q = exp(fma(beta1, logE, -qoldpow)); // qoldpow holds beta2 * log(qold) in this mode
-                q = fmax(1.0 / qmax, fmin(1.0 / qmin, q * (1.0 / gamma)));
+#if GB_OPT_LOGEXP
+            const double logE = gb_log_pos(EEst);
+#else
+            const double logE = log(EEst);
+#endif
+            double Epow;
+            if (fast32) {
+                Epow = ctrl_pow_log(logE, EEst, beta1, P.pow_mode);
+                if (accept) Epow *= gb_rcp(qoldpow);
+            } else {
+                const double arg = accept ? fma(beta1, logE, -qoldpow) : beta1 * logE; // qoldpow = beta2 * log(qold) in this mode
+#if GB_OPT_LOGEXP
+                Epow = gb_exp_small(fmax(-8.0, fmin(8.0, arg))); // q is clamped to [1/qmax, 1/qmin] = exp(-2.2 .. 1.7) afterwards
+#else
+                Epow = exp(arg);
+#endif
             }
-            if (EEst <= 1.0) {
-                ++naccept;
-                const double dtnew = dt * gb_rcp(q);
-                if (fast32) qoldpow = ctrl_pow_log(fmax(logE, log_qoldinit), fmax(EEst, 1e-4), beta2, P.pow_mode);
-                else qoldpow = beta2 * ((EEst == 0.0) ? log_qoldinit : fmax(logE, log_qoldinit));
-                const double ttmp = lam + dt;
-                const double tnew = (fabs(ttmp - tstop) < 100.0 * (fabs(tstop) * 2.220446049250313e-16)) ? tstop : ttmp;
-                const double dtprop = fmax(fmin(dtmax, dtnew), dtmin);
-                // ---- callbacks: continuous (disc) first, then discrete (user, chart)
-                bool event = false;
-                double cnext = 1.0;
-                if (GEOM != GB200_GEOMETRY_NONE) {
-                    cnext = disc_condition<GEOM>(P, nr, s_, c_, hgt);
-                    const double sprev = sgn(cprev);
-                    if (sprev != 0.0) {
-                        if (sprev * sgn(cnext) <= 0.0) { event = true; ev_lo = 0.0; ev_hi = 1.0; }
-                        else {
-                            // cheap bound first: |u(Th) - u0| <= |dt| * L * max_j |k_j| with L = max_Th sum_j |b_j(Th)| = 7.5822
-                            // for the Tsit5 dense output; only when it is inconclusive are the polynomial coefficients formed
-                            const double adt = fabs(dt);
-                            const double mth = fmax(fmax(fmax(fabs(vth), fabs(kT[1])), fmax(fabs(kT[2]), fabs(kT[3]))), fmax(fmax(fabs(kT[4]), fabs(kT[5])), fabs(nvth)));
-                            const double mr = fmax(fmax(fmax(fabs(vr), fabs(kR[1])), fmax(fabs(kR[2]), fabs(kR[3]))), fmax(fmax(fabs(kR[4]), fabs(kR[5])), fabs(nvr)));
-                            bool need = sprev < 0.0 || scan_needed<GEOM>(P, r, acos_prev, cprev, adt * 7.5823 * mth, adt * 7.5823 * mr);
-                            double C2r = 0, C3r = 0, C4r = 0, C2t = 0, C3t = 0, C4t = 0;
-                            if (need) {
-                                dense_coeffs(vth, kT, nvth, C2t, C3t, C4t);
-                                dense_coeffs(vr, kR, nvr, C2r, C3r, C4r);
-                                const double Bth = adt * (fabs(vth) + fabs(C2t) + fabs(C3t) + fabs(C4t));
-                                const double Br = adt * (fabs(vr) + fabs(C2r) + fabs(C3r) + fabs(C4r));
-                                need = sprev < 0.0 || scan_needed<GEOM>(P, r, acos_prev, cprev, Bth, Br);
-                            }
-                            if (need) {
+            const double q = fmax(1.0 / qmax, fmin(1.0 / qmin, Epow * (1.0 / gamma)));
+            // ---- accept / reject, callbacks and the commit of the step.  Everything up to the commit is computed
+            // unconditionally and committed with selects: the loop-carried state then lives in the same registers on
+            // every path (the branchy form cost ~200 register moves per attempt where the paths merged).
+            const double dtnew = dt * gb_rcp(q);
+            const double ttmp = lam + dt;
+            const double tnew = (fabs(ttmp - tstop) < 100.0 * (fabs(tstop) * 2.220446049250313e-16)) ? tstop : ttmp;
+            const double dtprop = fmax(fmin(dtmax, dtnew), dtmin);
+            double dtrej = dt;
+            if (!accept) dtrej = dt / fmin(1.0 / qmin, Epow / gamma);
+            // ---- callbacks: continuous (disc) first, then discrete (user, chart)
+            bool event = false;
+            double cnext = 1.0;
+            if (GEOM != GB200_GEOMETRY_NONE) {
+                cnext = disc_condition<GEOM>(P, nr, s_, c_, hgt);
+                const double sprev = sgn(cprev);
+                if (accept && sprev != 0.0) {
+                    if (sprev * sgn(cnext) <= 0.0) { event = true; ev_lo = 0.0; ev_hi = 1.0; }
+                    else {
+                        // cheap bound first: |u(Th) - u0| <= |dt| * L * max_j |k_j| with L = max_Th sum_j |b_j(Th)| = 7.5822
+                        // for the Tsit5 dense output; only when it is inconclusive are the polynomial coefficients formed
+                        const double adt = fabs(dt);
+#if GB_OPT_INTMAX
+                        const double mth = absmax7_bound(vth, kT[1], kT[2], kT[3], kT[4], kT[5], nvth);
+                        const double mr = absmax7_bound(vr, kR[1], kR[2], kR[3], kR[4], kR[5], nvr);
+#else
+                        const double mth = fmax(fmax(fmax(fabs(vth), fabs(kT[1])), fmax(fabs(kT[2]), fabs(kT[3]))), fmax(fmax(fabs(kT[4]), fabs(kT[5])), fabs(nvth)));
+                        const double mr = fmax(fmax(fmax(fabs(vr), fabs(kR[1])), fmax(fabs(kR[2]), fabs(kR[3]))), fmax(fmax(fabs(kR[4]), fabs(kR[5])), fabs(nvr)));
+#endif
+                        bool need = sprev < 0.0 || scan_needed<GEOM>(P, r, acos_prev, cprev, adt * 7.5823 * mth, adt * 7.5823 * mr);
+                        double C2r = 0, C3r = 0, C4r = 0, C2t = 0, C3t = 0, C4t = 0;
+                        if (need) {
+                            dense_coeffs(vth, kT, nvth, C2t, C3t, C4t);
+                            dense_coeffs(vr, kR, nvr, C2r, C3r, C4r);
+                            const double Bth = adt * (fabs(vth) + fabs(C2t) + fabs(C3t) + fabs(C4t));
+                            const double Br = adt * (fabs(vr) + fabs(C2r) + fabs(C3r) + fabs(C4r));
+                            need = sprev < 0.0 || scan_needed<GEOM>(P, r, acos_prev, cprev, Bth, Br);
+                        }
+                        if (need) {
 #pragma unroll 1
-                                for (int i = 1; i <= 6; ++i) { // interp_points = 8: Theta = 1/7 .. 6/7 (7/7 is u itself)
-                                    const double Th = (double)i / 7.0;
-                                    double si, ci;
-                                    gb_sincos(dense_eval(th, dt, Th, vth, C2t, C3t, C4t), &si, &ci);
-                                    const double cn = disc_condition<GEOM>(P, dense_eval(r, dt, Th, vr, C2r, C3r, C4r), si, ci, hgt);
-                                    if (sprev * cn < 0.0) { event = true; ev_lo = (double)(i - 1) / 7.0; ev_hi = Th; break; }
-                                }
+                            for (int i = 1; i <= 6; ++i) { // interp_points = 8: Theta = 1/7 .. 6/7 (7/7 is u itself)
+                                const double Th = (double)i / 7.0;
+                                double si, ci;
+                                gb_sincos(dense_eval(th, dt, Th, vth, C2t, C3t, C4t), &si, &ci);
+                                const double cn = disc_condition<GEOM>(P, dense_eval(r, dt, Th, vr, C2r, C3r, C4r), si, ci, hgt);
+                                if (sprev * cn < 0.0) { event = true; ev_lo = (double)(i - 1) / 7.0; ev_hi = Th; break; }
                             }
                         }
                     }
                 }
-                if (event) {
-                    // keep u_prev, the stage data and dt in registers; the root find happens at finalise
-                    dt_step = dt; tfinal = lam; pend_event = true; pend_status = GB200_STATUS_INTERSECTED_WITH_GEOMETRY;
-                    state = LANE_PENDING;
-                } else {
-                    int status = GB200_STATUS_NO_STATUS;
-                    bool term = false;
-                    if (P.callback_kind == GB200_CALLBACK_UPPER_HEMISPHERE && nr * c_ < P.callback_delta) { status = GB200_STATUS_OUT_OF_DOMAIN; term = true; }
-                    if (nr <= P.chart_inner) { status = GB200_STATUS_WITHIN_INNER_BOUNDARY; term = true; }
-                    else if (nr > P.chart_outer) { status = GB200_STATUS_OUT_OF_DOMAIN; term = true; }
-                    if (!(tnew < tstop)) term = true; // reached lambda_max: NoStatus unless a callback fired
-                    if (term) {
-                        tfinal = tnew; pend_status = status; pend_event = false; state = LANE_PENDING;
-                    } else { // apply_step!: u_prev <- u, FSAL
-                        lam = tnew; ct = nct; r = nr; th = nth; ph = nph; vt = nvt; vr = nvr; vth = nvth; vph = nvph;
-                        kA0[0] = kA0[6]; kA1[0] = kA1[6]; kA2[0] = kA2[6]; kA3[0] = kA3[6];
-                        cprev = cnext; acos_prev = fabs(c_);
-                        dt = dtprop;
-                    }
-                }
-            } else {
-                ++nreject;
-                const double q11 = ctrl_pow_log(logE, EEst, beta1, P.pow_mode);
-                dt = dt / fmin(1.0 / qmin, q11 / gamma); // step_reject_controller!
             }
+            int status = GB200_STATUS_NO_STATUS;
+            bool term = false;
+            if (P.callback_kind == GB200_CALLBACK_UPPER_HEMISPHERE && nr * c_ < P.callback_delta) { status = GB200_STATUS_OUT_OF_DOMAIN; term = true; }
+            if (nr <= P.chart_inner) { status = GB200_STATUS_WITHIN_INNER_BOUNDARY; term = true; }
+            else if (nr > P.chart_outer) { status = GB200_STATUS_OUT_OF_DOMAIN; term = true; }
+            if (!(tnew < tstop)) term = true; // reached lambda_max: NoStatus unless a callback fired
+            const bool finish = accept && (event || term);
+            const bool advance = accept && !finish; // apply_step!: u_prev <- u, FSAL
+            naccept += accept ? 1 : 0;
+            nreject += accept ? 0 : 1;
+            if (accept) { // controller memory
+                if (fast32) qoldpow = ctrl_pow_log(fmax(logE, log_qoldinit), fmax(EEst, 1e-4), beta2, P.pow_mode);
+                else qoldpow = beta2 * fmax(logE, log_qoldinit);
+            }
+            // an event keeps u_prev, the stage data and dt (= the step's dt) in registers: the root find happens at
+            // finalise; tfinal holds lambda_prev for event lanes, the end of the step otherwise
+            tfinal = event ? lam : tnew;
+            pend_event = event;
+            pend_status = event ? GB200_STATUS_INTERSECTED_WITH_GEOMETRY : status;
+            state = finish ? LANE_PENDING : LANE_RUN;
+            lam = advance ? tnew : lam;
+            ct = advance ? nct : ct; r = advance ? nr : r; th = advance ? nth : th; ph = advance ? nph : ph;
+            vt = advance ? nvt : vt; vr = advance ? nvr : vr; vth = advance ? nvth : vth; vph = advance ? nvph : vph;
+            kA0[0] = advance ? kA0[6] : kA0[0]; kA1[0] = advance ? kA1[6] : kA1[0];
+            kA2[0] = advance ? kA2[6] : kA2[0]; kA3[0] = advance ? kA3[6] : kA3[0];
+            cprev = advance ? cnext : cprev; acos_prev = advance ? fabs(c_) : acos_prev;
+            dt = advance ? dtprop : (accept ? dt : dtrej);
         }
     }
     // ---- flush per-thread counters (warp-reduced)
@@ -743,12 +793,14 @@ __global__ void gb200_debug_rhs_kernel(const GbParams P, long long n, const doub
     rhs_accel<METRIC>(P, u[8 * i + 1], u[8 * i + 2], u[8 * i + 4], u[8 * i + 5], u[8 * i + 6], u[8 * i + 7], acc, s_, c_);
     for (int k = 0; k < 4; ++k) { du[8 * i + k] = u[8 * i + 4 + k]; du[8 * i + 4 + k] = acc[k]; }
 }
-__global__ void gb200_debug_math_kernel(long long n, const double* __restrict__ x, double* __restrict__ out3) {
+__global__ void gb200_debug_math_kernel(long long n, const double* __restrict__ x, double* __restrict__ out5) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double s_, c_;
     gb_sincos(x[i], &s_, &c_);
-    out3[3 * i] = s_; out3[3 * i + 1] = c_; out3[3 * i + 2] = gb_rcp(x[i]);
+    out5[5 * i] = s_; out5[5 * i + 1] = c_; out5[5 * i + 2] = gb_rcp(x[i]);
+    out5[5 * i + 3] = gb_log_pos(fabs(x[i]));
+    out5[5 * i + 4] = gb_exp_small(fmax(-8.0, fmin(8.0, x[i])));
 }
 cudaError_t gb200_launch_debug_rhs(const GbParams& P, long long n, const double* d_u, double* d_du, cudaStream_t stream) {
     const unsigned grid = (unsigned)((n + 127) / 128);
@@ -761,8 +813,8 @@ cudaError_t gb200_launch_debug_rhs(const GbParams& P, long long n, const double*
     }
     return cudaGetLastError();
 }
-cudaError_t gb200_launch_debug_math(long long n, const double* d_x, double* d_out3, cudaStream_t stream) {
-    gb200_debug_math_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, d_x, d_out3);
+cudaError_t gb200_launch_debug_math(long long n, const double* d_x, double* d_out5, cudaStream_t stream) {
+    gb200_debug_math_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, d_x, d_out5);
     return cudaGetLastError();
 }
 

@@ -288,10 +288,11 @@ int gb200_lineprofile_device(gb200_ctx* ctx, const gb200_problem* p, const gb200
                              void* cuda_stream, int async);
 
 /* Diagnostics: evaluate the device right-hand side (_second_order_ode_f, src/tracing/geodesic-problem.jl:87-92) for
-   n states u (row-major n x 8) -> du (n x 8), and the kernel's branch-free sincos / reciprocal on n inputs
-   (out3 = n x 3: sin, cos, 1/x).  Lets tests check the closed forms against the oracle's AD-based RHS directly. */
+   n states u (row-major n x 8) -> du (n x 8), and the kernel's branch-free elementary functions on n inputs
+   (out5 = n x 5: sin x, cos x, 1/x, log|x|, exp(clamp(x, -8, 8))).  Lets tests check the closed forms against the
+   oracle's AD-based RHS and libm directly. */
 int gb200_debug_rhs(gb200_ctx* ctx, int32_t metric_kind, const double* metric_params, int64_t n, const double* u, double* du);
-int gb200_debug_math(gb200_ctx* ctx, int64_t n, const double* x, double* out3);
+int gb200_debug_math(gb200_ctx* ctx, int64_t n, const double* x, double* out5);
 
 /* Dependent-free DFMA micro-benchmark: measured FP64 FMA throughput of the
    device in TFLOP/s (2 flop per FMA); the roofline denominator. */

@@ -503,11 +503,19 @@ def test_device_math_against_oracle(ensemble):
         assert np.array_equal(du[:, :4], u[:, 4:])
         assert err.max() < 1e-10 and np.median(err) < 1e-14, (kind, mp, err.max(), np.median(err))
     x = np.concatenate([rs.uniform(-60, 60, 20000), np.array([0.0, 1e-300, math.pi / 2, math.pi, -math.pi / 4, 40.0, 1e-9])])
-    out = np.zeros((len(x), 3))
+    nsc = len(x)  # sin / cos are checked on the polar-angle range only
+    x = np.concatenate([x, 10.0 ** rs.uniform(-12, 6, 4000), rs.uniform(-8, 8, 4000)])
+    out = np.zeros((len(x), 5))
     cabi.check(lib.gb200_debug_math(ctx, len(x), cabi.dptr(x), cabi.dptr(out.reshape(-1))), ctx)
-    assert np.abs(out[:, 0] - np.sin(x)).max() < 2.5e-16 and np.abs(out[:, 1] - np.cos(x)).max() < 2.5e-16
+    assert np.abs(out[:nsc, 0] - np.sin(x[:nsc])).max() < 2.5e-16 and np.abs(out[:nsc, 1] - np.cos(x[:nsc])).max() < 2.5e-16
     nz = x != 0
     assert np.max(np.abs(out[nz, 2] * x[nz] - 1.0)) < 4.5e-16
+    # the step controller's log / exp: a few ulp of libm (the controller only needs ~1e-10)
+    lg = np.log(np.abs(x[nz]))
+    assert np.max(np.abs(out[nz, 3] - lg) / np.maximum(np.abs(lg), 1.0)) < 4.5e-16
+    assert out[~nz, 3].max() < -700.0  # log 0: very negative instead of -inf, clamped by the controller all the same
+    ex = np.exp(np.clip(x, -8.0, 8.0))
+    assert np.max(np.abs(out[:, 4] - ex) / ex) < 1e-15
 
 
 def test_gpu_against_committed_golden_fixtures(ensemble):
