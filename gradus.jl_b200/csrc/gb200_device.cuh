@@ -53,6 +53,30 @@ GB_HD inline double gb_rcp_lo(double x) {
 #endif
 }
 
+// max / min as one compare and a select.  fmax()/fmin() cost ~8 instructions each on sm_100a (IEEE nan quieting);
+// these return b when either argument is a nan, and every use below either cannot see a nan or lets it propagate
+// into the step-size, where the integrator's nan check flags the ray.
+GB_HD inline double gb_max(double a, double b) { return a > b ? a : b; }
+GB_HD inline double gb_min(double a, double b) { return a < b ? a : b; }
+
+// Branch-free square root for x >= 1e-300 (callers clamp): rsqrt seed + two coupled Newton steps + a final residual
+// correction, <= 1 ulp.  The library sqrt() keeps a slow-path call whose register save/restore spilled in the hot loop.
+GB_HD inline double gb_sqrt_pos(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double e = fma(-h, g, 0.5);
+    g = fma(g, e, g); h = fma(h, e, h);
+    e = fma(-h, g, 0.5);
+    g = fma(g, e, g); h = fma(h, e, h);
+    const double d = fma(-g, g, x);
+    return fma(d, h, g);
+#else
+    return sqrt(x);
+#endif
+}
+
 #include "jp_metric_generated.cuh"
 #include "metrics_generated.cuh"
 

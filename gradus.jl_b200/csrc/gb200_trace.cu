@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
     int state = LANE_EMPTY, pend_status = GB200_STATUS_NO_STATUS;
     bool pend_event = false;
     int naccept = 0, nreject = 0, flags = 0;
-    int64_t slot = -1, iter = 0;
+    int64_t slot = -1;
+    const int maxit = (int)(P.maxiters < 0x7fffffff ? P.maxiters : 0x7fffffff); // step attempts are counted in 32 bits
     bool exhausted = false;
     unsigned long long tot_acc = 0, tot_rej = 0, tot_flag = 0;
 #pragma unroll
@@ -260,8 +261,9 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                 }
                 // ---- store: GeodesicPoint fields, point functions, line-profile samples
                 const int64_t n = slot;
-                const double xe[4] = {nct, nr, nth, nph};
-                const double ve[4] = {nvt, nvr, nvth, nvph};
+                const bool failed = flags != 0; // integrator failure: last accepted state
+                const double xe[4] = {failed ? ct : nct, failed ? r : nr, failed ? th : nth, failed ? ph : nph};
+                const double ve[4] = {failed ? vt : nvt, failed ? vr : nvr, failed ? vth : nvth, failed ? vph : nvph};
                 if (P.o_status) P.o_status[n] = status;
                 if (P.o_lambda) P.o_lambda[n] = tfinal;
 #pragma unroll
@@ -283,8 +285,8 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                         if (pf == GB200_PF_SHADOW) { if (tfinal < P.lam1) val = tfinal; }
                         else if (pf == GB200_PF_REDSHIFT) {
                             if (hit) { if (!have_g) { g_red = redshift_endpoint<METRIC>(P, xe, ve, E_obs); have_g = true; } val = g_red; }
-                        } else if (pf == GB200_PF_DISC_RADIUS) { if (hit) val = nr * fabs(sin(nth)); }
-                        else if (pf == GB200_PF_COORDINATE_TIME) { if (hit) val = nct; }
+                        } else if (pf == GB200_PF_DISC_RADIUS) { if (hit) val = xe[1] * fabs(sin(xe[2])); }
+                        else if (pf == GB200_PF_COORDINATE_TIME) { if (hit) val = xe[0]; }
                         else if (pf == GB200_PF_STATUS) val = (double)status;
                         else if (pf == GB200_PF_AFFINE_TIME) val = tfinal;
                         P.o_img[k][n] = val;
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                     if (P.o_g) { // lineprofile BinningMethod, src/line-profiles.jl:186-194
                         double gg = nan(""), ff = 0.0;
                         if (hit) {
-                            const double rho = nr * fabs(sin(nth));
+                            const double rho = xe[1] * fabs(sin(xe[2]));
                             if (P.min_re <= rho && rho <= P.max_re) {
                                 gg = have_g ? g_red : redshift_endpoint<METRIC>(P, xe, ve, E_obs);
                                 ff = emissivity_eval(P, rho) * gg * gg * gg * area;
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                             metric_components_t<METRIC>(P, r, sx, cx, go);
                             E_obs = go[0] * vt + go[4] * vph;
                         } else E_obs = P.go[0] * vt + P.go[4] * vph;
-                        naccept = 0; nreject = 0; flags = 0; iter = 0;
+                        naccept = 0; nreject = 0; flags = 0;
                         pend_event = false;
                         // f0 and the Hairer-Wanner initial step (ode_determine_initdt)
                         double acc[4], s_, c_;
@@ -390,17 +392,15 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
 
         // ================= one Tsit5 step attempt for every running lane (straight-line: no taken branches) ==========
         if (state == LANE_RUN) {
-            ++iter;
-            bool stop_now = false;
-            if (iter > P.maxiters) { flags |= GB200_FLAG_MAXITERS; stop_now = true; }
-            else if (!(dt == dt) || !(r == r)) { flags |= GB200_FLAG_UNSTABLE; stop_now = true; }
-            else {
-                dt = fmax(fmin(dt, dtmax), dtmin);
-                dt = fmin(dt, tstop - lam); // modify_dt_for_tstops!
-                if (dt <= dtmin && (tstop - lam) > dtmin) { flags |= GB200_FLAG_DT_MIN; stop_now = true; }
-            }
-            if (stop_now) { // integrator failure: the ray keeps NoStatus at its last accepted state
-                nct = ct; nr = r; nth = th; nph = ph; nvt = vt; nvr = vr; nvth = vth; nvph = vph;
+            // dt arrives clamped to [dtmin, dtmax] (refill and commit do it); modify_dt_for_tstops! clips it to the end
+            const double rem = tstop - lam;
+            int fail = 0;
+            if (naccept + nreject >= maxit) fail = GB200_FLAG_MAXITERS;
+            else if (!(dt == dt) || !(r == r)) fail = GB200_FLAG_UNSTABLE;
+            else if (!(gb_min(dt, rem) > dtmin) && rem > dtmin) fail = GB200_FLAG_DT_MIN;
+            dt = gb_min(dt, rem);
+            if (fail) { // integrator failure: the ray keeps NoStatus at its last accepted state (finalise reads u_prev for flagged rays)
+                flags |= fail;
                 tfinal = lam; pend_status = GB200_STATUS_NO_STATUS; pend_event = false; state = LANE_PENDING;
             }
         }
@@ -441,19 +441,20 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                 const double e4 = edt * errcomb(kA0[0], kA0, kA0[6]), e5 = edt * errcomb(kA1[0], kA1, kA1[6]);
                 const double e6 = edt * errcomb(kA2[0], kA2, kA2[6]), e7 = edt * errcomb(kA3[0], kA3, kA3[6]);
                 double q_;
-                q_ = e0 * gb_rcp_lo(fma(fmax(fabs(ct), fabs(nct)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e1 * gb_rcp_lo(fma(fmax(fabs(r), fabs(nr)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e2 * gb_rcp_lo(fma(fmax(fabs(th), fabs(nth)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e3 * gb_rcp_lo(fma(fmax(fabs(ph), fabs(nph)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e4 * gb_rcp_lo(fma(fmax(fabs(vt), fabs(nvt)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e5 * gb_rcp_lo(fma(fmax(fabs(vr), fabs(nvr)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e6 * gb_rcp_lo(fma(fmax(fabs(vth), fabs(nvth)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e7 * gb_rcp_lo(fma(fmax(fabs(vph), fabs(nvph)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e0 * gb_rcp_lo(fma(gb_max(fabs(ct), fabs(nct)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e1 * gb_rcp_lo(fma(gb_max(fabs(r), fabs(nr)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e2 * gb_rcp_lo(fma(gb_max(fabs(th), fabs(nth)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e3 * gb_rcp_lo(fma(gb_max(fabs(ph), fabs(nph)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e4 * gb_rcp_lo(fma(gb_max(fabs(vt), fabs(nvt)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e5 * gb_rcp_lo(fma(gb_max(fabs(vr), fabs(nvr)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e6 * gb_rcp_lo(fma(gb_max(fabs(vth), fabs(nvth)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e7 * gb_rcp_lo(fma(gb_max(fabs(vph), fabs(nvph)), reltol, abstol)); ee = fma(q_, q_, ee);
             }
+            // an exactly zero estimate is raised to 1e-150: the controller clamps q to 1/qmax and qold to 1e-4 either way
 #if GB_OPT_ERRDT
-            const double EEst = fabs(dt) * sqrt(ee * 0.125);
+            const double EEst = fabs(dt) * gb_sqrt_pos(gb_max(ee * 0.125, 1e-300));
 #else
-            const double EEst = sqrt(ee * 0.125);
+            const double EEst = gb_sqrt_pos(gb_max(ee * 0.125, 1e-300));
 #endif
             // PI controller (stepsize_controller!, OrdinaryDiffEq): q = EEst^beta1 / qold^beta2 / gamma, clamped; a rejected
             // attempt uses EEst^beta1 / gamma (step_reject_controller!).  One log and one exp serve both:
@@ -472,21 +473,21 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
             } else {
                 const double arg = accept ? fma(beta1, logE, -qoldpow) : beta1 * logE; // qoldpow = beta2 * log(qold) in this mode
 #if GB_OPT_LOGEXP
-                Epow = gb_exp_small(fmax(-8.0, fmin(8.0, arg))); // q is clamped to [1/qmax, 1/qmin] = exp(-2.2 .. 1.7) afterwards
+                Epow = gb_exp_small(gb_max(-8.0, gb_min(8.0, arg))); // q is clamped to [1/qmax, 1/qmin] = exp(-2.2 .. 1.7) afterwards
 #else
                 Epow = exp(arg);
 #endif
             }
-            const double q = fmax(1.0 / qmax, fmin(1.0 / qmin, Epow * (1.0 / gamma)));
+            const double q = gb_max(1.0 / qmax, gb_min(1.0 / qmin, Epow * (1.0 / gamma)));
             // ---- accept / reject, callbacks and the commit of the step.  Everything up to the commit is computed
             // unconditionally and committed with selects: the loop-carried state then lives in the same registers on
             // every path (the branchy form cost ~200 register moves per attempt where the paths merged).
             const double dtnew = dt * gb_rcp(q);
             const double ttmp = lam + dt;
             const double tnew = (fabs(ttmp - tstop) < 100.0 * (fabs(tstop) * 2.220446049250313e-16)) ? tstop : ttmp;
-            const double dtprop = fmax(fmin(dtmax, dtnew), dtmin);
+            const double dtprop = gb_max(gb_min(dtmax, dtnew), dtmin);
             double dtrej = dt;
-            if (!accept) dtrej = dt / fmin(1.0 / qmin, Epow / gamma);
+            if (!accept) dtrej = gb_max(dt / gb_min(1.0 / qmin, Epow / gamma), dtmin);
             // ---- callbacks: continuous (disc) first, then discrete (user, chart)
             bool event = false;
             double cnext = 1.0;
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
             nreject += accept ? 0 : 1;
             if (accept) { // controller memory
                 if (fast32) qoldpow = ctrl_pow_log(fmax(logE, log_qoldinit), fmax(EEst, 1e-4), beta2, P.pow_mode);
-                else qoldpow = beta2 * fmax(logE, log_qoldinit);
+                else qoldpow = beta2 * gb_max(logE, log_qoldinit);
             }
             // an event keeps u_prev, the stage data and dt (= the step's dt) in registers: the root find happens at
             // finalise; tfinal holds lambda_prev for event lanes, the end of the step otherwise
