@@ -27,14 +27,24 @@
 // Branch-free FP64 reciprocal: hardware seed (rcp.approx, >= 20 good bits) + two Newton steps -> <= 1-2 ulp.
 // Used for the well-conditioned denominators of the hot loop (Sigma, Delta, sin^2, error scales); an IEEE
 // division costs ~25 instructions including a divergent slow-path check, this costs 5.
+#ifndef GB_OPT_RCP3
+#define GB_OPT_RCP3 1 /* one third-order correction y (1 + e + e^2) instead of two Newton steps (3 DFMA instead of 4) */
+#endif
 GB_HD inline double gb_rcp(double x) {
 #ifdef __CUDA_ARCH__
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if GB_OPT_RCP3
+    // 1/x = y / (1 - e) = y (1 + e + e^2 + e^3 + ...), e = 1 - x y: |e| <= 2^-20 for the hardware seed, so the
+    // truncation e^3 is below 2^-60
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);
+#else
     double e = fma(-x, y, 1.0);
     y = fma(y, e, y);
     e = fma(-x, y, 1.0);
     return fma(y, e, y);
+#endif
 #else
     return 1.0 / x;
 #endif
@@ -87,6 +97,7 @@ struct GbParams {
     // metric
     int32_t metric_kind;
     double M, a, eps3;
+    double a2, twoM; // a^2 and 2M: read from the constant bank at every RHS evaluation instead of recomputed
     double mp[8]; // all metric parameters in the order of include/gradus_b200.h (M = mp[0], a = mp[1])
     // integrator
     double lam0, lam1, abstol, reltol, dtmax, mu;
@@ -468,6 +479,12 @@ GB_HD inline void geodesic_accel(const double g[5], const double dr[5], const do
 #ifndef GB_OPT_SIGNFLIP
 #define GB_OPT_SIGNFLIP 1 /* quadrant signs of sincos through the integer pipe */
 #endif
+#ifndef GB_OPT_CW2
+#define GB_OPT_CW2 1 /* two-term Cody-Waite reduction (the third term is 2e-21 per quadrant) */
+#endif
+#ifndef GB_OPT_KERR1R
+#define GB_OPT_KERR1R 1 /* Kerr RHS with a single reciprocal 1/(Sigma Delta sin^2) */
+#endif
 #ifndef GB_OPT_KERR_SQ
 #define GB_OPT_KERR_SQ 1 /* Kerr RHS from sin^2, cos^2, sin 2theta of the reduced argument (signs of sin, cos only where needed) */
 #endif
@@ -486,7 +503,9 @@ GB_D GbSinCos gb_sincos_reduced(double x) {
     const double q = rint(x * GB_SC_2OPI);
     double rr = fma(-q, GB_SC_PIO2_1, x);
     rr = fma(-q, GB_SC_PIO2_2, rr);
-    rr = fma(-q, GB_SC_PIO2_3, rr);
+#if !GB_OPT_CW2
+    rr = fma(-q, GB_SC_PIO2_3, rr); // 2.0e-21 |q|: below 1e-18 for the |theta| < 500 a geodesic can reach
+#endif
     const double z = rr * rr;
     double ps = fma(z, GB_SC_S6, GB_SC_S5);
     ps = fma(z, ps, GB_SC_S4);
@@ -561,20 +580,32 @@ GB_D double gb_exp_small(double x) {
 
 // Kerr right-hand side with everything folded: two reciprocals (1/(Sigma Delta) and 1/sin^2) and the identity
 // g_tt g_phph - g_tph^2 = -Delta sin^2, so  g^tt = -B/Delta, g^tph = -a w/Delta, g^phph = (1 - w)/(Delta sin^2).
-GB_D void kerr_rhs_accel_sq(double M, double a, double r, double s2, double c2, double sin2, double vt, double vr, double vth, double vph, double acc[4]);
+GB_D void kerr_rhs_accel_sq(double M, double a, double a2, double twoM, double r, double s2, double c2, double sin2, double vt, double vr, double vth, double vph, double acc[4]);
 GB_D void kerr_rhs_accel(double M, double a, double r, double s, double c, double vt, double vr, double vth, double vph, double acc[4]) {
-    kerr_rhs_accel_sq(M, a, r, s * s, c * c, 2.0 * s * c, vt, vr, vth, vph, acc);
+    kerr_rhs_accel_sq(M, a, a * a, 2.0 * M, r, s * s, c * c, 2.0 * s * c, vt, vr, vth, vph, acc);
 }
-GB_D void kerr_rhs_accel_sq(double M, double a, double r, double s2, double c2, double sin2, double vt, double vr, double vth, double vph, double acc[4]) {
-    const double a2 = a * a, r2 = r * r;
+GB_D void kerr_rhs_accel_sq(double M, double a, double a2, double twoM, double r, double s2, double c2, double sin2, double vt, double vr, double vth, double vph, double acc[4]) {
+    const double r2 = r * r;
     const double Sig = fma(a2, c2, r2);
-    const double Del = fma(r, r - 2.0 * M, a2);
+    const double Del = fma(r, r - twoM, a2);
+#if GB_OPT_KERR1R
+    const double Ds = Del * s2;
+    const double R = gb_rcp(Sig * Ds);
+    const double iSig = R * Ds, iDel_is2 = R * Sig, iDel = iDel_is2 * s2;
+    const double a2sin2 = a2 * sin2;
+    const double w = twoM * r * iSig;
+    const double w_r = 2.0 * (M - w * r) * iSig;
+    const double w_t = w * iSig * a2sin2;
+    const double Sig_t = -a2sin2;
+#else
     const double R = gb_rcp(Sig * Del), is2 = gb_rcp(s2);
     const double iSig = R * Del, iDel = R * Sig;
+    const double iDel_is2 = iDel * is2;
     const double w = 2.0 * M * r * iSig;
     const double w_r = 2.0 * (M - w * r) * iSig;
     const double w_t = w * a2 * sin2 * iSig;
     const double Sig_t = -a2 * sin2;
+#endif
     const double as2 = a2 * s2;
     const double B = fma(as2, w, r2 + a2);
     const double q = fma(s2, w_t, sin2 * w);
@@ -586,7 +617,7 @@ GB_D void kerr_rhs_accel_sq(double M, double a, double r, double s2, double c2, 
     const double r3 = s2 * fma(as2, w_r, 2.0 * r), t3 = fma(sin2, B, as2 * q);
     const double r4 = -a * s2 * w_r, t4 = -a * q;
     // inverse metric
-    const double gitt = -B * iDel, gitph = -a * w * iDel, giphph = (1.0 - w) * iDel * is2;
+    const double gitt = -B * iDel, gitph = -a * w * iDel, giphph = (1.0 - w) * iDel_is2;
     const double girr = Del * iSig, githth = iSig;
     const double d0 = fma(vr, r0, vth * t0), d1 = fma(vr, r1, vth * t1), d2 = fma(vr, r2_, vth * t2);
     const double d3 = fma(vr, r3, vth * t3), d4 = fma(vr, r4, vth * t4);
@@ -622,7 +653,7 @@ GB_RHS_ATTR GbAcc rhs_eval(const GbParams& P, double r, double th, double vt, do
         const double sa = swap ? q.cs : q.sn, ca = swap ? q.sn : q.cs;
         o.s = gb_flip_sign(sa, q.n << 30);
         o.c = gb_flip_sign(ca, (q.n + 1) << 30);
-        kerr_rhs_accel_sq(P.M, P.a, r, sa * sa, ca * ca, gb_flip_sign(2.0 * sa * ca, q.n << 31), vt, vr, vth, vph, acc);
+        kerr_rhs_accel_sq(P.M, P.a, P.a2, P.twoM, r, sa * sa, ca * ca, gb_flip_sign(2.0 * sa * ca, q.n << 31), vt, vr, vth, vph, acc);
         o.a0 = acc[0]; o.a1 = acc[1]; o.a2 = acc[2]; o.a3 = acc[3];
         return o;
     }

@@ -26,10 +26,10 @@
 #include "gb200_internal.h"
 
 #ifndef GB_BLOCK
-#define GB_BLOCK 128
+#define GB_BLOCK 64 /* two warps per CTA: the per-CTA barrier waits on one other warp only */
 #endif
 #ifndef GB_MIN_BLOCKS
-#define GB_MIN_BLOCKS 3
+#define GB_MIN_BLOCKS 6 /* 12 warps per SM at 168 registers per thread */
 #endif
 #ifndef GB_REFILL_THRESH
 #define GB_REFILL_THRESH 8 /* idle lanes per warp that trigger a service pass (per CTA: x warps per CTA) */
@@ -38,7 +38,7 @@
 #define GB_BLOCK_SYNC 1 /* CTA-synchronous stepping: one barrier per step attempt keeps the warps of a CTA in lockstep */
 #endif
 #ifndef GB_SYNC_EVERY
-#define GB_SYNC_EVERY 4 /* barrier (and service decision) every n-th attempt */
+#define GB_SYNC_EVERY 8 /* barrier (and service decision) every n-th attempt */
 #endif
 
 #ifndef GB_OPT_LOGEXP
