@@ -121,8 +121,13 @@ GB_D bool scan_needed(const GbParams& P, double r0, double acos0, double cprev, 
 }
 
 
+#ifdef GB_MAXRREG /* tuning: explicit register cap instead of the occupancy target */
+#define GB_LAUNCH_BOUNDS __maxnreg__(GB_MAXRREG)
+#else
+#define GB_LAUNCH_BOUNDS __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS)
+#endif
 template <int METRIC, int GEOM>
-__global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(const __grid_constant__ GbParams P) {
+__global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbParams P) {
     const unsigned lane = threadIdx.x & 31u;
     const double abstol = P.abstol, reltol = P.reltol;
     const double tstop = P.lam1;
@@ -450,22 +455,26 @@ __global__ void __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS) gb200_trace_kernel(co
                 q_ = e6 * gb_rcp_lo(fma(gb_max(fabs(vth), fabs(nvth)), reltol, abstol)); ee = fma(q_, q_, ee);
                 q_ = e7 * gb_rcp_lo(fma(gb_max(fabs(vph), fabs(nvph)), reltol, abstol)); ee = fma(q_, q_, ee);
             }
-            // an exactly zero estimate is raised to 1e-150: the controller clamps q to 1/qmax and qold to 1e-4 either way
+            // EEst^2 = dt^2 sum_i (.)^2 / 8; the controller only needs log EEst = log(EEst^2) / 2 and the test EEst <= 1, so no
+            // square root is taken (the Float32 controller mode takes it where it needs EEst itself).  An exactly zero
+            // estimate is raised to 1e-150: the controller clamps q to 1/qmax and qold to 1e-4 either way.
 #if GB_OPT_ERRDT
-            const double EEst = fabs(dt) * gb_sqrt_pos(gb_max(ee * 0.125, 1e-300));
+            const double EEst2 = gb_max((dt * dt) * (ee * 0.125), 1e-300);
 #else
-            const double EEst = gb_sqrt_pos(gb_max(ee * 0.125, 1e-300));
+            const double EEst2 = gb_max(ee * 0.125, 1e-300);
 #endif
             // PI controller (stepsize_controller!, OrdinaryDiffEq): q = EEst^beta1 / qold^beta2 / gamma, clamped; a rejected
             // attempt uses EEst^beta1 / gamma (step_reject_controller!).  One log and one exp serve both:
-            // exp(beta1 log EEst - [accepted] beta2 log qold).  EEst = 0 gives log = -inf, exp = 0, q = 1/qmax as required.
-            const bool accept = EEst <= 1.0;
+            // exp(beta1 log EEst - [accepted] beta2 log qold).
+            const bool accept = EEst2 <= 1.0;
             const bool fast32 = (P.pow_mode == GB200_POW_FAST32);
 #if GB_OPT_LOGEXP
-            const double logE = gb_log_pos(EEst);
+            const double logE = 0.5 * gb_log_pos(EEst2);
 #else
-            const double logE = log(EEst);
+            const double logE = 0.5 * log(EEst2);
 #endif
+            double EEst = 1.0; // only the Float32 mode reads it
+            if (fast32) EEst = gb_sqrt_pos(EEst2);
             double Epow;
             if (fast32) {
                 Epow = ctrl_pow_log(logE, EEst, beta1, P.pow_mode);
