@@ -470,10 +470,10 @@ GB_HD inline void geodesic_accel(const double g[5], const double dr[5], const do
     const double vtt = vt * vt, vrr = vr * vr, vthth = vth * vth, vpp = vph * vph, vtp2 = 2.0 * vt * vph;
     const double Sr = dr[0] * vtt + dr[1] * vrr + dr[2] * vthth + dr[3] * vpp + dr[4] * vtp2;
     const double St = dth[0] * vtt + dth[1] * vrr + dth[2] * vthth + dth[3] * vpp + dth[4] * vtp2;
-    acc[0] = -(gitt * Pt + gitph * Pp);
-    acc[1] = -girr * (d1 * vr - 0.5 * Sr);
-    acc[2] = -githth * (d2 * vth - 0.5 * St);
-    acc[3] = -(gitph * Pt + giphph * Pp);
+    acc[0] = fma(-gitt, Pt, -gitph * Pp);
+    acc[1] = girr * fma(-d1, vr, 0.5 * Sr);
+    acc[2] = githth * fma(-d2, vth, 0.5 * St);
+    acc[3] = fma(-gitph, Pt, -giphph * Pp);
 }
 
 #ifndef GB_OPT_SIGNFLIP
@@ -617,7 +617,8 @@ GB_D void kerr_rhs_accel_sq(double M, double a, double a2, double twoM, double r
     const double r3 = s2 * fma(as2, w_r, 2.0 * r), t3 = fma(sin2, B, as2 * q);
     const double r4 = -a * s2 * w_r, t4 = -a * q;
     // inverse metric
-    const double gitt = -B * iDel, gitph = -a * w * iDel, giphph = (1.0 - w) * iDel_is2;
+    // -g^tt, -g^tph, g^phph: the signs are carried by operand modifiers below, never by a separate negation
+    const double mgitt = B * iDel, mgitph = a * w * iDel, giphph = (1.0 - w) * iDel_is2;
     const double girr = Del * iSig, githth = iSig;
     const double d0 = fma(vr, r0, vth * t0), d1 = fma(vr, r1, vth * t1), d2 = fma(vr, r2_, vth * t2);
     const double d3 = fma(vr, r3, vth * t3), d4 = fma(vr, r4, vth * t4);
@@ -625,10 +626,10 @@ GB_D void kerr_rhs_accel_sq(double M, double a, double a2, double twoM, double r
     const double vtt = vt * vt, vrr = vr * vr, vthth = vth * vth, vpp = vph * vph, vtp2 = 2.0 * vt * vph;
     const double Sr = fma(r0, vtt, fma(r1, vrr, fma(r2_, vthth, fma(r3, vpp, r4 * vtp2))));
     const double St = fma(t0, vtt, fma(t1, vrr, fma(t2, vthth, fma(t3, vpp, t4 * vtp2))));
-    acc[0] = -fma(gitt, Pt, gitph * Pp);
-    acc[1] = -girr * fma(d1, vr, -0.5 * Sr);
-    acc[2] = -githth * fma(d2, vth, -0.5 * St);
-    acc[3] = -fma(gitph, Pt, giphph * Pp);
+    acc[0] = fma(mgitt, Pt, mgitph * Pp);
+    acc[1] = girr * fma(-d1, vr, 0.5 * Sr);
+    acc[2] = githth * fma(-d2, vth, 0.5 * St);
+    acc[3] = fma(mgitph, Pt, -giphph * Pp);
 }
 
 // The right-hand side, inlined at each of the six stages.  (Measured alternatives, profiles/r01_tuning_log.md: one

@@ -45,6 +45,9 @@
 #define GB_OPT_LOGEXP 1 /* branch-free log/exp with constant-bank coefficients in the step controller */
 #endif
 
+#ifndef GB_OPT_PARK
+#define GB_OPT_PARK 1 /* event lanes park their stage data in shared memory until finalise */
+#endif
 #ifndef GB_OPT_INTMAX
 #define GB_OPT_INTMAX 1 /* event-scan pre-test bound from integer maxima of the high words */
 #endif
@@ -94,6 +97,10 @@ GB_D double ctrl_pow_log(double logx, double x, double y, int mode) {
     if (mode == GB200_POW_FAST32) return (double)exp2f((float)y * log2f((float)x));
     return exp(y * logx);
 }
+
+// The argument of larger magnitude (the caller applies fabs as an operand modifier: selecting |a| or |b| directly makes the
+// compiler materialise both absolute values with two extra FP64 instructions).
+GB_D double gb_absmax(double a, double b) { return fabs(a) > fabs(b) ? a : b; }
 
 // An upper bound of max_i |a_i| from the high words alone (integer pipe): doubles order like their bit patterns, and
 // (hi + 1, 0) exceeds every double whose high word is hi.  inf/nan inputs give a nan bound, which the caller's
@@ -159,6 +166,12 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
 #pragma unroll
     for (int j = 0; j < 6; ++j) { kR[j] = kT[j] = 0.0; }
 
+#if GB_OPT_PARK
+    // Stage data of a lane whose step ended in a disc event, parked until the lane is finalised: k2..k7 accelerations
+    // (24) and the k2..k6 stage velocities of r and theta (10), [value][thread] so a warp's accesses are conflict-free.
+    // Keeping them in registers instead made every attempt spill ~20 of them for the (rare) root find.
+    __shared__ double sh_park[34][GB_BLOCK];
+#endif
 #if GB_BLOCK_SYNC
     unsigned loop_count = 0;
     __shared__ int sh_exhausted;
@@ -186,6 +199,15 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
             if (state == LANE_PENDING) {
                 int status = pend_status;
                 if (GEOM != GB200_GEOMETRY_NONE && pend_event) {
+#if GB_OPT_PARK
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        kA0[j + 1] = sh_park[j][threadIdx.x]; kA1[j + 1] = sh_park[6 + j][threadIdx.x];
+                        kA2[j + 1] = sh_park[12 + j][threadIdx.x]; kA3[j + 1] = sh_park[18 + j][threadIdx.x];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) { kR[j + 1] = sh_park[24 + j][threadIdx.x]; kT[j + 1] = sh_park[29 + j][threadIdx.x]; }
+#endif
                     // ContinuousCallback root find on the dense output (DiffEqBase find_callback_time, LeftRootFind)
                     double C2r, C3r, C4r, C2t, C3t, C4t;
                     dense_coeffs(vr, kR, nvr, C2r, C3r, C4r);
@@ -446,14 +468,14 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                 const double e4 = edt * errcomb(kA0[0], kA0, kA0[6]), e5 = edt * errcomb(kA1[0], kA1, kA1[6]);
                 const double e6 = edt * errcomb(kA2[0], kA2, kA2[6]), e7 = edt * errcomb(kA3[0], kA3, kA3[6]);
                 double q_;
-                q_ = e0 * gb_rcp_lo(fma(gb_max(fabs(ct), fabs(nct)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e1 * gb_rcp_lo(fma(gb_max(fabs(r), fabs(nr)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e2 * gb_rcp_lo(fma(gb_max(fabs(th), fabs(nth)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e3 * gb_rcp_lo(fma(gb_max(fabs(ph), fabs(nph)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e4 * gb_rcp_lo(fma(gb_max(fabs(vt), fabs(nvt)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e5 * gb_rcp_lo(fma(gb_max(fabs(vr), fabs(nvr)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e6 * gb_rcp_lo(fma(gb_max(fabs(vth), fabs(nvth)), reltol, abstol)); ee = fma(q_, q_, ee);
-                q_ = e7 * gb_rcp_lo(fma(gb_max(fabs(vph), fabs(nvph)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e0 * gb_rcp_lo(fma(fabs(gb_absmax(ct, nct)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e1 * gb_rcp_lo(fma(fabs(gb_absmax(r, nr)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e2 * gb_rcp_lo(fma(fabs(gb_absmax(th, nth)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e3 * gb_rcp_lo(fma(fabs(gb_absmax(ph, nph)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e4 * gb_rcp_lo(fma(fabs(gb_absmax(vt, nvt)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e5 * gb_rcp_lo(fma(fabs(gb_absmax(vr, nvr)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e6 * gb_rcp_lo(fma(fabs(gb_absmax(vth, nvth)), reltol, abstol)); ee = fma(q_, q_, ee);
+                q_ = e7 * gb_rcp_lo(fma(fabs(gb_absmax(vph, nvph)), reltol, abstol)); ee = fma(q_, q_, ee);
             }
             // EEst^2 = dt^2 sum_i (.)^2 / 8; the controller only needs log EEst = log(EEst^2) / 2 and the test EEst <= 1, so no
             // square root is taken (the Float32 controller mode takes it where it needs EEst itself).  An exactly zero
@@ -538,6 +560,17 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                     }
                 }
             }
+#if GB_OPT_PARK
+            if (GEOM != GB200_GEOMETRY_NONE && event) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    sh_park[j][threadIdx.x] = kA0[j + 1]; sh_park[6 + j][threadIdx.x] = kA1[j + 1];
+                    sh_park[12 + j][threadIdx.x] = kA2[j + 1]; sh_park[18 + j][threadIdx.x] = kA3[j + 1];
+                }
+#pragma unroll
+                for (int j = 0; j < 5; ++j) { sh_park[24 + j][threadIdx.x] = kR[j + 1]; sh_park[29 + j][threadIdx.x] = kT[j + 1]; }
+            }
+#endif
             int status = GB200_STATUS_NO_STATUS;
             bool term = false;
             if (P.callback_kind == GB200_CALLBACK_UPPER_HEMISPHERE && nr * c_ < P.callback_delta) { status = GB200_STATUS_OUT_OF_DOMAIN; term = true; }
