@@ -21,7 +21,7 @@ CALLBACK_NONE, CALLBACK_UPPER_HEMISPHERE = 0, 1
 POW_EXACT, POW_FAST32 = 0, 1
 IC_RENDER_GRID, IC_POLAR_PLANE, IC_EXPLICIT, IC_CARTESIAN_PLANE, IC_IMPACT_PARAMETERS = 0, 1, 2, 3, 4
 GRID_LINEAR, GRID_GEOMETRIC, GRID_INVERSE = 0, 1, 2
-PF_SHADOW, PF_REDSHIFT, PF_DISC_RADIUS, PF_COORDINATE_TIME, PF_STATUS, PF_AFFINE_TIME = 0, 1, 2, 3, 4, 5
+PF_SHADOW, PF_REDSHIFT, PF_DISC_RADIUS, PF_COORDINATE_TIME, PF_STATUS, PF_AFFINE_TIME, PF_RADIUS = 0, 1, 2, 3, 4, 5, 6
 EMISSIVITY_POWERLAW, EMISSIVITY_TABLE = 0, 1
 FLAG_MAXITERS, FLAG_DT_MIN, FLAG_UNSTABLE = 1, 2, 4
 

@@ -176,6 +176,13 @@ class ShakuraSunyaev:
     def to_c(self):
         return cabi.GEOMETRY_SHAKURA_SUNYAEV, (self.Mdot_Medd, self.inv_eta, self.inner_radius, 0.0)
 
+    def cross_section(self, rho):
+        """`cross_section(d::ShakuraSunyaev, ρ)`, shakura-sunyaev.jl:28-33 (vectorised)."""
+        rho = np.asarray(rho, np.float64)
+        with np.errstate(all="ignore"):
+            h = 3.0 * self.inv_eta * self.Mdot_Medd * (1.0 - np.sqrt(self.inner_radius / rho))
+        return np.where(rho < self.inner_radius, -0.0, h)
+
 
 _SUPPORTED_GEOMETRY = (ThinDisc, ShakuraSunyaev, DatumPlane)
 
@@ -674,6 +681,7 @@ class PointFunction:
             ("coordinate_time", "intersected"): cabi.PF_COORDINATE_TIME,
             ("status", None): cabi.PF_STATUS,
             ("affine_time", None): cabi.PF_AFFINE_TIME,
+            ("radius", None): cabi.PF_RADIUS,
         }
         key = (self.name, self.filter)
         if key not in table:

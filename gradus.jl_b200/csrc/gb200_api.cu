@@ -694,7 +694,7 @@ static int render_common(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic*
     rc = validate_range(ctx, ic, rg); if (rc) return rc;
     if (npf < 1 || npf > GB_MAX_PF || !pfs || !images) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "need 1..%d point functions", GB_MAX_PF);
     for (int k = 0; k < npf; ++k) {
-        if (pfs[k] < GB200_PF_SHADOW || pfs[k] > GB200_PF_AFFINE_TIME) return fail(ctx, GB200_ERR_UNSUPPORTED, "point function %d", pfs[k]);
+        if (pfs[k] < GB200_PF_SHADOW || pfs[k] > GB200_PF_RADIUS) return fail(ctx, GB200_ERR_UNSUPPORTED, "point function %d", pfs[k]);
         if (!images[k]) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null image pointer");
     }
     CU(ctx, cudaSetDevice(ctx->device));

@@ -316,6 +316,7 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                         else if (pf == GB200_PF_COORDINATE_TIME) { if (hit) val = xe[0]; }
                         else if (pf == GB200_PF_STATUS) val = (double)status;
                         else if (pf == GB200_PF_AFFINE_TIME) val = tfinal;
+                        else if (pf == GB200_PF_RADIUS) val = xe[1] * fabs(sin(xe[2]));
                         P.o_img[k][n] = val;
                     }
                     if (P.o_g) { // lineprofile BinningMethod, src/line-profiles.jl:186-194

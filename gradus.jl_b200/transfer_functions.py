@@ -51,10 +51,16 @@ class DeviceProber:
 
     def __init__(self, m, x, d, max_time=None, chart=None, ensemble=None, **solver_kwargs):
         self.m, self.x = m, np.asarray(x, np.float64)
+        self.thick = None
         if isinstance(d, api.ThinDisc):  # `_promote_disc_for_transfer_functions`, cunningham-transfer-functions.jl:2-5
             d = api.DatumPlane(0.0)
+        elif isinstance(d, api.ShakuraSunyaev):
+            # thick disc: offsets are found on `datumplane(d, rₑ)` (one plane height per ray), visibility and the
+            # Jacobian on the disc itself (`_rear_workhorse(::AbstractThickAccretionDisc)`, :274-333)
+            self.thick = d
+            d = api.DatumPlane(0.0)
         elif not isinstance(d, api.DatumPlane):
-            raise ValueError("transfer functions on the device are implemented for thin discs / datum planes")
+            raise ValueError("transfer functions on the device are implemented for thin discs, datum planes and ShakuraSunyaev")
         self.d = d
         self.max_time = 2 * self.x[1] if max_time is None else max_time
         self.chart = chart if chart is not None else api.chart_for_metric(m, 2 * self.x[1])
@@ -62,17 +68,22 @@ class DeviceProber:
         self.solver_kwargs = solver_kwargs
         self.pfs = [api.ConstPointFunctions.redshift(m, x) @ api.ConstPointFunctions.filter_intersected(),
                     api.ConstPointFunctions.radius() @ api.ConstPointFunctions.filter_intersected(),
-                    api.ConstPointFunctions.coordinate_time() @ api.ConstPointFunctions.filter_intersected()]
+                    api.ConstPointFunctions.coordinate_time() @ api.ConstPointFunctions.filter_intersected(),
+                    api.ConstPointFunctions.radius()]  # unfiltered: where a ray that missed the plane ended up
         self.plunging = None
         self.launches = 0
         self.rays = 0
 
-    def config(self, alpha, beta, tol=None):
+    def config(self, alpha, beta, tol=None, height=None, thick=False, chart=None, callback=None):
         kw = dict(self.solver_kwargs)
         if tol is not None:
             kw["abstol"] = kw["reltol"] = tol
-        return api.tracing_configuration(self.m, self.x, api.ImpactParameters(alpha, beta), self.d, self.max_time,
-                                         chart=self.chart, ensemble=self.ensemble, **kw)
+        if callback is not None:
+            kw["callback"] = callback
+        geometry = self.thick if thick else self.d
+        return api.tracing_configuration(self.m, self.x, api.ImpactParameters(alpha, beta, None if thick else height),
+                                         geometry, self.max_time, chart=self.chart if chart is None else chart,
+                                         ensemble=self.ensemble, **kw)
 
     def _plunging(self):
         if self.plunging is None and not isinstance(self.m, api.KerrMetric):
@@ -82,16 +93,30 @@ class DeviceProber:
     def evaluate(self, config):
         return api.apply_point_functions(config, self.pfs, plunging=self._plunging())
 
-    def __call__(self, alpha, beta, tol=None):
+    def evaluate_points(self, config):
+        return api.solve_tracing_problem(config)
+
+    def __call__(self, alpha, beta, tol=None, height=None, thick=False, callback=None, with_end_radius=False):
+        """(g, ρ, t) at the intersection: with the datum plane(s) (one height per ray if `height` is given), or with the
+        thick disc itself (`thick=True`, the Jacobian's traces).  `with_end_radius` adds r|sin θ| of the end point
+        whatever its status (the reference's root finder reads that for rays that missed, precision-solvers.jl:124)."""
         alpha = np.ascontiguousarray(alpha, np.float64)
         beta = np.ascontiguousarray(beta, np.float64)
         if alpha.size == 0:
             z = np.zeros(0)
-            return z, z, z
+            return (z, z, z, z) if with_end_radius else (z, z, z)
         self.launches += 1
         self.rays += alpha.size
-        out = self.evaluate(self.config(alpha, beta, tol))
-        return out[0], out[1], out[2]
+        out = self.evaluate(self.config(alpha, beta, tol, height=height, thick=thick, callback=callback))
+        return (out[0], out[1], out[2], out[3]) if with_end_radius else (out[0], out[1], out[2])
+
+    def points(self, alpha, beta, height=None, thick=False, chart=None):
+        """`GeodesicPoint`s of the same rays (status, λ_max, x): what the thick-disc visibility test compares."""
+        alpha = np.ascontiguousarray(alpha, np.float64)
+        beta = np.ascontiguousarray(beta, np.float64)
+        self.launches += 1
+        self.rays += alpha.size
+        return self.evaluate_points(self.config(alpha, beta, height=height, thick=thick, chart=chart))
 
 
 @dataclass
@@ -108,6 +133,9 @@ class TransferFunctionSetup:
     # integrator tolerance of the differenced traces
     fd_step: float = 2e-5
     fd_tol: float = 1e-12
+    # origin of the polar coordinates on the image plane (`_rθ_to_αβ`, precision-solvers.jl:1-7)
+    alpha0: float = 0.0
+    beta0: float = 0.0
 
 
 def theta_samples(setup: TransferFunctionSetup) -> np.ndarray:
@@ -118,7 +146,8 @@ def theta_samples(setup: TransferFunctionSetup) -> np.ndarray:
                            np.linspace(math.pi - o, math.pi + o, K)])
 
 
-def find_offset_for_radius(prober, r_target, theta, setup: TransferFunctionSetup = TransferFunctionSetup(), initial_r=None):
+def find_offset_for_radius(prober, r_target, theta, setup: TransferFunctionSetup = TransferFunctionSetup(), initial_r=None,
+                           height=None):
     """Batched `_find_offset_for_radius` (precision-solvers.jl:133-241): for each pair (r_target[i], theta[i]) the
     image-plane offset r with ρ(r cos θ, r sin θ) = r_target.  Newton steps on ρ(r) − r_target, safeguarded by the
     bracket the monotonicity of ρ(r) provides (the lower end starts inside the hole, like the reference's contrapoint).
@@ -144,12 +173,16 @@ def find_offset_for_radius(prober, r_target, theta, setup: TransferFunctionSetup
             break
         ra = r[idx]
         rb = ra * (1 + rel)
-        gq, rho, tq = prober(np.concatenate([ra * ct[idx], rb * ct[idx]]), np.concatenate([ra * st[idx], rb * st[idx]]))
+        hq = {} if height is None else {"height": np.concatenate([height[idx], height[idx]])}
+        gq, rho, tq, rho_end = prober(np.concatenate([ra * ct[idx], rb * ct[idx]]) + setup.alpha0,
+                                      np.concatenate([ra * st[idx], rb * st[idx]]) + setup.beta0, with_end_radius=True, **hq)
         m = idx.size
         ya = rho[:m] - r_target[idx]
         yb = rho[m:] - r_target[idx]
-        lost = ~np.isfinite(ya)  # fell into the hole (or missed the plane): the root lies further out
-        ya = np.where(lost, -np.inf, ya)
+        # no intersection: the ray fell into the hole (its end point projects inside the target: the root lies further
+        # out) or left the domain before reaching the plane (end point far outside: the root lies further in)
+        lost = ~np.isfinite(ya)
+        ya = np.where(lost, np.where(rho_end[:m] < r_target[idx], -np.inf, np.inf), ya)
         for yc, rc, off in ((ya, ra, 0), (np.where(np.isfinite(yb), yb, -np.inf), rb, m)):  # both traces are candidates
             improved = np.abs(yc) < np.abs(y[idx])
             k = idx[improved]
@@ -175,7 +208,7 @@ def find_offset_for_radius(prober, r_target, theta, setup: TransferFunctionSetup
     return np.where(poor, np.nan, best), g, t
 
 
-def jacobian_ab_gr(prober, alpha, beta, setup: TransferFunctionSetup = TransferFunctionSetup()):
+def jacobian_ab_gr(prober, alpha, beta, setup: TransferFunctionSetup = TransferFunctionSetup(), thick=False):
     """|∂(ρ, g)/∂(α, β)|⁻¹ (`jacobian_∂αβ_∂gr`, precision-solvers.jl:401-451) by central differences: four traces
     per point at tolerance `fd_tol`, all points in one launch."""
     alpha = np.asarray(alpha, np.float64)
@@ -184,7 +217,10 @@ def jacobian_ab_gr(prober, alpha, beta, setup: TransferFunctionSetup = TransferF
     h = setup.fd_step * np.maximum(np.hypot(alpha, beta), 1.0)
     a = np.concatenate([alpha + h, alpha - h, alpha, alpha])
     b = np.concatenate([beta, beta, beta + h, beta - h])
-    g, rho, _ = prober(a, b, setup.fd_tol)
+    if thick:  # on the disc itself, upper hemisphere only (precision-solvers.jl:411,424-426)
+        g, rho, _ = prober(a, b, setup.fd_tol, thick=True, callback=api.domain_upper_hemisphere())
+    else:
+        g, rho, _ = prober(a, b, setup.fd_tol)
     with np.errstate(all="ignore"):
         drho_da = (rho[:n] - rho[n:2 * n]) / (2 * h)
         drho_db = (rho[2 * n:3 * n] - rho[3 * n:]) / (2 * h)
@@ -204,7 +240,40 @@ class _Workhorse:
         if np.any(np.isnan(r)):
             k = int(np.nonzero(np.isnan(r))[0][0])
             raise RuntimeError(f"Transfer function integration failed (rₑ={r_e[k]}, θ={theta[k]}).")
-        J = jacobian_ab_gr(self.prober, r * np.cos(theta), r * np.sin(theta), self.setup)
+        J = jacobian_ab_gr(self.prober, r * np.cos(theta) + self.setup.alpha0, r * np.sin(theta) + self.setup.beta0, self.setup)
+        return g, J, t
+
+
+class _ThickWorkhorse:
+    """`_thick_workhorse` (cunningham-transfer-functions.jl:274-333), batched: the offset is found on the datum plane
+    through the disc surface at rₑ, the same ray is then traced against the disc itself, and the sample only counts
+    (finite J) if it ends in the same way at (nearly) the same place, i.e. if that patch of the surface is visible."""
+
+    def __init__(self, prober, setup):
+        self.prober, self.setup, self.disc = prober, setup, prober.thick
+
+    def __call__(self, r_e, theta):
+        r_e = np.asarray(r_e, np.float64)
+        h = self.disc.cross_section(r_e)
+        r, g, t = find_offset_for_radius(self.prober, r_e, theta, self.setup, height=h)
+        if np.any(np.isnan(r)):
+            k = int(np.nonzero(np.isnan(r))[0][0])
+            raise RuntimeError(f"Transfer function integration failed (rₑ={r_e[k]}, θ={theta[k]}).")
+        alpha = r * np.cos(theta) + self.setup.alpha0
+        beta = r * np.sin(theta) + self.setup.beta0
+        gp = self.prober.points(alpha, beta, height=h)
+        # the reference re-traces with the default chart and stops at 1.1 λ_max of the datum-plane point: a disc hit
+        # later than that is no hit
+        gt = self.prober.points(alpha, beta, thick=True, chart=api.chart_for_metric(self.prober.m))
+        status = np.where((gt.status == api.StatusCodes.IntersectedWithGeometry) & (gt.lambda_max > 1.1 * gp.lambda_max),
+                          api.StatusCodes.NoStatus, gt.status)
+        dist = np.linalg.norm(gp.x - gt.x, axis=0)
+        close = dist <= 1e-3 * np.maximum(np.linalg.norm(gp.x, axis=0), np.linalg.norm(gt.x, axis=0))  # isapprox(rtol = 1e-3)
+        ok = (status == gp.status) & close
+        J = np.full(r.size, np.nan)
+        if ok.any():
+            J[ok] = jacobian_ab_gr(self.prober, alpha[ok], beta[ok], self.setup, thick=True)
+        J[~np.isfinite(J)] = np.nan  # `is_visible = isfinite(J)`; invisible samples keep g and t, J = NaN (utils.jl:71-78)
         return g, J, t
 
 
@@ -244,16 +313,16 @@ def cunningham_transfer_functions(m, x, d, radii: Sequence[float], *, prober: Op
                                   **kwargs) -> list:
     """`cunningham_transfer_function(m, x, d, rₑ; N, chart, max_time, ...)` for every rₑ in `radii` at once (the loop
     `interpolated_transfer_branches` threads over, cunningham-transfer-functions.jl:428-462)."""
-    setup_keys = {"theta_offset", "zero_atol", "N", "N_extrema", "h", "max_iter", "fd_step", "fd_tol"}
+    setup_keys = {"theta_offset", "zero_atol", "N", "N_extrema", "h", "max_iter", "fd_step", "fd_tol", "alpha0", "beta0"}
     if setup is None:
-        alias = {"θ_offset": "theta_offset"}
+        alias = {"θ_offset": "theta_offset", "α₀": "alpha0", "β₀": "beta0"}
         skw = {alias.get(k, k): kwargs.pop(k) for k in list(kwargs) if alias.get(k, k) in setup_keys}
         setup = TransferFunctionSetup(**skw)
     if prober is None:
         prober = DeviceProber(m, x, d, max_time=max_time, chart=chart, ensemble=ensemble, **kwargs)
     radii = np.atleast_1d(np.asarray(radii, np.float64))
     R = radii.size
-    work = _Workhorse(prober, setup)
+    work = _ThickWorkhorse(prober, setup) if getattr(prober, "thick", None) is not None else _Workhorse(prober, setup)
     th0 = theta_samples(setup)
     N = th0.size
     M = N + 2 * setup.N_extrema

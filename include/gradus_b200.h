@@ -163,6 +163,8 @@ typedef struct gb200_endpoints {
 #define GB200_PF_COORDINATE_TIME 3 /* x[1] o filter_intersected */
 #define GB200_PF_STATUS 4          /* status as double, no filter */
 #define GB200_PF_AFFINE_TIME 5     /* lambda_max, no filter */
+#define GB200_PF_RADIUS 6          /* r |sin(theta)| of the end point whatever its status (ConstPointFunctions.radius,
+                                      src/const-point-functions.jl; the offset root finder reads it, precision-solvers.jl:124) */
 
 /* ---- emissivity for the binned line profile ---------------------------- */
 #define GB200_EMISSIVITY_POWERLAW 0 /* eps(r) = r^(-index) */

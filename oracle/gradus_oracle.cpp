@@ -884,6 +884,7 @@ T point_function(int pf, const gb200_problem& p, const Metric& m, double r_isco,
     case GB200_PF_COORDINATE_TIME: return hit ? gp.x[0] : nan;
     case GB200_PF_STATUS: return T(gp.status);
     case GB200_PF_AFFINE_TIME: return gp.lambda;
+    case GB200_PF_RADIUS: return gp.x[1] * rabs(rsin(gp.x[2]));
     }
     return nan;
 }

@@ -51,6 +51,12 @@ class OracleProber(gb.DeviceProber):
         kinds = [f.kind() for f in self.pfs]
         return oracle.render(p, ic, kinds, plunging=None)
 
+    def evaluate_points(self, config):
+        from oracle import oracle
+        from gradus_b200 import api
+        p, ic = config.to_c()
+        return api.GeodesicPoints(oracle.trace(p, ic), config.lambda_domain[0])
+
 
 def oracle_plunging_table(kind, mp):
     """interpolate_plunging_velocities (src/orbits/orbit-solving.jl:137-167) restated with the oracle's pieces."""
