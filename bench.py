@@ -47,6 +47,27 @@ def build_workload(world, ensemble=None):
     return cfg, w, h
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keep the process's stdout for the single JSON line: fd 1 is pointed at stderr for everything else (NCCL prints its
+    version banner to stdout from C, whatever NCCL_DEBUG the box sets)."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(out):
+    line = (json.dumps(out) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -117,7 +138,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(world, w, h):
@@ -270,7 +291,7 @@ def run_ours(args, rank, world, local):
         out["lineprofile"] = lp
     if world == 1 and not args.no_callers:
         out["callers"] = run_callers(ens)
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def run_callers(ens):
@@ -369,6 +390,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
