@@ -91,7 +91,7 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = (
     "gb200_version", "gb200_init", "gb200_destroy", "gb200_last_error", "gb200_get_stats", "gb200_validate",
     "gb200_isco", "gb200_radiative_efficiency", "gb200_trace", "gb200_trace_batch", "gb200_trace_path", "gb200_build_plunging_table", "gb200_render", "gb200_lineprofile",
-    "gb200_render_device", "gb200_lineprofile_device", "gb200_fp64_peak", "gb200_debug_rhs", "gb200_debug_math",
+    "gb200_render_batch", "gb200_render_device", "gb200_lineprofile_device", "gb200_fp64_peak", "gb200_debug_rhs", "gb200_debug_math",
 )
 
 
@@ -175,6 +175,8 @@ def load():
                                  C.POINTER(PlungingTable), C.POINTER(_dp)]
     lib.gb200_lineprofile.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range), C.POINTER(Emissivity),
                                       C.POINTER(PlungingTable), _dp, C.c_int32, C.POINTER(LineProfileOpts), _dp]
+    lib.gb200_render_batch.argtypes = [vp, C.c_int32, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range), _ip, C.c_int32,
+                                       C.POINTER(C.POINTER(PlungingTable)), C.POINTER(_dp)]
     lib.gb200_render_device.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range), _ip, C.c_int32,
                                         C.POINTER(PlungingTable), C.POINTER(vp), vp, C.c_int]
     lib.gb200_lineprofile_device.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range),

@@ -759,6 +759,30 @@ def apply_point_functions(config, pfs, plunging=None):
     return images
 
 
+def apply_point_functions_batch(configs: Sequence[TracingConfiguration], pfs, plungings=None) -> list:
+    """`apply_point_functions` for many configurations in one `gb200_render_batch` call (one launch per configuration
+    on the first device's stream pool, one staged copy each way).  Returns one (len(pfs), n_rays) array per
+    configuration.  Used by the transfer-function table, where every probe round spans all (a, θ) cells."""
+    if not configs:
+        return []
+    kinds = np.array([f.kind() for f in pfs], np.int32)
+    npf, nb = len(pfs), len(configs)
+    ens = configs[0].ensemble
+    pcs = [c.to_c() for c in configs]
+    problems = (cabi.Problem * nb)(*[pc[0] for pc in pcs])
+    ics = (cabi.IC * nb)(*[pc[1] for pc in pcs])
+    ranges = (cabi.Range * nb)(*[cabi.Range(0, pc[1].n, 1) for pc in pcs])
+    images = [np.zeros((npf, pc[1].n)) for pc in pcs]
+    ptrs = (cabi._dp * (nb * npf))(*[C.cast(images[b][k].ctypes.data, cabi._dp) for b in range(nb) for k in range(npf)])
+    pl_ptrs = None
+    if plungings is not None and any(p is not None for p in plungings):
+        PT = C.POINTER(cabi.PlungingTable)
+        pl_ptrs = (PT * nb)(*[C.pointer(p.c) if p is not None else PT() for p in plungings])
+    ctx = ens.ctx(ens.devices[0])
+    cabi.check(cabi.load().gb200_render_batch(ctx, nb, problems, ics, ranges, cabi.iptr(kinds), npf, pl_ptrs, ptrs), ctx)
+    return images
+
+
 def rendergeodesics(m, position, *args, pf=None, image_width=375, image_height=250, ensemble=None, plunging=None, **kwargs):
     """`rendergeodesics(m, x, [d], λ_max; pf, image_width, image_height, αlims, βlims, ensemble, ...)`
     (src/rendering/rendering.jl:28-54).  Returns (α, β, image) with image of shape (H, W).

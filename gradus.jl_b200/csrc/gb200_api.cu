@@ -731,6 +731,119 @@ int gb200_render_device(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* 
     return render_common(ctx, p, ic, rg, pfs, npf, pl, d_images, true, s, async);
 }
 
+int gb200_render_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* problems, const gb200_ic* ics, const gb200_range* ranges,
+                       const int32_t* pfs, int32_t npf, const gb200_plunging_table* const* pls, double* const* images) {
+    if (!ctx) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null context");
+    if (nbatch < 1 || !problems || !ics || !ranges || !pfs || !images) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad batch arguments");
+    if (npf < 1 || npf > GB_MAX_PF) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "need 1..%d point functions", GB_MAX_PF);
+    for (int k = 0; k < npf; ++k)
+        if (pfs[k] < GB200_PF_SHADOW || pfs[k] > GB200_PF_RADIUS) return fail(ctx, GB200_ERR_UNSUPPORTED, "point function %d", pfs[k]);
+    for (int b = 0; b < nbatch; ++b) {
+        int rc = validate(ctx, &problems[b], &ics[b]); if (rc) return rc;
+        rc = validate_range(ctx, &ics[b], &ranges[b]); if (rc) return rc;
+        if (ics[b].kind == GB200_IC_EXPLICIT) return fail(ctx, GB200_ERR_UNSUPPORTED, "explicit initial conditions are batched by gb200_trace_batch");
+        for (int k = 0; k < npf; ++k) if (ranges[b].count && !images[(size_t)b * npf + k]) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null image pointer");
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    ctx->stats = gb200_stats{};
+    ctx->cur = ctx->stream;
+    const int nstreams = nbatch < 32 ? nbatch : 32;
+    while ((int)ctx->pool_streams.size() < nstreams) {
+        cudaStream_t st;
+        CU(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ctx->pool_streams.push_back(st);
+    }
+    // One arena: [impact-parameter lists (+ heights) and plunging tables of every problem | images of every problem],
+    // mirrored by one pinned staging buffer: one H2D and one D2H copy for the whole batch.
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    struct Off { size_t ex[3], pl[4], img[GB_MAX_PF]; };
+    std::vector<Off> off((size_t)nbatch);
+    size_t total = 0;
+    for (int b = 0; b < nbatch; ++b) {
+        Off& o = off[(size_t)b];
+        if (ics[b].kind == GB200_IC_IMPACT_PARAMETERS)
+            for (int k = 0; k < 3; ++k) if (ics[b].x[k]) { o.ex[k] = total; total += al(8 * (size_t)ics[b].n); }
+        if (pls && pls[b] && pls[b]->n >= 2) {
+            if (b > 0 && pls[b] == pls[b - 1]) { for (int k = 0; k < 4; ++k) o.pl[k] = off[(size_t)b - 1].pl[k]; }
+            else for (int k = 0; k < 4; ++k) { o.pl[k] = total; total += al(8 * (size_t)pls[b]->n); }
+        }
+    }
+    const size_t in_bytes = total;
+    for (int b = 0; b < nbatch; ++b)
+        for (int k = 0; k < npf; ++k) { off[(size_t)b].img[k] = total; total += al(8 * (size_t)ranges[b].count); }
+    void* arena_v = nullptr;
+    int rc = pool_get(ctx, SL_BATCH, total + 256, &arena_v); if (rc) return rc;
+    char* arena = (char*)arena_v;
+    if (ctx->stage_cap < total) {
+        if (ctx->stage) cudaFreeHost(ctx->stage);
+        ctx->stage = nullptr; ctx->stage_cap = 0;
+        CU(ctx, cudaMallocHost(&ctx->stage, total + 256));
+        ctx->stage_cap = total;
+    }
+    char* stage = (char*)ctx->stage;
+    void* qv = nullptr;
+    rc = pool_get(ctx, SL_BATCH_QUEUE, sizeof(unsigned long long) * 4 * (size_t)nbatch, &qv); if (rc) return rc;
+    unsigned long long* queues = (unsigned long long*)qv;
+    for (int b = 0; b < nbatch; ++b) {
+        const Off& o = off[(size_t)b];
+        if (ics[b].kind == GB200_IC_IMPACT_PARAMETERS)
+            for (int k = 0; k < 3; ++k) if (ics[b].x[k]) memcpy(stage + o.ex[k], ics[b].x[k], 8 * (size_t)ics[b].n);
+        if (pls && pls[b] && pls[b]->n >= 2 && !(b > 0 && pls[b] == pls[b - 1])) {
+            const double* src[4] = {pls[b]->r, pls[b]->ut, pls[b]->ur, pls[b]->uphi};
+            for (int k = 0; k < 4; ++k) memcpy(stage + o.pl[k], src[k], 8 * (size_t)pls[b]->n);
+        }
+    }
+    CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(ctx, cudaMemsetAsync(queues, 0, sizeof(unsigned long long) * 4 * (size_t)nbatch, ctx->stream));
+    if (in_bytes) CU(ctx, cudaMemcpyAsync(arena, stage, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    for (int sidx = 0; sidx < nstreams; ++sidx) CU(ctx, cudaStreamWaitEvent(ctx->pool_streams[(size_t)sidx], ctx->ev1, 0));
+    const bool want_isco = needs_isco(pfs, npf, false);
+    for (int b = 0; b < nbatch; ++b) {
+        if (!ranges[b].count) continue;
+        cudaStream_t st = ctx->pool_streams[(size_t)(b % nstreams)];
+        const Off& o = off[(size_t)b];
+        GbParams P;
+        fill_params(&problems[b], &ics[b], &ranges[b], P);
+        if (want_isco) { rc = set_isco(ctx, &problems[b], P); if (rc) return rc; }
+        if (ics[b].kind == GB200_IC_IMPACT_PARAMETERS)
+            for (int k = 0; k < 3; ++k) P.ex[k] = ics[b].x[k] ? (const double*)(arena + o.ex[k]) : nullptr;
+        if (pls && pls[b] && pls[b]->n >= 2) {
+            P.pl_n = pls[b]->n;
+            P.pl_r = (const double*)(arena + o.pl[0]); P.pl_ut = (const double*)(arena + o.pl[1]);
+            P.pl_ur = (const double*)(arena + o.pl[2]); P.pl_uphi = (const double*)(arena + o.pl[3]);
+        }
+        P.npf = npf;
+        for (int k = 0; k < npf; ++k) { P.pf[k] = pfs[k]; P.o_img[k] = (double*)(arena + o.img[k]); }
+        P.queue = queues + 4 * (size_t)b;
+        P.counters = P.queue + 1;
+        int blocks = 0;
+        CU(ctx, gb200_launch_trace(P, ctx->sm_count, st, &blocks));
+        ctx->stats.launches += 1;
+    }
+    for (int sidx = 0; sidx < nstreams; ++sidx) { // join the pool back into the context stream
+        CU(ctx, cudaEventRecord(ctx->ev2, ctx->pool_streams[(size_t)sidx]));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev2, 0));
+    }
+    std::vector<unsigned long long> c((size_t)nbatch * 4);
+    if (total > in_bytes) CU(ctx, cudaMemcpyAsync(stage + in_bytes, arena + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(c.data(), queues, sizeof(unsigned long long) * c.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < nbatch; ++b)
+        for (int k = 0; k < npf; ++k)
+            if (ranges[b].count) memcpy(images[(size_t)b * npf + k], stage + off[(size_t)b].img[k], 8 * (size_t)ranges[b].count);
+    float tot = 0;
+    cudaEventElapsedTime(&tot, ctx->ev0, ctx->ev3);
+    ctx->stats.kernel_ms = tot; ctx->stats.total_ms = tot;
+    for (int b = 0; b < nbatch; ++b) {
+        ctx->stats.rays += ranges[b].count;
+        ctx->stats.steps_accepted += (int64_t)c[(size_t)b * 4 + 1]; ctx->stats.steps_rejected += (int64_t)c[(size_t)b * 4 + 2];
+        ctx->stats.flagged += (int64_t)c[(size_t)b * 4 + 3];
+    }
+    return GB200_OK;
+}
+
 static int lineprofile_common(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, const gb200_emissivity* em,
                               const gb200_plunging_table* pl, const double* bins, int32_t nbins, const gb200_lineprofile_opts* opts,
                               double* flux, bool device_out, cudaStream_t stream, int async) {

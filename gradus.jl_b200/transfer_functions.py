@@ -96,7 +96,10 @@ class DeviceProber:
     def evaluate_points(self, config):
         return api.solve_tracing_problem(config)
 
-    def __call__(self, alpha, beta, tol=None, height=None, thick=False, callback=None, with_end_radius=False):
+    def cross_section(self, rho, group=None):
+        return self.thick.cross_section(rho)
+
+    def __call__(self, alpha, beta, tol=None, height=None, thick=False, callback=None, with_end_radius=False, group=None):
         """(g, ρ, t) at the intersection: with the datum plane(s) (one height per ray if `height` is given), or with the
         thick disc itself (`thick=True`, the Jacobian's traces).  `with_end_radius` adds r|sin θ| of the end point
         whatever its status (the reference's root finder reads that for rays that missed, precision-solvers.jl:124)."""
@@ -110,13 +113,83 @@ class DeviceProber:
         out = self.evaluate(self.config(alpha, beta, tol, height=height, thick=thick, callback=callback))
         return (out[0], out[1], out[2], out[3]) if with_end_radius else (out[0], out[1], out[2])
 
-    def points(self, alpha, beta, height=None, thick=False, chart=None):
+    def points(self, alpha, beta, height=None, thick=False, default_chart=False, group=None):
         """`GeodesicPoint`s of the same rays (status, λ_max, x): what the thick-disc visibility test compares."""
         alpha = np.ascontiguousarray(alpha, np.float64)
         beta = np.ascontiguousarray(beta, np.float64)
         self.launches += 1
         self.rays += alpha.size
+        chart = api.chart_for_metric(self.m) if default_chart else None
         return self.evaluate_points(self.config(alpha, beta, height=height, thick=thick, chart=chart))
+
+
+class CellProber:
+    """Several probers — one per (metric, observer) cell of a transfer-function table — behind the prober interface.
+    Every call carries `group`, the cell of each ray; the rays of all cells go out in ONE `gb200_render_batch` call
+    (one launch per cell on the stream pool), so a probe round of the lock-step orchestration costs one host round trip
+    for the whole table instead of one per cell (`make_transfer_function_table`, cunningham-transfer-functions.jl:507-530,
+    runs its cells one after the other)."""
+
+    def __init__(self, probers):
+        self.probers = list(probers)
+        self.thick = self.probers[0].thick
+        self.launches = 0
+        self.rays = 0
+
+    def cross_section(self, rho, group):
+        out = np.empty(len(rho))
+        for c in np.unique(group):
+            sel = group == c
+            out[sel] = self.probers[c].thick.cross_section(rho[sel])
+        return out
+
+    def evaluate_batch(self, configs, cells):
+        plungings = [self.probers[c]._plunging() for c in cells]
+        return api.apply_point_functions_batch(configs, self.probers[0].pfs, plungings)
+
+    def __call__(self, alpha, beta, tol=None, height=None, thick=False, callback=None, with_end_radius=False, group=None):
+        alpha = np.ascontiguousarray(alpha, np.float64)
+        beta = np.ascontiguousarray(beta, np.float64)
+        n = alpha.size
+        out = np.full((4, n), np.nan)
+        if n:
+            cells, sels = _split_by_group(group)
+            configs = [self.probers[c].config(alpha[s], beta[s], tol, height=None if height is None else height[s], thick=thick,
+                                              callback=callback) for c, s in zip(cells, sels)]
+            self.launches += 1
+            self.rays += n
+            for s, img in zip(sels, self.evaluate_batch(configs, cells)):
+                out[:, s] = img
+        return (out[0], out[1], out[2], out[3]) if with_end_radius else (out[0], out[1], out[2])
+
+    def points(self, alpha, beta, height=None, thick=False, default_chart=False, group=None):
+        """Per cell (two calls per sample set, off the probe-round path)."""
+        alpha = np.asarray(alpha, np.float64)
+        n = alpha.size
+        status = np.zeros(n, np.int32)
+        lam = np.zeros(n)
+        x = np.zeros((4, n))
+        for c, s in zip(*_split_by_group(group)):
+            gp = self.probers[c].points(alpha[s], np.asarray(beta)[s], height=None if height is None else height[s], thick=thick,
+                                        default_chart=default_chart)
+            status[s], lam[s], x[:, s] = gp.status, gp.lambda_max, gp.x
+        return _Points(status, lam, x)
+
+
+def _split_by_group(group):
+    """cells present in `group` and, per cell, the (ascending) indices of its rays: one stable sort."""
+    group = np.asarray(group)
+    order = np.argsort(group, kind="stable")
+    sorted_g = group[order]
+    cuts = np.nonzero(np.diff(sorted_g))[0] + 1
+    return sorted_g[np.concatenate([[0], cuts])] if group.size else np.zeros(0, int), np.split(order, cuts)
+
+
+@dataclass
+class _Points:
+    status: np.ndarray
+    lambda_max: np.ndarray
+    x: np.ndarray
 
 
 @dataclass
@@ -147,7 +220,7 @@ def theta_samples(setup: TransferFunctionSetup) -> np.ndarray:
 
 
 def find_offset_for_radius(prober, r_target, theta, setup: TransferFunctionSetup = TransferFunctionSetup(), initial_r=None,
-                           height=None):
+                           height=None, group=None):
     """Batched `_find_offset_for_radius` (precision-solvers.jl:133-241): for each pair (r_target[i], theta[i]) the
     image-plane offset r with ρ(r cos θ, r sin θ) = r_target.  Newton steps on ρ(r) − r_target, safeguarded by the
     bracket the monotonicity of ρ(r) provides (the lower end starts inside the hole, like the reference's contrapoint).
@@ -174,6 +247,8 @@ def find_offset_for_radius(prober, r_target, theta, setup: TransferFunctionSetup
         ra = r[idx]
         rb = ra * (1 + rel)
         hq = {} if height is None else {"height": np.concatenate([height[idx], height[idx]])}
+        if group is not None:
+            hq["group"] = np.concatenate([group[idx], group[idx]])
         gq, rho, tq, rho_end = prober(np.concatenate([ra * ct[idx], rb * ct[idx]]) + setup.alpha0,
                                       np.concatenate([ra * st[idx], rb * st[idx]]) + setup.beta0, with_end_radius=True, **hq)
         m = idx.size
@@ -208,7 +283,7 @@ def find_offset_for_radius(prober, r_target, theta, setup: TransferFunctionSetup
     return np.where(poor, np.nan, best), g, t
 
 
-def jacobian_ab_gr(prober, alpha, beta, setup: TransferFunctionSetup = TransferFunctionSetup(), thick=False):
+def jacobian_ab_gr(prober, alpha, beta, setup: TransferFunctionSetup = TransferFunctionSetup(), thick=False, group=None):
     """|∂(ρ, g)/∂(α, β)|⁻¹ (`jacobian_∂αβ_∂gr`, precision-solvers.jl:401-451) by central differences: four traces
     per point at tolerance `fd_tol`, all points in one launch."""
     alpha = np.asarray(alpha, np.float64)
@@ -217,10 +292,11 @@ def jacobian_ab_gr(prober, alpha, beta, setup: TransferFunctionSetup = TransferF
     h = setup.fd_step * np.maximum(np.hypot(alpha, beta), 1.0)
     a = np.concatenate([alpha + h, alpha - h, alpha, alpha])
     b = np.concatenate([beta, beta, beta + h, beta - h])
+    gq = {} if group is None else {"group": np.tile(group, 4)}
     if thick:  # on the disc itself, upper hemisphere only (precision-solvers.jl:411,424-426)
-        g, rho, _ = prober(a, b, setup.fd_tol, thick=True, callback=api.domain_upper_hemisphere())
+        g, rho, _ = prober(a, b, setup.fd_tol, thick=True, callback=api.domain_upper_hemisphere(), **gq)
     else:
-        g, rho, _ = prober(a, b, setup.fd_tol)
+        g, rho, _ = prober(a, b, setup.fd_tol, **gq)
     with np.errstate(all="ignore"):
         drho_da = (rho[:n] - rho[n:2 * n]) / (2 * h)
         drho_db = (rho[2 * n:3 * n] - rho[3 * n:]) / (2 * h)
@@ -235,12 +311,13 @@ class _Workhorse:
     def __init__(self, prober, setup):
         self.prober, self.setup = prober, setup
 
-    def __call__(self, r_e, theta):
-        r, g, t = find_offset_for_radius(self.prober, r_e, theta, self.setup)
+    def __call__(self, r_e, theta, group=None):
+        r, g, t = find_offset_for_radius(self.prober, r_e, theta, self.setup, group=group)
         if np.any(np.isnan(r)):
             k = int(np.nonzero(np.isnan(r))[0][0])
             raise RuntimeError(f"Transfer function integration failed (rₑ={r_e[k]}, θ={theta[k]}).")
-        J = jacobian_ab_gr(self.prober, r * np.cos(theta) + self.setup.alpha0, r * np.sin(theta) + self.setup.beta0, self.setup)
+        J = jacobian_ab_gr(self.prober, r * np.cos(theta) + self.setup.alpha0, r * np.sin(theta) + self.setup.beta0, self.setup,
+                           group=group)
         return g, J, t
 
 
@@ -252,19 +329,20 @@ class _ThickWorkhorse:
     def __init__(self, prober, setup):
         self.prober, self.setup, self.disc = prober, setup, prober.thick
 
-    def __call__(self, r_e, theta):
+    def __call__(self, r_e, theta, group=None):
         r_e = np.asarray(r_e, np.float64)
-        h = self.disc.cross_section(r_e)
-        r, g, t = find_offset_for_radius(self.prober, r_e, theta, self.setup, height=h)
+        gq = {} if group is None else {"group": group}
+        h = self.prober.cross_section(r_e, group)
+        r, g, t = find_offset_for_radius(self.prober, r_e, theta, self.setup, height=h, group=group)
         if np.any(np.isnan(r)):
             k = int(np.nonzero(np.isnan(r))[0][0])
             raise RuntimeError(f"Transfer function integration failed (rₑ={r_e[k]}, θ={theta[k]}).")
         alpha = r * np.cos(theta) + self.setup.alpha0
         beta = r * np.sin(theta) + self.setup.beta0
-        gp = self.prober.points(alpha, beta, height=h)
+        gp = self.prober.points(alpha, beta, height=h, **gq)
         # the reference re-traces with the default chart and stops at 1.1 λ_max of the datum-plane point: a disc hit
         # later than that is no hit
-        gt = self.prober.points(alpha, beta, thick=True, chart=api.chart_for_metric(self.prober.m))
+        gt = self.prober.points(alpha, beta, thick=True, default_chart=True, **gq)
         status = np.where((gt.status == api.StatusCodes.IntersectedWithGeometry) & (gt.lambda_max > 1.1 * gp.lambda_max),
                           api.StatusCodes.NoStatus, gt.status)
         dist = np.linalg.norm(gp.x - gt.x, axis=0)
@@ -272,7 +350,7 @@ class _ThickWorkhorse:
         ok = (status == gp.status) & close
         J = np.full(r.size, np.nan)
         if ok.any():
-            J[ok] = jacobian_ab_gr(self.prober, alpha[ok], beta[ok], self.setup, thick=True)
+            J[ok] = jacobian_ab_gr(self.prober, alpha[ok], beta[ok], self.setup, thick=True, group=None if group is None else group[ok])
         J[~np.isfinite(J)] = np.nan  # `is_visible = isfinite(J)`; invisible samples keep g and t, J = NaN (utils.jl:71-78)
         return g, J, t
 
@@ -310,7 +388,7 @@ def _golden_sections(fn, lower, upper, iterations, rel_tol=math.sqrt(np.finfo(fl
 
 def cunningham_transfer_functions(m, x, d, radii: Sequence[float], *, prober: Optional[Callable] = None,
                                   setup: Optional[TransferFunctionSetup] = None, chart=None, max_time=None, ensemble=None,
-                                  **kwargs) -> list:
+                                  groups=None, **kwargs) -> list:
     """`cunningham_transfer_function(m, x, d, rₑ; N, chart, max_time, ...)` for every rₑ in `radii` at once (the loop
     `interpolated_transfer_branches` threads over, cunningham-transfer-functions.jl:428-462)."""
     setup_keys = {"theta_offset", "zero_atol", "N", "N_extrema", "h", "max_iter", "fd_step", "fd_tol", "alpha0", "beta0"}
@@ -322,6 +400,8 @@ def cunningham_transfer_functions(m, x, d, radii: Sequence[float], *, prober: Op
         prober = DeviceProber(m, x, d, max_time=max_time, chart=chart, ensemble=ensemble, **kwargs)
     radii = np.atleast_1d(np.asarray(radii, np.float64))
     R = radii.size
+    groups = None if groups is None else np.asarray(groups, np.int64)  # cell of each radius (CellProber)
+    gq = (lambda sel: {}) if groups is None else (lambda sel: {"group": sel})
     work = _ThickWorkhorse(prober, setup) if getattr(prober, "thick", None) is not None else _Workhorse(prober, setup)
     th0 = theta_samples(setup)
     N = th0.size
@@ -330,7 +410,7 @@ def cunningham_transfer_functions(m, x, d, radii: Sequence[float], *, prober: Op
     gs = np.full((R, M), np.nan)
     Js = np.full((R, M), np.nan)
     ts = np.full((R, M), np.nan)
-    g, J, t = work(np.repeat(radii, N), np.tile(th0, R))
+    g, J, t = work(np.repeat(radii, N), np.tile(th0, R), **gq(None if groups is None else np.repeat(groups, N)))
     thetas[:, :N] = th0
     gs[:, :N], Js[:, :N], ts[:, :N] = g.reshape(R, N), J.reshape(R, N), t.reshape(R, N)
 
@@ -338,20 +418,20 @@ def cunningham_transfer_functions(m, x, d, radii: Sequence[float], *, prober: Op
     fill = np.full(2 * R, 0)
     sign = np.concatenate([np.ones(R), -np.ones(R)])
     re2 = np.concatenate([radii, radii])
+    grp2 = None if groups is None else np.concatenate([groups, groups])
 
     def objective(theta, mask):
         idx = np.nonzero(mask)[0]
         th = theta[idx].copy()
         pole = (np.abs(th) < 1e-4) | (np.abs(np.abs(th) - math.pi) < 1e-4)
         th = np.where(pole, th + 1e-4, th)
-        gq, Jq, tq = work(re2[idx], th)
+        gq_, Jq, tq = work(re2[idx], th, **gq(None if grp2 is None else grp2[idx]))
         out = np.full(theta.size, np.inf)
-        for j, k in enumerate(idx):
-            rr = k % R
-            col = N + (0 if k < R else setup.N_extrema) + fill[k]
-            thetas[rr, col], gs[rr, col], Js[rr, col], ts[rr, col] = th[j], gq[j], Jq[j], tq[j]
-            fill[k] += 1
-        out[idx] = sign[idx] * gq
+        rr = idx % R
+        col = N + np.where(idx < R, 0, setup.N_extrema) + fill[idx]
+        thetas[rr, col], gs[rr, col], Js[rr, col], ts[rr, col] = th, gq_, Jq, tq
+        fill[idx] += 1
+        out[idx] = sign[idx] * gq_
         return out
 
     off = setup.theta_offset
@@ -393,3 +473,28 @@ def cunningham_transfer_function(m, x, d, r_e: float, **kwargs) -> CunninghamTra
 def measure_ctf(ctf: CunninghamTransferData) -> float:
     """The scalar the reference's smoke test pins (test/smoke-tests/cunningham-transfer-functions.jl:19-21)."""
     return float(np.sum(ctf.f * ctf.g_star) / len(ctf.f))
+
+
+def transfer_function_table(metrics, observers, d, radii_of, *, ensemble=None, setup: Optional[TransferFunctionSetup] = None,
+                            prober_cls=DeviceProber, **kwargs) -> list:
+    """Cunningham transfer functions of many (metric, observer) cells in one lock-step computation: the device-side
+    form of `make_transfer_function_table` (cunningham-transfer-functions.jl:507-530), which loops `for a in a_range,
+    θ in θ_range` and computes one cell after the other.  `metrics[c]`, `observers[c]` describe cell c, `d` is the disc
+    (or a callable m -> disc, for discs that depend on the metric), `radii_of(m)` the emission radii of a cell.
+    Returns, per cell, the list of `CunninghamTransferData` of its radii."""
+    ensemble = ensemble if ensemble is not None else api.EnsembleB200()
+    probers, radii, groups = [], [], []
+    for c, (m, x) in enumerate(zip(metrics, observers)):
+        disc = d(m) if callable(d) else d
+        probers.append(prober_cls(m, x, disc, ensemble=ensemble, **kwargs))
+        r = np.atleast_1d(np.asarray(radii_of(m), np.float64))
+        radii.append(r)
+        groups.append(np.full(r.size, c))
+    cell = CellProber(probers)
+    ctfs = cunningham_transfer_functions(None, None, None, np.concatenate(radii), prober=cell, setup=setup or TransferFunctionSetup(),
+                                         groups=np.concatenate(groups))
+    out, k = [], 0
+    for r in radii:
+        out.append(ctfs[k:k + r.size])
+        k += r.size
+    return out

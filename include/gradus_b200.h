@@ -255,6 +255,17 @@ int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic,
 int gb200_trace_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* problems, const gb200_ic* ics,
                       const gb200_range* ranges, gb200_endpoints* outs);
 
+/* Many fused renders at once: `nbatch` independent (problem, initial conditions, range) triples, the same `npf` point
+   functions for all, images[b * npf + k] -> ranges[b].count doubles.  This is the transfer-function table of
+   BASELINE config 4 (make_transfer_function_table, src/transfer-functions/cunningham-transfer-functions.jl:507-530: one
+   Cunningham transfer-function computation per (a, theta) cell, each a sequence of small probes): every probe round of
+   every cell goes out in one call, one launch per cell on a stream pool, one staged H2D and one D2H copy.
+   pls: optional array of nbatch plunging-table pointers (NULL, or NULL entries, where none is needed).
+   Explicit-SoA initial conditions are not accepted here (gb200_trace_batch batches those). */
+int gb200_render_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* problems, const gb200_ic* ics,
+                       const gb200_range* ranges, const int32_t* pointfns, int32_t npf,
+                       const gb200_plunging_table* const* pls, double* const* images);
+
 /* rendergeodesics fused path (rendering.jl:28-54,89-107): trace + point
    function(s); writes `npf` images of `range->count` doubles each, image k at
    images[k], ray order (for the full range this is the (H,W) column-major image). */

@@ -153,6 +153,30 @@ def test_unsupported_geometry_is_rejected():
         gb.DeviceProber(m, [0.0, 1e4, 1.0, 0.0], object())
 
 
+def test_table_cells_in_lock_step_equal_cell_by_cell(monkeypatch):
+    """`transfer_function_table`: every probe round of all (a, θ) cells is one batched call; with the oracle standing in
+    for the batched device call the result must equal the cell-by-cell computation sample for sample."""
+    from oracle import oracle
+
+    def oracle_batch(self, configs, cells):
+        kinds = [f.kind() for f in self.probers[0].pfs]
+        return [oracle.render(*c.to_c(), kinds, plunging=None) for c in configs]
+
+    monkeypatch.setattr(tf.CellProber, "evaluate_batch", oracle_batch)
+    cells = [(0.998, 30), (0.5, 60), (0.0, 75)]
+    metrics = [gb.KerrMetric(1.0, a) for a, _ in cells]
+    observers = [[0.0, 10_000.0, math.radians(th), 0.0] for _, th in cells]
+    d = gb.ThinDisc(0.0, float("inf"))
+    setup = tf.TransferFunctionSetup(N=20, N_extrema=5)
+    table = tf.transfer_function_table(metrics, observers, d, lambda m: [gb.isco(m) + 1.0, 12.0], setup=setup, prober_cls=OracleProber)
+    assert len(table) == 3 and all(len(row) == 2 for row in table)
+    for m, x, row in zip(metrics, observers, table):
+        single = tf.cunningham_transfer_functions(m, x, d, [gb.isco(m) + 1.0, 12.0], prober=OracleProber(m, x, d), setup=setup)
+        for a_, b_ in zip(row, single):
+            assert a_.r_e == b_.r_e and a_.gmin == b_.gmin and a_.gmax == b_.gmax
+            assert np.array_equal(a_.f, b_.f, equal_nan=True) and np.array_equal(a_.g_star, b_.g_star)
+
+
 # --------------------------------------------------------------------------- thick discs
 # test/transfer-functions/test-thick-disc.jl:4-19: Σ of the finite f over the 114 samples.  As for the thin-disc literals the
 # 34 golden-section probes sit where f = 0·∞, so the sum of an independent implementation scatters with the integrator
@@ -290,3 +314,22 @@ def test_thick_disc_transfer_functions_on_the_device():
         ok = np.isfinite(fd) & np.isfinite(fo) & (gs * (1 - gs) > 1e-3)
         assert ok.sum() > 30
         assert np.max(np.abs(fd[ok] / fo[ok] - 1)) < 1e-4
+
+
+@pytest.mark.gpu
+def test_transfer_function_table_on_the_device():
+    """gb200_render_batch: a 3 x 2 (a, θ) table in lock step equals the cell-by-cell device computation bit for bit
+    (same kernel, same rays), for a thin and for a thick disc, with far fewer host round trips."""
+    cells = [(a, th) for a in (0.998, 0.5, 0.0) for th in (30, 70)]
+    metrics = [gb.KerrMetric(1.0, a) for a, _ in cells]
+    observers = [[0.0, 10_000.0, math.radians(th), 0.0] for _, th in cells]
+    setup = tf.TransferFunctionSetup(N=24, N_extrema=6)
+    for disc in (gb.ThinDisc(0.0, float("inf")), lambda m: gb.ShakuraSunyaev(m, eddington_ratio=0.2)):
+        radii_of = lambda m: [gb.isco(m) + 1.5, 9.0, 40.0]
+        table = tf.transfer_function_table(metrics, observers, disc, radii_of, setup=setup)
+        for m, x, row in zip(metrics, observers, table):
+            d = disc(m) if callable(disc) else disc
+            single = tf.cunningham_transfer_functions(m, x, d, radii_of(m), setup=setup)
+            for a_, b_ in zip(row, single):
+                assert a_.gmin == b_.gmin and a_.gmax == b_.gmax
+                assert np.array_equal(a_.f, b_.f, equal_nan=True) and np.array_equal(a_.g_star, b_.g_star)
