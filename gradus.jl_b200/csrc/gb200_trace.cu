@@ -45,6 +45,9 @@
 #define GB_OPT_LOGEXP 1 /* branch-free log/exp with constant-bank coefficients in the step controller */
 #endif
 
+#ifndef GB_OPT_PROGERR
+#define GB_OPT_PROGERR 1 /* error sums accumulated stage by stage, error scales formed under the seventh RHS */
+#endif
 #ifndef GB_OPT_PARK
 #define GB_OPT_PARK 1 /* event lanes park their stage data in shared memory until finalise */
 #endif
@@ -53,6 +56,10 @@
 #endif
 #ifndef GB_OPT_ERRDT
 #define GB_OPT_ERRDT 1 /* error norm with dt factored out of the eight components */
+#endif
+
+#if GB_OPT_PROGERR && !GB_OPT_ERRDT
+#error "GB_OPT_PROGERR accumulates the error sums without the dt factor: it needs GB_OPT_ERRDT"
 #endif
 
 #define LANE_EMPTY 0
@@ -436,6 +443,19 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
             double acc[4], s_ = 0, c_ = 1;
             double tsum = GB_A71 * vt, psum = GB_A71 * vph; // sum_j a7j k_j[1], k_j[4]
             double terr = GB_BT1 * vt, perr = GB_BT1 * vph; // sum_j btilde_j k_j[1], k_j[4]
+#if GB_OPT_PROGERR
+            // the other six error sums are accumulated stage by stage too (same order of summation as errcomb): their
+            // FMAs fill the latency gaps of the next stage instead of forming a serial tail after the seventh
+            double rerr = GB_BT1 * vr, therr = GB_BT1 * vth;
+            double a0err = GB_BT1 * kA0[0], a1err = GB_BT1 * kA1[0], a2err = GB_BT1 * kA2[0], a3err = GB_BT1 * kA3[0];
+#define GB_STAGE_ERR_V(S) rerr = fma(btcoef<S>(), w1, rerr); therr = fma(btcoef<S>(), w2, therr);
+#define GB_STAGE_ERR_A(S)                                                                                               \
+    a0err = fma(btcoef<S>(), acc[0], a0err); a1err = fma(btcoef<S>(), acc[1], a1err);                                   \
+    a2err = fma(btcoef<S>(), acc[2], a2err); a3err = fma(btcoef<S>(), acc[3], a3err);
+#else
+#define GB_STAGE_ERR_V(S)
+#define GB_STAGE_ERR_A(S)
+#endif
 #define GB_STAGE(S)                                                                                                     \
     {                                                                                                                   \
         const double xr = comb<S>(r, dt, vr, kR), xt = comb<S>(th, dt, vth, kT);                                        \
@@ -444,8 +464,10 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
         kR[S] = w1; kT[S] = w2;                                                                                         \
         tsum = fma(a7coef<S>(), w0, tsum); psum = fma(a7coef<S>(), w3, psum);                                           \
         terr = fma(btcoef<S>(), w0, terr); perr = fma(btcoef<S>(), w3, perr);                                           \
+        GB_STAGE_ERR_V(S)                                                                                               \
         rhs_accel<METRIC>(P, xr, xt, w0, w1, w2, w3, acc, s_, c_);                                                      \
         kA0[S] = acc[0]; kA1[S] = acc[1]; kA2[S] = acc[2]; kA3[S] = acc[3];                                             \
+        GB_STAGE_ERR_A(S)                                                                                               \
     }
             GB_STAGE(1) GB_STAGE(2) GB_STAGE(3) GB_STAGE(4) GB_STAGE(5)
 #undef GB_STAGE
@@ -455,9 +477,34 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
             nvth = comb<6>(vth, dt, kA2[0], kA2); nvph = comb<6>(vph, dt, kA3[0], kA3);
             nct = fma(dt, tsum, ct); nph = fma(dt, psum, ph);
             terr = fma(GB_BT7, nvt, terr); perr = fma(GB_BT7, nvph, perr);
+#if GB_OPT_PROGERR
+            rerr = fma(GB_BT7, nvr, rerr); therr = fma(GB_BT7, nvth, therr);
+            // the eight error scales only need u_prev and u: they are formed while the seventh RHS is in flight
+            const double is0 = gb_rcp_lo(fma(fabs(gb_absmax(ct, nct)), reltol, abstol)), is1 = gb_rcp_lo(fma(fabs(gb_absmax(r, nr)), reltol, abstol));
+            const double is2 = gb_rcp_lo(fma(fabs(gb_absmax(th, nth)), reltol, abstol)), is3 = gb_rcp_lo(fma(fabs(gb_absmax(ph, nph)), reltol, abstol));
+            const double is4 = gb_rcp_lo(fma(fabs(gb_absmax(vt, nvt)), reltol, abstol)), is5 = gb_rcp_lo(fma(fabs(gb_absmax(vr, nvr)), reltol, abstol));
+            const double is6 = gb_rcp_lo(fma(fabs(gb_absmax(vth, nvth)), reltol, abstol)), is7 = gb_rcp_lo(fma(fabs(gb_absmax(vph, nvph)), reltol, abstol));
+            double ee = 0;
+            {
+                double q_;
+                q_ = terr * is0; ee = fma(q_, q_, ee);
+                q_ = rerr * is1; ee = fma(q_, q_, ee);
+                q_ = therr * is2; ee = fma(q_, q_, ee);
+                q_ = perr * is3; ee = fma(q_, q_, ee);
+            }
+#endif
             rhs_accel<METRIC>(P, nr, nth, nvt, nvr, nvth, nvph, acc, s_, c_);
             kA0[6] = acc[0]; kA1[6] = acc[1]; kA2[6] = acc[2]; kA3[6] = acc[3];
             // ---- error estimate: rms( dt*sum btilde_j k_j / (abstol + max(|u_prev|,|u|) reltol) )
+#if GB_OPT_PROGERR
+            {
+                double q_;
+                q_ = fma(GB_BT7, acc[0], a0err) * is4; ee = fma(q_, q_, ee);
+                q_ = fma(GB_BT7, acc[1], a1err) * is5; ee = fma(q_, q_, ee);
+                q_ = fma(GB_BT7, acc[2], a2err) * is6; ee = fma(q_, q_, ee);
+                q_ = fma(GB_BT7, acc[3], a3err) * is7; ee = fma(q_, q_, ee);
+            }
+#else
             double ee = 0;
             {
 #if GB_OPT_ERRDT
@@ -478,6 +525,7 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                 q_ = e6 * gb_rcp_lo(fma(fabs(gb_absmax(vth, nvth)), reltol, abstol)); ee = fma(q_, q_, ee);
                 q_ = e7 * gb_rcp_lo(fma(fabs(gb_absmax(vph, nvph)), reltol, abstol)); ee = fma(q_, q_, ee);
             }
+#endif
             // EEst^2 = dt^2 sum_i (.)^2 / 8; the controller only needs log EEst = log(EEst^2) / 2 and the test EEst <= 1, so no
             // square root is taken (the Float32 controller mode takes it where it needs EEst itself).  An exactly zero
             // estimate is raised to 1e-150: the controller clamps q to 1/qmax and qold to 1e-4 either way.
