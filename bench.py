@@ -181,6 +181,8 @@ def run_ours(args, rank, world, local):
 
     peak = C.c_double()
     cabi.check(lib.gb200_fp64_peak(ctx, C.byref(peak)), ctx)
+    peak3 = C.c_double()  # the same stream with three distinct register operands per DFMA (register-file bound)
+    cabi.check(lib.gb200_fp64_issue_probe(ctx, 3, C.byref(peak3)), ctx)
     step_device(0)  # synchronous once: per-call counters for the algorithmic flop count
     st = ens.stats(local)
     attempts = st.steps_accepted + st.steps_rejected
@@ -258,6 +260,9 @@ def run_ours(args, rank, world, local):
         "traffic_note": "bytes per launch (dram read + write) from profiles/r01_traffic.json; algorithmic bytes per launch = 16 B x rays",
         "peak_source": "measured in this run: dependent-free DFMA micro-benchmark (gb200_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
         "peak_nominal": nominal_fp64,
+        "peak_three_register_dfma": peak3.value,
+        "peak_note": "peak = DFMAs with one constant operand; DFMAs whose three operands are distinct registers sustain only "
+                     "peak_three_register_dfma on this chip (register-file read bandwidth), and 22 % of this kernel's FP64 instructions are such",
         "flops_per_step_attempt": fpa, "step_attempts_per_ray": attempts / max(n_local, 1),
         "hbm": {"algorithmic_bytes_per_ray": 16, "achieved_GBs": 16.0 * n_local / (ms_local * 1e-3) / 1e9, "peak_GBs": peaks.get("hbm_gbs")},
     }

@@ -91,7 +91,7 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = (
     "gb200_version", "gb200_init", "gb200_destroy", "gb200_last_error", "gb200_get_stats", "gb200_validate",
     "gb200_isco", "gb200_radiative_efficiency", "gb200_trace", "gb200_trace_batch", "gb200_trace_path", "gb200_build_plunging_table", "gb200_render", "gb200_lineprofile",
-    "gb200_render_batch", "gb200_render_device", "gb200_lineprofile_device", "gb200_fp64_peak", "gb200_debug_rhs", "gb200_debug_math",
+    "gb200_render_batch", "gb200_render_device", "gb200_lineprofile_device", "gb200_fp64_peak", "gb200_fp64_issue_probe", "gb200_debug_rhs", "gb200_debug_math",
 )
 
 
@@ -183,6 +183,7 @@ def load():
                                              C.POINTER(Emissivity), C.POINTER(PlungingTable), _dp, C.c_int32,
                                              C.POINTER(LineProfileOpts), vp, vp, C.c_int]
     lib.gb200_fp64_peak.argtypes = [vp, _dp]
+    lib.gb200_fp64_issue_probe.argtypes = [vp, C.c_int32, _dp]
     lib.gb200_debug_rhs.argtypes = [vp, C.c_int32, _dp, C.c_int64, _dp, _dp]
     lib.gb200_debug_math.argtypes = [vp, C.c_int64, _dp, _dp]
     for name in EXPORTED_SYMBOLS:

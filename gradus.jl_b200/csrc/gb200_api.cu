@@ -954,4 +954,25 @@ int gb200_fp64_peak(gb200_ctx* ctx, double* tflops_out) {
     return GB200_OK;
 }
 
+int gb200_fp64_issue_probe(gb200_ctx* ctx, int32_t mix, double* tflops_out) {
+    if (!ctx || !tflops_out || mix < 0 || mix > 4) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    void* d;
+    int rc = pool_get(ctx, SL_SCRATCH, 64, &d); if (rc) return rc;
+    const int blocks = ctx->sm_count * 8, iters = 20000;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(ctx, gb200_launch_dfma_mix((double*)d, blocks, iters, mix, ctx->stream));
+        CU(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev2);
+        const double tf = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    *tflops_out = best;
+    return GB200_OK;
+}
+
 } // extern "C"

@@ -7,6 +7,7 @@ cudaError_t gb200_launch_trace(const GbParams& P, int sm_count, cudaStream_t str
 cudaError_t gb200_launch_hist(const double* g, const double* f, int64_t n, const double* bins, int nbins, int right_closed,
                               double* partial, int nblocks, double* out, cudaStream_t stream);
 cudaError_t gb200_launch_dfma(double* d_out, int blocks, int iters, cudaStream_t stream);
+cudaError_t gb200_launch_dfma_mix(double* d_out, int blocks, int iters, int mix, cudaStream_t stream);
 cudaError_t gb200_launch_path(const GbParams& P, const double* d_u0, int cap, double* d_lambda, double* d_u, int* d_meta, cudaStream_t stream);
 cudaError_t gb200_launch_debug_rhs(const GbParams& P, long long n, const double* d_u, double* d_du, cudaStream_t stream);
 cudaError_t gb200_launch_debug_math(long long n, const double* d_x, double* d_out5, cudaStream_t stream);

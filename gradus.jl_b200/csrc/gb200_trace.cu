@@ -69,18 +69,38 @@
 
 // stage input  u + dt * sum_{l<S} a_{S+1,l+1} k_l   (S = 1..6 -> stages 2..7), summed left to right like the reference.
 // k0 is the FSAL slope (k1 of the tableau); k[1..5] are k2..k6.
+#ifndef GB_OPT_SMEMK
+#define GB_OPT_SMEMK 1 /* stage values k2..k6 live in shared memory instead of 60 registers */
+#endif
+// Storage of the stage values of one component: get(0) = k1 (FSAL), get(1..5) = k2..k6, get(6) = k7.  With GB_OPT_SMEMK
+// k2..k6 sit in shared memory ([stage][thread], conflict-free), k1 and k7 in registers; the indices are compile-time
+// constants after unrolling, so the selection folds away.
+#if GB_OPT_SMEMK
+struct GbK {
+    double k1, k7;
+    double* p; // &sh_k[first row of this component][threadIdx.x]
+    GB_D double get(int j) const { return j == 0 ? k1 : (j == 6 ? k7 : p[(j - 1) * GB_BLOCK]); }
+    GB_D void set(int j, double v) { if (j == 0) k1 = v; else if (j == 6) k7 = v; else p[(j - 1) * GB_BLOCK] = v; }
+};
+#else
+struct GbK {
+    double v[7];
+    GB_D double get(int j) const { return v[j]; }
+    GB_D void set(int j, double x) { v[j] = x; }
+};
+#endif
 template <int S>
-GB_D double comb(double u, double dt, double k0, const double* k) {
+GB_D double comb(double u, double dt, double k0, const GbK& k) {
     if (S == 1) return fma(dt * GB_A21, k0, u);
-    if (S == 2) return fma(dt, fma(GB_A32, k[1], GB_A31 * k0), u);
-    if (S == 3) return fma(dt, fma(GB_A43, k[2], fma(GB_A42, k[1], GB_A41 * k0)), u);
-    if (S == 4) return fma(dt, fma(GB_A54, k[3], fma(GB_A53, k[2], fma(GB_A52, k[1], GB_A51 * k0))), u);
-    if (S == 5) return fma(dt, fma(GB_A65, k[4], fma(GB_A64, k[3], fma(GB_A63, k[2], fma(GB_A62, k[1], GB_A61 * k0)))), u);
-    return fma(dt, fma(GB_A76, k[5], fma(GB_A75, k[4], fma(GB_A74, k[3], fma(GB_A73, k[2], fma(GB_A72, k[1], GB_A71 * k0))))), u);
+    if (S == 2) return fma(dt, fma(GB_A32, k.get(1), GB_A31 * k0), u);
+    if (S == 3) return fma(dt, fma(GB_A43, k.get(2), fma(GB_A42, k.get(1), GB_A41 * k0)), u);
+    if (S == 4) return fma(dt, fma(GB_A54, k.get(3), fma(GB_A53, k.get(2), fma(GB_A52, k.get(1), GB_A51 * k0))), u);
+    if (S == 5) return fma(dt, fma(GB_A65, k.get(4), fma(GB_A64, k.get(3), fma(GB_A63, k.get(2), fma(GB_A62, k.get(1), GB_A61 * k0)))), u);
+    return fma(dt, fma(GB_A76, k.get(5), fma(GB_A75, k.get(4), fma(GB_A74, k.get(3), fma(GB_A73, k.get(2), fma(GB_A72, k.get(1), GB_A71 * k0))))), u);
 }
 // sum_j btilde_j k_j with k_1 = k0, k_7 = k6
-GB_D double errcomb(double k0, const double* k, double k6) {
-    return fma(GB_BT7, k6, fma(GB_BT6, k[5], fma(GB_BT5, k[4], fma(GB_BT4, k[3], fma(GB_BT3, k[2], fma(GB_BT2, k[1], GB_BT1 * k0))))));
+GB_D double errcomb(double k0, const GbK& k, double k6) {
+    return fma(GB_BT7, k6, fma(GB_BT6, k.get(5), fma(GB_BT5, k.get(4), fma(GB_BT4, k.get(3), fma(GB_BT3, k.get(2), fma(GB_BT2, k.get(1), GB_BT1 * k0))))));
 }
 template <int S> GB_D constexpr double a7coef() {
     return S == 0 ? GB_A71 : S == 1 ? GB_A72 : S == 2 ? GB_A73 : S == 3 ? GB_A74 : S == 4 ? GB_A75 : GB_A76;
@@ -89,10 +109,11 @@ template <int S> GB_D constexpr double btcoef() {
     return S == 0 ? GB_BT1 : S == 1 ? GB_BT2 : S == 2 ? GB_BT3 : S == 3 ? GB_BT4 : S == 4 ? GB_BT5 : S == 5 ? GB_BT6 : GB_BT7;
 }
 // dense-output polynomial coefficients  u(Th) = u0 + dt*Th*(k0 + Th*(C2 + Th*(C3 + Th*C4)))
-GB_D void dense_coeffs(double k0, const double* k, double k6, double& C2, double& C3, double& C4) {
-    C2 = fma(GB_R72, k6, fma(GB_R62, k[5], fma(GB_R52, k[4], fma(GB_R42, k[3], fma(GB_R32, k[2], fma(GB_R22, k[1], GB_R12 * k0))))));
-    C3 = fma(GB_R73, k6, fma(GB_R63, k[5], fma(GB_R53, k[4], fma(GB_R43, k[3], fma(GB_R33, k[2], fma(GB_R23, k[1], GB_R13 * k0))))));
-    C4 = fma(GB_R74, k6, fma(GB_R64, k[5], fma(GB_R54, k[4], fma(GB_R44, k[3], fma(GB_R34, k[2], fma(GB_R24, k[1], GB_R14 * k0))))));
+GB_D void dense_coeffs(double k0, const GbK& k, double k6, double& C2, double& C3, double& C4) {
+    const double k2 = k.get(1), k3 = k.get(2), k4 = k.get(3), k5 = k.get(4), k6_ = k.get(5);
+    C2 = fma(GB_R72, k6, fma(GB_R62, k6_, fma(GB_R52, k5, fma(GB_R42, k4, fma(GB_R32, k3, fma(GB_R22, k2, GB_R12 * k0))))));
+    C3 = fma(GB_R73, k6, fma(GB_R63, k6_, fma(GB_R53, k5, fma(GB_R43, k4, fma(GB_R33, k3, fma(GB_R23, k2, GB_R13 * k0))))));
+    C4 = fma(GB_R74, k6, fma(GB_R64, k6_, fma(GB_R54, k5, fma(GB_R44, k4, fma(GB_R34, k3, fma(GB_R24, k2, GB_R14 * k0))))));
 }
 GB_D double dense_eval(double u0, double dt, double Th, double C1, double C2, double C3, double C4) {
     return fma(dt * Th, fma(Th, fma(Th, fma(Th, C4, C3), C2), C1), u0);
@@ -154,8 +175,8 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
     double lam = 0;                                                         // affine parameter at u_prev (integrator.t)
     double ct = 0, r = 0, th = 0, ph = 0, vt = 0, vr = 0, vth = 0, vph = 0; // u_prev (ct = coordinate time x^t)
     double nct = 0, nr = 0, nth = 0, nph = 0, nvt = 0, nvr = 0, nvth = 0, nvph = 0; // u (proposed / final)
-    double kA0[7], kA1[7], kA2[7], kA3[7]; // accelerations: [0] = FSAL k1, [1..5] = k2..k6, [6] = k7
-    double kR[6], kT[6];                   // stage velocities v^r, v^theta of k2..k6 ([0] unused: k1's are vr, vth)
+    GbK kA0, kA1, kA2, kA3; // accelerations: get(0) = FSAL k1, get(1..5) = k2..k6, get(6) = k7
+    GbK kR, kT;             // stage velocities v^r, v^theta of k2..k6 (k1, k7 unused: those are vr, vth and nvr, nvth)
     double dt = 0, cprev = 1, acos_prev = 1, ev_lo = 0, ev_hi = 0;
     double qoldpow = 1; // controller memory: beta2 * log(qold) (POW_EXACT) or qold^beta2 (POW_FAST32)
     double tfinal = 0;
@@ -168,12 +189,22 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
     const int maxit = (int)(P.maxiters < 0x7fffffff ? P.maxiters : 0x7fffffff); // step attempts are counted in 32 bits
     bool exhausted = false;
     unsigned long long tot_acc = 0, tot_rej = 0, tot_flag = 0;
+#if GB_OPT_SMEMK
+    // k2..k6 of the four accelerations and of the r, theta stage velocities: 30 rows; rows 30..33 park the k7
+    // accelerations of a lane whose step ended in a disc event until it is finalised.
+    __shared__ double sh_k[34][GB_BLOCK];
+    kA0.p = &sh_k[0][threadIdx.x]; kA1.p = &sh_k[5][threadIdx.x]; kA2.p = &sh_k[10][threadIdx.x]; kA3.p = &sh_k[15][threadIdx.x];
+    kR.p = &sh_k[20][threadIdx.x]; kT.p = &sh_k[25][threadIdx.x];
+    kR.k1 = kR.k7 = kT.k1 = kT.k7 = 0.0;
 #pragma unroll
-    for (int j = 0; j < 7; ++j) { kA0[j] = kA1[j] = kA2[j] = kA3[j] = 0.0; }
+    for (int j = 0; j < 34; ++j) sh_k[j][threadIdx.x] = 0.0;
+#endif
 #pragma unroll
-    for (int j = 0; j < 6; ++j) { kR[j] = kT[j] = 0.0; }
+    for (int j = 0; j < 7; ++j) { kA0.set(j, 0.0); kA1.set(j, 0.0); kA2.set(j, 0.0); kA3.set(j, 0.0); }
+#pragma unroll
+    for (int j = 1; j < 6; ++j) { kR.set(j, 0.0); kT.set(j, 0.0); }
 
-#if GB_OPT_PARK
+#if GB_OPT_PARK && !GB_OPT_SMEMK
     // Stage data of a lane whose step ended in a disc event, parked until the lane is finalised: k2..k7 accelerations
     // (24) and the k2..k6 stage velocities of r and theta (10), [value][thread] so a warp's accesses are conflict-free.
     // Keeping them in registers instead made every attempt spill ~20 of them for the (rare) root find.
@@ -206,14 +237,16 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
             if (state == LANE_PENDING) {
                 int status = pend_status;
                 if (GEOM != GB200_GEOMETRY_NONE && pend_event) {
-#if GB_OPT_PARK
+#if GB_OPT_SMEMK
+                    kA0.k7 = sh_k[30][threadIdx.x]; kA1.k7 = sh_k[31][threadIdx.x]; kA2.k7 = sh_k[32][threadIdx.x]; kA3.k7 = sh_k[33][threadIdx.x];
+#elif GB_OPT_PARK
 #pragma unroll
                     for (int j = 0; j < 6; ++j) {
-                        kA0[j + 1] = sh_park[j][threadIdx.x]; kA1[j + 1] = sh_park[6 + j][threadIdx.x];
-                        kA2[j + 1] = sh_park[12 + j][threadIdx.x]; kA3[j + 1] = sh_park[18 + j][threadIdx.x];
+                        kA0.set(j + 1, sh_park[j][threadIdx.x]); kA1.set(j + 1, sh_park[6 + j][threadIdx.x]);
+                        kA2.set(j + 1, sh_park[12 + j][threadIdx.x]); kA3.set(j + 1, sh_park[18 + j][threadIdx.x]);
                     }
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) { kR[j + 1] = sh_park[24 + j][threadIdx.x]; kT[j + 1] = sh_park[29 + j][threadIdx.x]; }
+                    for (int j = 0; j < 5; ++j) { kR.set(j + 1, sh_park[24 + j][threadIdx.x]); kT.set(j + 1, sh_park[29 + j][threadIdx.x]); }
 #endif
                     // ContinuousCallback root find on the dense output (DiffEqBase find_callback_time, LeftRootFind)
                     double C2r, C3r, C4r, C2t, C3t, C4t;
@@ -270,19 +303,19 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                     // stage v^t, v^phi are recomputed from the stored accelerations (bitwise the same values)
                     double W0[7], W3[7], WR[7], WT[7];
                     W0[0] = vt; W3[0] = vph; WR[0] = vr; WT[0] = vth;
-                    W0[1] = comb<1>(vt, dt, kA0[0], kA0); W3[1] = comb<1>(vph, dt, kA3[0], kA3);
-                    W0[2] = comb<2>(vt, dt, kA0[0], kA0); W3[2] = comb<2>(vph, dt, kA3[0], kA3);
-                    W0[3] = comb<3>(vt, dt, kA0[0], kA0); W3[3] = comb<3>(vph, dt, kA3[0], kA3);
-                    W0[4] = comb<4>(vt, dt, kA0[0], kA0); W3[4] = comb<4>(vph, dt, kA3[0], kA3);
-                    W0[5] = comb<5>(vt, dt, kA0[0], kA0); W3[5] = comb<5>(vph, dt, kA3[0], kA3);
+                    W0[1] = comb<1>(vt, dt, kA0.get(0), kA0); W3[1] = comb<1>(vph, dt, kA3.get(0), kA3);
+                    W0[2] = comb<2>(vt, dt, kA0.get(0), kA0); W3[2] = comb<2>(vph, dt, kA3.get(0), kA3);
+                    W0[3] = comb<3>(vt, dt, kA0.get(0), kA0); W3[3] = comb<3>(vph, dt, kA3.get(0), kA3);
+                    W0[4] = comb<4>(vt, dt, kA0.get(0), kA0); W3[4] = comb<4>(vph, dt, kA3.get(0), kA3);
+                    W0[5] = comb<5>(vt, dt, kA0.get(0), kA0); W3[5] = comb<5>(vph, dt, kA3.get(0), kA3);
                     W0[6] = nvt; W3[6] = nvph; WR[6] = nvr; WT[6] = nvth;
 #pragma unroll
-                    for (int j = 1; j < 6; ++j) { WR[j] = kR[j]; WT[j] = kT[j]; }
+                    for (int j = 1; j < 6; ++j) { WR[j] = kR.get(j); WT[j] = kT.get(j); }
                     double st = 0, sr = 0, sth = 0, sph = 0, s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
                     for (int j = 0; j < 7; ++j) {
                         st = fma(b[j], W0[j], st); sr = fma(b[j], WR[j], sr); sth = fma(b[j], WT[j], sth); sph = fma(b[j], W3[j], sph);
-                        s0 = fma(b[j], kA0[j], s0); s1 = fma(b[j], kA1[j], s1); s2 = fma(b[j], kA2[j], s2); s3 = fma(b[j], kA3[j], s3);
+                        s0 = fma(b[j], kA0.get(j), s0); s1 = fma(b[j], kA1.get(j), s1); s2 = fma(b[j], kA2.get(j), s2); s3 = fma(b[j], kA3.get(j), s3);
                     }
                     nct = fma(dt, st, ct); nr = fma(dt, sr, r); nth = fma(dt, sth, th); nph = fma(dt, sph, ph);
                     nvt = fma(dt, s0, vt); nvr = fma(dt, s1, vr); nvth = fma(dt, s2, vth); nvph = fma(dt, s3, vph);
@@ -403,7 +436,7 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                         // 10^(-(2 + log10 md)/5) = (100 md)^(-1/5)
                         const double dt1 = (md <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : exp(-0.2 * log(100.0 * md));
                         dt = fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
-                        kA0[0] = acc[0]; kA1[0] = acc[1]; kA2[0] = acc[2]; kA3[0] = acc[3];
+                        kA0.set(0, acc[0]); kA1.set(0, acc[1]); kA2.set(0, acc[2]); kA3.set(0, acc[3]);
                         qoldpow = (P.pow_mode == GB200_POW_FAST32) ? ctrl_pow_log(log_qoldinit, 1e-4, beta2, P.pow_mode) : beta2 * log_qoldinit;
                         state = LANE_RUN;
                     }
@@ -447,7 +480,7 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
             // the other six error sums are accumulated stage by stage too (same order of summation as errcomb): their
             // FMAs fill the latency gaps of the next stage instead of forming a serial tail after the seventh
             double rerr = GB_BT1 * vr, therr = GB_BT1 * vth;
-            double a0err = GB_BT1 * kA0[0], a1err = GB_BT1 * kA1[0], a2err = GB_BT1 * kA2[0], a3err = GB_BT1 * kA3[0];
+            double a0err = GB_BT1 * kA0.get(0), a1err = GB_BT1 * kA1.get(0), a2err = GB_BT1 * kA2.get(0), a3err = GB_BT1 * kA3.get(0);
 #define GB_STAGE_ERR_V(S) rerr = fma(btcoef<S>(), w1, rerr); therr = fma(btcoef<S>(), w2, therr);
 #define GB_STAGE_ERR_A(S)                                                                                               \
     a0err = fma(btcoef<S>(), acc[0], a0err); a1err = fma(btcoef<S>(), acc[1], a1err);                                   \
@@ -456,25 +489,33 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
 #define GB_STAGE_ERR_V(S)
 #define GB_STAGE_ERR_A(S)
 #endif
+#if GB_OPT_SMEMK && GB_OPT_INTMAX
+            // running maxima of the high words of |k_j[r]|, |k_j[theta]| for the event-scan pre-test (no re-read from shared memory)
+            int mxr = __double2hiint(vr) & 0x7fffffff, mxt = __double2hiint(vth) & 0x7fffffff;
+#define GB_STAGE_MAX mxr = max(mxr, __double2hiint(w1) & 0x7fffffff); mxt = max(mxt, __double2hiint(w2) & 0x7fffffff);
+#else
+#define GB_STAGE_MAX
+#endif
 #define GB_STAGE(S)                                                                                                     \
     {                                                                                                                   \
         const double xr = comb<S>(r, dt, vr, kR), xt = comb<S>(th, dt, vth, kT);                                        \
-        const double w0 = comb<S>(vt, dt, kA0[0], kA0), w1 = comb<S>(vr, dt, kA1[0], kA1),                              \
-                     w2 = comb<S>(vth, dt, kA2[0], kA2), w3 = comb<S>(vph, dt, kA3[0], kA3);                            \
-        kR[S] = w1; kT[S] = w2;                                                                                         \
+        const double w0 = comb<S>(vt, dt, kA0.get(0), kA0), w1 = comb<S>(vr, dt, kA1.get(0), kA1),                              \
+                     w2 = comb<S>(vth, dt, kA2.get(0), kA2), w3 = comb<S>(vph, dt, kA3.get(0), kA3);                            \
+        kR.set(S, w1); kT.set(S, w2);                                                                                   \
+        GB_STAGE_MAX                                                                                                    \
         tsum = fma(a7coef<S>(), w0, tsum); psum = fma(a7coef<S>(), w3, psum);                                           \
         terr = fma(btcoef<S>(), w0, terr); perr = fma(btcoef<S>(), w3, perr);                                           \
         GB_STAGE_ERR_V(S)                                                                                               \
         rhs_accel<METRIC>(P, xr, xt, w0, w1, w2, w3, acc, s_, c_);                                                      \
-        kA0[S] = acc[0]; kA1[S] = acc[1]; kA2[S] = acc[2]; kA3[S] = acc[3];                                             \
+        kA0.set(S, acc[0]); kA1.set(S, acc[1]); kA2.set(S, acc[2]); kA3.set(S, acc[3]);                                 \
         GB_STAGE_ERR_A(S)                                                                                               \
     }
             GB_STAGE(1) GB_STAGE(2) GB_STAGE(3) GB_STAGE(4) GB_STAGE(5)
 #undef GB_STAGE
             // 7th stage = the proposed state (FSAL)
             nr = comb<6>(r, dt, vr, kR); nth = comb<6>(th, dt, vth, kT);
-            nvt = comb<6>(vt, dt, kA0[0], kA0); nvr = comb<6>(vr, dt, kA1[0], kA1);
-            nvth = comb<6>(vth, dt, kA2[0], kA2); nvph = comb<6>(vph, dt, kA3[0], kA3);
+            nvt = comb<6>(vt, dt, kA0.get(0), kA0); nvr = comb<6>(vr, dt, kA1.get(0), kA1);
+            nvth = comb<6>(vth, dt, kA2.get(0), kA2); nvph = comb<6>(vph, dt, kA3.get(0), kA3);
             nct = fma(dt, tsum, ct); nph = fma(dt, psum, ph);
             terr = fma(GB_BT7, nvt, terr); perr = fma(GB_BT7, nvph, perr);
 #if GB_OPT_PROGERR
@@ -494,7 +535,7 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
             }
 #endif
             rhs_accel<METRIC>(P, nr, nth, nvt, nvr, nvth, nvph, acc, s_, c_);
-            kA0[6] = acc[0]; kA1[6] = acc[1]; kA2[6] = acc[2]; kA3[6] = acc[3];
+            kA0.set(6, acc[0]); kA1.set(6, acc[1]); kA2.set(6, acc[2]); kA3.set(6, acc[3]);
             // ---- error estimate: rms( dt*sum btilde_j k_j / (abstol + max(|u_prev|,|u|) reltol) )
 #if GB_OPT_PROGERR
             {
@@ -513,8 +554,8 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                 const double edt = dt;
 #endif
                 const double e0 = edt * terr, e1 = edt * errcomb(vr, kR, nvr), e2 = edt * errcomb(vth, kT, nvth), e3 = edt * perr;
-                const double e4 = edt * errcomb(kA0[0], kA0, kA0[6]), e5 = edt * errcomb(kA1[0], kA1, kA1[6]);
-                const double e6 = edt * errcomb(kA2[0], kA2, kA2[6]), e7 = edt * errcomb(kA3[0], kA3, kA3[6]);
+                const double e4 = edt * errcomb(kA0.get(0), kA0, kA0.get(6)), e5 = edt * errcomb(kA1.get(0), kA1, kA1.get(6));
+                const double e6 = edt * errcomb(kA2.get(0), kA2, kA2.get(6)), e7 = edt * errcomb(kA3.get(0), kA3, kA3.get(6));
                 double q_;
                 q_ = e0 * gb_rcp_lo(fma(fabs(gb_absmax(ct, nct)), reltol, abstol)); ee = fma(q_, q_, ee);
                 q_ = e1 * gb_rcp_lo(fma(fabs(gb_absmax(r, nr)), reltol, abstol)); ee = fma(q_, q_, ee);
@@ -580,12 +621,15 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                         // cheap bound first: |u(Th) - u0| <= |dt| * L * max_j |k_j| with L = max_Th sum_j |b_j(Th)| = 7.5822
                         // for the Tsit5 dense output; only when it is inconclusive are the polynomial coefficients formed
                         const double adt = fabs(dt);
-#if GB_OPT_INTMAX
-                        const double mth = absmax7_bound(vth, kT[1], kT[2], kT[3], kT[4], kT[5], nvth);
-                        const double mr = absmax7_bound(vr, kR[1], kR[2], kR[3], kR[4], kR[5], nvr);
+#if GB_OPT_SMEMK && GB_OPT_INTMAX
+                        const double mth = __hiloint2double(max(mxt, __double2hiint(nvth) & 0x7fffffff) + 1, 0);
+                        const double mr = __hiloint2double(max(mxr, __double2hiint(nvr) & 0x7fffffff) + 1, 0);
+#elif GB_OPT_INTMAX
+                        const double mth = absmax7_bound(vth, kT.get(1), kT.get(2), kT.get(3), kT.get(4), kT.get(5), nvth);
+                        const double mr = absmax7_bound(vr, kR.get(1), kR.get(2), kR.get(3), kR.get(4), kR.get(5), nvr);
 #else
-                        const double mth = fmax(fmax(fmax(fabs(vth), fabs(kT[1])), fmax(fabs(kT[2]), fabs(kT[3]))), fmax(fmax(fabs(kT[4]), fabs(kT[5])), fabs(nvth)));
-                        const double mr = fmax(fmax(fmax(fabs(vr), fabs(kR[1])), fmax(fabs(kR[2]), fabs(kR[3]))), fmax(fmax(fabs(kR[4]), fabs(kR[5])), fabs(nvr)));
+                        const double mth = fmax(fmax(fmax(fabs(vth), fabs(kT.get(1))), fmax(fabs(kT.get(2)), fabs(kT.get(3)))), fmax(fmax(fabs(kT.get(4)), fabs(kT.get(5))), fabs(nvth)));
+                        const double mr = fmax(fmax(fmax(fabs(vr), fabs(kR.get(1))), fmax(fabs(kR.get(2)), fabs(kR.get(3)))), fmax(fmax(fabs(kR.get(4)), fabs(kR.get(5))), fabs(nvr)));
 #endif
                         bool need = sprev < 0.0 || scan_needed<GEOM>(P, r, acos_prev, cprev, adt * 7.5823 * mth, adt * 7.5823 * mr);
                         double C2r = 0, C3r = 0, C4r = 0, C2t = 0, C3t = 0, C4t = 0;
@@ -609,15 +653,19 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                     }
                 }
             }
-#if GB_OPT_PARK
+#if GB_OPT_SMEMK
+            if (GEOM != GB200_GEOMETRY_NONE && event) { // k2..k6 are in shared memory already; k7 joins them
+                sh_k[30][threadIdx.x] = kA0.k7; sh_k[31][threadIdx.x] = kA1.k7; sh_k[32][threadIdx.x] = kA2.k7; sh_k[33][threadIdx.x] = kA3.k7;
+            }
+#elif GB_OPT_PARK
             if (GEOM != GB200_GEOMETRY_NONE && event) {
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
-                    sh_park[j][threadIdx.x] = kA0[j + 1]; sh_park[6 + j][threadIdx.x] = kA1[j + 1];
-                    sh_park[12 + j][threadIdx.x] = kA2[j + 1]; sh_park[18 + j][threadIdx.x] = kA3[j + 1];
+                    sh_park[j][threadIdx.x] = kA0.get(j + 1); sh_park[6 + j][threadIdx.x] = kA1.get(j + 1);
+                    sh_park[12 + j][threadIdx.x] = kA2.get(j + 1); sh_park[18 + j][threadIdx.x] = kA3.get(j + 1);
                 }
 #pragma unroll
-                for (int j = 0; j < 5; ++j) { sh_park[24 + j][threadIdx.x] = kR[j + 1]; sh_park[29 + j][threadIdx.x] = kT[j + 1]; }
+                for (int j = 0; j < 5; ++j) { sh_park[24 + j][threadIdx.x] = kR.get(j + 1); sh_park[29 + j][threadIdx.x] = kT.get(j + 1); }
             }
 #endif
             int status = GB200_STATUS_NO_STATUS;
@@ -643,8 +691,8 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
             lam = advance ? tnew : lam;
             ct = advance ? nct : ct; r = advance ? nr : r; th = advance ? nth : th; ph = advance ? nph : ph;
             vt = advance ? nvt : vt; vr = advance ? nvr : vr; vth = advance ? nvth : vth; vph = advance ? nvph : vph;
-            kA0[0] = advance ? kA0[6] : kA0[0]; kA1[0] = advance ? kA1[6] : kA1[0];
-            kA2[0] = advance ? kA2[6] : kA2[0]; kA3[0] = advance ? kA3[6] : kA3[0];
+            kA0.set(0, advance ? kA0.get(6) : kA0.get(0)); kA1.set(0, advance ? kA1.get(6) : kA1.get(0));
+            kA2.set(0, advance ? kA2.get(6) : kA2.get(0)); kA3.set(0, advance ? kA3.get(6) : kA3.get(0));
             cprev = advance ? cnext : cprev; acos_prev = advance ? fabs(c_) : acos_prev;
             dt = advance ? dtprop : (accept ? dt : dtrej);
         }
@@ -923,6 +971,62 @@ __global__ void __launch_bounds__(256) gb200_dfma_kernel(double* out, int iters,
     }
     const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 12345.678) out[0] = s; // never true: keeps the chain alive
+}
+
+// The same DFMA stream with MIX independent integer-pipe instructions (LOP3) per DFMA: probes whether non-FP64
+// instructions issue in the shadow of the two-cycle FP64 instructions or add to them.
+template <int MIX>
+__global__ void __launch_bounds__(256) gb200_dfma_mix_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    unsigned b0 = threadIdx.x, b1 = b0 + 1, b2 = b0 + 2, b3 = b0 + 3, b4 = b0 + 4, b5 = b0 + 5, b6 = b0 + 6, b7 = b0 + 7;
+    const unsigned x = blockIdx.x | 1u, y = gridDim.x;
+    const double m = 1.0000001, c = 1e-9;
+#define GB_LOP(b) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b) : "r"(x), "r"(y));
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+#pragma unroll
+            for (int v = 0; v < MIX; ++v) { GB_LOP(b0) GB_LOP(b1) GB_LOP(b2) GB_LOP(b3) GB_LOP(b4) GB_LOP(b5) GB_LOP(b6) GB_LOP(b7) }
+        }
+    }
+#undef GB_LOP
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    const unsigned t = b0 ^ b1 ^ b2 ^ b3 ^ b4 ^ b5 ^ b6 ^ b7;
+    if (s == 12345.678 || t == 0xdeadbeefu) out[0] = s + t; // practically never true: keeps both chains alive
+}
+// DFMA / DMUL streams whose operands are all distinct vector registers (the probes above multiply by a uniform constant):
+// mode 3 = DFMA a <- a * m_k + c_k with per-thread m_k, c_k; mode 4 = the same with DMUL + DADD pairs.
+template <int MODE>
+__global__ void __launch_bounds__(256) gb200_dfma_reg_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m0 = 1.0 + 1e-9 * threadIdx.x, m1 = m0 + 1e-9, m2 = m0 + 2e-9, m3 = m0 + 3e-9;
+    const double c0 = 1e-9 * (threadIdx.x + 1), c1 = c0 * 2, c2 = c0 * 3, c3 = c0 * 4;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (MODE == 3) {
+                a0 = fma(a0, m0, c0); a1 = fma(a1, m1, c1); a2 = fma(a2, m2, c2); a3 = fma(a3, m3, c3);
+                a4 = fma(a4, m0, c1); a5 = fma(a5, m1, c2); a6 = fma(a6, m2, c3); a7 = fma(a7, m3, c0);
+            } else {
+                a0 = __dmul_rn(a0, m0); a1 = __dadd_rn(a1, c1); a2 = __dmul_rn(a2, m2); a3 = __dadd_rn(a3, c3);
+                a4 = __dmul_rn(a4, m0); a5 = __dadd_rn(a5, c2); a6 = __dmul_rn(a6, m2); a7 = __dadd_rn(a7, c0);
+            }
+        }
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) out[0] = s;
+}
+
+cudaError_t gb200_launch_dfma_mix(double* d_out, int blocks, int iters, int mix, cudaStream_t stream) {
+    if (mix == 3) { gb200_dfma_reg_kernel<3><<<blocks, 256, 0, stream>>>(d_out, iters, 0.5); return cudaGetLastError(); }
+    if (mix == 4) { gb200_dfma_reg_kernel<4><<<blocks, 256, 0, stream>>>(d_out, iters, 0.5); return cudaGetLastError(); }
+    if (mix == 0) gb200_dfma_mix_kernel<0><<<blocks, 256, 0, stream>>>(d_out, iters, 0.5);
+    else if (mix == 1) gb200_dfma_mix_kernel<1><<<blocks, 256, 0, stream>>>(d_out, iters, 0.5);
+    else if (mix == 2) gb200_dfma_mix_kernel<2><<<blocks, 256, 0, stream>>>(d_out, iters, 0.5);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
 }
 
 cudaError_t gb200_launch_dfma(double* d_out, int blocks, int iters, cudaStream_t stream) {
