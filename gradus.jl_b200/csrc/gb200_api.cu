@@ -955,7 +955,7 @@ int gb200_fp64_peak(gb200_ctx* ctx, double* tflops_out) {
 }
 
 int gb200_fp64_issue_probe(gb200_ctx* ctx, int32_t mix, double* tflops_out) {
-    if (!ctx || !tflops_out || mix < 0 || mix > 4) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad argument");
+    if (!ctx || !tflops_out || mix < 0 || mix > 5) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad argument");
     CU(ctx, cudaSetDevice(ctx->device));
     void* d;
     int rc = pool_get(ctx, SL_SCRATCH, 64, &d); if (rc) return rc;

@@ -1006,7 +1006,10 @@ __global__ void __launch_bounds__(256) gb200_dfma_reg_kernel(double* out, int it
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            if (MODE == 3) {
+            if (MODE == 5) { // one register operand shared by consecutive DFMAs (operand reuse cache)
+                a0 = fma(a0, m0, c0); a1 = fma(a1, m0, c1); a2 = fma(a2, m0, c2); a3 = fma(a3, m0, c3);
+                a4 = fma(a4, m0, c1); a5 = fma(a5, m0, c2); a6 = fma(a6, m0, c3); a7 = fma(a7, m0, c0);
+            } else if (MODE == 3) {
                 a0 = fma(a0, m0, c0); a1 = fma(a1, m1, c1); a2 = fma(a2, m2, c2); a3 = fma(a3, m3, c3);
                 a4 = fma(a4, m0, c1); a5 = fma(a5, m1, c2); a6 = fma(a6, m2, c3); a7 = fma(a7, m3, c0);
             } else {
@@ -1022,6 +1025,7 @@ __global__ void __launch_bounds__(256) gb200_dfma_reg_kernel(double* out, int it
 cudaError_t gb200_launch_dfma_mix(double* d_out, int blocks, int iters, int mix, cudaStream_t stream) {
     if (mix == 3) { gb200_dfma_reg_kernel<3><<<blocks, 256, 0, stream>>>(d_out, iters, 0.5); return cudaGetLastError(); }
     if (mix == 4) { gb200_dfma_reg_kernel<4><<<blocks, 256, 0, stream>>>(d_out, iters, 0.5); return cudaGetLastError(); }
+    if (mix == 5) { gb200_dfma_reg_kernel<5><<<blocks, 256, 0, stream>>>(d_out, iters, 0.5); return cudaGetLastError(); }
     if (mix == 0) gb200_dfma_mix_kernel<0><<<blocks, 256, 0, stream>>>(d_out, iters, 0.5);
     else if (mix == 1) gb200_dfma_mix_kernel<1><<<blocks, 256, 0, stream>>>(d_out, iters, 0.5);
     else if (mix == 2) gb200_dfma_mix_kernel<2><<<blocks, 256, 0, stream>>>(d_out, iters, 0.5);

@@ -313,7 +313,8 @@ int gb200_fp64_peak(gb200_ctx* ctx, double* tflops_out);
 
 /* Diagnostic behind the roofline discussion: the DFMA stream of gb200_fp64_peak with `mix` = 1 or 2
    independent integer-pipe instructions per DFMA (do non-FP64 instructions issue in the shadow of the FP64 ones?),
-   mix = 3: DFMAs whose three operands are distinct vector registers, mix = 4: DMUL / DADD with register operands.
+   mix = 3: DFMAs whose three operands are distinct vector registers, mix = 4: DMUL / DADD with register operands,
+   mix = 5: three register operands of which one is shared by consecutive DFMAs (operand reuse).
    Returns the FP64 instruction rate x 2 in T/s (= TFLOP/s for the DFMA modes). */
 int gb200_fp64_issue_probe(gb200_ctx* ctx, int32_t mix, double* tflops_out);
 
