@@ -479,6 +479,9 @@ GB_HD inline void geodesic_accel(const double g[5], const double dr[5], const do
 #ifndef GB_OPT_SIGNFLIP
 #define GB_OPT_SIGNFLIP 1 /* quadrant signs of sincos through the integer pipe */
 #endif
+#ifndef GB_OPT_MAGIC
+#define GB_OPT_MAGIC 1 /* nearest-integer through the 1.5 * 2^52 shift instead of rint + double->int conversion */
+#endif
 #ifndef GB_OPT_CW2
 #define GB_OPT_CW2 1 /* two-term Cody-Waite reduction (the third term is 2e-21 per quadrant) */
 #endif
@@ -500,7 +503,14 @@ GB_D double gb_flip_sign(double x, int signbit31) {
 // Reduced form: x = n pi/2 + rr, returns sn = sin(rr), cs = cos(rr) and the quadrant n.
 struct GbSinCos { double sn, cs; int n; };
 GB_D GbSinCos gb_sincos_reduced(double x) {
+#if GB_OPT_MAGIC
+    // round-to-nearest through the 1.5 * 2^52 shift: the integer lands in the low mantissa word (two's complement) and the
+    // rounded value comes back with one subtraction; rint + double->int conversions are slow-rate instructions
+    const double tq = fma(x, GB_SC_2OPI, 6755399441055744.0);
+    const double q = tq - 6755399441055744.0;
+#else
     const double q = rint(x * GB_SC_2OPI);
+#endif
     double rr = fma(-q, GB_SC_PIO2_1, x);
     rr = fma(-q, GB_SC_PIO2_2, rr);
 #if !GB_OPT_CW2
@@ -520,7 +530,12 @@ GB_D GbSinCos gb_sincos_reduced(double x) {
     pc = fma(z, pc, GB_SC_C1);
     const double cs = fma(z * z, pc, fma(z, -0.5, 1.0));
     GbSinCos o;
-    o.sn = sn; o.cs = cs; o.n = __double2int_rn(q);
+    o.sn = sn; o.cs = cs;
+#if GB_OPT_MAGIC
+    o.n = __double2loint(tq);
+#else
+    o.n = __double2int_rn(q);
+#endif
     return o;
 }
 GB_D void gb_sincos(double x, double* sp, double* cp) {
@@ -561,7 +576,12 @@ GB_D double gb_log_pos(double x) {
 // Branch-free exp for |x| <= 8 (the controller clamps its argument first): x = k ln2 + rr, degree-12 Taylor polynomial on
 // |rr| <= ln2/2 (truncation 1.7e-16 relative), scaled by 2^k through the exponent field.
 GB_D double gb_exp_small(double x) {
+#if GB_OPT_MAGIC
+    const double tk = fma(x, GB_INVLN2, 6755399441055744.0);
+    const double kf = tk - 6755399441055744.0;
+#else
     const double kf = rint(x * GB_INVLN2);
+#endif
     double rr = fma(-kf, GB_LN2_HI, x);
     rr = fma(-kf, GB_LN2_LO, rr);
     // Estrin-style split into even/odd halves keeps the dependency chain short
@@ -574,7 +594,11 @@ GB_D double gb_exp_small(double x) {
     pe = fma(r2, pe, GB_EX2);
     // exp(rr) = 1 + rr + r2 * (pe + rr * po)
     const double p = fma(r2, fma(rr, po, pe), rr) + 1.0;
+#if GB_OPT_MAGIC
+    const int k = __double2loint(tk);
+#else
     const int k = __double2int_rn(kf);
+#endif
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
