@@ -461,23 +461,26 @@ GB_HD inline void geodesic_accel(const double g[5], const double dr[5], const do
     const double gitt = g[3] * iD, giphph = g[0] * iD, gitph = -g[4] * iD;
     const double girr = gb_rcp(g[1]), githth = gb_rcp(g[2]);
     const double d0 = vr * dr[0] + vth * dth[0];
-    const double d1 = vr * dr[1] + vth * dth[1];
-    const double d2 = vr * dr[2] + vth * dth[2];
     const double d3 = vr * dr[3] + vth * dth[3];
     const double d4 = vr * dr[4] + vth * dth[4];
     const double Pt = d0 * vt + d4 * vph;
     const double Pp = d4 * vt + d3 * vph;
     const double vtt = vt * vt, vrr = vr * vr, vthth = vth * vth, vpp = vph * vph, vtp2 = 2.0 * vt * vph;
-    const double Sr = dr[0] * vtt + dr[1] * vrr + dr[2] * vthth + dr[3] * vpp + dr[4] * vtp2;
-    const double St = dth[0] * vtt + dth[1] * vrr + dth[2] * vthth + dth[3] * vpp + dth[4] * vtp2;
+    // S_r / 2 - gdot_rr v^r and S_th / 2 - gdot_thth v^th with the (v^r)^2, (v^th)^2 terms merged (see kerr_rhs_accel_sq)
+    const double X = vr * vth;
+    const double Br = dr[0] * vtt - dr[1] * vrr + dr[2] * vthth + dr[3] * vpp + dr[4] * vtp2;
+    const double Bt = dth[0] * vtt + dth[1] * vrr - dth[2] * vthth + dth[3] * vpp + dth[4] * vtp2;
     acc[0] = fma(-gitt, Pt, -gitph * Pp);
-    acc[1] = girr * fma(-d1, vr, 0.5 * Sr);
-    acc[2] = githth * fma(-d2, vth, 0.5 * St);
+    acc[1] = girr * fma(-dth[1], X, 0.5 * Br);
+    acc[2] = githth * fma(-dr[2], X, 0.5 * Bt);
     acc[3] = fma(-gitph, Pt, -giphph * Pp);
 }
 
 #ifndef GB_OPT_SIGNFLIP
 #define GB_OPT_SIGNFLIP 1 /* quadrant signs of sincos through the integer pipe */
+#endif
+#ifndef GB_OPT_KERR_NOD12
+#define GB_OPT_KERR_NOD12 1 /* Kerr a^r, a^theta without gdot_rr, gdot_thth */
 #endif
 #ifndef GB_OPT_MAGIC
 #define GB_OPT_MAGIC 1 /* nearest-integer through the 1.5 * 2^52 shift instead of rint + double->int conversion */
@@ -644,16 +647,27 @@ GB_D void kerr_rhs_accel_sq(double M, double a, double a2, double twoM, double r
     // -g^tt, -g^tph, g^phph: the signs are carried by operand modifiers below, never by a separate negation
     const double mgitt = B * iDel, mgitph = a * w * iDel, giphph = (1.0 - w) * iDel_is2;
     const double girr = Del * iSig, githth = iSig;
-    const double d0 = fma(vr, r0, vth * t0), d1 = fma(vr, r1, vth * t1), d2 = fma(vr, r2_, vth * t2);
-    const double d3 = fma(vr, r3, vth * t3), d4 = fma(vr, r4, vth * t4);
+    const double d0 = fma(vr, r0, vth * t0), d3 = fma(vr, r3, vth * t3), d4 = fma(vr, r4, vth * t4);
     const double Pt = fma(d0, vt, d4 * vph), Pp = fma(d4, vt, d3 * vph);
     const double vtt = vt * vt, vrr = vr * vr, vthth = vth * vth, vpp = vph * vph, vtp2 = 2.0 * vt * vph;
+    acc[0] = fma(mgitt, Pt, mgitph * Pp);
+    acc[3] = fma(mgitph, Pt, -giphph * Pp);
+#if GB_OPT_KERR_NOD12
+    // a^r = g^rr (S_r / 2 - gdot_rr v^r) with gdot_rr v^r = d_r g_rr v^r v^r + d_th g_rr v^r v^th: the d_r g_rr (v^r)^2 term
+    // flips its sign inside the sum and only the cross term -d_th g_rr v^r v^th remains (same for a^theta), which
+    // saves forming gdot_rr and gdot_thth
+    const double X = vr * vth;
+    const double Br = fma(r0, vtt, fma(-r1, vrr, fma(r2_, vthth, fma(r3, vpp, r4 * vtp2))));
+    const double Bt = fma(t0, vtt, fma(t1, vrr, fma(-t2, vthth, fma(t3, vpp, t4 * vtp2))));
+    acc[1] = girr * fma(-t1, X, 0.5 * Br);
+    acc[2] = githth * fma(-r2_, X, 0.5 * Bt);
+#else
+    const double d1 = fma(vr, r1, vth * t1), d2 = fma(vr, r2_, vth * t2);
     const double Sr = fma(r0, vtt, fma(r1, vrr, fma(r2_, vthth, fma(r3, vpp, r4 * vtp2))));
     const double St = fma(t0, vtt, fma(t1, vrr, fma(t2, vthth, fma(t3, vpp, t4 * vtp2))));
-    acc[0] = fma(mgitt, Pt, mgitph * Pp);
     acc[1] = girr * fma(-d1, vr, 0.5 * Sr);
     acc[2] = githth * fma(-d2, vth, 0.5 * St);
-    acc[3] = fma(mgitph, Pt, -giphph * Pp);
+#endif
 }
 
 // The right-hand side, inlined at each of the six stages.  (Measured alternatives, profiles/r01_tuning_log.md: one
