@@ -91,7 +91,8 @@ class BumblebeeMetric:
 
 @dataclass(frozen=True)
 class KerrNewmanMetric:
-    """src/metrics/kerr-newman-ad.jl:41-58.  Neutral test particles only (the reference's `q = 0` default)."""
+    """src/metrics/kerr-newman-ad.jl:41-58.  Charged test particles: pass `q=` to the tracing call (Lorentz force,
+    kerr-newman-ad.jl:66-102)."""
 
     M: float = 1.0
     a: float = 0.0
@@ -348,6 +349,7 @@ class TracingConfiguration:
     reltol: float
     gtol: float = 1e-2
     mu: float = 0.0
+    q: float = 0.0  # charge of the test particle (TraceGeodesic(μ, q), src/tracing/tracing.jl; Kerr-Newman only)
     pow_mode: int = cabi.POW_EXACT
     maxiters: int = 0
     dtmax: float = 0.0
@@ -360,6 +362,11 @@ class TracingConfiguration:
         p = cabi.Problem()
         p.metric_kind = m.kind
         p.metric_params[:] = m.params()
+        if self.q != 0.0:
+            if not isinstance(m, KerrNewmanMetric):
+                raise ValueError("charged test particles need a metric with an electromagnetic potential (KerrNewmanMetric)")
+            # geodesic_ode_problem(::KerrNewmanMetric), kerr-newman-ad.jl:74-78: q for photons, q / μ otherwise
+            p.metric_params[3] = self.q if abs(self.mu) < 1e-8 else self.q / self.mu
         if self.geometry is None:
             p.geometry_kind = cabi.GEOMETRY_NONE
         elif isinstance(self.geometry, _SUPPORTED_GEOMETRY):
@@ -459,7 +466,7 @@ class TracingConfiguration:
 
 
 _CONFIG_KWARGS = {"chart", "callback", "solver", "ensemble", "trajectories", "abstol", "reltol", "gtol", "mu", "μ",
-                  "pow_mode", "maxiters", "dtmax", "save_on", "verbose", "progress_bar", "integrator_verbose"}
+                  "q", "pow_mode", "maxiters", "dtmax", "save_on", "verbose", "progress_bar", "integrator_verbose"}
 
 
 def tracing_configuration(m, position, velocity, *args, **kwargs):
@@ -500,6 +507,7 @@ def tracing_configuration(m, position, velocity, *args, **kwargs):
         reltol=kwargs.get("reltol", DEFAULT_TOLERANCE),
         gtol=kwargs.get("gtol", 1e-2),
         mu=kwargs.get("mu", kwargs.get("μ", 0.0)),
+        q=float(kwargs.get("q", 0.0)),
         pow_mode=kwargs.get("pow_mode", cabi.POW_EXACT),
         maxiters=kwargs.get("maxiters", 0),
         dtmax=kwargs.get("dtmax", 0.0),

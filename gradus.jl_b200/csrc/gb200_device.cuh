@@ -455,11 +455,12 @@ GB_HD inline void metric_jacobian_rt(const GbParams& P, double r, double s, doub
 // a^mu = -g^{mu m} ( gdot_{mk} v^k - 1/2 S_m ),  gdot = v^r d_r g + v^th d_th g,  S_m = d_m g_{kl} v^k v^l
 // (the contraction of auto-diff.jl:115-141 with d_t = d_phi = 0 written out)
 GB_HD inline void geodesic_accel(const double g[5], const double dr[5], const double dth[5],
-                                 double vt, double vr, double vth, double vph, double acc[4]) {
+                                 double vt, double vr, double vth, double vph, double acc[4], double* gi_out = nullptr) {
     const double D = g[0] * g[3] - g[4] * g[4];
     const double iD = gb_rcp(D);
     const double gitt = g[3] * iD, giphph = g[0] * iD, gitph = -g[4] * iD;
     const double girr = gb_rcp(g[1]), githth = gb_rcp(g[2]);
+    if (gi_out) { gi_out[0] = gitt; gi_out[1] = girr; gi_out[2] = githth; gi_out[3] = giphph; gi_out[4] = gitph; }
     const double d0 = vr * dr[0] + vth * dth[0];
     const double d3 = vr * dr[3] + vth * dth[3];
     const double d4 = vr * dr[4] + vth * dth[4];
@@ -670,6 +671,29 @@ GB_D void kerr_rhs_accel_sq(double M, double a, double a2, double twoM, double r
 #endif
 }
 
+// Lorentz force on a charged test particle in the Kerr-Newman field, q/mu F^mu_kappa v^kappa with
+// F = g^-1 (dA - dA') (faraday_tensor, src/tracing/utility.jl:89-99; geodesic_ode_problem(::KerrNewmanMetric),
+// src/metrics/kerr-newman-ad.jl:66-102) and A = (r Q / Sigma) (1, 0, 0, -a sin^2 theta) (:29-33), derivatives in closed form.
+GB_HD inline void kerr_newman_lorentz(const double* mp, double r, double s, double c, const double gi[5],
+                                      double vt, double vr, double vth, double vph, double acc[4]) {
+    const double a = mp[1], Q = mp[2], q = mp[3];
+    const double a2 = a * a, s2 = s * s, sc2 = 2.0 * s * c;
+    const double Sig = fma(a2, c * c, r * r);
+    const double iS = gb_rcp(Sig);
+    const double At = Q * r * iS;
+    const double At_r = Q * (Sig - 2.0 * r * r) * iS * iS; // d_r (r / Sigma) = (Sigma - 2 r^2) / Sigma^2
+    const double At_t = At * a2 * sc2 * iS;                 // d_theta (1 / Sigma) = 2 a^2 sin cos / Sigma^2
+    const double Ap_r = -a * s2 * At_r;
+    const double Ap_t = -a * fma(sc2, At, s2 * At_t);
+    // w_sigma = (d_kappa A_sigma - d_sigma A_kappa) v^kappa
+    const double wt = fma(At_r, vr, At_t * vth), wp = fma(Ap_r, vr, Ap_t * vth);
+    const double wr = -fma(At_r, vt, Ap_r * vph), wth = -fma(At_t, vt, Ap_t * vph);
+    acc[0] = fma(q, fma(gi[0], wt, gi[4] * wp), acc[0]);
+    acc[1] = fma(q * gi[1], wr, acc[1]);
+    acc[2] = fma(q * gi[2], wth, acc[2]);
+    acc[3] = fma(q, fma(gi[4], wt, gi[3] * wp), acc[3]);
+}
+
 // The right-hand side, inlined at each of the six stages.  (Measured alternatives, profiles/r01_tuning_log.md: one
 // out-of-line copy removes instruction-fetch stalls but pays ~25% more instructions in call marshalling; with the
 // CTA-synchronous stepping of gb200_trace.cu the inlined form is the faster one.)
@@ -703,7 +727,11 @@ GB_RHS_ATTR GbAcc rhs_eval(const GbParams& P, double r, double th, double vt, do
     } else {
         double g[5], dr[5], dth[5];
         metric_jacobian<METRIC>(P, r, o.s, o.c, g, dr, dth);
-        geodesic_accel(g, dr, dth, vt, vr, vth, vph, acc);
+        if (METRIC == GB200_METRIC_KERR_NEWMAN) {
+            double gi[5];
+            geodesic_accel(g, dr, dth, vt, vr, vth, vph, acc, gi);
+            if (P.mp[3] != 0.0) kerr_newman_lorentz(P.mp, r, o.s, o.c, gi, vt, vr, vth, vph, acc);
+        } else geodesic_accel(g, dr, dth, vt, vr, vth, vph, acc);
     }
     o.a0 = acc[0]; o.a1 = acc[1]; o.a2 = acc[2]; o.a3 = acc[3];
     return o;

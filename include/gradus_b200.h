@@ -48,7 +48,8 @@ extern "C" {
 #define GB200_METRIC_JOHANNSEN_PSALTIS 1 /* params: M, a, eps3    */
 #define GB200_METRIC_JOHANNSEN 2         /* src/metrics/johannsen-ad.jl:40-62     params: M, a, alpha13, alpha22, alpha52, eps3 */
 #define GB200_METRIC_BUMBLEBEE 3         /* src/metrics/bumblebee-ad.jl:26-46     params: M, a, l  (l > -1, |a| <= 0.3)        */
-#define GB200_METRIC_KERR_NEWMAN 4       /* src/metrics/kerr-newman-ad.jl:41-58   params: M, a, Q  (neutral particles: q = 0)  */
+#define GB200_METRIC_KERR_NEWMAN 4       /* src/metrics/kerr-newman-ad.jl:41-58   params: M, a, Q, q/mu (charge of the test particle:
+                                            Lorentz force q/mu F v of geodesic_ode_problem(::KerrNewmanMetric), :66-102; 0 = neutral) */
 #define GB200_METRIC_COUNT 5
 
 /* ---- accretion geometry: src/geometry/discs/ --------------------------- */

@@ -257,6 +257,40 @@ void compute_geodesic_equation(const S gi[5], const S j1[5], const S j2[5], cons
     }
 }
 
+// electromagnetic_potential of the Kerr-Newman hole, kerr-newman-ad.jl:29-33: (r Q / Sigma) (1, 0, 0, -a sin^2 theta)
+template <class S>
+void electromagnetic_potential(const Metric& m, const S& r, const S& th, S A[4]) {
+    S Sigma = sq(r) + sq(S(m.a) * rcos(th));
+    S f = r * S(m.p[2]) / Sigma;
+    A[0] = f; A[1] = S(0.0); A[2] = S(0.0); A[3] = -f * S(m.a) * sq(rsin(th));
+}
+
+// faraday_tensor, src/tracing/utility.jl:89-99: F = g^-1 (dA - dA'), dA[kappa][sigma] = d_sigma A_kappa (ForwardDiff in the
+// reference, dual numbers here); the charged test particle feels q/mu (F v) on top of the geodesic acceleration
+// (geodesic_ode_problem(::KerrNewmanMetric), kerr-newman-ad.jl:66-102).
+template <class T>
+void lorentz_acceleration(const Metric& m, const T gi[5], const T u[8], T q_mu, T out[4]) {
+    typedef Dual<T, 2> D;
+    D rd(u[1]), td(u[2]);
+    rd.d[0] = T(1.0);
+    td.d[1] = T(1.0);
+    D Ad[4];
+    electromagnetic_potential<D>(m, rd, td, Ad);
+    T dA[4][4];
+    for (int k = 0; k < 4; ++k) { dA[k][0] = T(0.0); dA[k][1] = Ad[k].d[0]; dA[k][2] = Ad[k].d[1]; dA[k][3] = T(0.0); }
+    T GI[4][4];
+    symmetric_matrix(gi, GI);
+    for (int mu = 0; mu < 4; ++mu) {
+        T tot = T(0.0);
+        for (int k = 0; k < 4; ++k) {
+            T f = T(0.0);
+            for (int s = 0; s < 4; ++s) f = f + GI[mu][s] * (dA[s][k] - dA[k][s]);
+            tot = tot + f * u[4 + k];
+        }
+        out[mu] = q_mu * tot;
+    }
+}
+
 // geodesic_equation (auto-diff.jl:213-226) wrapped as _second_order_ode_f (geodesic-problem.jl:87-92)
 template <class T>
 void rhs(const Metric& m, const T u[8], T du[8]) {
@@ -264,6 +298,11 @@ void rhs(const Metric& m, const T u[8], T du[8]) {
     metric_jacobian<T>(m, u[1], u[2], g, j1, j2);
     inverse_metric_components<T>(g, gi);
     compute_geodesic_equation<T>(gi, j1, j2, u + 4, acc);
+    if (m.kind == GB200_METRIC_KERR_NEWMAN && m.p[3] != 0.0) { // metric_params[3]: q / mu of the test particle
+        T em[4];
+        lorentz_acceleration<T>(m, gi, u, T(m.p[3]), em);
+        for (int i = 0; i < 4; ++i) acc[i] = acc[i] + em[i];
+    }
     for (int i = 0; i < 4; ++i) { du[i] = u[4 + i]; du[4 + i] = acc[i]; }
 }
 

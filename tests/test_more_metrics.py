@@ -119,3 +119,46 @@ def test_device_matches_oracle_at_nontrivial_parameters(m):
     assert np.max(np.abs(got[0][hit] - want[0][hit])) < 1e-6
     assert np.max(np.abs(got[1][hit] / want[1][hit] - 1)) < 1e-6
     assert np.array_equal(np.isnan(got[0][ok]), np.isnan(want[0][ok]))
+
+
+# --------------------------------------------------------------------------- charged test particles in Kerr-Newman
+# test/unit/metrics.kerr-newman.jl:6-30: shadow fingerprints of a 40 x 40 render for q = 0, +1, -1 (rtol 1e-3 there)
+CHARGED = [(0.0, 428809.9681726607), (1.0, 253280.6794972752), (-1.0, 619335.5670363897)]
+
+
+def _charged_config(q, w=40, h=40):
+    m = gb.KerrNewmanMetric(M=1.0, a=0.6, Q=0.6)
+    x = [0.0, 1000.0, math.pi / 2, 0.0]
+    return m, x, api.tracing_configuration(m, x, api.RenderGrid(w, h, (-8, 8), (-8, 8)), 2000.0, q=q, trajectories=w * h)
+
+
+@pytest.mark.parametrize("q, literal", CHARGED)
+def test_oracle_reproduces_the_charged_particle_literals(q, literal):
+    """Lorentz force q F v (faraday_tensor, src/tracing/utility.jl:89-99; kerr-newman-ad.jl:66-102), dual-number dA."""
+    p, ic = _charged_config(q)[2].to_c()
+    assert np.nansum(oracle.render(p, ic, [cabi.PF_SHADOW])[0]) == pytest.approx(literal, rel=1e-6)
+
+
+def test_charge_needs_an_electromagnetic_potential():
+    m = gb.KerrMetric(1.0, 0.5)
+    with pytest.raises(ValueError):
+        api.tracing_configuration(m, [0.0, 1000.0, 1.0, 0.0], api.RenderGrid(4, 4, (-8, 8), (-8, 8)), 2000.0, q=1.0).to_c()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("q, literal", CHARGED)
+def test_device_reproduces_the_charged_particle_literals(q, literal):
+    m, x, cfg = _charged_config(q)
+    _, _, img = gb.rendergeodesics(m, x, 2000.0, image_width=40, image_height=40, alpha_lims=(-8, 8), beta_lims=(-8, 8), q=q)
+    assert np.nansum(img) == pytest.approx(literal, rel=1e-6)
+    # ray by ray against the oracle (closed-form Faraday tensor vs dual numbers): same classes, same affine times
+    m, x, cfg = _charged_config(q, 64, 64)
+    p, ic = cfg.to_c()
+    ref = oracle.trace(p, ic)
+    ref_l = oracle.trace(p, ic, precision=1)
+    got = api.solve_tracing_problem(cfg)
+    ok = ref.status == ref_l.status
+    assert ok.mean() > 0.99 and np.array_equal(got.status[ok], ref.status[ok])
+    esc = ok & (ref.status == cabi.STATUS_NO_STATUS)  # reached lambda_max: a well-defined end state
+    assert esc.sum() > 1000
+    assert np.max(np.abs(got.x[:, esc] - ref.x[:, esc]) / np.maximum(np.abs(ref.x[:, esc]), 1.0)) < 1e-6
