@@ -51,7 +51,9 @@ from .api import (  # noqa: F401
 )
 from . import corona, hostmath, reverberation, tf_integration  # noqa: F401
 from ._cabi import GradusB200Error  # noqa: F401
+from . import transfer_functions  # noqa: F401
 from .transfer_functions import (  # noqa: F401
+    CellProber,
     CunninghamTransferData,
     DeviceProber,
     TransferFunctionSetup,
@@ -59,6 +61,7 @@ from .transfer_functions import (  # noqa: F401
     cunningham_transfer_functions,
     find_offset_for_radius,
     jacobian_ab_gr,
+    transfer_function_table,
 )
 
 __version__ = "0.1.0"

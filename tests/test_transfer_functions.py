@@ -333,3 +333,40 @@ def test_transfer_function_table_on_the_device():
             for a_, b_ in zip(row, single):
                 assert a_.gmin == b_.gmin and a_.gmax == b_.gmax
                 assert np.array_equal(a_.f, b_.f, equal_nan=True) and np.array_equal(a_.g_star, b_.g_star)
+
+
+# test/transfer-functions/test-problem-cases.jl:17-31: "transfer functions that have caused issue in the past" (observer at
+# r = 500 000, mostly 88 degrees); they must run.  (a, theta_obs in degrees, r_e)
+PROBLEM_CASES = [(0.998, 88.0, 1.2469706551751847), (0.10324137931034483, 82.06896551724138, 21.755193176415617),
+                 (0.0, 88.0, 264.549754423346), (0.998, 88.0, 1.2369706551751847), (0.034413793103448276, 88.0, 396.93135746662),
+                 (0.034413793103448276, 88.0, 377.0698611), (0.034413793103448276, 88.0, 417.83902340237086),
+                 (0.0, 88.0, 794.4185036834359), (0.9291724137931034, 88.0, 2.1204839212537308)]
+
+
+def _problem_case(a, th, cls, **kw):
+    m = gb.KerrMetric(1.0, a)
+    x = [0.0, 500_000.0, math.radians(th), 0.0]
+    d = gb.ThinDisc(0.0, float("inf"))
+    return m, x, d, cls(m, x, d, **kw)
+
+
+def test_reference_problem_cases_with_the_oracle_as_tracer():
+    for a, th, re in PROBLEM_CASES[:3]:
+        m, x, d, pr = _problem_case(a, th, OracleProber)
+        ctf = tf.cunningham_transfer_function(m, x, d, re, prober=pr)
+        assert len(ctf.f) == 114 and np.all(np.isfinite(ctf.g_star)) and 0 < ctf.gmin < ctf.gmax < 2
+
+
+@pytest.mark.gpu
+def test_reference_problem_cases_on_the_device():
+    """All nine, as one lock-step table (every case is its own (metric, observer) cell) and one by one: same result."""
+    metrics = [gb.KerrMetric(1.0, a) for a, _, _ in PROBLEM_CASES]
+    observers = [[0.0, 500_000.0, math.radians(th), 0.0] for _, th, _ in PROBLEM_CASES]
+    radii = {id(m): re for m, (_, _, re) in zip(metrics, PROBLEM_CASES)}
+    table = tf.transfer_function_table(metrics, observers, gb.ThinDisc(0.0, float("inf")), lambda m: [radii[id(m)]])
+    for (a, th, re), row in zip(PROBLEM_CASES, table):
+        ctf = row[0]
+        assert len(ctf.f) == 114 and np.all(np.isfinite(ctf.g_star)) and 0 < ctf.gmin < ctf.gmax < 2
+        m, x, d, pr = _problem_case(a, th, gb.DeviceProber)
+        single = tf.cunningham_transfer_function(m, x, d, re, prober=pr)
+        assert single.gmin == ctf.gmin and single.gmax == ctf.gmax and np.array_equal(single.f, ctf.f, equal_nan=True)
