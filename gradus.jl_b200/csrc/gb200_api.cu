@@ -34,7 +34,8 @@ struct gb200_ctx {
     std::vector<DevBuf> pool;
     unsigned long long* d_queue = nullptr; // [0] queue, [1..3] counters
     double fp64_peak = 0.0;
-    std::vector<cudaStream_t> pool_streams; // gb200_trace_batch
+    std::vector<cudaStream_t> pool_streams; // gb200_trace_batch, gb200_render_batch, pipelined gb200_render
+    std::vector<cudaEvent_t> chunk_events;  // pipelined gb200_render: one per chunk
     void* stage = nullptr;                  // pinned host staging for gb200_trace_batch
     size_t stage_cap = 0;
 };
@@ -401,6 +402,7 @@ void gb200_destroy(gb200_ctx* ctx) {
     for (auto& b : ctx->pool) if (b.p) cudaFree(b.p);
     if (ctx->d_queue) cudaFree(ctx->d_queue);
     for (auto st : ctx->pool_streams) cudaStreamDestroy(st);
+    for (auto ev : ctx->chunk_events) cudaEventDestroy(ev);
     if (ctx->stage) cudaFreeHost(ctx->stage);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -711,6 +713,84 @@ static int render_common(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic*
         P.pf[k] = pfs[k];
         if (device_out) P.o_img[k] = images[k];
         else { void* d; rc = pool_get(ctx, SL_IMG0 + k, n * sizeof(double) + 8, &d); if (rc) return rc; P.o_img[k] = (double*)d; }
+    }
+    // Large host-output renders are pipelined: the range is cut into chunks of whole tile strips, the chunk kernels
+    // alternate between two streams (the next chunk's CTAs take over the SMs as the previous chunk drains, so there is
+    // no idle tail between them) and every chunk's images travel to the host while the following chunks compute.
+    const int64_t strip = P.tile_h ? (int64_t)GB_TILE_C * P.tile_h : 1;
+    const int64_t unit = (P.block % strip == 0) ? P.block : ((strip % P.block == 0) ? strip : 0);
+    if (!device_out && !async && unit > 0 && rg->count >= (1 << 20) && rg->count / unit >= 8 && !getenv("GB200_NO_PIPELINE")) {
+        const int K = 4;
+        const int64_t per = ((rg->count / unit + K - 1) / K) * unit;
+        while (ctx->pool_streams.size() < 2) {
+            cudaStream_t st;
+            CU(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            ctx->pool_streams.push_back(st);
+        }
+        while (ctx->chunk_events.size() < (size_t)K + 2) {
+            cudaEvent_t ev;
+            CU(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            ctx->chunk_events.push_back(ev);
+        }
+        cudaStream_t alt = ctx->pool_streams[0], copy = ctx->pool_streams[1];
+        void* qv = nullptr;
+        rc = pool_get(ctx, SL_BATCH_QUEUE, sizeof(unsigned long long) * 4 * K, &qv); if (rc) return rc;
+        unsigned long long* queues = (unsigned long long*)qv;
+        CU(ctx, cudaMemsetAsync(queues, 0, sizeof(unsigned long long) * 4 * K, stream));
+        CU(ctx, cudaEventRecord(ctx->ev1, stream)); // uploads and queue reset done: the other stream may start
+        CU(ctx, cudaStreamWaitEvent(alt, ctx->ev1, 0));
+        int nchunks = 0;
+        for (int c = 0; c < K; ++c) {
+            const int64_t slot0 = (int64_t)c * per;
+            if (slot0 >= rg->count) break;
+            const int64_t cnt = (rg->count - slot0 < per) ? rg->count - slot0 : per;
+            gb200_range sub = *rg;
+            sub.first = rg->first + (slot0 / P.block) * (P.stride * P.block);
+            sub.count = cnt;
+            GbParams Pc;
+            fill_params(p, ic, &sub, Pc);
+            // everything fill_params does not set comes from the full-range block
+            Pc.r_isco = P.r_isco;
+            for (int k = 0; k < 4; ++k) { Pc.ex[k] = P.ex[k]; Pc.ev[k] = P.ev[k]; }
+            Pc.pl_n = P.pl_n; Pc.pl_r = P.pl_r; Pc.pl_ut = P.pl_ut; Pc.pl_ur = P.pl_ur; Pc.pl_uphi = P.pl_uphi;
+            Pc.npf = npf;
+            for (int k = 0; k < npf; ++k) { Pc.pf[k] = pfs[k]; Pc.o_img[k] = P.o_img[k] + slot0; }
+            Pc.queue = queues + 4 * c;
+            Pc.counters = Pc.queue + 1;
+            cudaStream_t st = (c % 2 == 0) ? stream : alt;
+            int blocks = 0;
+            CU(ctx, gb200_launch_trace(Pc, ctx->sm_count, st, &blocks));
+            ctx->stats.launches += 1;
+            CU(ctx, cudaEventRecord(ctx->chunk_events[(size_t)c], st));
+            ++nchunks;
+        }
+        // the copies are enqueued after all the launches: a device-to-host copy into pageable memory blocks the calling
+        // thread, and must not hold back the launch of the following chunks
+        for (int c = 0; c < nchunks; ++c) {
+            const int64_t slot0 = (int64_t)c * per;
+            const int64_t cnt = (rg->count - slot0 < per) ? rg->count - slot0 : per;
+            CU(ctx, cudaStreamWaitEvent(copy, ctx->chunk_events[(size_t)c], 0));
+            for (int k = 0; k < npf; ++k)
+                CU(ctx, cudaMemcpyAsync(images[k] + slot0, P.o_img[k] + slot0, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, copy));
+        }
+        // join: the context stream waits for the other stream's kernels (kernel time) and for the copies
+        for (int c = 1; c < nchunks; c += 2) CU(ctx, cudaStreamWaitEvent(stream, ctx->chunk_events[(size_t)c], 0));
+        CU(ctx, cudaEventRecord(ctx->ev2, stream));
+        CU(ctx, cudaEventRecord(ctx->chunk_events[(size_t)K], copy));
+        CU(ctx, cudaStreamWaitEvent(stream, ctx->chunk_events[(size_t)K], 0));
+        std::vector<unsigned long long> cq((size_t)4 * K);
+        CU(ctx, cudaMemcpyAsync(cq.data(), queues, sizeof(unsigned long long) * cq.size(), cudaMemcpyDeviceToHost, stream));
+        CU(ctx, cudaEventRecord(ctx->ev3, stream));
+        CU(ctx, cudaStreamSynchronize(stream));
+        float kms = 0, tot = 0;
+        cudaEventElapsedTime(&kms, ctx->ev1, ctx->ev2);
+        cudaEventElapsedTime(&tot, ctx->ev0, ctx->ev3);
+        ctx->stats.kernel_ms = kms; ctx->stats.total_ms = tot; ctx->stats.rays = rg->count;
+        for (int c = 0; c < nchunks; ++c) {
+            ctx->stats.steps_accepted += (int64_t)cq[(size_t)c * 4 + 1]; ctx->stats.steps_rejected += (int64_t)cq[(size_t)c * 4 + 2];
+            ctx->stats.flagged += (int64_t)cq[(size_t)c * 4 + 3];
+        }
+        return GB200_OK;
     }
     rc = run_trace(ctx, P, stream, true); if (rc) return rc;
     if (!device_out)
