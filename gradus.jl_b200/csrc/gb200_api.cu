@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <mutex>
 #include <string>
+#include <functional>
 #include <vector>
 #include "gb200_device.cuh"
 #include "gb200_internal.h"
@@ -366,6 +367,89 @@ static int finish_stats(gb200_ctx* ctx, int64_t rays) {
     return GB200_OK;
 }
 
+// ---------------------------------------------------------------- pipelined host-output launches
+// Large host-output calls are pipelined: the range is cut into chunks of whole tile strips, the chunk kernels alternate
+// between two streams (the next chunk's CTAs take over the SMs as the previous chunk drains, so there is no idle tail
+// between them) and every chunk's results travel to the host while the following chunks compute.
+static int64_t pipeline_unit(const GbParams& P) {
+    const int64_t strip = P.tile_h ? (int64_t)GB_TILE_C * P.tile_h : 1;
+    return (P.block % strip == 0) ? P.block : ((strip % P.block == 0) ? strip : 0);
+}
+static bool pipeline_eligible(const GbParams& P, const gb200_range* rg) {
+    const int64_t unit = pipeline_unit(P);
+    return unit > 0 && rg->count >= (1 << 20) && rg->count / unit >= 8 && !getenv("GB200_NO_PIPELINE");
+}
+// bind(Pc, slot0): point the chunk's outputs at slot0 of the full-range device buffers;
+// copy_back(slot0, cnt, stream): enqueue the device-to-host copies of that chunk.
+static int run_pipelined(gb200_ctx* ctx, const gb200_range* rg, const GbParams& P,
+                         const std::function<void(GbParams&, int64_t)>& bind,
+                         const std::function<cudaError_t(int64_t, int64_t, cudaStream_t)>& copy_back) {
+    const int K = 4;
+    cudaStream_t stream = ctx->cur;
+    const int64_t unit = pipeline_unit(P);
+    const int64_t per = ((rg->count / unit + K - 1) / K) * unit;
+    while (ctx->pool_streams.size() < 2) {
+        cudaStream_t st;
+        CU(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ctx->pool_streams.push_back(st);
+    }
+    while (ctx->chunk_events.size() < (size_t)K + 2) {
+        cudaEvent_t ev;
+        CU(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->chunk_events.push_back(ev);
+    }
+    cudaStream_t alt = ctx->pool_streams[0], copy = ctx->pool_streams[1];
+    void* qv = nullptr;
+    int rc = pool_get(ctx, SL_BATCH_QUEUE, sizeof(unsigned long long) * 4 * K, &qv); if (rc) return rc;
+    unsigned long long* queues = (unsigned long long*)qv;
+    CU(ctx, cudaMemsetAsync(queues, 0, sizeof(unsigned long long) * 4 * K, stream));
+    CU(ctx, cudaEventRecord(ctx->ev1, stream)); // uploads and queue reset done: the other stream may start
+    CU(ctx, cudaStreamWaitEvent(alt, ctx->ev1, 0));
+    int nchunks = 0;
+    for (int c = 0; c < K; ++c) {
+        const int64_t slot0 = (int64_t)c * per;
+        if (slot0 >= rg->count) break;
+        GbParams Pc = P; // same problem, same tables; only the slot range and the output pointers move
+        Pc.first = rg->first + (slot0 / P.block) * (P.stride * P.block);
+        Pc.count = (rg->count - slot0 < per) ? rg->count - slot0 : per;
+        bind(Pc, slot0);
+        Pc.queue = queues + 4 * c;
+        Pc.counters = Pc.queue + 1;
+        cudaStream_t st = (c % 2 == 0) ? stream : alt;
+        int blocks = 0;
+        CU(ctx, gb200_launch_trace(Pc, ctx->sm_count, st, &blocks));
+        ctx->stats.launches += 1;
+        CU(ctx, cudaEventRecord(ctx->chunk_events[(size_t)c], st));
+        ++nchunks;
+    }
+    // the copies are enqueued after all the launches: a device-to-host copy into pageable memory blocks the calling
+    // thread, and must not hold back the launch of the following chunks
+    for (int c = 0; c < nchunks; ++c) {
+        const int64_t slot0 = (int64_t)c * per;
+        const int64_t cnt = (rg->count - slot0 < per) ? rg->count - slot0 : per;
+        CU(ctx, cudaStreamWaitEvent(copy, ctx->chunk_events[(size_t)c], 0));
+        CU(ctx, copy_back(slot0, cnt, copy));
+    }
+    // join: the context stream waits for the other stream's kernels (kernel time) and for the copies
+    for (int c = 1; c < nchunks; c += 2) CU(ctx, cudaStreamWaitEvent(stream, ctx->chunk_events[(size_t)c], 0));
+    CU(ctx, cudaEventRecord(ctx->ev2, stream));
+    CU(ctx, cudaEventRecord(ctx->chunk_events[(size_t)K], copy));
+    CU(ctx, cudaStreamWaitEvent(stream, ctx->chunk_events[(size_t)K], 0));
+    std::vector<unsigned long long> cq((size_t)4 * K);
+    CU(ctx, cudaMemcpyAsync(cq.data(), queues, sizeof(unsigned long long) * cq.size(), cudaMemcpyDeviceToHost, stream));
+    CU(ctx, cudaEventRecord(ctx->ev3, stream));
+    CU(ctx, cudaStreamSynchronize(stream));
+    float kms = 0, tot = 0;
+    cudaEventElapsedTime(&kms, ctx->ev1, ctx->ev2);
+    cudaEventElapsedTime(&tot, ctx->ev0, ctx->ev3);
+    ctx->stats.kernel_ms = kms; ctx->stats.total_ms = tot; ctx->stats.rays = rg->count;
+    for (int c = 0; c < nchunks; ++c) {
+        ctx->stats.steps_accepted += (int64_t)cq[(size_t)c * 4 + 1]; ctx->stats.steps_rejected += (int64_t)cq[(size_t)c * 4 + 2];
+        ctx->stats.flagged += (int64_t)cq[(size_t)c * 4 + 3];
+    }
+    return GB200_OK;
+}
+
 // ---------------------------------------------------------------- C ABI
 extern "C" {
 
@@ -467,7 +551,41 @@ int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, cons
     WANT(out->nreject, SL_NREJ, int32_t, P.o_nreject)
     WANT(out->flags, SL_FLAGS, int32_t, P.o_flags)
 #undef WANT
-    // x_init / v_init are written together with point functions; request at least x0[0] consistently
+    if (pipeline_eligible(P, rg)) {
+        const GbParams Pf = P;
+        return run_pipelined(ctx, rg, P,
+            [&](GbParams& Pc, int64_t s0) {
+                if (Pf.o_status) Pc.o_status = Pf.o_status + s0;
+                if (Pf.o_lambda) Pc.o_lambda = Pf.o_lambda + s0;
+                for (int k = 0; k < 4; ++k) {
+                    if (Pf.o_x[k]) Pc.o_x[k] = Pf.o_x[k] + s0;
+                    if (Pf.o_v[k]) Pc.o_v[k] = Pf.o_v[k] + s0;
+                    if (Pf.o_x0[k]) Pc.o_x0[k] = Pf.o_x0[k] + s0;
+                    if (Pf.o_v0[k]) Pc.o_v0[k] = Pf.o_v0[k] + s0;
+                }
+                if (Pf.o_naccept) Pc.o_naccept = Pf.o_naccept + s0;
+                if (Pf.o_nreject) Pc.o_nreject = Pf.o_nreject + s0;
+                if (Pf.o_flags) Pc.o_flags = Pf.o_flags + s0;
+            },
+            [&](int64_t s0, int64_t cnt, cudaStream_t copy) -> cudaError_t {
+                cudaError_t e = cudaSuccess;
+#define BACKC(ptr, field, type) \
+    if (e == cudaSuccess && ptr) e = cudaMemcpyAsync(ptr + s0, field + s0, (size_t)cnt * sizeof(type), cudaMemcpyDeviceToHost, copy);
+                BACKC(out->status, Pf.o_status, int32_t)
+                BACKC(out->lambda_max, Pf.o_lambda, double)
+                for (int k = 0; k < 4; ++k) {
+                    BACKC(out->x[k], Pf.o_x[k], double)
+                    BACKC(out->v[k], Pf.o_v[k], double)
+                    BACKC(out->x_init[k], Pf.o_x0[k], double)
+                    BACKC(out->v_init[k], Pf.o_v0[k], double)
+                }
+                BACKC(out->naccept, Pf.o_naccept, int32_t)
+                BACKC(out->nreject, Pf.o_nreject, int32_t)
+                BACKC(out->flags, Pf.o_flags, int32_t)
+#undef BACKC
+                return e;
+            });
+    }
     rc = run_trace(ctx, P, ctx->stream, true); if (rc) return rc;
 #define BACK(ptr, field, type) \
     if (ptr && n) CU(ctx, cudaMemcpyAsync(ptr, field, n * sizeof(type), cudaMemcpyDeviceToHost, ctx->stream));
@@ -714,83 +832,17 @@ static int render_common(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic*
         if (device_out) P.o_img[k] = images[k];
         else { void* d; rc = pool_get(ctx, SL_IMG0 + k, n * sizeof(double) + 8, &d); if (rc) return rc; P.o_img[k] = (double*)d; }
     }
-    // Large host-output renders are pipelined: the range is cut into chunks of whole tile strips, the chunk kernels
-    // alternate between two streams (the next chunk's CTAs take over the SMs as the previous chunk drains, so there is
-    // no idle tail between them) and every chunk's images travel to the host while the following chunks compute.
-    const int64_t strip = P.tile_h ? (int64_t)GB_TILE_C * P.tile_h : 1;
-    const int64_t unit = (P.block % strip == 0) ? P.block : ((strip % P.block == 0) ? strip : 0);
-    if (!device_out && !async && unit > 0 && rg->count >= (1 << 20) && rg->count / unit >= 8 && !getenv("GB200_NO_PIPELINE")) {
-        const int K = 4;
-        const int64_t per = ((rg->count / unit + K - 1) / K) * unit;
-        while (ctx->pool_streams.size() < 2) {
-            cudaStream_t st;
-            CU(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-            ctx->pool_streams.push_back(st);
-        }
-        while (ctx->chunk_events.size() < (size_t)K + 2) {
-            cudaEvent_t ev;
-            CU(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            ctx->chunk_events.push_back(ev);
-        }
-        cudaStream_t alt = ctx->pool_streams[0], copy = ctx->pool_streams[1];
-        void* qv = nullptr;
-        rc = pool_get(ctx, SL_BATCH_QUEUE, sizeof(unsigned long long) * 4 * K, &qv); if (rc) return rc;
-        unsigned long long* queues = (unsigned long long*)qv;
-        CU(ctx, cudaMemsetAsync(queues, 0, sizeof(unsigned long long) * 4 * K, stream));
-        CU(ctx, cudaEventRecord(ctx->ev1, stream)); // uploads and queue reset done: the other stream may start
-        CU(ctx, cudaStreamWaitEvent(alt, ctx->ev1, 0));
-        int nchunks = 0;
-        for (int c = 0; c < K; ++c) {
-            const int64_t slot0 = (int64_t)c * per;
-            if (slot0 >= rg->count) break;
-            const int64_t cnt = (rg->count - slot0 < per) ? rg->count - slot0 : per;
-            gb200_range sub = *rg;
-            sub.first = rg->first + (slot0 / P.block) * (P.stride * P.block);
-            sub.count = cnt;
-            GbParams Pc;
-            fill_params(p, ic, &sub, Pc);
-            // everything fill_params does not set comes from the full-range block
-            Pc.r_isco = P.r_isco;
-            for (int k = 0; k < 4; ++k) { Pc.ex[k] = P.ex[k]; Pc.ev[k] = P.ev[k]; }
-            Pc.pl_n = P.pl_n; Pc.pl_r = P.pl_r; Pc.pl_ut = P.pl_ut; Pc.pl_ur = P.pl_ur; Pc.pl_uphi = P.pl_uphi;
-            Pc.npf = npf;
-            for (int k = 0; k < npf; ++k) { Pc.pf[k] = pfs[k]; Pc.o_img[k] = P.o_img[k] + slot0; }
-            Pc.queue = queues + 4 * c;
-            Pc.counters = Pc.queue + 1;
-            cudaStream_t st = (c % 2 == 0) ? stream : alt;
-            int blocks = 0;
-            CU(ctx, gb200_launch_trace(Pc, ctx->sm_count, st, &blocks));
-            ctx->stats.launches += 1;
-            CU(ctx, cudaEventRecord(ctx->chunk_events[(size_t)c], st));
-            ++nchunks;
-        }
-        // the copies are enqueued after all the launches: a device-to-host copy into pageable memory blocks the calling
-        // thread, and must not hold back the launch of the following chunks
-        for (int c = 0; c < nchunks; ++c) {
-            const int64_t slot0 = (int64_t)c * per;
-            const int64_t cnt = (rg->count - slot0 < per) ? rg->count - slot0 : per;
-            CU(ctx, cudaStreamWaitEvent(copy, ctx->chunk_events[(size_t)c], 0));
-            for (int k = 0; k < npf; ++k)
-                CU(ctx, cudaMemcpyAsync(images[k] + slot0, P.o_img[k] + slot0, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, copy));
-        }
-        // join: the context stream waits for the other stream's kernels (kernel time) and for the copies
-        for (int c = 1; c < nchunks; c += 2) CU(ctx, cudaStreamWaitEvent(stream, ctx->chunk_events[(size_t)c], 0));
-        CU(ctx, cudaEventRecord(ctx->ev2, stream));
-        CU(ctx, cudaEventRecord(ctx->chunk_events[(size_t)K], copy));
-        CU(ctx, cudaStreamWaitEvent(stream, ctx->chunk_events[(size_t)K], 0));
-        std::vector<unsigned long long> cq((size_t)4 * K);
-        CU(ctx, cudaMemcpyAsync(cq.data(), queues, sizeof(unsigned long long) * cq.size(), cudaMemcpyDeviceToHost, stream));
-        CU(ctx, cudaEventRecord(ctx->ev3, stream));
-        CU(ctx, cudaStreamSynchronize(stream));
-        float kms = 0, tot = 0;
-        cudaEventElapsedTime(&kms, ctx->ev1, ctx->ev2);
-        cudaEventElapsedTime(&tot, ctx->ev0, ctx->ev3);
-        ctx->stats.kernel_ms = kms; ctx->stats.total_ms = tot; ctx->stats.rays = rg->count;
-        for (int c = 0; c < nchunks; ++c) {
-            ctx->stats.steps_accepted += (int64_t)cq[(size_t)c * 4 + 1]; ctx->stats.steps_rejected += (int64_t)cq[(size_t)c * 4 + 2];
-            ctx->stats.flagged += (int64_t)cq[(size_t)c * 4 + 3];
-        }
-        return GB200_OK;
+    if (!device_out && !async && pipeline_eligible(P, rg)) {
+        const GbParams Pfull = P;
+        return run_pipelined(ctx, rg, P,
+            [&](GbParams& Pc, int64_t slot0) { for (int k = 0; k < npf; ++k) Pc.o_img[k] = Pfull.o_img[k] + slot0; },
+            [&](int64_t slot0, int64_t cnt, cudaStream_t copy) -> cudaError_t {
+                for (int k = 0; k < npf; ++k) {
+                    cudaError_t e = cudaMemcpyAsync(images[k] + slot0, Pfull.o_img[k] + slot0, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, copy);
+                    if (e != cudaSuccess) return e;
+                }
+                return cudaSuccess;
+            });
     }
     rc = run_trace(ctx, P, stream, true); if (rc) return rc;
     if (!device_out)

@@ -532,3 +532,25 @@ def test_gpu_against_committed_golden_fixtures(ensemble):
         assert hit.sum() > 50
         assert _x_rel(got.x[:, hit], gold[name + "_x"][:, hit]).max() < 1e-6
         assert _vec_rel(got.v[:, hit], gold[name + "_v"][:, hit], 1e-12).max() < 2e-6
+
+
+def test_pipelined_host_output_calls_equal_single_launches(ensemble, monkeypatch):
+    """Calls with >= 2^20 rays and host output run as four chunks on two streams with overlapped copies
+    (run_pipelined): endpoints, images and step counters must equal the single-launch path bit for bit, for a plain and
+    for a strided (multi-GPU style) range."""
+    m, x, d, cfg = common.c1(1024, 1152, ensemble=ensemble)
+    pfs = [gb.ConstPointFunctions.redshift(m, x) @ gb.ConstPointFunctions.filter_intersected(),
+           gb.ConstPointFunctions.radius() @ gb.ConstPointFunctions.filter_intersected()]
+    got = solve_tracing_problem(cfg)
+    st_p = ensemble.stats()
+    imgs_p = gb.api.apply_point_functions(cfg, pfs)
+    assert st_p.launches == 4
+    monkeypatch.setenv("GB200_NO_PIPELINE", "1")
+    ref = solve_tracing_problem(cfg)
+    st_1 = ensemble.stats()
+    imgs_1 = gb.api.apply_point_functions(cfg, pfs)
+    assert st_1.launches == 1
+    assert (st_p.steps_accepted, st_p.steps_rejected) == (st_1.steps_accepted, st_1.steps_rejected)
+    for name in ("status", "lambda_max", "x", "v", "x_init", "v_init", "naccept", "nreject"):
+        assert np.array_equal(getattr(got, name), getattr(ref, name), equal_nan=True), name
+    assert np.array_equal(imgs_p, imgs_1, equal_nan=True)
