@@ -422,17 +422,16 @@ static int run_pipelined(gb200_ctx* ctx, const gb200_range* rg, const GbParams& 
         CU(ctx, cudaEventRecord(ctx->chunk_events[(size_t)c], st));
         ++nchunks;
     }
-    // the copies are enqueued after all the launches: a device-to-host copy into pageable memory blocks the calling
-    // thread, and must not hold back the launch of the following chunks
+    // join the kernels on the context stream (end of the kernel span) before any copy is enqueued: a device-to-host
+    // copy into pageable memory blocks the calling thread, so the copies come after all launches and event records
+    for (int c = 1; c < nchunks; c += 2) CU(ctx, cudaStreamWaitEvent(stream, ctx->chunk_events[(size_t)c], 0));
+    CU(ctx, cudaEventRecord(ctx->ev2, stream));
     for (int c = 0; c < nchunks; ++c) {
         const int64_t slot0 = (int64_t)c * per;
         const int64_t cnt = (rg->count - slot0 < per) ? rg->count - slot0 : per;
         CU(ctx, cudaStreamWaitEvent(copy, ctx->chunk_events[(size_t)c], 0));
         CU(ctx, copy_back(slot0, cnt, copy));
     }
-    // join: the context stream waits for the other stream's kernels (kernel time) and for the copies
-    for (int c = 1; c < nchunks; c += 2) CU(ctx, cudaStreamWaitEvent(stream, ctx->chunk_events[(size_t)c], 0));
-    CU(ctx, cudaEventRecord(ctx->ev2, stream));
     CU(ctx, cudaEventRecord(ctx->chunk_events[(size_t)K], copy));
     CU(ctx, cudaStreamWaitEvent(stream, ctx->chunk_events[(size_t)K], 0));
     std::vector<unsigned long long> cq((size_t)4 * K);

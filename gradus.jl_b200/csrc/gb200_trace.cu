@@ -128,7 +128,24 @@ GB_D double ctrl_pow_log(double logx, double x, double y, int mode) {
 
 // The argument of larger magnitude (the caller applies fabs as an operand modifier: selecting |a| or |b| directly makes the
 // compiler materialise both absolute values with two extra FP64 instructions).
+#ifndef GB_OPT_INTCMP
+#define GB_OPT_INTCMP 0 /* comparisons of non-negative doubles as 64-bit integers: measured slower (42.8 vs 42.5 ms), kept as a switch */
+#endif
+#if GB_OPT_INTCMP
+// IEEE doubles of equal sign order like their bit patterns; a nan compares as larger than every finite value, so it is
+// the one selected and keeps propagating (the FP form selects b for a nan a).
+GB_D double gb_absmax(double a, double b) {
+    return (__double_as_longlong(a) & 0x7fffffffffffffffLL) > (__double_as_longlong(b) & 0x7fffffffffffffffLL) ? a : b;
+}
+GB_D double gb_max_pos(double a, double b) { return __double_as_longlong(a) > __double_as_longlong(b) ? a : b; } // a, b >= 0
+GB_D double gb_min_pos(double a, double b) { return __double_as_longlong(a) < __double_as_longlong(b) ? a : b; }
+GB_D bool gb_le_one_pos(double a) { return (unsigned long long)__double_as_longlong(a) <= 0x3ff0000000000000ULL; } // 0 <= a <= 1 (false for nan)
+#else
 GB_D double gb_absmax(double a, double b) { return fabs(a) > fabs(b) ? a : b; }
+GB_D double gb_max_pos(double a, double b) { return gb_max(a, b); }
+GB_D double gb_min_pos(double a, double b) { return gb_min(a, b); }
+GB_D bool gb_le_one_pos(double a) { return a <= 1.0; }
+#endif
 
 // An upper bound of max_i |a_i| from the high words alone (integer pipe): doubles order like their bit patterns, and
 // (hi + 1, 0) exceeds every double whose high word is hi.  inf/nan inputs give a nan bound, which the caller's
@@ -571,14 +588,14 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
             // square root is taken (the Float32 controller mode takes it where it needs EEst itself).  An exactly zero
             // estimate is raised to 1e-150: the controller clamps q to 1/qmax and qold to 1e-4 either way.
 #if GB_OPT_ERRDT
-            const double EEst2 = gb_max((dt * dt) * (ee * 0.125), 1e-300);
+            const double EEst2 = gb_max_pos((dt * dt) * (ee * 0.125), 1e-300);
 #else
             const double EEst2 = gb_max(ee * 0.125, 1e-300);
 #endif
             // PI controller (stepsize_controller!, OrdinaryDiffEq): q = EEst^beta1 / qold^beta2 / gamma, clamped; a rejected
             // attempt uses EEst^beta1 / gamma (step_reject_controller!).  One log and one exp serve both:
             // exp(beta1 log EEst - [accepted] beta2 log qold).
-            const bool accept = EEst2 <= 1.0;
+            const bool accept = gb_le_one_pos(EEst2);
             const bool fast32 = (P.pow_mode == GB200_POW_FAST32);
 #if GB_OPT_LOGEXP
             const double logE = 0.5 * gb_log_pos(EEst2);
@@ -599,14 +616,14 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                 Epow = exp(arg);
 #endif
             }
-            const double q = gb_max(1.0 / qmax, gb_min(1.0 / qmin, Epow * (1.0 / gamma)));
+            const double q = gb_max_pos(1.0 / qmax, gb_min_pos(1.0 / qmin, Epow * (1.0 / gamma)));
             // ---- accept / reject, callbacks and the commit of the step.  Everything up to the commit is computed
             // unconditionally and committed with selects: the loop-carried state then lives in the same registers on
             // every path (the branchy form cost ~200 register moves per attempt where the paths merged).
             const double dtnew = dt * gb_rcp(q);
             const double ttmp = lam + dt;
             const double tnew = (fabs(ttmp - tstop) < 100.0 * (fabs(tstop) * 2.220446049250313e-16)) ? tstop : ttmp;
-            const double dtprop = gb_max(gb_min(dtmax, dtnew), dtmin);
+            const double dtprop = gb_max_pos(gb_min_pos(dtmax, dtnew), dtmin);
             double dtrej = dt;
             if (!accept) dtrej = gb_max(dt / gb_min(1.0 / qmin, Epow / gamma), dtmin);
             // ---- callbacks: continuous (disc) first, then discrete (user, chart)
