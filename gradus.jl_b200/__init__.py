@@ -36,7 +36,12 @@ from .api import (  # noqa: F401
     TabulatedEmissivity,
     ThinDisc,
     TracingConfiguration,
+    EndpointCache,
+    HostPointFunction,
+    apply,
     apply_point_functions,
+    apply_point_functions_batch,
+    prerendergeodesics,
     chart_for_metric,
     domain_upper_hemisphere,
     impact_axes,

@@ -808,6 +808,77 @@ def rendergeodesics(m, position, *args, pf=None, image_width=375, image_height=2
     return (alpha, beta, imgs[0]) if not isinstance(pf, (list, tuple)) else (alpha, beta, imgs)
 
 
+# --------------------------------------------------------------------------- endpoint caches
+@dataclass
+class EndpointCache:
+    """`EndpointCache` (src/rendering/cache.jl): the `GeodesicPoint`s of an image, kept so that any number of point
+    functions can be applied afterwards without tracing again."""
+
+    metric: Any
+    max_time: float
+    height: int
+    width: int
+    points: GeodesicPoints
+
+
+class HostPointFunction:
+    """`PointFunction(f)` / `FilterPointFunction(f, default)` with user callables (src/point-functions.jl:81-125),
+    evaluated on the host over a cache: `f(m, gps, max_time)` receives the whole `GeodesicPoints` SoA and returns one
+    value (or one boolean, for a filter) per point.  `pf @ filt` is `pf ∘ filt`."""
+
+    def __init__(self, f, default=None):
+        self.f, self.default, self.inner = f, default, None
+
+    def __matmul__(self, other):
+        out = HostPointFunction(self.f, self.default)
+        out.inner = other
+        return out
+
+    def __call__(self, m, gps, max_time):
+        if self.default is not None:  # a filter on its own: pass mask
+            return np.asarray(self.f(m, gps, max_time), bool)
+        val = np.asarray(self.f(m, gps, max_time), np.float64)
+        if self.inner is not None:
+            keep = np.asarray(self.inner.f(m, gps, max_time), bool)
+            val = np.where(keep, val, self.inner.default)
+        return val
+
+
+_HOST_FIELDS = {"affine_time": lambda m, g, t: g.lambda_max, "coordinate_time": lambda m, g, t: g.x[0],
+                "radius": lambda m, g, t: g.x[1] * np.abs(np.sin(g.x[2])), "status": lambda m, g, t: g.status.astype(np.float64)}
+_HOST_FILTERS = {"early_term": lambda m, g, t: g.lambda_max < t, "intersected": lambda m, g, t: g.status == StatusCodes.IntersectedWithGeometry}
+
+
+def prerendergeodesics(m, position, *args, image_width=375, image_height=250, ensemble=None, **kwargs):
+    """`prerendergeodesics(m, x, [d], λ_max; image_width, image_height, αlims, βlims, ...)` (src/rendering/rendering.jl:56-87).
+    Returns (α, β, cache)."""
+    alpha_lims = _pop_alias(kwargs, ("αlims", "alpha_lims"), (-60, 60))
+    beta_lims = _pop_alias(kwargs, ("βlims", "beta_lims"), (-40, 40))
+    velocity = RenderGrid(int(image_width), int(image_height), tuple(alpha_lims), tuple(beta_lims))
+    config = tracing_configuration(m, position, velocity, *args, ensemble=ensemble, trajectories=image_width * image_height, **kwargs)
+    gps = solve_tracing_problem(config)
+    alpha, beta = impact_axes(image_width, image_height, alpha_lims, beta_lims)
+    return alpha, beta, EndpointCache(m, config.lambda_domain[1], int(image_height), int(image_width), gps)
+
+
+def apply(pf, cache: EndpointCache):
+    """`apply(pf, cache)` (src/rendering/cache.jl): the (H, W) image of a point function over cached endpoints.  Accepts
+    `HostPointFunction`s (user callables) and the built-in endpoint fields of `ConstPointFunctions`; the redshift needs the
+    disc velocity field and is evaluated by the fused device path (`rendergeodesics(..., pf=redshift ∘ filter)`)."""
+    gps = cache.points
+    if isinstance(pf, HostPointFunction):
+        vals = pf(cache.metric, gps, cache.max_time)
+    elif isinstance(pf, PointFunction):
+        if pf.name not in _HOST_FIELDS:
+            raise ValueError(f"point function {pf.name!r} is evaluated on the device: use rendergeodesics(..., pf=...)")
+        vals = np.asarray(_HOST_FIELDS[pf.name](cache.metric, gps, cache.max_time), np.float64)
+        if pf.filter is not None:
+            vals = np.where(_HOST_FILTERS[pf.filter](cache.metric, gps, cache.max_time), vals, np.nan)
+    else:
+        raise TypeError("apply expects a PointFunction or a HostPointFunction")
+    return np.asarray(vals, np.float64).reshape(cache.width, cache.height).T  # column-major (H, W), rendering.jl:50
+
+
 # --------------------------------------------------------------------------- line profiles
 @dataclass(frozen=True)
 class PowerLawEmissivity:

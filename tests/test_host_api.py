@@ -149,3 +149,25 @@ def test_point_function_composition():
         (cpf.redshift() @ cpf.filter_early_term()).kind()
     a, b = gb.impact_axes(5, 3, (-60, 60), (-40, 40))
     assert a.tolist() == [-60, -30, 0, 30, 60] and b.tolist() == [-40, 0, 40]
+
+
+def test_apply_over_an_endpoint_cache_reproduces_the_prerender_literal():
+    """test/smoke-tests/prerendergeodesics.jl:3-21,33-43: `apply(pf, cache)` with a user point function ∘ filter over the
+    cached endpoints of a 20 x 20 render; the cache is filled by the oracle here (the device fills it in the GPU test)."""
+    import math
+
+    from oracle import oracle
+
+    import common
+
+    m = gb.KerrMetric(1.0, 0.0)
+    cfg = common.render_config(m, [0.0, 100.0, math.radians(85), 0.0], None, 200.0, 20, 20, (-9.5, 9.5), (-9.5, 9.5))
+    p, ic = cfg.to_c()
+    cache = gb.EndpointCache(m, 200.0, 20, 20, gb.api.GeodesicPoints(oracle.trace(p, ic), 0.0))
+    pf = gb.HostPointFunction(lambda m_, gp, lam: gp.lambda_max) @ gb.HostPointFunction(lambda m_, gp, lam: gp.lambda_max < lam, np.nan)
+    img = gb.apply(pf, cache)
+    assert img.shape == (20, 20)
+    assert np.nansum(img) == pytest.approx(9009.452876609641, rel=1e-6)
+    assert np.array_equal(img, gb.apply(gb.ConstPointFunctions.shadow(), cache), equal_nan=True)
+    with pytest.raises(ValueError):
+        gb.apply(gb.ConstPointFunctions.redshift(m, None) @ gb.ConstPointFunctions.filter_intersected(), cache)

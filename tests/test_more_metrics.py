@@ -162,3 +162,16 @@ def test_device_reproduces_the_charged_particle_literals(q, literal):
     esc = ok & (ref.status == cabi.STATUS_NO_STATUS)  # reached lambda_max: a well-defined end state
     assert esc.sum() > 1000
     assert np.max(np.abs(got.x[:, esc] - ref.x[:, esc]) / np.maximum(np.abs(ref.x[:, esc]), 1.0)) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m, shadow, thin, ss", SMOKE + [(gb.KerrMetric(1.0, 0.0), 9009.452876609641, None, None)], ids=IDS + ["kerr"])
+def test_prerendergeodesics_cache_on_the_device(m, shadow, thin, ss):
+    """test/smoke-tests/prerendergeodesics.jl: endpoints cached once, point functions applied afterwards."""
+    x = [0.0, 100.0, math.radians(85), 0.0]
+    _, _, cache = gb.prerendergeodesics(m, x, 200.0, image_width=20, image_height=20, alpha_lims=(-9.5, 9.5), beta_lims=(-9.5, 9.5))
+    pf = gb.HostPointFunction(lambda m_, gp, lam: gp.lambda_max) @ gb.HostPointFunction(lambda m_, gp, lam: gp.lambda_max < lam, np.nan)
+    img = gb.apply(pf, cache)
+    assert np.nansum(img) == pytest.approx(shadow, rel=1e-6)
+    _, _, fused = gb.rendergeodesics(m, x, 200.0, image_width=20, image_height=20, alpha_lims=(-9.5, 9.5), beta_lims=(-9.5, 9.5))
+    assert np.array_equal(img, fused, equal_nan=True)  # the fused device point function writes the same numbers
