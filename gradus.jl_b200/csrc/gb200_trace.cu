@@ -26,13 +26,13 @@
 #include "gb200_internal.h"
 
 #ifndef GB_BLOCK
-#define GB_BLOCK 64 /* two warps per CTA: the per-CTA barrier waits on one other warp only */
+#define GB_BLOCK 32 /* one warp per CTA: the service decision needs no cross-warp barrier (v21 sweep, profiles/r01_tuning_log.md) */
 #endif
 #ifndef GB_MIN_BLOCKS
-#define GB_MIN_BLOCKS 6 /* 12 warps per SM at 168 registers per thread */
+#define GB_MIN_BLOCKS 12 /* 12 warps per SM at 168 registers per thread */
 #endif
 #ifndef GB_REFILL_THRESH
-#define GB_REFILL_THRESH 8 /* idle lanes per warp that trigger a service pass (per CTA: x warps per CTA) */
+#define GB_REFILL_THRESH 16 /* idle lanes per warp that trigger a service pass (per CTA: x warps per CTA) */
 #endif
 #ifndef GB_BLOCK_SYNC
 #define GB_BLOCK_SYNC 1 /* CTA-synchronous stepping: one barrier per step attempt keeps the warps of a CTA in lockstep */
