@@ -171,3 +171,21 @@ def test_apply_over_an_endpoint_cache_reproduces_the_prerender_literal():
     assert np.array_equal(img, gb.apply(gb.ConstPointFunctions.shadow(), cache), equal_nan=True)
     with pytest.raises(ValueError):
         gb.apply(gb.ConstPointFunctions.redshift(m, None) @ gb.ConstPointFunctions.filter_intersected(), cache)
+
+
+def test_reference_arm_prints_exactly_one_json_line():
+    """bench.py --impl reference: one JSON line on stdout (everything else goes to stderr), with the contract's keys."""
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-stride", "1024"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.strip().splitlines()
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"):
+        assert key in j, key
+    assert j["impl"] == "reference" and j["unit"] == "rays/s" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port"
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in j["config"]
