@@ -38,7 +38,7 @@
 #define GB_BLOCK_SYNC 1 /* CTA-synchronous stepping: one barrier per step attempt keeps the warps of a CTA in lockstep */
 #endif
 #ifndef GB_SYNC_EVERY
-#define GB_SYNC_EVERY 8 /* barrier (and service decision) every n-th attempt */
+#define GB_SYNC_EVERY 16 /* service decision (a single-warp barrier count) every n-th attempt */
 #endif
 
 #ifndef GB_OPT_LOGEXP
