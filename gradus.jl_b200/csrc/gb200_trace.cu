@@ -1,16 +1,16 @@
 // gb200_trace.cu -- the hot path: persistent-thread FP64 adaptive Tsit5 ray tracer for sm_100a.
 //
-// One ray per thread, whole integrator state in registers (k1..k7 accelerations, the stage
-// velocities of r and theta for the dense output, previous and proposed state).  The step
-// is straight-line code (taken branches cost instruction-fetch bubbles that two warps per
-// scheduler cannot hide): reciprocals and sincos are branch-free, the tableau sits in the
-// constant bank, and the 6 interior event samples are skipped when a bound on the dense
-// output proves the disc condition cannot change sign.  Warps stay
-// full through a work queue: a global ticket counter hands out ray slots, and a warp
-// refills its lanes (one warp-aggregated atomicAdd) once GB_REFILL_THRESH of them have
-// terminated.  Terminated lanes keep their last step in registers and are finalised
-// together (event root find on the dense output, discrete callbacks, point function,
-// endpoint store), so the divergent epilogue is paid once per batch, not once per ray.
+// One ray per thread, one warp per CTA.  Registers hold the previous and the proposed state, the FSAL slope and k7,
+// running sums and the controller; the stage values k2..k6 live in shared memory (GbK).  A step attempt is
+// straight-line code committed with selects (no taken branch, the loop-carried state stays in the same registers on
+// every path): reciprocals, sincos and the controller's log / exp are branch-free with their coefficients in the
+// constant bank, and the 6 interior event samples are skipped when a bound on the dense output proves that the disc
+// condition cannot change sign.  Warps stay full through a work queue: a global ticket counter hands out ray slots,
+// and a warp refills its lanes (one warp-aggregated atomicAdd) once GB_REFILL_THRESH of them have terminated.
+// Terminated lanes keep their last step and are finalised together (event root find on the dense output, discrete
+// callbacks, point function, endpoint store), so the divergent epilogue is paid once per batch, not once per ray.
+// The GB_OPT_* switches document the tuning steps of profiles/r01_tuning_log.md: each can be turned off to reproduce
+// the measurement behind it.
 //
 // What it replaces in the reference (all per ray, on CPU threads):
 //   prob_func -> velfunc(i) -> constrain_all         src/tracing/geodesic-problem.jl:121-154
