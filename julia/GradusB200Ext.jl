@@ -55,7 +55,9 @@ _metric(m::KerrMetric) = (Int32(0), _mp8(m.M, m.a))
 _metric(m::JohannsenPsaltisMetric) = (Int32(1), _mp8(m.M, m.a, m.ϵ3))
 _metric(m::JohannsenMetric) = (Int32(2), _mp8(m.M, m.a, m.α13, m.α22, m.α52, m.ϵ3))
 _metric(m::BumblebeeMetric) = (Int32(3), _mp8(m.M, m.a, m.l))
-_metric(m::KerrNewmanMetric) = (Int32(4), _mp8(m.M, m.a, m.Q))   # neutral particles only: trace.q must be 0
+# slot 4 (metric_params[3]) carries the charge of the test particle, q for photons and q/μ otherwise
+# (geodesic_ode_problem(::KerrNewmanMetric), src/metrics/kerr-newman-ad.jl:74-78); the caller passes trace.q, trace.μ
+_metric(m::KerrNewmanMetric; q = 0.0, μ = 0.0) = (Int32(4), _mp8(m.M, m.a, m.Q, isapprox(μ, 0.0) ? q : q / μ))
 _metric(m) = throw(ArgumentError("EnsembleB200 has no closed-form right-hand side for $(typeof(m)); there is no CPU fallback"))
 _geometry(::Nothing) = (Int32(0), (0.0, 0.0, 0.0, 0.0))
 _geometry(d::ThinDisc) = (Int32(1), (d.inner_radius, d.outer_radius, 0.0, 0.0))
