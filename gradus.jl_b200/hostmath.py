@@ -97,13 +97,44 @@ def dot(g, u, v):
             + g[4] * (u[0] * v[3] + u[3] * v[0]))
 
 
-def circular_fourvelocity(m, r, contra_rotating=False):
-    """CircularOrbits.fourvelocity(m, r) in the equatorial plane: (u^t, 0, 0, u^φ) (circular-orbits.jl:10-130)."""
+def _charged_omega(m, r, dg, q, mu, contra_rotating):
+    """CircularOrbits.Ω(::KerrNewmanMetric; q) (kerr-newman-ad.jl:113-146): the angular velocity of a circular orbit of a
+    charged particle, root of  ½ ∂_r(g_tt + 2ω g_tφ + ω² g_φφ) − q (∂_r A_φ ω + ∂_r A_t) / u^t  (the reference writes the
+    force through F^r_κ g_rr; g^rr g_rr = 1), Newton from Ω = r / 100 like `Roots.find_zero((f, f'), Ω_init)`."""
+    g = metric_components(m, r, np.pi / 2)
+    Sig = r * r  # equatorial plane
+    At_r = m.Q * (Sig - 2 * r * r) / Sig**2  # ∂_r (r Q / Σ) at θ = π/2
+    Ap_r = -m.a * At_r                        # A_φ = −a sin²θ A_t
+
+    def f(w):
+        delta = w * w * dg[3] + 2 * w * dg[4] + dg[0]
+        arg = -(w * w * g[3] + 2 * w * g[4] + g[0]) / mu**2
+        inv_ut = np.sign(arg) * np.sqrt(abs(arg))
+        return 0.5 * delta - (Ap_r * w + At_r) * q * inv_ut
+
+    w = -r / 100 if contra_rotating else r / 100
+    for _ in range(100):
+        h = 1e-7 * max(abs(w), 1e-3)
+        step = f(w) / ((f(w + h) - f(w - h)) / (2 * h))
+        w -= step
+        if abs(step) <= 1e-15 * max(abs(w), 1e-300):
+            break
+    return w
+
+
+def circular_fourvelocity(m, r, contra_rotating=False, q=0.0, mu=1.0):
+    """CircularOrbits.fourvelocity(m, r) in the equatorial plane: (u^t, 0, 0, u^φ) (circular-orbits.jl:10-130); `q`, `mu`:
+    charged particles in the Kerr–Newman field (kerr-newman-ad.jl:104-146)."""
     r = np.asarray(r, np.float64)
     th = np.pi / 2
     dg = metric_dr(m, r, th)
-    disc = np.sqrt(dg[4] ** 2 - dg[0] * dg[3])
-    omega = -(dg[4] + disc) / dg[3] if contra_rotating else -(dg[4] - disc) / dg[3]
+    if q != 0.0:
+        if not hasattr(m, "Q") or r.ndim:
+            raise ValueError("charged circular orbits: scalar radius in a KerrNewmanMetric")
+        omega = _charged_omega(m, float(r), dg, q, mu, contra_rotating)
+    else:
+        disc = np.sqrt(dg[4] ** 2 - dg[0] * dg[3])
+        omega = -(dg[4] + disc) / dg[3] if contra_rotating else -(dg[4] - disc) / dg[3]
     gi = inverse_metric_components(metric_components(m, r, th))
     A = -(omega * gi[0] - gi[4])
     B = omega * gi[4] - gi[3]

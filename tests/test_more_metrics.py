@@ -175,3 +175,14 @@ def test_prerendergeodesics_cache_on_the_device(m, shadow, thin, ss):
     assert np.nansum(img) == pytest.approx(shadow, rel=1e-6)
     _, _, fused = gb.rendergeodesics(m, x, 200.0, image_width=20, image_height=20, alpha_lims=(-9.5, 9.5), beta_lims=(-9.5, 9.5))
     assert np.array_equal(img, fused, equal_nan=True)  # the fused device point function writes the same numbers
+
+
+def test_charged_circular_orbits_reproduce_the_reference_literals():
+    """test/unit/metrics.kerr-newman.jl:38-41: CircularOrbits.fourvelocity(m, 20.0; q = +-1), rtol 1e-5 there."""
+    m = gb.KerrNewmanMetric(M=1.0, a=0.6, Q=0.6)
+    assert np.allclose(hostmath.circular_fourvelocity(m, 20.0, q=1.0), [1.065341126764724, 0.0, 0.0, 0.007652504287280518], rtol=1e-8, atol=0)
+    assert np.allclose(hostmath.circular_fourvelocity(m, 20.0, q=-1.0), [1.099562453625687, 0.0, 0.0, 0.015091823134051219], rtol=1e-8, atol=0)
+    # q = 0 falls back to the analytic angular velocity
+    v0 = hostmath.circular_fourvelocity(m, 20.0)
+    g = hostmath.metric_components(m, 20.0, math.pi / 2)
+    assert hostmath.dot(g, v0, v0) == pytest.approx(-1.0, abs=1e-12)
