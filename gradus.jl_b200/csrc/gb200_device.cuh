@@ -914,8 +914,12 @@ static double table_lerp(const double* xs, const double* ys, int n, double x) { 
 template <int METRIC>
 GB_HD inline double redshift_endpoint(const GbParams& P, const double x[4], const double v[4], double E_obs) {
     const double sth = sin(x[2]);
-    const double rho = x[1] * fabs(sth);
+    double rho = x[1] * fabs(sth);
     double u0, u1 = 0.0, u3;
+    // A disc whose inner edge is the ISCO itself is hit at the edge to rounding (the event is the discontinuity of
+    // distance_to_disc there): without a plunging table such a hit takes the circular orbit at the ISCO, where the
+    // plunging flow starts, instead of having no velocity field at all.
+    if (METRIC != GB200_METRIC_KERR && P.pl_n < 2 && rho < P.r_isco && rho >= P.r_isco * (1.0 - 1e-9)) rho = P.r_isco;
     if (rho < P.r_isco) {
         if (METRIC == GB200_METRIC_KERR) { // Cunningham (1975) plunging flow
             const double M = P.M, a = P.a, rms = P.r_isco, r = rho;

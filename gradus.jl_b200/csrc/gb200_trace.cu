@@ -872,11 +872,16 @@ cudaError_t gb200_launch_path(const GbParams& P, const double* d_u0, int cap, do
 // fixed order, so the result does not depend on atomic arrival order across blocks.
 __global__ void __launch_bounds__(256) gb200_hist_kernel(const double* __restrict__ g, const double* __restrict__ f, int64_t n,
                                                          const double* __restrict__ bins, int nbins, int right_closed,
-                                                         double* __restrict__ partial) {
+                                                         double* __restrict__ partial, int hist_rows) {
     extern __shared__ double sh[];
     double* sbins = sh;
-    double* shist = sh + nbins;
-    for (int b = threadIdx.x; b < nbins; b += blockDim.x) { sbins[b] = bins[b]; shist[b] = 0.0; }
+    // one histogram row per warp when they fit (rows = warps per block), else one row for the block: with a row of
+    // its own a warp's additions happen in program order, so the block's result does not depend on which warp's
+    // atomic arrives first and the whole histogram is bitwise reproducible
+    const int rows = hist_rows;
+    double* shist = sh + nbins + (rows > 1 ? (int)(threadIdx.x >> 5) * nbins : 0);
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) sbins[b] = bins[b];
+    for (int b = threadIdx.x; b < nbins * rows; b += blockDim.x) sh[nbins + b] = 0.0;
     __syncthreads();
     const unsigned lane = threadIdx.x & 31u;
     const int64_t per_block = (n + gridDim.x - 1) / gridDim.x;
@@ -916,7 +921,11 @@ __global__ void __launch_bounds__(256) gb200_hist_kernel(const double* __restric
         }
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < nbins; b += blockDim.x) partial[(size_t)blockIdx.x * nbins + b] = shist[b];
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
+        double s = 0.0;
+        for (int w = 0; w < rows; ++w) s += sh[nbins + w * nbins + b]; // fixed warp order
+        partial[(size_t)blockIdx.x * nbins + b] = s;
+    }
 }
 
 __global__ void gb200_hist_reduce_kernel(const double* __restrict__ partial, int nblocks, int nbins, double* __restrict__ out, int accumulate) {
@@ -929,12 +938,13 @@ __global__ void gb200_hist_reduce_kernel(const double* __restrict__ partial, int
 
 cudaError_t gb200_launch_hist(const double* g, const double* f, int64_t n, const double* bins, int nbins, int right_closed,
                               double* partial, int nblocks, double* out, cudaStream_t stream) {
-    const size_t smem = (size_t)nbins * 2 * sizeof(double);
+    const int rows = ((size_t)nbins * 9 * sizeof(double) <= 96 * 1024) ? 8 : 1; // 256 threads = 8 warps
+    const size_t smem = (size_t)nbins * (1 + rows) * sizeof(double);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(gb200_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    gb200_hist_kernel<<<nblocks, 256, smem, stream>>>(g, f, n, bins, nbins, right_closed, partial);
+    gb200_hist_kernel<<<nblocks, 256, smem, stream>>>(g, f, n, bins, nbins, right_closed, partial, rows);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     gb200_hist_reduce_kernel<<<(nbins + 127) / 128, 128, 0, stream>>>(partial, nblocks, nbins, out, 0);

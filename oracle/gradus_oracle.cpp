@@ -876,6 +876,9 @@ static double isco_of(const Metric& m) { return m.kind == GB200_METRIC_KERR ? ke
 template <class T>
 T redshift_of(const Metric& m, double r_isco, const gb200_plunging_table* pl, const RayResult<T>& gp) {
     T rho = gp.x[1] * rabs(rsin(gp.x[2])); // _equatorial_project
+    // a hit at the inner edge of a disc that starts at the ISCO lands there to rounding: without a plunging table it
+    // takes the circular orbit at the ISCO (the library does the same)
+    if (m.kind != GB200_METRIC_KERR && (!pl || pl->n < 2) && rho < T(r_isco) && rho >= T(r_isco * (1.0 - 1e-9))) rho = T(r_isco);
     T vd[4];
     if (rho < T(r_isco)) {
         if (m.kind == GB200_METRIC_KERR) {

@@ -554,3 +554,74 @@ def test_pipelined_host_output_calls_equal_single_launches(ensemble, monkeypatch
     for name in ("status", "lambda_max", "x", "v", "x_init", "v_init", "naccept", "nreject"):
         assert np.array_equal(getattr(got, name), getattr(ref, name), equal_nan=True), name
     assert np.array_equal(imgs_p, imgs_1, equal_nan=True)
+
+
+def test_full_size_lineprofile_properties(ensemble):
+    """BASELINE configs[2] at full size (PolarPlane 4096 x 4096 = 1.7e7 rays, 180 bins): determinism, the raw histogram
+    of 8 strip-interleaved shards sums to the single-launch histogram (what the NCCL all-reduce relies on), unit area,
+    and a strided oracle sample of the (g, f) pairs behind the histogram."""
+    from gradus_b200 import distributed as gd
+
+    m, x, d, plane, cfg = common.c3(4096, 4096, ensemble=ensemble)
+    p, ic = cfg.to_c()
+    lib = cabi.load()
+    ctx = ensemble.ctx(ensemble.devices[0])
+    bins = np.linspace(0.1, 1.5, 180)
+    emis = cabi.Emissivity(cabi.EMISSIVITY_POWERLAW, 0, 3.0, None, None)
+    opts = cabi.LineProfileOpts(gb.isco(m), 50.0, 0, 0)  # raw partial sums
+
+    def hist(rng):
+        flux = np.zeros(len(bins))
+        cabi.check(lib.gb200_lineprofile(ctx, C.byref(p), C.byref(ic), C.byref(rng), C.byref(emis), None, cabi.dptr(bins), len(bins),
+                                         C.byref(opts), cabi.dptr(flux)), ctx)
+        return flux
+
+    full = hist(cabi.Range(0, ic.n, 1))
+    assert np.array_equal(full, hist(cabi.Range(0, ic.n, 1)))  # fixed-order partial sums: bitwise reproducible
+    parts = sum(hist(gd.strip_interleaved_range(ic, r, 8)) for r in range(8))
+    assert np.max(np.abs(parts - full)) <= 1e-12 * full.max()
+    flux = full / full.sum()
+    assert flux.sum() == pytest.approx(1.0) and flux[0] < 1e-3 and flux[-1] == 0.0  # g < 0.1 is clamped into the first bin (Buckets.Simple)
+    g_peak = bins[np.argmax(flux)]
+    assert 1.0 < g_peak < 1.15  # blue horn of an a = 0.998 disc seen at 40 degrees
+    # strided oracle sample: the same 4096 rays through the oracle's line-profile path, compared as a histogram
+    rng = cabi.Range(29, 4096, 4093)
+    want = oracle.lineprofile(p, ic, emis, bins, opts, rng=rng)
+    got = hist(rng)
+    assert np.abs(got - want).sum() <= 1e-4 * np.abs(want).sum()
+
+
+def test_full_size_johannsen_psaltis_properties(ensemble):
+    """BASELINE configs[4] at full size (JP a = 0.6, eps3 = 2, 2048 x 2048): determinism, shard invariance, physical ranges
+    and a strided oracle sample (the generated closed-form Jacobian against the oracle's dual numbers)."""
+    m, x, d, cfg = common.c5(2048, 2048, ensemble=ensemble)
+    p, ic = cfg.to_c()
+    lib = cabi.load()
+    ctx = ensemble.ctx(ensemble.devices[0])
+    pfs = np.array([cabi.PF_REDSHIFT, cabi.PF_DISC_RADIUS, cabi.PF_STATUS], np.int32)
+
+    def render(rng):
+        imgs = np.zeros((3, rng.count))
+        ptrs = (cabi._dp * 3)(*[cabi.dptr(imgs[k]) for k in range(3)])
+        cabi.check(lib.gb200_render(ctx, C.byref(p), C.byref(ic), C.byref(rng), cabi.iptr(pfs), 3, None, ptrs), ctx)
+        return imgs
+
+    full = render(cabi.Range(0, ic.n, 1))
+    assert np.array_equal(full, render(cabi.Range(0, ic.n, 1)), equal_nan=True)
+    shard = render(cabi.Range(5, ic.n // 8, 8))
+    assert np.array_equal(shard, full[:, 5::8][:, : ic.n // 8], equal_nan=True)
+    g, rho, status = full
+    hit = status == cabi.STATUS_INTERSECTED
+    assert np.array_equal(np.isnan(g), ~hit) and 0.3 < hit.mean() < 0.5
+    assert np.nanmin(rho) >= gb.isco(m) * (1 - 1e-12) and np.nanmax(rho) <= 50.0 * (1 + 1e-12)
+    assert 0.1 < np.nanmin(g) < 0.5 and 1.1 < np.nanmax(g) < 1.5
+    rng = cabi.Range(23, 4096, 1021)
+    want = oracle.render(p, ic, [cabi.PF_REDSHIFT, cabi.PF_DISC_RADIUS, cabi.PF_STATUS], rng=rng)
+    ratio = oracle.band_ratio(p, ic, rng=rng)
+    ok = ~((ratio > 0) & (ratio < 1.3))
+    got = full[:, 23::1021][:, :4096]
+    agree = got[2] == want[2]
+    assert agree[ok].mean() > 0.999
+    both = ok & agree & ~np.isnan(want[0])
+    assert both.sum() > 1000
+    assert np.abs(got[0][both] - want[0][both]).max() < 1e-6 and np.abs(got[1][both] / want[1][both] - 1).max() < 1e-6
