@@ -80,6 +80,21 @@ class LineProfileOpts(C.Structure):
     _fields_ = [("min_re", C.c_double), ("max_re", C.c_double), ("normalise", C.c_int32), ("bin_right_closed", C.c_int32)]
 
 
+class DualIC(C.Structure):
+    """gb200_dual_ic: impact parameters with seeded partials (forward-mode traces)."""
+
+    _fields_ = [("n", C.c_int64), ("npartials", C.c_int32), ("reserved", C.c_int32), ("alpha", _dp), ("beta", _dp),
+                ("dalpha", _dp), ("dbeta", _dp), ("height", _dp)]
+
+
+class DualOut(C.Structure):
+    _fields_ = [("status", _ip), ("lambda_max", _dp), ("x", _dp * 4), ("v", _dp * 4), ("g", _dp), ("dg", _dp),
+                ("rho", _dp), ("drho", _dp), ("naccept", _ip), ("nreject", _ip), ("flags", _ip)]
+
+
+DUAL_NORM_WITH_PARTIALS, DUAL_NORM_VALUES_ONLY = 0, 1
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("kernel_ms", C.c_double), ("total_ms", C.c_double), ("rays", C.c_int64), ("steps_accepted", C.c_int64),
@@ -92,6 +107,7 @@ EXPORTED_SYMBOLS = (
     "gb200_version", "gb200_init", "gb200_destroy", "gb200_last_error", "gb200_get_stats", "gb200_validate",
     "gb200_isco", "gb200_radiative_efficiency", "gb200_trace", "gb200_trace_batch", "gb200_trace_path", "gb200_build_plunging_table", "gb200_render", "gb200_lineprofile",
     "gb200_render_batch", "gb200_render_device", "gb200_lineprofile_device", "gb200_fp64_peak", "gb200_fp64_issue_probe", "gb200_debug_rhs", "gb200_debug_math",
+    "gb200_trace_dual", "gb200_trace_dual_batch",
 )
 
 
@@ -108,6 +124,36 @@ def iptr(a):
         return C.cast(None, _ip)
     assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(_ip)
+
+
+class DualArrays:
+    """Caller-owned inputs and outputs of one forward-mode trace call plus the ctypes views handed to the library."""
+
+    def __init__(self, alpha, beta, dalpha, dbeta, height=None):
+        self.alpha = np.ascontiguousarray(alpha, np.float64)
+        self.beta = np.ascontiguousarray(beta, np.float64)
+        n = self.alpha.size
+        self.dalpha = np.ascontiguousarray(np.atleast_2d(np.asarray(dalpha, np.float64)))
+        self.dbeta = np.ascontiguousarray(np.atleast_2d(np.asarray(dbeta, np.float64)))
+        nd = self.dalpha.shape[0]
+        if self.beta.shape != (n,) or self.dalpha.shape != (nd, n) or self.dbeta.shape != (nd, n) or nd not in (1, 2):
+            raise ValueError("alpha, beta: (n,); dalpha, dbeta: (npartials, n) with npartials 1 or 2")
+        self.height = None if height is None else np.ascontiguousarray(np.broadcast_to(np.asarray(height, np.float64), (n,)))
+        self.n, self.npartials = n, nd
+        self.ic = DualIC(n, nd, 0, dptr(self.alpha), dptr(self.beta), dptr(self.dalpha), dptr(self.dbeta), dptr(self.height))
+        self.status = np.full(n, -1, np.int32)
+        self.lambda_max = np.zeros(n)
+        self.x, self.v = np.zeros((4, n)), np.zeros((4, n))
+        self.g, self.rho = np.zeros(n), np.zeros(n)
+        self.dg, self.drho = np.zeros((nd, n)), np.zeros((nd, n))
+        self.naccept, self.nreject, self.flags = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        o = DualOut()
+        o.status, o.lambda_max = iptr(self.status), dptr(self.lambda_max)
+        for k in range(4):
+            o.x[k], o.v[k] = dptr(self.x[k]), dptr(self.v[k])
+        o.g, o.dg, o.rho, o.drho = dptr(self.g), dptr(self.dg), dptr(self.rho), dptr(self.drho)
+        o.naccept, o.nreject, o.flags = iptr(self.naccept), iptr(self.nreject), iptr(self.flags)
+        self.out = o
 
 
 class EndpointArrays:
@@ -186,6 +232,9 @@ def load():
     lib.gb200_fp64_issue_probe.argtypes = [vp, C.c_int32, _dp]
     lib.gb200_debug_rhs.argtypes = [vp, C.c_int32, _dp, C.c_int64, _dp, _dp]
     lib.gb200_debug_math.argtypes = [vp, C.c_int64, _dp, _dp]
+    lib.gb200_trace_dual.argtypes = [vp, C.POINTER(Problem), C.POINTER(DualIC), C.c_int32, C.POINTER(PlungingTable), C.POINTER(DualOut)]
+    lib.gb200_trace_dual_batch.argtypes = [vp, C.c_int32, C.POINTER(Problem), C.POINTER(DualIC), C.c_int32,
+                                           C.POINTER(C.POINTER(PlungingTable)), C.POINTER(DualOut)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("gb200_destroy", "gb200_last_error", "gb200_version"):

@@ -322,6 +322,19 @@ class EnsembleB200:
         return s
 
 
+_DEFAULT_ENSEMBLE = None
+
+
+def default_ensemble() -> EnsembleB200:
+    """The ensemble used when a call passes none: one shared `EnsembleB200` on device 0, so repeated calls reuse one CUDA
+    context, stream pool and device-buffer pool instead of creating one each (contexts are created lazily: building a
+    configuration on a box without a GPU does not fail, running it does)."""
+    global _DEFAULT_ENSEMBLE
+    if _DEFAULT_ENSEMBLE is None:
+        _DEFAULT_ENSEMBLE = EnsembleB200()
+    return _DEFAULT_ENSEMBLE
+
+
 class EnsembleEndpointThreads:
     """The reference's CPU ensemble.  Not available here by design: there is no CPU fallback."""
 
@@ -355,8 +368,9 @@ class TracingConfiguration:
     dtmax: float = 0.0
     _keep: list = field(default_factory=list, repr=False)
 
-    def to_c(self):
-        """-> (gb200_problem, gb200_ic).  Raises ValueError for anything outside the hot-path scope."""
+    def to_c(self, validate=True):
+        """-> (gb200_problem, gb200_ic).  Raises ValueError for anything outside the hot-path scope.  `validate=False` skips
+        the library's own `gb200_validate` (callers that must not load libgradus_b200: the CPU reference arm of bench.py)."""
         m = self.metric
         _check_metric(m)
         p = cabi.Problem()
@@ -461,7 +475,8 @@ class TracingConfiguration:
                 ic.x[k] = cabi.dptr(xs_soa[k])
                 ic.v[k] = cabi.dptr(vs_soa[k])
             ic.n = n
-        cabi.check(cabi.load().gb200_validate(C.byref(p), C.byref(ic)))
+        if validate:
+            cabi.check(cabi.load().gb200_validate(C.byref(p), C.byref(ic)))
         return p, ic
 
 
@@ -489,7 +504,7 @@ def tracing_configuration(m, position, velocity, *args, **kwargs):
     lam_dom = (0.0, float(lam)) if np.isscalar(lam) else (float(lam[0]), float(lam[1]))
     ensemble = kwargs.get("ensemble", None)
     if ensemble is None:
-        ensemble = EnsembleB200()
+        ensemble = default_ensemble()
     if not isinstance(ensemble, EnsembleB200):
         raise ValueError("this build integrates on the GPU only: pass ensemble=EnsembleB200(...) (no CPU fallback)")
     return TracingConfiguration(
@@ -615,6 +630,39 @@ def tracegeodesics_batch(configs: Sequence[TracingConfiguration]) -> list:
     return [GeodesicPoints(a, c.lambda_domain[0]) for a, c in zip(arrays, configs)]
 
 
+def trace_dual(config: TracingConfiguration, arrays: "cabi.DualArrays", norm_mode=cabi.DUAL_NORM_WITH_PARTIALS, plunging=None):
+    """Forward-mode trace (`gb200_trace_dual`): the rays of `arrays` (impact parameters with seeded partials) through the
+    problem `config` describes (metric, observer, geometry, chart, tolerances; its own velocity source is ignored).  What
+    the reference does by pushing ForwardDiff duals through `_solve_reinit!` / `tracegeodesics`
+    (src/tracing/precision-solvers.jl:73-131, 401-451).  Fills and returns `arrays`."""
+    p, _ = config.to_c()
+    ens = config.ensemble
+    ctx = ens.ctx(ens.devices[0])
+    pl_ref = C.byref(plunging.c) if plunging is not None else None
+    cabi.check(cabi.load().gb200_trace_dual(ctx, C.byref(p), C.byref(arrays.ic), norm_mode, pl_ref, C.byref(arrays.out)), ctx)
+    return arrays
+
+
+def trace_dual_batch(configs: Sequence[TracingConfiguration], arrays: Sequence["cabi.DualArrays"], norm_mode=cabi.DUAL_NORM_WITH_PARTIALS,
+                     plungings=None):
+    """`trace_dual` for many (configuration, rays) pairs in one `gb200_trace_dual_batch` call (one launch per pair on the
+    first device's stream pool, one staged copy each way)."""
+    nb = len(configs)
+    if nb == 0:
+        return arrays
+    ens = configs[0].ensemble
+    problems = (cabi.Problem * nb)(*[c.to_c()[0] for c in configs])
+    ics = (cabi.DualIC * nb)(*[a.ic for a in arrays])
+    outs = (cabi.DualOut * nb)(*[a.out for a in arrays])
+    pl_ptrs = None
+    if plungings is not None and any(pl is not None for pl in plungings):
+        PT = C.POINTER(cabi.PlungingTable)
+        pl_ptrs = (PT * nb)(*[C.pointer(pl.c) if pl is not None else PT() for pl in plungings])
+    ctx = ens.ctx(ens.devices[0])
+    cabi.check(cabi.load().gb200_trace_dual_batch(ctx, nb, problems, ics, norm_mode, pl_ptrs, outs), ctx)
+    return arrays
+
+
 def tracegeodesics(m, position, velocity, *args, **kwargs) -> GeodesicPoints:
     """`tracegeodesics(m, x, v | plane | velfunc, [geometry], λ; kwargs...)` (src/tracing/tracing.jl:66-80)."""
     config = tracing_configuration(m, position, velocity, *args, **kwargs)
@@ -644,7 +692,7 @@ def interpolate_plunging_velocities(m, ensemble=None, cap=1 << 17) -> PlungingIn
     key = (type(m).__name__, m.params())
     if key in _PLUNGING_CACHE:
         return _PLUNGING_CACHE[key]
-    ens = ensemble or EnsembleB200()
+    ens = ensemble or default_ensemble()
     ctx = ens.ctx(ens.devices[0])
     arrs = [np.zeros(cap) for _ in range(4)]
     n = C.c_int32()

@@ -738,6 +738,8 @@ int gb200_trace_path(gb200_ctx* ctx, const gb200_problem* p, const double* u0, i
     gb200_range rg{0, 1, 1};
     GbParams P;
     fill_params(p, &ic, &rg, P);
+    P.geometry_kind = GB200_GEOMETRY_NONE; // a bare geodesic: chart boundaries and lambda_max only
+    P.callback_kind = GB200_CALLBACK_NONE;
     void *d_u0, *d_lam, *d_u, *d_meta;
     rc = pool_get(ctx, SL_EX0, 64, &d_u0); if (rc) return rc;
     rc = pool_get(ctx, SL_LAMBDA, sizeof(double) * (size_t)cap, &d_lam); if (rc) return rc;
@@ -973,6 +975,162 @@ int gb200_render_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* prob
         ctx->stats.flagged += (int64_t)c[(size_t)b * 4 + 3];
     }
     return GB200_OK;
+}
+
+// ---------------------------------------------------------------- forward-mode traces (gb200_dual.cu)
+int gb200_trace_dual_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* problems, const gb200_dual_ic* ics, int32_t norm_mode,
+                           const gb200_plunging_table* const* pls, gb200_dual_out* outs) {
+    if (!ctx) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null context");
+    if (nbatch < 1 || !problems || !ics || !outs) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad batch arguments");
+    if (norm_mode != GB200_DUAL_NORM_WITH_PARTIALS && norm_mode != GB200_DUAL_NORM_VALUES_ONLY) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad norm_mode");
+    std::vector<gb200_ic> fake((size_t)nbatch);
+    for (int b = 0; b < nbatch; ++b) {
+        const gb200_dual_ic& d = ics[b];
+        if (d.n < 0 || (d.npartials != 1 && d.npartials != 2)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "dual IC needs n >= 0 and 1 or 2 partials");
+        if (d.n > 0 && (!d.alpha || !d.beta || !d.dalpha || !d.dbeta)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "dual IC needs alpha, beta and their partials");
+        gb200_ic& f = fake[(size_t)b];
+        memset(&f, 0, sizeof f);
+        f.kind = GB200_IC_IMPACT_PARAMETERS; f.n = d.n > 0 ? d.n : 1;
+        f.x[0] = d.alpha ? d.alpha : (const double*)&f; f.x[1] = d.beta ? d.beta : (const double*)&f;
+        int rc = validate(ctx, &problems[b], &f); if (rc) return rc;
+        if (d.height && problems[b].geometry_kind != GB200_GEOMETRY_DATUM_PLANE) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "per-ray heights need GB200_GEOMETRY_DATUM_PLANE");
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    ctx->stats = gb200_stats{};
+    ctx->cur = ctx->stream;
+    const int nstreams = nbatch < 32 ? nbatch : 32;
+    while ((int)ctx->pool_streams.size() < nstreams) {
+        cudaStream_t st;
+        CU(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ctx->pool_streams.push_back(st);
+    }
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    struct Off { size_t alpha, beta, dalpha, dbeta, height, pl[4], status, lambda, x[4], v[4], g, dg, rho, drho, nacc, nrej, flags; };
+    std::vector<Off> off((size_t)nbatch);
+    size_t total = 0;
+    for (int b = 0; b < nbatch; ++b) {
+        Off& o = off[(size_t)b];
+        const size_t n = (size_t)ics[b].n, nd = (size_t)ics[b].npartials;
+        o.alpha = total; total += al(8 * n); o.beta = total; total += al(8 * n);
+        o.dalpha = total; total += al(8 * n * nd); o.dbeta = total; total += al(8 * n * nd);
+        o.height = total; if (ics[b].height) total += al(8 * n);
+        if (pls && pls[b] && pls[b]->n >= 2) {
+            if (b > 0 && pls[b] == pls[b - 1]) { for (int k = 0; k < 4; ++k) o.pl[k] = off[(size_t)b - 1].pl[k]; }
+            else for (int k = 0; k < 4; ++k) { o.pl[k] = total; total += al(8 * (size_t)pls[b]->n); }
+        }
+    }
+    const size_t in_bytes = total;
+    for (int b = 0; b < nbatch; ++b) {
+        Off& o = off[(size_t)b];
+        const size_t n = (size_t)ics[b].n, nd = (size_t)ics[b].npartials;
+        o.status = total; total += al(4 * n); o.lambda = total; total += al(8 * n);
+        for (int k = 0; k < 4; ++k) { o.x[k] = total; total += al(8 * n); o.v[k] = total; total += al(8 * n); }
+        o.g = total; total += al(8 * n); o.dg = total; total += al(8 * n * nd);
+        o.rho = total; total += al(8 * n); o.drho = total; total += al(8 * n * nd);
+        o.nacc = total; total += al(4 * n); o.nrej = total; total += al(4 * n); o.flags = total; total += al(4 * n);
+    }
+    void* arena_v = nullptr;
+    int rc = pool_get(ctx, SL_BATCH, total + 256, &arena_v); if (rc) return rc;
+    char* arena = (char*)arena_v;
+    if (ctx->stage_cap < total) {
+        if (ctx->stage) cudaFreeHost(ctx->stage);
+        ctx->stage = nullptr; ctx->stage_cap = 0;
+        CU(ctx, cudaMallocHost(&ctx->stage, total + 256));
+        ctx->stage_cap = total;
+    }
+    char* stage = (char*)ctx->stage;
+    for (int b = 0; b < nbatch; ++b) {
+        const Off& o = off[(size_t)b];
+        const gb200_dual_ic& d = ics[b];
+        const size_t n = (size_t)d.n, nd = (size_t)d.npartials;
+        if (n) {
+            memcpy(stage + o.alpha, d.alpha, 8 * n); memcpy(stage + o.beta, d.beta, 8 * n);
+            memcpy(stage + o.dalpha, d.dalpha, 8 * n * nd); memcpy(stage + o.dbeta, d.dbeta, 8 * n * nd);
+            if (d.height) memcpy(stage + o.height, d.height, 8 * n);
+        }
+        if (pls && pls[b] && pls[b]->n >= 2 && !(b > 0 && pls[b] == pls[b - 1])) {
+            const double* src[4] = {pls[b]->r, pls[b]->ut, pls[b]->ur, pls[b]->uphi};
+            for (int k = 0; k < 4; ++k) memcpy(stage + o.pl[k], src[k], 8 * (size_t)pls[b]->n);
+        }
+    }
+    CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (in_bytes) CU(ctx, cudaMemcpyAsync(arena, stage, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    for (int sidx = 0; sidx < nstreams; ++sidx) CU(ctx, cudaStreamWaitEvent(ctx->pool_streams[(size_t)sidx], ctx->ev1, 0));
+    for (int b = 0; b < nbatch; ++b) {
+        const gb200_dual_ic& d = ics[b];
+        if (d.n == 0) continue;
+        const gb200_dual_out& out = outs[b];
+        const Off& o = off[(size_t)b];
+        gb200_range rg{0, d.n, 1, 1};
+        GbParams P;
+        fill_params(&problems[b], &fake[(size_t)b], &rg, P);
+        if (out.g) { rc = set_isco(ctx, &problems[b], P); if (rc) return rc; }
+        if (pls && pls[b] && pls[b]->n >= 2) {
+            P.pl_n = pls[b]->n;
+            P.pl_r = (const double*)(arena + o.pl[0]); P.pl_ut = (const double*)(arena + o.pl[1]);
+            P.pl_ur = (const double*)(arena + o.pl[2]); P.pl_uphi = (const double*)(arena + o.pl[3]);
+        }
+        GbDualIO io;
+        memset(&io, 0, sizeof io);
+        io.n = d.n; io.npartials = d.npartials; io.norm_partials = (norm_mode == GB200_DUAL_NORM_WITH_PARTIALS) ? 1 : 0;
+        io.alpha = (const double*)(arena + o.alpha); io.beta = (const double*)(arena + o.beta);
+        io.dalpha = (const double*)(arena + o.dalpha); io.dbeta = (const double*)(arena + o.dbeta);
+        io.height = d.height ? (const double*)(arena + o.height) : nullptr;
+        if (out.status) io.status = (int32_t*)(arena + o.status);
+        if (out.lambda_max) io.lambda = (double*)(arena + o.lambda);
+        for (int k = 0; k < 4; ++k) {
+            if (out.x[k]) io.x[k] = (double*)(arena + o.x[k]);
+            if (out.v[k]) io.v[k] = (double*)(arena + o.v[k]);
+        }
+        if (out.g) io.g = (double*)(arena + o.g);
+        if (out.dg) { if (!out.g) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "dg needs g"); io.dg = (double*)(arena + o.dg); }
+        if (out.rho) io.rho = (double*)(arena + o.rho);
+        if (out.drho) io.drho = (double*)(arena + o.drho);
+        if (out.naccept) io.naccept = (int32_t*)(arena + o.nacc);
+        if (out.nreject) io.nreject = (int32_t*)(arena + o.nrej);
+        if (out.flags) io.flags = (int32_t*)(arena + o.flags);
+        CU(ctx, gb200_launch_dual(P, io, ctx->pool_streams[(size_t)(b % nstreams)]));
+        ctx->stats.launches += 1;
+        ctx->stats.rays += d.n;
+    }
+    for (int sidx = 0; sidx < nstreams; ++sidx) {
+        CU(ctx, cudaEventRecord(ctx->ev2, ctx->pool_streams[(size_t)sidx]));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev2, 0));
+    }
+    if (total > in_bytes) CU(ctx, cudaMemcpyAsync(stage + in_bytes, arena + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < nbatch; ++b) {
+        const gb200_dual_out& out = outs[b];
+        const Off& o = off[(size_t)b];
+        const size_t n = (size_t)ics[b].n, nd = (size_t)ics[b].npartials;
+        if (!n) continue;
+        if (out.status) memcpy(out.status, stage + o.status, 4 * n);
+        if (out.lambda_max) memcpy(out.lambda_max, stage + o.lambda, 8 * n);
+        for (int k = 0; k < 4; ++k) {
+            if (out.x[k]) memcpy(out.x[k], stage + o.x[k], 8 * n);
+            if (out.v[k]) memcpy(out.v[k], stage + o.v[k], 8 * n);
+        }
+        if (out.g) memcpy(out.g, stage + o.g, 8 * n);
+        if (out.dg) memcpy(out.dg, stage + o.dg, 8 * n * nd);
+        if (out.rho) memcpy(out.rho, stage + o.rho, 8 * n);
+        if (out.drho) memcpy(out.drho, stage + o.drho, 8 * n * nd);
+        if (out.naccept) memcpy(out.naccept, stage + o.nacc, 4 * n);
+        if (out.nreject) memcpy(out.nreject, stage + o.nrej, 4 * n);
+        if (out.flags) memcpy(out.flags, stage + o.flags, 4 * n);
+    }
+    float tot = 0;
+    cudaEventElapsedTime(&tot, ctx->ev0, ctx->ev3);
+    ctx->stats.kernel_ms = tot; ctx->stats.total_ms = tot;
+    return GB200_OK;
+}
+
+int gb200_trace_dual(gb200_ctx* ctx, const gb200_problem* p, const gb200_dual_ic* ic, int32_t norm_mode,
+                     const gb200_plunging_table* plunging, gb200_dual_out* out) {
+    if (!p || !ic || !out) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null argument");
+    const gb200_plunging_table* pls[1] = {plunging};
+    return gb200_trace_dual_batch(ctx, 1, p, ic, norm_mode, pls, out);
 }
 
 static int lineprofile_common(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, const gb200_emissivity* em,

@@ -612,6 +612,54 @@ GB_D void kerr_rhs_accel_sq(double M, double a, double a2, double twoM, double r
 GB_D void kerr_rhs_accel(double M, double a, double r, double s, double c, double vt, double vr, double vth, double vph, double acc[4]) {
     kerr_rhs_accel_sq(M, a, a * a, 2.0 * M, r, s * s, c * c, 2.0 * s * c, vt, vr, vth, vph, acc);
 }
+#ifndef GB_OPT_KERR_LAG
+#define GB_OPT_KERR_LAG 0 /* Kerr accelerations from the Euler-Lagrange form with A = tdot - a sin^2 phdot (see below) */
+#endif
+#if GB_OPT_KERR_LAG
+// The same accelerations from 2L = -tdot^2 + (r^2 + a^2) s^2 phdot^2 + w A^2 + (Sigma / Delta) rdot^2 + Sigma thdot^2,
+// w = 2 M r / Sigma, A = tdot - a s^2 phdot: p_t = -tdot + w A and p_phi = s^2 ((r^2 + a^2) phdot - a w A) are conserved,
+// so tddot = d(w A)/dlambda =: Udot and phddot follows from p_phi; rddot and thddot are the Euler-Lagrange equations.
+// 79 FP64 instructions against 83 and 15 three-register DFMAs against 21; a second reciprocal 1 / (r^2 + a^2) whose chain
+// does not wait for the sine and cosine.
+GB_D void kerr_rhs_accel_sq(double M, double a, double a2, double twoM, double r, double s2, double c2, double sin2, double vt, double vr, double vth, double vph, double acc[4]) {
+    const double r2 = r * r;
+    const double rho2 = r2 + a2;
+    const double irho2 = gb_rcp(rho2);
+    const double Sig = fma(a2, c2, r2);
+    const double Del = fma(r, r - twoM, a2);
+    const double Ds = Del * s2;
+    const double R = gb_rcp(Sig * Ds);
+    const double iSig = R * Ds, iDel_is2 = R * Sig, iDel = iDel_is2 * s2, is2 = iDel_is2 * Del;
+    const double w = twoM * r * iSig;
+    const double hw_r = fma(-w, r, M) * iSig; // w_r / 2
+    const double a2sin2 = a2 * sin2;
+    const double wS = w * iSig;
+    const double as2 = a * s2;
+    const double A = fma(-as2, vph, vt), U = w * A;
+    const double h = a2sin2 * vth;
+    const double wdot = fma(2.0 * hw_r, vr, wS * h);
+    const double rr = r * vr;
+    double x = fma(rho2 * wdot, A, -(w * h) * U);
+    x = fma(2.0 * ((w * as2) * rr), vph, x);
+    const double Udot = x * iDel;
+    const double pp = vph * vph, tt = vth * vth, rr2 = vr * vr, X = vr * vth;
+    acc[0] = Udot;
+    {
+        const double q3 = fma(hw_r, A * A, r * fma(s2, pp, tt));
+        const double c2_ = fma(r, iSig, -((r - M) * iDel));
+        acc[1] = fma(a2sin2 * iSig, X, fma(-c2_, rr2, (Del * iSig) * q3));
+    }
+    {
+        const double e2 = fma(-(2.0 * a) * U, vph, rho2 * pp);
+        const double e5 = fma(U * A, iSig, tt - rr2 * iDel);
+        acc[2] = iSig * fma(-(2.0 * r), X, (0.5 * sin2) * fma(a2, e5, e2));
+    }
+    {
+        const double m = (sin2 * is2) * vth;
+        acc[3] = fma(-m, vph, fma(-(2.0 * rr), vph, a * fma(m, U, Udot)) * irho2);
+    }
+}
+#else
 GB_D void kerr_rhs_accel_sq(double M, double a, double a2, double twoM, double r, double s2, double c2, double sin2, double vt, double vr, double vth, double vph, double acc[4]) {
     const double r2 = r * r;
     const double Sig = fma(a2, c2, r2);
@@ -670,6 +718,7 @@ GB_D void kerr_rhs_accel_sq(double M, double a, double a2, double twoM, double r
     acc[2] = githth * fma(-d2, vth, 0.5 * St);
 #endif
 }
+#endif
 
 // Lorentz force on a charged test particle in the Kerr-Newman field, q/mu F^mu_kappa v^kappa with
 // F = g^-1 (dA - dA') (faraday_tensor, src/tracing/utility.jl:89-99; geodesic_ode_problem(::KerrNewmanMetric),

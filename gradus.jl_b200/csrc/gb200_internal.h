@@ -11,3 +11,17 @@ cudaError_t gb200_launch_dfma_mix(double* d_out, int blocks, int iters, int mix,
 cudaError_t gb200_launch_path(const GbParams& P, const double* d_u0, int cap, double* d_lambda, double* d_u, int* d_meta, cudaStream_t stream);
 cudaError_t gb200_launch_debug_rhs(const GbParams& P, long long n, const double* d_u, double* d_du, cudaStream_t stream);
 cudaError_t gb200_launch_debug_math(long long n, const double* d_x, double* d_out5, cudaStream_t stream);
+
+// forward-mode (dual-number) traces and the single-ray path recorder: gb200_dual.cu
+struct GbDualIO {
+    int64_t n;
+    int32_t npartials, norm_partials;
+    const double *alpha, *beta, *dalpha, *dbeta, *height; // device
+    int32_t* status;
+    double* lambda;
+    double* x[4];
+    double* v[4];
+    double *g, *dg, *rho, *drho;
+    int32_t *naccept, *nreject, *flags;
+};
+cudaError_t gb200_launch_dual(const GbParams& P, const GbDualIO& io, cudaStream_t stream);

@@ -765,106 +765,6 @@ cudaError_t gb200_launch_trace(const GbParams& P, int sm_count, cudaStream_t str
     return cudaErrorInvalidValue;
 }
 
-// ---------------------------------------------------------------- single-ray path recorder (set-up tool)
-// Same integrator semantics as the ensemble kernel (initial dt, Tsit5, PI controller, chart callback), written
-// plainly with loops because it runs on ONE thread: it records every accepted step, which the reference does for
-// single geodesics (save_on) and needs for the plunging-velocity table of non-Kerr redshifts.
-template <int METRIC>
-__global__ void gb200_path_kernel(const GbParams P, const double* __restrict__ u0in, int cap, double* __restrict__ lam_out,
-                                  double* __restrict__ u_out, int* __restrict__ meta) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const double A[7][6] = {{0, 0, 0, 0, 0, 0}, {GB_A21, 0, 0, 0, 0, 0}, {GB_A31, GB_A32, 0, 0, 0, 0}, {GB_A41, GB_A42, GB_A43, 0, 0, 0},
-                            {GB_A51, GB_A52, GB_A53, GB_A54, 0, 0}, {GB_A61, GB_A62, GB_A63, GB_A64, GB_A65, 0},
-                            {GB_A71, GB_A72, GB_A73, GB_A74, GB_A75, GB_A76}};
-    const double BT[7] = {GB_BT1, GB_BT2, GB_BT3, GB_BT4, GB_BT5, GB_BT6, GB_BT7};
-    double u[8], un[8], k[7][8], tmp[8];
-    for (int i = 0; i < 8; ++i) u[i] = u0in[i];
-    {
-        double g[5], sx, cx;
-        sincos(u[2], &sx, &cx);
-        metric_components_t<METRIC>(P, u[1], sx, cx, g);
-        u[4] = constrain_vt(g, u[5], u[6], u[7], P.mu);
-    }
-    auto f = [&](const double* x, double* dx) {
-        double acc[4], s_, c_;
-        rhs_accel<METRIC>(P, x[1], x[2], x[4], x[5], x[6], x[7], acc, s_, c_);
-        for (int i = 0; i < 4; ++i) { dx[i] = x[4 + i]; dx[4 + i] = acc[i]; }
-    };
-    const double abstol = P.abstol, reltol = P.reltol, dtmax = P.dtmax, dtmin = 2.220446049250313e-16, tstop = P.lam1;
-    double t = P.lam0;
-    int rows = 0, status = GB200_STATUS_NO_STATUS;
-    auto record = [&](double tt, const double* x) {
-        if (rows < cap) { lam_out[rows] = tt; for (int i = 0; i < 8; ++i) u_out[8 * rows + i] = x[i]; }
-        ++rows;
-    };
-    record(t, u);
-    f(u, k[0]);
-    double dt;
-    { // ode_determine_initdt
-        double sk[8], d0 = 0, d1 = 0, d2 = 0;
-        for (int i = 0; i < 8; ++i) { sk[i] = fma(fabs(u[i]), reltol, abstol); d0 += (u[i] / sk[i]) * (u[i] / sk[i]); d1 += (k[0][i] / sk[i]) * (k[0][i] / sk[i]); }
-        d0 = sqrt(d0 / 8.0); d1 = sqrt(d1 / 8.0);
-        double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
-        dt0 = fmin(dt0, dtmax);
-        for (int i = 0; i < 8; ++i) tmp[i] = fma(dt0, k[0][i], u[i]);
-        f(tmp, k[1]);
-        for (int i = 0; i < 8; ++i) { const double a2 = (k[1][i] - k[0][i]) / sk[i]; d2 += a2 * a2; }
-        d2 = sqrt(d2 / 8.0) / dt0;
-        const double md = fmax(d1, d2);
-        const double dt1 = (md <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : exp(-0.2 * log(100.0 * md));
-        dt = fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
-    }
-    double logqold = -9.210340371976182;
-    for (int64_t iter = 1; iter <= P.maxiters && t < tstop; ++iter) {
-        dt = fmin(fmax(fmin(dt, dtmax), dtmin), tstop - t);
-        for (int s = 1; s < 7; ++s) {
-            for (int i = 0; i < 8; ++i) {
-                double acc = 0;
-                for (int l = 0; l < s; ++l) acc = fma(A[s][l], k[l][i], acc);
-                tmp[i] = fma(dt, acc, u[i]);
-            }
-            if (s == 6) for (int i = 0; i < 8; ++i) un[i] = tmp[i];
-            f(tmp, k[s]);
-        }
-        double ee = 0;
-        for (int i = 0; i < 8; ++i) {
-            double e = 0;
-            for (int l = 0; l < 7; ++l) e = fma(BT[l], k[l][i], e);
-            const double q_ = dt * e / fma(fmax(fabs(u[i]), fabs(un[i])), reltol, abstol);
-            ee = fma(q_, q_, ee);
-        }
-        const double EEst = sqrt(ee / 8.0);
-        const double logE = (EEst > 0) ? log(EEst) : -700.0;
-        double q = (EEst == 0.0) ? 0.1 : fmax(0.1, fmin(5.0, exp(fma(7.0 / 50.0, logE, -(2.0 / 25.0) * logqold)) / 0.9));
-        if (EEst <= 1.0) {
-            const double ttmp = t + dt;
-            t = (fabs(ttmp - tstop) < 100.0 * (fabs(tstop) * 2.220446049250313e-16)) ? tstop : ttmp;
-            logqold = fmax(logE, -9.210340371976182);
-            for (int i = 0; i < 8; ++i) { u[i] = un[i]; k[0][i] = k[6][i]; }
-            dt = fmax(fmin(dtmax, dt / q), dtmin);
-            record(t, u);
-            if (u[1] <= P.chart_inner) { status = GB200_STATUS_WITHIN_INNER_BOUNDARY; break; }
-            if (u[1] > P.chart_outer) { status = GB200_STATUS_OUT_OF_DOMAIN; break; }
-            if (!(u[1] == u[1])) break;
-        } else {
-            dt = dt / fmin(5.0, exp((7.0 / 50.0) * logE) / 0.9);
-        }
-    }
-    meta[0] = rows;
-    meta[1] = status;
-}
-
-cudaError_t gb200_launch_path(const GbParams& P, const double* d_u0, int cap, double* d_lambda, double* d_u, int* d_meta, cudaStream_t stream) {
-    switch (P.metric_kind) {
-    case GB200_METRIC_KERR: gb200_path_kernel<GB200_METRIC_KERR><<<1, 32, 0, stream>>>(P, d_u0, cap, d_lambda, d_u, d_meta); break;
-    case GB200_METRIC_JOHANNSEN_PSALTIS: gb200_path_kernel<GB200_METRIC_JOHANNSEN_PSALTIS><<<1, 32, 0, stream>>>(P, d_u0, cap, d_lambda, d_u, d_meta); break;
-    case GB200_METRIC_JOHANNSEN: gb200_path_kernel<GB200_METRIC_JOHANNSEN><<<1, 32, 0, stream>>>(P, d_u0, cap, d_lambda, d_u, d_meta); break;
-    case GB200_METRIC_BUMBLEBEE: gb200_path_kernel<GB200_METRIC_BUMBLEBEE><<<1, 32, 0, stream>>>(P, d_u0, cap, d_lambda, d_u, d_meta); break;
-    default: gb200_path_kernel<GB200_METRIC_KERR_NEWMAN><<<1, 32, 0, stream>>>(P, d_u0, cap, d_lambda, d_u, d_meta); break;
-    }
-    return cudaGetLastError();
-}
-
 // ---------------------------------------------------------------- line-profile histogram (Buckets.bucket(Simple(), g, f, bins))
 // Shared-memory FP64 bins; lanes of a warp that hit the same bin are combined first
 // (__match_any_sync) so one shared atomic per distinct bin per warp is issued; each block

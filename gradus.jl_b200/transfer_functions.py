@@ -1,19 +1,19 @@
 """Cunningham transfer functions on top of the device tracer.
 
 What the reference does (src/transfer-functions/cunningham-transfer-functions.jl:336-426,
-src/tracing/precision-solvers.jl:133-241, 401-451): for an emission radius rₑ it walks N image-plane angles θ, root-finds
-the image-plane offset r(θ) whose geodesic lands on the disc at rₑ, takes the redshift g and the Jacobian
-|∂(α,β)/∂(g,rₑ)| there, refines g_min / g_max with two golden-section searches and forms
+src/tracing/precision-solvers.jl:73-241, 401-451): for an emission radius rₑ it walks N image-plane angles θ, root-finds
+the image-plane offset r(θ) whose geodesic lands on the disc at rₑ (Newton on ρ(r) − rₑ with dρ/dr from a dual number
+pushed through the integrator), takes the redshift g and the Jacobian |∂(α,β)/∂(g,rₑ)| there (two partials pushed
+through the integrator), refines g_min / g_max with two golden-section searches and forms
 
     f = g √(g✶(1 − g✶)) |∂(α,β)/∂(g,rₑ)| / (π rₑ),      g✶ = (g − g_min) / (g_max − g_min).
 
-Every one of those ~1300 geodesics per radius is an ordinary endpoint trace, i.e. the hot path this library puts on the
-GPU.  The reference runs them one after the other (one radius per thread); here the *control* stays on the host, in the
-reference's own order, but it is written in lock step over all (rₑ, θ) pairs: every Newton / golden-section iteration
-is one `gb200_render` launch over all still-active pairs of all radii, so a table of 150 radii costs the same number of
-launches as a single radius.  Derivatives: the reference pushes dual numbers through the integrator; this version takes
-central differences of traces run at a tighter tolerance (rays are cheap here), which reproduces the reference's
-transfer-function literals (test/smoke-tests/cunningham-transfer-functions.jl:25-39) well inside their tolerance.
+Every one of those geodesics is a forward-mode trace on the device (`gb200_trace_dual`: the integrator state carries the
+partials, the step-size control sees them through the error norm as DiffEqBase's does, the event time moves with the
+parameters).  The reference runs them one after the other (one radius per thread); here the *control* stays on the host,
+in the reference's own order and with its own update rules, but it is written in lock step over all (rₑ, θ) pairs: every
+Newton / golden-section iteration is one launch over all still-active pairs of all radii, so a table of 150 radii costs
+the same number of launches as a single radius.
 
 The tracer is injected (`prober`): the product default is `DeviceProber` (C ABI, GPU, no fallback); the CPU test-suite
 plugs the oracle into the same orchestration to pin the host logic without a GPU.
@@ -64,7 +64,7 @@ class DeviceProber:
         self.d = d
         self.max_time = 2 * self.x[1] if max_time is None else max_time
         self.chart = chart if chart is not None else api.chart_for_metric(m, 2 * self.x[1])
-        self.ensemble = ensemble if ensemble is not None else api.EnsembleB200()
+        self.ensemble = ensemble if ensemble is not None else api.default_ensemble()
         self.solver_kwargs = solver_kwargs
         self.pfs = [api.ConstPointFunctions.redshift(m, x) @ api.ConstPointFunctions.filter_intersected(),
                     api.ConstPointFunctions.radius() @ api.ConstPointFunctions.filter_intersected(),
@@ -73,6 +73,7 @@ class DeviceProber:
         self.plunging = None
         self.launches = 0
         self.rays = 0
+        self.norm_mode = api.cabi.DUAL_NORM_WITH_PARTIALS  # DiffEqBase's norm on dual-valued states
 
     def config(self, alpha, beta, tol=None, height=None, thick=False, chart=None, callback=None):
         kw = dict(self.solver_kwargs)
@@ -96,8 +97,25 @@ class DeviceProber:
     def evaluate_points(self, config):
         return api.solve_tracing_problem(config)
 
+    def evaluate_dual(self, config, arrays, norm_mode):
+        return api.trace_dual(config, arrays, norm_mode, plunging=self._plunging())
+
     def cross_section(self, rho, group=None):
         return self.thick.cross_section(rho)
+
+    def disc_inner_radius(self, group=None):
+        return self.thick.inner_radius
+
+    def dual(self, alpha, beta, dalpha, dbeta, height=None, thick=False, callback=None, group=None):
+        """Forward-mode trace of the rays (α, β) whose partials are (dalpha[k], dbeta[k]), k < 1 or 2: returns the filled
+        `DualArrays` (g, dg, rho, drho, x, status, ...).  ρ = r sin θ of the end point whatever its status."""
+        arrays = api.cabi.DualArrays(alpha, beta, dalpha, dbeta, None if thick else height)
+        if arrays.n == 0:
+            return arrays
+        self.launches += 1
+        self.rays += arrays.n
+        cfg = self.config(arrays.alpha, arrays.beta, None, height=None, thick=thick, callback=callback)
+        return self.evaluate_dual(cfg, arrays, self.norm_mode)
 
     def __call__(self, alpha, beta, tol=None, height=None, thick=False, callback=None, with_end_radius=False, group=None):
         """(g, ρ, t) at the intersection: with the datum plane(s) (one height per ray if `height` is given), or with the
@@ -143,6 +161,9 @@ class CellProber:
             out[sel] = self.probers[c].thick.cross_section(rho[sel])
         return out
 
+    def disc_inner_radius(self, group):
+        return np.array([p.thick.inner_radius for p in self.probers])[np.asarray(group)]
+
     def evaluate_batch(self, configs, cells):
         plungings = [self.probers[c]._plunging() for c in cells]
         return api.apply_point_functions_batch(configs, self.probers[0].pfs, plungings)
@@ -161,6 +182,30 @@ class CellProber:
             for s, img in zip(sels, self.evaluate_batch(configs, cells)):
                 out[:, s] = img
         return (out[0], out[1], out[2], out[3]) if with_end_radius else (out[0], out[1], out[2])
+
+    def evaluate_dual_batch(self, configs, arrays, cells):
+        plungings = [self.probers[c]._plunging() for c in cells]
+        return api.trace_dual_batch(configs, arrays, self.probers[0].norm_mode, plungings)
+
+    def dual(self, alpha, beta, dalpha, dbeta, height=None, thick=False, callback=None, group=None):
+        """All cells' rays in ONE `gb200_trace_dual_batch` call; returns one merged `DualArrays`-like result."""
+        merged = api.cabi.DualArrays(alpha, beta, dalpha, dbeta, None if thick else height)
+        if merged.n == 0:
+            return merged
+        cells, sels = _split_by_group(group)
+        parts = [api.cabi.DualArrays(merged.alpha[s], merged.beta[s], merged.dalpha[:, s], merged.dbeta[:, s],
+                                     None if (thick or height is None) else merged.height[s]) for s in sels]
+        configs = [self.probers[c].config(pa.alpha, pa.beta, None, height=None, thick=thick, callback=callback) for c, pa in zip(cells, parts)]
+        self.launches += 1
+        self.rays += merged.n
+        self.evaluate_dual_batch(configs, parts, cells)
+        for s, pa in zip(sels, parts):
+            merged.status[s], merged.lambda_max[s] = pa.status, pa.lambda_max
+            merged.x[:, s], merged.v[:, s] = pa.x, pa.v
+            merged.g[s], merged.rho[s] = pa.g, pa.rho
+            merged.dg[:, s], merged.drho[:, s] = pa.dg, pa.drho
+            merged.naccept[s], merged.nreject[s], merged.flags[s] = pa.naccept, pa.nreject, pa.flags
+        return merged
 
     def points(self, alpha, beta, height=None, thick=False, default_chart=False, group=None):
         """Per cell (two calls per sample set, off the probe-round path)."""
@@ -194,7 +239,8 @@ class _Points:
 
 @dataclass
 class TransferFunctionSetup:
-    """`_TransferFunctionSetup`, cunningham-transfer-functions.jl:7-58."""
+    """`_TransferFunctionSetup`, cunningham-transfer-functions.jl:7-58, and the keyword defaults of
+    `_find_offset_for_radius`, precision-solvers.jl:133-147."""
 
     theta_offset: float = 0.3
     zero_atol: float = 1e-7
@@ -202,10 +248,7 @@ class TransferFunctionSetup:
     N_extrema: int = 17
     h: float = 1e-6
     max_iter: int = 50
-    # central-difference Jacobian (the reference uses dual numbers): relative step on the image plane and the
-    # integrator tolerance of the differenced traces
-    fd_step: float = 2e-5
-    fd_tol: float = 1e-12
+    contrapoint_bias: float = 2.0
     # origin of the polar coordinates on the image plane (`_rθ_to_αβ`, precision-solvers.jl:1-7)
     alpha0: float = 0.0
     beta0: float = 0.0
@@ -219,90 +262,143 @@ def theta_samples(setup: TransferFunctionSetup) -> np.ndarray:
                            np.linspace(math.pi - o, math.pi + o, K)])
 
 
+def _bracket_offsets(step_y, lo, hi, atol, max_halvings=80):
+    """`find_zero(f, (contra, x), atol = zero_atol)` (Roots.jl bisection on a bracketing interval) for a batch of
+    independent intervals: `step_y(idx, x)` evaluates ρ(x) − rₑ for the problems `idx`.  Returns the roots, NaN where the
+    end points do not bracket a sign change (Roots.jl raises there)."""
+    n = lo.size
+    idx = np.arange(n)
+    flo, fhi = step_y(idx, lo), step_y(idx, hi)
+    root = np.where(np.abs(flo) <= np.abs(fhi), lo, hi).astype(np.float64)
+    best = np.minimum(np.abs(flo), np.abs(fhi))
+    ok = np.sign(flo) * np.sign(fhi) < 0
+    root[~ok & (best > atol)] = np.nan
+    active = ok & (best > atol)
+    lo, hi, flo = lo.copy(), hi.copy(), flo.copy()
+    for _ in range(max_halvings):
+        k = np.nonzero(active)[0]
+        if k.size == 0:
+            break
+        mid = 0.5 * (lo[k] + hi[k])
+        fm = step_y(k, mid)
+        better = np.abs(fm) < best[k]
+        root[k[better]], best[k[better]] = mid[better], np.abs(fm[better])
+        same = np.sign(fm) == np.sign(flo[k])
+        lo[k] = np.where(same, mid, lo[k])
+        flo[k] = np.where(same, fm, flo[k])
+        hi[k] = np.where(same, hi[k], mid)
+        active[k] = (np.abs(fm) > atol) & (hi[k] - lo[k] > 4 * np.finfo(float).eps * np.abs(mid))
+    return root
+
+
 def find_offset_for_radius(prober, r_target, theta, setup: TransferFunctionSetup = TransferFunctionSetup(), initial_r=None,
-                           height=None, group=None):
-    """Batched `_find_offset_for_radius` (precision-solvers.jl:133-241): for each pair (r_target[i], theta[i]) the
-    image-plane offset r with ρ(r cos θ, r sin θ) = r_target.  Newton steps on ρ(r) − r_target, safeguarded by the
-    bracket the monotonicity of ρ(r) provides (the lower end starts inside the hole, like the reference's contrapoint).
-    One launch per iteration for all unconverged pairs.  Returns (r, g, t); r is NaN where no offset was found
-    (|ρ − r_target| > 1e-4 r_target after `max_iter` iterations)."""
+                           height=None, group=None, r_min=None):
+    """`_find_offset_for_radius` (precision-solvers.jl:133-241) for a batch of (r_target[i], theta[i]) pairs: the
+    image-plane offset x with ρ(x cos θ, x sin θ) = r_target.  The reference's iteration, pair by pair -- Newton steps
+    x − y / y′ with y′ = dρ/dx read off a dual number pushed through the trace, a contrapoint inside the hole that pulls
+    overshoots back (`contrapoint_bias`), cycle detection on the relative decrease with a bracketing finish -- run in
+    lock step: every `step` of every still-active pair goes out in one launch.  Returns (x, point) with point the
+    `DualArrays`-like record (g, rho, x, status, ...) of the last trace of each pair; x is NaN where the reference
+    returns NaN (negative offset, or |y| > 1e-4 r_target at the end)."""
     r_target = np.asarray(r_target, np.float64)
     theta = np.asarray(theta, np.float64)
     n = r_target.size
     ct, st = np.cos(theta), np.sin(theta)
-    r = np.maximum(20.0, r_target) if initial_r is None else np.array(initial_r, np.float64)
-    lo = np.zeros(n)
-    hi = np.full(n, np.inf)
-    g = np.full(n, np.nan)
-    t = np.full(n, np.nan)
-    y = np.full(n, np.inf)
-    best = r.copy()  # the evaluated offset with the smallest |ρ − r_target| so far
-    stall = np.zeros(n, int)
-    active = np.ones(n, bool)
-    rel = 1e-6  # forward-difference step for dρ/dr
-    for _ in range(setup.max_iter + 1):
-        idx = np.nonzero(active)[0]
-        if idx.size == 0:
-            break
-        ra = r[idx]
-        rb = ra * (1 + rel)
-        hq = {} if height is None else {"height": np.concatenate([height[idx], height[idx]])}
+    atol, bias = setup.zero_atol, setup.contrapoint_bias
+    pt = dict(g=np.full(n, np.nan), rho=np.full(n, np.nan), t=np.full(n, np.nan), status=np.full(n, -1, np.int32),
+              lambda_max=np.full(n, np.nan), x=np.full((4, n), np.nan), alpha=np.full(n, np.nan), beta=np.full(n, np.nan))
+    df = np.zeros(n)
+
+    def step(idx, xr):
+        """(point, df, y) of the reference's `step`, for the pairs idx at offsets xr; records point and df."""
+        al, be = xr * ct[idx] + setup.alpha0, xr * st[idx] + setup.beta0
+        kw = {}
+        if height is not None:
+            kw["height"] = height[idx]
         if group is not None:
-            hq["group"] = np.concatenate([group[idx], group[idx]])
-        gq, rho, tq, rho_end = prober(np.concatenate([ra * ct[idx], rb * ct[idx]]) + setup.alpha0,
-                                      np.concatenate([ra * st[idx], rb * st[idx]]) + setup.beta0, with_end_radius=True, **hq)
-        m = idx.size
-        ya = rho[:m] - r_target[idx]
-        yb = rho[m:] - r_target[idx]
-        # no intersection: the ray fell into the hole (its end point projects inside the target: the root lies further
-        # out) or left the domain before reaching the plane (end point far outside: the root lies further in)
-        lost = ~np.isfinite(ya)
-        ya = np.where(lost, np.where(rho_end[:m] < r_target[idx], -np.inf, np.inf), ya)
-        for yc, rc, off in ((ya, ra, 0), (np.where(np.isfinite(yb), yb, -np.inf), rb, m)):  # both traces are candidates
-            improved = np.abs(yc) < np.abs(y[idx])
-            k = idx[improved]
-            y[k], best[k], g[k], t[k] = yc[improved], rc[improved], gq[off:off + m][improved], tq[off:off + m][improved]
-            stall[idx] = np.where(improved, 0, stall[idx] + (off > 0))
-        # converged, or stuck at the resolution of ρ(r) (the integrator's own error, ~reltol·ρ, can exceed zero_atol
-        # at large radii): three iterations without improvement on an already good offset
-        done = (np.abs(y[idx]) <= setup.zero_atol) | ((stall[idx] >= 3) & (np.abs(y[idx]) <= 1e-6 * r_target[idx]))
-        active[idx[done]] = False
-        below = ya < 0
-        lo[idx] = np.where(below, np.maximum(lo[idx], ra), lo[idx])
-        hi[idx] = np.where(~below, np.minimum(hi[idx], ra), hi[idx])
+            kw["group"] = group[idx]
+        res = prober.dual(al, be, ct[idx][None, :], st[idx][None, :], **kw)
+        pt["g"][idx], pt["rho"][idx], pt["t"][idx], pt["status"][idx] = res.g, res.rho, res.x[0], res.status
+        pt["lambda_max"][idx], pt["x"][:, idx], pt["alpha"][idx], pt["beta"][idx] = res.lambda_max, res.x, al, be
+        df[idx] = res.drho[0]
+        return res.rho - r_target[idx]
+
+    if r_min is None:
+        r_min = api.inner_radius(prober.m) if getattr(prober, "m", None) is not None else 0.0
+    r_min = np.broadcast_to(np.asarray(r_min, np.float64), (n,))
+    x = np.maximum(20.0, r_target) if initial_r is None else np.array(np.broadcast_to(initial_r, (n,)), np.float64)
+    contra = np.zeros(n)
+    allidx = np.arange(n)
+    y = step(allidx, x)
+    dy = np.zeros(n)
+    previous = np.zeros((n, 6))
+    it = np.zeros(n, int)
+    active = ~(np.abs(y) <= atol)
+    while True:
+        A = np.nonzero(active & (it <= setup.max_iter))[0]
+        if A.size == 0:
+            break
         with np.errstate(all="ignore"):
-            dy = (yb - ya) / (rb - ra)
-            nxt = ra - ya / dy
-        # outside the bracket (or no derivative): bisect it, or double while there is no upper end yet
-        bad = ~np.isfinite(nxt) | (nxt <= lo[idx]) | (nxt >= hi[idx])
+            next_x = x[A] - y[A] / df[A]
+        next_y = step(A, next_x)
+        pull = (next_x < 0) | ((next_y < 0) & (y[A] > 0))
+        contra[A] = np.where(pull, np.maximum(contra[A], next_x), contra[A])
+        # the overshoot ended in (or next to) the hole: step back towards the contrapoint instead
+        redo = pull & ((next_x < 0) | (pt["rho"][A] < r_min[A] + 1))
+        if redo.any():
+            R = A[redo]
+            next_x[redo] = (contra[R] * bias + x[R]) / (1 + bias)
+            next_y[redo] = step(R, next_x[redo])
         with np.errstate(all="ignore"):
-            bis = np.where(np.isfinite(hi[idx]), 0.5 * (lo[idx] + hi[idx]), 2.0 * ra)
-        nxt = np.where(bad, bis, nxt)
-        r[idx] = np.where(done, ra, nxt)
-    poor = ~(np.abs(y) <= 1e-4 * r_target)
-    return np.where(poor, np.nan, best), g, t
+            failed = (next_y < 0) & (y[A] < 0) & ((-y[A] / df[A]) < 0)  # "Converge failed": x, y keep their old values
+            next_dy = (y[A] - next_y) / y[A]
+            cycle = ~failed & (y[A] > 0) & np.any(np.abs(next_dy[:, None] - previous[A]) <= atol * 100, axis=1)
+        active[A[failed]] = False
+        if cycle.any():  # stuck with Newton-Raphson: finish off by bracketing between the contrapoint and x
+            Cy = A[cycle]
+            x[Cy] = _bracket_offsets(lambda k, xr: step(Cy[k], xr), contra[Cy], x[Cy], atol)
+            good = np.isfinite(x[Cy])
+            y[Cy[good]] = step(Cy[good], x[Cy[good]])
+            y[Cy[~good]] = np.inf
+            active[Cy] = False
+        go = ~failed & ~cycle
+        G = A[go]
+        x[G], dy[G], y[G] = next_x[go], next_dy[go], next_y[go]
+        previous[G, it[G] % 6] = dy[G]
+        it[G] += 1
+        active[G] = ~(np.abs(y[G]) <= atol)
+    # exceeded max_iter with a large residual: "Attempting to bracket"
+    late = np.nonzero((it >= setup.max_iter) & (y > 10.0) & np.isfinite(x))[0]
+    if late.size:
+        x[late] = _bracket_offsets(lambda k, xr: step(late[k], xr), contra[late], x[late], atol)
+        good = np.isfinite(x[late])
+        y[late[good]] = step(late[good], x[late[good]])
+        y[late[~good]] = np.inf
+    with np.errstate(invalid="ignore"):
+        poor = ~np.isfinite(x) | (x < 0) | ~(np.abs(y) <= 1e-4 * r_target)
+    return np.where(poor, np.nan, x), pt
 
 
-def jacobian_ab_gr(prober, alpha, beta, setup: TransferFunctionSetup = TransferFunctionSetup(), thick=False, group=None):
-    """|∂(ρ, g)/∂(α, β)|⁻¹ (`jacobian_∂αβ_∂gr`, precision-solvers.jl:401-451) by central differences: four traces
-    per point at tolerance `fd_tol`, all points in one launch."""
+def jacobian_ab_gr(prober, alpha, beta, setup: TransferFunctionSetup = TransferFunctionSetup(), thick=False, group=None,
+                   disc_inner_radius=None):
+    """|∂(ρ, g)/∂(α, β)|⁻¹ (`jacobian_∂αβ_∂gr`, precision-solvers.jl:401-451): one forward-mode trace per point with the two
+    partials of (α, β), all points in one launch.  On a thick disc the trace runs against the disc itself under
+    `domain_upper_hemisphere`, and g is set to zero inside the disc's inner radius (:431-435), which makes the inverse
+    Jacobian infinite: the visibility flag of `_thick_workhorse`."""
     alpha = np.asarray(alpha, np.float64)
     beta = np.asarray(beta, np.float64)
     n = alpha.size
-    h = setup.fd_step * np.maximum(np.hypot(alpha, beta), 1.0)
-    a = np.concatenate([alpha + h, alpha - h, alpha, alpha])
-    b = np.concatenate([beta, beta, beta + h, beta - h])
-    gq = {} if group is None else {"group": np.tile(group, 4)}
-    if thick:  # on the disc itself, upper hemisphere only (precision-solvers.jl:411,424-426)
-        g, rho, _ = prober(a, b, setup.fd_tol, thick=True, callback=api.domain_upper_hemisphere(), **gq)
-    else:
-        g, rho, _ = prober(a, b, setup.fd_tol, **gq)
+    one, zero = np.ones(n), np.zeros(n)
+    kw = {} if group is None else {"group": group}
+    if thick:
+        kw.update(thick=True, callback=api.domain_upper_hemisphere())
+    res = prober.dual(alpha, beta, np.stack([one, zero]), np.stack([zero, one]), **kw)
+    dg = res.dg.copy()
+    if thick and disc_inner_radius is not None:
+        dg[:, res.rho < disc_inner_radius] = 0.0
     with np.errstate(all="ignore"):
-        drho_da = (rho[:n] - rho[n:2 * n]) / (2 * h)
-        drho_db = (rho[2 * n:3 * n] - rho[3 * n:]) / (2 * h)
-        dg_da = (g[:n] - g[n:2 * n]) / (2 * h)
-        dg_db = (g[2 * n:3 * n] - g[3 * n:]) / (2 * h)
-        return np.abs(1.0 / (drho_da * dg_db - drho_db * dg_da))
+        det = res.drho[0] * dg[1] - res.drho[1] * dg[0]
+        return np.abs(1.0 / det)
 
 
 class _Workhorse:
@@ -312,13 +408,21 @@ class _Workhorse:
         self.prober, self.setup = prober, setup
 
     def __call__(self, r_e, theta, group=None):
-        r, g, t = find_offset_for_radius(self.prober, r_e, theta, self.setup, group=group)
+        r, pt = find_offset_for_radius(self.prober, r_e, theta, self.setup, group=group, r_min=_r_min_of(self.prober, group))
         if np.any(np.isnan(r)):
             k = int(np.nonzero(np.isnan(r))[0][0])
             raise RuntimeError(f"Transfer function integration failed (rₑ={r_e[k]}, θ={theta[k]}).")
         J = jacobian_ab_gr(self.prober, r * np.cos(theta) + self.setup.alpha0, r * np.sin(theta) + self.setup.beta0, self.setup,
                            group=group)
-        return g, J, t
+        return pt["g"], J, pt["t"]
+
+
+def _r_min_of(prober, group):
+    """`inner_radius(m)` of each pair's metric (one metric per cell of a table)."""
+    if group is None or not hasattr(prober, "probers"):
+        return api.inner_radius(prober.m)
+    rm = np.array([api.inner_radius(p.m) for p in prober.probers])
+    return rm[np.asarray(group)]
 
 
 class _ThickWorkhorse:
@@ -333,26 +437,27 @@ class _ThickWorkhorse:
         r_e = np.asarray(r_e, np.float64)
         gq = {} if group is None else {"group": group}
         h = self.prober.cross_section(r_e, group)
-        r, g, t = find_offset_for_radius(self.prober, r_e, theta, self.setup, height=h, group=group)
+        r, pt = find_offset_for_radius(self.prober, r_e, theta, self.setup, height=h, group=group, r_min=_r_min_of(self.prober, group))
         if np.any(np.isnan(r)):
             k = int(np.nonzero(np.isnan(r))[0][0])
             raise RuntimeError(f"Transfer function integration failed (rₑ={r_e[k]}, θ={theta[k]}).")
         alpha = r * np.cos(theta) + self.setup.alpha0
         beta = r * np.sin(theta) + self.setup.beta0
-        gp = self.prober.points(alpha, beta, height=h, **gq)
         # the reference re-traces with the default chart and stops at 1.1 λ_max of the datum-plane point: a disc hit
         # later than that is no hit
         gt = self.prober.points(alpha, beta, thick=True, default_chart=True, **gq)
-        status = np.where((gt.status == api.StatusCodes.IntersectedWithGeometry) & (gt.lambda_max > 1.1 * gp.lambda_max),
+        status = np.where((gt.status == api.StatusCodes.IntersectedWithGeometry) & (gt.lambda_max > 1.1 * pt["lambda_max"]),
                           api.StatusCodes.NoStatus, gt.status)
-        dist = np.linalg.norm(gp.x - gt.x, axis=0)
-        close = dist <= 1e-3 * np.maximum(np.linalg.norm(gp.x, axis=0), np.linalg.norm(gt.x, axis=0))  # isapprox(rtol = 1e-3)
-        ok = (status == gp.status) & close
+        dist = np.linalg.norm(pt["x"] - gt.x, axis=0)
+        close = dist <= 1e-3 * np.maximum(np.linalg.norm(pt["x"], axis=0), np.linalg.norm(gt.x, axis=0))  # isapprox(rtol = 1e-3)
+        ok = (status == pt["status"]) & close
         J = np.full(r.size, np.nan)
         if ok.any():
-            J[ok] = jacobian_ab_gr(self.prober, alpha[ok], beta[ok], self.setup, thick=True, group=None if group is None else group[ok])
+            inner = self.prober.disc_inner_radius(None if group is None else group[ok])
+            J[ok] = jacobian_ab_gr(self.prober, alpha[ok], beta[ok], self.setup, thick=True, group=None if group is None else group[ok],
+                                   disc_inner_radius=inner)
         J[~np.isfinite(J)] = np.nan  # `is_visible = isfinite(J)`; invisible samples keep g and t, J = NaN (utils.jl:71-78)
-        return g, J, t
+        return pt["g"], J, pt["t"]
 
 
 def _golden_sections(fn, lower, upper, iterations, rel_tol=math.sqrt(np.finfo(float).eps), abs_tol=np.finfo(float).eps):
@@ -391,7 +496,7 @@ def cunningham_transfer_functions(m, x, d, radii: Sequence[float], *, prober: Op
                                   groups=None, **kwargs) -> list:
     """`cunningham_transfer_function(m, x, d, rₑ; N, chart, max_time, ...)` for every rₑ in `radii` at once (the loop
     `interpolated_transfer_branches` threads over, cunningham-transfer-functions.jl:428-462)."""
-    setup_keys = {"theta_offset", "zero_atol", "N", "N_extrema", "h", "max_iter", "fd_step", "fd_tol", "alpha0", "beta0"}
+    setup_keys = {"theta_offset", "zero_atol", "N", "N_extrema", "h", "max_iter", "contrapoint_bias", "alpha0", "beta0"}
     if setup is None:
         alias = {"θ_offset": "theta_offset", "α₀": "alpha0", "β₀": "beta0"}
         skw = {alias.get(k, k): kwargs.pop(k) for k in list(kwargs) if alias.get(k, k) in setup_keys}
@@ -482,7 +587,7 @@ def transfer_function_table(metrics, observers, d, radii_of, *, ensemble=None, s
     θ in θ_range` and computes one cell after the other.  `metrics[c]`, `observers[c]` describe cell c, `d` is the disc
     (or a callable m -> disc, for discs that depend on the metric), `radii_of(m)` the emission radii of a cell.
     Returns, per cell, the list of `CunninghamTransferData` of its radii."""
-    ensemble = ensemble if ensemble is not None else api.EnsembleB200()
+    ensemble = ensemble if ensemble is not None else api.default_ensemble()
     probers, radii, groups = [], [], []
     for c, (m, x) in enumerate(zip(metrics, observers)):
         disc = d(m) if callable(d) else d

@@ -282,6 +282,55 @@ int gb200_lineprofile(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic
                       const double* bins, int32_t nbins,
                       const gb200_lineprofile_opts* opts, double* flux_out);
 
+/* ---- forward-mode (dual-number) traces: the transfer-function solvers ---- */
+/* The reference differentiates through the integrator with ForwardDiff: `_make_image_plane_mapper`
+   (src/tracing/precision-solvers.jl:73-131) seeds the image-plane offset with one partial for the Newton iteration of
+   `_find_offset_for_radius` (:133-241), `jacobian_∂αβ_∂gr` (:401-451) seeds (alpha, beta) with two for
+   |d(rho, g) / d(alpha, beta)|.  Ray i starts at problem.observer with impact parameters alpha[i], beta[i]
+   (map_impact_parameters, src/tracing/utility.jl:70-87) whose partials are dalpha[k*n + i], dbeta[k*n + i],
+   k < npartials; the whole integrator state carries the partials, the step-size control reads them through the error
+   norm exactly as DiffEqBase does for dual-valued states (norm_mode), and an event time found on the dense output moves
+   with the parameters so that the end point stays on the surface. */
+typedef struct gb200_dual_ic {
+    int64_t n;
+    int32_t npartials;    /* 1 or 2 */
+    int32_t reserved;
+    const double* alpha;  /* n */
+    const double* beta;   /* n */
+    const double* dalpha; /* npartials x n */
+    const double* dbeta;  /* npartials x n */
+    const double* height; /* optional, n: per-ray datum-plane height (GB200_GEOMETRY_DATUM_PLANE), NULL = geometry_params[0] */
+} gb200_dual_ic;
+
+/* Caller-allocated host arrays, n entries each (dg, drho: npartials x n); any pointer may be NULL.
+   g = redshift (NaN unless the ray intersected the geometry), rho = r sin(theta) of the end point whatever its
+   status (`_equatorial_project`, the quantity the offset root finder reads for rays that missed, precision-solvers.jl:124). */
+typedef struct gb200_dual_out {
+    int32_t* status;
+    double* lambda_max;
+    double* x[4];
+    double* v[4];
+    double* g;
+    double* dg;
+    double* rho;
+    double* drho;
+    int32_t* naccept;
+    int32_t* nreject;
+    int32_t* flags;
+} gb200_dual_out;
+
+#define GB200_DUAL_NORM_WITH_PARTIALS 0 /* DiffEqBase's ODE_DEFAULT_NORM on duals: partials are error-controlled too */
+#define GB200_DUAL_NORM_VALUES_ONLY 1   /* step sequence of the plain trace */
+
+int gb200_trace_dual(gb200_ctx* ctx, const gb200_problem* p, const gb200_dual_ic* ic, int32_t norm_mode,
+                     const gb200_plunging_table* plunging, gb200_dual_out* out);
+
+/* `nbatch` independent (problem, rays) pairs in one call (every probe round of a transfer-function table over (a, theta)
+   cells, make_transfer_function_table, cunningham-transfer-functions.jl:507-530): one launch per pair on the stream pool,
+   one staged copy each way.  pls: optional array of nbatch plunging-table pointers. */
+int gb200_trace_dual_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* problems, const gb200_dual_ic* ics,
+                           int32_t norm_mode, const gb200_plunging_table* const* pls, gb200_dual_out* outs);
+
 /* ---- device-resident variants (inputs/outputs stay in HBM) ------------- */
 /* Same as gb200_render but `d_images[k]` are DEVICE pointers on ctx's device and no
    host copy is made; work is enqueued on `cuda_stream` (a cudaStream_t cast to

@@ -34,6 +34,7 @@
 #include <cstring>
 #include <algorithm>
 #include <limits>
+#include <type_traits>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -101,6 +102,11 @@ template <class S, int N> Dual<S, N> rcos(const Dual<S, N>& a) {
 template <class S, int N> Dual<S, N> rsqrt_(const Dual<S, N>& a) {
     Dual<S, N> r; r.v = rsqrt_(a.v); S h = S(1) / (S(2) * r.v); for (int i = 0; i < N; ++i) r.d[i] = h * a.d[i]; return r; }
 template <class S, int N> Dual<S, N> rabs(const Dual<S, N>& a) { return (value_of(a) < 0) ? -a : a; }
+// ordering of duals = ordering of their values (ForwardDiff defines <, <=, == on the value alone for control flow)
+template <class S, int N> bool operator<(const Dual<S, N>& a, const Dual<S, N>& b) { return value_of(a) < value_of(b); }
+template <class S, int N> bool operator>(const Dual<S, N>& a, const Dual<S, N>& b) { return value_of(a) > value_of(b); }
+template <class S, int N> bool operator<=(const Dual<S, N>& a, const Dual<S, N>& b) { return value_of(a) <= value_of(b); }
+template <class S, int N> bool operator>=(const Dual<S, N>& a, const Dual<S, N>& b) { return value_of(a) >= value_of(b); }
 template <class S> S sq(const S& x) { return x * x; }
 
 // ------------------------------------------------------------------ metrics
@@ -293,7 +299,7 @@ void lorentz_acceleration(const Metric& m, const T gi[5], const T u[8], T q_mu, 
 
 // geodesic_equation (auto-diff.jl:213-226) wrapped as _second_order_ode_f (geodesic-problem.jl:87-92)
 template <class T>
-void rhs(const Metric& m, const T u[8], T du[8]) {
+void rhs_generic(const Metric& m, const T u[8], T du[8]) {
     T g[5], j1[5], j2[5], gi[5], acc[4];
     metric_jacobian<T>(m, u[1], u[2], g, j1, j2);
     inverse_metric_components<T>(g, gi);
@@ -304,6 +310,45 @@ void rhs(const Metric& m, const T u[8], T du[8]) {
         for (int i = 0; i < 4; ++i) acc[i] = acc[i] + em[i];
     }
     for (int i = 0; i < 4; ++i) { du[i] = u[4 + i]; du[4 + i] = acc[i]; }
+}
+
+#ifdef ORACLE_FAST_KERR
+// TIMING VARIANT ONLY (liboracle_fast.so, bench.py's "port_optimised" CPU baseline; never used by a parity test).
+// Kerr geodesic accelerations in closed form from the Euler-Lagrange equations of
+//   2L = -tdot^2 + (r^2 + a^2) sin^2(th) phdot^2 + w A^2 + (Sigma / Delta) rdot^2 + Sigma thdot^2,
+//   w = 2 M r / Sigma, A = tdot - a sin^2(th) phdot
+// (p_t = -tdot + w A and p_phi = sin^2(th) ((r^2 + a^2) phdot - a w A) are conserved, which gives tddot and phddot).
+// An optimised CPU implementation would evaluate the right-hand side like this instead of differentiating the metric
+// with dual numbers; tests/test_oracle_unit.py checks it against the dual-number form to 1e-12.
+static inline void kerr_rhs_closed(const Metric& m, const double u[8], double du[8]) {
+    const double M = m.M, a = m.a, a2 = a * a;
+    const double r = u[1], td = u[4], rd = u[5], thd = u[6], phd = u[7];
+    double s, c;
+    sincos(u[2], &s, &c);
+    const double s2 = s * s, sin2 = 2.0 * s * c, r2 = r * r, rho2 = r2 + a2;
+    const double Sig = r2 + a2 * c * c, Del = r2 - 2.0 * M * r + a2;
+    const double iSig = 1.0 / Sig, iDel = 1.0 / Del;
+    const double w = 2.0 * M * r * iSig;
+    const double w_r = 2.0 * (M - w * r) * iSig, w_t = w * a2 * sin2 * iSig;
+    const double A = td - a * s2 * phd, U = w * A;
+    const double wdot = w_r * rd + w_t * thd;
+    const double Udot = (rho2 * wdot * A - w * a2 * sin2 * thd * U + 2.0 * a * w * s2 * r * rd * phd) * iDel;
+    const double cot2 = sin2 / s2;
+    du[0] = td; du[1] = rd; du[2] = thd; du[3] = phd;
+    du[4] = Udot;
+    du[5] = Del * iSig * (r * (s2 * phd * phd + thd * thd) + 0.5 * w_r * A * A) - (r * iSig - (r - M) * iDel) * rd * rd + a2 * sin2 * iSig * rd * thd;
+    du[6] = iSig * (0.5 * sin2 * (rho2 * phd * phd - 2.0 * a * U * phd + a2 * (thd * thd - rd * rd * iDel + U * A * iSig)) - 2.0 * r * rd * thd);
+    du[7] = (a * cot2 * thd * U + a * Udot - 2.0 * r * rd * phd) / rho2 - cot2 * thd * phd;
+}
+#endif
+template <class T>
+void rhs(const Metric& m, const T u[8], T du[8]) {
+#ifdef ORACLE_FAST_KERR
+    if constexpr (std::is_same<T, double>::value) {
+        if (m.kind == GB200_METRIC_KERR) { kerr_rhs_closed(m, u, du); return; }
+    }
+#endif
+    rhs_generic<T>(m, u, du);
 }
 
 // constrain_time, auto-diff.jl:161-173 (positive branch)
@@ -894,14 +939,18 @@ T redshift_of(const Metric& m, double r_isco, const gb200_plunging_table* pl, co
             T ut = ge * (T(1) + T(2) * M * (T(1) + H) / r);
             vd[0] = ut; vd[1] = -ur; vd[2] = T(0); vd[3] = uph;
         } else {
-            if (!pl || pl->n < 2) return std::numeric_limits<T>::quiet_NaN();
+            if (!pl || pl->n < 2) return T(std::numeric_limits<double>::quiet_NaN());
             // NaNLinearInterpolator, src/interpolations.jl:7-26, with clamped abscissa
-            double x = std::min(std::max((double)rho, pl->r[0]), pl->r[pl->n - 1]);
+            const double xv = (double)value_of(rho);
+            T xc = rho; // clamped abscissa (a clamped value carries no derivative)
+            if (xv < pl->r[0]) xc = T(pl->r[0]);
+            if (xv > pl->r[pl->n - 1]) xc = T(pl->r[pl->n - 1]);
+            double x = std::min(std::max(xv, pl->r[0]), pl->r[pl->n - 1]);
             int idx = (int)(std::upper_bound(pl->r, pl->r + pl->n, x) - pl->r) - 1;
             idx = std::min(std::max(idx, 0), pl->n - 2);
-            double w = (x - pl->r[idx]) / (pl->r[idx + 1] - pl->r[idx]);
-            auto li = [&](const double* y) { return (1 - w) * y[idx] + w * y[idx + 1]; };
-            vd[0] = T(li(pl->ut)); vd[1] = -T(li(pl->ur)); vd[2] = T(0); vd[3] = T(li(pl->uphi));
+            T w = (xc - T(pl->r[idx])) / T(pl->r[idx + 1] - pl->r[idx]);
+            auto li = [&](const double* y) { return (T(1) - w) * T(y[idx]) + w * T(y[idx + 1]); };
+            vd[0] = li(pl->ut); vd[1] = -li(pl->ur); vd[2] = T(0); vd[3] = li(pl->uphi);
         }
     } else {
         circ_fourvelocity<T>(m, rho, vd);
@@ -1020,6 +1069,264 @@ int run(const gb200_problem& p, const gb200_ic& ic, const gb200_range& rg, int n
     return 0;
 }
 
+// ------------------------------------------------------------------ forward-mode traces (transfer functions)
+// The reference differentiates THROUGH the integrator: `_make_image_plane_mapper` (src/tracing/precision-solvers.jl:73-131)
+// seeds the image-plane offset r with a ForwardDiff.Dual and reads d rho / d r off the end point for its Newton
+// iteration, and `jacobian_∂αβ_∂gr` (:401-451) pushes the two partials of ForwardDiff.jacobian over (alpha, beta)
+// through `tracegeodesics` to get d(rho, g) / d(alpha, beta).  Here the state is Dual<double, N>; time, dt and the
+// error estimate are real numbers.  What DiffEqBase does with duals (un-vendored, restated):
+//   * ODE_DEFAULT_NORM of an array of duals = sqrt(sum(value^2 + partials^2) / (length * (1 + N))), and of one dual
+//     sqrt(value^2 + sum partials^2): the partials are error-controlled with the values (norm_partials = true);
+//     norm_partials = false drops them, which must reproduce the plain trace bit for bit (tests/test_oracle_dual.py);
+//   * control flow (accept test, sign tests of the callbacks) reads values only;
+//   * the ContinuousCallback root find runs on dual-valued condition samples, so the event time it returns carries
+//     partials: to first order the implicit-function derivative -(dc/dp) / (dc/dTheta) along the interpolant.  The
+//     end point therefore moves ALONG the ray with the parameters and stays on the surface; without that term the
+//     partials of rho would be those of a point at fixed affine parameter.
+template <int N>
+static double dual_abs(const Dual<double, N>& x, bool partials) {
+    if (!partials) return std::fabs(x.v);
+    double s = x.v * x.v;
+    for (int i = 0; i < N; ++i) s += x.d[i] * x.d[i];
+    return std::sqrt(s);
+}
+template <int N>
+static Dual<double, N> div_real(const Dual<double, N>& a, double s) { // value = a.v / s exactly as the plain trace divides
+    Dual<double, N> r; r.v = a.v / s; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] / s; return r;
+}
+template <int N>
+static double dual_norm8(const Dual<double, N> a[8], bool partials) {
+    double s = 0;
+    for (int i = 0; i < 8; ++i) {
+        s += a[i].v * a[i].v;
+        if (partials) for (int k = 0; k < N; ++k) s += a[i].d[k] * a[i].d[k];
+    }
+    return std::sqrt(s / (partials ? 8.0 * (1 + N) : 8.0));
+}
+static void interpolant_weights(double Th, double b[7], double db[7]) { // b_j(Theta) and d b_j / d Theta
+    const double R2[7] = {R12, R22, R32, R42, R52, R62, R72}, R3[7] = {R13, R23, R33, R43, R53, R63, R73}, R4[7] = {R14, R24, R34, R44, R54, R64, R74};
+    for (int j = 0; j < 7; ++j) {
+        const double lead = (j == 0) ? R11 : 0.0;
+        b[j] = Th * (lead + Th * (R2[j] + Th * (R3[j] + Th * R4[j])));
+        db[j] = lead + Th * (2.0 * R2[j] + Th * (3.0 * R3[j] + Th * 4.0 * R4[j]));
+    }
+}
+
+template <int N>
+void trace_ray_dual(const gb200_problem& p, const Metric& m, const Dual<double, N> u_init[8], bool norm_partials, RayResult<Dual<double, N>>& res) {
+    typedef Dual<double, N> D;
+    const double abstol = p.abstol, reltol = p.reltol, t0 = p.lambda_min, tstop = p.lambda_max;
+    const double dtmax = (p.dtmax > 0) ? p.dtmax : (tstop - t0);
+    const double dtmin = std::numeric_limits<double>::epsilon();
+    const int64_t maxiters = p.maxiters > 0 ? p.maxiters : 1000000;
+    const double beta1 = 7.0 / 50.0, beta2 = 2.0 / 25.0, gamma = 9.0 / 10.0, qmin = 1.0 / 5.0, qmax = 10.0, qoldinit = 1e-4;
+    D u[8], uprev[8], k[7][8], tmp[8];
+    for (int i = 0; i < 8; ++i) { u[i] = u_init[i]; uprev[i] = u_init[i]; }
+    for (int i = 0; i < 4; ++i) { res.x0[i] = u_init[i]; res.v0[i] = u_init[4 + i]; }
+    res.status = GB200_STATUS_NO_STATUS; res.naccept = 0; res.nreject = 0; res.flags = 0; res.margin = 0;
+    double t = t0, tprev = t0;
+    D f0[8];
+    rhs<D>(m, u, f0);
+    double dt;
+    { // ode_determine_initdt with internalnorm = ODE_DEFAULT_NORM on duals
+        double sk[8];
+        D w[8];
+        for (int i = 0; i < 8; ++i) sk[i] = abstol + dual_abs(u[i], norm_partials) * reltol;
+        for (int i = 0; i < 8; ++i) w[i] = div_real(u[i], sk[i]);
+        double d0 = dual_norm8(w, norm_partials);
+        for (int i = 0; i < 8; ++i) w[i] = div_real(f0[i], sk[i]);
+        double d1 = dual_norm8(w, norm_partials);
+        double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
+        dt0 = std::min(dt0, dtmax);
+        D u1[8], f1[8];
+        for (int i = 0; i < 8; ++i) u1[i] = u[i] + dt0 * f0[i];
+        rhs<D>(m, u1, f1);
+        for (int i = 0; i < 8; ++i) w[i] = div_real(f1[i] - f0[i], sk[i]);
+        double d2 = dual_norm8(w, norm_partials) / dt0;
+        double md = std::max(d1, d2);
+        double dt1 = (md <= 1e-15) ? std::max(1e-6, dt0 * 1e-3) : std::pow(10.0, -(2.0 + std::log10(md)) / 5.0);
+        dt = std::max(dtmin, std::min(std::min(100.0 * dt0, dt1), dtmax));
+    }
+    for (int i = 0; i < 8; ++i) k[0][i] = f0[i];
+    double qold = qoldinit, q11 = 1.0, dtpropose = dt, EEst = 1.0;
+    bool accept = false, terminated = false;
+    int64_t iter = 0;
+    while (t < tstop && !terminated) {
+        if (iter > 0) {
+            if (accept) { for (int i = 0; i < 8; ++i) { uprev[i] = u[i]; k[0][i] = k[6][i]; } dt = dtpropose; }
+            else dt = dt / std::min(1.0 / qmin, q11 / gamma);
+        }
+        ++iter;
+        if (iter > maxiters) { res.flags |= GB200_FLAG_MAXITERS; break; }
+        if (!(dt == dt) || !(u[1].v == u[1].v)) { res.flags |= GB200_FLAG_UNSTABLE; break; }
+        dt = std::min(dt, dtmax);
+        dt = std::max(dt, dtmin);
+        dt = std::min(dt, tstop - t);
+        if (dt <= dtmin && (tstop - t) > dtmin) { res.flags |= GB200_FLAG_DT_MIN; break; }
+        for (int i = 0; i < 8; ++i) tmp[i] = uprev[i] + (dt * A21) * k[0][i];
+        rhs<D>(m, tmp, k[1]);
+        for (int i = 0; i < 8; ++i) tmp[i] = uprev[i] + dt * (A31 * k[0][i] + A32 * k[1][i]);
+        rhs<D>(m, tmp, k[2]);
+        for (int i = 0; i < 8; ++i) tmp[i] = uprev[i] + dt * (A41 * k[0][i] + A42 * k[1][i] + A43 * k[2][i]);
+        rhs<D>(m, tmp, k[3]);
+        for (int i = 0; i < 8; ++i) tmp[i] = uprev[i] + dt * (A51 * k[0][i] + A52 * k[1][i] + A53 * k[2][i] + A54 * k[3][i]);
+        rhs<D>(m, tmp, k[4]);
+        for (int i = 0; i < 8; ++i) tmp[i] = uprev[i] + dt * (A61 * k[0][i] + A62 * k[1][i] + A63 * k[2][i] + A64 * k[3][i] + A65 * k[4][i]);
+        rhs<D>(m, tmp, k[5]);
+        for (int i = 0; i < 8; ++i) u[i] = uprev[i] + dt * (A71 * k[0][i] + A72 * k[1][i] + A73 * k[2][i] + A74 * k[3][i] + A75 * k[4][i] + A76 * k[5][i]);
+        rhs<D>(m, u, k[6]);
+        {
+            D at[8];
+            for (int i = 0; i < 8; ++i) {
+                D ut = dt * (BT1 * k[0][i] + BT2 * k[1][i] + BT3 * k[2][i] + BT4 * k[3][i] + BT5 * k[4][i] + BT6 * k[5][i] + BT7 * k[6][i]);
+                at[i] = div_real(ut, abstol + std::max(dual_abs(uprev[i], norm_partials), dual_abs(u[i], norm_partials)) * reltol);
+            }
+            EEst = dual_norm8(at, norm_partials);
+        }
+        double q;
+        if (EEst == 0.0) q = 1.0 / qmax;
+        else {
+            q11 = ctrl_pow<double>(EEst, beta1, p.pow_mode);
+            q = q11 / ctrl_pow<double>(qold, beta2, p.pow_mode);
+            q = std::max(1.0 / qmax, std::min(1.0 / qmin, q / gamma));
+        }
+        accept = (EEst <= 1.0);
+        if (!accept) { ++res.nreject; continue; }
+        ++res.naccept;
+        double dtnew = dt / q;
+        qold = std::max(EEst, qoldinit);
+        tprev = t;
+        double ttmp = t + dt;
+        {
+            double big = std::max(t, tstop);
+            double epsb = std::nextafter(std::fabs(big), INFINITY) - std::fabs(big);
+            t = (std::fabs(ttmp - tstop) < 100.0 * epsb) ? tstop : ttmp;
+        }
+        dtpropose = std::max(std::min(dtmax, dtnew), dtmin);
+        if (p.geometry_kind != GB200_GEOMETRY_NONE) { // ContinuousCallback: decisions on values
+            double uv[8], kv[7][8];
+            for (int i = 0; i < 8; ++i) uv[i] = uprev[i].v;
+            for (int j = 0; j < 7; ++j) for (int i = 0; i < 8; ++i) kv[j][i] = k[j][i].v;
+            double cprev = disc_condition<double>(p, uprev[1].v, uprev[2].v);
+            double cnext = disc_condition<double>(p, u[1].v, u[2].v);
+            int sprev = (cprev > 0) - (cprev < 0), snext = (cnext > 0) - (cnext < 0);
+            bool event = false;
+            double bottom = tprev, top = t;
+            if (sprev != 0 && sprev * snext <= 0) event = true;
+            else if (sprev != 0) {
+                double last = tprev;
+                for (int i = 2; i <= 8; ++i) {
+                    double abst = (i == 8) ? t : tprev + ((double)(i - 1) * (t - tprev)) / 7.0;
+                    double cnew;
+                    if (i == 8) cnew = cnext;
+                    else { double ui[8]; interpolant<double>((abst - tprev) / dt, dt, uv, kv, ui, 3); cnew = disc_condition<double>(p, ui[1], ui[2]); }
+                    if ((double)sprev * cnew < 0.0) { event = true; bottom = last; top = abst; break; }
+                    last = abst;
+                }
+            }
+            if (event) {
+                auto zf = [&](double abst) -> double {
+                    if (abst == t) return cnext;
+                    if (abst == tprev) return cprev;
+                    double ui[8]; interpolant<double>((abst - tprev) / dt, dt, uv, kv, ui, 3);
+                    return disc_condition<double>(p, ui[1], ui[2]);
+                };
+                double tev;
+                if (zf(top) == 0.0) tev = top;
+                else {
+                    double lo = bottom, hi = top;
+                    for (int it = 0; it < 200; ++it) {
+                        double mid = lo + (hi - lo) / 2.0;
+                        if (!(mid > lo && mid < hi)) break;
+                        double cm = zf(mid);
+                        if (cm == 0.0) { hi = mid; continue; }
+                        if ((cm > 0) == (sprev > 0)) lo = mid; else hi = mid;
+                    }
+                    tev = lo;
+                }
+                const double Th = (tev == t) ? 1.0 : (tev - tprev) / dt;
+                double b[7], db[7];
+                interpolant_weights(Th, b, db);
+                D ue[8];
+                if (tev == t) { for (int i = 0; i < 8; ++i) ue[i] = u[i]; }
+                else for (int i = 0; i < 8; ++i) ue[i] = uprev[i] + dt * (k[0][i] * b[0] + k[1][i] * b[1] + k[2][i] * b[2] + k[3][i] * b[3] + k[4][i] * b[4] + k[5][i] * b[5] + k[6][i] * b[6]);
+                // the event time moves with the parameters: Theta_p = -(dc/dp) / (dc/dTheta) on the interpolant
+                double dudTh[8];
+                for (int i = 0; i < 8; ++i) { double s = 0; for (int j = 0; j < 7; ++j) s += db[j] * k[j][i].v; dudTh[i] = dt * s; }
+                D cD = disc_condition<D>(p, ue[1], ue[2]);
+                Dual<double, 2> rr(ue[1].v), tt(ue[2].v);
+                rr.d[0] = 1.0; tt.d[1] = 1.0;
+                Dual<double, 2> cg = disc_condition<Dual<double, 2>>(p, rr, tt);
+                const double dcdTh = cg.d[0] * dudTh[1] + cg.d[1] * dudTh[2];
+                if (dcdTh != 0.0 && std::isfinite(dcdTh))
+                    for (int kk = 0; kk < N; ++kk) {
+                        const double Thp = -cD.d[kk] / dcdTh;
+                        for (int i = 0; i < 8; ++i) ue[i].d[kk] += dudTh[i] * Thp;
+                    }
+                for (int i = 0; i < 8; ++i) u[i] = ue[i];
+                t = tev;
+                res.status = GB200_STATUS_INTERSECTED_WITH_GEOMETRY;
+                terminated = true;
+            }
+        }
+        if (p.callback_kind == GB200_CALLBACK_UPPER_HEMISPHERE && u[1].v * std::cos(u[2].v) < p.callback_delta) { res.status = GB200_STATUS_OUT_OF_DOMAIN; terminated = true; }
+        if (u[1].v <= p.chart_inner || u[1].v > p.chart_outer) {
+            res.status = (u[1].v <= p.chart_inner) ? GB200_STATUS_WITHIN_INNER_BOUNDARY : GB200_STATUS_OUT_OF_DOMAIN;
+            terminated = true;
+        }
+    }
+    res.lambda = D(t);
+    for (int i = 0; i < 4; ++i) { res.x[i] = u[i]; res.v[i] = u[4 + i]; }
+}
+
+// n rays (alpha_i, beta_i) with N seeded partials each; map_impact_parameters + constrain_all in dual arithmetic
+template <int N>
+int run_dual(const gb200_problem& p, const gb200_dual_ic& ic, int norm_mode, const gb200_plunging_table* pl, gb200_dual_out* out, int nthreads) {
+    typedef Dual<double, N> D;
+    Metric m = make_metric(p.metric_kind, p.metric_params);
+    LnrTransform<double> xfm;
+    xfm.build(m, p.observer);
+    const double r_isco = isco_of(m);
+    const int64_t n = ic.n;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = 0; i < n; ++i) {
+        D al(ic.alpha[i]), be(ic.beta[i]);
+        for (int k = 0; k < N; ++k) { al.d[k] = ic.dalpha[(size_t)k * n + i]; be.d[k] = ic.dbeta[(size_t)k * n + i]; }
+        D x[4], v[4], pm[4];
+        for (int k = 0; k < 4; ++k) x[k] = D(p.observer[k]);
+        local_momentum<D>(x[1], al, be, pm);
+        for (int a = 0; a < 4; ++a) { D s(0.0); for (int b = 0; b < 4; ++b) s = s + xfm.A[a][b] * pm[b]; v[a] = s; }
+        D g[5];
+        metric_components<D>(m, x[1], x[2], g);
+        v[0] = constrain_time<D>(g, v, D(p.mu));
+        D u0[8];
+        for (int k = 0; k < 4; ++k) { u0[k] = x[k]; u0[4 + k] = v[k]; }
+        gb200_problem pray = p;
+        if (ic.height) pray.geometry_params[0] = ic.height[i];
+        RayResult<D> res;
+        trace_ray_dual<N>(pray, m, u0, norm_mode == GB200_DUAL_NORM_WITH_PARTIALS, res);
+        if (out->status) out->status[i] = res.status;
+        if (out->lambda_max) out->lambda_max[i] = res.lambda.v;
+        for (int k = 0; k < 4; ++k) { if (out->x[k]) out->x[k][i] = res.x[k].v; if (out->v[k]) out->v[k][i] = res.v[k].v; }
+        if (out->naccept) out->naccept[i] = res.naccept;
+        if (out->nreject) out->nreject[i] = res.nreject;
+        if (out->flags) out->flags[i] = res.flags;
+        D rho = res.x[1] * rsin(res.x[2]); // _equatorial_project(gp.x), whatever the status (precision-solvers.jl:124)
+        if (out->rho) out->rho[i] = rho.v;
+        if (out->drho) for (int k = 0; k < N; ++k) out->drho[(size_t)k * n + i] = rho.d[k];
+        if (out->g) {
+            const bool hit = res.status == GB200_STATUS_INTERSECTED_WITH_GEOMETRY;
+            D g_ = hit ? redshift_of<D>(m, r_isco, pl, res) : D(std::numeric_limits<double>::quiet_NaN());
+            out->g[i] = g_.v;
+            if (out->dg) for (int k = 0; k < N; ++k) out->dg[(size_t)k * n + i] = hit ? g_.d[k] : std::numeric_limits<double>::quiet_NaN();
+        }
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------ grazing-band analysis
 // The reference detects the disc by sampling the condition at step ends and at 7 interior points of the dense
 // output (DiffEqBase interp_points = 8).  A ray whose path through the region {condition < 0} is shorter than the
@@ -1119,6 +1426,13 @@ int oracle_rhs(int kind, const double* mp, const double* u8, double* du8) {
     orc::rhs<double>(m, u8, du8);
     return 0;
 }
+int oracle_is_fast_variant(void) {
+#ifdef ORACLE_FAST_KERR
+    return 1;
+#else
+    return 0;
+#endif
+}
 int oracle_lnrbasis(int kind, const double* mp, double r, double th, double* basis16, double* frame16) {
     orc::Metric m = orc::make_metric(kind, mp);
     double gc[5], g[4][4];
@@ -1194,6 +1508,12 @@ int oracle_trace_to(const gb200_problem* p, int64_t n, const double* u0 /* n x 8
         for (int k = 0; k < 4; ++k) { u_out[8 * i + k] = res.x[k]; u_out[8 * i + 4 + k] = res.v[k]; }
     }
     return 0;
+}
+// forward-mode traces: npartials = 1 (Newton derivative of the offset search) or 2 (Jacobian over alpha, beta)
+int oracle_trace_dual(const gb200_problem* p, const gb200_dual_ic* ic, int norm_mode, const gb200_plunging_table* pl, gb200_dual_out* out, int nthreads) {
+    if (ic->npartials == 1) return orc::run_dual<1>(*p, *ic, norm_mode, pl, out, nthreads);
+    if (ic->npartials == 2) return orc::run_dual<2>(*p, *ic, norm_mode, pl, out, nthreads);
+    return -1;
 }
 int oracle_max_threads(void) {
 #ifdef _OPENMP

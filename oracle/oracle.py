@@ -19,7 +19,7 @@ _lib = None
 
 def build(force=False):
     src = os.path.join(_HERE, "gradus_oracle.cpp")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+    if force or not os.path.exists(LIB) or not os.path.exists(os.path.join(_HERE, "liboracle_fast.so")) or os.path.getmtime(LIB) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return LIB
 
@@ -31,6 +31,40 @@ def lib():
             build()
         _lib = C.CDLL(LIB)
     return _lib
+
+
+LIB_FAST = os.path.join(_HERE, "liboracle_fast.so")
+_lib_fast = None
+
+
+def lib_fast():
+    """The timing variant (-O3, FMA, closed-form Kerr right-hand side): bench.py's "port_optimised" baseline only."""
+    global _lib_fast
+    if _lib_fast is None:
+        if not os.path.exists(LIB_FAST):
+            build(force=True)
+        _lib_fast = C.CDLL(LIB_FAST)
+        assert _lib_fast.oracle_is_fast_variant() == 1
+    return _lib_fast
+
+
+def render_fast(problem, ic, pointfns, rng=None, nthreads=0):
+    """`render` through the timing variant (no end points, no plunging table)."""
+    rng = _range(ic, rng)
+    pfs = np.asarray(pointfns, np.int32)
+    imgs = np.zeros((len(pfs), rng.count))
+    ptrs = (cabi._dp * len(pfs))(*[cabi.dptr(imgs[k]) for k in range(len(pfs))])
+    rc = lib_fast().oracle_render(C.byref(problem), C.byref(ic), C.byref(rng), nthreads, 0, cabi.iptr(pfs), len(pfs), None, ptrs, None)
+    assert rc == 0
+    return imgs
+
+
+def rhs_fast(kind, params, u):
+    u = np.ascontiguousarray(u, np.float64)
+    du = np.zeros(8)
+    mp = _mp(params)
+    lib_fast().oracle_rhs(kind, cabi.dptr(mp), cabi.dptr(u), cabi.dptr(du))
+    return du
 
 
 def max_threads():
@@ -76,6 +110,14 @@ def lineprofile(problem, ic, emis, bins, opts, rng=None, nthreads=0, precision=0
                                   C.byref(opts), cabi.dptr(flux), C.byref(out.c) if out is not None else None)
     assert rc == 0
     return (flux, out) if endpoints else flux
+
+
+def trace_dual(problem, arrays, norm_mode=0, plunging=None, nthreads=0):
+    """Forward-mode trace of `arrays` (a gradus_b200._cabi.DualArrays): fills its outputs and returns it."""
+    rc = lib().oracle_trace_dual(C.byref(problem), C.byref(arrays.ic), norm_mode, C.byref(plunging) if plunging is not None else None,
+                                 C.byref(arrays.out), nthreads)
+    assert rc == 0
+    return arrays
 
 
 def _mp(params):

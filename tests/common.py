@@ -57,6 +57,11 @@ class OracleProber(gb.DeviceProber):
         p, ic = config.to_c()
         return api.GeodesicPoints(oracle.trace(p, ic), config.lambda_domain[0])
 
+    def evaluate_dual(self, config, arrays, norm_mode):
+        from oracle import oracle
+        p, _ = config.to_c()
+        return oracle.trace_dual(p, arrays, norm_mode)
+
 
 def oracle_plunging_table(kind, mp):
     """interpolate_plunging_velocities (src/orbits/orbit-solving.jl:137-167) restated with the oracle's pieces."""

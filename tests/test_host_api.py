@@ -42,6 +42,8 @@ int main(void) {
          sizeof(gb200_emissivity), sizeof(gb200_plunging_table), sizeof(gb200_lineprofile_opts), sizeof(gb200_stats),
          offsetof(gb200_problem, maxiters));
   printf("%zu %zu %zu %zu\n", offsetof(gb200_ic, x), offsetof(gb200_ic, n), offsetof(gb200_endpoints, naccept), offsetof(gb200_problem, gtol));
+  printf("%zu %zu %zu %zu %zu\n", sizeof(gb200_dual_ic), sizeof(gb200_dual_out), offsetof(gb200_dual_ic, alpha), offsetof(gb200_dual_out, g),
+         offsetof(gb200_dual_out, flags));
   return 0; }'''
     with tempfile.TemporaryDirectory() as d:
         cfile = os.path.join(d, "l.c")
@@ -52,7 +54,8 @@ int main(void) {
     sizes = [int(v) for v in out]
     want = [C.sizeof(cabi.Problem), C.sizeof(cabi.IC), C.sizeof(cabi.Range), C.sizeof(cabi.Endpoints), C.sizeof(cabi.Emissivity),
             C.sizeof(cabi.PlungingTable), C.sizeof(cabi.LineProfileOpts), C.sizeof(cabi.Stats), cabi.Problem.maxiters.offset,
-            cabi.IC.x.offset, cabi.IC.n.offset, cabi.Endpoints.naccept.offset, cabi.Problem.gtol.offset]
+            cabi.IC.x.offset, cabi.IC.n.offset, cabi.Endpoints.naccept.offset, cabi.Problem.gtol.offset,
+            C.sizeof(cabi.DualIC), C.sizeof(cabi.DualOut), cabi.DualIC.alpha.offset, cabi.DualOut.g.offset, cabi.DualOut.flags.offset]
     assert sizes == want
 
 
