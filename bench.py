@@ -350,24 +350,30 @@ def run_callers(ens):
     pr = gb.DeviceProber(m, x, d, chart=gb.chart_for_metric(m, 2e5, closest_approach=1.005), ensemble=ens)
     radii = np.geomspace(gb.isco(m) + 1e-2, 1000.0, 150)
     tf.cunningham_transfer_functions(m, x, d, radii[::10], prober=pr)
-    pr.launches = pr.rays = 0
-    t0 = time.perf_counter()
-    tf.cunningham_transfer_functions(m, x, d, radii, prober=pr)
-    dt = time.perf_counter() - t0
-    out = {"transfer_functions": {"workload": "Kerr a=0.998, observer r=1e5 at 30deg, 150 emission radii x 114 samples (N=80 + 2x17)",
-                                  "seconds": dt, "radii_per_s": len(radii) / dt, "launches": pr.launches, "rays": pr.rays}}
+    out = {}
+    # "exact": the reference's own iteration (every offset search from max(20, r_e), all max_iter trials at the noise floor);
+    # "fast": golden-section probes warm-started, noise-floor pairs stopped after 6 trials without progress (same roots to
+    # zero_atol / the same acceptance rule; fewer sequential launches)
+    for mode, kw in (("transfer_functions", {}), ("transfer_functions_fast", {"warm_start": True, "stall_exit": 6})):
+        pr.launches = pr.rays = 0
+        t0 = time.perf_counter()
+        tf.cunningham_transfer_functions(m, x, d, radii, prober=pr, **kw)
+        dt = time.perf_counter() - t0
+        out[mode] = {"workload": "Kerr a=0.998, observer r=1e5 at 30deg, 150 emission radii x 114 samples (N=80 + 2x17), forward-mode traces at 1e-9",
+                     "seconds": dt, "radii_per_s": len(radii) / dt, "launches": pr.launches, "rays": pr.rays, "options": kw}
     # BASELINE config 4, transfer-function half: an (a, theta) table, all cells in lock step (gb200_render_batch)
     cells = [(a, th) for a in np.linspace(0.0, 0.998, 8) for th in np.linspace(10.0, 80.0, 8)]
     metrics = [gb.KerrMetric(1.0, a) for a, _ in cells]
     observers = [[0.0, 10_000.0, math.radians(th), 0.0] for _, th in cells]
     radii_of = lambda mm: 1.0 / np.linspace(1.0 / 500.0, 1.0 / (gb.isco(mm) + 1e-2), 50)[::-1]
-    tf.transfer_function_table(metrics[:2], observers[:2], d, radii_of, ensemble=ens)
+    fast = tf.TransferFunctionSetup(warm_start=True, stall_exit=6)
+    tf.transfer_function_table(metrics[:2], observers[:2], d, radii_of, ensemble=ens, setup=fast)
     t0 = time.perf_counter()
-    table = tf.transfer_function_table(metrics, observers, d, radii_of, ensemble=ens)
+    table = tf.transfer_function_table(metrics, observers, d, radii_of, ensemble=ens, setup=fast)
     dt = time.perf_counter() - t0
     nctf = sum(len(row) for row in table)
     out["transfer_function_table"] = {"workload": "Kerr, 8 spins x 8 inclinations, observer r=1e4, 50 emission radii x 114 samples per cell, "
-                                                  "every probe round of all cells in one gb200_render_batch call",
+                                                  "every probe round of all cells in one gb200_trace_dual_batch call (warm_start, stall_exit = 6)",
                                       "seconds": dt, "transfer_functions": nctf, "transfer_functions_per_s": nctf / dt}
     disc = gb.ThinDisc(0.0, 1000.0)
     grid = [(gb.KerrMetric(1.0, a), disc, corona.LampPostModel(h=h)) for a in np.linspace(0.0, 0.998, 10) for h in np.geomspace(2.5, 50.0, 10)]

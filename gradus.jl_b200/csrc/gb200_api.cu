@@ -39,6 +39,11 @@ struct gb200_ctx {
     std::vector<cudaEvent_t> chunk_events;  // pipelined gb200_render: one per chunk
     void* stage = nullptr;                  // pinned host staging for gb200_trace_batch
     size_t stage_cap = 0;
+    // An asynchronous call (gb200_render_device / gb200_lineprofile_device with async != 0) returns while its kernels still
+    // use the context's work queue and pool buffers: it records `inflight` at its end, and every entry point makes the
+    // stream it works on wait for that event before touching the queue or the pool.
+    cudaEvent_t inflight = nullptr;
+    bool have_inflight = false;
 };
 
 static int fail(gb200_ctx* ctx, int code, const char* fmt, ...) {
@@ -118,6 +123,19 @@ static int generic_isco_host(int kind, const double* mp, double* out) {
         if ((fm > 0) == (flo > 0)) { lo = mid; flo = fm; } else hi = mid;
     }
     *out = lo + (hi - lo) / 2;
+    return GB200_OK;
+}
+
+// Start of every entry point that uses the context's queue / pool on `stream`: order it after an earlier asynchronous call.
+static int begin_call(gb200_ctx* ctx, cudaStream_t stream) {
+    { int rc_ = begin_call(ctx, stream); if (rc_) return rc_; }
+    if (ctx->have_inflight) CU(ctx, cudaStreamWaitEvent(stream, ctx->inflight, 0));
+    return GB200_OK;
+}
+// End of an asynchronous call: later calls (on any stream) wait for the work enqueued so far.
+static int end_async_call(gb200_ctx* ctx, cudaStream_t stream) {
+    CU(ctx, cudaEventRecord(ctx->inflight, stream));
+    ctx->have_inflight = true;
     return GB200_OK;
 }
 
@@ -474,6 +492,7 @@ int gb200_init(int device, gb200_ctx** out) {
     CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(nullptr, cudaEventCreate(&ctx->ev0)); CU(nullptr, cudaEventCreate(&ctx->ev1));
     CU(nullptr, cudaEventCreate(&ctx->ev2)); CU(nullptr, cudaEventCreate(&ctx->ev3));
+    CU(nullptr, cudaEventCreateWithFlags(&ctx->inflight, cudaEventDisableTiming));
     CU(nullptr, cudaMalloc(&ctx->d_queue, 4 * sizeof(unsigned long long)));
     *out = ctx;
     return GB200_OK;
@@ -487,6 +506,7 @@ void gb200_destroy(gb200_ctx* ctx) {
     for (auto st : ctx->pool_streams) cudaStreamDestroy(st);
     for (auto ev : ctx->chunk_events) cudaEventDestroy(ev);
     if (ctx->stage) cudaFreeHost(ctx->stage);
+    if (ctx->inflight) cudaEventDestroy(ctx->inflight);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -527,9 +547,7 @@ int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, cons
     int rc = validate(ctx, p, ic); if (rc) return rc;
     rc = validate_range(ctx, ic, rg); if (rc) return rc;
     if (!out) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null endpoints");
-    CU(ctx, cudaSetDevice(ctx->device));
-    ctx->stats = gb200_stats{};
-    ctx->cur = ctx->stream;
+    { int rc_ = begin_call(ctx, ctx->stream); if (rc_) return rc_; }
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     GbParams P;
     fill_params(p, ic, rg, P);
@@ -612,9 +630,7 @@ int gb200_trace_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* probl
         rc = validate_range(ctx, &ics[b], &ranges[b]); if (rc) return rc;
         if (ics[b].kind == GB200_IC_IMPACT_PARAMETERS) return fail(ctx, GB200_ERR_UNSUPPORTED, "impact-parameter lists are not batched; use gb200_trace / gb200_render");
     }
-    CU(ctx, cudaSetDevice(ctx->device));
-    ctx->stats = gb200_stats{};
-    ctx->cur = ctx->stream;
+    { int rc_ = begin_call(ctx, ctx->stream); if (rc_) return rc_; }
     const int nstreams = nbatch < 32 ? nbatch : 32;
     while ((int)ctx->pool_streams.size() < nstreams) {
         cudaStream_t st;
@@ -732,9 +748,7 @@ int gb200_trace_path(gb200_ctx* ctx, const gb200_problem* p, const double* u0, i
     ic.kind = GB200_IC_EXPLICIT; ic.n = 1;
     for (int k = 0; k < 4; ++k) { ic.x[k] = u0 + k; ic.v[k] = u0 + 4 + k; }
     int rc = validate(ctx, p, &ic); if (rc) return rc;
-    CU(ctx, cudaSetDevice(ctx->device));
-    ctx->stats = gb200_stats{};
-    ctx->cur = ctx->stream;
+    { int rc_ = begin_call(ctx, ctx->stream); if (rc_) return rc_; }
     gb200_range rg{0, 1, 1};
     GbParams P;
     fill_params(p, &ic, &rg, P);
@@ -818,9 +832,7 @@ static int render_common(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic*
         if (pfs[k] < GB200_PF_SHADOW || pfs[k] > GB200_PF_RADIUS) return fail(ctx, GB200_ERR_UNSUPPORTED, "point function %d", pfs[k]);
         if (!images[k]) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null image pointer");
     }
-    CU(ctx, cudaSetDevice(ctx->device));
-    ctx->stats = gb200_stats{};
-    ctx->cur = stream;
+    { int rc_ = begin_call(ctx, stream); if (rc_) return rc_; }
     CU(ctx, cudaEventRecord(ctx->ev0, stream));
     GbParams P;
     fill_params(p, ic, rg, P);
@@ -849,7 +861,7 @@ static int render_common(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic*
     if (!device_out)
         for (int k = 0; k < npf; ++k)
             if (n) CU(ctx, cudaMemcpyAsync(images[k], P.o_img[k], n * sizeof(double), cudaMemcpyDeviceToHost, stream));
-    if (async) { ctx->stats.rays = rg->count; return GB200_OK; }
+    if (async) { ctx->stats.rays = rg->count; return end_async_call(ctx, stream); }
     return finish_stats(ctx, rg->count);
 }
 
@@ -877,9 +889,7 @@ int gb200_render_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* prob
         if (ics[b].kind == GB200_IC_EXPLICIT) return fail(ctx, GB200_ERR_UNSUPPORTED, "explicit initial conditions are batched by gb200_trace_batch");
         for (int k = 0; k < npf; ++k) if (ranges[b].count && !images[(size_t)b * npf + k]) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null image pointer");
     }
-    CU(ctx, cudaSetDevice(ctx->device));
-    ctx->stats = gb200_stats{};
-    ctx->cur = ctx->stream;
+    { int rc_ = begin_call(ctx, ctx->stream); if (rc_) return rc_; }
     const int nstreams = nbatch < 32 ? nbatch : 32;
     while ((int)ctx->pool_streams.size() < nstreams) {
         cudaStream_t st;
@@ -995,9 +1005,7 @@ int gb200_trace_dual_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* 
         int rc = validate(ctx, &problems[b], &f); if (rc) return rc;
         if (d.height && problems[b].geometry_kind != GB200_GEOMETRY_DATUM_PLANE) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "per-ray heights need GB200_GEOMETRY_DATUM_PLANE");
     }
-    CU(ctx, cudaSetDevice(ctx->device));
-    ctx->stats = gb200_stats{};
-    ctx->cur = ctx->stream;
+    { int rc_ = begin_call(ctx, ctx->stream); if (rc_) return rc_; }
     const int nstreams = nbatch < 32 ? nbatch : 32;
     while ((int)ctx->pool_streams.size() < nstreams) {
         cudaStream_t st;
@@ -1141,9 +1149,7 @@ static int lineprofile_common(gb200_ctx* ctx, const gb200_problem* p, const gb20
     rc = validate_range(ctx, ic, rg); if (rc) return rc;
     if (!em || !bins || !opts || !flux || nbins < 1 || nbins > 8192) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad line-profile arguments (1 <= nbins <= 8192)");
     for (int b = 1; b < nbins; ++b) if (!(bins[b] > bins[b - 1])) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bins must be strictly increasing");
-    CU(ctx, cudaSetDevice(ctx->device));
-    ctx->stats = gb200_stats{};
-    ctx->cur = stream;
+    { int rc_ = begin_call(ctx, stream); if (rc_) return rc_; }
     CU(ctx, cudaEventRecord(ctx->ev0, stream));
     GbParams P;
     fill_params(p, ic, rg, P);
@@ -1172,7 +1178,7 @@ static int lineprofile_common(gb200_ctx* ctx, const gb200_problem* p, const gb20
         for (int b = 0; b < nbins; ++b) tot += h[(size_t)b];
         for (int b = 0; b < nbins; ++b) flux[b] = opts->normalise ? h[(size_t)b] / tot : h[(size_t)b]; // flux ./ sum(flux), line-profiles.jl:197
     }
-    if (async) { ctx->stats.rays = rg->count; return GB200_OK; }
+    if (async) { ctx->stats.rays = rg->count; return end_async_call(ctx, stream); }
     return finish_stats(ctx, rg->count);
 }
 
@@ -1191,7 +1197,7 @@ int gb200_lineprofile_device(gb200_ctx* ctx, const gb200_problem* p, const gb200
 int gb200_debug_rhs(gb200_ctx* ctx, int32_t metric_kind, const double* mp, int64_t n, const double* u, double* du) {
     if (!ctx || !mp || !u || !du || n < 1) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad arguments");
     if (metric_kind < 0 || metric_kind >= GB200_METRIC_COUNT) return fail(ctx, GB200_ERR_UNSUPPORTED, "metric kind %d", metric_kind);
-    CU(ctx, cudaSetDevice(ctx->device));
+    { int rc_ = begin_call(ctx, ctx->stream); if (rc_) return rc_; }
     GbParams P;
     memset(&P, 0, sizeof P);
     P.metric_kind = metric_kind; P.M = mp[0]; P.a = mp[1]; P.eps3 = mp[2];
@@ -1209,7 +1215,7 @@ int gb200_debug_rhs(gb200_ctx* ctx, int32_t metric_kind, const double* mp, int64
 
 int gb200_debug_math(gb200_ctx* ctx, int64_t n, const double* x, double* out5) {
     if (!ctx || !x || !out5 || n < 1) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad arguments");
-    CU(ctx, cudaSetDevice(ctx->device));
+    { int rc_ = begin_call(ctx, ctx->stream); if (rc_) return rc_; }
     void *d_x, *d_o;
     int rc = pool_get(ctx, SL_X0, sizeof(double) * (size_t)n, &d_x); if (rc) return rc;
     rc = pool_get(ctx, SL_V0, sizeof(double) * 5 * (size_t)n, &d_o); if (rc) return rc;
@@ -1222,7 +1228,7 @@ int gb200_debug_math(gb200_ctx* ctx, int64_t n, const double* x, double* out5) {
 
 int gb200_fp64_peak(gb200_ctx* ctx, double* tflops_out) {
     if (!ctx || !tflops_out) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null argument");
-    CU(ctx, cudaSetDevice(ctx->device));
+    { int rc_ = begin_call(ctx, ctx->stream); if (rc_) return rc_; }
     void* d;
     int rc = pool_get(ctx, SL_SCRATCH, 64, &d); if (rc) return rc;
     const int blocks = ctx->sm_count * 8, iters = 20000;
@@ -1245,7 +1251,7 @@ int gb200_fp64_peak(gb200_ctx* ctx, double* tflops_out) {
 
 int gb200_fp64_issue_probe(gb200_ctx* ctx, int32_t mix, double* tflops_out) {
     if (!ctx || !tflops_out || mix < 0 || mix > 5) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad argument");
-    CU(ctx, cudaSetDevice(ctx->device));
+    { int rc_ = begin_call(ctx, ctx->stream); if (rc_) return rc_; }
     void* d;
     int rc = pool_get(ctx, SL_SCRATCH, 64, &d); if (rc) return rc;
     const int blocks = ctx->sm_count * 8, iters = 20000;

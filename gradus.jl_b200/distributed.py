@@ -42,9 +42,16 @@ def strip_interleaved_range(ic, rank, world, columns=4) -> cabi.Range:
     Balances like ray interleaving but keeps neighbouring rays on the same GPU and in the same warp, which is worth
     up to 15 % of kernel time at 8 ranks (profiles/r01_tuning_log.md).  Falls back to ray interleaving when the image
     does not divide into strips."""
-    h = ic.height if ic.kind == cabi.IC_RENDER_GRID else ic.width
+    if ic.kind in (cabi.IC_EXPLICIT, cabi.IC_IMPACT_PARAMETERS):
+        return interleaved_range(ic.n, rank, world)  # ray lists have no image structure
+    if ic.kind == cabi.IC_RENDER_GRID:
+        h = ic.height
+    elif ic.kind == cabi.IC_CARTESIAN_PLANE:
+        h = 2 * (ic.height // 2) - 1  # fastest-varying extent of the mirrored grid (fill_params, gb200_api.cu)
+    else:
+        h = ic.width
     strip = columns * h
-    if ic.kind == cabi.IC_EXPLICIT or ic.n % strip != 0:
+    if strip <= 0 or ic.n % strip != 0:
         return interleaved_range(ic.n, rank, world)
     nstrips = ic.n // strip
     mine = (nstrips - rank + world - 1) // world if nstrips > rank else 0

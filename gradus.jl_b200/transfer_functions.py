@@ -249,6 +249,16 @@ class TransferFunctionSetup:
     h: float = 1e-6
     max_iter: int = 50
     contrapoint_bias: float = 2.0
+    # False: every offset search starts from max(20, rₑ) like the reference's (`initial_r`, precision-solvers.jl:141).
+    # True: a golden-section probe starts from the offset its predecessor converged to (the angle moved by < 0.2 rad), which
+    # cuts its Newton iteration from ~20 trials to ~4 and with it the number of sequential launches of a table; the roots
+    # satisfy the same |ρ − rₑ| ≤ zero_atol, the iteration path -- and hence the last digits of g -- differ.
+    warm_start: bool = False
+    # 0: a Newton iteration that cannot reach zero_atol runs all `max_iter` trials like the reference's (about 5 % of the
+    # pairs sit at the noise floor of ρ(x), |y| ≈ 1e-6: the trace's own error at 1e-9 from r = 1e5, and are accepted by the
+    # |y| ≤ 1e-4 rₑ rule in the end).  n > 0: such a pair stops after n trials without a new smallest |y| -- the same
+    # acceptance rule, 40 fewer sequential launches for whoever waits for that pair.
+    stall_exit: int = 0
     # origin of the polar coordinates on the image plane (`_rθ_to_αβ`, precision-solvers.jl:1-7)
     alpha0: float = 0.0
     beta0: float = 0.0
@@ -262,121 +272,247 @@ def theta_samples(setup: TransferFunctionSetup) -> np.ndarray:
                            np.linspace(math.pi - o, math.pi + o, K)])
 
 
-def _bracket_offsets(step_y, lo, hi, atol, max_halvings=80):
-    """`find_zero(f, (contra, x), atol = zero_atol)` (Roots.jl bisection on a bracketing interval) for a batch of
-    independent intervals: `step_y(idx, x)` evaluates ρ(x) − rₑ for the problems `idx`.  Returns the roots, NaN where the
-    end points do not bracket a sign change (Roots.jl raises there)."""
-    n = lo.size
-    idx = np.arange(n)
-    flo, fhi = step_y(idx, lo), step_y(idx, hi)
-    root = np.where(np.abs(flo) <= np.abs(fhi), lo, hi).astype(np.float64)
-    best = np.minimum(np.abs(flo), np.abs(fhi))
-    ok = np.sign(flo) * np.sign(fhi) < 0
-    root[~ok & (best > atol)] = np.nan
-    active = ok & (best > atol)
-    lo, hi, flo = lo.copy(), hi.copy(), flo.copy()
-    for _ in range(max_halvings):
-        k = np.nonzero(active)[0]
-        if k.size == 0:
-            break
-        mid = 0.5 * (lo[k] + hi[k])
-        fm = step_y(k, mid)
-        better = np.abs(fm) < best[k]
-        root[k[better]], best[k[better]] = mid[better], np.abs(fm[better])
-        same = np.sign(fm) == np.sign(flo[k])
-        lo[k] = np.where(same, mid, lo[k])
-        flo[k] = np.where(same, fm, flo[k])
-        hi[k] = np.where(same, hi[k], mid)
-        active[k] = (np.abs(fm) > atol) & (hi[k] - lo[k] > 4 * np.finfo(float).eps * np.abs(mid))
-    return root
+# phases of one (r_target, θ) pair inside `OffsetEngine`
+_INIT, _NEWTON, _REDO, _BR_LO, _BR_MID, _FINAL, _DONE = range(7)
+
+
+class OffsetEngine:
+    """`_find_offset_for_radius` (precision-solvers.jl:133-241) as a batch of independent state machines, one per
+    (r_target, θ) pair: the image-plane offset x with ρ(x cos θ, x sin θ) = r_target.  The iteration is the reference's,
+    pair by pair -- Newton steps x − y / y′ with y′ = dρ/dx read off a dual number pushed through the trace, a contrapoint
+    inside the hole that pulls overshoots back (`contrapoint_bias`), the "converge failed" exit, cycle detection on the
+    relative decrease with a bracketing finish (`find_zero(f, (contra, x), atol)`), the late bracketing after `max_iter`
+    -- but every pair advances on its own: one `round()` evaluates the next trial offset of EVERY unfinished pair in a
+    single launch, whatever phase each is in, and pairs can be added between rounds.  A straggler (a pair that sits at
+    the noise floor of ρ(x) for all `max_iter` iterations, or bisects for 60 halvings) therefore costs rounds only to
+    whoever waits for that very pair."""
+
+    def __init__(self, prober, setup):
+        self.prober, self.setup = prober, setup
+        self.n = 0
+        cap = 1024
+        f = lambda fill=0.0, dt=np.float64, shape=(): np.full((cap,) + shape, fill, dt)
+        self.a = dict(rt=f(), ct=f(), st=f(), hgt=f(), grp=f(0, np.int64), rmin=f(), x=f(), y=f(), df=f(), contra=f(), dy=f(),
+                      prev=f(0.0, np.float64, (6,)), it=f(0, np.int64), phase=f(_DONE, np.int64), trial=f(), lo=f(), hi=f(), flo=f(),
+                      fhi=f(), best=f(), root=f(), halvings=f(0, np.int64), ymin=f(np.inf), stalled=f(0, np.int64),
+                      g=f(np.nan), rho=f(np.nan), t=f(np.nan), status=f(-1, np.int32), lam=f(np.nan), px=f(np.nan, np.float64, (4,)),
+                      alpha=f(np.nan), beta=f(np.nan))
+        self.has_height = False
+        self.has_group = False
+        self.rounds = 0
+
+    def _grow(self, need):
+        cap = self.a["rt"].shape[0]
+        if need <= cap:
+            return
+        new = max(need, 2 * cap)
+        for k, v in self.a.items():
+            w = np.empty((new,) + v.shape[1:], v.dtype)
+            w[:cap] = v
+            if k == "phase":
+                w[cap:] = _DONE
+            self.a[k] = w
+
+    def add(self, r_target, theta, height=None, group=None, r_min=0.0, initial_r=None):
+        """New pairs; returns their ids."""
+        r_target = np.atleast_1d(np.asarray(r_target, np.float64))
+        theta = np.atleast_1d(np.asarray(theta, np.float64))
+        m = r_target.size
+        ids = np.arange(self.n, self.n + m)
+        self._grow(self.n + m)
+        A = self.a
+        A["rt"][ids], A["ct"][ids], A["st"][ids] = r_target, np.cos(theta), np.sin(theta)
+        A["rmin"][ids] = r_min
+        if height is not None:
+            A["hgt"][ids] = height
+            self.has_height = True
+        if group is not None:
+            A["grp"][ids] = group
+            self.has_group = True
+        A["x"][ids] = np.maximum(20.0, r_target) if initial_r is None else initial_r
+        A["trial"][ids] = A["x"][ids]
+        for k in ("contra", "dy", "y", "df"):
+            A[k][ids] = 0.0
+        A["prev"][ids] = 0.0
+        A["it"][ids] = 0
+        A["halvings"][ids] = 0
+        A["ymin"][ids] = np.inf
+        A["stalled"][ids] = 0
+        A["phase"][ids] = _INIT
+        self.n += m
+        return ids
+
+    def pending(self):
+        return bool(np.any(self.a["phase"][: self.n] != _DONE))
+
+    def _finish_loop(self, ids):
+        """After the Newton loop of `ids` ended (converged or out of iterations): the late bracketing, or done."""
+        A, s = self.a, self.setup
+        late = (A["it"][ids] >= s.max_iter) & (A["y"][ids] > 10.0)
+        L, D = ids[late], ids[~late]
+        A["lo"][L], A["hi"][L], A["fhi"][L] = A["contra"][L], A["x"][L], A["y"][L]
+        A["trial"][L] = A["lo"][L]
+        A["phase"][L] = _BR_LO
+        A["phase"][D] = _DONE
+        return D
+
+    def round(self):
+        """One launch: the next trial offset of every unfinished pair.  Returns the ids that finished in this round."""
+        A, s = self.a, self.setup
+        atol, bias = s.zero_atol, s.contrapoint_bias
+        act = np.nonzero(A["phase"][: self.n] != _DONE)[0]
+        if act.size == 0:
+            return act
+        self.rounds += 1
+        xr = A["trial"][act]
+        al, be = xr * A["ct"][act] + s.alpha0, xr * A["st"][act] + s.beta0
+        kw = {}
+        if self.has_height:
+            kw["height"] = A["hgt"][act]
+        if self.has_group:
+            kw["group"] = A["grp"][act]
+        res = self.prober.dual(al, be, A["ct"][act][None, :], A["st"][act][None, :], **kw)
+        A["g"][act], A["rho"][act], A["t"][act], A["status"][act] = res.g, res.rho, res.x[0], res.status
+        A["lam"][act], A["px"][act], A["alpha"][act], A["beta"][act] = res.lambda_max, res.x.T, al, be
+        fy = res.rho - A["rt"][act]  # y of the reference's `step`
+        ph = A["phase"][act].copy()
+        done = []
+
+        # ---- first evaluation
+        I = act[ph == _INIT]
+        if I.size:
+            A["y"][I], A["df"][I] = fy[ph == _INIT], res.drho[0][ph == _INIT]
+            conv = np.abs(A["y"][I]) <= atol
+            A["phase"][I[conv]] = _DONE
+            done.append(I[conv])
+            G = I[~conv]
+            A["phase"][G] = _NEWTON
+            with np.errstate(all="ignore"):
+                A["trial"][G] = A["x"][G] - A["y"][G] / A["df"][G]
+
+        # ---- a Newton trial (or its contrapoint replacement) came back
+        for code in (_NEWTON, _REDO):
+            sel = ph == code
+            K = act[sel]
+            if K.size == 0:
+                continue
+            next_x, next_y = A["trial"][K].copy(), fy[sel]
+            A["df"][K] = res.drho[0][sel]
+            proceed = np.ones(K.size, bool)
+            if code == _NEWTON:
+                pull = (next_x < 0) | ((next_y < 0) & (A["y"][K] > 0))
+                A["contra"][K] = np.where(pull, np.maximum(A["contra"][K], next_x), A["contra"][K])
+                # the overshoot ended in (or next to) the hole: step back towards the contrapoint instead
+                redo = pull & ((next_x < 0) | (res.rho[sel] < A["rmin"][K] + 1))
+                R = K[redo]
+                A["trial"][R] = (A["contra"][R] * bias + A["x"][R]) / (1 + bias)
+                A["phase"][R] = _REDO
+                proceed = ~redo
+            P, nx, ny = K[proceed], next_x[proceed], next_y[proceed]
+            if P.size == 0:
+                continue
+            with np.errstate(all="ignore"):
+                failed = (ny < 0) & (A["y"][P] < 0) & ((-A["y"][P] / A["df"][P]) < 0)  # "Converge failed": x, y keep their old values
+                next_dy = (A["y"][P] - ny) / A["y"][P]
+                cycle = ~failed & (A["y"][P] > 0) & np.any(np.abs(next_dy[:, None] - A["prev"][P]) <= atol * 100, axis=1)
+            F = P[failed]
+            done.append(self._finish_loop(F))
+            Cy = P[cycle]  # stuck with Newton-Raphson: finish off by bracketing between the contrapoint and x
+            A["lo"][Cy], A["hi"][Cy], A["fhi"][Cy] = A["contra"][Cy], A["x"][Cy], A["y"][Cy]
+            A["trial"][Cy] = A["lo"][Cy]
+            A["phase"][Cy] = _BR_LO
+            go = ~failed & ~cycle
+            G = P[go]
+            A["x"][G], A["dy"][G], A["y"][G] = nx[go], next_dy[go], ny[go]
+            A["prev"][G, A["it"][G] % 6] = A["dy"][G]
+            A["it"][G] += 1
+            stop = (np.abs(A["y"][G]) <= atol) | (A["it"][G] > s.max_iter)
+            if s.stall_exit > 0:
+                improved = np.abs(A["y"][G]) < A["ymin"][G]
+                A["ymin"][G] = np.where(improved, np.abs(A["y"][G]), A["ymin"][G])
+                A["stalled"][G] = np.where(improved, 0, A["stalled"][G] + 1)
+                stop |= (A["stalled"][G] >= s.stall_exit) & (np.abs(A["y"][G]) <= 1e-4 * A["rt"][G])
+            done.append(self._finish_loop(G[stop]))
+            C = G[~stop]
+            A["phase"][C] = _NEWTON
+            with np.errstate(all="ignore"):
+                A["trial"][C] = A["x"][C] - A["y"][C] / A["df"][C]
+
+        # ---- bracketing: f(lo) came back
+        sel = ph == _BR_LO
+        B = act[sel]
+        if B.size:
+            A["flo"][B] = fy[sel]
+            lo_better = np.abs(A["flo"][B]) <= np.abs(A["fhi"][B])
+            A["root"][B] = np.where(lo_better, A["lo"][B], A["hi"][B])
+            A["best"][B] = np.minimum(np.abs(A["flo"][B]), np.abs(A["fhi"][B]))
+            ok = np.sign(A["flo"][B]) * np.sign(A["fhi"][B]) < 0
+            good_enough = A["best"][B] <= atol
+            bad = ~ok & ~good_enough  # no sign change: Roots.jl raises; the pair is reported as not found
+            A["x"][B[bad]], A["y"][B[bad]] = np.nan, np.inf
+            A["phase"][B[bad]] = _DONE
+            done.append(B[bad])
+            fin = ~bad & good_enough
+            A["x"][B[fin]] = A["root"][B[fin]]
+            A["trial"][B[fin]] = A["root"][B[fin]]
+            A["phase"][B[fin]] = _FINAL
+            M = B[~bad & ~good_enough]
+            A["halvings"][M] = 0
+            A["trial"][M] = 0.5 * (A["lo"][M] + A["hi"][M])
+            A["phase"][M] = _BR_MID
+        sel = ph == _BR_MID
+        B = act[sel]
+        if B.size:
+            fm, mid = fy[sel], A["trial"][B].copy()
+            better = np.abs(fm) < A["best"][B]
+            A["root"][B[better]], A["best"][B[better]] = mid[better], np.abs(fm[better])
+            same = np.sign(fm) == np.sign(A["flo"][B])
+            A["lo"][B] = np.where(same, mid, A["lo"][B])
+            A["flo"][B] = np.where(same, fm, A["flo"][B])
+            A["hi"][B] = np.where(same, A["hi"][B], mid)
+            A["halvings"][B] += 1
+            more = (np.abs(fm) > atol) & (A["hi"][B] - A["lo"][B] > 4 * np.finfo(float).eps * np.abs(mid)) & (A["halvings"][B] < 80)
+            A["trial"][B[more]] = 0.5 * (A["lo"][B[more]] + A["hi"][B[more]])
+            E = B[~more]
+            A["x"][E] = A["root"][E]
+            A["trial"][E] = A["root"][E]
+            A["phase"][E] = _FINAL
+        # ---- `point, df, y = step(x)` at the bracketed root
+        sel = ph == _FINAL
+        B = act[sel]
+        if B.size:
+            A["y"][B], A["df"][B] = fy[sel], res.drho[0][sel]
+            A["phase"][B] = _DONE
+            done.append(B)
+        return np.concatenate(done) if done else np.zeros(0, np.int64)
+
+    def offset(self, ids):
+        """The offsets of finished pairs: NaN where the reference returns NaN (negative offset, or |y| > 1e-4 r_target)."""
+        A = self.a
+        x, y = A["x"][ids], A["y"][ids]
+        with np.errstate(invalid="ignore"):
+            poor = ~np.isfinite(x) | (x < 0) | ~(np.abs(y) <= 1e-4 * A["rt"][ids])
+        return np.where(poor, np.nan, x)
+
+    def point(self, ids):
+        """The last trace of each pair (`point` of the reference): g, rho, t = x[0], status, lambda_max, x, alpha, beta."""
+        A = self.a
+        return dict(g=A["g"][ids], rho=A["rho"][ids], t=A["t"][ids], status=A["status"][ids], lambda_max=A["lam"][ids],
+                    x=A["px"][ids].T, alpha=A["alpha"][ids], beta=A["beta"][ids])
 
 
 def find_offset_for_radius(prober, r_target, theta, setup: TransferFunctionSetup = TransferFunctionSetup(), initial_r=None,
                            height=None, group=None, r_min=None):
-    """`_find_offset_for_radius` (precision-solvers.jl:133-241) for a batch of (r_target[i], theta[i]) pairs: the
-    image-plane offset x with ρ(x cos θ, x sin θ) = r_target.  The reference's iteration, pair by pair -- Newton steps
-    x − y / y′ with y′ = dρ/dx read off a dual number pushed through the trace, a contrapoint inside the hole that pulls
-    overshoots back (`contrapoint_bias`), cycle detection on the relative decrease with a bracketing finish -- run in
-    lock step: every `step` of every still-active pair goes out in one launch.  Returns (x, point) with point the
-    `DualArrays`-like record (g, rho, x, status, ...) of the last trace of each pair; x is NaN where the reference
-    returns NaN (negative offset, or |y| > 1e-4 r_target at the end)."""
+    """`find_offset_for_radius` (precision-solvers.jl:243-270) for a batch of (r_target[i], theta[i]) pairs: runs an
+    `OffsetEngine` to completion.  Returns (x, point): x is NaN where no offset was found."""
     r_target = np.asarray(r_target, np.float64)
-    theta = np.asarray(theta, np.float64)
-    n = r_target.size
-    ct, st = np.cos(theta), np.sin(theta)
-    atol, bias = setup.zero_atol, setup.contrapoint_bias
-    pt = dict(g=np.full(n, np.nan), rho=np.full(n, np.nan), t=np.full(n, np.nan), status=np.full(n, -1, np.int32),
-              lambda_max=np.full(n, np.nan), x=np.full((4, n), np.nan), alpha=np.full(n, np.nan), beta=np.full(n, np.nan))
-    df = np.zeros(n)
-
-    def step(idx, xr):
-        """(point, df, y) of the reference's `step`, for the pairs idx at offsets xr; records point and df."""
-        al, be = xr * ct[idx] + setup.alpha0, xr * st[idx] + setup.beta0
-        kw = {}
-        if height is not None:
-            kw["height"] = height[idx]
-        if group is not None:
-            kw["group"] = group[idx]
-        res = prober.dual(al, be, ct[idx][None, :], st[idx][None, :], **kw)
-        pt["g"][idx], pt["rho"][idx], pt["t"][idx], pt["status"][idx] = res.g, res.rho, res.x[0], res.status
-        pt["lambda_max"][idx], pt["x"][:, idx], pt["alpha"][idx], pt["beta"][idx] = res.lambda_max, res.x, al, be
-        df[idx] = res.drho[0]
-        return res.rho - r_target[idx]
-
     if r_min is None:
         r_min = api.inner_radius(prober.m) if getattr(prober, "m", None) is not None else 0.0
-    r_min = np.broadcast_to(np.asarray(r_min, np.float64), (n,))
-    x = np.maximum(20.0, r_target) if initial_r is None else np.array(np.broadcast_to(initial_r, (n,)), np.float64)
-    contra = np.zeros(n)
-    allidx = np.arange(n)
-    y = step(allidx, x)
-    dy = np.zeros(n)
-    previous = np.zeros((n, 6))
-    it = np.zeros(n, int)
-    active = ~(np.abs(y) <= atol)
-    while True:
-        A = np.nonzero(active & (it <= setup.max_iter))[0]
-        if A.size == 0:
-            break
-        with np.errstate(all="ignore"):
-            next_x = x[A] - y[A] / df[A]
-        next_y = step(A, next_x)
-        pull = (next_x < 0) | ((next_y < 0) & (y[A] > 0))
-        contra[A] = np.where(pull, np.maximum(contra[A], next_x), contra[A])
-        # the overshoot ended in (or next to) the hole: step back towards the contrapoint instead
-        redo = pull & ((next_x < 0) | (pt["rho"][A] < r_min[A] + 1))
-        if redo.any():
-            R = A[redo]
-            next_x[redo] = (contra[R] * bias + x[R]) / (1 + bias)
-            next_y[redo] = step(R, next_x[redo])
-        with np.errstate(all="ignore"):
-            failed = (next_y < 0) & (y[A] < 0) & ((-y[A] / df[A]) < 0)  # "Converge failed": x, y keep their old values
-            next_dy = (y[A] - next_y) / y[A]
-            cycle = ~failed & (y[A] > 0) & np.any(np.abs(next_dy[:, None] - previous[A]) <= atol * 100, axis=1)
-        active[A[failed]] = False
-        if cycle.any():  # stuck with Newton-Raphson: finish off by bracketing between the contrapoint and x
-            Cy = A[cycle]
-            x[Cy] = _bracket_offsets(lambda k, xr: step(Cy[k], xr), contra[Cy], x[Cy], atol)
-            good = np.isfinite(x[Cy])
-            y[Cy[good]] = step(Cy[good], x[Cy[good]])
-            y[Cy[~good]] = np.inf
-            active[Cy] = False
-        go = ~failed & ~cycle
-        G = A[go]
-        x[G], dy[G], y[G] = next_x[go], next_dy[go], next_y[go]
-        previous[G, it[G] % 6] = dy[G]
-        it[G] += 1
-        active[G] = ~(np.abs(y[G]) <= atol)
-    # exceeded max_iter with a large residual: "Attempting to bracket"
-    late = np.nonzero((it >= setup.max_iter) & (y > 10.0) & np.isfinite(x))[0]
-    if late.size:
-        x[late] = _bracket_offsets(lambda k, xr: step(late[k], xr), contra[late], x[late], atol)
-        good = np.isfinite(x[late])
-        y[late[good]] = step(late[good], x[late[good]])
-        y[late[~good]] = np.inf
-    with np.errstate(invalid="ignore"):
-        poor = ~np.isfinite(x) | (x < 0) | ~(np.abs(y) <= 1e-4 * r_target)
-    return np.where(poor, np.nan, x), pt
+    eng = OffsetEngine(prober, setup)
+    ids = eng.add(r_target, theta, height=height, group=group, r_min=r_min, initial_r=initial_r)
+    while eng.pending():
+        eng.round()
+    return eng.offset(ids), eng.point(ids)
 
 
 def jacobian_ab_gr(prober, alpha, beta, setup: TransferFunctionSetup = TransferFunctionSetup(), thick=False, group=None,
@@ -401,22 +537,6 @@ def jacobian_ab_gr(prober, alpha, beta, setup: TransferFunctionSetup = TransferF
         return np.abs(1.0 / det)
 
 
-class _Workhorse:
-    """`_rear_workhorse` for thin discs (cunningham-transfer-functions.jl:253-272): θ → (g, J, t), batched."""
-
-    def __init__(self, prober, setup):
-        self.prober, self.setup = prober, setup
-
-    def __call__(self, r_e, theta, group=None):
-        r, pt = find_offset_for_radius(self.prober, r_e, theta, self.setup, group=group, r_min=_r_min_of(self.prober, group))
-        if np.any(np.isnan(r)):
-            k = int(np.nonzero(np.isnan(r))[0][0])
-            raise RuntimeError(f"Transfer function integration failed (rₑ={r_e[k]}, θ={theta[k]}).")
-        J = jacobian_ab_gr(self.prober, r * np.cos(theta) + self.setup.alpha0, r * np.sin(theta) + self.setup.beta0, self.setup,
-                           group=group)
-        return pt["g"], J, pt["t"]
-
-
 def _r_min_of(prober, group):
     """`inner_radius(m)` of each pair's metric (one metric per cell of a table)."""
     if group is None or not hasattr(prober, "probers"):
@@ -425,39 +545,47 @@ def _r_min_of(prober, group):
     return rm[np.asarray(group)]
 
 
-class _ThickWorkhorse:
-    """`_thick_workhorse` (cunningham-transfer-functions.jl:274-333), batched: the offset is found on the datum plane
-    through the disc surface at rₑ, the same ray is then traced against the disc itself, and the sample only counts
-    (finite J) if it ends in the same way at (nearly) the same place, i.e. if that patch of the surface is visible."""
+class _GoldenChain:
+    """Optim.jl's `GoldenSection` univariate minimiser, one evaluation at a time: `theta` is the next abscissa to evaluate
+    (None when finished), `feed(f)` hands over the objective there.  `_search_extremal!` runs it with
+    `iterations = N_extrema − 1` on g (minimum near θ = 0) and on −g (maximum near θ = π),
+    cunningham-transfer-functions.jl:391-426.  Same sequence of abscissae as `_golden_sections`."""
 
-    def __init__(self, prober, setup):
-        self.prober, self.setup, self.disc = prober, setup, prober.thick
+    def __init__(self, lower, upper, iterations, sign, rel_tol=math.sqrt(np.finfo(float).eps), abs_tol=np.finfo(float).eps):
+        self.lower, self.upper, self.left, self.sign = float(lower), float(upper), int(iterations), sign
+        self.rel_tol, self.abs_tol = rel_tol, abs_tol
+        self.xm = self.lower + _GOLDEN * (self.upper - self.lower)
+        self.fm = None
+        self.theta = self.xm
+        self.right = False
 
-    def __call__(self, r_e, theta, group=None):
-        r_e = np.asarray(r_e, np.float64)
-        gq = {} if group is None else {"group": group}
-        h = self.prober.cross_section(r_e, group)
-        r, pt = find_offset_for_radius(self.prober, r_e, theta, self.setup, height=h, group=group, r_min=_r_min_of(self.prober, group))
-        if np.any(np.isnan(r)):
-            k = int(np.nonzero(np.isnan(r))[0][0])
-            raise RuntimeError(f"Transfer function integration failed (rₑ={r_e[k]}, θ={theta[k]}).")
-        alpha = r * np.cos(theta) + self.setup.alpha0
-        beta = r * np.sin(theta) + self.setup.beta0
-        # the reference re-traces with the default chart and stops at 1.1 λ_max of the datum-plane point: a disc hit
-        # later than that is no hit
-        gt = self.prober.points(alpha, beta, thick=True, default_chart=True, **gq)
-        status = np.where((gt.status == api.StatusCodes.IntersectedWithGeometry) & (gt.lambda_max > 1.1 * pt["lambda_max"]),
-                          api.StatusCodes.NoStatus, gt.status)
-        dist = np.linalg.norm(pt["x"] - gt.x, axis=0)
-        close = dist <= 1e-3 * np.maximum(np.linalg.norm(pt["x"], axis=0), np.linalg.norm(gt.x, axis=0))  # isapprox(rtol = 1e-3)
-        ok = (status == pt["status"]) & close
-        J = np.full(r.size, np.nan)
-        if ok.any():
-            inner = self.prober.disc_inner_radius(None if group is None else group[ok])
-            J[ok] = jacobian_ab_gr(self.prober, alpha[ok], beta[ok], self.setup, thick=True, group=None if group is None else group[ok],
-                                   disc_inner_radius=inner)
-        J[~np.isfinite(J)] = np.nan  # `is_visible = isfinite(J)`; invisible samples keep g and t, J = NaN (utils.jl:71-78)
-        return pt["g"], J, pt["t"]
+    def feed(self, f):
+        if self.fm is None:
+            self.fm = f
+        else:
+            xn, better = self.theta, f < self.fm
+            if self.right:
+                if better:
+                    self.lower = self.xm
+                else:
+                    self.upper = xn
+            else:
+                if better:
+                    self.upper = self.xm
+                else:
+                    self.lower = xn
+            if better:
+                self.xm, self.fm = xn, f
+        self.theta = None
+        if self.left <= 0:
+            return
+        self.left -= 1
+        tolx = self.rel_tol * abs(self.xm) + self.abs_tol
+        mid = 0.5 * (self.upper + self.lower)
+        if abs(self.xm - mid) <= 2 * tolx - 0.5 * (self.upper - self.lower):
+            return
+        self.right = (self.upper - self.xm) > (self.xm - self.lower)
+        self.theta = self.xm + _GOLDEN * (self.upper - self.xm) if self.right else self.xm - _GOLDEN * (self.xm - self.lower)
 
 
 def _golden_sections(fn, lower, upper, iterations, rel_tol=math.sqrt(np.finfo(float).eps), abs_tol=np.finfo(float).eps):
@@ -496,7 +624,7 @@ def cunningham_transfer_functions(m, x, d, radii: Sequence[float], *, prober: Op
                                   groups=None, **kwargs) -> list:
     """`cunningham_transfer_function(m, x, d, rₑ; N, chart, max_time, ...)` for every rₑ in `radii` at once (the loop
     `interpolated_transfer_branches` threads over, cunningham-transfer-functions.jl:428-462)."""
-    setup_keys = {"theta_offset", "zero_atol", "N", "N_extrema", "h", "max_iter", "contrapoint_bias", "alpha0", "beta0"}
+    setup_keys = {"theta_offset", "zero_atol", "N", "N_extrema", "h", "max_iter", "contrapoint_bias", "alpha0", "beta0", "warm_start", "stall_exit"}
     if setup is None:
         alias = {"θ_offset": "theta_offset", "α₀": "alpha0", "β₀": "beta0"}
         skw = {alias.get(k, k): kwargs.pop(k) for k in list(kwargs) if alias.get(k, k) in setup_keys}
@@ -506,42 +634,103 @@ def cunningham_transfer_functions(m, x, d, radii: Sequence[float], *, prober: Op
     radii = np.atleast_1d(np.asarray(radii, np.float64))
     R = radii.size
     groups = None if groups is None else np.asarray(groups, np.int64)  # cell of each radius (CellProber)
-    gq = (lambda sel: {}) if groups is None else (lambda sel: {"group": sel})
-    work = _ThickWorkhorse(prober, setup) if getattr(prober, "thick", None) is not None else _Workhorse(prober, setup)
+    thick = getattr(prober, "thick", None) is not None
     th0 = theta_samples(setup)
-    N = th0.size
-    M = N + 2 * setup.N_extrema
+    N, NE = th0.size, setup.N_extrema
+    M = N + 2 * NE
     thetas = np.full((R, M), np.nan)
     gs = np.full((R, M), np.nan)
     Js = np.full((R, M), np.nan)
     ts = np.full((R, M), np.nan)
-    g, J, t = work(np.repeat(radii, N), np.tile(th0, R), **gq(None if groups is None else np.repeat(groups, N)))
-    thetas[:, :N] = th0
-    gs[:, :N], Js[:, :N], ts[:, :N] = g.reshape(R, N), J.reshape(R, N), t.reshape(R, N)
 
-    # `_search_extremal!`: problems 0..R-1 minimise g near θ = 0, R..2R-1 maximise near θ = π; every probe is kept
-    fill = np.full(2 * R, 0)
-    sign = np.concatenate([np.ones(R), -np.ones(R)])
-    re2 = np.concatenate([radii, radii])
-    grp2 = None if groups is None else np.concatenate([groups, groups])
+    # Every sample (rₑ, θ) is one pair of the offset engine; when it has converged its redshift and arrival time are
+    # final and its Jacobian (for a thick disc: after the visibility re-trace) is queued.  The two golden-section chains
+    # of a radius only need g of their own last probe to choose the next angle, so every radius walks through its 17
+    # probes at its own pace while the 80 fixed angles of all radii converge alongside
+    # (`_cunningham_transfer_function!` and `_search_extremal!` do the same evaluations one after the other).
+    eng = OffsetEngine(prober, setup)
+    info = {}  # pair id -> (radius index, sample slot, golden chain or None)
+    rmin_k = np.broadcast_to(np.asarray(_r_min_of(prober, groups), np.float64), (R,))
+    h_k = prober.cross_section(radii, groups) if thick else None
 
-    def objective(theta, mask):
-        idx = np.nonzero(mask)[0]
-        th = theta[idx].copy()
-        pole = (np.abs(th) < 1e-4) | (np.abs(np.abs(th) - math.pi) < 1e-4)
-        th = np.where(pole, th + 1e-4, th)
-        gq_, Jq, tq = work(re2[idx], th, **gq(None if grp2 is None else grp2[idx]))
-        out = np.full(theta.size, np.inf)
-        rr = idx % R
-        col = N + np.where(idx < R, 0, setup.N_extrema) + fill[idx]
-        thetas[rr, col], gs[rr, col], Js[rr, col], ts[rr, col] = th, gq_, Jq, tq
-        fill[idx] += 1
-        out[idx] = sign[idx] * gq_
-        return out
+    def request(ks, slots, angles, chains, initial_r=None):
+        ks = np.asarray(ks)
+        ids = eng.add(radii[ks], angles, height=None if h_k is None else h_k[ks], group=None if groups is None else groups[ks],
+                      r_min=rmin_k[ks], initial_r=initial_r)
+        thetas[ks, slots] = angles
+        for i, k, sl, ch in zip(ids, ks, slots, chains):
+            info[int(i)] = (int(k), int(sl), ch)
 
+    def nudged(theta):  # "avoid poles", cunningham-transfer-functions.jl:404-406
+        return theta + 1e-4 if (abs(theta) < 1e-4 or abs(abs(theta) - math.pi) < 1e-4) else theta
+
+    request(np.repeat(np.arange(R), N), np.tile(np.arange(N), R), np.tile(th0, R), [None] * (R * N))
     off = setup.theta_offset
-    best = _golden_sections(objective, np.concatenate([np.full(R, -off), np.full(R, math.pi - off)]),
-                            np.concatenate([np.full(R, off), np.full(R, math.pi + off)]), setup.N_extrema - 1)
+    cmin = [_GoldenChain(-off, off, NE - 1, 1.0) for _ in range(R)]
+    cmax = [_GoldenChain(math.pi - off, math.pi + off, NE - 1, -1.0) for _ in range(R)]
+    fill = np.zeros((R, 2), int)
+    for base, chains in ((0, cmin), (1, cmax)):
+        request(np.arange(R), np.full(R, N + base * NE), [nudged(c.theta) for c in chains], chains)
+        fill[:, base] = 1
+
+    vis_q, jac_q = [], []  # (radius index, slot, alpha, beta[, point status, lambda_max, x]) awaiting their traces
+
+    def flush_visibility():
+        k = np.array([q[0] for q in vis_q]); sl = np.array([q[1] for q in vis_q])
+        al = np.array([q[2] for q in vis_q]); be = np.array([q[3] for q in vis_q])
+        st = np.array([q[4] for q in vis_q]); lam = np.array([q[5] for q in vis_q]); px = np.array([q[6] for q in vis_q]).T
+        vis_q.clear()
+        gq = {} if groups is None else {"group": groups[k]}
+        # the reference re-traces with the default chart and stops at 1.1 λ_max of the datum-plane point: a disc hit
+        # later than that is no hit (`_thick_workhorse`, cunningham-transfer-functions.jl:301-316)
+        gt = prober.points(al, be, thick=True, default_chart=True, **gq)
+        status = np.where((gt.status == api.StatusCodes.IntersectedWithGeometry) & (gt.lambda_max > 1.1 * lam), api.StatusCodes.NoStatus, gt.status)
+        dist = np.linalg.norm(px - gt.x, axis=0)
+        close = dist <= 1e-3 * np.maximum(np.linalg.norm(px, axis=0), np.linalg.norm(gt.x, axis=0))  # isapprox(rtol = 1e-3)
+        for j in np.nonzero((status == st) & close)[0]:
+            jac_q.append((int(k[j]), int(sl[j]), al[j], be[j]))
+
+    def flush_jacobians():
+        k = np.array([q[0] for q in jac_q]); sl = np.array([q[1] for q in jac_q])
+        al = np.array([q[2] for q in jac_q]); be = np.array([q[3] for q in jac_q])
+        jac_q.clear()
+        grp = None if groups is None else groups[k]
+        J = jacobian_ab_gr(prober, al, be, setup, thick=thick, group=grp, disc_inner_radius=prober.disc_inner_radius(grp) if thick else None)
+        J[~np.isfinite(J)] = np.nan  # `is_visible = isfinite(J)`; invisible samples keep g and t, J = NaN (utils.jl:71-78)
+        Js[k, sl] = J
+
+    while eng.pending() or vis_q or jac_q:
+        if eng.pending():
+            fin = eng.round()
+            if fin.size:
+                xs, pt = eng.offset(fin), eng.point(fin)
+                if np.any(np.isnan(xs)):
+                    j = int(np.nonzero(np.isnan(xs))[0][0])
+                    k, sl, _ = info[int(fin[j])]
+                    raise RuntimeError(f"Transfer function integration failed (rₑ={radii[k]}, θ={thetas[k, sl]}).")
+                again = []
+                for j, i in enumerate(fin):
+                    k, sl, chain = info.pop(int(i))
+                    gs[k, sl], ts[k, sl] = pt["g"][j], pt["t"][j]
+                    if thick:
+                        vis_q.append((k, sl, pt["alpha"][j], pt["beta"][j], pt["status"][j], pt["lambda_max"][j], pt["x"][:, j]))
+                    else:
+                        jac_q.append((k, sl, pt["alpha"][j], pt["beta"][j]))
+                    if chain is not None:
+                        chain.feed(chain.sign * pt["g"][j])
+                        if chain.theta is not None:
+                            base = 0 if chain.sign > 0 else 1
+                            again.append((k, N + base * NE + fill[k, base], nudged(chain.theta), chain, xs[j]))
+                            fill[k, base] += 1
+                if again:
+                    request([a_[0] for a_ in again], [a_[1] for a_ in again], [a_[2] for a_ in again], [a_[3] for a_ in again],
+                            initial_r=np.array([a_[4] for a_ in again]) if setup.warm_start else None)
+        idle = not eng.pending()
+        if vis_q and (idle or len(vis_q) >= 4096):
+            flush_visibility()
+        if jac_q and (idle or len(jac_q) >= 4096):
+            flush_jacobians()
+    best = np.array([c.fm for c in cmin] + [c.fm for c in cmax], np.float64)  # minima of g and of −g
     out = []
     for k in range(R):
         used = np.isfinite(thetas[k])

@@ -335,7 +335,11 @@ int gb200_trace_dual_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* 
 /* Same as gb200_render but `d_images[k]` are DEVICE pointers on ctx's device and no
    host copy is made; work is enqueued on `cuda_stream` (a cudaStream_t cast to
    void*, NULL = the context's own stream) and the call returns without
-   synchronising when `async` != 0. */
+   synchronising when `async` != 0.  An asynchronous call leaves kernels running that use the
+   context's work queue and scratch buffers: the library orders every later call on the same context (on
+   whatever stream) after them with an event, so calls may be issued back to back; the caller only has
+   to synchronise `cuda_stream` before it reads the results, and gb200_get_stats reports no step
+   counters for asynchronous calls. */
 int gb200_render_device(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic,
                         const gb200_range* range, const int32_t* pointfns, int32_t npf,
                         const gb200_plunging_table* plunging, double* const* d_images,

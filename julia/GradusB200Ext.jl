@@ -1,34 +1,74 @@
 # GradusB200Ext.jl -- reference-side binding for libgradus_b200 (the `ccall` shim a Gradus.jl maintainer adds).
 #
-# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia toolchain.  Every entry point used below is
-# exercised through the very same C ABI from Python (gradus.jl_b200/_cabi.py, tests/).  Struct layouts mirror
-# include/gradus_b200.h field for field.
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia toolchain (DESIGN.md section 1).  Every entry point
+# used below is exercised through the very same C ABI from Python (gradus.jl_b200/_cabi.py, tests/) and from plain C
+# (tests/c/cabi_render.c).  Struct layouts mirror include/gradus_b200.h field for field
+# (tests/test_host_api.py::test_ctypes_struct_layout_matches_header checks the sizes and offsets used here).
 #
-# It replaces ext/GradusDiffEqGPUExt/GradusDiffEqGPUExt.jl:10-31 by adding a method of
-#     Gradus.ensemble_solve_tracing_problem(ensemble, problem, config; ...)      (src/tracing/tracing.jl:113-196)
-# for the new ensemble type `EnsembleB200`, next to `EnsembleEndpointThreads` (src/Gradus.jl:412).
+# What it adds, next to the stock ensembles (`EnsembleEndpointThreads`, src/Gradus.jl:412):
+#   * `EnsembleB200(devices)`                                 -- a new ensemble type;
+#   * a method of `Gradus.ensemble_solve_tracing_problem`     -- the seam of src/tracing/tracing.jl:113-196; it replaces
+#     ext/GradusDiffEqGPUExt/GradusDiffEqGPUExt.jl:10-31.  With it `tracegeodesics`, `rendergeodesics`,
+#     `prerendergeodesics`, `lineprofile(...; ensemble = EnsembleB200())` (the keyword reaches `tracegeodesics` through
+#     `solver_args...`, src/line-profiles.jl:172-184), `tracecorona`, ... run their rays on the GPU with no other change;
+#   * fused methods that skip the 152 B/ray `GeodesicPoint` round trip: `render_into_image!` for device point
+#     functions (src/rendering/rendering.jl:89-107) and `lineprofile_b200` (src/line-profiles.jl:152-198).
+# It overrides NO existing Gradus method: stock ensembles keep working with the extension loaded.  The initial
+# conditions are recognised from the closures the reference builds (their captured variables are read as fields and the
+# reading is verified against the closure itself on two rays); anything unrecognised takes the generic path, which
+# evaluates `prob_func` on host threads exactly as the reference's ensembles do.
 module GradusB200Ext
 
 using Gradus
-using Gradus: TracingConfiguration, GeodesicPoint, StatusCodes, KerrMetric, JohannsenPsaltisMetric, ThinDisc, ShakuraSunyaev,
-    DatumPlane, PolarChart, PolarPlane, GeometricGrid, LinearGrid, InverseGrid
+using Gradus: TracingConfiguration, GeodesicPoint, StatusCodes, KerrMetric, JohannsenPsaltisMetric, JohannsenMetric,
+    BumblebeeMetric, KerrNewmanMetric, ThinDisc, ShakuraSunyaev, DatumPlane, PolarChart, PolarPlane, GeometricGrid,
+    LinearGrid, InverseGrid, AbstractTrace, BinningMethod
 using StaticArrays
 import SciMLBase
 
 const libgradus_b200 = get(ENV, "GRADUS_B200_LIB", "libgradus_b200")
 
+# ---------------------------------------------------------------------------------------------------------------------
+# ensemble type: one library context per device, created on first use and kept for the life of the ensemble
 """
     EnsembleB200(devices = [0])
 
-Integrate every ray of an ensemble on the listed CUDA devices (B200, sm_100a) with libgradus_b200.
+Integrate every ray of an ensemble on the listed CUDA devices (B200, sm_100a) with libgradus_b200.  There is no CPU
+fallback: configurations outside the library's scope raise `ArgumentError`.
 """
-struct EnsembleB200
+mutable struct EnsembleB200
     devices::Vector{Int}
+    contexts::Vector{Ptr{Cvoid}}
+    function EnsembleB200(devices::AbstractVector{<:Integer} = [0])
+        isempty(devices) && throw(ArgumentError("EnsembleB200 needs at least one device"))
+        e = new(collect(Int, devices), fill(C_NULL, length(devices)))
+        finalizer(e) do x
+            for c in x.contexts
+                c == C_NULL || ccall((:gb200_destroy, libgradus_b200), Cvoid, (Ptr{Cvoid},), c)
+            end
+        end
+        e
+    end
 end
-EnsembleB200() = EnsembleB200([0])
 Gradus.restrict_ensemble(::Gradus.AbstractMetric, e::EnsembleB200) = e
 
-# ---- POD mirrors of include/gradus_b200.h ---------------------------------------------------------------------
+function _context(e::EnsembleB200, d::Int)
+    if e.contexts[d] == C_NULL
+        ctx = Ref{Ptr{Cvoid}}(C_NULL)
+        _check(ccall((:gb200_init, libgradus_b200), Cint, (Cint, Ref{Ptr{Cvoid}}), e.devices[d], ctx), C_NULL)
+        e.contexts[d] = ctx[]
+    end
+    e.contexts[d]
+end
+
+function _check(rc, ctx)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:gb200_last_error, libgradus_b200), Cstring, (Ptr{Cvoid},), ctx))
+    (rc == -1 || rc == -4) ? throw(ArgumentError(msg)) : error("libgradus_b200 ($rc): $msg")
+end
+
+# ---------------------------------------------------------------------------------------------------------------------
+# POD mirrors of include/gradus_b200.h
 struct CProblem
     metric_kind::Int32; geometry_kind::Int32; callback_kind::Int32; pow_mode::Int32
     metric_params::NTuple{8,Float64}; observer::NTuple{4,Float64}; geometry_params::NTuple{4,Float64}
@@ -49,67 +89,177 @@ struct CEndpoints
     x::NTuple{4,Ptr{Float64}}; v::NTuple{4,Ptr{Float64}}; x_init::NTuple{4,Ptr{Float64}}; v_init::NTuple{4,Ptr{Float64}}
     naccept::Ptr{Int32}; nreject::Ptr{Int32}; flags::Ptr{Int32}
 end
+struct CEmissivity
+    kind::Int32; n::Int32; index::Float64; r::Ptr{Float64}; eps::Ptr{Float64}
+end
+struct CLineProfileOpts
+    min_re::Float64; max_re::Float64; normalise::Int32; bin_right_closed::Int32
+end
+const NULL4 = ntuple(_ -> Ptr{Float64}(C_NULL), 4)
 
+# ---------------------------------------------------------------------------------------------------------------------
+# configuration -> POD
 _mp8(v...) = ntuple(i -> i <= length(v) ? Float64(v[i]) : 0.0, 8)
-_metric(m::KerrMetric) = (Int32(0), _mp8(m.M, m.a))
-_metric(m::JohannsenPsaltisMetric) = (Int32(1), _mp8(m.M, m.a, m.ϵ3))
-_metric(m::JohannsenMetric) = (Int32(2), _mp8(m.M, m.a, m.α13, m.α22, m.α52, m.ϵ3))
-_metric(m::BumblebeeMetric) = (Int32(3), _mp8(m.M, m.a, m.l))
-# slot 4 (metric_params[3]) carries the charge of the test particle, q for photons and q/μ otherwise
-# (geodesic_ode_problem(::KerrNewmanMetric), src/metrics/kerr-newman-ad.jl:74-78); the caller passes trace.q, trace.μ
-_metric(m::KerrNewmanMetric; q = 0.0, μ = 0.0) = (Int32(4), _mp8(m.M, m.a, m.Q, isapprox(μ, 0.0) ? q : q / μ))
-_metric(m) = throw(ArgumentError("EnsembleB200 has no closed-form right-hand side for $(typeof(m)); there is no CPU fallback"))
+_metric(m::KerrMetric, qμ) = (Int32(0), _mp8(m.M, m.a))
+_metric(m::JohannsenPsaltisMetric, qμ) = (Int32(1), _mp8(m.M, m.a, m.ϵ3))
+_metric(m::JohannsenMetric, qμ) = (Int32(2), _mp8(m.M, m.a, m.α13, m.α22, m.α52, m.ϵ3))
+_metric(m::BumblebeeMetric, qμ) = (Int32(3), _mp8(m.M, m.a, m.l))
+# slot 4 (metric_params[3]) carries q for photons and q/μ otherwise (geodesic_ode_problem(::KerrNewmanMetric),
+# src/metrics/kerr-newman-ad.jl:74-78)
+_metric(m::KerrNewmanMetric, qμ) = (Int32(4), _mp8(m.M, m.a, m.Q, qμ))
+_metric(m, qμ) = throw(ArgumentError("EnsembleB200 has no closed-form right-hand side for $(typeof(m)); there is no CPU fallback"))
+
 _geometry(::Nothing) = (Int32(0), (0.0, 0.0, 0.0, 0.0))
-_geometry(d::ThinDisc) = (Int32(1), (d.inner_radius, d.outer_radius, 0.0, 0.0))
-_geometry(d::ShakuraSunyaev) = (Int32(2), (d.Ṁ_Ṁedd, d.inv_η, d.inner_radius, 0.0))
-_geometry(d::DatumPlane) = (Int32(3), (d.height, 0.0, 0.0, 0.0))
+_geometry(d::ThinDisc) = (Int32(1), (Float64(d.inner_radius), Float64(d.outer_radius), 0.0, 0.0))
+_geometry(d::ShakuraSunyaev) = (Int32(2), (Float64(d.Ṁ_Ṁedd), Float64(d.inv_η), Float64(d.inner_radius), 0.0))
+_geometry(d::DatumPlane) = (Int32(3), (Float64(d.height), 0.0, 0.0, 0.0))
 _geometry(d) = throw(ArgumentError("geometry $(typeof(d)) is outside the EnsembleB200 scope"))
 
-# The shim recognises `domain_upper_hemisphere(δ)` (src/tracing/callbacks.jl:31-39) by the closure type of its condition
-# and reads δ from the captured variable; anything else cannot run on the device.
-function _callback(cb)
-    isnothing(cb) && return (Int32(0), 0.0)
-    if cb isa SciMLBase.DiscreteCallback && nameof(typeof(cb.condition)) === Symbol("#_domain_upper_hemisphere_check")
-        return (Int32(1), Float64(cb.condition.δ))
-    end
-    throw(ArgumentError("only `domain_upper_hemisphere` user callbacks can run on the device"))
-end
+# Julia names a closure type "#name#NN": recognise the reference's closures by the stem of that name.
+_closure_is(f, stem::AbstractString) = startswith(string(nameof(typeof(f))), "#" * stem)
 
-"""Render-grid initial conditions as data (what `_render_velocity_function`, src/rendering/rendering.jl:140-163, closes over)."""
-struct RenderGridVelocity{T}
-    image_width::Int; image_height::Int; αlims::Tuple{T,T}; βlims::Tuple{T,T}
-end
+_flatten_callbacks(::Nothing) = ()
+_flatten_callbacks(cb::SciMLBase.CallbackSet) = (cb.continuous_callbacks..., cb.discrete_callbacks...)
+_flatten_callbacks(cb) = (cb,)
 
-function _ic(config::TracingConfiguration, problem, keep)
-    v = config.velocity
-    np = (C_NULL, C_NULL, C_NULL, C_NULL) .|> p -> convert(Ptr{Float64}, p)
-    if v isa RenderGridVelocity
-        return CIC(0, 0, v.image_width, v.image_height, v.αlims[1], v.αlims[2], v.βlims[1], v.βlims[2], np, np, v.image_width * v.image_height)
-    elseif v isa PolarPlane
-        gk = v.grid isa GeometricGrid ? 1 : v.grid isa InverseGrid ? 2 : v.grid isa LinearGrid ? 0 :
-             throw(ArgumentError("grid $(typeof(v.grid)) is outside the EnsembleB200 scope"))
-        return CIC(1, gk, v.Nr, v.Nθ, v.r_min, v.r_max, v.θ_min, v.θ_max, np, np, v.Nr * v.Nθ)
-    else
-        # generic path: evaluate prob_func on host threads into SoA (corona ensembles, lamp-post.jl:89-100)
-        n = config.trajectories
-        xs = [Vector{Float64}(undef, n) for _ = 1:4]; vs = [Vector{Float64}(undef, n) for _ = 1:4]
-        Threads.@threads for i = 1:n
-            u0 = problem.prob_func(problem.prob, i, 0).u0
-            for k = 1:4
-                xs[k][i] = u0[k]; vs[k][i] = u0[4+k]
-            end
+"""
+`config.callback` is what `tracing_configuration` stored: `merge_callbacks(user_callback, geometry_callback)`
+(src/geometry/bootstrap.jl:12-19, src/tracing/callbacks.jl:13-23), i.e. a `CallbackSet` holding the geometry's
+`ContinuousCallback` (condition closure `_distance_to_disc_wrapper`, capturing `g` and `gtol`, bootstrap.jl:56-60) and the
+user's callbacks.  Returns (callback_kind, δ, gtol); the geometry itself is taken from `config.geometry`.
+"""
+function _callbacks(config)
+    kind, δ, gtol, seen_geometry = Int32(0), 0.0, 1e-2, false
+    for cb in _flatten_callbacks(config.callback)
+        isnothing(cb) && continue
+        cond = cb.condition
+        if cb isa SciMLBase.ContinuousCallback && _closure_is(cond, "_distance_to_disc_wrapper")
+            cond.g === config.geometry || throw(ArgumentError("the geometry callback does not belong to config.geometry"))
+            gtol = Float64(cond.gtol)
+            seen_geometry = true
+        elseif cb isa SciMLBase.DiscreteCallback && _closure_is(cond, "_domain_upper_hemisphere_check")
+            kind == 0 || throw(ArgumentError("only one `domain_upper_hemisphere` callback can run on the device"))
+            kind, δ = Int32(1), Float64(cond.δ)          # src/tracing/callbacks.jl:31-39
+        else
+            throw(ArgumentError("callback $(typeof(cond)) cannot run on the device: only the disc intersection and `domain_upper_hemisphere` do"))
         end
-        append!(keep, xs); append!(keep, vs)
-        return CIC(2, 0, 0, 0, 0.0, 0.0, 0.0, 0.0, Tuple(pointer.(xs)), Tuple(pointer.(vs)), n)
     end
+    isnothing(config.geometry) || seen_geometry || throw(ArgumentError("config.geometry has no intersection callback in config.callback"))
+    kind, δ, gtol
 end
 
-function _check(rc, ctx)
-    rc == 0 && return
-    msg = unsafe_string(ccall((:gb200_last_error, libgradus_b200), Cstring, (Ptr{Cvoid},), ctx))
-    rc == -1 || rc == -4 ? throw(ArgumentError(msg)) : error("libgradus_b200: $msg")
+# mass of the traced particle: not stored in `config` (it lives in `trace`); recover it from the norm of the first,
+# already constrained, initial state (constrain_all, src/tracing/constraints.jl:14-15)
+function _mass(m, u0)
+    x, v = SVector{4}(u0[1:4]), SVector{4}(u0[5:8])
+    μ2 = -Gradus.dotproduct(Gradus.metric(m, x), v, v)
+    μ2 < 1e-10 ? 0.0 : sqrt(μ2)
+end
+# q/μ of a charged particle: captured by the Kerr-Newman ODE function (kerr-newman-ad.jl:73-92)
+_charge(prob) = hasproperty(prob.f.f, :q_μ) ? Float64(prob.f.f.q_μ) : 0.0
+
+function _problem(config::TracingConfiguration, prob::SciMLBase.ODEProblem; mu = _mass(config.metric, prob.u0), solver_opts...)
+    config.solver isa Gradus.Tsit5 || throw(ArgumentError("EnsembleB200 integrates with Tsit5 only"))
+    config.chart isa PolarChart || throw(ArgumentError("EnsembleB200 supports PolarChart only"))
+    # the device integrator has two further options; everything else errors like `kwargshandle = KeywordArgError`
+    # (src/tracing/tracing.jl:106,146)
+    dtmax, maxiters = 0.0, 0
+    for (k, v) in pairs(solver_opts)
+        k === :dtmax ? (dtmax = Float64(v)) : k === :maxiters ? (maxiters = Int(v)) :
+        throw(ArgumentError("unrecognised keyword argument $k for the B200 integrator"))
+    end
+    mk, mp = _metric(config.metric, _charge(prob))
+    gk, gp = _geometry(config.geometry)
+    ck, cδ, gtol = _callbacks(config)
+    CProblem(mk, gk, ck, 0, mp, Tuple(Float64.(prob.u0[1:4])), gp, gtol, config.chart.inner_radius, config.chart.outer_radius, cδ,
+             config.λ_domain[1], config.λ_domain[2], config.abstol, config.reltol, dtmax, mu, maxiters)
 end
 
+# ---------------------------------------------------------------------------------------------------------------------
+# initial conditions
+"""
+Structured initial conditions read off the reference's velocity closures, or `nothing`.
+  * `_render_velocity_function` (src/rendering/rendering.jl:140-163) returns `velfunc` capturing the ranges `αs`, `βs` and
+    `image_height`: -> GB200_IC_RENDER_GRID (rays generated on the device from six scalars).
+  * `promote_velfunc(m, x, plane)` (src/image-planes/planes.jl:180-184) returns `velfunc` capturing the materialised `αs`, `βs`
+    arrays of any image plane: -> GB200_IC_IMPACT_PARAMETERS (two host arrays, 16 B/ray); `lineprofile_b200` below passes a
+    `PolarPlane` as data instead (GB200_IC_POLAR_PLANE, nothing uploaded).
+The reading is checked against the closure itself on the first and last ray.
+"""
+function _structured_ic(config, keep)
+    v = config.velocity
+    (v isa Function && _closure_is(v, "velfunc") && hasproperty(v, :αs) && hasproperty(v, :βs)) || return nothing
+    m, x, n = config.metric, config.position, config.trajectories
+    if v.αs isa AbstractRange && v.βs isa AbstractRange && hasproperty(v, :image_height)
+        w, h = length(v.αs), Int(v.image_height)
+        (length(v.βs) == h && w * h == n) || return nothing
+        for i in (1, n)
+            col, row = (i - 1) ÷ h + 1, mod1(i, h)
+            Gradus.map_impact_parameters(m, x, v.αs[col] + 1e-6, v.βs[row] + 1e-6) == v(i) || return nothing
+        end
+        return CIC(0, 0, w, h, first(v.αs), last(v.αs), first(v.βs), last(v.βs), NULL4, NULL4, n)
+    elseif v.αs isa AbstractArray{Float64} && length(v.αs) == n == length(v.βs)
+        for i in (1, n)
+            Gradus.map_impact_parameters(m, x, v.αs[i], v.βs[i]) == v(i) || return nothing
+        end
+        αs, βs = vec(collect(v.αs)), vec(collect(v.βs))
+        push!(keep, αs, βs)
+        return CIC(4, 0, 0, 0, 0.0, 0.0, 0.0, 0.0, (pointer(αs), pointer(βs), Ptr{Float64}(C_NULL), Ptr{Float64}(C_NULL)), NULL4, n)
+    end
+    nothing
+end
+
+# generic path: evaluate prob_func on host threads into SoA, as the reference's ensembles do per ray
+# (corona fans, src/corona/models/lamp-post.jl:89-100; arrays of positions and velocities)
+function _explicit_ic(problem, n, keep)
+    xs = [Vector{Float64}(undef, n) for _ = 1:4]
+    vs = [Vector{Float64}(undef, n) for _ = 1:4]
+    Threads.@threads for i = 1:n
+        u0 = problem.prob_func(problem.prob, i, 0).u0
+        for k = 1:4
+            xs[k][i] = u0[k]
+            vs[k][i] = u0[4+k]
+        end
+    end
+    append!(keep, xs)
+    append!(keep, vs)
+    CIC(2, 0, 0, 0, 0.0, 0.0, 0.0, 0.0, Tuple(pointer.(xs)), Tuple(pointer.(vs)), n)
+end
+
+_grid_kind(::LinearGrid) = Int32(0)
+_grid_kind(::GeometricGrid) = Int32(1)
+_grid_kind(::InverseGrid) = Int32(2)
+_grid_kind(g) = throw(ArgumentError("grid $(typeof(g)) is outside the EnsembleB200 scope"))
+_plane_ic(p::PolarPlane) = CIC(1, _grid_kind(p.grid), p.Nr, p.Nθ, p.r_min, p.r_max, p.θ_min, p.θ_max, NULL4, NULL4, p.Nr * p.Nθ)
+
+# ---------------------------------------------------------------------------------------------------------------------
+# sharding: whole strips of four image columns (render grid) / θ-rows (polar plane), strip d, d + ndev, ... on device d:
+# balances the expensive photon-ring region and keeps neighbouring rays in one warp (15 % of kernel time at 8 devices,
+# DESIGN.md section 6).  Output slot s of a range holds ray first + (s ÷ block) * stride * block + s % block (0-based).
+function _ranges(ic::CIC, ndev)
+    h = ic.kind == 0 ? ic.height : ic.kind == 1 ? ic.width : 0
+    strip = 4h
+    if ndev == 1
+        return [CRange(0, ic.n, 1, 1)]
+    elseif strip > 0 && ic.n % strip == 0
+        nstrips = ic.n ÷ strip
+        return [CRange(d * strip, (d < nstrips ? (nstrips - d + ndev - 1) ÷ ndev : 0) * strip, ndev, strip) for d = 0:ndev-1]
+    end
+    [CRange(d, ic.n > d ? (ic.n - d + ndev - 1) ÷ ndev : 0, ndev, 1) for d = 0:ndev-1]
+end
+_ray_of_slot(r::CRange, s) = r.first + (s ÷ r.block) * r.stride * r.block + s % r.block   # 0-based
+
+# run f(device_index, context, range) for every device on its own task (the library call blocks; contexts are
+# independent, one thread at a time per context)
+function _foreach_device(f, e::EnsembleB200, ranges)
+    tasks = map(1:length(e.devices)) do d
+        Threads.@spawn ranges[d].count > 0 && f(d, _context(e, d), ranges[d])
+    end
+    foreach(fetch, tasks)
+end
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the seam: ensemble_solve_tracing_problem(::EnsembleB200, ...) -> Vector{GeodesicPoint}
 function Gradus.ensemble_solve_tracing_problem(
     ensemble::EnsembleB200,
     problem::SciMLBase.EnsembleProblem,
@@ -119,47 +269,150 @@ function Gradus.ensemble_solve_tracing_problem(
     solver_opts...,
 ) where {T}
     save_on && error("Cannot use `EnsembleB200` with `save_on`")                      # tracing.jl:159-161
-    isempty(solver_opts) || throw(ArgumentError("unrecognised solver options $(keys(solver_opts))"))  # KeywordArgError
-    config.solver isa Gradus.Tsit5 || throw(ArgumentError("EnsembleB200 integrates with Tsit5 only"))
-    isnothing(progress_bar) || @warn "Progress bar not supported with EnsembleB200"
-    mk, mp = _metric(config.metric)
-    gk, gp = _geometry(config.geometry)
-    ck, cδ = _callback(config.callback)
-    chart = config.chart::PolarChart
+    isnothing(progress_bar) || @warn "Progress bar not supported with EnsembleB200" maxlog = 1
     keep = Any[]
-    p = CProblem(mk, gk, ck, 0, mp, Tuple(Float64.(config.position)), gp, 1e-2, chart.inner_radius, chart.outer_radius, cδ,
-                 config.λ_domain[1], config.λ_domain[2], config.abstol, config.reltol, 0.0, 0.0, 0)
-    ic = _ic(config, problem, keep)
-    n = ic.n
-    status = Vector{Int32}(undef, n); λ = Vector{Float64}(undef, n)
-    x = [Vector{Float64}(undef, n) for _ = 1:4]; v = [Vector{Float64}(undef, n) for _ = 1:4]
-    x0 = [Vector{Float64}(undef, n) for _ = 1:4]; v0 = [Vector{Float64}(undef, n) for _ = 1:4]
-    ndev = length(ensemble.devices)
-    GC.@preserve keep status λ x v x0 v0 begin
-        Threads.@threads for d = 1:ndev                 # contiguous ray blocks, one context per GPU
-            first = (d - 1) * n ÷ ndev; count = d * n ÷ ndev - first
-            ctx = Ref{Ptr{Cvoid}}()
-            _check(ccall((:gb200_init, libgradus_b200), Cint, (Cint, Ref{Ptr{Cvoid}}), ensemble.devices[d], ctx), C_NULL)
-            off(a) = pointer(a, first + 1)
-            out = CEndpoints(off(status), off(λ), Tuple(off.(x)), Tuple(off.(v)), Tuple(off.(x0)), Tuple(off.(v0)), C_NULL, C_NULL, C_NULL)
-            rc = ccall((:gb200_trace, libgradus_b200), Cint, (Ptr{Cvoid}, Ref{CProblem}, Ref{CIC}, Ref{CRange}, Ref{CEndpoints}),
-                       ctx[], p, ic, CRange(first, count, 1, 1), out)
-            _check(rc, ctx[])
-            ccall((:gb200_destroy, libgradus_b200), Cvoid, (Ptr{Cvoid},), ctx[])
+    n = config.trajectories
+    ic = _structured_ic(config, keep)
+    # explicit states arrive constrained for the trace's own μ: mu = NaN tells the library to keep v^t as given
+    p = isnothing(ic) ? _problem(config, problem.prob; mu = NaN, solver_opts...) : _problem(config, problem.prob; solver_opts...)
+    isnothing(ic) && (ic = _explicit_ic(problem, n, keep))
+    ranges = _ranges(ic, length(ensemble.devices))
+    outs = map(ranges) do r
+        (status = Vector{Int32}(undef, r.count), λ = Vector{Float64}(undef, r.count),
+         x = [Vector{Float64}(undef, r.count) for _ = 1:4], v = [Vector{Float64}(undef, r.count) for _ = 1:4],
+         x0 = [Vector{Float64}(undef, r.count) for _ = 1:4], v0 = [Vector{Float64}(undef, r.count) for _ = 1:4])
+    end
+    GC.@preserve keep outs begin
+        _foreach_device(ensemble, ranges) do d, ctx, r
+            o = outs[d]
+            ep = CEndpoints(pointer(o.status), pointer(o.λ), Tuple(pointer.(o.x)), Tuple(pointer.(o.v)), Tuple(pointer.(o.x0)),
+                            Tuple(pointer.(o.v0)), C_NULL, C_NULL, C_NULL)
+            _check(ccall((:gb200_trace, libgradus_b200), Cint, (Ptr{Cvoid}, Ref{CProblem}, Ref{CIC}, Ref{CRange}, Ref{CEndpoints}),
+                         ctx, p, ic, r, ep), ctx)
         end
     end
     # return contract of tracing.jl:179-189: a concretely typed Vector{GeodesicPoint{T,Nothing}} in ray order
-    map(1:n) do i
-        GeodesicPoint(StatusCodes.T(status[i]), T(config.λ_domain[1]), λ[i],
-                      SVector{4,T}(x0[1][i], x0[2][i], x0[3][i], x0[4][i]), SVector{4,T}(x[1][i], x[2][i], x[3][i], x[4][i]),
-                      SVector{4,T}(v0[1][i], v0[2][i], v0[3][i], v0[4][i]), SVector{4,T}(v[1][i], v[2][i], v[3][i], v[4][i]), nothing)
+    points = Vector{GeodesicPoint{T,Nothing}}(undef, n)
+    λ0 = T(config.λ_domain[1])
+    for (r, o) in zip(ranges, outs)
+        Threads.@threads for s = 0:r.count-1
+            j = s + 1
+            points[_ray_of_slot(r, s)+1] = GeodesicPoint(
+                StatusCodes.T(o.status[j]), λ0, T(o.λ[j]),
+                SVector{4,T}(o.x0[1][j], o.x0[2][j], o.x0[3][j], o.x0[4][j]), SVector{4,T}(o.x[1][j], o.x[2][j], o.x[3][j], o.x[4][j]),
+                SVector{4,T}(o.v0[1][j], o.v0[2][j], o.v0[3][j], o.v0[4][j]), SVector{4,T}(o.v[1][j], o.v[2][j], o.v[3][j], o.v[4][j]),
+                nothing)
+        end
     end
+    points
 end
 
-# device-side initial conditions for the two structured generators: the closures of the reference become data
-Gradus._render_velocity_function(m::Union{KerrMetric{T},JohannsenPsaltisMetric{T}}, position, w, h, αlims, βlims) where {T} =
-    RenderGridVelocity{T}(w, h, T.(αlims), T.(βlims))
-# (when the ensemble is not EnsembleB200 the maintainer keeps the stock closure: dispatch on the ensemble in render_configuration)
+# ---------------------------------------------------------------------------------------------------------------------
+# fused paths
+"""
+    B200PointFunction(:redshift | :radius | :shadow | :coordinate_time | :status | :affine_time | :end_radius)
 
-export EnsembleB200
+A point function the device evaluates at the ray end point inside the trace kernel (include/gradus_b200.h, GB200_PF_*):
+`:redshift` = `ConstPointFunctions.redshift(m, x) ∘ ConstPointFunctions.filter_intersected()`, `:radius` =
+`PointFunction((m, gp, λ) -> gp.x[2] * sin(gp.x[3])) ∘ filter_intersected()`, `:shadow` = the default `pf` of
+`render_into_image!` (affine time of rays that ended early), ...  Pass it as `pf = ...` to `rendergeodesics`.
+"""
+struct B200PointFunction
+    kind::Int32
+end
+const _PF_KINDS = Dict(:shadow => 0, :redshift => 1, :radius => 2, :coordinate_time => 3, :status => 4, :affine_time => 5, :end_radius => 6)
+B200PointFunction(s::Symbol) = B200PointFunction(Int32(_PF_KINDS[s]))
+
+const _B200Config{T} = TracingConfiguration{T,M,P,V,G,C,Ch,S,<:EnsembleB200} where {M,P,V,G,C,Ch,S}
+
+"""
+`render_into_image!` (src/rendering/rendering.jl:89-102) for an `EnsembleB200` configuration and a device point function:
+one fused launch per device writes the (H, W) column-major image; no `GeodesicPoint` is materialised.  Any other `pf`
+takes the stock method (trace on the GPU through `ensemble_solve_tracing_problem`, point function on the host).
+"""
+function Gradus.render_into_image!(image, trace::AbstractTrace, config::_B200Config{T}; pf = B200PointFunction(:shadow), solver_opts...) where {T}
+    if !(pf isa B200PointFunction)
+        return invoke(Gradus.render_into_image!, Tuple{Any,AbstractTrace,TracingConfiguration{T}}, image, trace, config; pf = pf, solver_opts...)
+    end
+    problem = Gradus.assemble_tracing_problem(trace, config)
+    keep = Any[]
+    ic = _structured_ic(config, keep)
+    isnothing(ic) && throw(ArgumentError("render_into_image! needs the render-grid velocity function"))
+    p = _problem(config, problem.prob; mu = Float64(trace.μ), solver_opts...)
+    ensemble = config.ensemble
+    ranges = _ranges(ic, length(ensemble.devices))
+    pfs = Int32[pf.kind]
+    if length(ranges) == 1          # the whole image in ray order: write straight into `image`
+        GC.@preserve keep image pfs begin
+            imgs = [pointer(image)]
+            _check(ccall((:gb200_render, libgradus_b200), Cint,
+                         (Ptr{Cvoid}, Ref{CProblem}, Ref{CIC}, Ref{CRange}, Ptr{Int32}, Int32, Ptr{Cvoid}, Ptr{Ptr{Float64}}),
+                         _context(ensemble, 1), p, ic, ranges[1], pfs, 1, C_NULL, imgs), _context(ensemble, 1))
+        end
+    else
+        parts = [Vector{T}(undef, r.count) for r in ranges]
+        GC.@preserve keep parts pfs begin
+            _foreach_device(ensemble, ranges) do d, ctx, r
+                imgs = [pointer(parts[d])]
+                _check(ccall((:gb200_render, libgradus_b200), Cint,
+                             (Ptr{Cvoid}, Ref{CProblem}, Ref{CIC}, Ref{CRange}, Ptr{Int32}, Int32, Ptr{Cvoid}, Ptr{Ptr{Float64}}),
+                             ctx, p, ic, r, pfs, 1, C_NULL, imgs), ctx)
+            end
+        end
+        for (r, part) in zip(ranges, parts), b = 0:(r.count ÷ r.block)-1     # whole strips are contiguous in the image
+            dst = r.first + b * r.stride * r.block
+            copyto!(image, dst + 1, part, b * r.block + 1, r.block)
+        end
+    end
+    image
+end
+
+"""
+    lineprofile_b200(bins, ε, m, u, d; ensemble = EnsembleB200(), λ_max, minrₑ, maxrₑ, plane, callback, power_law_index, solver_args...)
+
+`lineprofile(bins, ε, m, u, d, BinningMethod(); ...)` (src/line-profiles.jl:152-198) fused on the device: trace, redshift,
+`ε(rₑ) g³ area`, and the `Buckets.Simple` histogram in shared memory; with several devices the raw histograms are summed
+with one NCCL all-reduce inside the library (`gb200_comm_lineprofile`).  `ε` crosses the ABI as a power-law index when
+`power_law_index` is given (`ε(r) = r^-index`), otherwise as a 4096-point table of `ε` on a geometric grid over
+[minrₑ, maxrₑ] (linear interpolation: 1e-6 relative for power laws).  Returns `(bins, flux ./ sum(flux))`.
+"""
+function lineprofile_b200(bins, ε, m::Gradus.AbstractMetric{T}, u, d;
+                          ensemble::EnsembleB200 = EnsembleB200(), λ_max = 2 * u[2], minrₑ = Gradus.isco(m), maxrₑ = T(50),
+                          plane::PolarPlane = PolarPlane(GeometricGrid(); Nr = 450, Nθ = 1300, r_max = 5maxrₑ),
+                          callback = Gradus.domain_upper_hemisphere(), power_law_index = nothing, solver_args...) where {T}
+    trace = Gradus.TraceGeodesic()
+    config, solver_opts = Gradus.tracing_configuration(trace, m, u, plane, d, (0.0, λ_max); callback = callback, ensemble = ensemble, solver_args...)
+    problem = Gradus.assemble_tracing_problem(trace, config)
+    p = _problem(config, problem.prob; mu = 0.0, solver_opts...)
+    ic = _plane_ic(plane)
+    binsv = collect(Float64, bins)
+    rs = isnothing(power_law_index) ? collect(exp.(range(log(minrₑ), log(maxrₑ), 4096))) : Float64[]
+    es = isnothing(power_law_index) ? Float64.(ε.(rs)) : Float64[]
+    flux = zeros(Float64, length(binsv))
+    GC.@preserve binsv rs es flux begin
+        emis = isnothing(power_law_index) ? CEmissivity(1, length(rs), 0.0, pointer(rs), pointer(es)) :
+               CEmissivity(0, 0, Float64(power_law_index), C_NULL, C_NULL)
+        opts = CLineProfileOpts(minrₑ, maxrₑ, 1, 0)
+        if length(ensemble.devices) == 1
+            ctx = _context(ensemble, 1)
+            _check(ccall((:gb200_lineprofile, libgradus_b200), Cint,
+                         (Ptr{Cvoid}, Ref{CProblem}, Ref{CIC}, Ref{CRange}, Ref{CEmissivity}, Ptr{Cvoid}, Ptr{Float64}, Int32, Ref{CLineProfileOpts}, Ptr{Float64}),
+                         ctx, p, ic, CRange(0, ic.n, 1, 1), emis, C_NULL, binsv, length(binsv), opts, flux), ctx)
+        else
+            comm = Ref{Ptr{Cvoid}}(C_NULL)
+            devs = Int32.(ensemble.devices)
+            _check(ccall((:gb200_comm_init, libgradus_b200), Cint, (Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}), devs, length(devs), comm), C_NULL)
+            try
+                _check(ccall((:gb200_comm_lineprofile, libgradus_b200), Cint,
+                             (Ptr{Cvoid}, Ref{CProblem}, Ref{CIC}, Ref{CEmissivity}, Ptr{Cvoid}, Ptr{Float64}, Int32, Ref{CLineProfileOpts}, Ptr{Float64}),
+                             comm[], p, ic, emis, C_NULL, binsv, length(binsv), opts, flux), C_NULL)
+            finally
+                ccall((:gb200_comm_destroy, libgradus_b200), Cvoid, (Ptr{Cvoid},), comm[])
+            end
+        end
+    end
+    bins, flux
+end
+
+export EnsembleB200, B200PointFunction, lineprofile_b200
 end # module

@@ -92,3 +92,18 @@ def test_range_helpers_partition_the_rays():
         seen = np.concatenate([gd.strip_interleaved_range(ic, r, world).indices() for r in range(world)])
         assert sorted(seen.tolist()) == list(range(384))
         assert all(gd.strip_interleaved_range(ic, r, world).block == 64 for r in range(world))
+    # ray lists have no strips (ic.width = 0 must not divide), Cartesian planes use their mirrored column height
+    from gradus_b200 import api
+
+    al = np.linspace(-3, 3, 37)
+    _, ic = tracing_configuration(gb.KerrMetric(), [0.0, 100.0, 1.0, 0.0], api.ImpactParameters(al, al), gb.DatumPlane(0.0), 200.0).to_c()
+    for world in (1, 2, 5):
+        seen = np.concatenate([gd.strip_interleaved_range(ic, r, world).indices() for r in range(world)])
+        assert sorted(seen.tolist()) == list(range(37))
+    plane = gb.CartesianPlane(gb.LinearGrid(), Nx=18, Ny=34, x_max=20.0, y_max=20.0)  # 17 columns of 33 rays
+    _, ic = tracing_configuration(gb.KerrMetric(), [0.0, 100.0, 1.0, 0.0], plane, (0.0, 200.0)).to_c()
+    assert ic.n == 33 * 17
+    for world in (1, 2, 3):
+        rngs = [gd.strip_interleaved_range(ic, r, world) for r in range(world)]
+        seen = np.concatenate([r_.indices() for r_ in rngs])
+        assert sorted(seen.tolist()) == list(range(ic.n))

@@ -19,14 +19,15 @@ def main():
     chart = gb.chart_for_metric(m, 2e5, closest_approach=1.005)
     pr = gb.DeviceProber(m, x, d, chart=chart)
     tf.cunningham_transfer_function(m, x, d, 7.0, prober=pr)  # warm-up
-    for nr in (1, 16, 150):
-        radii = np.geomspace(gb.isco(m) + 1e-2, 1000.0, nr) if nr > 1 else [7.0]
-        pr.launches = pr.rays = 0
-        t0 = time.perf_counter()
-        out = tf.cunningham_transfer_functions(m, x, d, radii, prober=pr)
-        dt = time.perf_counter() - t0
-        print(f"device: {nr:4d} radii  {dt*1e3:9.1f} ms  {pr.launches} launches  {pr.rays} rays  "
-              f"{dt/nr*1e3:8.2f} ms/radius  measure[0]={tf.measure_ctf(out[0]):.6f}", flush=True)
+    for mode, kw in (("exact", {}), ("fast", {"warm_start": True, "stall_exit": 6})):
+        for nr in (1, 16, 150):
+            radii = np.geomspace(gb.isco(m) + 1e-2, 1000.0, nr) if nr > 1 else [7.0]
+            pr.launches = pr.rays = 0
+            t0 = time.perf_counter()
+            out = tf.cunningham_transfer_functions(m, x, d, radii, prober=pr, **kw)
+            dt = time.perf_counter() - t0
+            print(f"device ({mode}): {nr:4d} radii  {dt*1e3:9.1f} ms  {pr.launches} launches  {pr.rays} rays  "
+                  f"{dt/nr*1e3:8.2f} ms/radius  {dt/pr.launches*1e3:6.2f} ms/launch  measure[0]={tf.measure_ctf(out[0]):.6f}", flush=True)
     if "--oracle" in sys.argv:
         from common import OracleProber
         po = OracleProber(m, x, d, chart=chart)
