@@ -34,6 +34,7 @@ from .api import (  # noqa: F401
     ShakuraSunyaev,
     StatusCodes,
     TabulatedEmissivity,
+    ThickDisc,
     ThinDisc,
     TracingConfiguration,
     EndpointCache,

@@ -16,7 +16,7 @@ OK = 0
 ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = -1, -2, -3, -4, -5
 STATUS_OUT_OF_DOMAIN, STATUS_WITHIN_INNER_BOUNDARY, STATUS_INTERSECTED, STATUS_NO_STATUS = 0, 1, 2, 3
 METRIC_KERR, METRIC_JP, METRIC_JOHANNSEN, METRIC_BUMBLEBEE, METRIC_KERR_NEWMAN = 0, 1, 2, 3, 4
-GEOMETRY_NONE, GEOMETRY_THIN_DISC, GEOMETRY_SHAKURA_SUNYAEV, GEOMETRY_DATUM_PLANE = 0, 1, 2, 3
+GEOMETRY_NONE, GEOMETRY_THIN_DISC, GEOMETRY_SHAKURA_SUNYAEV, GEOMETRY_DATUM_PLANE, GEOMETRY_THICK_TABLE = 0, 1, 2, 3, 4
 CALLBACK_NONE, CALLBACK_UPPER_HEMISPHERE = 0, 1
 POW_EXACT, POW_FAST32 = 0, 1
 IC_RENDER_GRID, IC_POLAR_PLANE, IC_EXPLICIT, IC_CARTESIAN_PLANE, IC_IMPACT_PARAMETERS = 0, 1, 2, 3, 4
@@ -108,6 +108,7 @@ EXPORTED_SYMBOLS = (
     "gb200_isco", "gb200_radiative_efficiency", "gb200_trace", "gb200_trace_batch", "gb200_trace_path", "gb200_build_plunging_table", "gb200_render", "gb200_lineprofile",
     "gb200_render_batch", "gb200_render_device", "gb200_lineprofile_device", "gb200_fp64_peak", "gb200_fp64_issue_probe", "gb200_debug_rhs", "gb200_debug_math",
     "gb200_trace_dual", "gb200_trace_dual_batch",
+    "gb200_set_cross_section", "gb200_bucket2d", "gb200_comm_init", "gb200_comm_destroy", "gb200_comm_size", "gb200_comm_context", "gb200_comm_lineprofile", "gb200_comm_render",
 )
 
 
@@ -235,9 +236,20 @@ def load():
     lib.gb200_trace_dual.argtypes = [vp, C.POINTER(Problem), C.POINTER(DualIC), C.c_int32, C.POINTER(PlungingTable), C.POINTER(DualOut)]
     lib.gb200_trace_dual_batch.argtypes = [vp, C.c_int32, C.POINTER(Problem), C.POINTER(DualIC), C.c_int32,
                                            C.POINTER(C.POINTER(PlungingTable)), C.POINTER(DualOut)]
+    lib.gb200_set_cross_section.argtypes = [vp, _dp, _dp, C.c_int32]
+    lib.gb200_bucket2d.argtypes = [vp, C.c_int64, _dp, _dp, _dp, _dp, C.c_int32, _dp, C.c_int32, _dp]
+    lib.gb200_comm_init.argtypes = [_ip, C.c_int32, C.POINTER(vp)]
+    lib.gb200_comm_destroy.argtypes = [vp]
+    lib.gb200_comm_destroy.restype = None
+    lib.gb200_comm_size.argtypes = [vp]
+    lib.gb200_comm_context.argtypes = [vp, C.c_int32]
+    lib.gb200_comm_context.restype = vp
+    lib.gb200_comm_lineprofile.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Emissivity), C.POINTER(PlungingTable), _dp, C.c_int32,
+                                           C.POINTER(LineProfileOpts), _dp]
+    lib.gb200_comm_render.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), _ip, C.c_int32, C.POINTER(PlungingTable), C.POINTER(_dp)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("gb200_destroy", "gb200_last_error", "gb200_version"):
+        if name not in ("gb200_destroy", "gb200_last_error", "gb200_version", "gb200_comm_destroy", "gb200_comm_context"):
             fn.restype = C.c_int
     _lib = lib
     return lib

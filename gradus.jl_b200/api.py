@@ -185,7 +185,34 @@ class ShakuraSunyaev:
         return np.where(rho < self.inner_radius, -0.0, h)
 
 
-_SUPPORTED_GEOMETRY = (ThinDisc, ShakuraSunyaev, DatumPlane)
+class ThickDisc:
+    """`ThickDisc(f; inner_radius, outer_radius)` (src/geometry/discs/thick-disc.jl:32-52): a disc whose height above the
+    equatorial plane is the closure `f(ρ)` (non-positive where there is no disc).  A closure cannot cross the C ABI, so it is
+    tabulated once: `n` Chebyshev nodes over `support = (ρ_lo, ρ_hi)` -- they crowd towards the ends as 1/n², which resolves
+    the square-root edges of tori -- and the device interpolates linearly (GB200_GEOMETRY_THICK_TABLE); outside the support
+    there is no disc."""
+
+    def __init__(self, f, support, n=4097, inner_radius=0.0, outer_radius=float("inf")):
+        lo, hi = float(support[0]), float(support[1])
+        if not (hi > lo) or n < 2:
+            raise ValueError("ThickDisc needs support = (lo, hi) with hi > lo and n >= 2")
+        k = np.arange(n)
+        self.rho = np.ascontiguousarray(0.5 * (lo + hi) - 0.5 * (hi - lo) * np.cos(math.pi * k / (n - 1)))
+        self.rho[0], self.rho[-1] = lo, hi
+        self.height = np.ascontiguousarray([float(f(r)) for r in self.rho])
+        self.f, self.inner_radius, self.outer_radius = f, float(inner_radius), float(outer_radius)
+
+    def to_c(self):
+        return cabi.GEOMETRY_THICK_TABLE, (float(self.height.max()), float(self.rho[0]), float(self.rho[-1]), 0.0)
+
+    def cross_section(self, rho):
+        return np.interp(rho, self.rho, self.height, left=-1.0, right=-1.0)
+
+    def install(self, ctx):
+        cabi.check(cabi.load().gb200_set_cross_section(ctx, cabi.dptr(self.rho), cabi.dptr(self.height), len(self.rho)), ctx)
+
+
+_SUPPORTED_GEOMETRY = (ThinDisc, ShakuraSunyaev, DatumPlane, ThickDisc)
 
 
 # --------------------------------------------------------------------------- charts and callbacks
@@ -295,6 +322,7 @@ class EnsembleB200:
         if not self.devices:
             raise ValueError("EnsembleB200 needs at least one device")
         self._ctx = {}
+        self._comm = None
 
     def ctx(self, device, slot=0):
         """Context for `device`; `slot` distinguishes several contexts on the same device (one per host thread)."""
@@ -305,10 +333,26 @@ class EnsembleB200:
             self._ctx[key] = h
         return self._ctx[key]
 
+    def comm(self):
+        """The library's own multi-device communicator over `devices` (`gb200_comm_init`: one context per device plus an
+        NCCL communicator, all in this process) -- what a Julia caller uses.  None for a single device or a list that
+        names a device twice (those run through per-device contexts on host threads)."""
+        if len(self.devices) < 2 or len(set(self.devices)) != len(self.devices):
+            return None
+        if self._comm is None:
+            h = C.c_void_p()
+            devs = np.array(self.devices, np.int32)
+            cabi.check(cabi.load().gb200_comm_init(cabi.iptr(devs), len(devs), C.byref(h)))
+            self._comm = h
+        return self._comm
+
     def close(self):
         for h in self._ctx.values():
             cabi.load().gb200_destroy(h)
         self._ctx = {}
+        if self._comm is not None:
+            cabi.load().gb200_comm_destroy(self._comm)
+            self._comm = None
 
     def __del__(self):
         try:
@@ -561,7 +605,7 @@ def _shards(n, ndev):
     return out
 
 
-def _run_sharded(ensemble, n, fn):
+def _run_sharded(ensemble, n, fn, geometry=None):
     """Call fn(ctx, first, count, slot) for each device concurrently (ctypes drops the GIL)."""
     devs = ensemble.devices
     shards = [(i, d, f, c) for i, (d, (f, c)) in enumerate(zip(devs, _shards(n, len(devs)))) if c > 0]
@@ -570,7 +614,10 @@ def _run_sharded(ensemble, n, fn):
     def work(i, dev, first, count):
         try:
             # a device listed twice gets two contexts: a context is used by one thread at a time
-            fn(ensemble.ctx(dev, devs[:i].count(dev)), first, count, i)
+            ctx = ensemble.ctx(dev, devs[:i].count(dev))
+            if geometry is not None and hasattr(geometry, "install"):
+                geometry.install(ctx)
+            fn(ctx, first, count, i)
         except Exception as e:  # noqa: BLE001
             errs.append(e)
 
@@ -584,6 +631,13 @@ def _run_sharded(ensemble, n, fn):
     if errs:
         raise errs[0]
     return shards
+
+
+def _install_on_comm(comm, geometry):
+    if geometry is not None and hasattr(geometry, "install"):
+        lib = cabi.load()
+        for i in range(lib.gb200_comm_size(comm)):
+            geometry.install(C.c_void_p(lib.gb200_comm_context(comm, i)))
 
 
 def solve_tracing_problem(config: TracingConfiguration) -> GeodesicPoints:
@@ -607,7 +661,7 @@ def solve_tracing_problem(config: TracingConfiguration) -> GeodesicPoints:
         rng = cabi.Range(first, count, 1)
         cabi.check(lib.gb200_trace(ctx, C.byref(p), C.byref(ic), C.byref(rng), C.byref(view)), ctx)
 
-    _run_sharded(config.ensemble, n, fn)
+    _run_sharded(config.ensemble, n, fn, config.geometry)
     return GeodesicPoints(out, config.lambda_domain[0])
 
 
@@ -806,12 +860,19 @@ def apply_point_functions(config, pfs, plunging=None):
     plunging = _auto_plunging(config.metric, config.geometry, config.ensemble, cabi.PF_REDSHIFT in kinds, plunging)
     pl_ref = C.byref(plunging.c) if plunging is not None else None
 
+    comm = config.ensemble.comm()
+    if comm is not None:  # several GPUs: strips interleaved over the devices inside the library
+        _install_on_comm(comm, config.geometry)
+        ptrs = (cabi._dp * len(pfs))(*[cabi.dptr(images[k]) for k in range(len(pfs))])
+        cabi.check(lib.gb200_comm_render(comm, C.byref(p), C.byref(ic), cabi.iptr(kinds), len(pfs), pl_ref, ptrs))
+        return images
+
     def fn(ctx, first, count, slot):
         ptrs = (cabi._dp * len(pfs))(*[C.cast(images[k].ctypes.data + 8 * first, cabi._dp) for k in range(len(pfs))])
         rng = cabi.Range(first, count, 1)
         cabi.check(lib.gb200_render(ctx, C.byref(p), C.byref(ic), C.byref(rng), cabi.iptr(kinds), len(pfs), pl_ref, ptrs), ctx)
 
-    _run_sharded(config.ensemble, n, fn)
+    _run_sharded(config.ensemble, n, fn, config.geometry)
     return images
 
 
@@ -978,6 +1039,14 @@ def lineprofile(bins, emissivity, m, position, d, method=None, *, lambda_max=Non
     opts = cabi.LineProfileOpts(float(min_re), float(max_re), 0, 1 if bin_right_closed else 0)
     plunging = _auto_plunging(m, d, config.ensemble, min_re < (isco(m) if not isinstance(m, KerrMetric) else 0.0), plunging)
     pl_ref = C.byref(plunging.c) if plunging is not None else None
+    comm = config.ensemble.comm()
+    if comm is not None:  # several GPUs: sharded inside the library, histograms summed with one NCCL all-reduce
+        _install_on_comm(comm, config.geometry)
+        flux = np.zeros(len(bins))
+        opts.normalise = 1
+        cabi.check(lib.gb200_comm_lineprofile(comm, C.byref(p), C.byref(ic), C.byref(emis), pl_ref, cabi.dptr(bins), len(bins), C.byref(opts),
+                                              cabi.dptr(flux)))
+        return bins, flux
     ndev = len(config.ensemble.devices)
     partial = np.zeros((ndev, len(bins)))
 
@@ -986,6 +1055,6 @@ def lineprofile(bins, emissivity, m, position, d, method=None, *, lambda_max=Non
         cabi.check(lib.gb200_lineprofile(ctx, C.byref(p), C.byref(ic), C.byref(rng), C.byref(emis), pl_ref,
                                          cabi.dptr(bins), len(bins), C.byref(opts), cabi.dptr(partial[slot])), ctx)
 
-    _run_sharded(config.ensemble, n, fn)
+    _run_sharded(config.ensemble, n, fn, config.geometry)
     flux = partial.sum(axis=0)  # fixed device order: deterministic
     return bins, flux / flux.sum()

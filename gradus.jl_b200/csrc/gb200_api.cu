@@ -3,6 +3,8 @@
 // No CPU implementation of the path exists in this library: every compute entry point runs
 // the sm_100a kernels of gb200_trace.cu or fails.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h> // types and enums only: the library is opened at run time (see gb200_comm_init)
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -44,6 +46,10 @@ struct gb200_ctx {
     // stream it works on wait for that event before touching the queue or the pool.
     cudaEvent_t inflight = nullptr;
     bool have_inflight = false;
+    // cross-section table of GB200_GEOMETRY_THICK_TABLE (gb200_set_cross_section)
+    double* d_cs = nullptr; // [rho (n) | height (n)]
+    int cs_n = 0;
+    double cs_max = 0.0;
 };
 
 static int fail(gb200_ctx* ctx, int code, const char* fmt, ...) {
@@ -150,13 +156,14 @@ static int validate(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic) 
         return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "Bumblebee metric needs l > -1 and |a| <= 0.3 (bumblebee-ad.jl:33-40)");
     if (p->metric_kind == GB200_METRIC_KERR_NEWMAN && a * a + p->metric_params[2] * p->metric_params[2] > M * M)
         return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "Kerr-Newman metric needs a^2 + Q^2 <= M^2 (kerr-newman-ad.jl:50-52)");
-    if (p->geometry_kind < GB200_GEOMETRY_NONE || p->geometry_kind > GB200_GEOMETRY_DATUM_PLANE)
+    if (p->geometry_kind < GB200_GEOMETRY_NONE || p->geometry_kind > GB200_GEOMETRY_THICK_TABLE)
         return fail(ctx, GB200_ERR_UNSUPPORTED, "geometry kind %d is outside the hot-path scope", p->geometry_kind);
     if (p->geometry_kind == GB200_GEOMETRY_THIN_DISC && !(p->geometry_params[0] <= p->geometry_params[1]))
         return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "ThinDisc needs inner_radius <= outer_radius");
     if (p->callback_kind != GB200_CALLBACK_NONE && p->callback_kind != GB200_CALLBACK_UPPER_HEMISPHERE)
         return fail(ctx, GB200_ERR_UNSUPPORTED, "callback kind %d cannot run on the device", p->callback_kind);
     if (p->pow_mode != GB200_POW_EXACT && p->pow_mode != GB200_POW_FAST32) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad pow_mode");
+    if (!(p->mu == p->mu) && ic->kind != GB200_IC_EXPLICIT) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "mu = NaN (keep v^t as given) needs explicit initial conditions");
     if (!(p->lambda_max > p->lambda_min)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "need lambda_max > lambda_min");
     if (!(p->abstol > 0) || !(p->reltol > 0)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "abstol and reltol must be positive");
     if (!(p->chart_outer > p->chart_inner)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "chart outer radius must exceed inner radius");
@@ -345,6 +352,15 @@ static int upload_ic_and_tables(gb200_ctx* ctx, const gb200_ic* ic, const gb200_
     return GB200_OK;
 }
 
+// GB200_GEOMETRY_THICK_TABLE: point the launch at the context's cross-section table
+static int bind_geometry(gb200_ctx* ctx, GbParams& P) {
+    if (P.geometry_kind != GB200_GEOMETRY_THICK_TABLE) return GB200_OK;
+    if (ctx->cs_n < 2) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "GB200_GEOMETRY_THICK_TABLE needs a table: call gb200_set_cross_section first");
+    P.cs_n = ctx->cs_n; P.cs_rho = ctx->d_cs; P.cs_h = ctx->d_cs + ctx->cs_n;
+    P.gp0 = ctx->cs_max;
+    return GB200_OK;
+}
+
 static bool needs_isco(const int32_t* pfs, int npf, bool lineprofile) {
     if (lineprofile) return true;
     for (int k = 0; k < npf; ++k) if (pfs[k] == GB200_PF_REDSHIFT) return true;
@@ -498,9 +514,27 @@ int gb200_init(int device, gb200_ctx** out) {
     return GB200_OK;
 }
 
+int gb200_set_cross_section(gb200_ctx* ctx, const double* rho, const double* height, int32_t n) {
+    if (!ctx) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null context");
+    if (n != 0 && (n < 2 || !rho || !height)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "cross-section table needs n >= 2 points");
+    for (int i = 1; i < n; ++i) if (!(rho[i] > rho[i - 1])) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "cross-section radii must be strictly increasing");
+    { int rc_ = begin_call(ctx, ctx->stream); if (rc_) return rc_; }
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); // nothing in flight may still read the old table
+    if (ctx->d_cs) { cudaFree(ctx->d_cs); ctx->d_cs = nullptr; }
+    ctx->cs_n = 0; ctx->cs_max = 0.0;
+    if (n == 0) return GB200_OK;
+    CU(ctx, cudaMalloc(&ctx->d_cs, sizeof(double) * 2 * (size_t)n));
+    CU(ctx, cudaMemcpy(ctx->d_cs, rho, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    CU(ctx, cudaMemcpy(ctx->d_cs + n, height, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    ctx->cs_n = n;
+    for (int i = 0; i < n; ++i) ctx->cs_max = std::max(ctx->cs_max, height[i]);
+    return GB200_OK;
+}
+
 void gb200_destroy(gb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->d_cs) cudaFree(ctx->d_cs);
     for (auto& b : ctx->pool) if (b.p) cudaFree(b.p);
     if (ctx->d_queue) cudaFree(ctx->d_queue);
     for (auto st : ctx->pool_streams) cudaStreamDestroy(st);
@@ -551,6 +585,7 @@ int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, cons
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     GbParams P;
     fill_params(p, ic, rg, P);
+    { int rcg_ = bind_geometry(ctx, P); if (rcg_) return rcg_; }
     rc = upload_ic_and_tables(ctx, ic, nullptr, nullptr, P); if (rc) return rc;
     const size_t n = (size_t)rg->count;
     void* d;
@@ -686,6 +721,7 @@ int gb200_trace_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* probl
         const Off& o = off[(size_t)b];
         GbParams P;
         fill_params(&problems[b], &ics[b], &ranges[b], P);
+        { int rcg_ = bind_geometry(ctx, P); if (rcg_) return rcg_; }
         if (ics[b].kind == GB200_IC_EXPLICIT)
             for (int k = 0; k < 4; ++k) { P.ex[k] = (const double*)(arena + o.ex[k]); P.ev[k] = (const double*)(arena + o.ev[k]); }
         if (out.status) P.o_status = (int32_t*)(arena + o.status);
@@ -752,6 +788,7 @@ int gb200_trace_path(gb200_ctx* ctx, const gb200_problem* p, const double* u0, i
     gb200_range rg{0, 1, 1};
     GbParams P;
     fill_params(p, &ic, &rg, P);
+    { int rcg_ = bind_geometry(ctx, P); if (rcg_) return rcg_; }
     P.geometry_kind = GB200_GEOMETRY_NONE; // a bare geodesic: chart boundaries and lambda_max only
     P.callback_kind = GB200_CALLBACK_NONE;
     void *d_u0, *d_lam, *d_u, *d_meta;
@@ -836,6 +873,7 @@ static int render_common(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic*
     CU(ctx, cudaEventRecord(ctx->ev0, stream));
     GbParams P;
     fill_params(p, ic, rg, P);
+    { int rcg_ = bind_geometry(ctx, P); if (rcg_) return rcg_; }
     if (needs_isco(pfs, npf, false)) { rc = set_isco(ctx, p, P); if (rc) return rc; }
     rc = upload_ic_and_tables(ctx, ic, pl, nullptr, P); if (rc) return rc;
     const size_t n = (size_t)rg->count;
@@ -948,6 +986,7 @@ int gb200_render_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* prob
         const Off& o = off[(size_t)b];
         GbParams P;
         fill_params(&problems[b], &ics[b], &ranges[b], P);
+        { int rcg_ = bind_geometry(ctx, P); if (rcg_) return rcg_; }
         if (want_isco) { rc = set_isco(ctx, &problems[b], P); if (rc) return rc; }
         if (ics[b].kind == GB200_IC_IMPACT_PARAMETERS)
             for (int k = 0; k < 3; ++k) P.ex[k] = ics[b].x[k] ? (const double*)(arena + o.ex[k]) : nullptr;
@@ -1073,6 +1112,7 @@ int gb200_trace_dual_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* 
         gb200_range rg{0, d.n, 1, 1};
         GbParams P;
         fill_params(&problems[b], &fake[(size_t)b], &rg, P);
+        { int rcg_ = bind_geometry(ctx, P); if (rcg_) return rcg_; }
         if (out.g) { rc = set_isco(ctx, &problems[b], P); if (rc) return rc; }
         if (pls && pls[b] && pls[b]->n >= 2) {
             P.pl_n = pls[b]->n;
@@ -1153,23 +1193,44 @@ static int lineprofile_common(gb200_ctx* ctx, const gb200_problem* p, const gb20
     CU(ctx, cudaEventRecord(ctx->ev0, stream));
     GbParams P;
     fill_params(p, ic, rg, P);
+    { int rcg_ = bind_geometry(ctx, P); if (rcg_) return rcg_; }
     rc = set_isco(ctx, p, P); if (rc) return rc;
     rc = upload_ic_and_tables(ctx, ic, pl, em, P); if (rc) return rc;
     P.min_re = opts->min_re; P.max_re = opts->max_re;
     const size_t n = (size_t)rg->count;
     void* d;
-    rc = pool_get(ctx, SL_G, n * sizeof(double) + 8, &d); if (rc) return rc; P.o_g = (double*)d;
-    rc = pool_get(ctx, SL_F, n * sizeof(double) + 8, &d); if (rc) return rc; P.o_f = (double*)d;
     const void* dbins;
     rc = upload(ctx, SL_BINS, bins, sizeof(double) * nbins, &dbins); if (rc) return rc;
-    const int nblocks = ctx->sm_count * 4;
-    rc = pool_get(ctx, SL_PARTIAL, sizeof(double) * (size_t)nblocks * nbins, &d); if (rc) return rc;
-    double* dpartial = (double*)d;
     double* dflux = flux;
     if (!device_out) { rc = pool_get(ctx, SL_FLUX, sizeof(double) * nbins, &d); if (rc) return rc; dflux = (double*)d; }
-    rc = run_trace(ctx, P, stream, true); if (rc) return rc;
-    CU(ctx, gb200_launch_hist(P.o_g, P.o_f, rg->count, (const double*)dbins, nbins, opts->bin_right_closed, dpartial, nblocks, dflux, stream));
-    ctx->stats.launches += 2;
+    // Fused path: the histogram is accumulated inside the trace kernel, per CTA in shared memory, as 128-bit fixed point
+    // (gb_hist_add).  The scale is a power of two chosen from a generous bound on sum f = sum eps(rho) g^3 area
+    // (g <= 1e3), so f * scale is exact and the bins hold the exact sum of the contributions, whatever the order.
+    double eps_max = 0.0;
+    if (em->kind == GB200_EMISSIVITY_POWERLAW) eps_max = std::max(std::pow(opts->min_re, -em->index), std::pow(opts->max_re, -em->index));
+    else for (int k = 0; k < em->n; ++k) eps_max = std::max(eps_max, std::fabs(em->eps[k]));
+    const double area_max = (ic->kind == GB200_IC_POLAR_PLANE) ? ic->hi0 * ic->hi0 : 1.0;
+    const double bound = (double)(n > 0 ? n : 1) * eps_max * 1e9 * area_max;
+    const bool fused = nbins <= 512 && std::isfinite(bound) && bound > 0.0 && !getenv("GB200_HIST_TWO_PASS");
+    if (fused) {
+        rc = pool_get(ctx, SL_PARTIAL, sizeof(unsigned long long) * 2 * (size_t)nbins, &d); if (rc) return rc;
+        P.lp_acc = (unsigned long long*)d;
+        P.lp_bins = (const double*)dbins; P.lp_nbins = nbins; P.lp_right_closed = opts->bin_right_closed;
+        P.lp_scale = std::exp2(std::floor(120.0 - std::log2(bound)));
+        CU(ctx, cudaMemsetAsync(P.lp_acc, 0, sizeof(unsigned long long) * 2 * (size_t)nbins, stream));
+        rc = run_trace(ctx, P, stream, true); if (rc) return rc;
+        CU(ctx, gb200_launch_hist128_finish(P.lp_acc, nbins, P.lp_scale, dflux, stream));
+        ctx->stats.launches += 1;
+    } else { // more bins than fit beside the stage data in shared memory: (g, f) per ray through HBM, then the binning kernels
+        rc = pool_get(ctx, SL_G, n * sizeof(double) + 8, &d); if (rc) return rc; P.o_g = (double*)d;
+        rc = pool_get(ctx, SL_F, n * sizeof(double) + 8, &d); if (rc) return rc; P.o_f = (double*)d;
+        const int nblocks = ctx->sm_count * 4;
+        rc = pool_get(ctx, SL_PARTIAL, sizeof(double) * (size_t)nblocks * nbins, &d); if (rc) return rc;
+        double* dpartial = (double*)d;
+        rc = run_trace(ctx, P, stream, true); if (rc) return rc;
+        CU(ctx, gb200_launch_hist(P.o_g, P.o_f, rg->count, (const double*)dbins, nbins, opts->bin_right_closed, dpartial, nblocks, dflux, stream));
+        ctx->stats.launches += 2;
+    }
     if (!device_out) {
         std::vector<double> h((size_t)nbins);
         CU(ctx, cudaMemcpyAsync(h.data(), dflux, sizeof(double) * nbins, cudaMemcpyDeviceToHost, stream));
@@ -1192,6 +1253,223 @@ int gb200_lineprofile_device(gb200_ctx* ctx, const gb200_problem* p, const gb200
                              double* d_flux, void* cuda_stream, int async) {
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : (ctx ? ctx->stream : nullptr);
     return lineprofile_common(ctx, p, ic, rg, em, pl, bins, nbins, opts, d_flux, true, s, async);
+}
+
+// ---------------------------------------------------------------- single-process multi-GPU (what a Julia caller uses)
+// NCCL is opened at run time (dlopen("libnccl.so.2")): a process that already holds an NCCL (PyTorch bundles one) shares it,
+// and a single-GPU caller needs none at all.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string* why) {
+        if (handle) return true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) { *why = dlerror() ? dlerror() : "libnccl.so.2 not found"; return false; }
+        CommInitAll = (decltype(CommInitAll))dlsym(handle, "ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
+        GroupStart = (decltype(GroupStart))dlsym(handle, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(handle, "ncclGroupEnd");
+        GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+        if (!CommInitAll || !CommDestroy || !AllReduce || !GroupStart || !GroupEnd || !GetErrorString) { *why = "libnccl lacks a required symbol"; return false; }
+        return true;
+    }
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mutex;
+
+struct gb200_comm {
+    std::vector<gb200_ctx*> ctx;
+    std::vector<ncclComm_t> nccl; // empty when ndev == 1 and NCCL is unavailable
+    std::vector<double*> d_flux;  // per device: nbins doubles
+    int flux_cap = 0;
+};
+#define NC(call)                                                                                                         \
+    do {                                                                                                                 \
+        ncclResult_t r__ = (call);                                                                                       \
+        if (r__ != ncclSuccess) return fail(nullptr, GB200_ERR_CUDA, "%s: %s", #call, g_nccl.GetErrorString(r__));       \
+    } while (0)
+
+// rank d's share of the rays: whole strips of four image columns / theta-rows, strip d, d + n, ...
+static gb200_range shard_range(const gb200_ic* ic, int d, int n) {
+    int64_t h = 0;
+    if (ic->kind == GB200_IC_RENDER_GRID) h = ic->height;
+    else if (ic->kind == GB200_IC_POLAR_PLANE) h = ic->width;
+    else if (ic->kind == GB200_IC_CARTESIAN_PLANE) h = 2 * (ic->height / 2) - 1;
+    const int64_t strip = GB_TILE_C * h;
+    if (n == 1) return gb200_range{0, ic->n, 1, 1};
+    if (strip > 0 && ic->n % strip == 0) {
+        const int64_t nstrips = ic->n / strip;
+        const int64_t mine = nstrips > d ? (nstrips - d + n - 1) / n : 0;
+        return gb200_range{(int64_t)d * strip, mine * strip, n, strip};
+    }
+    return gb200_range{d, ic->n > d ? (ic->n - d + n - 1) / n : 0, n, 1};
+}
+
+int gb200_comm_init(const int32_t* devices, int32_t ndev, gb200_comm** out) {
+    if (!devices || ndev < 1 || !out) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "bad communicator arguments");
+    *out = nullptr;
+    for (int a = 0; a < ndev; ++a)
+        for (int b = a + 1; b < ndev; ++b)
+            if (devices[a] == devices[b]) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "device %d listed twice", devices[a]);
+    gb200_comm* c = new gb200_comm();
+    for (int d = 0; d < ndev; ++d) {
+        gb200_ctx* ctx = nullptr;
+        int rc = gb200_init(devices[d], &ctx);
+        if (rc) { gb200_comm_destroy(c); return rc; }
+        c->ctx.push_back(ctx);
+    }
+    std::string why;
+    bool have;
+    { std::lock_guard<std::mutex> lock(g_nccl_mutex); have = g_nccl.load(&why); }
+    if (!have) {
+        if (ndev > 1) { gb200_comm_destroy(c); return fail(nullptr, GB200_ERR_UNSUPPORTED, "several devices need NCCL: %s", why.c_str()); }
+    } else {
+        c->nccl.resize((size_t)ndev);
+        std::vector<int> devs(devices, devices + ndev);
+        ncclResult_t r = g_nccl.CommInitAll(c->nccl.data(), ndev, devs.data());
+        if (r != ncclSuccess) { c->nccl.clear(); gb200_comm_destroy(c); return fail(nullptr, GB200_ERR_CUDA, "ncclCommInitAll: %s", g_nccl.GetErrorString(r)); }
+    }
+    *out = c;
+    return GB200_OK;
+}
+
+void gb200_comm_destroy(gb200_comm* c) {
+    if (!c) return;
+    for (size_t d = 0; d < c->ctx.size(); ++d) {
+        if (d < c->d_flux.size() && c->d_flux[d]) { cudaSetDevice(c->ctx[d]->device); cudaFree(c->d_flux[d]); }
+        if (d < c->nccl.size() && c->nccl[d]) g_nccl.CommDestroy(c->nccl[d]);
+        gb200_destroy(c->ctx[d]);
+    }
+    delete c;
+}
+
+int gb200_comm_size(gb200_comm* c) { return c ? (int)c->ctx.size() : 0; }
+gb200_ctx* gb200_comm_context(gb200_comm* c, int32_t i) { return (c && i >= 0 && i < (int)c->ctx.size()) ? c->ctx[(size_t)i] : nullptr; }
+
+int gb200_comm_lineprofile(gb200_comm* c, const gb200_problem* p, const gb200_ic* ic, const gb200_emissivity* em, const gb200_plunging_table* pl,
+                           const double* bins, int32_t nbins, const gb200_lineprofile_opts* opts, double* flux_out) {
+    if (!c || !ic || !opts || !flux_out) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null argument");
+    const int n = (int)c->ctx.size();
+    if (c->flux_cap < nbins) {
+        c->d_flux.resize((size_t)n, nullptr);
+        for (int d = 0; d < n; ++d) {
+            CU(c->ctx[(size_t)d], cudaSetDevice(c->ctx[(size_t)d]->device));
+            if (c->d_flux[(size_t)d]) cudaFree(c->d_flux[(size_t)d]);
+            CU(c->ctx[(size_t)d], cudaMalloc(&c->d_flux[(size_t)d], sizeof(double) * (size_t)nbins));
+        }
+        c->flux_cap = nbins;
+    }
+    // every device traces its strips and bins them into its own raw histogram (asynchronous launches, one host thread) ...
+    for (int d = 0; d < n; ++d) {
+        gb200_ctx* ctx = c->ctx[(size_t)d];
+        gb200_range rg = shard_range(ic, d, n);
+        int rc = lineprofile_common(ctx, p, ic, &rg, em, pl, bins, nbins, opts, c->d_flux[(size_t)d], true, ctx->stream, 1);
+        if (rc) return fail(nullptr, rc, "device %d: %s", ctx->device, ctx->err.c_str());
+    }
+    // ... one all-reduce over NVLink sums them in place on every device's own stream ...
+    if (n > 1) {
+        NC(g_nccl.GroupStart());
+        for (int d = 0; d < n; ++d) {
+            ncclResult_t r = g_nccl.AllReduce(c->d_flux[(size_t)d], c->d_flux[(size_t)d], (size_t)nbins, ncclDouble, ncclSum, c->nccl[(size_t)d], c->ctx[(size_t)d]->stream);
+            if (r != ncclSuccess) { g_nccl.GroupEnd(); return fail(nullptr, GB200_ERR_CUDA, "ncclAllReduce: %s", g_nccl.GetErrorString(r)); }
+        }
+        NC(g_nccl.GroupEnd());
+    }
+    // ... and device 0 hands the sum to the host, which normalises it (flux ./ sum(flux), line-profiles.jl:197)
+    std::vector<double> h((size_t)nbins);
+    CU(c->ctx[0], cudaSetDevice(c->ctx[0]->device));
+    CU(c->ctx[0], cudaMemcpyAsync(h.data(), c->d_flux[0], sizeof(double) * (size_t)nbins, cudaMemcpyDeviceToHost, c->ctx[0]->stream));
+    for (int d = 0; d < n; ++d) {
+        CU(c->ctx[(size_t)d], cudaSetDevice(c->ctx[(size_t)d]->device));
+        CU(c->ctx[(size_t)d], cudaStreamSynchronize(c->ctx[(size_t)d]->stream));
+    }
+    double tot = 0;
+    for (int b = 0; b < nbins; ++b) tot += h[(size_t)b];
+    for (int b = 0; b < nbins; ++b) flux_out[b] = opts->normalise ? h[(size_t)b] / tot : h[(size_t)b];
+    return GB200_OK;
+}
+
+int gb200_comm_render(gb200_comm* c, const gb200_problem* p, const gb200_ic* ic, const int32_t* pfs, int32_t npf,
+                      const gb200_plunging_table* pl, double* const* images) {
+    if (!c || !ic || !pfs || !images || npf < 1 || npf > GB_MAX_PF) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "bad render arguments");
+    const int n = (int)c->ctx.size();
+    std::vector<gb200_range> rgs((size_t)n);
+    std::vector<std::vector<double*>> dimg((size_t)n);
+    // all launches first (asynchronous), then the copies: the devices compute concurrently
+    for (int d = 0; d < n; ++d) {
+        gb200_ctx* ctx = c->ctx[(size_t)d];
+        rgs[(size_t)d] = shard_range(ic, d, n);
+        CU(ctx, cudaSetDevice(ctx->device));
+        dimg[(size_t)d].resize((size_t)npf);
+        for (int k = 0; k < npf; ++k) {
+            void* dv = nullptr;
+            int rc = pool_get(ctx, SL_IMG0 + k, sizeof(double) * (size_t)rgs[(size_t)d].count + 8, &dv);
+            if (rc) return fail(nullptr, rc, "device %d: %s", ctx->device, ctx->err.c_str());
+            dimg[(size_t)d][(size_t)k] = (double*)dv;
+        }
+        if (rgs[(size_t)d].count == 0) continue;
+        int rc = render_common(ctx, p, ic, &rgs[(size_t)d], pfs, npf, pl, dimg[(size_t)d].data(), true, ctx->stream, 1);
+        if (rc) return fail(nullptr, rc, "device %d: %s", ctx->device, ctx->err.c_str());
+    }
+    for (int d = 0; d < n; ++d) {
+        gb200_ctx* ctx = c->ctx[(size_t)d];
+        const gb200_range& rg = rgs[(size_t)d];
+        if (rg.count == 0) continue;
+        CU(ctx, cudaSetDevice(ctx->device));
+        const size_t blk = (size_t)(rg.block > 0 ? rg.block : 1);
+        for (int k = 0; k < npf; ++k) // strip b of this device sits at ray first + b * stride * block of the image
+            CU(ctx, cudaMemcpy2DAsync(images[k] + rg.first, sizeof(double) * blk * (size_t)rg.stride, dimg[(size_t)d][(size_t)k], sizeof(double) * blk,
+                                      sizeof(double) * blk, (size_t)rg.count / blk, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    for (int d = 0; d < n; ++d) {
+        CU(c->ctx[(size_t)d], cudaSetDevice(c->ctx[(size_t)d]->device));
+        CU(c->ctx[(size_t)d], cudaStreamSynchronize(c->ctx[(size_t)d]->stream));
+    }
+    return GB200_OK;
+}
+
+int gb200_bucket2d(gb200_ctx* ctx, int64_t n, const double* x, const double* y, const double* w, const double* xbins, int32_t nx,
+                   const double* ybins, int32_t ny, double* out) {
+    if (!ctx) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null context");
+    if (n < 0 || (n > 0 && (!x || !y || !w)) || !xbins || !ybins || !out || nx < 1 || ny < 1 || (int64_t)nx * ny > (1 << 26))
+        return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad bucket arguments");
+    for (int b = 1; b < nx; ++b) if (!(xbins[b] > xbins[b - 1])) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bins must be strictly increasing");
+    for (int b = 1; b < ny; ++b) if (!(ybins[b] > ybins[b - 1])) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bins must be strictly increasing");
+    { int rc_ = begin_call(ctx, ctx->stream); if (rc_) return rc_; }
+    long double tot = 0.0L;
+    for (int64_t i = 0; i < n; ++i) if (w[i] == w[i]) tot += fabsl((long double)w[i]);
+    const double scale = tot > 0.0L ? (double)(4611686018427387904.0L / tot) : 1.0; // 2^62 / sum |w|
+    void *dx, *dy, *dw, *dxb, *dyb, *dacc, *dout;
+    const size_t nb = sizeof(double) * (size_t)(n > 0 ? n : 1), ncell = (size_t)nx * ny;
+    int rc = pool_get(ctx, SL_G, nb, &dx); if (rc) return rc;
+    rc = pool_get(ctx, SL_F, nb, &dy); if (rc) return rc;
+    rc = pool_get(ctx, SL_X0, nb, &dw); if (rc) return rc;
+    rc = pool_get(ctx, SL_BINS, sizeof(double) * (size_t)(nx + ny), &dxb); if (rc) return rc;
+    dyb = (double*)dxb + nx;
+    rc = pool_get(ctx, SL_PARTIAL, sizeof(long long) * ncell, &dacc); if (rc) return rc;
+    rc = pool_get(ctx, SL_FLUX, sizeof(double) * ncell, &dout); if (rc) return rc;
+    if (n > 0) {
+        CU(ctx, cudaMemcpyAsync(dx, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(dy, y, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(dw, w, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(ctx, cudaMemcpyAsync(dxb, xbins, sizeof(double) * (size_t)nx, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(dyb, ybins, sizeof(double) * (size_t)ny, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, gb200_launch_bucket2d((const double*)dx, (const double*)dy, (const double*)dw, n, (const double*)dxb, nx, (const double*)dyb, ny, scale,
+                                  (long long*)dacc, (double*)dout, ctx->sm_count * 8, ctx->stream));
+    ctx->stats.launches = 2;
+    CU(ctx, cudaMemcpyAsync(out, dout, sizeof(double) * ncell, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB200_OK;
 }
 
 int gb200_debug_rhs(gb200_ctx* ctx, int32_t metric_kind, const double* mp, int64_t n, const double* u, double* du) {

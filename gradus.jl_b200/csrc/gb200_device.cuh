@@ -145,11 +145,21 @@ struct GbParams {
     // line profile: per-ray (g, f) written for the binning kernel
     double* o_g;
     double* o_f;
+    // fused line-profile histogram (lp_bins != nullptr): Buckets.Simple bins in HBM (read through L1), per-CTA 128-bit
+    // fixed-point bins in shared memory, flushed into lp_acc[2 * nbins] = (low words | high words) at the end of the CTA
+    const double* lp_bins;
+    int32_t lp_nbins, lp_right_closed;
+    double lp_scale;            // f is accumulated as round(f * lp_scale) in 128-bit integers
+    unsigned long long* lp_acc;
     double min_re, max_re;
     int32_t emis_kind, emis_n;
     double emis_index;
     const double* emis_r;
     const double* emis_eps;
+    // tabulated cross-section of GB200_GEOMETRY_THICK_TABLE (device pointers, rho ascending)
+    int32_t cs_n;
+    const double* cs_rho;
+    const double* cs_h;
     // redshift
     double r_isco;
     int32_t pl_n;
@@ -809,6 +819,15 @@ GB_HD inline double constrain_vt(const double g[5], double vr, double vth, doubl
     return -(g[4] * vph + sqrt(disc)) / g[0];
 }
 
+// cross_section(rho) of a tabulated ThickDisc: linear interpolation, -1 (no disc) outside the table
+GB_HD inline double cross_section_table(const double* xs, const double* ys, int n, double x) {
+    if (n < 2 || !(x >= xs[0]) || !(x <= xs[n - 1])) return -1.0;
+    int lo = 0, hi = n - 1; // last index with xs[idx] <= x, clamped to [0, n-2]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (xs[mid] <= x) lo = mid; else hi = mid; }
+    const double w = (x - xs[lo]) / (xs[lo + 1] - xs[lo]);
+    return (1.0 - w) * ys[lo] + w * ys[lo + 1];
+}
+
 // ---------------------------------------------------------------- disc conditions (distance_to_disc)
 // `hgt` is the datum-plane height of this ray (P.gp0 unless the IC carries per-ray heights); unused otherwise.
 template <int GEOM>
@@ -825,6 +844,10 @@ GB_HD inline double disc_condition(const GbParams& P, double r, double s, double
         return r * fabs(c) - h;
     } else if (GEOM == GB200_GEOMETRY_DATUM_PLANE) { // datum-plane.jl:6-10
         return r * c - hgt;
+    } else if (GEOM == GB200_GEOMETRY_THICK_TABLE) { // thick-disc.jl:57-63 with the closure's cross-section tabulated
+        const double h = cross_section_table(P.cs_rho, P.cs_h, P.cs_n, r * fabs(s));
+        if (h <= 0.0) return 1.0;
+        return r * fabs(c) - h;
     }
     return 1.0;
 }
@@ -878,9 +901,11 @@ GB_HD inline void ray_initial_state(const GbParams& P, int64_t i, GbRayInit& o) 
     o.area = 1.0;
     if (P.ic_kind == GB200_IC_EXPLICIT) {
         for (int k = 0; k < 4; ++k) { o.x[k] = P.ex[k][i]; o.v[k] = P.ev[k][i]; }
-        double g[5];
-        metric_components_rt(P, o.x[1], o.x[2], g);
-        o.v[0] = constrain_vt(g, o.v[1], o.v[2], o.v[3], P.mu);
+        if (P.mu == P.mu) { // mu = NaN: the caller's v^t is already constrained (for its own mass) and is kept as given
+            double g[5];
+            metric_components_rt(P, o.x[1], o.x[2], g);
+            o.v[0] = constrain_vt(g, o.v[1], o.v[2], o.v[3], P.mu);
+        }
         return;
     }
     double alpha, beta;

@@ -75,7 +75,7 @@ __global__ void gb200_path_kernel(const __grid_constant__ GbParams P, const doub
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     GD<0> u[8];
     for (int i = 0; i < 8; ++i) u[i] = GD<0>(u0in[i]);
-    { // constrain_all for mass P.mu at the starting point
+    if (P.mu == P.mu) { // constrain_all for mass P.mu at the starting point (mu = NaN: v^t is kept as given)
         GD<0> s, c, g[5], dr[5], dth[5];
         gd_sincos(u[2], s, c);
         metric_jacobian_kind<GD<0>>(P.metric_kind, P.mp, u[1], s, c, g, dr, dth);

@@ -153,6 +153,14 @@ GB_HD inline void rhs_g(const GbParams& P, const GD<N> u[8], GD<N> du[8], GD<N>&
     for (int i = 0; i < 4; ++i) { du[i] = u[4 + i]; du[4 + i] = acc[i]; }
 }
 
+template <class S>
+GB_HD inline S cross_section_table_g(const double* xs, const double* ys, int n, const S& x) { // cross_section_table over S
+    if (n < 2 || !(x >= xs[0]) || !(x <= xs[n - 1])) return S(-1.0);
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (x >= xs[mid]) lo = mid; else hi = mid; }
+    const S w = (x - xs[lo]) / (xs[lo + 1] - xs[lo]);
+    return (1.0 - w) * ys[lo] + w * ys[lo + 1];
+}
 // distance_to_disc over S, geometry chosen at run time (src/geometry/discs/*.jl, see disc_condition<GEOM>)
 template <class S>
 GB_HD inline S disc_condition_g(const GbParams& P, const S& r, const S& s, const S& c, double hgt) {
@@ -168,6 +176,10 @@ GB_HD inline S disc_condition_g(const GbParams& P, const S& r, const S& s, const
         return r * gd_abs(c) - h;
     } else if (P.geometry_kind == GB200_GEOMETRY_DATUM_PLANE) {
         return r * c - hgt;
+    } else if (P.geometry_kind == GB200_GEOMETRY_THICK_TABLE) {
+        const S h = cross_section_table_g<S>(P.cs_rho, P.cs_h, P.cs_n, r * gd_abs(s));
+        if (h <= 0.0) return S(1.0);
+        return r * gd_abs(c) - h;
     }
     return S(1.0);
 }

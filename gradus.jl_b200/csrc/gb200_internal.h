@@ -6,6 +6,9 @@ struct GbParams;
 cudaError_t gb200_launch_trace(const GbParams& P, int sm_count, cudaStream_t stream, int* blocks_out);
 cudaError_t gb200_launch_hist(const double* g, const double* f, int64_t n, const double* bins, int nbins, int right_closed,
                               double* partial, int nblocks, double* out, cudaStream_t stream);
+cudaError_t gb200_launch_bucket2d(const double* x, const double* y, const double* w, int64_t n, const double* xb, int nx, const double* yb, int ny,
+                                  double scale, long long* acc, double* out, int blocks, cudaStream_t stream);
+cudaError_t gb200_launch_hist128_finish(const unsigned long long* acc, int nbins, double scale, double* out, cudaStream_t stream);
 cudaError_t gb200_launch_dfma(double* d_out, int blocks, int iters, cudaStream_t stream);
 cudaError_t gb200_launch_dfma_mix(double* d_out, int blocks, int iters, int mix, cudaStream_t stream);
 cudaError_t gb200_launch_path(const GbParams& P, const double* d_u0, int cap, double* d_lambda, double* d_u, int* d_meta, cudaStream_t stream);

@@ -169,9 +169,37 @@ GB_D bool scan_needed(const GbParams& P, double r0, double acos0, double cprev, 
         return !((acos0 - Bth) > 0.0 && (acos0 - Bth) * (r0 - Br) > hmax * slack + 1e-12);
     }
     if (GEOM == GB200_GEOMETRY_DATUM_PLANE) return !(fabs(cprev) > (Br + (fabs(r0) + Br) * Bth) * slack + 1e-12);
+    if (GEOM == GB200_GEOMETRY_THICK_TABLE) return !((acos0 - Bth) > 0.0 && (acos0 - Bth) * (r0 - Br) > P.gp0 * slack + 1e-12); // gp0 = max of the table
     return false;
 }
 
+
+// ---------------------------------------------------------------- fused line-profile histogram
+// bucket(Simple(), g, f, bins) (src/line-profiles.jl:196) accumulated where the ray is finalised: the (g, f) pair never
+// goes through HBM.  Each CTA owns a histogram in shared memory; contributions are added as 128-bit fixed-point integers
+// (two 64-bit words with carry), because integer addition is associative: which CTA finalises which ray, in what order,
+// on how many GPUs -- the tickets are handed out dynamically -- cannot change a single bit of the result.
+__device__ __forceinline__ void gb_acc128(unsigned long long* lo, unsigned long long* hi, unsigned long long vlo, unsigned long long vhi) {
+    const unsigned long long old = atomicAdd(lo, vlo);
+    if (old + vlo < old) ++vhi; // carry out of the low word
+    if (vhi) atomicAdd(hi, vhi);
+}
+__device__ __noinline__ void gb_hist_add(const GbParams& P, unsigned long long* sh_hist, double g, double f) {
+    int lo = 0, hi = P.lp_nbins; // right_closed: first idx with bins[idx] >= g; else first idx with bins[idx] > g, minus 1
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const bool go_right = P.lp_right_closed ? (P.lp_bins[mid] < g) : (P.lp_bins[mid] <= g);
+        if (go_right) lo = mid + 1; else hi = mid;
+    }
+    int bin = P.lp_right_closed ? lo : lo - 1;
+    bin = bin < 0 ? 0 : (bin > P.lp_nbins - 1 ? P.lp_nbins - 1 : bin);
+    const double v = fmin(f * P.lp_scale, 8.5e37); // < 2^126: the host chooses lp_scale from a bound on sum f
+    if (!(v > 0.0)) return;
+    const double vh = floor(v * 5.421010862427522e-20); // v / 2^64: exact, v has 53 significant bits
+    const unsigned long long whi = __double2ull_rz(vh);
+    const unsigned long long wlo = __double2ull_rz(fma(-vh, 18446744073709551616.0, v));
+    gb_acc128(&sh_hist[bin], &sh_hist[P.lp_nbins + bin], wlo, whi);
+}
 
 #ifdef GB_MAXRREG /* tuning: explicit register cap instead of the occupancy target */
 #define GB_LAUNCH_BOUNDS __maxnreg__(GB_MAXRREG)
@@ -221,6 +249,9 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
 #pragma unroll
     for (int j = 1; j < 6; ++j) { kR.set(j, 0.0); kT.set(j, 0.0); }
 
+    extern __shared__ unsigned long long sh_hist[]; // 2 * lp_nbins words when the line-profile histogram is fused, else empty
+    if (P.lp_bins)
+        for (int b = threadIdx.x; b < 2 * P.lp_nbins; b += GB_BLOCK) sh_hist[b] = 0ull;
 #if GB_OPT_PARK && !GB_OPT_SMEMK
     // Stage data of a lane whose step ended in a disc event, parked until the lane is finalised: k2..k7 accelerations
     // (24) and the k2..k6 stage velocities of r and theta (10), [value][thread] so a warp's accesses are conflict-free.
@@ -359,7 +390,7 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                 if (P.o_nreject) P.o_nreject[n] = nreject;
                 if (P.o_flags) P.o_flags[n] = flags;
                 tot_acc += (unsigned)naccept; tot_rej += (unsigned)nreject; tot_flag += (flags != 0);
-                if (P.npf > 0 || P.o_g != nullptr) {
+                if (P.npf > 0 || P.o_g != nullptr || P.lp_bins != nullptr) {
                     const bool hit = (status == GB200_STATUS_INTERSECTED_WITH_GEOMETRY);
                     double g_red = nan("");
                     bool have_g = false;
@@ -376,7 +407,7 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                         else if (pf == GB200_PF_RADIUS) val = xe[1] * fabs(sin(xe[2]));
                         P.o_img[k][n] = val;
                     }
-                    if (P.o_g) { // lineprofile BinningMethod, src/line-profiles.jl:186-194
+                    if (P.o_g || P.lp_bins) { // lineprofile BinningMethod, src/line-profiles.jl:186-194
                         double gg = nan(""), ff = 0.0;
                         if (hit) {
                             const double rho = xe[1] * fabs(sin(xe[2]));
@@ -385,8 +416,8 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                                 ff = emissivity_eval(P, rho) * gg * gg * gg * area;
                             }
                         }
-                        P.o_g[n] = gg;
-                        P.o_f[n] = ff;
+                        if (P.o_g) { P.o_g[n] = gg; P.o_f[n] = ff; }
+                        if (P.lp_bins && gg == gg) gb_hist_add(P, sh_hist, gg, ff);
                     }
                 }
                 state = LANE_EMPTY;
@@ -714,6 +745,13 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
             dt = advance ? dtprop : (accept ? dt : dtrej);
         }
     }
+    if (P.lp_bins) { // this CTA's histogram joins the launch's (carry-correct 128-bit adds: order independent)
+        __syncthreads();
+        for (int b = threadIdx.x; b < P.lp_nbins; b += GB_BLOCK) {
+            const unsigned long long wlo = sh_hist[b], whi = sh_hist[P.lp_nbins + b];
+            if (wlo | whi) gb_acc128(&P.lp_acc[b], &P.lp_acc[P.lp_nbins + b], wlo, whi);
+        }
+    }
     // ---- flush per-thread counters (warp-reduced)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -732,14 +770,15 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
 template <int METRIC, int GEOM>
 static cudaError_t launch_one(const GbParams& P, int sm_count, cudaStream_t stream, int* blocks_out) {
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gb200_trace_kernel<METRIC, GEOM>, GB_BLOCK, 0);
+    const size_t dyn = P.lp_bins ? sizeof(unsigned long long) * 2 * (size_t)P.lp_nbins : 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gb200_trace_kernel<METRIC, GEOM>, GB_BLOCK, dyn);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     long long want = ((long long)P.count + GB_BLOCK - 1) / GB_BLOCK;
     long long grid = (long long)sm_count * per_sm; // persistent: one wave, sized in multiples of the SM count
     if (want < grid) grid = want > 0 ? want : 1;
     if (blocks_out) *blocks_out = (int)grid;
-    gb200_trace_kernel<METRIC, GEOM><<<(unsigned)grid, GB_BLOCK, 0, stream>>>(P);
+    gb200_trace_kernel<METRIC, GEOM><<<(unsigned)grid, GB_BLOCK, dyn, stream>>>(P);
     return cudaGetLastError();
 }
 
@@ -750,6 +789,7 @@ static cudaError_t launch_geom(const GbParams& P, int sm_count, cudaStream_t str
     case GB200_GEOMETRY_THIN_DISC: return launch_one<METRIC, GB200_GEOMETRY_THIN_DISC>(P, sm_count, stream, blocks_out);
     case GB200_GEOMETRY_SHAKURA_SUNYAEV: return launch_one<METRIC, GB200_GEOMETRY_SHAKURA_SUNYAEV>(P, sm_count, stream, blocks_out);
     case GB200_GEOMETRY_DATUM_PLANE: return launch_one<METRIC, GB200_GEOMETRY_DATUM_PLANE>(P, sm_count, stream, blocks_out);
+    case GB200_GEOMETRY_THICK_TABLE: return launch_one<METRIC, GB200_GEOMETRY_THICK_TABLE>(P, sm_count, stream, blocks_out);
     }
     return cudaErrorInvalidValue;
 }
@@ -836,6 +876,16 @@ __global__ void gb200_hist_reduce_kernel(const double* __restrict__ partial, int
     out[b] = accumulate ? out[b] + s : s;
 }
 
+// (high, low) 128-bit fixed-point bins -> doubles: out[b] = (hi 2^64 + lo) / scale
+__global__ void gb200_hist128_finish_kernel(const unsigned long long* __restrict__ acc, int nbins, double inv_scale, double* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nbins) out[b] = fma((double)acc[nbins + b], 18446744073709551616.0, (double)acc[b]) * inv_scale;
+}
+cudaError_t gb200_launch_hist128_finish(const unsigned long long* acc, int nbins, double scale, double* out, cudaStream_t stream) {
+    gb200_hist128_finish_kernel<<<(nbins + 127) / 128, 128, 0, stream>>>(acc, nbins, 1.0 / scale, out);
+    return cudaGetLastError();
+}
+
 cudaError_t gb200_launch_hist(const double* g, const double* f, int64_t n, const double* bins, int nbins, int right_closed,
                               double* partial, int nblocks, double* out, cudaStream_t stream) {
     const int rows = ((size_t)nbins * 9 * sizeof(double) <= 96 * 1024) ? 8 : 1; // 256 threads = 8 warps
@@ -848,6 +898,58 @@ cudaError_t gb200_launch_hist(const double* g, const double* f, int64_t n, const
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     gb200_hist_reduce_kernel<<<(nbins + 127) / 128, 128, 0, stream>>>(partial, nblocks, nbins, out, 0);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- two-dimensional bucket (lag-energy transfer functions)
+// `bucket(energy, time, flux, energy_bins, time_bins; reduction = sum)` of bin_transfer_function
+// (src/transfer-functions/transfer-functions-2d.jl:100-122, Buckets.Simple in both axes).  300 x 300 bins do not fit shared
+// memory, so the bins live in HBM; to keep the result independent of the order in which atomics arrive (and of how the
+// samples are split over GPUs) the weights are accumulated as 64-bit fixed-point integers -- integer addition is
+// associative -- with the scale chosen from sum |w|, so that the quantisation (2^-62 of the total per sample) is far below
+// the rounding of a floating-point sum.  Lanes of a warp that hit the same cell are combined first (__match_any_sync).
+__device__ __forceinline__ int gb_simple_bucket(const double* __restrict__ bins, int nb, double v) {
+    int lo = 0, hi = nb; // first idx with bins[idx] > v, minus 1 (searchsortedlast), clamped to the ends
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (bins[mid] <= v) lo = mid + 1; else hi = mid; }
+    const int b = lo - 1;
+    return b < 0 ? 0 : (b > nb - 1 ? nb - 1 : b);
+}
+__global__ void __launch_bounds__(256) gb200_bucket2d_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ w,
+                                                             int64_t n, const double* __restrict__ xb, int nx, const double* __restrict__ yb, int ny,
+                                                             double scale, long long* __restrict__ acc) {
+    const unsigned lane = threadIdx.x & 31u;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        int cell = -1;
+        long long q = 0;
+        if (i < n) {
+            const double xi = x[i], yi = y[i], wi = w[i];
+            if (xi == xi && yi == yi && wi == wi) {
+                cell = gb_simple_bucket(xb, nx, xi) * ny + gb_simple_bucket(yb, ny, yi);
+                q = __double2ll_rn(wi * scale);
+            }
+        }
+        const unsigned active = __ballot_sync(FULLMASK, cell >= 0);
+        if (cell >= 0) {
+            const unsigned peers = __match_any_sync(active, cell);
+            long long sum = 0;
+            unsigned rem = peers;
+            while (rem) { const int src = __ffs(rem) - 1; sum += __shfl_sync(peers, q, src); rem &= rem - 1; }
+            if ((int)lane == __ffs(peers) - 1) atomicAdd((unsigned long long*)&acc[cell], (unsigned long long)sum);
+        }
+    }
+}
+__global__ void gb200_bucket2d_finish_kernel(const long long* __restrict__ acc, int ncell, double inv_scale, double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncell) out[c] = (double)acc[c] * inv_scale;
+}
+cudaError_t gb200_launch_bucket2d(const double* x, const double* y, const double* w, int64_t n, const double* xb, int nx, const double* yb, int ny,
+                                  double scale, long long* acc, double* out, int blocks, cudaStream_t stream) {
+    const int ncell = nx * ny;
+    cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(long long) * (size_t)ncell, stream);
+    if (e != cudaSuccess) return e;
+    if (n > 0) gb200_bucket2d_kernel<<<blocks, 256, 0, stream>>>(x, y, w, n, xb, nx, yb, ny, scale, acc);
+    gb200_bucket2d_finish_kernel<<<(ncell + 255) / 256, 256, 0, stream>>>(acc, ncell, 1.0 / scale, out);
     return cudaGetLastError();
 }
 

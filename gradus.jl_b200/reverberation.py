@@ -101,15 +101,33 @@ def _simple_bucket_index(bins, v):
     return np.clip(np.searchsorted(bins, v, side="right") - 1, 0, len(bins) - 1)
 
 
-def bin_transfer_function(time_delays, energy, flux, *, N_E=300, N_t=300, energy_lims=None, time_lims=None):
+def bucket2d(x, y, w, xbins, ybins, ensemble=None):
+    """`bucket(x, y, w, xbins, ybins; reduction = sum)` (Buckets.Simple in both axes).  With an `ensemble` the histogram is
+    accumulated on the device (`gb200_bucket2d`, order-independent fixed-point sums); without, on the host."""
+    xbins = np.ascontiguousarray(xbins, np.float64)
+    ybins = np.ascontiguousarray(ybins, np.float64)
+    if ensemble is None:
+        out = np.zeros((len(xbins), len(ybins)))
+        np.add.at(out, (_simple_bucket_index(xbins, x), _simple_bucket_index(ybins, y)), w)
+        return out
+    import ctypes as C
+
+    x, y, w = (np.ascontiguousarray(a, np.float64) for a in (x, y, w))
+    out = np.zeros((len(xbins), len(ybins)))
+    ctx = ensemble.ctx(ensemble.devices[0])
+    cabi.check(cabi.load().gb200_bucket2d(ctx, len(x), cabi.dptr(x), cabi.dptr(y), cabi.dptr(w), cabi.dptr(xbins), len(xbins), cabi.dptr(ybins),
+                                          len(ybins), cabi.dptr(out.reshape(-1))), ctx)
+    return out
+
+
+def bin_transfer_function(time_delays, energy, flux, *, N_E=300, N_t=300, energy_lims=None, time_lims=None, ensemble=None):
     """transfer-functions-2d.jl:100-122 → (time_bins, energy_bins, tf[N_E, N_t]) with empty cells NaN."""
     energy_lims = (np.min(energy), np.max(energy)) if energy_lims is None else energy_lims
     time_lims = (np.min(time_delays), np.max(time_delays)) if time_lims is None else time_lims
     eb = np.linspace(energy_lims[0], energy_lims[1], N_E)
     tb = np.linspace(time_lims[0], time_lims[1], N_t)
     de, dt = eb[1] - eb[0], tb[1] - tb[0]
-    out = np.zeros((N_E, N_t))
-    np.add.at(out, (_simple_bucket_index(eb, energy), _simple_bucket_index(tb, time_delays)), flux)
+    out = bucket2d(energy, time_delays, flux, eb, tb, ensemble)
     out /= de * dt
     out[out == 0.0] = np.nan
     return tb, eb, out

@@ -57,6 +57,10 @@ extern "C" {
 #define GB200_GEOMETRY_THIN_DISC 1       /* thin-disc.jl:9-26       params: inner_radius, outer_radius */
 #define GB200_GEOMETRY_SHAKURA_SUNYAEV 2 /* shakura-sunyaev.jl:22-33 params: Mdot/Mdot_edd, inv_eta, inner_radius(isco) */
 #define GB200_GEOMETRY_DATUM_PLANE 3     /* datum-plane.jl:1-10     params: height */
+#define GB200_GEOMETRY_THICK_TABLE 4     /* thick-disc.jl:32-63: `ThickDisc(f)` with its closure f(rho) tabulated -- a closure cannot
+                                            cross the ABI.  cross_section(rho) = linear interpolation in the table installed with
+                                            gb200_set_cross_section, -1 (no disc) outside its range; distance_to_disc = |r cos theta| - h,
+                                            1 where h <= 0.  params: max of the table (filled in by the library) */
 
 /* ---- user discrete callback: src/tracing/callbacks.jl:31-39 ------------ */
 #define GB200_CALLBACK_NONE 0
@@ -94,7 +98,8 @@ typedef struct gb200_problem {
     double abstol;
     double reltol;
     double dtmax; /* <= 0 -> lambda_max - lambda_min (OrdinaryDiffEq default) */
-    double mu;    /* geodesic mass, 0 for photons (constrain_time, auto-diff.jl:161-173) */
+    double mu;    /* geodesic mass, 0 for photons (constrain_time, auto-diff.jl:161-173); NaN with explicit initial conditions:
+                     v^t is kept as given (states taken from an ensemble's prob_func are already constrained) */
     int64_t maxiters; /* <= 0 -> 1000000 */
 } gb200_problem;
 
@@ -220,6 +225,12 @@ void gb200_destroy(gb200_ctx* ctx);
 const char* gb200_last_error(gb200_ctx* ctx); /* ctx may be NULL: last global error */
 int gb200_get_stats(gb200_ctx* ctx, gb200_stats* out);
 
+/* Cross-section table of GB200_GEOMETRY_THICK_TABLE for this context: n >= 2 points, rho ascending; copied to the device and
+   kept until replaced (n = 0 removes it).  A Julia caller tabulates `cross_section(d, rho)` of its ThickDisc once, e.g. on
+   Chebyshev nodes of the support so that square-root edges are resolved (tests/test_more_metrics.py uses 4097 nodes for the
+   torus of test/smoke-tests/rendergeodesics.jl:8-15). */
+int gb200_set_cross_section(gb200_ctx* ctx, const double* rho, const double* height, int32_t n);
+
 /* Validate a configuration without running it (what the Julia shim calls first
    so that unsupported set-ups raise ArgumentError before any work). */
 int gb200_validate(const gb200_problem* p, const gb200_ic* ic);
@@ -331,6 +342,14 @@ int gb200_trace_dual(gb200_ctx* ctx, const gb200_problem* p, const gb200_dual_ic
 int gb200_trace_dual_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* problems, const gb200_dual_ic* ics,
                            int32_t norm_mode, const gb200_plunging_table* const* pls, gb200_dual_out* outs);
 
+/* Two-dimensional weighted histogram: `bucket(x, y, w, xbins, ybins; reduction = sum)` of bin_transfer_function
+   (src/transfer-functions/transfer-functions-2d.jl:100-122), Buckets.Simple in both axes (cell (i, j) takes
+   xbins[i] <= x < xbins[i+1], ybins[j] <= y < ybins[j+1], clamped to the ends).  n host samples -> out[i * ny + j] on the
+   host.  Weights are accumulated as 64-bit fixed point (2^-62 of sum |w| per sample), so the result does not depend on
+   the order of accumulation. */
+int gb200_bucket2d(gb200_ctx* ctx, int64_t n, const double* x, const double* y, const double* w,
+                   const double* xbins, int32_t nx, const double* ybins, int32_t ny, double* out);
+
 /* ---- device-resident variants (inputs/outputs stay in HBM) ------------- */
 /* Same as gb200_render but `d_images[k]` are DEVICE pointers on ctx's device and no
    host copy is made; work is enqueued on `cuda_stream` (a cudaStream_t cast to
@@ -353,6 +372,26 @@ int gb200_lineprofile_device(gb200_ctx* ctx, const gb200_problem* p, const gb200
                              const double* bins, int32_t nbins,
                              const gb200_lineprofile_opts* opts, double* d_flux,
                              void* cuda_stream, int async);
+
+/* ---- several GPUs from ONE process (the Julia extension: EnsembleB200(devices)) ---------------------------- */
+/* One context per listed device plus, for more than one device, an NCCL communicator over them (ncclCommInitAll).  NCCL is
+   opened at run time (dlopen "libnccl.so.2"): a single-GPU caller does not need it.  Rays are sharded by whole strips of
+   four image columns / theta-rows (strip d, d + ndev, ... on device d); there is no data-path collective except the
+   line-profile histogram, which is summed with one ncclAllReduce(sum, nbins doubles) on the devices' own streams
+   (SURVEY 8e).  torchrun-style callers (one process per GPU) use gb200_lineprofile_device + their own all-reduce instead. */
+typedef struct gb200_comm gb200_comm;
+int gb200_comm_init(const int32_t* devices, int32_t ndev, gb200_comm** out);
+void gb200_comm_destroy(gb200_comm* comm);
+int gb200_comm_size(gb200_comm* comm);
+gb200_ctx* gb200_comm_context(gb200_comm* comm, int32_t i); /* borrowed: the context of the i-th device */
+/* lineprofile(::BinningMethod) over all devices; flux_out: nbins doubles on the host, identical whatever ndev up to the
+   order of summation (<= 1e-12 of the peak). */
+int gb200_comm_lineprofile(gb200_comm* comm, const gb200_problem* p, const gb200_ic* ic, const gb200_emissivity* emis,
+                           const gb200_plunging_table* plunging, const double* bins, int32_t nbins,
+                           const gb200_lineprofile_opts* opts, double* flux_out);
+/* rendergeodesics over all devices: images[k] -> ic->n doubles on the host in ray order (the (H, W) column-major image). */
+int gb200_comm_render(gb200_comm* comm, const gb200_problem* p, const gb200_ic* ic, const int32_t* pointfns, int32_t npf,
+                      const gb200_plunging_table* plunging, double* const* images);
 
 /* Diagnostics: evaluate the device right-hand side (_second_order_ode_f, src/tracing/geodesic-problem.jl:87-92) for
    n states u (row-major n x 8) -> du (n x 8), and the kernel's branch-free elementary functions on n inputs

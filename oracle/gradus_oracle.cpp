@@ -538,6 +538,17 @@ static void ic_for_ray(const gb200_problem& p, const gb200_ic& ic, int64_t i, Ra
     }
 }
 
+// GB200_GEOMETRY_THICK_TABLE: the cross-section table the test installed (oracle_set_cross_section); process-global, tests only
+static std::vector<double> g_cs_rho, g_cs_h;
+static double cross_section_table(double x) { // linear interpolation, -1 (no disc) outside the table
+    const size_t n = g_cs_rho.size();
+    if (n < 2 || !(x >= g_cs_rho[0]) || !(x <= g_cs_rho[n - 1])) return -1.0;
+    size_t idx = (size_t)(std::upper_bound(g_cs_rho.begin(), g_cs_rho.end(), x) - g_cs_rho.begin());
+    idx = std::min(std::max(idx, (size_t)1), n - 1) - 1;
+    const double w = (x - g_cs_rho[idx]) / (g_cs_rho[idx + 1] - g_cs_rho[idx]);
+    return (1.0 - w) * g_cs_h[idx] + w * g_cs_h[idx + 1];
+}
+
 // ------------------------------------------------------------------ geometry conditions
 // distance_to_disc: thin-disc.jl:20-26, thick-disc.jl:57-63 + shakura-sunyaev.jl:28-33, datum-plane.jl:6-10
 template <class T>
@@ -562,9 +573,15 @@ T disc_condition(const gb200_problem& p, T r, T th) {
         if (rho < T(9) || rho > T(11)) height = T(-1);
         else { T x = rho - T(10); height = rsqrt_(T(1) - x * x); }
         if (height <= T(0)) return T(1);
+        if (p.geometry_params[3] != 0.0) return r * rabs(rcos(th)) - height - T(p.gtol) * rabs(r); // legacy form, see ORACLE_GEOMETRY_SS_LEGACY_GTOL
         return r * rabs(rcos(th)) - height;
     } else if (p.geometry_kind == GB200_GEOMETRY_DATUM_PLANE) {
         return r * rcos(th) - T(p.geometry_params[0]);
+    } else if (p.geometry_kind == GB200_GEOMETRY_THICK_TABLE) { // thick-disc.jl:57-63 with a tabulated cross_section (values only)
+        T rho = r * rabs(rsin(th));
+        T height = T(cross_section_table((double)value_of(rho)));
+        if (height <= T(0)) return T(1);
+        return r * rabs(rcos(th)) - height;
     }
     return T(1);
 }
@@ -853,7 +870,7 @@ void initial_state(const gb200_problem& p, const Metric& m, const RayIC& ric, co
     }
     T g[5];
     metric_components<T>(m, x[1], x[2], g);
-    v[0] = constrain_time<T>(g, v, T(p.mu)); // constrain_all, constraints.jl:14-15
+    if (!(ric.explicit_v && p.mu != p.mu)) v[0] = constrain_time<T>(g, v, T(p.mu)); // constrain_all, constraints.jl:14-15 (mu = NaN: v^t kept as given)
     for (int k = 0; k < 4; ++k) { u0[k] = x[k]; u0[4 + k] = v[k]; }
 }
 
@@ -1424,6 +1441,11 @@ int oracle_metric(int kind, const double* mp, double r, double th, double* g5, d
 int oracle_rhs(int kind, const double* mp, const double* u8, double* du8) {
     orc::Metric m = orc::make_metric(kind, mp);
     orc::rhs<double>(m, u8, du8);
+    return 0;
+}
+int oracle_set_cross_section(const double* rho, const double* h, int n) {
+    orc::g_cs_rho.assign(rho, rho + n);
+    orc::g_cs_h.assign(h, h + n);
     return 0;
 }
 int oracle_is_fast_variant(void) {

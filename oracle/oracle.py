@@ -120,6 +120,13 @@ def trace_dual(problem, arrays, norm_mode=0, plunging=None, nthreads=0):
     return arrays
 
 
+def set_cross_section(rho, h):
+    """Install the cross-section table of GB200_GEOMETRY_THICK_TABLE (process-global; tests only)."""
+    rho = np.ascontiguousarray(rho, np.float64)
+    h = np.ascontiguousarray(h, np.float64)
+    lib().oracle_set_cross_section(cabi.dptr(rho), cabi.dptr(h), len(rho))
+
+
 def _mp(params):
     a = np.zeros(8)
     a[: len(params)] = params

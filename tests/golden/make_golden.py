@@ -18,6 +18,12 @@ from oracle import oracle  # noqa: E402
 
 
 def main():
+    if "--c-only" in sys.argv:
+        p, ic = common.c1(128, 128)[3].to_c()
+        img = oracle.render(p, ic, [cabi.PF_REDSHIFT], nthreads=1)[0]
+        img.astype("<f8").tofile(os.path.join(os.path.dirname(os.path.abspath(__file__)), "c1_128x128_redshift.f64"))
+        print("wrote c1_128x128_redshift.f64:", img.size, "doubles,", int(np.sum(~np.isnan(img))), "hits")
+        return
     out = {}
     for name, cfg in [("c1_24x24", common.c1(24, 24)[3]), ("c3_20x20", common.c3(20, 20)[4]), ("c5_20x20", common.c5(20, 20)[3])]:
         p, ic = cfg.to_c()
@@ -31,6 +37,11 @@ def main():
         out[name + "_radius"] = imgs[1]
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_small.npz"), **out)
     print("wrote", len(out), "arrays")
+    # the C1 redshift image as raw little-endian doubles in ray order, for the plain-C boundary test (tests/c/cabi_render.c)
+    p, ic = common.c1(128, 128)[3].to_c()
+    img = oracle.render(p, ic, [cabi.PF_REDSHIFT], nthreads=1)[0]
+    img.astype("<f8").tofile(os.path.join(os.path.dirname(os.path.abspath(__file__)), "c1_128x128_redshift.f64"))
+    print("wrote c1_128x128_redshift.f64:", img.size, "doubles,", int(np.sum(~np.isnan(img))), "hits")
 
 
 if __name__ == "__main__":

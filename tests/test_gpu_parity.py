@@ -417,6 +417,13 @@ def test_fast32_controller_and_massive_geodesics(ensemble):
     norm = (-(1 - 2 * r_ / S) * vv[0] ** 2 + S / D * vv[1] ** 2 + S * vv[2] ** 2 + s2 * (r_**2 + 0.25 + 2 * r_ * 0.25 * s2 / S) * vv[3] ** 2
             - 2 * (2 * r_ * 0.5 * s2 / S) * vv[0] * vv[3])
     assert np.abs(norm + 1.0).max() < 1e-6
+    # mu = NaN: states that arrive already constrained (an ensemble's prob_func output, what the Julia extension uploads)
+    # keep their v^t -- the very same rays again, bit for bit
+    cfg2 = tracing_configuration(mk, [0.0, 8.0, math.pi / 2 - 0.05, 0.0], got.v_init.T.copy(), 5.0, mu=float("nan"), ensemble=ensemble)
+    again = solve_tracing_problem(cfg2)
+    assert np.array_equal(again.v_init, got.v_init) and np.array_equal(again.x, got.x) and np.array_equal(again.status, got.status)
+    ref2 = oracle.trace(*cfg2.to_c())
+    assert np.array_equal(ref2.v_init, ref.v_init) and np.array_equal(ref2.x, ref.x)
 
 
 def test_in_process_sharding_over_contexts(ensemble):
@@ -577,9 +584,18 @@ def test_full_size_lineprofile_properties(ensemble):
         return flux
 
     full = hist(cabi.Range(0, ic.n, 1))
-    assert np.array_equal(full, hist(cabi.Range(0, ic.n, 1)))  # fixed-order partial sums: bitwise reproducible
+    assert np.array_equal(full, hist(cabi.Range(0, ic.n, 1)))  # exact fixed-point sums in the kernel: bitwise reproducible
     parts = sum(hist(gd.strip_interleaved_range(ic, r, 8)) for r in range(8))
-    assert np.max(np.abs(parts - full)) <= 1e-12 * full.max()
+    assert np.max(np.abs(parts - full)) <= 1e-14 * full.max()  # each shard is an exact sum; only the 8-term host sum rounds
+    # the histogram fused into the trace kernel against the two-pass form ((g, f) per ray through HBM, then the binning kernels)
+    import os
+
+    os.environ["GB200_HIST_TWO_PASS"] = "1"
+    try:
+        two_pass = hist(cabi.Range(0, ic.n, 1))
+    finally:
+        del os.environ["GB200_HIST_TWO_PASS"]
+    assert np.max(np.abs(two_pass - full)) <= 1e-12 * full.max()
     flux = full / full.sum()
     assert flux.sum() == pytest.approx(1.0) and flux[0] < 1e-3 and flux[-1] == 0.0  # g < 0.1 is clamped into the first bin (Buckets.Simple)
     g_peak = bins[np.argmax(flux)]
@@ -625,3 +641,73 @@ def test_full_size_johannsen_psaltis_properties(ensemble):
     both = ok & agree & ~np.isnan(want[0])
     assert both.sum() > 1000
     assert np.abs(got[0][both] - want[0][both]).max() < 1e-6 and np.abs(got[1][both] / want[1][both] - 1).max() < 1e-6
+
+
+# --------------------------------------------------------------------------- the library's own multi-device path
+def _comm(devices):
+    h = C.c_void_p()
+    devs = np.array(devices, np.int32)
+    cabi.check(cabi.load().gb200_comm_init(cabi.iptr(devs), len(devs), C.byref(h)))
+    return h
+
+
+@pytest.mark.gpu
+def test_comm_entry_points_on_one_device_equal_the_single_context_calls(ensemble):
+    """`gb200_comm_render` / `gb200_comm_lineprofile` (one process, NCCL inside the library) with a single device: the same
+    numbers as `gb200_render` / `gb200_lineprofile`; a device listed twice is refused."""
+    lib = cabi.load()
+    m, x, d, cfg = common.c1(96, 64, ensemble=ensemble)
+    p, ic = cfg.to_c()
+    pfs = np.array([cabi.PF_REDSHIFT, cabi.PF_DISC_RADIUS], np.int32)
+    a, b = np.zeros((2, ic.n)), np.zeros((2, ic.n))
+    rng = cabi.Range(0, ic.n, 1)
+    cabi.check(lib.gb200_render(ensemble.ctx(0), C.byref(p), C.byref(ic), C.byref(rng), cabi.iptr(pfs), 2, None,
+                                (cabi._dp * 2)(cabi.dptr(a[0]), cabi.dptr(a[1]))), ensemble.ctx(0))
+    comm = _comm([0])
+    try:
+        assert lib.gb200_comm_size(comm) == 1 and lib.gb200_comm_context(comm, 0)
+        cabi.check(lib.gb200_comm_render(comm, C.byref(p), C.byref(ic), cabi.iptr(pfs), 2, None, (cabi._dp * 2)(cabi.dptr(b[0]), cabi.dptr(b[1]))))
+        assert np.array_equal(a, b, equal_nan=True)
+        m, x, d, plane, cfg = common.c3(64, 64, ensemble=ensemble)
+        p, ic = cfg.to_c()
+        bins = np.ascontiguousarray(np.linspace(0.1, 1.5, 180))
+        emis = cabi.Emissivity(cabi.EMISSIVITY_POWERLAW, 0, 3.0, None, None)
+        opts = cabi.LineProfileOpts(gb.isco(m), 50.0, 1, 0)
+        f1, f2 = np.zeros(180), np.zeros(180)
+        rng = cabi.Range(0, ic.n, 1)
+        cabi.check(lib.gb200_lineprofile(ensemble.ctx(0), C.byref(p), C.byref(ic), C.byref(rng), C.byref(emis), None, cabi.dptr(bins), 180,
+                                         C.byref(opts), cabi.dptr(f1)), ensemble.ctx(0))
+        cabi.check(lib.gb200_comm_lineprofile(comm, C.byref(p), C.byref(ic), C.byref(emis), None, cabi.dptr(bins), 180, C.byref(opts), cabi.dptr(f2)))
+        assert np.array_equal(f1, f2)
+    finally:
+        lib.gb200_comm_destroy(comm)
+    h = C.c_void_p()
+    devs = np.array([0, 0], np.int32)
+    assert lib.gb200_comm_init(cabi.iptr(devs), 2, C.byref(h)) == cabi.ERR_INVALID_ARGUMENT
+
+
+@pytest.mark.gpu
+def test_comm_entry_points_over_two_devices(ensemble):
+    """Real distinct GPUs in one process (run under `gpurun --gpus 2`): the image equals the single-GPU image bit for bit
+    (a ray's result does not depend on who traces it) and the NCCL-reduced histogram equals the single-GPU one to the
+    order of summation."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    lib = cabi.load()
+    ens2 = gb.EnsembleB200(devices=(0, 1))
+    m, x, d, cfg = common.c1(256, 128, ensemble=ensemble)
+    pf = [gb.ConstPointFunctions.redshift(m, x) @ gb.ConstPointFunctions.filter_intersected()]
+    one = gb.api.apply_point_functions(cfg, pf)
+    cfg2 = common.c1(256, 128, ensemble=ens2)[3]
+    two = gb.api.apply_point_functions(cfg2, pf)
+    assert np.array_equal(one, two, equal_nan=True)
+    bins = np.linspace(0.1, 1.5, 180)
+    plane = gb.PolarPlane(gb.GeometricGrid(), Nr=256, Ntheta=256, r_min=1.0, r_max=250.0)
+    m = gb.KerrMetric(1.0, 0.998)
+    x = [0.0, 1000.0, math.radians(40.0), 0.0]
+    _, f1 = gb.lineprofile(bins, gb.PowerLawEmissivity(3.0), m, x, gb.ThinDisc(0.0, 400.0), gb.BinningMethod(), plane=plane, lambda_max=2000.0, ensemble=ensemble)
+    _, f2 = gb.lineprofile(bins, gb.PowerLawEmissivity(3.0), m, x, gb.ThinDisc(0.0, 400.0), gb.BinningMethod(), plane=plane, lambda_max=2000.0, ensemble=ens2)
+    assert np.abs(f1 - f2).sum() <= 1e-12 * f1.max() * len(bins)
+    ens2.close()

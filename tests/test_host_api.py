@@ -192,3 +192,36 @@ def test_reference_arm_prints_exactly_one_json_line():
         assert key in j, key
     assert j["impl"] == "reference" and j["unit"] == "rays/s" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port"
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in j["config"]
+
+
+def _build_c_program(tmpdir):
+    exe = os.path.join(tmpdir, "cabi_render")
+    csrc = os.path.join(ROOT, "gradus.jl_b200", "csrc")
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "cabi_render.c"),
+                           "-L", csrc, "-lgradus_b200", f"-Wl,-rpath,{csrc}", "-lm", "-o", exe])
+    return exe
+
+
+def test_plain_c_program_links_against_the_boundary():
+    """tests/c/cabi_render.c: only the header and the shared library, no Python in between.  Without a device it must stop
+    at gb200_init with GB200_ERR_NO_DEVICE (exit 77), after validating its problem description on the host."""
+    import torch
+
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build_c_program(d)
+        r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "c1_128x128_redshift.f64")], capture_output=True, text=True, cwd=ROOT)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 77 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_program_renders_config_1_with_parity():
+    """The same program on the GPU: gb200_render driven from C reproduces the frozen oracle image of BASELINE config 1."""
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build_c_program(d)
+        r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "c1_128x128_redshift.f64")], capture_output=True, text=True, cwd=ROOT)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "NaN-mask mismatches" in r.stdout

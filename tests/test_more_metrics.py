@@ -186,3 +186,63 @@ def test_charged_circular_orbits_reproduce_the_reference_literals():
     v0 = hostmath.circular_fourvelocity(m, 20.0)
     g = hostmath.metric_components(m, 20.0, math.pi / 2)
     assert hostmath.dot(g, v0, v0) == pytest.approx(-1.0, abs=1e-12)
+
+
+# --------------------------------------------------------------------------- ThickDisc(f): closure cross-sections as tables
+# test/smoke-tests/rendergeodesics.jl:8-15,85-96: a torus of unit radius centred on rho = 10; literals last computed 25/08/2023,
+# i.e. (like the Shakura-Sunyaev ones) when the thick-disc distance still subtracted gtol |r|.
+def _torus(rho):
+    if rho < 9.0 or rho > 11.0:
+        return -1.0
+    return math.sqrt(1 - (rho - 10.0) ** 2)
+
+
+TORUS = [(gb.KerrMetric(1.0, 0.0), 16918.69258396256), (gb.JohannsenMetric(), 16918.689593279843), (gb.BumblebeeMetric(), 16918.692092917947),
+         (gb.KerrNewmanMetric(), 16918.691837255217)]
+ORACLE_GEOMETRY_TEST_THICK_DISC = 100  # oracle-only: the closure itself
+
+
+@pytest.mark.parametrize("m, literal", TORUS, ids=["kerr", "johannsen", "bumblebee", "kerr_newman"])
+def test_oracle_torus_literal_and_its_tabulated_form(m, literal):
+    p, ic = _smoke_fixture(m, gb.ThinDisc(0.0, 40.0)).to_c()
+    p.geometry_kind = ORACLE_GEOMETRY_TEST_THICK_DISC
+    exact = np.nansum(oracle.render(p, ic, [cabi.PF_SHADOW])[0])
+    assert exact == pytest.approx(literal, rel=0.1)  # the reference's own tolerance, current source (measured -2.3 %)
+    p.geometry_params[3] = 1.0  # the form the literal was recorded with: distance - gtol |r|
+    assert np.nansum(oracle.render(p, ic, [cabi.PF_SHADOW])[0]) == pytest.approx(literal, rel=1e-4)  # measured 3.2e-5
+    # what crosses the ABI is a table of the closure on 4097 Chebyshev nodes: same image to 1e-8
+    d = gb.ThickDisc(_torus, (9.0, 11.0))
+    p2, ic2 = _smoke_fixture(m, d).to_c()
+    assert p2.geometry_kind == cabi.GEOMETRY_THICK_TABLE
+    oracle.set_cross_section(d.rho, d.height)
+    assert np.nansum(oracle.render(p2, ic2, [cabi.PF_SHADOW])[0]) == pytest.approx(exact, rel=1e-8)
+
+
+@pytest.mark.gpu
+def test_device_thick_disc_table(ensemble):
+    """GB200_GEOMETRY_THICK_TABLE on the device: the smoke-matrix torus against the oracle (closure and table), and a
+    128 x 128 render under the main parity protocol (same termination class outside the grazing band, hits to 1e-6)."""
+    d = gb.ThickDisc(_torus, (9.0, 11.0))
+    oracle.set_cross_section(d.rho, d.height)
+    x = [0.0, 100.0, math.radians(85), 0.0]
+    for m, literal in TORUS:
+        _, _, img = gb.rendergeodesics(m, x, d, 200.0, image_width=20, image_height=20, alpha_lims=(-9.5, 9.5), beta_lims=(-9.5, 9.5), ensemble=ensemble)
+        p, ic = _smoke_fixture(m, gb.ThinDisc(0.0, 40.0)).to_c()
+        p.geometry_kind = ORACLE_GEOMETRY_TEST_THICK_DISC
+        exact = np.nansum(oracle.render(p, ic, [cabi.PF_SHADOW])[0])
+        assert np.nansum(img) == pytest.approx(exact, rel=1e-6) and np.nansum(img) == pytest.approx(literal, rel=0.1)
+    m = gb.KerrMetric(1.0, 0.9)
+    cfg = render_config(m, x, d, 200.0, 128, 128, (-14, 14), (-6, 6), ensemble=ensemble)
+    p, ic = cfg.to_c()
+    ref = oracle.trace(p, ic)
+    got = api.solve_tracing_problem(cfg)
+    agree = got.status == ref.status
+    assert agree.mean() > 0.995
+    hit = agree & (ref.status == cabi.STATUS_INTERSECTED)
+    assert hit.sum() > 1000
+    rel = np.abs(got.x[1:3, hit] - ref.x[1:3, hit]) / np.maximum(np.abs(ref.x[1:3, hit]), 1e-3)
+    assert np.quantile(rel.max(axis=0), 0.995) < 1e-6
+    # the tabulated height is what the hits sit on
+    rho = got.x[1, hit] * np.abs(np.sin(got.x[2, hit]))
+    z = got.x[1, hit] * np.abs(np.cos(got.x[2, hit]))
+    assert np.quantile(np.abs(z - d.cross_section(rho)), 0.99) < 1e-9

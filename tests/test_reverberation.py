@@ -93,3 +93,28 @@ def test_reference_reverberation_literals_with_the_oracle_tracer(oracle_plunging
 def test_reference_reverberation_literals_on_the_device():
     lt, binned, flux = run_reference_test()
     check(lt, binned, flux, tol_sum=1e-4, tol_row=1e-5)
+
+
+@pytest.mark.gpu
+def test_device_bucket2d_equals_the_host_bucket_and_ignores_the_order(ensemble):
+    """`gb200_bucket2d` (bin_transfer_function's 2-D `bucket`, transfer-functions-2d.jl:100-122): the host histogram to the
+    rounding of a float sum, and bit-identical when the samples are shuffled (fixed-point accumulation)."""
+    from gradus_b200 import reverberation as rv
+
+    rng = np.random.default_rng(2)
+    n = 400_000
+    t = rng.uniform(900.0, 1400.0, n)
+    e = 6.4 * rng.uniform(0.2, 1.4, n)
+    f = rng.uniform(0.0, 1.0, n) ** 3
+    f /= f.sum()
+    f[::1000] = np.nan  # samples without a value are skipped
+    eb, tb = np.linspace(e.min(), e.max(), 300), np.linspace(t.min(), t.max(), 300)
+    ok = np.isfinite(f)
+    host = rv.bucket2d(e[ok], t[ok], f[ok], eb, tb)
+    dev = rv.bucket2d(e, t, f, eb, tb, ensemble)
+    assert np.abs(dev - host).max() < 1e-15 and abs(dev.sum() - host.sum()) < 1e-14
+    perm = rng.permutation(n)
+    assert np.array_equal(rv.bucket2d(e[perm], t[perm], f[perm], eb, tb, ensemble), dev)
+    tb2, eb2, td = rv.bin_transfer_function(t[ok], e[ok], f[ok], ensemble=ensemble)
+    _, _, td_host = rv.bin_transfer_function(t[ok], e[ok], f[ok])
+    assert np.array_equal(np.isnan(td), np.isnan(td_host)) and np.nanmax(np.abs(td - td_host)) < 1e-12 * np.nanmax(td_host)
