@@ -252,6 +252,20 @@ def run_ours(args, rank, world, local):
     e2e_value = total_rays / e2e_s
     checksum = float(np.nansum(h_imgs[0].numpy()))
 
+    # ---- which parity tolerance covers which share of this workload's rays (tests/test_gpu_parity.py::check_parity)
+    d_status = torch.empty(n_local, dtype=torch.float64, device=dev)
+    spf = np.array([cabi.PF_STATUS], np.int32)
+    cabi.check(lib.gb200_render_device(ctx, C.byref(p), C.byref(ic), C.byref(rng), cabi.iptr(spf), 1, None, (C.c_void_p * 1)(C.c_void_p(d_status.data_ptr())), sptr, 0), ctx)
+    frac = torch.bincount(d_status.to(torch.int64), minlength=4).double().cpu().numpy() / n_local
+    parity = {
+        "protocol": "GPU vs CPU oracle on identical inputs; identical termination class for every ray outside the grazing band (0.42 % of C1/C2 rays)",
+        "intersected_with_geometry": {"fraction": float(frac[2]), "tolerance": "end point and momentum 1e-6 relative, redshift 1e-6 absolute (root-found on the dense output)"},
+        "no_status": {"fraction": float(frac[3]), "tolerance": "end point 1e-6 relative at lambda_max"},
+        "within_inner_boundary": {"fraction": float(frac[1]), "tolerance": "class identical; state on the oracle's geodesic at the same affine parameter to 2e-4 "
+                                  "(the chart callback r <= 1.01 r_h has no root find, charts.jl:8-24: the stored point is wherever the last step landed)"},
+        "out_of_domain": {"fraction": float(frac[0]), "tolerance": "class identical; state on the oracle's geodesic to 1e-5"},
+    }
+
     # ---- secondary: binned line profile with the histogram all-reduced over NCCL (BASELINE.json configs[2])
     lp = None
     if not args.no_lineprofile:
@@ -326,6 +340,7 @@ def run_ours(args, rank, world, local):
         "ms_per_step_per_rank": ms_ranks,
         "total_rays_per_step": total_rays, "step_attempts_per_step": total_attempts, "image_checksum": checksum,
     }
+    out["parity"] = parity
     if strong is not None:
         out["strong"] = strong
     if lp is not None:
@@ -546,8 +561,21 @@ def run_lineprofile(args, rank, world, local, ens, dev, stream, sptr):
     ms = gd.max_over_ranks(a.elapsed_time(b) / args.lp_steps, dev)
     total = gd.sum_over_ranks(float(rng.count), dev)
     fl = flux.cpu().numpy()
+    # end to end through the blocking C-ABI call: host bins in, host flux out (this rank's shard), wall clock
+    h_flux = np.zeros(len(bins))
+    e2e_call = lambda: cabi.check(lib.gb200_lineprofile(ctx, C.byref(p), C.byref(ic), C.byref(rng), C.byref(emis), None, cabi.dptr(bins), len(bins),
+                                                        C.byref(opts), cabi.dptr(h_flux)), ctx)
+    e2e_call()
+    gd.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.lp_steps):
+        e2e_call()
+    e2e_s = gd.max_over_ranks((time.perf_counter() - t0) / args.lp_steps, dev)
     return {"metric": "geodesics/sec (binned line profile, NCCL-reduced histogram)", "value": total / (ms * 1e-3), "unit": "rays/s",
             "ms_per_step": ms, "rays_per_step": total, "plane": f"PolarPlane geometric {args.lp_n}x{args.lp_n * world}", "nbins": 180,
+            "histogram": "fused into the trace kernel: per-CTA shared-memory bins, exact 128-bit fixed-point sums, 0 B/ray through HBM",
+            "e2e": {"value": total / e2e_s, "unit": "rays/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": 8 * len(bins) + C.sizeof(cabi.Problem),
+                    "d2h_bytes_per_step": 8 * len(bins), "timing": "wall clock around the blocking gb200_lineprofile call (host bins in, host flux out)"},
             "flux_sum": float(fl.sum()), "flux_argmax_g": float(bins[int(np.argmax(fl))])}
 
 

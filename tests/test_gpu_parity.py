@@ -39,19 +39,21 @@ def _x_rel(a, b):
     return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0), axis=0)
 
 
-def grazing_band(p, ic, ref):
-    ratio = oracle.band_ratio(p, ic)
+def grazing_band(p, ic, ref, rng=None):
+    ratio = oracle.band_ratio(p, ic, rng=rng)
     band = (ratio > 0) & (ratio < 1.3)
     # rounding-sensitive rays: the same oracle in x87 long double (64-bit mantissa) takes a different step sequence
     # (the first steps' error estimates are rounding noise), exactly as any other correct implementation does
-    alt = oracle.trace(p, ic, precision=1)
+    alt = oracle.trace(p, ic, rng=rng, precision=1)
     hit = (ref.status == cabi.STATUS_INTERSECTED) & (alt.status == cabi.STATUS_INTERSECTED)
     moved = np.zeros(len(band), bool)
     moved[hit] = (_x_rel(alt.x[:, hit], ref.x[:, hit]) > 3e-7) | (_vec_rel(alt.v[:, hit], ref.v[:, hit], 1e-12) > 3e-7)
     return band | (alt.status != ref.status) | moved
 
 
-def check_parity(cfg, name, max_band=2e-2, discrete_tol=1e-5):
+def check_parity(cfg, name, max_band, discrete_tol=1e-5):
+    """`max_band`: the grazing band of this configuration may not be larger (1.5 x what was measured: C1 0.42 %, C3 0.06 %,
+    Johannsen-Psaltis 0.41 %; none at all in the Shakura-Sunyaev, datum-plane, no-geometry and lamp-post fixtures)."""
     p, ic = cfg.to_c()
     ref = oracle.trace(p, ic)
     band = grazing_band(p, ic, ref)
@@ -94,10 +96,30 @@ def check_parity(cfg, name, max_band=2e-2, discrete_tol=1e-5):
     return p, ic, ref, gps, band
 
 
+def check_sampled_parity(p, ic, rng, got_g, got_rho, got_status, name, max_band):
+    """A strided sample (>= 65 536 rays) of a full-size launch against the oracle, by the protocol of `check_parity`:
+    identical termination class for EVERY sampled ray outside the grazing band (band-ratio rays plus the rays the
+    oracle itself moves between double and long double), redshift within 1e-6 absolute, radius within 1e-6 relative."""
+    want, ref = oracle.render(p, ic, [cabi.PF_REDSHIFT, cabi.PF_DISC_RADIUS], rng=rng, endpoints=True)
+    band = grazing_band(p, ic, ref, rng=rng)
+    assert band.mean() < max_band, f"{name}: grazing band {band.mean():.3%}"
+    ok = ~band
+    mism = (got_status.astype(np.int32) != ref.status) & ok
+    assert not mism.any(), f"{name}: {mism.sum()} of {ok.sum()} sampled rays outside the band differ in status (sample indices {np.where(mism)[0][:10]})"
+    hit = ok & (ref.status == cabi.STATUS_INTERSECTED)
+    assert hit.sum() > 0.25 * rng.count
+    assert np.array_equal(np.isnan(got_g[ok]), np.isnan(want[0][ok]))
+    assert np.abs(got_g[hit] - want[0][hit]).max() < 1e-6 and np.abs(got_rho[hit] / want[1][hit] - 1).max() < 1e-6
+    counts = np.bincount(ref.status, minlength=4) / rng.count
+    print(f"{name}: {rng.count} sampled rays, band {band.mean():.3%}; status fractions out-of-domain {counts[0]:.3f} inner-boundary {counts[1]:.3f} "
+          f"intersected {counts[2]:.3f} no-status {counts[3]:.3f}")
+    return band
+
+
 def test_c1_kerr_thin_disc_128(ensemble):
     """BASELINE configs[0]: Kerr a=0.998, r=1000, theta=60deg, 128x128, ThinDisc(0,50), Tsit5 1e-9."""
     m, x, d, cfg = common.c1(128, 128, ensemble=ensemble)
-    p, ic, ref, gps, band = check_parity(cfg, "C1")
+    p, ic, ref, gps, band = check_parity(cfg, "C1", 6e-3)
     # redshift + disc-radius images through the fused render path
     pfs = [gb.ConstPointFunctions.redshift(m, x) @ gb.ConstPointFunctions.filter_intersected(),
            gb.ConstPointFunctions.radius() @ gb.ConstPointFunctions.filter_intersected()]
@@ -116,7 +138,7 @@ def test_c1_kerr_thin_disc_128(ensemble):
 def test_c3_line_profile_plane(ensemble):
     """BASELINE configs[2] at reduced size: PolarPlane(GeometricGrid) + hemisphere callback + binned line profile."""
     m, x, d, plane, cfg = common.c3(128, 128, ensemble=ensemble)
-    p, ic, ref, gps, band = check_parity(cfg, "C3")
+    p, ic, ref, gps, band = check_parity(cfg, "C3", 2e-3)
     bins = np.linspace(0.1, 1.5, 180)
     _, flux = gb.lineprofile(bins, gb.PowerLawEmissivity(3.0), m, x, d, gb.BinningMethod(), plane=plane, lambda_max=2000.0, ensemble=ensemble)
     emis = cabi.Emissivity(cabi.EMISSIVITY_POWERLAW, 0, 3.0, None, None)
@@ -136,7 +158,7 @@ def test_c5_johannsen_psaltis(ensemble, a, eps3):
     """BASELINE configs[4]: closed-form non-Kerr RHS (the reference's JP test points)."""
     inner = None if a == 0.6 else 2.0  # the near-naked-singularity point has no ISCO
     m, x, d, cfg = common.c5(96, 96, a=a, eps3=eps3, ensemble=ensemble, inner=inner)
-    p, ic, ref, gps, band = check_parity(cfg, f"C5 a={a}")
+    p, ic, ref, gps, band = check_parity(cfg, f"C5 a={a}", 6e-3)
     if a == 0.6:
         pf = gb.ConstPointFunctions.redshift(m, x) @ gb.ConstPointFunctions.filter_intersected()
         _, _, img = gb.rendergeodesics(m, x, d, 2000.0, pf=pf, image_width=96, image_height=96, ensemble=ensemble)
@@ -149,11 +171,11 @@ def test_shakura_sunyaev_and_datum_plane(ensemble):
     m = gb.KerrMetric(1.0, 0.9)
     x = [0.0, 1000.0, math.radians(70.0), 0.0]
     cfg = common.render_config(m, x, gb.ShakuraSunyaev(m, eddington_ratio=0.3), 2000.0, 64, 64, (-40, 40), (-30, 30), ensemble=ensemble)
-    check_parity(cfg, "ShakuraSunyaev")
+    check_parity(cfg, "ShakuraSunyaev", 1e-3)
     cfg = common.render_config(m, x, gb.DatumPlane(0.5), 2000.0, 48, 48, (-30, 30), (-20, 20), ensemble=ensemble)
-    check_parity(cfg, "DatumPlane")
+    check_parity(cfg, "DatumPlane", 1e-3)
     cfg = common.render_config(m, x, None, 2000.0, 48, 48, (-12, 12), (-12, 12), ensemble=ensemble)
-    check_parity(cfg, "no geometry")
+    check_parity(cfg, "no geometry", 1e-3)
 
 
 def test_explicit_initial_conditions_lamp_post_like(ensemble):
@@ -164,7 +186,7 @@ def test_explicit_initial_conditions_lamp_post_like(ensemble):
     # unnormalised directions in the (r, theta) plane; v^t is re-constrained by the library like constrain_all does
     vs = np.stack([np.zeros_like(delta), -np.cos(delta), np.sin(delta) / 10.0, np.zeros_like(delta)], axis=1)
     cfg = tracing_configuration(m, xs, vs, gb.ThinDisc(0.0, 1000.0), 10000.0, callback=gb.domain_upper_hemisphere(), ensemble=ensemble)
-    p, ic, ref, gps, band = check_parity(cfg, "explicit IC", max_band=5e-2)
+    p, ic, ref, gps, band = check_parity(cfg, "explicit IC", 1e-3)
     assert (gps.status == cabi.STATUS_INTERSECTED).sum() > 50
 
 
@@ -246,17 +268,10 @@ def test_full_size_render_properties(ensemble):
     assert np.array_equal(np.isnan(g), ~hit) and np.array_equal(np.isnan(rho), ~hit)
     assert 0.4 < hit.mean() < 0.5
     assert 0.0 < np.nanmin(g) < 0.3 and 1.2 < np.nanmax(g) < 1.5 and np.nanmax(rho) <= 50.0 * (1 + 1e-12)
-    # strided oracle sample of the full-size image: 4096 rays
-    rng = cabi.Range(17, 4096, 1024)
-    want = oracle.render(p, ic, [cabi.PF_REDSHIFT, cabi.PF_DISC_RADIUS, cabi.PF_STATUS], rng=rng)
-    ratio = oracle.band_ratio(p, ic, rng=rng)
-    ok = ~((ratio > 0) & (ratio < 1.3))
-    got = full[:, 17::1024][:, :4096]
-    # the same tiny photon-ring population as in check_parity is excluded by requiring equal status on >= 99.9 %
-    agree = got[2] == want[2]
-    assert agree[ok].mean() > 0.999
-    both = ok & agree & ~np.isnan(want[0])
-    assert np.abs(got[0][both] - want[0][both]).max() < 1e-6
+    # strided oracle sample of the full-size image: every 64th ray, 65 536 rays
+    rng = cabi.Range(17, 65536, 64)
+    got = full[:, 17::64][:, :65536]
+    check_sampled_parity(p, ic, rng, got[0], got[1], got[2], "C2 2048x2048", 6e-3)
 
 
 def test_full_size_trace_conservation_laws(ensemble):
@@ -600,11 +615,16 @@ def test_full_size_lineprofile_properties(ensemble):
     assert flux.sum() == pytest.approx(1.0) and flux[0] < 1e-3 and flux[-1] == 0.0  # g < 0.1 is clamped into the first bin (Buckets.Simple)
     g_peak = bins[np.argmax(flux)]
     assert 1.0 < g_peak < 1.15  # blue horn of an a = 0.998 disc seen at 40 degrees
-    # strided oracle sample: the same 4096 rays through the oracle's line-profile path, compared as a histogram
-    rng = cabi.Range(29, 4096, 4093)
+    # strided oracle sample: every 255th ray (65 536 rays) through the oracle's line-profile path, compared as a histogram,
+    # and ray by ray through the fused render of the same rays
+    rng = cabi.Range(29, 65536, 255)
     want = oracle.lineprofile(p, ic, emis, bins, opts, rng=rng)
     got = hist(rng)
     assert np.abs(got - want).sum() <= 1e-4 * np.abs(want).sum()
+    pfs = np.array([cabi.PF_REDSHIFT, cabi.PF_DISC_RADIUS, cabi.PF_STATUS], np.int32)
+    imgs = np.zeros((3, rng.count))
+    cabi.check(lib.gb200_render(ctx, C.byref(p), C.byref(ic), C.byref(rng), cabi.iptr(pfs), 3, None, (cabi._dp * 3)(*[cabi.dptr(imgs[k]) for k in range(3)])), ctx)
+    check_sampled_parity(p, ic, rng, imgs[0], imgs[1], imgs[2], "C3 4096x4096", 2e-3)
 
 
 def test_full_size_johannsen_psaltis_properties(ensemble):
@@ -631,16 +651,9 @@ def test_full_size_johannsen_psaltis_properties(ensemble):
     assert np.array_equal(np.isnan(g), ~hit) and 0.3 < hit.mean() < 0.5
     assert np.nanmin(rho) >= gb.isco(m) * (1 - 1e-12) and np.nanmax(rho) <= 50.0 * (1 + 1e-12)
     assert 0.1 < np.nanmin(g) < 0.5 and 1.1 < np.nanmax(g) < 1.5
-    rng = cabi.Range(23, 4096, 1021)
-    want = oracle.render(p, ic, [cabi.PF_REDSHIFT, cabi.PF_DISC_RADIUS, cabi.PF_STATUS], rng=rng)
-    ratio = oracle.band_ratio(p, ic, rng=rng)
-    ok = ~((ratio > 0) & (ratio < 1.3))
-    got = full[:, 23::1021][:, :4096]
-    agree = got[2] == want[2]
-    assert agree[ok].mean() > 0.999
-    both = ok & agree & ~np.isnan(want[0])
-    assert both.sum() > 1000
-    assert np.abs(got[0][both] - want[0][both]).max() < 1e-6 and np.abs(got[1][both] / want[1][both] - 1).max() < 1e-6
+    rng = cabi.Range(23, 65536, 63)  # every 63rd ray: 65 536 rays
+    got = full[:, 23::63][:, :65536]
+    check_sampled_parity(p, ic, rng, got[0], got[1], got[2], "C5 2048x2048", 6e-3)
 
 
 # --------------------------------------------------------------------------- the library's own multi-device path

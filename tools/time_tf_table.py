@@ -21,9 +21,10 @@ def main():
     d = gb.ThinDisc(0.0, float("inf"))
     radii_of = lambda m: 1.0 / np.linspace(1.0 / 500.0, 1.0 / (gb.isco(m) + 1e-2), nr)[::-1]  # Grids._inverse_grid
     ens = gb.EnsembleB200(devices=(0,))
-    tf.transfer_function_table(metrics[:2], observers[:2], d, radii_of, ensemble=ens)  # warm-up
+    fast = tf.TransferFunctionSetup(warm_start=True, stall_exit=6)
+    tf.transfer_function_table(metrics[:2], observers[:2], d, radii_of, ensemble=ens, setup=fast)  # warm-up
     t0 = time.perf_counter()
-    table = tf.transfer_function_table(metrics, observers, d, radii_of, ensemble=ens)
+    table = tf.transfer_function_table(metrics, observers, d, radii_of, ensemble=ens, setup=fast)
     dt_table = time.perf_counter() - t0
     nctf = sum(len(r) for r in table)
     print(f"lock-step table: {len(cells)} cells x {nr} radii = {nctf} transfer functions in {dt_table:.2f} s "
@@ -31,7 +32,7 @@ def main():
     ncmp = min(len(cells), 4)
     t0 = time.perf_counter()
     for m, x in zip(metrics[:ncmp], observers[:ncmp]):
-        tf.cunningham_transfer_functions(m, x, d, radii_of(m), ensemble=ens)
+        tf.cunningham_transfer_functions(m, x, d, radii_of(m), ensemble=ens, setup=fast)
     dt_cell = (time.perf_counter() - t0) / ncmp
     print(f"cell by cell: {dt_cell:.2f} s per cell -> {dt_cell * len(cells):.2f} s for the table "
           f"({dt_cell / nr * 1e3:.2f} ms per transfer function); lock step is {dt_cell * len(cells) / dt_table:.1f}x faster", flush=True)
