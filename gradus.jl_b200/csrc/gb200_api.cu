@@ -134,7 +134,9 @@ static int generic_isco_host(int kind, const double* mp, double* out) {
 
 // Start of every entry point that uses the context's queue / pool on `stream`: order it after an earlier asynchronous call.
 static int begin_call(gb200_ctx* ctx, cudaStream_t stream) {
-    { int rc_ = begin_call(ctx, stream); if (rc_) return rc_; }
+    CU(ctx, cudaSetDevice(ctx->device));
+    ctx->stats = gb200_stats{};
+    ctx->cur = stream;
     if (ctx->have_inflight) CU(ctx, cudaStreamWaitEvent(stream, ctx->inflight, 0));
     return GB200_OK;
 }

@@ -45,6 +45,9 @@
 #define GB_OPT_LOGEXP 1 /* branch-free log/exp with constant-bank coefficients in the step controller */
 #endif
 
+#ifndef GB_OPT_INVQ
+#define GB_OPT_INVQ 0 /* step-size update from 1/q = clamp(gamma exp(-arg)): no reciprocal, no division on the reject path */
+#endif
 #ifndef GB_OPT_PROGERR
 #define GB_OPT_PROGERR 1 /* error sums accumulated stage by stage, error scales formed under the seventh RHS */
 #endif
@@ -635,6 +638,22 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
 #endif
             double EEst = 1.0; // only the Float32 mode reads it
             if (fast32) EEst = gb_sqrt_pos(EEst2);
+#if GB_OPT_INVQ
+            // The controller only ever divides by q: form 1/q = clamp(gamma / (EEst^beta1 / qold^beta2), qmin, qmax) from
+            // exp(-arg) directly -- no reciprocal of q, and the rejected step's dt / min(1/qmin, EEst^beta1 / gamma) becomes a
+            // product as well (that one was an IEEE division).
+            double Einv; // 1 / (EEst^beta1 / qold^beta2) for an accepted step, 1 / EEst^beta1 for a rejected one
+            if (fast32) {
+                double Epow = ctrl_pow_log(logE, EEst, beta1, P.pow_mode);
+                if (accept) Epow *= gb_rcp(qoldpow);
+                Einv = gb_rcp(Epow);
+            } else {
+                const double arg = accept ? fma(beta1, logE, -qoldpow) : beta1 * logE; // qoldpow = beta2 * log(qold) in this mode
+                Einv = gb_exp_small(gb_max(-8.0, gb_min(8.0, -arg))); // 1/q is clamped to [qmin, qmax] = exp(-1.7 .. 2.3) afterwards
+            }
+            const double gEinv = gamma * Einv;
+            const double dtnew = dt * gb_max_pos(qmin, gb_min_pos(qmax, gEinv));
+#else
             double Epow;
             if (fast32) {
                 Epow = ctrl_pow_log(logE, EEst, beta1, P.pow_mode);
@@ -652,11 +671,16 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
             // unconditionally and committed with selects: the loop-carried state then lives in the same registers on
             // every path (the branchy form cost ~200 register moves per attempt where the paths merged).
             const double dtnew = dt * gb_rcp(q);
+#endif
             const double ttmp = lam + dt;
             const double tnew = (fabs(ttmp - tstop) < 100.0 * (fabs(tstop) * 2.220446049250313e-16)) ? tstop : ttmp;
             const double dtprop = gb_max_pos(gb_min_pos(dtmax, dtnew), dtmin);
+#if GB_OPT_INVQ
+            const double dtrej = gb_max(dt * gb_max_pos(qmin, gEinv), dtmin); // only read when the step is rejected
+#else
             double dtrej = dt;
             if (!accept) dtrej = gb_max(dt / gb_min(1.0 / qmin, Epow / gamma), dtmin);
+#endif
             // ---- callbacks: continuous (disc) first, then discrete (user, chart)
             bool event = false;
             double cnext = 1.0;

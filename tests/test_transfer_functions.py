@@ -216,7 +216,7 @@ def test_reference_literals_with_the_oracle_tracer(case):
     vals, res = ctf_variants(case, OracleProber, variants=VARIANTS[::2] + VARIANTS[1:2])
     how = hold_literal(vals, res, case[3], reference_tolerance(case[3], case[4]))
     # the literals that any implementation can reproduce are reproduced at the reference's own tolerance
-    if (case[1], case[2]) in {(74, 4.0), (85, 4.0), (30, 300.0), (30, 800.0), (30, 1000.0)}:
+    if (case[1], case[2]) in {(74, 4.0), (85, 4.0), (30, 15.0), (30, 300.0), (30, 800.0), (30, 1000.0)}:
         assert how == "strict"
 
 
@@ -344,7 +344,7 @@ def test_reference_literals_on_the_device(case):
     """All eleven literals with the device's forward-mode tracer at the reference's tolerance, all eight variants."""
     vals, res = ctf_variants(case, gb.DeviceProber)
     how = hold_literal(vals, res, case[3], reference_tolerance(case[3], case[4]))
-    if (case[1], case[2]) in {(74, 4.0), (85, 4.0), (30, 300.0), (30, 800.0), (30, 1000.0)}:
+    if (case[1], case[2]) in {(74, 4.0), (85, 4.0), (30, 15.0), (30, 300.0), (30, 800.0), (30, 1000.0)}:
         assert how == "strict"
     # the resolved part of the statistic is the same number on the device and with the oracle as tracer
     _, res_o = ctf_variants(case, OracleProber, variants=VARIANTS[:1])
