@@ -92,8 +92,11 @@ def test_values_only_norm_retraces_the_plain_render(ensemble):
     assert np.array_equal(dev.status, img[2].astype(np.int32))
     hit = dev.status == cabi.STATUS_INTERSECTED
     assert hit.sum() > 100
-    assert np.max(np.abs(dev.g[hit] - img[0][hit])) < 1e-9
-    assert np.max(np.abs(dev.rho[hit] / img[1][hit] - 1)) < 1e-9
+    # same steps up to rounding: the two kernels order their arithmetic differently, and a last-bit difference in an error
+    # estimate moves the following step sizes (measured 7e-8 in g; the protocol of the main path asks for 1e-6)
+    assert np.max(np.abs(dev.g[hit] - img[0][hit])) < 1e-6
+    assert np.max(np.abs(dev.rho[hit] / img[1][hit] - 1)) < 1e-6
+    assert abs(int(dev.naccept.sum()) - int(api.solve_tracing_problem(cfg).naccept.sum())) <= 0.002 * dev.naccept.sum()
 
 
 def test_jacobian_against_finite_differences_of_the_throughput_kernel(ensemble):
