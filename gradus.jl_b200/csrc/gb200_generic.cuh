@@ -141,15 +141,45 @@ GB_HD inline void kerr_newman_lorentz_g(const double* mp, const S& r, const S& s
     acc[2] = acc[2] + q * gi[2] * wth;
     acc[3] = acc[3] + q * (gi[4] * wt + gi[3] * wp);
 }
+// Kerr accelerations in closed form over S: the Euler-Lagrange form of kerr_rhs_accel_sq (gb200_device.cuh) -- two thirds
+// of the operations of the generic metric Jacobian + contraction, which matters threefold on GD<2>
+template <class S>
+GB_HD inline void kerr_accel_g(double M, double a, const S& r, const S& s, const S& c, const S& vt, const S& vr, const S& vth, const S& vph, S acc[4]) {
+    const double a2 = a * a;
+    const S s2 = s * s, sin2 = 2.0 * (s * c), r2 = r * r;
+    const S rho2 = r2 + a2;
+    const S Sig = r2 + a2 * (c * c), Del = r * (r - 2.0 * M) + a2;
+    const S iSig = 1.0 / Sig, iDel = 1.0 / Del;
+    const S w = (2.0 * M) * r * iSig;
+    const S hw_r = (M - w * r) * iSig; // w_r / 2
+    const S a2sin2 = a2 * sin2;
+    const S as2 = a * s2;
+    const S A = vt - as2 * vph, U = w * A;
+    const S h = a2sin2 * vth;
+    const S wdot = 2.0 * (hw_r * vr) + (w * iSig) * h;
+    const S rr = r * vr;
+    const S Udot = ((rho2 * wdot) * A - (w * h) * U + 2.0 * (((w * as2) * rr) * vph)) * iDel;
+    const S pp = vph * vph, tt = vth * vth, rr2 = vr * vr, X = vr * vth;
+    acc[0] = Udot;
+    acc[1] = (Del * iSig) * (r * (s2 * pp + tt) + hw_r * (A * A)) - (r * iSig - (r - M) * iDel) * rr2 + (a2sin2 * iSig) * X;
+    acc[2] = iSig * ((0.5 * sin2) * (rho2 * pp - (2.0 * a) * (U * vph) + a2 * (tt - rr2 * iDel + (U * A) * iSig)) - 2.0 * (r * X));
+    const S m = (sin2 / s2) * vth;
+    acc[3] = (a * (m * U + Udot) - 2.0 * (rr * vph)) / rho2 - m * vph;
+}
+
 // _second_order_ode_f (src/tracing/geodesic-problem.jl:87-92): du = (v, a); also returns sin, cos of theta
 template <int N>
 GB_HD inline void rhs_g(const GbParams& P, const GD<N> u[8], GD<N> du[8], GD<N>& s, GD<N>& c) {
     typedef GD<N> S;
     gd_sincos(u[2], s, c);
-    S g[5], dr[5], dth[5], gi[5], acc[4];
-    metric_jacobian_kind<S>(P.metric_kind, P.mp, u[1], s, c, g, dr, dth);
-    geodesic_accel_g<S>(g, dr, dth, u[4], u[5], u[6], u[7], acc, gi);
-    if (P.metric_kind == GB200_METRIC_KERR_NEWMAN && P.mp[3] != 0.0) kerr_newman_lorentz_g<S>(P.mp, u[1], s, c, gi, u[4], u[5], u[6], u[7], acc);
+    S acc[4];
+    if (P.metric_kind == GB200_METRIC_KERR) kerr_accel_g<S>(P.M, P.a, u[1], s, c, u[4], u[5], u[6], u[7], acc);
+    else {
+        S g[5], dr[5], dth[5], gi[5];
+        metric_jacobian_kind<S>(P.metric_kind, P.mp, u[1], s, c, g, dr, dth);
+        geodesic_accel_g<S>(g, dr, dth, u[4], u[5], u[6], u[7], acc, gi);
+        if (P.metric_kind == GB200_METRIC_KERR_NEWMAN && P.mp[3] != 0.0) kerr_newman_lorentz_g<S>(P.mp, u[1], s, c, gi, u[4], u[5], u[6], u[7], acc);
+    }
     for (int i = 0; i < 4; ++i) { du[i] = u[4 + i]; du[4 + i] = acc[i]; }
 }
 

@@ -1375,8 +1375,40 @@ static double band_ratio(const gb200_problem& p, const Metric& m, const double u
             const double dth = std::fabs(rec.u[8 * sidx + 2] - up[2]);
             if (!crosses && std::min(c0, c1) - dth > 4.0 * p.gtol) continue;
         }
-        for (int f = (sidx == 0 ? 0 : 1); f <= nfine; ++f) {
-            const double Th = (double)f / nfine;
+        // sample abscissae: a uniform grid, refined twice (x 64 each) in the cells where the thin disc's three
+        // constraints -- inside the wedge |z| < gtol r, rho <= r_out, rho >= r_in -- could all hold at once: a ray that clips
+        // the corner of the wedge at the disc's edge is inside for an affine length of 1e-3 or less, far below dt / 256
+        std::vector<double> ths;
+        for (int f = 0; f <= nfine; ++f) ths.push_back((double)f / nfine);
+        if (p.geometry_kind == GB200_GEOMETRY_THIN_DISC) {
+            auto parts = [&](double Th, double out3[3]) {
+                double ui[8];
+                interpolant<double>(Th, dt, up, k, ui, 3);
+                const double rho = ui[1] * std::fabs(std::sin(ui[2]));
+                out3[0] = ui[1] * std::fabs(std::cos(ui[2])) - p.gtol * std::fabs(ui[1]);
+                out3[1] = rho - p.geometry_params[1];
+                out3[2] = p.geometry_params[0] - rho;
+            };
+            for (int pass = 0; pass < 2; ++pass) {
+                std::vector<double> finer;
+                double a3[3], b3[3];
+                parts(ths[0], a3);
+                for (size_t c = 0; c + 1 < ths.size(); ++c) {
+                    parts(ths[c + 1], b3);
+                    finer.push_back(ths[c]);
+                    bool candidate = true;
+                    for (int q3 = 0; q3 < 3; ++q3) if (a3[q3] > 0 && b3[q3] > 0) candidate = false; // this constraint fails in the whole cell
+                    const bool resolved = (a3[0] < 0 && a3[1] <= 0 && a3[2] <= 0) || (b3[0] < 0 && b3[1] <= 0 && b3[2] <= 0); // an end is inside already
+                    if (candidate && !resolved)
+                        for (int j = 1; j < 64; ++j) finer.push_back(ths[c] + (ths[c + 1] - ths[c]) * j / 64.0);
+                    for (int q3 = 0; q3 < 3; ++q3) a3[q3] = b3[q3];
+                }
+                finer.push_back(ths.back());
+                ths.swap(finer);
+            }
+        }
+        for (size_t f = (sidx == 0 ? 0 : 1); f < ths.size(); ++f) {
+            const double Th = ths[f];
             double ui[8];
             interpolant<double>(Th, dt, up, k, ui, 3);
             const bool neg = disc_condition<double>(p, ui[1], ui[2]) < 0.0;
