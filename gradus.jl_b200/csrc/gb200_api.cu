@@ -1404,38 +1404,72 @@ int gb200_comm_render(gb200_comm* c, const gb200_problem* p, const gb200_ic* ic,
                       const gb200_plunging_table* pl, double* const* images) {
     if (!c || !ic || !pfs || !images || npf < 1 || npf > GB_MAX_PF) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "bad render arguments");
     const int n = (int)c->ctx.size();
+    const int K = 4; // chunks per device: a chunk's images travel to the host while the next chunks compute
     std::vector<gb200_range> rgs((size_t)n);
     std::vector<std::vector<double*>> dimg((size_t)n);
-    // all launches first (asynchronous), then the copies: the devices compute concurrently
+    std::vector<std::vector<cudaEvent_t>> done((size_t)n);
+    std::vector<int64_t> per((size_t)n, 0);
+    auto cleanup = [&]() { for (auto& v : done) for (auto e : v) cudaEventDestroy(e); };
+    // all launches first (asynchronous, one host thread): the devices compute concurrently
     for (int d = 0; d < n; ++d) {
         gb200_ctx* ctx = c->ctx[(size_t)d];
-        rgs[(size_t)d] = shard_range(ic, d, n);
+        gb200_range& rg = rgs[(size_t)d];
+        rg = shard_range(ic, d, n);
+        if (rg.block < 1) rg.block = 1;
         CU(ctx, cudaSetDevice(ctx->device));
+        while (ctx->pool_streams.size() < 2) {
+            cudaStream_t st;
+            CU(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            ctx->pool_streams.push_back(st);
+        }
         dimg[(size_t)d].resize((size_t)npf);
         for (int k = 0; k < npf; ++k) {
             void* dv = nullptr;
-            int rc = pool_get(ctx, SL_IMG0 + k, sizeof(double) * (size_t)rgs[(size_t)d].count + 8, &dv);
-            if (rc) return fail(nullptr, rc, "device %d: %s", ctx->device, ctx->err.c_str());
+            int rc = pool_get(ctx, SL_IMG0 + k, sizeof(double) * (size_t)rg.count + 8, &dv);
+            if (rc) { cleanup(); return fail(nullptr, rc, "device %d: %s", ctx->device, ctx->err.c_str()); }
             dimg[(size_t)d][(size_t)k] = (double*)dv;
         }
-        if (rgs[(size_t)d].count == 0) continue;
-        int rc = render_common(ctx, p, ic, &rgs[(size_t)d], pfs, npf, pl, dimg[(size_t)d].data(), true, ctx->stream, 1);
-        if (rc) return fail(nullptr, rc, "device %d: %s", ctx->device, ctx->err.c_str());
+        if (rg.count == 0) continue;
+        const int64_t nblk = rg.count / rg.block; // strips (or single rays in the fallback decomposition)
+        const int chunks = nblk >= 2 * K ? K : 1;
+        per[(size_t)d] = ((nblk + chunks - 1) / chunks) * rg.block;
+        for (int64_t s0 = 0; s0 < rg.count; s0 += per[(size_t)d]) {
+            gb200_range sub{rg.first + (s0 / rg.block) * rg.stride * rg.block, std::min(per[(size_t)d], rg.count - s0), rg.stride, rg.block};
+            double* sub_img[GB_MAX_PF];
+            for (int k = 0; k < npf; ++k) sub_img[k] = dimg[(size_t)d][(size_t)k] + s0;
+            int rc = render_common(ctx, p, ic, &sub, pfs, npf, pl, sub_img, true, ctx->stream, 1);
+            if (rc) { cleanup(); return fail(nullptr, rc, "device %d: %s", ctx->device, ctx->err.c_str()); }
+            cudaEvent_t ev;
+            CU(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            done[(size_t)d].push_back(ev);
+            CU(ctx, cudaEventRecord(ev, ctx->stream));
+        }
     }
+    // copies chunk by chunk, round robin over the devices, on each device's copy stream: strip b of a device sits at ray
+    // first + b * stride * block of the image (a strided 2-D copy); copies into pageable memory block this thread, the
+    // kernels of the later chunks keep running meanwhile
+    for (int ch = 0; ch < K; ++ch)
+        for (int d = 0; d < n; ++d) {
+            if ((size_t)ch >= done[(size_t)d].size()) continue;
+            gb200_ctx* ctx = c->ctx[(size_t)d];
+            const gb200_range& rg = rgs[(size_t)d];
+            const int64_t s0 = (int64_t)ch * per[(size_t)d], cnt = std::min(per[(size_t)d], rg.count - s0);
+            const size_t blk = (size_t)rg.block;
+            CU(ctx, cudaSetDevice(ctx->device));
+            cudaStream_t copy = ctx->pool_streams[1];
+            CU(ctx, cudaStreamWaitEvent(copy, done[(size_t)d][(size_t)ch], 0));
+            for (int k = 0; k < npf; ++k)
+                CU(ctx, cudaMemcpy2DAsync(images[k] + rg.first + (s0 / rg.block) * rg.stride * rg.block, sizeof(double) * blk * (size_t)rg.stride,
+                                          dimg[(size_t)d][(size_t)k] + s0, sizeof(double) * blk, sizeof(double) * blk, (size_t)cnt / blk,
+                                          cudaMemcpyDeviceToHost, copy));
+        }
     for (int d = 0; d < n; ++d) {
         gb200_ctx* ctx = c->ctx[(size_t)d];
-        const gb200_range& rg = rgs[(size_t)d];
-        if (rg.count == 0) continue;
         CU(ctx, cudaSetDevice(ctx->device));
-        const size_t blk = (size_t)(rg.block > 0 ? rg.block : 1);
-        for (int k = 0; k < npf; ++k) // strip b of this device sits at ray first + b * stride * block of the image
-            CU(ctx, cudaMemcpy2DAsync(images[k] + rg.first, sizeof(double) * blk * (size_t)rg.stride, dimg[(size_t)d][(size_t)k], sizeof(double) * blk,
-                                      sizeof(double) * blk, (size_t)rg.count / blk, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ctx->pool_streams.size() >= 2) CU(ctx, cudaStreamSynchronize(ctx->pool_streams[1]));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    for (int d = 0; d < n; ++d) {
-        CU(c->ctx[(size_t)d], cudaSetDevice(c->ctx[(size_t)d]->device));
-        CU(c->ctx[(size_t)d], cudaStreamSynchronize(c->ctx[(size_t)d]->stream));
-    }
+    cleanup();
     return GB200_OK;
 }
 
