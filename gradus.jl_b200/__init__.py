@@ -23,6 +23,7 @@ from .api import (  # noqa: F401
     GeometricGrid,
     InverseGrid,
     BumblebeeMetric,
+    MorrisThorneWormhole,
     JohannsenMetric,
     JohannsenPsaltisMetric,
     KerrNewmanMetric,

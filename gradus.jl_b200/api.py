@@ -107,11 +107,23 @@ class KerrNewmanMetric:
         return _pad8(self.M, self.a, self.Q)
 
 
+@dataclass(frozen=True)
+class MorrisThorneWormhole:
+    """src/metrics/morris-thorne-ad.jl:28-40: wormhole with throat size b; the radial coordinate is the proper distance l
+    (negative on the far side of the throat), `inner_radius` = 0, no horizon and no ISCO."""
+
+    b: float = 1.0
+    kind = cabi.METRIC_MORRIS_THORNE
+
+    def params(self):
+        return _pad8(self.b)
+
+
 def _pad8(*vals):
     return tuple(float(v) for v in vals) + (0.0,) * (8 - len(vals))
 
 
-_SUPPORTED_METRICS = (KerrMetric, JohannsenPsaltisMetric, JohannsenMetric, BumblebeeMetric, KerrNewmanMetric)
+_SUPPORTED_METRICS = (KerrMetric, JohannsenPsaltisMetric, JohannsenMetric, BumblebeeMetric, KerrNewmanMetric, MorrisThorneWormhole)
 
 
 def _check_metric(m):
@@ -123,6 +135,8 @@ def _check_metric(m):
 def inner_radius(m) -> float:
     """kerr-metric.jl:72, johannsen-psaltis-ad.jl:50, johannsen-ad.jl:66, bumblebee-ad.jl:51, kerr-newman-ad.jl:65"""
     _check_metric(m)
+    if isinstance(m, MorrisThorneWormhole):
+        return 0.0  # morris-thorne-ad.jl:40
     q2 = m.Q**2 if isinstance(m, KerrNewmanMetric) else 0.0
     return m.M + math.sqrt(m.M**2 - m.a**2 - q2)
 

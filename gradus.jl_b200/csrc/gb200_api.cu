@@ -153,7 +153,9 @@ static int validate(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic) 
     if (p->metric_kind < 0 || p->metric_kind >= GB200_METRIC_COUNT)
         return fail(ctx, GB200_ERR_UNSUPPORTED, "metric kind %d has no closed-form right-hand side in this library", p->metric_kind);
     const double M = p->metric_params[0], a = p->metric_params[1];
-    if (!(M > 0) || !(std::fabs(a) <= M)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "need M > 0 and |a| <= M (M=%g a=%g)", M, a);
+    if (p->metric_kind == GB200_METRIC_MORRIS_THORNE) { // metric_params[0] is the throat size b, there is no mass or spin
+        if (!(M == M)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "Morris-Thorne throat size b is NaN");
+    } else if (!(M > 0) || !(std::fabs(a) <= M)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "need M > 0 and |a| <= M (M=%g a=%g)", M, a);
     if (p->metric_kind == GB200_METRIC_BUMBLEBEE && (!(p->metric_params[2] > -1.0) || std::fabs(a) > 0.3))
         return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "Bumblebee metric needs l > -1 and |a| <= 0.3 (bumblebee-ad.jl:33-40)");
     if (p->metric_kind == GB200_METRIC_KERR_NEWMAN && a * a + p->metric_params[2] * p->metric_params[2] > M * M)
@@ -562,6 +564,8 @@ int gb200_validate(const gb200_problem* p, const gb200_ic* ic) { return validate
 int gb200_isco(int32_t metric_kind, const double* mp, double* out) {
     if (!mp || !out) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null argument");
     if (metric_kind == GB200_METRIC_KERR) { *out = kerr_isco_host(mp[0], mp[1]); return GB200_OK; }
+    if (metric_kind == GB200_METRIC_MORRIS_THORNE)
+        return fail(nullptr, GB200_ERR_UNSUPPORTED, "the Morris-Thorne wormhole has no circular-orbit energy minimum: no ISCO");
     if (metric_kind > GB200_METRIC_KERR && metric_kind < GB200_METRIC_COUNT) {
         int rc = generic_isco_host(metric_kind, mp, out);
         if (rc) return fail(nullptr, rc, "No boundaries for minimization could be determined. It is likely this configuration does not have an ISCO solution.");

@@ -443,6 +443,17 @@ GB_HD inline void kerr_metric_jacobian(double M, double a, S r, S s, S c, S g[5]
     dth[4] = -a * q;
 }
 
+// Morris-Thorne wormhole, src/metrics/morris-thorne-ad.jl:4-15; mp = (b).  The reference's phi-phi component carries a
+// single power of sin(theta) (:11); restated as written there.
+template <class S>
+GB_HD inline void morris_thorne_metric_jacobian(const double* mp, S r, S s, S c, S g[5], S dr[5], S dth[5]) {
+    const S rho2 = r * r + mp[0] * mp[0];
+    const S zero = 0.0 * r;
+    g[0] = zero - 1.0; g[1] = zero + 1.0; g[2] = rho2; g[3] = rho2 * s; g[4] = zero;
+    dr[0] = zero; dr[1] = zero; dr[2] = 2.0 * r; dr[3] = 2.0 * r * s; dr[4] = zero;
+    dth[0] = zero; dth[1] = zero; dth[2] = zero; dth[3] = rho2 * c; dth[4] = zero;
+}
+
 // components + Jacobian of metric `kind` with parameters mp[] (s = sin theta, c = cos theta)
 template <class S>
 GB_HD inline void metric_jacobian_kind(int kind, const double* mp, S r, S s, S c, S g[5], S dr[5], S dth[5]) {
@@ -451,6 +462,7 @@ GB_HD inline void metric_jacobian_kind(int kind, const double* mp, S r, S s, S c
     case GB200_METRIC_JOHANNSEN_PSALTIS: jp_metric_jacobian<S>(mp[0], mp[1], mp[2], r, s, c, g, dr, dth); break;
     case GB200_METRIC_JOHANNSEN: johannsen_metric_jacobian<S>(mp, r, s, c, g, dr, dth); break;
     case GB200_METRIC_BUMBLEBEE: bumblebee_metric_jacobian<S>(mp, r, s, c, g, dr, dth); break;
+    case GB200_METRIC_MORRIS_THORNE: morris_thorne_metric_jacobian<S>(mp, r, s, c, g, dr, dth); break;
     default: kerr_newman_metric_jacobian<S>(mp, r, s, c, g, dr, dth); break;
     }
 }

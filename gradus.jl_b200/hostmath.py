@@ -21,6 +21,10 @@ def metric_components(m, r, theta):
     """(g_tt, g_rr, g_θθ, g_φφ, g_tφ), each broadcast over r, θ."""
     r = np.asarray(r)
     theta = np.asarray(theta, np.float64)
+    if isinstance(m, api.MorrisThorneWormhole):  # morris-thorne-ad.jl:4-15 (one power of sin θ in g_φφ, as there)
+        b2l2 = m.b**2 + r * r
+        zero = 0 * r + 0 * theta
+        return np.stack(np.broadcast_arrays(zero - 1, zero + 1, b2l2 + zero, b2l2 * np.sin(theta), zero))
     M, a = m.M, m.a
     c2 = np.cos(theta) ** 2
     s2 = np.sin(theta) ** 2

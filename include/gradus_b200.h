@@ -50,7 +50,9 @@ extern "C" {
 #define GB200_METRIC_BUMBLEBEE 3         /* src/metrics/bumblebee-ad.jl:26-46     params: M, a, l  (l > -1, |a| <= 0.3)        */
 #define GB200_METRIC_KERR_NEWMAN 4       /* src/metrics/kerr-newman-ad.jl:41-58   params: M, a, Q, q/mu (charge of the test particle:
                                             Lorentz force q/mu F v of geodesic_ode_problem(::KerrNewmanMetric), :66-102; 0 = neutral) */
-#define GB200_METRIC_COUNT 5
+#define GB200_METRIC_MORRIS_THORNE 5     /* src/metrics/morris-thorne-ad.jl:4-15  params: b (throat size, metric_params[0]); r is the proper
+                                            radial coordinate l, inner_radius = 0 (:40), no ISCO */
+#define GB200_METRIC_COUNT 6
 
 /* ---- accretion geometry: src/geometry/discs/ --------------------------- */
 #define GB200_GEOMETRY_NONE 0

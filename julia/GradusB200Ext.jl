@@ -21,7 +21,7 @@ module GradusB200Ext
 
 using Gradus
 using Gradus: TracingConfiguration, GeodesicPoint, StatusCodes, KerrMetric, JohannsenPsaltisMetric, JohannsenMetric,
-    BumblebeeMetric, KerrNewmanMetric, ThinDisc, ShakuraSunyaev, DatumPlane, PolarChart, PolarPlane, GeometricGrid,
+    BumblebeeMetric, KerrNewmanMetric, MorrisThorneWormhole, ThinDisc, ShakuraSunyaev, DatumPlane, PolarChart, PolarPlane, GeometricGrid,
     LinearGrid, InverseGrid, AbstractTrace, BinningMethod
 using StaticArrays
 import SciMLBase
@@ -104,6 +104,7 @@ _metric(m::KerrMetric, qμ) = (Int32(0), _mp8(m.M, m.a))
 _metric(m::JohannsenPsaltisMetric, qμ) = (Int32(1), _mp8(m.M, m.a, m.ϵ3))
 _metric(m::JohannsenMetric, qμ) = (Int32(2), _mp8(m.M, m.a, m.α13, m.α22, m.α52, m.ϵ3))
 _metric(m::BumblebeeMetric, qμ) = (Int32(3), _mp8(m.M, m.a, m.l))
+_metric(m::MorrisThorneWormhole, qμ) = (Int32(5), _mp8(m.b))
 # slot 4 (metric_params[3]) carries q for photons and q/μ otherwise (geodesic_ode_problem(::KerrNewmanMetric),
 # src/metrics/kerr-newman-ad.jl:74-78)
 _metric(m::KerrNewmanMetric, qμ) = (Int32(4), _mp8(m.M, m.a, m.Q, qμ))

@@ -164,6 +164,13 @@ void metric_components(const Metric& m, const S& r, const S& th, S g[5]) {
         g[2] = sq(r);
         g[3] = sq(r) * sinth2;
         g[4] = -S(2.0) * M * a * sinth2 / r;
+    } else if (m.kind == GB200_METRIC_MORRIS_THORNE) { // src/metrics/morris-thorne-ad.jl:4-15 (b = m.p[0]; sin, not sin^2, :11)
+        S b2l2 = S(m.p[0] * m.p[0]) + sq(r);
+        g[0] = S(-1.0);
+        g[1] = S(1.0);
+        g[2] = b2l2;
+        g[3] = b2l2 * rsin(th);
+        g[4] = S(0.0);
     } else if (m.kind == GB200_METRIC_KERR_NEWMAN) { // src/metrics/kerr-newman-ad.jl:5-27
         S M = S(m.M), a = S(m.a), Q = S(m.p[2]);
         S R = S(2.0) * M;
@@ -194,6 +201,7 @@ void metric_components(const Metric& m, const S& r, const S& th, S g[5]) {
 
 // src/metrics/kerr-metric.jl:72, johannsen-psaltis-ad.jl:50
 inline double inner_radius(const Metric& m) {
+    if (m.kind == GB200_METRIC_MORRIS_THORNE) return 0.0; // morris-thorne-ad.jl:40
     const double q2 = (m.kind == GB200_METRIC_KERR_NEWMAN) ? m.p[2] * m.p[2] : 0.0; // kerr-newman-ad.jl:65
     return m.M + std::sqrt(m.M * m.M - m.a * m.a - q2);
 }

@@ -1,4 +1,5 @@
-"""Further static, axis-symmetric metrics: Johannsen, Bumblebee, Kerr-Newman (neutral particles).
+"""Further static, axis-symmetric metrics: Johannsen, Bumblebee, Kerr-Newman (neutral particles),
+Morris-Thorne wormhole.
 
 Pins: the reference's `rendergeodesics` smoke matrix (test/smoke-tests/rendergeodesics.jl:32-82 — shadow, thin-disc and
 Shakura-Sunyaev fingerprints per metric, default parameters) for the oracle; GPU vs oracle at non-trivial parameters
@@ -79,6 +80,68 @@ def test_constructor_checks_follow_the_reference():
         gb.BumblebeeMetric(1.0, 0.5, 0.0)
     with pytest.raises(ValueError):
         gb.KerrNewmanMetric(1.0, 0.9, 0.9)
+
+
+# --------------------------------------------------------------------------- Morris-Thorne wormhole
+# test/smoke-tests/rendergeodesics.jl:36,46,60,93: the fourth column of the smoke matrix.  The only rays with a finite
+# fingerprint in the shadow image are the four that pass the throat (l <= 0, the chart's inner boundary at
+# inner_radius = 0): a discrete callback without a root find, so their lambda is the end of whichever step crossed l = 0.
+# The oracle lands within 2e-6 (shadow), 7e-7 (thin disc) of the literals (the reference's own tolerance: rtol 1e-1).
+MT_SHADOW, MT_THIN, MT_TORUS = 402.17907632733284, 9375.430228131403, 5104.032822512765
+
+
+def test_oracle_reproduces_the_morris_thorne_column():
+    m = gb.MorrisThorneWormhole()
+    assert api.inner_radius(m) == 0.0
+    p, ic = _smoke_fixture(m, None).to_c()
+    img, ep = oracle.render(p, ic, [cabi.PF_SHADOW], endpoints=True)
+    assert np.nansum(img) == pytest.approx(MT_SHADOW, rel=1e-5)
+    assert np.count_nonzero(ep.status == cabi.STATUS_WITHIN_INNER_BOUNDARY) == 4 and np.all(ep.x[1, ep.status == cabi.STATUS_WITHIN_INNER_BOUNDARY] <= 0)
+    p, ic = _smoke_fixture(m, gb.ThinDisc(0.0, 40.0)).to_c()
+    assert np.nansum(oracle.render(p, ic, [cabi.PF_SHADOW])[0]) == pytest.approx(MT_THIN, rel=1e-5)
+    p.geometry_kind = 100  # the torus closure (below), in the form the literal was recorded with
+    p.geometry_params[3] = 1.0
+    assert np.nansum(oracle.render(p, ic, [cabi.PF_SHADOW])[0]) == pytest.approx(MT_TORUS, rel=1e-3)
+    with pytest.raises(gb.GradusB200Error):
+        api.isco(m)  # no ISCO, as in the reference (the Shakura-Sunyaev entry of this column is skipped there, :63-64)
+
+
+def test_morris_thorne_host_algebra():
+    m = gb.MorrisThorneWormhole(b=1.5)
+    for l_, th in [(-3.0, 0.4), (0.0, 1.3), (250.0, 2.2)]:
+        g, dr, dth = oracle.metric(m.kind, list(m.params()), l_, th)
+        assert np.allclose(hostmath.metric_components(m, l_, th), g, rtol=1e-15, atol=0)
+        assert np.allclose(g, [-1.0, 1.0, 2.25 + l_ * l_, (2.25 + l_ * l_) * math.sin(th), 0.0])
+        assert np.allclose(dr, [0, 0, 2 * l_, 2 * l_ * math.sin(th), 0]) and np.allclose(dth, [0, 0, 0, (2.25 + l_ * l_) * math.cos(th), 0])
+
+
+@pytest.mark.gpu
+def test_device_morris_thorne(ensemble):
+    m = gb.MorrisThorneWormhole()
+    x = [0.0, 100.0, math.radians(85), 0.0]
+    kw = dict(image_width=20, image_height=20, alpha_lims=(-9.5, 9.5), beta_lims=(-9.5, 9.5), ensemble=ensemble)
+    for d, literal in [(None, MT_SHADOW), (gb.ThinDisc(0.0, 40.0), MT_THIN)]:
+        args = (m, x, 200.0) if d is None else (m, x, d, 200.0)
+        _, _, img = gb.rendergeodesics(*args, **kw)
+        p, ic = _smoke_fixture(m, d).to_c()
+        want = oracle.render(p, ic, [cabi.PF_SHADOW])[0]
+        assert np.nansum(img) == pytest.approx(literal, rel=1e-5)
+        assert np.array_equal(np.isnan(img.T.reshape(-1)), np.isnan(want))
+    # a wider view under the main protocol: same class everywhere (no grazing geometry here), disc hits to 1e-6
+    d = gb.ThinDisc(2.0, 30.0)
+    cfg = render_config(gb.MorrisThorneWormhole(b=2.0), x, d, 400.0, 96, 96, (-30, 30), (-12, 12), ensemble=ensemble)
+    p, ic = cfg.to_c()
+    ref = oracle.trace(p, ic)
+    band = oracle.band_ratio(p, ic)
+    graze = (band > 0) & (band < 1.3)
+    got = api.solve_tracing_problem(cfg)
+    ok = ~graze
+    assert graze.mean() < 0.01 and np.array_equal(np.asarray(got.status)[ok], ref.status[ok])
+    hit = ok & (ref.status == cabi.STATUS_INTERSECTED)
+    assert hit.sum() > 500
+    assert np.max(np.abs(got.x[1:3, hit] - ref.x[1:3, hit])) < 1e-6
+    through = ok & (ref.status == cabi.STATUS_WITHIN_INNER_BOUNDARY)
+    assert through.sum() > 20 and np.all(got.x[1, through] <= 0)
 
 
 # --------------------------------------------------------------------------- device
@@ -225,7 +288,7 @@ def test_device_thick_disc_table(ensemble):
     d = gb.ThickDisc(_torus, (9.0, 11.0))
     oracle.set_cross_section(d.rho, d.height)
     x = [0.0, 100.0, math.radians(85), 0.0]
-    for m, literal in TORUS:
+    for m, literal in TORUS + [(gb.MorrisThorneWormhole(), MT_TORUS)]:
         _, _, img = gb.rendergeodesics(m, x, d, 200.0, image_width=20, image_height=20, alpha_lims=(-9.5, 9.5), beta_lims=(-9.5, 9.5), ensemble=ensemble)
         p, ic = _smoke_fixture(m, gb.ThinDisc(0.0, 40.0)).to_c()
         p.geometry_kind = ORACLE_GEOMETRY_TEST_THICK_DISC
