@@ -220,7 +220,7 @@ static void fill_params(const gb200_problem* p, const gb200_ic* ic, const gb200_
     memset(&P, 0, sizeof P);
     P.metric_kind = p->metric_kind;
     P.M = p->metric_params[0]; P.a = p->metric_params[1]; P.eps3 = p->metric_params[2];
-    P.a2 = P.a * P.a; P.twoM = 2.0 * P.M;
+    P.a2 = P.a * P.a; P.twoM = 2.0 * P.M; P.jp_e = P.eps3 * P.M * P.M * P.M;
     for (int k = 0; k < 8; ++k) P.mp[k] = p->metric_params[k];
     P.lam0 = p->lambda_min; P.lam1 = p->lambda_max; P.abstol = p->abstol; P.reltol = p->reltol;
     P.dtmax = p->dtmax > 0 ? p->dtmax : (p->lambda_max - p->lambda_min);
@@ -1519,7 +1519,7 @@ int gb200_debug_rhs(gb200_ctx* ctx, int32_t metric_kind, const double* mp, int64
     GbParams P;
     memset(&P, 0, sizeof P);
     P.metric_kind = metric_kind; P.M = mp[0]; P.a = mp[1]; P.eps3 = mp[2];
-    P.a2 = P.a * P.a; P.twoM = 2.0 * P.M;
+    P.a2 = P.a * P.a; P.twoM = 2.0 * P.M; P.jp_e = P.eps3 * P.M * P.M * P.M;
     for (int k = 0; k < 8; ++k) P.mp[k] = mp[k];
     void *d_u, *d_du;
     int rc = pool_get(ctx, SL_X0, sizeof(double) * 8 * (size_t)n, &d_u); if (rc) return rc;

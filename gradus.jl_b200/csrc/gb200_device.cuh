@@ -98,6 +98,7 @@ struct GbParams {
     int32_t metric_kind;
     double M, a, eps3;
     double a2, twoM; // a^2 and 2M: read from the constant bank at every RHS evaluation instead of recomputed
+    double jp_e;     // Johannsen-Psaltis: eps3 M^3
     double mp[8]; // all metric parameters in the order of include/gradus_b200.h (M = mp[0], a = mp[1])
     // integrator
     double lam0, lam1, abstol, reltol, dtmax, mu;
@@ -768,6 +769,68 @@ GB_HD inline void kerr_newman_lorentz(const double* mp, double r, double s, doub
 // The right-hand side, inlined at each of the six stages.  (Measured alternatives, profiles/r01_tuning_log.md: one
 // out-of-line copy removes instruction-fetch stalls but pays ~25% more instructions in call marshalling; with the
 // CTA-synchronous stepping of gb200_trace.cu the inlined form is the faster one.)
+#ifndef GB_OPT_JP_LAG
+#define GB_OPT_JP_LAG 1 /* Johannsen-Psaltis accelerations from the Euler-Lagrange form (below) instead of the generated Jacobian + contraction */
+#endif
+// Johannsen-Psaltis accelerations in closed form.  With h = eps3 M^3 r / Sigma^2, k = 1 + h, w = 2 M r / Sigma, Z = k w,
+// A = tdot - a s^2 phdot, B = tdot + a s^2 phdot the Lagrangian of johannsen-psaltis-ad.jl:4-26 is
+//   2L = -tdot^2 + (r^2 + a^2) s^2 phdot^2 + Z A^2 - h A B + G rdot^2 + Sigma thdot^2,   G = Sigma k / Dh,  Dh = Delta + h a^2 s^2,
+// and g_tt g_phph - g_tph^2 = -k s^2 Dh, so g^tt = -Phi / (k Dh), g^tph = -a w / Dh, g^phph = (1 - w) / (s^2 Dh) with
+// Phi = r^2 + a^2 + a^2 s^2 (h + Z).  tddot, phddot: the 2 x 2 solve of d/dlambda (g_t. v) = d/dlambda (g_ph. v) = 0 with the
+// total derivatives hdot, Zdot; rddot, thddot: the Euler-Lagrange equations with d ln G.  Two reciprocals (1 / Sigma, which
+// h needs, and 1 / (k Dh s^2)) instead of five, 114 FP64 instructions instead of 156 with the generated Jacobian
+// (tools/sass_count.py), equal to the oracle's dual-number right-hand side to 2e-13 (tests/test_gpu_parity.py).
+GB_D void jp_rhs_accel_sq(double M, double a, double a2, double twoM, double e, double r, double s2, double c2, double sin2,
+                          double vt, double vr, double vth, double vph, double acc[4]) {
+    const double r2 = r * r;
+    const double Sig = fma(a2, c2, r2);
+    const double Del = fma(r, r - twoM, a2);
+    const double rho2 = r2 + a2;
+    const double a2s2 = a2 * s2;
+    const double iSig = gb_rcp(Sig);
+    const double iSig2 = iSig * iSig;
+    const double q = r2 * iSig;
+    const double mS = twoM * iSig, w = mS * r, w_r = mS * fma(-2.0, q, 1.0);
+    const double eS = e * iSig2, h = eS * r, h_r = eS * fma(-4.0, q, 1.0);
+    const double k = 1.0 + h, Z = k * w;
+    const double Delh = fma(h, a2s2, Del);
+    const double kD = k * Delh;
+    const double R2 = gb_rcp(kD * s2);
+    const double R2s = R2 * s2, ik = R2s * Delh, iDelh = R2s * k, is2 = R2 * kD;
+    const double a2sin2 = a2 * sin2, T = a2sin2 * iSig, hT = h * T, w_t = w * T;
+    const double Z_r = fma(h_r, w, k * w_r), Z_t = w_t * fma(3.0, h, 1.0);
+    const double x = (a * s2) * vph, A = vt - x, AB = fma(vt, vt, -(x * x)), AA = A * A;
+    const double hTv = hT * vth;
+    const double hdot = fma(h_r, vr, hTv + hTv), Zdot = fma(Z_r, vr, Z_t * vth);
+    const double m = (sin2 * is2) * vth, s2dot = sin2 * vth;
+    const double zv = Z * vph;
+    const double Pt = fma(Zdot, A, fma(-hdot, vt, -((a * s2dot) * zv)));
+    const double rr = r * vr;
+    const double Phi2 = fma(a2s2, fma(2.0, h, Z), rho2);
+    const double inner2 = fma(a2s2, hdot, rr + rr);
+    const double Pps = fma(vph, fma(m, Phi2, inner2), -((a * fma(m, Z, Zdot)) * A)); // (d/dlambda g_ph.) v / s^2
+    const double Phi = fma(a2s2, h + Z, rho2);
+    const double aw = a * w;
+    acc[0] = iDelh * fma(Phi * ik, Pt, aw * (s2 * Pps));
+    acc[3] = iDelh * fma(aw, Pt, -((1.0 - w) * Pps));
+    const double pp = vph * vph, tt = vth * vth, rr2 = vr * vr, X = vr * vth;
+    const double tr = r + r;
+    {
+        const double dQr = fma(Z_r, AA, fma(-h_r, AB, tr * (s2 * pp)));
+        const double lnGr = fma(-fma(h_r, a2s2, tr - twoM), iDelh, fma(h_r, ik, tr * iSig));
+        const double hi2 = 2.0 * (h * iSig);
+        const double lnGt = a2sin2 * fma(-fma(hi2, a2s2, h), iDelh, fma(hi2, ik, -iSig));
+        const double iG = (iSig * ik) * Delh;
+        acc[1] = fma(-lnGt, X, fma(-(0.5 * lnGr), rr2, iG * fma(r, tt, 0.5 * dQr)));
+        const double G = (Sig * k) * iDelh;
+        double dQt = (sin2 * pp) * fma(2.0 * h, a2s2, rho2);
+        dQt = fma(Z_t, AA, dQt);
+        dQt = fma(-2.0 * ((a * sin2) * zv), A, dQt);
+        dQt = fma(-2.0 * hT, AB, dQt);
+        acc[2] = (0.5 * iSig) * fma(-4.0 * rr, vth, fma(a2sin2, tt, fma(G * lnGt, rr2, dQt)));
+    }
+}
+
 struct GbAcc { double a0, a1, a2, a3, s, c; };
 #ifdef GB_RHS_CALL /* tuning variant: one out-of-line copy (smaller code, but ~25% more instructions for call marshalling) */
 #define GB_RHS_ATTR __device__ __noinline__
@@ -788,6 +851,18 @@ GB_RHS_ATTR GbAcc rhs_eval(const GbParams& P, double r, double th, double vt, do
         o.s = gb_flip_sign(sa, q.n << 30);
         o.c = gb_flip_sign(ca, (q.n + 1) << 30);
         kerr_rhs_accel_sq(P.M, P.a, P.a2, P.twoM, r, sa * sa, ca * ca, gb_flip_sign(2.0 * sa * ca, q.n << 31), vt, vr, vth, vph, acc);
+        o.a0 = acc[0]; o.a1 = acc[1]; o.a2 = acc[2]; o.a3 = acc[3];
+        return o;
+    }
+#endif
+#if GB_OPT_JP_LAG
+    if (METRIC == GB200_METRIC_JOHANNSEN_PSALTIS) {
+        const GbSinCos q = gb_sincos_reduced(th);
+        const bool swap = (q.n & 1) != 0;
+        const double sa = swap ? q.cs : q.sn, ca = swap ? q.sn : q.cs;
+        o.s = gb_flip_sign(sa, q.n << 30);
+        o.c = gb_flip_sign(ca, (q.n + 1) << 30);
+        jp_rhs_accel_sq(P.M, P.a, P.a2, P.twoM, P.jp_e, r, sa * sa, ca * ca, gb_flip_sign(2.0 * sa * ca, q.n << 31), vt, vr, vth, vph, acc);
         o.a0 = acc[0]; o.a1 = acc[1]; o.a2 = acc[2]; o.a3 = acc[3];
         return o;
     }
