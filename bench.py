@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 H_IMG = 2048
 W_IMG_PER_GPU = 2048
-F_RHS = {0: 118.0, 1: 222.0}  # algorithmic flops per RHS evaluation (Kerr: SURVEY 8d; JP: 151 (sympy CSE) + 71 contraction)
+F_RHS = {0: 118.0, 1: 163.0}  # algorithmic flops per RHS evaluation (Kerr: SURVEY 8d; JP: the Euler-Lagrange closed form, FMA = 2; round 1 counted 222 for the generated Jacobian + contraction)
 F_STAGE, F_EVENT, F_IC, F_END = 566.0, 280.0, 60.0, 150.0
 
 

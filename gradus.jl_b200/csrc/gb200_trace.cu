@@ -101,27 +101,6 @@ GB_D double comb(double u, double dt, double k0, const GbK& k) {
     if (S == 5) return fma(dt, fma(GB_A65, k.get(4), fma(GB_A64, k.get(3), fma(GB_A63, k.get(2), fma(GB_A62, k.get(1), GB_A61 * k0)))), u);
     return fma(dt, fma(GB_A76, k.get(5), fma(GB_A75, k.get(4), fma(GB_A74, k.get(3), fma(GB_A73, k.get(2), fma(GB_A72, k.get(1), GB_A71 * k0))))), u);
 }
-// K form (GB_OPT_KFORM): the stored stage values are K_j = dt k_j, so a stage input is u + sum_l a_{S+1,l+1} K_l -- S FMAs
-// with a constant-bank coefficient each.  The k form above ends in fma(dt, sum, u), whose three operands are all
-// registers: that instruction takes 2.88 instead of 2 cycles on the FP64 pipe (register-bank conflict, DESIGN K1) and
-// there are 36 of them per step attempt; the K form pays 36 two-register DMULs (dt k_j) for them and needs one
-// instruction fewer per stage input.
-#ifndef GB_OPT_KFORM
-#define GB_OPT_KFORM 0
-#endif
-#if GB_OPT_KFORM && !(GB_OPT_SMEMK && GB_OPT_PROGERR && GB_OPT_INTMAX)
-#error "GB_OPT_KFORM is written for the shared-memory stage storage with progressive error sums"
-#endif
-template <int S>
-GB_D double combK(double u, double K0, const GbK& k) {
-    double x = fma(S == 1 ? GB_A21 : S == 2 ? GB_A31 : S == 3 ? GB_A41 : S == 4 ? GB_A51 : S == 5 ? GB_A61 : GB_A71, K0, u);
-    if (S >= 2) x = fma(S == 2 ? GB_A32 : S == 3 ? GB_A42 : S == 4 ? GB_A52 : S == 5 ? GB_A62 : GB_A72, k.get(1), x);
-    if (S >= 3) x = fma(S == 3 ? GB_A43 : S == 4 ? GB_A53 : S == 5 ? GB_A63 : GB_A73, k.get(2), x);
-    if (S >= 4) x = fma(S == 4 ? GB_A54 : S == 5 ? GB_A64 : GB_A74, k.get(3), x);
-    if (S >= 5) x = fma(S == 5 ? GB_A65 : GB_A75, k.get(4), x);
-    if (S >= 6) x = fma(GB_A76, k.get(5), x);
-    return x;
-}
 // sum_j btilde_j k_j with k_1 = k0, k_7 = k6
 GB_D double errcomb(double k0, const GbK& k, double k6) {
     return fma(GB_BT7, k6, fma(GB_BT6, k.get(5), fma(GB_BT5, k.get(4), fma(GB_BT4, k.get(3), fma(GB_BT3, k.get(2), fma(GB_BT2, k.get(1), GB_BT1 * k0))))));
@@ -140,11 +119,7 @@ GB_D void dense_coeffs(double k0, const GbK& k, double k6, double& C2, double& C
     C4 = fma(GB_R74, k6, fma(GB_R64, k6_, fma(GB_R54, k5, fma(GB_R44, k4, fma(GB_R34, k3, fma(GB_R24, k2, GB_R14 * k0))))));
 }
 GB_D double dense_eval(double u0, double dt, double Th, double C1, double C2, double C3, double C4) {
-#if GB_OPT_KFORM
-    return fma(Th, fma(Th, fma(Th, fma(Th, C4, C3), C2), C1), u0); // C1..C4 carry the factor dt (from K_j = dt k_j)
-#else
     return fma(dt * Th, fma(Th, fma(Th, fma(Th, C4, C3), C2), C1), u0);
-#endif
 }
 GB_D double sgn(double x) { return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : 0.0); }
 
@@ -183,8 +158,10 @@ GB_D bool gb_le_one_pos(double a) { return a <= 1.0; }
 //   2  Float32 on the otherwise idle FP32 / integer / special-function pipes: max(|a|, |b|) from the high words (20
 //      mantissa bits), one FFMA, one rcp.approx.f32, widened back through the exponent field -- no FP64 instruction at all
 //   3  as 2 with conversion instructions instead of the integer exponent arithmetic
+// Measured on C2 (profiles/r02_tuning_log.md): 40.48 / 39.93 / 39.79 / 39.98 ms for 0 / 1 / 2 / 3.  1 is the default: 2 moves
+// 36 of 1.94 M disc hits across the grazing band (its truncated |u| biases every scale by up to 1e-6), 1 moves one.
 #ifndef GB_OPT_NORMRCP
-#define GB_OPT_NORMRCP 0
+#define GB_OPT_NORMRCP 1
 #endif
 GB_D double gb_inv_scale(double a, double b, double reltol, double abstol, float reltolf, float abstolf) {
 #if GB_OPT_NORMRCP == 0
@@ -362,26 +339,19 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
 #endif
                     // ContinuousCallback root find on the dense output (DiffEqBase find_callback_time, LeftRootFind)
                     double C2r, C3r, C4r, C2t, C3t, C4t;
-#if GB_OPT_KFORM
-                    const double dvr = dt * vr, dvth = dt * vth; // first dense-output coefficients in K form
-                    dense_coeffs(dvr, kR, dt * nvr, C2r, C3r, C4r);
-                    dense_coeffs(dvth, kT, dt * nvth, C2t, C3t, C4t);
-#else
-                    const double dvr = vr, dvth = vth;
                     dense_coeffs(vr, kR, nvr, C2r, C3r, C4r);
                     dense_coeffs(vth, kT, nvth, C2t, C3t, C4t);
-#endif
                     const double sprev = sgn(cprev);
                     double lo = ev_lo, hi = ev_hi;
                     double flo, fhi;
                     {
                         double s_, c_;
                         if (lo > 0.0) {
-                            gb_sincos(dense_eval(th, dt, lo, dvth, C2t, C3t, C4t), &s_, &c_);
-                            flo = disc_condition<GEOM>(P, dense_eval(r, dt, lo, dvr, C2r, C3r, C4r), s_, c_, hgt);
+                            gb_sincos(dense_eval(th, dt, lo, vth, C2t, C3t, C4t), &s_, &c_);
+                            flo = disc_condition<GEOM>(P, dense_eval(r, dt, lo, vr, C2r, C3r, C4r), s_, c_, hgt);
                         } else flo = cprev;
-                        gb_sincos(dense_eval(th, dt, hi, dvth, C2t, C3t, C4t), &s_, &c_);
-                        fhi = disc_condition<GEOM>(P, dense_eval(r, dt, hi, dvr, C2r, C3r, C4r), s_, c_, hgt);
+                        gb_sincos(dense_eval(th, dt, hi, vth, C2t, C3t, C4t), &s_, &c_);
+                        fhi = disc_condition<GEOM>(P, dense_eval(r, dt, hi, vr, C2r, C3r, C4r), s_, c_, hgt);
                     }
                     if (fhi == 0.0) lo = hi;
                     else {
@@ -395,8 +365,8 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                             if (!(mid > lo && mid < hi)) mid = 0.5 * (lo + hi);
                             if (!(mid > lo && mid < hi)) break;
                             double s_, c_;
-                            gb_sincos(dense_eval(th, dt, mid, dvth, C2t, C3t, C4t), &s_, &c_);
-                            const double fm = disc_condition<GEOM>(P, dense_eval(r, dt, mid, dvr, C2r, C3r, C4r), s_, c_, hgt);
+                            gb_sincos(dense_eval(th, dt, mid, vth, C2t, C3t, C4t), &s_, &c_);
+                            const double fm = disc_condition<GEOM>(P, dense_eval(r, dt, mid, vr, C2r, C3r, C4r), s_, c_, hgt);
                             if (fm != 0.0 && (fm > 0.0) == (sprev > 0.0)) {
                                 lo = mid; flo = fm;
                                 if (side == -1) fhi *= 0.5;
@@ -422,28 +392,6 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                     // stage v^t, v^phi are recomputed from the stored accelerations (bitwise the same values)
                     double W0[7], W3[7], WR[7], WT[7];
                     double st = 0, sr = 0, sth = 0, sph = 0, s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-#if GB_OPT_KFORM
-                    // rows 1..5 of the stage storage hold dt k_j; the register-resident k_1, k_7 are scaled here
-                    const double K00 = dt * kA0.get(0), K30 = dt * kA3.get(0);
-                    W0[0] = vt; W3[0] = vph; WR[0] = dvr; WT[0] = dvth;
-                    W0[1] = combK<1>(vt, K00, kA0); W3[1] = combK<1>(vph, K30, kA3);
-                    W0[2] = combK<2>(vt, K00, kA0); W3[2] = combK<2>(vph, K30, kA3);
-                    W0[3] = combK<3>(vt, K00, kA0); W3[3] = combK<3>(vph, K30, kA3);
-                    W0[4] = combK<4>(vt, K00, kA0); W3[4] = combK<4>(vph, K30, kA3);
-                    W0[5] = combK<5>(vt, K00, kA0); W3[5] = combK<5>(vph, K30, kA3);
-                    W0[6] = nvt; W3[6] = nvph; WR[6] = dt * nvr; WT[6] = dt * nvth;
-#pragma unroll
-                    for (int j = 1; j < 6; ++j) { WR[j] = kR.get(j); WT[j] = kT.get(j); }
-#pragma unroll
-                    for (int j = 0; j < 7; ++j) {
-                        const bool reg = (j == 0 || j == 6);
-                        st = fma(b[j], W0[j], st); sr = fma(b[j], WR[j], sr); sth = fma(b[j], WT[j], sth); sph = fma(b[j], W3[j], sph);
-                        s0 = fma(b[j], reg ? dt * kA0.get(j) : kA0.get(j), s0); s1 = fma(b[j], reg ? dt * kA1.get(j) : kA1.get(j), s1);
-                        s2 = fma(b[j], reg ? dt * kA2.get(j) : kA2.get(j), s2); s3 = fma(b[j], reg ? dt * kA3.get(j) : kA3.get(j), s3);
-                    }
-                    nct = fma(dt, st, ct); nr = r + sr; nth = th + sth; nph = fma(dt, sph, ph);
-                    nvt = vt + s0; nvr = vr + s1; nvth = vth + s2; nvph = vph + s3;
-#else
                     W0[0] = vt; W3[0] = vph; WR[0] = vr; WT[0] = vth;
                     W0[1] = comb<1>(vt, dt, kA0.get(0), kA0); W3[1] = comb<1>(vph, dt, kA3.get(0), kA3);
                     W0[2] = comb<2>(vt, dt, kA0.get(0), kA0); W3[2] = comb<2>(vph, dt, kA3.get(0), kA3);
@@ -460,7 +408,6 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                     }
                     nct = fma(dt, st, ct); nr = fma(dt, sr, r); nth = fma(dt, sth, th); nph = fma(dt, sph, ph);
                     nvt = fma(dt, s0, vt); nvr = fma(dt, s1, vr); nvth = fma(dt, s2, vth); nvph = fma(dt, s3, vph);
-#endif
                     tfinal = fma(Th, dt, tfinal); // tfinal held lambda_prev for event lanes
                     status = GB200_STATUS_INTERSECTED_WITH_GEOMETRY;
                     // DiscreteCallbacks still run on the event state (handle_callbacks!): user, then chart
@@ -638,24 +585,6 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
 #else
 #define GB_STAGE_MAX
 #endif
-#if GB_OPT_KFORM
-            const double KR0 = dt * vr, KT0 = dt * vth;
-            const double KA00 = dt * kA0.get(0), KA10 = dt * kA1.get(0), KA20 = dt * kA2.get(0), KA30 = dt * kA3.get(0);
-#define GB_STAGE(S)                                                                                                     \
-    {                                                                                                                   \
-        const double xr = combK<S>(r, KR0, kR), xt = combK<S>(th, KT0, kT);                                             \
-        const double w0 = combK<S>(vt, KA00, kA0), w1 = combK<S>(vr, KA10, kA1),                                        \
-                     w2 = combK<S>(vth, KA20, kA2), w3 = combK<S>(vph, KA30, kA3);                                      \
-        kR.set(S, dt * w1); kT.set(S, dt * w2);                                                                         \
-        GB_STAGE_MAX                                                                                                    \
-        tsum = fma(a7coef<S>(), w0, tsum); psum = fma(a7coef<S>(), w3, psum);                                           \
-        terr = fma(btcoef<S>(), w0, terr); perr = fma(btcoef<S>(), w3, perr);                                           \
-        GB_STAGE_ERR_V(S)                                                                                               \
-        rhs_accel<METRIC>(P, xr, xt, w0, w1, w2, w3, acc, s_, c_);                                                      \
-        kA0.set(S, dt * acc[0]); kA1.set(S, dt * acc[1]); kA2.set(S, dt * acc[2]); kA3.set(S, dt * acc[3]);             \
-        GB_STAGE_ERR_A(S)                                                                                               \
-    }
-#else
 #define GB_STAGE(S)                                                                                                     \
     {                                                                                                                   \
         const double xr = comb<S>(r, dt, vr, kR), xt = comb<S>(th, dt, vth, kT);                                        \
@@ -670,19 +599,12 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
         kA0.set(S, acc[0]); kA1.set(S, acc[1]); kA2.set(S, acc[2]); kA3.set(S, acc[3]);                                 \
         GB_STAGE_ERR_A(S)                                                                                               \
     }
-#endif
             GB_STAGE(1) GB_STAGE(2) GB_STAGE(3) GB_STAGE(4) GB_STAGE(5)
 #undef GB_STAGE
             // 7th stage = the proposed state (FSAL)
-#if GB_OPT_KFORM
-            nr = combK<6>(r, KR0, kR); nth = combK<6>(th, KT0, kT);
-            nvt = combK<6>(vt, KA00, kA0); nvr = combK<6>(vr, KA10, kA1);
-            nvth = combK<6>(vth, KA20, kA2); nvph = combK<6>(vph, KA30, kA3);
-#else
             nr = comb<6>(r, dt, vr, kR); nth = comb<6>(th, dt, vth, kT);
             nvt = comb<6>(vt, dt, kA0.get(0), kA0); nvr = comb<6>(vr, dt, kA1.get(0), kA1);
             nvth = comb<6>(vth, dt, kA2.get(0), kA2); nvph = comb<6>(vph, dt, kA3.get(0), kA3);
-#endif
             nct = fma(dt, tsum, ct); nph = fma(dt, psum, ph);
             terr = fma(GB_BT7, nvt, terr); perr = fma(GB_BT7, nvph, perr);
 #if GB_OPT_PROGERR
@@ -821,17 +743,6 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
 #endif
                         bool need = sprev < 0.0 || scan_needed<GEOM>(P, r, acos_prev, cprev, adt * 7.5823 * mth, adt * 7.5823 * mr);
                         double C2r = 0, C3r = 0, C4r = 0, C2t = 0, C3t = 0, C4t = 0;
-#if GB_OPT_KFORM
-                        const double C1t = KT0, C1r = KR0;
-                        if (need) {
-                            dense_coeffs(KT0, kT, dt * nvth, C2t, C3t, C4t);
-                            dense_coeffs(KR0, kR, dt * nvr, C2r, C3r, C4r);
-                            const double Bth = fabs(KT0) + fabs(C2t) + fabs(C3t) + fabs(C4t);
-                            const double Br = fabs(KR0) + fabs(C2r) + fabs(C3r) + fabs(C4r);
-                            need = sprev < 0.0 || scan_needed<GEOM>(P, r, acos_prev, cprev, Bth, Br);
-                        }
-#else
-                        const double C1t = vth, C1r = vr;
                         if (need) {
                             dense_coeffs(vth, kT, nvth, C2t, C3t, C4t);
                             dense_coeffs(vr, kR, nvr, C2r, C3r, C4r);
@@ -839,14 +750,13 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                             const double Br = adt * (fabs(vr) + fabs(C2r) + fabs(C3r) + fabs(C4r));
                             need = sprev < 0.0 || scan_needed<GEOM>(P, r, acos_prev, cprev, Bth, Br);
                         }
-#endif
                         if (need) {
 #pragma unroll 1
                             for (int i = 1; i <= 6; ++i) { // interp_points = 8: Theta = 1/7 .. 6/7 (7/7 is u itself)
                                 const double Th = (double)i / 7.0;
                                 double si, ci;
-                                gb_sincos(dense_eval(th, dt, Th, C1t, C2t, C3t, C4t), &si, &ci);
-                                const double cn = disc_condition<GEOM>(P, dense_eval(r, dt, Th, C1r, C2r, C3r, C4r), si, ci, hgt);
+                                gb_sincos(dense_eval(th, dt, Th, vth, C2t, C3t, C4t), &si, &ci);
+                                const double cn = disc_condition<GEOM>(P, dense_eval(r, dt, Th, vr, C2r, C3r, C4r), si, ci, hgt);
                                 if (sprev * cn < 0.0) { event = true; ev_lo = (double)(i - 1) / 7.0; ev_hi = Th; break; }
                             }
                         }

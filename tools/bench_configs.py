@@ -14,7 +14,7 @@ RED = [cpf.redshift() @ cpf.filter_intersected(), cpf.radius() @ cpf.filter_inte
 
 
 def fpa(metric_kind, disc):
-    return 6 * (118 if metric_kind == 0 else 222) + 566 + (280 if disc else 0)
+    return 6 * (118 if metric_kind == 0 else 163) + 566 + (280 if disc else 0)
 
 
 def report(name, n, st, metric_kind, disc, peak):
