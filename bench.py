@@ -289,14 +289,14 @@ def run_ours(args, rank, world, local):
     nominal_fp64 = 148 * 64 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
     traffic = None
     try:  # dram bytes per launch of the same kernel from the committed `ncu --set full` capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     except Exception:
         pass
     roofline = {
         "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None,
         "traffic": traffic,
-        "traffic_note": "bytes per launch (dram read + write) from profiles/r01_traffic.json; algorithmic bytes per launch = 16 B x rays",
+        "traffic_note": "bytes per launch (dram read + write) from profiles/r02_traffic.json; algorithmic bytes per launch = 16 B x rays",
         "peak_source": "measured in this run: dependent-free DFMA micro-benchmark (gb200_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
         "peak_nominal": nominal_fp64,
         "peak_three_register_dfma": peak3.value,
