@@ -582,11 +582,19 @@ int gb200_radiative_efficiency(int32_t metric_kind, const double* mp, double* ou
     return GB200_OK;
 }
 
-int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, gb200_endpoints* out) {
+// gb200_trace and gb200_trace_target: `target` (r, theta, phi) non-null selects the closest-approach objective (the generic
+// integrator with the distance condition in place of a geometry); `closest` then receives one distance per ray.
+static int trace_common(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, gb200_endpoints* out,
+                        const double* target, double d_tol, double* closest) {
     if (!ctx) return fail(nullptr, GB200_ERR_INVALID_ARGUMENT, "null context");
     int rc = validate(ctx, p, ic); if (rc) return rc;
     rc = validate_range(ctx, ic, rg); if (rc) return rc;
-    if (!out) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null endpoints");
+    static const gb200_endpoints no_endpoints{};
+    if (target) {
+        if (p->geometry_kind != GB200_GEOMETRY_NONE) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "gb200_trace_target: the distance callback takes the geometry's place (geometry_kind must be NONE)");
+        if (!(d_tol > 0) || !closest) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "gb200_trace_target needs d_tol > 0 and a closest[] array");
+        if (!out) out = const_cast<gb200_endpoints*>(&no_endpoints);
+    } else if (!out) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null endpoints");
     { int rc_ = begin_call(ctx, ctx->stream); if (rc_) return rc_; }
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     GbParams P;
@@ -595,6 +603,15 @@ int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, cons
     rc = upload_ic_and_tables(ctx, ic, nullptr, nullptr, P); if (rc) return rc;
     const size_t n = (size_t)rg->count;
     void* d;
+    if (target) { // to_cartesian(target), src/geometry/geometry.jl:13-16
+        P.geometry_kind = GB200_GEOMETRY_TARGET_POINT;
+        P.gp0 = target[0] * std::sin(target[1]) * std::cos(target[2]);
+        P.gp1 = target[0] * std::sin(target[1]) * std::sin(target[2]);
+        P.gp2 = target[0] * std::cos(target[1]);
+        P.gtol = d_tol;
+        rc = pool_get(ctx, SL_G, n * sizeof(double) + 8, &d); if (rc) return rc;
+        P.o_closest = (double*)d;
+    }
 #define WANT(ptr, slot, type, field)                                               \
     if (ptr) { rc = pool_get(ctx, slot, n * sizeof(type) + 8, &d); if (rc) return rc; field = (type*)d; }
     WANT(out->status, SL_STATUS, int32_t, P.o_status)
@@ -609,7 +626,7 @@ int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, cons
     WANT(out->nreject, SL_NREJ, int32_t, P.o_nreject)
     WANT(out->flags, SL_FLAGS, int32_t, P.o_flags)
 #undef WANT
-    if (pipeline_eligible(P, rg)) {
+    if (!target && pipeline_eligible(P, rg)) {
         const GbParams Pf = P;
         return run_pipelined(ctx, rg, P,
             [&](GbParams& Pc, int64_t s0) {
@@ -644,7 +661,14 @@ int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, cons
                 return e;
             });
     }
-    rc = run_trace(ctx, P, ctx->stream, true); if (rc) return rc;
+    if (target) { // one ray per thread through the generic integrator; no ticket queue, no step counters
+        CU(ctx, cudaMemsetAsync(ctx->d_queue, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(ctx, gb200_launch_target(P, ctx->stream));
+        CU(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+        ctx->stats.launches += n ? 1 : 0;
+        if (n) CU(ctx, cudaMemcpyAsync(closest, P.o_closest, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    } else { rc = run_trace(ctx, P, ctx->stream, true); if (rc) return rc; }
 #define BACK(ptr, field, type) \
     if (ptr && n) CU(ctx, cudaMemcpyAsync(ptr, field, n * sizeof(type), cudaMemcpyDeviceToHost, ctx->stream));
     BACK(out->status, P.o_status, int32_t)
@@ -660,6 +684,16 @@ int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, cons
     BACK(out->flags, P.o_flags, int32_t)
 #undef BACK
     return finish_stats(ctx, rg->count);
+}
+
+int gb200_trace(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, gb200_endpoints* out) {
+    return trace_common(ctx, p, ic, rg, out, nullptr, 0.0, nullptr);
+}
+
+int gb200_trace_target(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, const double* target, double d_tol,
+                       gb200_endpoints* out, double* closest) {
+    if (!target) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null target");
+    return trace_common(ctx, p, ic, rg, out, target, d_tol, closest);
 }
 
 int gb200_trace_batch(gb200_ctx* ctx, int32_t nbatch, const gb200_problem* problems, const gb200_ic* ics,

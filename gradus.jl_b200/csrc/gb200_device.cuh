@@ -140,6 +140,7 @@ struct GbParams {
     int32_t* o_naccept;
     int32_t* o_nreject;
     int32_t* o_flags;
+    double* o_closest; // GB200_GEOMETRY_TARGET_POINT: closest approach to the target
     int32_t npf;
     int32_t pf[GB_MAX_PF];
     double* o_img[GB_MAX_PF];

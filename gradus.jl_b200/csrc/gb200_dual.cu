@@ -57,6 +57,38 @@ cudaError_t gb200_launch_dual(const GbParams& P, const GbDualIO& io, cudaStream_
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- closest approach to a target point
+// The objective of optimize_for_target (src/tracing/precision-solvers.jl:452-546) over a set of rays: one ray per thread
+// through the generic integrator with the distance condition (disc_condition_g, GB200_GEOMETRY_TARGET_POINT).
+__global__ void __launch_bounds__(64) gb200_target_kernel(const __grid_constant__ GbParams P) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.count) return;
+    GbRayInit ri;
+    ray_initial_state(P, ray_index_of_slot(P, s), ri);
+    GD<0> u[8];
+    for (int k = 0; k < 4; ++k) { u[k] = GD<0>(ri.x[k]); u[4 + k] = GD<0>(ri.v[k]); }
+    GenResult<0> res;
+    gen_trace_ray<0>(P, u, 0.0, false, res, GbNoRecord());
+    if (P.o_status) P.o_status[s] = res.status;
+    if (P.o_lambda) P.o_lambda[s] = res.lambda;
+    for (int k = 0; k < 4; ++k) {
+        if (P.o_x[k]) P.o_x[k][s] = res.u[k].v;
+        if (P.o_v[k]) P.o_v[k][s] = res.u[4 + k].v;
+        if (P.o_x0[k]) P.o_x0[k][s] = ri.x[k];
+        if (P.o_v0[k]) P.o_v0[k][s] = ri.v[k];
+    }
+    if (P.o_naccept) P.o_naccept[s] = res.naccept;
+    if (P.o_nreject) P.o_nreject[s] = res.nreject;
+    if (P.o_flags) P.o_flags[s] = res.flags;
+    if (P.o_closest) P.o_closest[s] = res.closest;
+}
+
+cudaError_t gb200_launch_target(const GbParams& P, cudaStream_t stream) {
+    if (P.count <= 0) return cudaSuccess;
+    gb200_target_kernel<<<(unsigned)((P.count + 63) / 64), 64, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- single-ray path recorder
 struct GbPathRecord {
     int cap;

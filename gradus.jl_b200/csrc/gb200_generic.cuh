@@ -193,7 +193,17 @@ GB_HD inline S cross_section_table_g(const double* xs, const double* ys, int n, 
 }
 // distance_to_disc over S, geometry chosen at run time (src/geometry/discs/*.jl, see disc_condition<GEOM>)
 template <class S>
-GB_HD inline S disc_condition_g(const GbParams& P, const S& r, const S& s, const S& c, double hgt) {
+GB_HD inline S disc_condition_g(const GbParams& P, const S& r, const S& s, const S& c, double hgt, double ph = 0.0) {
+    if (P.geometry_kind == GB200_GEOMETRY_TARGET_POINT) {
+        // distance_callback of _make_target_objective (src/tracing/precision-solvers.jl:473-488): Euclidean distance between
+        // to_cartesian(u) (src/geometry/geometry.jl:13-16) and the target, minus d_tol; gp0..gp2 = target in Cartesian
+        // coordinates, gtol = d_tol.  phi enters as a value (no partials: this kind runs with N = 0 only).
+        double sp, cp;
+        sincos(ph, &sp, &cp);
+        const S rs = r * s;
+        const S dx = rs * cp - P.gp0, dy = rs * sp - P.gp1, dz = r * c - P.gp2;
+        return gd_sqrt(dx * dx + dy * dy + dz * dz) - P.gtol;
+    }
     if (P.geometry_kind == GB200_GEOMETRY_THIN_DISC) {
         const S rho = r * gd_abs(s);
         if (rho < P.gp0 || rho > P.gp1) return S(1.0);
@@ -294,6 +304,7 @@ struct GenResult {
     double lambda;
     GD<N> u[8];     // end state
     GD<N> E_obs;    // g_{mu nu}(x_init) v_init^mu (1,0,0,0)^nu
+    double closest; // GB200_GEOMETRY_TARGET_POINT: the smallest distance to the target over every evaluation of the condition
 };
 
 GB_HD inline void gen_dense_weights(double Th, double b[7], double db[7]) { // b_j(Theta) and d b_j / d Theta of the Tsit5 interpolant
@@ -343,7 +354,9 @@ GB_HD inline void gen_trace_ray(const GbParams& P, const GD<N> u_init[8], double
     rec(t, u);
     S s_, c_;
     rhs_g<N>(P, u, k[0], s_, c_);
-    double cprev = has_geom ? disc_condition_g<S>(P, u[1], s_, c_, hgt).v : 1.0;
+    const bool target = P.geometry_kind == GB200_GEOMETRY_TARGET_POINT;
+    double cprev = has_geom ? disc_condition_g<S>(P, u[1], s_, c_, hgt, u[3].v).v : 1.0;
+    res.closest = target ? cprev + P.gtol : nan("");
     double dt;
     { // ode_determine_initdt
         double sk[8];
@@ -411,7 +424,8 @@ GB_HD inline void gen_trace_ray(const GbParams& P, const GD<N> u_init[8], double
         bool event = false;
         double cnext = 1.0;
         if (has_geom) {
-            cnext = disc_condition_g<S>(P, un[1], s_, c_, hgt).v;
+            cnext = disc_condition_g<S>(P, un[1], s_, c_, hgt, un[3].v).v;
+            if (target) res.closest = fmin(res.closest, cnext + P.gtol);
             const double sprev = (cprev > 0.0) ? 1.0 : ((cprev < 0.0) ? -1.0 : 0.0);
             const double snext = (cnext > 0.0) ? 1.0 : ((cnext < 0.0) ? -1.0 : 0.0);
             double ev_lo = 0.0, ev_hi = 1.0;
@@ -419,12 +433,15 @@ GB_HD inline void gen_trace_ray(const GbParams& P, const GD<N> u_init[8], double
             auto cond_at = [&](double Th) -> double {
                 double b[7], db[7];
                 gen_dense_weights(Th, b, db);
-                double rr = 0.0, tt = 0.0;
+                double rr = 0.0, tt = 0.0, pp = 0.0;
                 for (int j = 0; j < 7; ++j) { rr += b[j] * k[j][1].v; tt += b[j] * k[j][2].v; }
-                rr = u[1].v + dt * rr; tt = u[2].v + dt * tt;
+                if (target) for (int j = 0; j < 7; ++j) pp += b[j] * k[j][3].v;
+                rr = u[1].v + dt * rr; tt = u[2].v + dt * tt; pp = u[3].v + dt * pp;
                 double sv, cv;
                 sincos(tt, &sv, &cv);
-                return disc_condition_g<double>(P, rr, sv, cv, hgt);
+                const double cv_ = disc_condition_g<double>(P, rr, sv, cv, hgt, pp);
+                if (target) res.closest = fmin(res.closest, cv_ + P.gtol); // closest_approach[] is updated by every evaluation
+                return cv_;
             };
             if (sprev != 0.0) {
                 if (sprev * snext <= 0.0) event = true;

@@ -28,3 +28,5 @@ struct GbDualIO {
     int32_t *naccept, *nreject, *flags;
 };
 cudaError_t gb200_launch_dual(const GbParams& P, const GbDualIO& io, cudaStream_t stream);
+// closest approach to a target point (optimize_for_target's objective): the generic integrator over the rays of P
+cudaError_t gb200_launch_target(const GbParams& P, cudaStream_t stream);

@@ -64,6 +64,9 @@ extern "C" {
                                             gb200_set_cross_section, -1 (no disc) outside its range; distance_to_disc = |r cos theta| - h,
                                             1 where h <= 0.  params: max of the table (filled in by the library) */
 
+#define GB200_GEOMETRY_TARGET_POINT 5    /* gb200_trace_target only: the distance ContinuousCallback of _make_target_objective,
+                                            src/tracing/precision-solvers.jl:473-488 */
+
 /* ---- user discrete callback: src/tracing/callbacks.jl:31-39 ------------ */
 #define GB200_CALLBACK_NONE 0
 #define GB200_CALLBACK_UPPER_HEMISPHERE 1 /* r cos(theta) < delta -> OutOfDomain */
@@ -250,6 +253,17 @@ int gb200_radiative_efficiency(int32_t metric_kind, const double* metric_params,
    rows the solve produced (may exceed cap), *status the final StatusCodes value.  One GPU thread; a set-up tool. */
 int gb200_trace_path(gb200_ctx* ctx, const gb200_problem* p, const double* u0, int32_t cap,
                      double* lambda, double* u, int32_t* nrows, int32_t* status);
+
+/* The objective of optimize_for_target / impact_parameters_for_target (src/tracing/precision-solvers.jl:452-546) for a whole
+   set of rays at once: every ray of `ic` / `rg` is traced with the reference's distance callback -- a ContinuousCallback on
+   |to_cartesian(u) - to_cartesian(target)| - d_tol with 8 interpolation points that terminates the ray
+   (IntersectedWithGeometry) where it first comes within d_tol -- and closest[i] receives the smallest distance seen by any
+   evaluation of that condition (closest_approach[], :466-481).  target = (r, theta, phi); p->geometry_kind must be
+   GB200_GEOMETRY_NONE (the callback takes the geometry's place), p->callback_kind and the chart apply as usual.  The
+   reference minimises this objective one ray at a time (Nelder-Mead); with a device under it the search is a grid of impact
+   parameters per call, refined around its minimum (the Python mirror's `optimize_for_target`).  `out` may be NULL. */
+int gb200_trace_target(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg,
+                       const double* target, double d_tol, gb200_endpoints* out, double* closest);
 
 /* Plunging-region four-velocity table for the redshift of non-Kerr metrics inside the ISCO
    (interpolate_plunging_velocities, src/orbits/orbit-solving.jl:99-167): a massive geodesic released at
