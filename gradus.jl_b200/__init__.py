@@ -55,6 +55,9 @@ from .api import (  # noqa: F401
     tracegeodesics,
     tracegeodesics_batch,
     tracing_configuration,
+    trace_target,
+    optimize_for_target,
+    impact_parameters_for_target,
 )
 from . import corona, hostmath, reverberation, tf_integration  # noqa: F401
 from ._cabi import GradusB200Error  # noqa: F401

@@ -17,6 +17,7 @@ ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = -1, 
 STATUS_OUT_OF_DOMAIN, STATUS_WITHIN_INNER_BOUNDARY, STATUS_INTERSECTED, STATUS_NO_STATUS = 0, 1, 2, 3
 METRIC_KERR, METRIC_JP, METRIC_JOHANNSEN, METRIC_BUMBLEBEE, METRIC_KERR_NEWMAN, METRIC_MORRIS_THORNE = 0, 1, 2, 3, 4, 5
 GEOMETRY_NONE, GEOMETRY_THIN_DISC, GEOMETRY_SHAKURA_SUNYAEV, GEOMETRY_DATUM_PLANE, GEOMETRY_THICK_TABLE = 0, 1, 2, 3, 4
+GEOMETRY_TARGET_POINT = 5  # gb200_trace_target only
 CALLBACK_NONE, CALLBACK_UPPER_HEMISPHERE = 0, 1
 POW_EXACT, POW_FAST32 = 0, 1
 IC_RENDER_GRID, IC_POLAR_PLANE, IC_EXPLICIT, IC_CARTESIAN_PLANE, IC_IMPACT_PARAMETERS = 0, 1, 2, 3, 4
@@ -107,7 +108,7 @@ EXPORTED_SYMBOLS = (
     "gb200_version", "gb200_init", "gb200_destroy", "gb200_last_error", "gb200_get_stats", "gb200_validate",
     "gb200_isco", "gb200_radiative_efficiency", "gb200_trace", "gb200_trace_batch", "gb200_trace_path", "gb200_build_plunging_table", "gb200_render", "gb200_lineprofile",
     "gb200_render_batch", "gb200_render_device", "gb200_lineprofile_device", "gb200_fp64_peak", "gb200_fp64_issue_probe", "gb200_debug_rhs", "gb200_debug_math",
-    "gb200_trace_dual", "gb200_trace_dual_batch",
+    "gb200_trace_dual", "gb200_trace_dual_batch", "gb200_trace_target",
     "gb200_set_cross_section", "gb200_bucket2d", "gb200_comm_init", "gb200_comm_destroy", "gb200_comm_size", "gb200_comm_context", "gb200_comm_lineprofile", "gb200_comm_render",
 )
 
@@ -217,6 +218,7 @@ def load():
     lib.gb200_trace.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range), C.POINTER(Endpoints)]
     lib.gb200_trace_batch.argtypes = [vp, C.c_int32, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range), C.POINTER(Endpoints)]
     lib.gb200_trace_path.argtypes = [vp, C.POINTER(Problem), _dp, C.c_int32, _dp, _dp, _ip, _ip]
+    lib.gb200_trace_target.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range), _dp, C.c_double, C.POINTER(Endpoints), _dp]
     lib.gb200_build_plunging_table.argtypes = [vp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, _dp, _ip]
     lib.gb200_render.argtypes = [vp, C.POINTER(Problem), C.POINTER(IC), C.POINTER(Range), _ip, C.c_int32,
                                  C.POINTER(PlungingTable), C.POINTER(_dp)]

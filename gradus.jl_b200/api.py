@@ -679,6 +679,65 @@ def solve_tracing_problem(config: TracingConfiguration) -> GeodesicPoints:
     return GeodesicPoints(out, config.lambda_domain[0])
 
 
+def trace_target(config: TracingConfiguration, target, d_tol=1e-2):
+    """The objective of `optimize_for_target` (src/tracing/precision-solvers.jl:452-510) for every ray of `config` in one
+    launch (`gb200_trace_target`): returns (closest approach to `target` = (r, θ, φ) per ray, GeodesicPoints).  Rays end
+    where they first come within `d_tol` of the target (status IntersectedWithGeometry), like the reference's
+    `distance_callback`."""
+    p, ic = config.to_c()
+    n = ic.n
+    out = cabi.EndpointArrays(n)
+    closest = np.zeros(n)
+    tgt = np.ascontiguousarray(target, np.float64)
+    if tgt.shape != (3,):
+        raise ValueError("target must be (r, θ, φ)")
+    ens = config.ensemble
+    ctx = ens.ctx(ens.devices[0])
+    rng = cabi.Range(0, n, 1)
+    cabi.check(cabi.load().gb200_trace_target(ctx, C.byref(p), C.byref(ic), C.byref(rng), cabi.dptr(tgt), float(d_tol),
+                                              C.byref(out.c), cabi.dptr(closest)), ctx)
+    return closest, GeodesicPoints(out, config.lambda_domain[0])
+
+
+def optimize_for_target(target, m, x0, *, d_tol=1e-2, max_time=None, p0=(0.0, 0.0), window=None, grid=33, max_rounds=10,
+                        tracer=trace_target, **kwargs):
+    """`optimize_for_target(target, m, x0; ...)` (src/tracing/precision-solvers.jl:512-531): impact parameters (α, β) of a
+    geodesic from `x0` that passes within `d_tol` of `target` = (r, θ, φ).  Returns (α, β, geodesic point, accuracy) with
+    accuracy = the closest approach reached.
+
+    The reference minimises the closest approach one trace at a time (Optim.NelderMead from `p0`, a local search).  A
+    device traces a thousand rays in the time of one, so the search here is a `grid` × `grid` patch of impact parameters
+    per launch, centred on the best ray so far and shrunk to two cells of the previous patch each round, until the best
+    ray is within `d_tol` (three to five launches).  The first patch spans ±`window` around `p0` (default: 1.5 r_target +
+    10, which contains the direct image of the target for any viewing angle).  `tracer` exists for the tests (the CPU
+    oracle in place of the device)."""
+    x0 = [float(v) for v in x0]
+    lam = 2.0 * x0[1] if max_time is None else float(max_time)
+    half = float(window) if window is not None else 1.5 * float(target[0]) + 10.0
+    ca, cb = float(p0[0]), float(p0[1])
+    best = (np.inf, ca, cb, None)
+    for _ in range(max_rounds):
+        a1 = ca + np.linspace(-half, half, grid)
+        b1 = cb + np.linspace(-half, half, grid)
+        aa, bb = np.meshgrid(a1, b1, indexing="ij")
+        cfg = tracing_configuration(m, x0, ImpactParameters(aa.ravel(), bb.ravel()), lam, trajectories=aa.size, **kwargs)
+        closest, gps = tracer(cfg, target, d_tol)
+        i = int(np.nanargmin(closest))
+        if closest[i] < best[0]:
+            best = (float(closest[i]), float(aa.ravel()[i]), float(bb.ravel()[i]), gps[i])
+        if best[0] < d_tol:
+            break
+        ca, cb = best[1], best[2]
+        half = 2.0 * (2.0 * half / (grid - 1))
+    return best[1], best[2], best[3], best[0]
+
+
+def impact_parameters_for_target(target, m, x0, **kwargs):
+    """`impact_parameters_for_target` (src/tracing/precision-solvers.jl:533-543): (α, β, accuracy)."""
+    a, b, _, acc = optimize_for_target(target, m, x0, **kwargs)
+    return a, b, acc
+
+
 def tracegeodesics_batch(configs: Sequence[TracingConfiguration]) -> list:
     """Many (short) ensembles in one call: every configuration is traced on its own stream of the first device's
     stream pool and the host synchronises once (the reference calls `tracegeodesics` once per corona

@@ -145,3 +145,15 @@ def binflux(tf: LagTransferFunction, profile=None, *, E0=6.4, t0=None, **kwargs)
     F = f / f.sum()
     tb, eb, td = bin_transfer_function(t, tf.g * E0, F, **kwargs)
     return tb - t0, eb, td
+
+
+def continuum_time(m, x, model, **kwargs):
+    """`continuum_time(m, x, model)` (src/reverberation.jl:81-93): coordinate time of the direct corona-to-observer light
+    path, found backwards as the geodesic from the observer that reaches the corona's position (`optimize_for_target`
+    with the upper-hemisphere callback and a chart of twice the observer's radius)."""
+    pos, _ = corona.sample_position_velocity(m, model)
+    kwargs.setdefault("chart", api.chart_for_metric(m, 2.0 * float(x[1])))
+    kwargs.setdefault("callback", api.domain_upper_hemisphere())
+    _, _, gp, _ = api.optimize_for_target(pos[1:], m, x, **kwargs)
+    return float(gp["x"][0])
+

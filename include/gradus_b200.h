@@ -257,8 +257,11 @@ int gb200_trace_path(gb200_ctx* ctx, const gb200_problem* p, const double* u0, i
 /* The objective of optimize_for_target / impact_parameters_for_target (src/tracing/precision-solvers.jl:452-546) for a whole
    set of rays at once: every ray of `ic` / `rg` is traced with the reference's distance callback -- a ContinuousCallback on
    |to_cartesian(u) - to_cartesian(target)| - d_tol with 8 interpolation points that terminates the ray
-   (IntersectedWithGeometry) where it first comes within d_tol -- and closest[i] receives the smallest distance seen by any
-   evaluation of that condition (closest_approach[], :466-481).  target = (r, theta, phi); p->geometry_kind must be
+   (IntersectedWithGeometry) where it first comes within d_tol -- and closest[i] receives the ray's closest approach
+   (closest_approach[], :466-481).  The reference records the smallest of the condition's own evaluations (eight samples per
+   step), which misses a d_tol sphere lying between two samples; here the distance is also minimised along the dense output
+   of each step (golden section around the smallest sample), and coming within d_tol there is an event as well.
+   target = (r, theta, phi); p->geometry_kind must be
    GB200_GEOMETRY_NONE (the callback takes the geometry's place), p->callback_kind and the chart apply as usual.  The
    reference minimises this objective one ray at a time (Nelder-Mead); with a device under it the search is a grid of impact
    parameters per call, refined around its minimum (the Python mirror's `optimize_for_target`).  `out` may be NULL. */

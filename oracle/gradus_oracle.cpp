@@ -560,7 +560,17 @@ static double cross_section_table(double x) { // linear interpolation, -1 (no di
 // ------------------------------------------------------------------ geometry conditions
 // distance_to_disc: thin-disc.jl:20-26, thick-disc.jl:57-63 + shakura-sunyaev.jl:28-33, datum-plane.jl:6-10
 template <class T>
-T disc_condition(const gb200_problem& p, T r, T th) {
+T disc_condition(const gb200_problem& p, T r, T th, T ph = T(0)) {
+    if (p.geometry_kind == GB200_GEOMETRY_TARGET_POINT) {
+        // distance_callback of _make_target_objective, src/tracing/precision-solvers.jl:473-488, with to_cartesian of
+        // src/geometry/geometry.jl:13-16; geometry_params = target (r, theta, phi), d_tol
+        const double tr = p.geometry_params[0], tth = p.geometry_params[1], tph = p.geometry_params[2];
+        T sth = rsin(th);
+        T dx = r * sth * rcos(ph) - T(tr * std::sin(tth) * std::cos(tph));
+        T dy = r * sth * rsin(ph) - T(tr * std::sin(tth) * std::sin(tph));
+        T dz = r * rcos(th) - T(tr * std::cos(tth));
+        return rsqrt_(dx * dx + dy * dy + dz * dz) - T(p.geometry_params[3]);
+    }
     if (p.geometry_kind == GB200_GEOMETRY_THIN_DISC) {
         T rho = r * rabs(rsin(th));
         if (rho < T(p.geometry_params[0]) || rho > T(p.geometry_params[1])) return T(1);
@@ -641,6 +651,7 @@ struct RayResult {
     // sign tests of the disc condition at the step ends and the 7 interior samples, chart and hemisphere tests),
     // each scaled to be dimensionless.  Rays with a tiny margin form the "grazing band" of DESIGN.md.
     double margin;
+    double closest; // GB200_GEOMETRY_TARGET_POINT: smallest distance to the target over every evaluation of the condition (closest_approach[])
 };
 
 // Dense output, OrdinaryDiffEq Tsit5 interpolant (order-4), Theta in [0,1]
@@ -683,6 +694,13 @@ void trace_ray(const gb200_problem& p, const Metric& m, const T u_init[8], RayRe
     for (int i = 0; i < 4; ++i) { res.x0[i] = u_init[i]; res.v0[i] = u_init[4 + i]; }
     res.status = GB200_STATUS_NO_STATUS; res.naccept = 0; res.nreject = 0; res.flags = 0;
     res.margin = 1e300;
+    res.closest = 1e300;
+    const bool target = p.geometry_kind == GB200_GEOMETRY_TARGET_POINT;
+    auto cond = [&](const T* y) -> T { // the continuous callback's condition; the target objective records every evaluation
+        T c = disc_condition<T>(p, y[1], y[2], y[3]);
+        if (target) res.closest = std::min(res.closest, (double)(c + T(p.geometry_params[3])));
+        return c;
+    };
     auto note = [&](T dist) { double d = (double)rabs(dist); if (d < res.margin) res.margin = d; };
     auto note_cond = [&](T c, T r_, T th_) { // disc condition margins, incl. the radial-range discontinuity of ThinDisc
         note(c / std::max(T(1), rabs(r_)));
@@ -801,8 +819,8 @@ void trace_ray(const gb200_problem& p, const Metric& m, const T u_init[8], RayRe
 
         // ---- handle_callbacks!: (1) ContinuousCallback(distance_to_disc), interp_points = 8
         if (p.geometry_kind != GB200_GEOMETRY_NONE) {
-            T cprev = disc_condition<T>(p, uprev[1], uprev[2]);
-            T cnext = disc_condition<T>(p, u[1], u[2]);
+            T cprev = cond(uprev);
+            T cnext = cond(u);
             int sprev = (cprev > 0) - (cprev < 0), snext = (cnext > 0) - (cnext < 0);
             note_cond(cnext, u[1], u[2]);
             bool event = false;
@@ -810,21 +828,38 @@ void trace_ray(const gb200_problem& p, const Metric& m, const T u_init[8], RayRe
             if (sprev != 0 && sprev * snext <= 0) event = true;
             else if (sprev != 0) {
                 T last = tprev;
+                T best = std::min(cprev, cnext), bestTh = (cnext < cprev) ? T(1) : T(0); // target objective only
                 for (int i = 2; i <= 8; ++i) {
                     T abst = (i == 8) ? t : tprev + (T(i - 1) * (t - tprev)) / T(7);
                     T cnew;
                     if (i == 8) cnew = cnext;
-                    else { T ui[8]; interpolant<T>((abst - tprev) / dt, dt, uprev, k, ui, 3); cnew = disc_condition<T>(p, ui[1], ui[2]); note_cond(cnew, ui[1], ui[2]); }
+                    else { T ui[8]; interpolant<T>((abst - tprev) / dt, dt, uprev, k, ui, 4); cnew = cond(ui); note_cond(cnew, ui[1], ui[2]); }
                     if (T(sprev) * cnew < T(0)) { event = true; bottom = last; top = abst; break; }
+                    if (cnew < best) { best = cnew; bestTh = T(i - 1) / T(7); }
                     last = abst;
+                }
+                if (target && !event) {
+                    // the closest approach along the dense output, not only at the eight samples (which miss a d_tol sphere
+                    // between two of them): golden-section search around the smallest sample -- the same refinement as
+                    // gen_trace_ray of the library (gb200_generic.cuh); an event when the minimum is inside d_tol
+                    auto at = [&](T Th) -> T { T ui[8]; interpolant<T>(Th, dt, uprev, k, ui, 4); return cond(ui); };
+                    T a = std::max(bestTh - T(1) / T(7), T(0)), b = std::min(bestTh + T(1) / T(7), T(1));
+                    const T gr = T(0.6180339887498949);
+                    T x1 = b - gr * (b - a), x2 = a + gr * (b - a), f1 = at(x1), f2 = at(x2);
+                    for (int it = 0; it < 30; ++it) {
+                        if (f1 < f2) { b = x2; x2 = x1; f2 = f1; x1 = b - gr * (b - a); f1 = at(x1); }
+                        else { a = x1; x1 = x2; f1 = f2; x2 = a + gr * (b - a); f2 = at(x2); }
+                    }
+                    const T xm = (f1 < f2) ? x1 : x2, fm = std::min(f1, f2);
+                    if (fm < T(0)) { event = true; bottom = tprev + std::max(bestTh - T(1) / T(7), T(0)) * dt; top = tprev + xm * dt; }
                 }
             }
             if (event) {
                 auto zf = [&](T abst) -> T {
-                    if (abst == t) return disc_condition<T>(p, u[1], u[2]);
+                    if (abst == t) return cond(u);
                     if (abst == tprev) return cprev;
-                    T ui[8]; interpolant<T>((abst - tprev) / dt, dt, uprev, k, ui, 3);
-                    return disc_condition<T>(p, ui[1], ui[2]);
+                    T ui[8]; interpolant<T>((abst - tprev) / dt, dt, uprev, k, ui, 4);
+                    return cond(ui);
                 };
                 T tev;
                 T ctop = zf(top);
@@ -1026,7 +1061,7 @@ static int bin_index(const double* bins, int nbins, double g, int right_closed) 
 template <class T>
 int run(const gb200_problem& p, const gb200_ic& ic, const gb200_range& rg, int nthreads,
         gb200_endpoints* out, double* margin, const int32_t* pfs, int npf, const gb200_plunging_table* pl, double* const* images,
-        const gb200_emissivity* emis, const double* bins, int nbins, const gb200_lineprofile_opts* lo, double* flux) {
+        const gb200_emissivity* emis, const double* bins, int nbins, const gb200_lineprofile_opts* lo, double* flux, double* closest = nullptr) {
     Metric m = make_metric(p.metric_kind, p.metric_params);
     LnrTransform<T> xfm;
     if (ic.kind != GB200_IC_EXPLICIT) {
@@ -1071,6 +1106,7 @@ int run(const gb200_problem& p, const gb200_ic& ic, const gb200_range& rg, int n
             if (out->flags) out->flags[n] = res.flags;
         }
         if (margin) margin[n] = res.margin;
+        if (closest) closest[n] = res.closest;
         for (int kpf = 0; kpf < npf; ++kpf) images[kpf][n] = (double)point_function<T>(pfs[kpf], p, m, r_isco, pl, res);
         if (flux && res.status == GB200_STATUS_INTERSECTED_WITH_GEOMETRY) { // line-profiles.jl:186-194
             double rho = (double)(res.x[1] * rabs(rsin(res.x[2])));
@@ -1440,6 +1476,14 @@ extern "C" {
 int oracle_trace(const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, int nthreads, int precision, gb200_endpoints* out, double* margin) {
     if (precision == 1) return orc::run<long double>(*p, *ic, *rg, nthreads, out, margin, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
     return orc::run<double>(*p, *ic, *rg, nthreads, out, margin, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+}
+// optimize_for_target's objective for every ray of the set: target = (r, theta, phi), closest[i] = closest_approach[]
+int oracle_trace_target(const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, int nthreads, const double* target, double d_tol,
+                        gb200_endpoints* out, double* closest) {
+    gb200_problem q = *p;
+    q.geometry_kind = GB200_GEOMETRY_TARGET_POINT;
+    q.geometry_params[0] = target[0]; q.geometry_params[1] = target[1]; q.geometry_params[2] = target[2]; q.geometry_params[3] = d_tol;
+    return orc::run<double>(q, *ic, *rg, nthreads, out, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, closest);
 }
 int oracle_render(const gb200_problem* p, const gb200_ic* ic, const gb200_range* rg, int nthreads, int precision,
                   const int32_t* pfs, int npf, const gb200_plunging_table* pl, double* const* images, gb200_endpoints* out) {

@@ -87,6 +87,18 @@ def trace(problem, ic, rng=None, nthreads=0, precision=0):
     return out
 
 
+def trace_target(problem, ic, target, d_tol, rng=None, nthreads=0):
+    """optimize_for_target's objective for every ray: (closest approach per ray, endpoints)."""
+    rng = _range(ic, rng)
+    out = cabi.EndpointArrays(rng.count)
+    closest = np.zeros(rng.count)
+    tgt = np.ascontiguousarray(target, np.float64)
+    rc = lib().oracle_trace_target(C.byref(problem), C.byref(ic), C.byref(rng), nthreads, cabi.dptr(tgt), C.c_double(d_tol),
+                                   C.byref(out.c), cabi.dptr(closest))
+    assert rc == 0
+    return closest, out
+
+
 def render(problem, ic, pointfns, rng=None, nthreads=0, precision=0, plunging=None, endpoints=False):
     rng = _range(ic, rng)
     pfs = np.asarray(pointfns, np.int32)

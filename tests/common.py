@@ -5,6 +5,7 @@ import numpy as np
 
 import gradus_b200 as gb
 from gradus_b200 import _cabi as cabi
+from gradus_b200 import api
 from gradus_b200.api import RenderGrid, tracing_configuration
 
 
@@ -104,3 +105,12 @@ def oracle_solver(configs):
         p, ic = config.to_c()
         out.append(api.GeodesicPoints(_oracle().trace(p, ic), config.lambda_domain[0]))
     return out
+
+
+def oracle_target_tracer(config, target, d_tol):
+    """`api.trace_target` with the CPU oracle in place of the device (tests only)."""
+    oracle = _oracle()
+    p, ic = config.to_c()
+    closest, out = oracle.trace_target(p, ic, target, d_tol)
+    return closest, api.GeodesicPoints(out, config.lambda_domain[0])
+
