@@ -14,6 +14,7 @@
 #include <mutex>
 #include <string>
 #include <functional>
+#include <thread>
 #include <vector>
 #include "gb200_device.cuh"
 #include "gb200_internal.h"
@@ -1483,30 +1484,75 @@ int gb200_comm_render(gb200_comm* c, const gb200_problem* p, const gb200_ic* ic,
             CU(ctx, cudaEventRecord(ev, ctx->stream));
         }
     }
-    // copies chunk by chunk, round robin over the devices, on each device's copy stream: strip b of a device sits at ray
-    // first + b * stride * block of the image (a strided 2-D copy); copies into pageable memory block this thread, the
-    // kernels of the later chunks keep running meanwhile
+    // Results travel chunk by chunk: a contiguous copy into the device's pinned staging buffer on its copy stream (truly
+    // asynchronous, every device on its own PCIe link), then one host thread per device scatters the chunk's strips into
+    // the caller's (pageable) images -- strip b of a device sits at ray first + b * stride * block.  A strided copy
+    // straight into pageable memory is staged by the driver on the calling thread and serialises the devices (measured:
+    // 8 GPUs 15.1 ms for the 2048 x 2048 render whose kernels take 5.3 ms).
+    std::vector<std::vector<cudaEvent_t>> copied((size_t)n);
+    auto cleanup2 = [&]() { for (auto& v : copied) for (auto e : v) cudaEventDestroy(e); };
+    for (int d = 0; d < n; ++d) {
+        gb200_ctx* ctx = c->ctx[(size_t)d];
+        const gb200_range& rg = rgs[(size_t)d];
+        if (rg.count == 0) continue;
+        CU(ctx, cudaSetDevice(ctx->device));
+        const size_t total = sizeof(double) * (size_t)rg.count * (size_t)npf;
+        if (ctx->stage_cap < total) {
+            if (ctx->stage) cudaFreeHost(ctx->stage);
+            ctx->stage = nullptr; ctx->stage_cap = 0;
+            CU(ctx, cudaMallocHost(&ctx->stage, total + 256));
+            ctx->stage_cap = total;
+        }
+    }
     for (int ch = 0; ch < K; ++ch)
         for (int d = 0; d < n; ++d) {
             if ((size_t)ch >= done[(size_t)d].size()) continue;
             gb200_ctx* ctx = c->ctx[(size_t)d];
             const gb200_range& rg = rgs[(size_t)d];
             const int64_t s0 = (int64_t)ch * per[(size_t)d], cnt = std::min(per[(size_t)d], rg.count - s0);
-            const size_t blk = (size_t)rg.block;
             CU(ctx, cudaSetDevice(ctx->device));
             cudaStream_t copy = ctx->pool_streams[1];
             CU(ctx, cudaStreamWaitEvent(copy, done[(size_t)d][(size_t)ch], 0));
             for (int k = 0; k < npf; ++k)
-                CU(ctx, cudaMemcpy2DAsync(images[k] + rg.first + (s0 / rg.block) * rg.stride * rg.block, sizeof(double) * blk * (size_t)rg.stride,
-                                          dimg[(size_t)d][(size_t)k] + s0, sizeof(double) * blk, sizeof(double) * blk, (size_t)cnt / blk,
-                                          cudaMemcpyDeviceToHost, copy));
+                CU(ctx, cudaMemcpyAsync((double*)ctx->stage + (size_t)k * (size_t)rg.count + s0, dimg[(size_t)d][(size_t)k] + s0,
+                                        sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, copy));
+            cudaEvent_t ev;
+            CU(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            copied[(size_t)d].push_back(ev);
+            CU(ctx, cudaEventRecord(ev, copy));
         }
+    std::vector<cudaError_t> terr((size_t)n, cudaSuccess);
+    std::vector<std::thread> workers;
+    for (int d = 0; d < n; ++d) {
+        if (copied[(size_t)d].empty()) continue;
+        workers.emplace_back([&, d]() {
+            gb200_ctx* ctx = c->ctx[(size_t)d];
+            const gb200_range& rg = rgs[(size_t)d];
+            const size_t blk = (size_t)rg.block;
+            for (size_t ch = 0; ch < copied[(size_t)d].size(); ++ch) {
+                const cudaError_t e = cudaEventSynchronize(copied[(size_t)d][ch]);
+                if (e != cudaSuccess) { terr[(size_t)d] = e; return; }
+                const int64_t s0 = (int64_t)ch * per[(size_t)d], cnt = std::min(per[(size_t)d], rg.count - s0);
+                for (int k = 0; k < npf; ++k) {
+                    const double* src = (const double*)ctx->stage + (size_t)k * (size_t)rg.count + s0;
+                    double* dst = images[k] + rg.first + (s0 / rg.block) * rg.stride * rg.block;
+                    if (rg.stride == 1) memcpy(dst, src, sizeof(double) * (size_t)cnt);
+                    else
+                        for (int64_t b_ = 0; b_ < cnt / rg.block; ++b_)
+                            memcpy(dst + (size_t)b_ * blk * (size_t)rg.stride, src + (size_t)b_ * blk, sizeof(double) * blk);
+                }
+            }
+        });
+    }
+    for (auto& w : workers) w.join();
     for (int d = 0; d < n; ++d) {
         gb200_ctx* ctx = c->ctx[(size_t)d];
+        if (terr[(size_t)d] != cudaSuccess) { cleanup(); cleanup2(); return fail(nullptr, GB200_ERR_CUDA, "device %d: %s", ctx->device, cudaGetErrorString(terr[(size_t)d])); }
         CU(ctx, cudaSetDevice(ctx->device));
         if (ctx->pool_streams.size() >= 2) CU(ctx, cudaStreamSynchronize(ctx->pool_streams[1]));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    cleanup2();
     cleanup();
     return GB200_OK;
 }
