@@ -444,30 +444,32 @@ GB_HD inline void gen_trace_ray(const GbParams& P, const GD<N> u_init[8], double
                 return cv_;
             };
             if (sprev != 0.0) {
-                if (sprev * snext <= 0.0) event = true;
-                else if (target) {
-                    // The reference's objective is the smallest of the eight samples of a step, which misses a d_tol sphere
-                    // that falls between two samples (steps are ~ 1 long near the hole, d_tol = 1e-2).  Here the distance
-                    // is minimised along the dense output: samples first (a sign change among them is an event as usual),
-                    // then a golden-section search around the smallest sample; an event when the minimum is inside d_tol.
-                    double best = fmin(cprev, cnext), bestTh = (cnext < cprev) ? 1.0 : 0.0;
-                    for (int i = 1; i <= 6 && !event; ++i) {
-                        const double Th = (double)i / 7.0, cv = cond_at(Th);
-                        if (cv < 0.0) { event = true; ev_lo = (double)(i - 1) / 7.0; ev_hi = Th; }
+                if (target) {
+                    // The reference's objective is the smallest of the condition's own evaluations -- eight samples per step,
+                    // which miss a d_tol sphere lying between two of them (steps are ~ 1 long near the hole, d_tol = 1e-2), plus
+                    // whatever the root finder happens to touch.  Here the distance is minimised along the dense output of
+                    // the step: all samples, then a golden-section search around the smallest one; the ray ends (event) at
+                    // its first entry into the d_tol sphere, and closest is the minimum over the whole step either way, so it
+                    // does not depend on which points a root finder visits.
+                    double best = cprev, bestTh = 0.0;
+                    int first_neg = 0;
+                    for (int i = 1; i <= 7; ++i) {
+                        const double Th = (double)i / 7.0, cv = (i == 7) ? cnext : cond_at(Th);
+                        if (cv < 0.0 && !first_neg) first_neg = i;
                         if (cv < best) { best = cv; bestTh = Th; }
                     }
-                    if (!event) {
-                        double a = fmax(bestTh - 1.0 / 7.0, 0.0), b = fmin(bestTh + 1.0 / 7.0, 1.0);
-                        const double gr = 0.6180339887498949;
-                        double x1 = b - gr * (b - a), x2 = a + gr * (b - a), f1 = cond_at(x1), f2 = cond_at(x2);
-                        for (int it = 0; it < 30; ++it) {
-                            if (f1 < f2) { b = x2; x2 = x1; f2 = f1; x1 = b - gr * (b - a); f1 = cond_at(x1); }
-                            else { a = x1; x1 = x2; f1 = f2; x2 = a + gr * (b - a); f2 = cond_at(x2); }
-                        }
-                        const double xm = (f1 < f2) ? x1 : x2, fm = fmin(f1, f2);
-                        if (fm < 0.0) { event = true; ev_lo = fmax(bestTh - 1.0 / 7.0, 0.0); ev_hi = xm; }
+                    double a = fmax(bestTh - 1.0 / 7.0, 0.0), b = fmin(bestTh + 1.0 / 7.0, 1.0);
+                    const double gr = 0.6180339887498949;
+                    double x1 = b - gr * (b - a), x2 = a + gr * (b - a), f1 = cond_at(x1), f2 = cond_at(x2);
+                    for (int it = 0; it < 30; ++it) {
+                        if (f1 < f2) { b = x2; x2 = x1; f2 = f1; x1 = b - gr * (b - a); f1 = cond_at(x1); }
+                        else { a = x1; x1 = x2; f1 = f2; x2 = a + gr * (b - a); f2 = cond_at(x2); }
                     }
-                } else if (gen_scan_needed(P, u[1].v, cprev, sprev, hgt, dt, k))
+                    const double xm = (f1 < f2) ? x1 : x2, fm = fmin(f1, f2);
+                    if (first_neg) { event = true; ev_lo = (double)(first_neg - 1) / 7.0; ev_hi = (double)first_neg / 7.0; }
+                    else if (fm < 0.0) { event = true; ev_lo = fmax(bestTh - 1.0 / 7.0, 0.0); ev_hi = xm; }
+                } else if (sprev * snext <= 0.0) event = true;
+                else if (gen_scan_needed(P, u[1].v, cprev, sprev, hgt, dt, k))
                     for (int i = 1; i <= 6; ++i) {
                         const double Th = (double)i / 7.0;
                         if (sprev * cond_at(Th) < 0.0) { event = true; ev_lo = (double)(i - 1) / 7.0; ev_hi = Th; break; }

@@ -825,33 +825,39 @@ void trace_ray(const gb200_problem& p, const Metric& m, const T u_init[8], RayRe
             note_cond(cnext, u[1], u[2]);
             bool event = false;
             T bottom = tprev, top = t;
-            if (sprev != 0 && sprev * snext <= 0) event = true;
+            if (sprev != 0 && target) {
+                // The closest approach along the dense output of the step, not only at the eight samples (which miss a d_tol
+                // sphere between two of them) or wherever a root finder happens to evaluate: all samples, then a golden-section
+                // search around the smallest -- the same refinement as gen_trace_ray of the library (gb200_generic.cuh).  The ray
+                // ends at its first entry into the d_tol sphere.
+                auto at = [&](T Th) -> T { T ui[8]; interpolant<T>(Th, dt, uprev, k, ui, 4); return cond(ui); };
+                T best = cprev, bestTh = T(0);
+                int first_neg = 0;
+                for (int i = 1; i <= 7; ++i) {
+                    T Th = T(i) / T(7), cv = (i == 7) ? cnext : at(Th);
+                    if (cv < T(0) && !first_neg) first_neg = i;
+                    if (cv < best) { best = cv; bestTh = Th; }
+                }
+                T a = std::max(bestTh - T(1) / T(7), T(0)), b = std::min(bestTh + T(1) / T(7), T(1));
+                const T gr = T(0.6180339887498949);
+                T x1 = b - gr * (b - a), x2 = a + gr * (b - a), f1 = at(x1), f2 = at(x2);
+                for (int it = 0; it < 30; ++it) {
+                    if (f1 < f2) { b = x2; x2 = x1; f2 = f1; x1 = b - gr * (b - a); f1 = at(x1); }
+                    else { a = x1; x1 = x2; f1 = f2; x2 = a + gr * (b - a); f2 = at(x2); }
+                }
+                const T xm = (f1 < f2) ? x1 : x2, fm = std::min(f1, f2);
+                if (first_neg) { event = true; bottom = tprev + (T(first_neg - 1) / T(7)) * dt; top = (first_neg == 7) ? t : tprev + (T(first_neg) / T(7)) * dt; }
+                else if (fm < T(0)) { event = true; bottom = tprev + std::max(bestTh - T(1) / T(7), T(0)) * dt; top = tprev + xm * dt; }
+            } else if (sprev != 0 && sprev * snext <= 0) event = true;
             else if (sprev != 0) {
                 T last = tprev;
-                T best = std::min(cprev, cnext), bestTh = (cnext < cprev) ? T(1) : T(0); // target objective only
                 for (int i = 2; i <= 8; ++i) {
                     T abst = (i == 8) ? t : tprev + (T(i - 1) * (t - tprev)) / T(7);
                     T cnew;
                     if (i == 8) cnew = cnext;
                     else { T ui[8]; interpolant<T>((abst - tprev) / dt, dt, uprev, k, ui, 4); cnew = cond(ui); note_cond(cnew, ui[1], ui[2]); }
                     if (T(sprev) * cnew < T(0)) { event = true; bottom = last; top = abst; break; }
-                    if (cnew < best) { best = cnew; bestTh = T(i - 1) / T(7); }
                     last = abst;
-                }
-                if (target && !event) {
-                    // the closest approach along the dense output, not only at the eight samples (which miss a d_tol sphere
-                    // between two of them): golden-section search around the smallest sample -- the same refinement as
-                    // gen_trace_ray of the library (gb200_generic.cuh); an event when the minimum is inside d_tol
-                    auto at = [&](T Th) -> T { T ui[8]; interpolant<T>(Th, dt, uprev, k, ui, 4); return cond(ui); };
-                    T a = std::max(bestTh - T(1) / T(7), T(0)), b = std::min(bestTh + T(1) / T(7), T(1));
-                    const T gr = T(0.6180339887498949);
-                    T x1 = b - gr * (b - a), x2 = a + gr * (b - a), f1 = at(x1), f2 = at(x2);
-                    for (int it = 0; it < 30; ++it) {
-                        if (f1 < f2) { b = x2; x2 = x1; f2 = f1; x1 = b - gr * (b - a); f1 = at(x1); }
-                        else { a = x1; x1 = x2; f1 = f2; x2 = a + gr * (b - a); f2 = at(x2); }
-                    }
-                    const T xm = (f1 < f2) ? x1 : x2, fm = std::min(f1, f2);
-                    if (fm < T(0)) { event = true; bottom = tprev + std::max(bestTh - T(1) / T(7), T(0)) * dt; top = tprev + xm * dt; }
                 }
             }
             if (event) {
