@@ -13,7 +13,7 @@ struct GbNoRecord {
     template <class U> GB_HD void operator()(double, const U*) const {}
 };
 
-template <int N>
+template <int N, int MK>
 __global__ void __launch_bounds__(64) gb200_dual_kernel(const __grid_constant__ GbParams P, const __grid_constant__ GbDualIO io) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= io.n) return;
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(64) gb200_dual_kernel(const __grid_constant__ 
     gen_initial_state<N>(P, al, be, u0, E_obs);
     const double hgt = io.height ? io.height[i] : P.gp0;
     GenResult<N> res;
-    gen_trace_ray<N>(P, u0, hgt, io.norm_partials != 0, res, GbNoRecord());
+    gen_trace_ray<N, MK>(P, u0, hgt, io.norm_partials != 0, res, GbNoRecord());
     if (io.status) io.status[i] = res.status;
     if (io.lambda) io.lambda[i] = res.lambda;
     for (int k = 0; k < 4; ++k) {
@@ -51,8 +51,9 @@ __global__ void __launch_bounds__(64) gb200_dual_kernel(const __grid_constant__ 
 cudaError_t gb200_launch_dual(const GbParams& P, const GbDualIO& io, cudaStream_t stream) {
     if (io.n <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)((io.n + 63) / 64);
-    if (io.npartials == 1) gb200_dual_kernel<1><<<grid, 64, 0, stream>>>(P, io);
-    else if (io.npartials == 2) gb200_dual_kernel<2><<<grid, 64, 0, stream>>>(P, io);
+    const bool kerr = P.metric_kind == GB200_METRIC_KERR; // its own instantiation: a third of the code of the run-time-metric one
+    if (io.npartials == 1) { if (kerr) gb200_dual_kernel<1, GB200_METRIC_KERR><<<grid, 64, 0, stream>>>(P, io); else gb200_dual_kernel<1, -1><<<grid, 64, 0, stream>>>(P, io); }
+    else if (io.npartials == 2) { if (kerr) gb200_dual_kernel<2, GB200_METRIC_KERR><<<grid, 64, 0, stream>>>(P, io); else gb200_dual_kernel<2, -1><<<grid, 64, 0, stream>>>(P, io); }
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(64) gb200_target_kernel(const __grid_constant_
     GD<0> u[8];
     for (int k = 0; k < 4; ++k) { u[k] = GD<0>(ri.x[k]); u[4 + k] = GD<0>(ri.v[k]); }
     GenResult<0> res;
-    gen_trace_ray<0>(P, u, 0.0, false, res, GbNoRecord());
+    gen_trace_ray<0, -1>(P, u, 0.0, false, res, GbNoRecord());
     if (P.o_status) P.o_status[s] = res.status;
     if (P.o_lambda) P.o_lambda[s] = res.lambda;
     for (int k = 0; k < 4; ++k) {
@@ -116,7 +117,7 @@ __global__ void gb200_path_kernel(const __grid_constant__ GbParams P, const doub
     int rows = 0;
     GbPathRecord rec{cap, lam_out, u_out, &rows};
     GenResult<0> res;
-    gen_trace_ray<0>(P, u, P.gp0, false, res, rec);
+    gen_trace_ray<0, -1>(P, u, P.gp0, false, res, rec);
     meta[0] = rows;
     meta[1] = res.status;
 }

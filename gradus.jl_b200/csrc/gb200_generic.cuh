@@ -168,17 +168,21 @@ GB_HD inline void kerr_accel_g(double M, double a, const S& r, const S& s, const
 }
 
 // _second_order_ode_f (src/tracing/geodesic-problem.jl:87-92): du = (v, a); also returns sin, cos of theta
-template <int N>
+// MK >= 0 fixes the metric kind at compile time (the Kerr instantiation of the forward-mode kernel then carries no other
+// metric's code: a lone warp walks the step code once per attempt, and what does not fit the instruction cache is fetched
+// again every attempt); MK = -1 reads it from P.
+template <int N, int MK = -1>
 GB_HD inline void rhs_g(const GbParams& P, const GD<N> u[8], GD<N> du[8], GD<N>& s, GD<N>& c) {
     typedef GD<N> S;
+    const int mk = (MK >= 0) ? MK : P.metric_kind;
     gd_sincos(u[2], s, c);
     S acc[4];
-    if (P.metric_kind == GB200_METRIC_KERR) kerr_accel_g<S>(P.M, P.a, u[1], s, c, u[4], u[5], u[6], u[7], acc);
+    if (mk == GB200_METRIC_KERR) kerr_accel_g<S>(P.M, P.a, u[1], s, c, u[4], u[5], u[6], u[7], acc);
     else {
         S g[5], dr[5], dth[5], gi[5];
-        metric_jacobian_kind<S>(P.metric_kind, P.mp, u[1], s, c, g, dr, dth);
+        metric_jacobian_kind<S>(mk, P.mp, u[1], s, c, g, dr, dth);
         geodesic_accel_g<S>(g, dr, dth, u[4], u[5], u[6], u[7], acc, gi);
-        if (P.metric_kind == GB200_METRIC_KERR_NEWMAN && P.mp[3] != 0.0) kerr_newman_lorentz_g<S>(P.mp, u[1], s, c, gi, u[4], u[5], u[6], u[7], acc);
+        if (mk == GB200_METRIC_KERR_NEWMAN && P.mp[3] != 0.0) kerr_newman_lorentz_g<S>(P.mp, u[1], s, c, gi, u[4], u[5], u[6], u[7], acc);
     }
     for (int i = 0; i < 4; ++i) { du[i] = u[4 + i]; du[4 + i] = acc[i]; }
 }
@@ -336,7 +340,7 @@ GB_HD inline bool gen_scan_needed(const GbParams& P, double r0, double cprev, do
 }
 
 // REC: callable (double lambda, const GD<N> u[8]) invoked with the initial state and after every accepted step
-template <int N, class REC>
+template <int N, int MK = -1, class REC>
 GB_HD inline void gen_trace_ray(const GbParams& P, const GD<N> u_init[8], double hgt, bool norm_partials, GenResult<N>& res, REC&& rec) {
     typedef GD<N> S;
     const double A[7][6] = {{0, 0, 0, 0, 0, 0}, {GB_A21_V, 0, 0, 0, 0, 0}, {GB_A31_V, GB_A32_V, 0, 0, 0, 0}, {GB_A41_V, GB_A42_V, GB_A43_V, 0, 0, 0},
@@ -353,7 +357,7 @@ GB_HD inline void gen_trace_ray(const GbParams& P, const GD<N> u_init[8], double
     res.status = GB200_STATUS_NO_STATUS; res.naccept = 0; res.nreject = 0; res.flags = 0;
     rec(t, u);
     S s_, c_;
-    rhs_g<N>(P, u, k[0], s_, c_);
+    rhs_g<N, MK>(P, u, k[0], s_, c_);
     const bool target = P.geometry_kind == GB200_GEOMETRY_TARGET_POINT;
     double cprev = has_geom ? disc_condition_g<S>(P, u[1], s_, c_, hgt, u[3].v).v : 1.0;
     res.closest = target ? cprev + P.gtol : nan("");
@@ -368,7 +372,7 @@ GB_HD inline void gen_trace_ray(const GbParams& P, const GD<N> u_init[8], double
         double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
         dt0 = fmin(dt0, dtmax);
         for (int i = 0; i < 8; ++i) tmp[i] = u[i] + dt0 * k[0][i];
-        rhs_g<N>(P, tmp, k[1], s_, c_);
+        rhs_g<N, MK>(P, tmp, k[1], s_, c_);
         for (int i = 0; i < 8; ++i) w[i] = (k[1][i] - k[0][i]) / sk[i];
         const double d2 = gd_norm8(w, norm_partials) / dt0;
         const double md = fmax(d1, d2);
@@ -383,6 +387,9 @@ GB_HD inline void gen_trace_ray(const GbParams& P, const GD<N> u_init[8], double
         if (!(dt == dt) || !(u[1].v == u[1].v)) { res.flags |= GB200_FLAG_UNSTABLE; break; }
         if (!(fmin(dt, rem) > dtmin) && rem > dtmin) { res.flags |= GB200_FLAG_DT_MIN; break; }
         dt = fmin(dt, rem);
+#ifdef __CUDA_ARCH__
+#pragma unroll 1 /* one copy of the right-hand side in the step loop: the loop body then stays inside the instruction cache */
+#endif
         for (int s = 1; s < 7; ++s) {
             for (int i = 0; i < 8; ++i) {
                 S acc = (s == 1) ? S(0.0) : A[s][0] * k[0][i];
@@ -390,7 +397,7 @@ GB_HD inline void gen_trace_ray(const GbParams& P, const GD<N> u_init[8], double
                 tmp[i] = (s == 1) ? u[i] + (dt * A[1][0]) * k[0][i] : u[i] + dt * acc;
             }
             if (s == 6) for (int i = 0; i < 8; ++i) un[i] = tmp[i];
-            rhs_g<N>(P, tmp, k[s], s_, c_);
+            rhs_g<N, MK>(P, tmp, k[s], s_, c_);
         }
         double EEst;
         {

@@ -415,5 +415,55 @@ function lineprofile_b200(bins, ε, m::Gradus.AbstractMetric{T}, u, d;
     bins, flux
 end
 
-export EnsembleB200, B200PointFunction, lineprofile_b200
+"""
+    optimize_for_target_b200(target, m, x0; ensemble, d_tol = 1e-2, max_time = 2x0[2], p0 = (0.0, 0.0), window, grid = 33, kwargs...)
+
+`Gradus.optimize_for_target` (src/tracing/precision-solvers.jl:512-531) with the device under it: instead of one trace per
+Nelder-Mead evaluation, every round traces a `grid` x `grid` patch of impact parameters in one `gb200_trace_target` call
+(the reference's distance callback, closest approach per ray), re-centres on the best ray and shrinks the patch to two of
+its cells, until the best ray passes within `d_tol` of `target` = (r, θ, ϕ).  Returns `(α, β, gp, accuracy)` like the
+reference (`gp` is a named tuple of the end point: status, λ, x, v).
+"""
+function optimize_for_target_b200(target, m::Gradus.AbstractMetric{T}, x0; ensemble::EnsembleB200 = EnsembleB200(), d_tol = 1e-2,
+                                  max_time = 2 * x0[2], p0 = (0.0, 0.0), window = 1.5 * target[1] + 10, grid = 33, max_rounds = 10,
+                                  callback = nothing, solver_args...) where {T}
+    trace = Gradus.TraceGeodesic()
+    ctx = _context(ensemble, 1)
+    tgt = collect(Float64, target)
+    half, ca, cb = Float64(window), Float64(p0[1]), Float64(p0[2])
+    best = (Inf, ca, cb, nothing)
+    n = grid * grid
+    αs, βs, closest = Vector{Float64}(undef, n), Vector{Float64}(undef, n), Vector{Float64}(undef, n)
+    status, λs = Vector{Int32}(undef, n), Vector{Float64}(undef, n)
+    xs, vs = [Vector{Float64}(undef, n) for _ = 1:4], [Vector{Float64}(undef, n) for _ = 1:4]
+    for _ = 1:max_rounds
+        for i = 1:grid, j = 1:grid
+            αs[(i-1)*grid+j] = ca - half + 2half * (i - 1) / (grid - 1)
+            βs[(i-1)*grid+j] = cb - half + 2half * (j - 1) / (grid - 1)
+        end
+        velfunc = i -> Gradus.map_impact_parameters(m, x0, αs[i], βs[i])
+        config, solver_opts = Gradus.tracing_configuration(trace, m, x0, velfunc, (0.0, max_time); callback = callback,
+                                                           ensemble = ensemble, trajectories = n, solver_args...)
+        problem = Gradus.assemble_tracing_problem(trace, config)
+        p = _problem(config, problem.prob; mu = 0.0, solver_opts...)
+        GC.@preserve αs βs closest status λs xs vs tgt begin
+            ic = CIC(4, 0, 0, 0, 0.0, 0.0, 0.0, 0.0, (pointer(αs), pointer(βs), Ptr{Float64}(C_NULL), Ptr{Float64}(C_NULL)), NULL4, n)
+            out = CEndpoints(pointer(status), pointer(λs), Tuple(pointer.(xs)), Tuple(pointer.(vs)), NULL4, NULL4, C_NULL, C_NULL, C_NULL)
+            _check(ccall((:gb200_trace_target, libgradus_b200), Cint,
+                         (Ptr{Cvoid}, Ref{CProblem}, Ref{CIC}, Ref{CRange}, Ptr{Float64}, Float64, Ref{CEndpoints}, Ptr{Float64}),
+                         ctx, p, ic, CRange(0, n, 1, 1), tgt, Float64(d_tol), out, closest), ctx)
+        end
+        i = argmin(closest)
+        if closest[i] < best[1]
+            gp = (status = Gradus.StatusCodes.T(status[i]), λ_max = λs[i], x = SVector{4}(ntuple(k -> xs[k][i], 4)), v = SVector{4}(ntuple(k -> vs[k][i], 4)))
+            best = (closest[i], αs[i], βs[i], gp)
+        end
+        best[1] < d_tol && break
+        ca, cb = best[2], best[3]
+        half = 2 * (2half / (grid - 1))
+    end
+    best[2], best[3], best[4], best[1]
+end
+
+export EnsembleB200, B200PointFunction, lineprofile_b200, optimize_for_target_b200
 end # module
