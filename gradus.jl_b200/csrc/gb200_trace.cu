@@ -601,6 +601,9 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
     }
             GB_STAGE(1) GB_STAGE(2) GB_STAGE(3) GB_STAGE(4) GB_STAGE(5)
 #undef GB_STAGE
+#if GB_OPT_SC7
+            const double th6 = comb<5>(th, dt, vth, kT); // the sixth stage's polar angle (the compiler merges it with the stage's own)
+#endif
             // 7th stage = the proposed state (FSAL)
             nr = comb<6>(r, dt, vr, kR); nth = comb<6>(th, dt, vth, kT);
             nvt = comb<6>(vt, dt, kA0.get(0), kA0); nvr = comb<6>(vr, dt, kA1.get(0), kA1);
@@ -623,7 +626,11 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                 q_ = perr * is3; ee = fma(q_, q_, ee);
             }
 #endif
+#if GB_OPT_SC7
+            rhs_accel_near<METRIC>(P, nr, nth, nvt, nvr, nvth, nvph, th6, s_, c_, acc, s_, c_);
+#else
             rhs_accel<METRIC>(P, nr, nth, nvt, nvr, nvth, nvph, acc, s_, c_);
+#endif
             kA0.set(6, acc[0]); kA1.set(6, acc[1]); kA2.set(6, acc[2]); kA3.set(6, acc[3]);
             // ---- error estimate: rms( dt*sum btilde_j k_j / (abstol + max(|u_prev|,|u|) reltol) )
 #if GB_OPT_PROGERR
