@@ -596,12 +596,6 @@ static int trace_common(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* 
         if (!(d_tol > 0) || !closest) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "gb200_trace_target needs d_tol > 0 and a closest[] array");
         if (!out) out = const_cast<gb200_endpoints*>(&no_endpoints);
     } else if (!out) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null endpoints");
-    // Small ensembles (corona fans, probe sets: ~10^3 rays) are bound by the ~30 small host<->device copies of the SoA, not
-    // by their 0.4 ms kernel: they take the batch path, which stages everything through one pinned arena -- one copy each
-    // way (0.85 -> 0.5 ms per 1000-ray call).
-    if (!target && rg->count <= (1 << 16) && ic->kind != GB200_IC_IMPACT_PARAMETERS && (ic->kind != GB200_IC_EXPLICIT || ic->n <= (1 << 16)) &&
-        !getenv("GB200_NO_SMALL_BATCH"))
-        return gb200_trace_batch(ctx, 1, p, ic, rg, out);
     { int rc_ = begin_call(ctx, ctx->stream); if (rc_) return rc_; }
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     GbParams P;
