@@ -143,18 +143,23 @@ class DualArrays:
         self.height = None if height is None else np.ascontiguousarray(np.broadcast_to(np.asarray(height, np.float64), (n,)))
         self.n, self.npartials = n, nd
         self.ic = DualIC(n, nd, 0, dptr(self.alpha), dptr(self.beta), dptr(self.dalpha), dptr(self.dbeta), dptr(self.height))
-        self.status = np.full(n, -1, np.int32)
-        self.lambda_max = np.zeros(n)
-        self.x, self.v = np.zeros((4, n)), np.zeros((4, n))
-        self.g, self.rho = np.zeros(n), np.zeros(n)
-        self.dg, self.drho = np.zeros((nd, n)), np.zeros((nd, n))
-        self.naccept, self.nreject, self.flags = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        # one block for the outputs, pointers by address arithmetic (a numpy `.ctypes` view per array costs more than the rest)
+        rows = 11 + 2 * nd  # lambda, x[4], v[4], g, rho, dg[nd], drho[nd]
+        dbl, ints = np.zeros((rows, n)), np.zeros((4, n), np.int32)
+        ints[0] = -1
+        self._blocks = (dbl, ints)
+        self.lambda_max, self.x, self.v, self.g, self.rho = dbl[0], dbl[1:5], dbl[5:9], dbl[9], dbl[10]
+        self.dg, self.drho = dbl[11:11 + nd], dbl[11 + nd:11 + 2 * nd]
+        self.status, self.naccept, self.nreject, self.flags = ints[0], ints[1], ints[2], ints[3]
+        db, ib, dstep, istep = dbl.ctypes.data, ints.ctypes.data, 8 * n, 4 * n
+        dp = lambda row: C.cast(db + row * dstep, _dp)  # noqa: E731
+        ip = lambda row: C.cast(ib + row * istep, _ip)  # noqa: E731
         o = DualOut()
-        o.status, o.lambda_max = iptr(self.status), dptr(self.lambda_max)
+        o.status, o.lambda_max = ip(0), dp(0)
         for k in range(4):
-            o.x[k], o.v[k] = dptr(self.x[k]), dptr(self.v[k])
-        o.g, o.dg, o.rho, o.drho = dptr(self.g), dptr(self.dg), dptr(self.rho), dptr(self.drho)
-        o.naccept, o.nreject, o.flags = iptr(self.naccept), iptr(self.nreject), iptr(self.flags)
+            o.x[k], o.v[k] = dp(1 + k), dp(5 + k)
+        o.g, o.rho, o.dg, o.drho = dp(9), dp(10), dp(11), dp(11 + nd)
+        o.naccept, o.nreject, o.flags = ip(1), ip(2), ip(3)
         self.out = o
 
 
@@ -163,26 +168,30 @@ class EndpointArrays:
 
     def __init__(self, count, init=True, stats=True):
         n = int(count)
-        self.status = np.full(n, -1, np.int32)
-        self.lambda_max = np.zeros(n)
-        self.x = np.zeros((4, n))
-        self.v = np.zeros((4, n))
-        self.x_init = np.zeros((4, n)) if init else None
-        self.v_init = np.zeros((4, n)) if init else None
-        self.naccept = np.zeros(n, np.int32) if stats else None
-        self.nreject = np.zeros(n, np.int32) if stats else None
-        self.flags = np.zeros(n, np.int32) if stats else None
+        # one block per element type, pointers by address arithmetic: building ~20 numpy `.ctypes` views per ensemble
+        # cost more than tracing a thousand rays
+        dbl = np.zeros((17 if init else 9, n))
+        ints = np.zeros((4 if stats else 1, n), np.int32)
+        ints[0] = -1
+        self._blocks = (dbl, ints)
+        self.lambda_max, self.x, self.v = dbl[0], dbl[1:5], dbl[5:9]
+        self.x_init = dbl[9:13] if init else None
+        self.v_init = dbl[13:17] if init else None
+        self.status = ints[0]
+        self.naccept, self.nreject, self.flags = (ints[1], ints[2], ints[3]) if stats else (None, None, None)
+        db, ib, dstep, istep = dbl.ctypes.data, ints.ctypes.data, 8 * n, 4 * n
+        null_d, null_i = C.cast(None, _dp), C.cast(None, _ip)
         e = Endpoints()
-        e.status = iptr(self.status)
-        e.lambda_max = dptr(self.lambda_max)
+        e.status = C.cast(ib, _ip)
+        e.lambda_max = C.cast(db, _dp)
         for k in range(4):
-            e.x[k] = dptr(self.x[k])
-            e.v[k] = dptr(self.v[k])
-            e.x_init[k] = dptr(self.x_init[k]) if init else C.cast(None, _dp)
-            e.v_init[k] = dptr(self.v_init[k]) if init else C.cast(None, _dp)
-        e.naccept = iptr(self.naccept)
-        e.nreject = iptr(self.nreject)
-        e.flags = iptr(self.flags)
+            e.x[k] = C.cast(db + (1 + k) * dstep, _dp)
+            e.v[k] = C.cast(db + (5 + k) * dstep, _dp)
+            e.x_init[k] = C.cast(db + (9 + k) * dstep, _dp) if init else null_d
+            e.v_init[k] = C.cast(db + (13 + k) * dstep, _dp) if init else null_d
+        e.naccept = C.cast(ib + istep, _ip) if stats else null_i
+        e.nreject = C.cast(ib + 2 * istep, _ip) if stats else null_i
+        e.flags = C.cast(ib + 3 * istep, _ip) if stats else null_i
         self.c = e
 
 
