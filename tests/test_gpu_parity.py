@@ -753,3 +753,32 @@ def test_seeded_random_configurations(ensemble, seed):
     assert hit.sum() > 100
     print(f"random configuration {seed}: {type(m).__name__} {m.params()[:3]} r_obs {x[1]:.0f} theta {math.degrees(x[2]):.1f} disc ({d.inner_radius:.2f}, {d.outer_radius:.1f}): "
           f"band {band.mean():.3%}, {int(hit.sum())} disc hits")
+
+
+def _random_config_other_metrics(seed, ensemble):
+    """The generated-Jacobian metrics and the other geometries under the same protocol."""
+    rng = np.random.default_rng(9100 + seed)
+    k = seed % 3
+    if k == 0:
+        m = gb.JohannsenMetric(1.0, float(rng.uniform(-0.8, 0.8)), *(float(v) for v in rng.uniform(-0.3, 0.3, 4)))
+    elif k == 1:
+        m = gb.BumblebeeMetric(1.0, float(rng.uniform(-0.1, 0.1)), float(rng.uniform(-0.3, 0.5)))
+    else:
+        a, q = float(rng.uniform(-0.7, 0.7)), float(rng.uniform(0.0, 0.5))
+        m = gb.KerrNewmanMetric(1.0, a, q)
+    r_obs = float(10.0 ** rng.uniform(2.3, 3.0))
+    x = [0.0, r_obs, math.radians(float(rng.uniform(20.0, 85.0))), 0.0]
+    outer = float(rng.uniform(20.0, 50.0))
+    g = seed % 4
+    d = gb.ThinDisc(gb.isco(m), outer) if g in (0, 1) else (gb.ShakuraSunyaev(m, eddington_ratio=float(rng.uniform(0.1, 0.4))) if g == 2 else None)
+    cfg = common.render_config(m, x, d, 2.0 * r_obs + 200.0, 64, 64, (-1.2 * outer, 1.2 * outer), (-0.9 * outer, 0.9 * outer), ensemble=ensemble)
+    return m, x, d, cfg
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(9))
+def test_seeded_random_configurations_other_metrics(ensemble, seed):
+    m, x, d, cfg = _random_config_other_metrics(seed, ensemble)
+    p, ic, ref, gps, band = check_parity(cfg, f"random configuration (other metrics) {seed}", max_band=0.01)
+    print(f"random configuration (other metrics) {seed}: {type(m).__name__} {tuple(round(v, 3) for v in m.params()[:6])} r_obs {x[1]:.0f} theta {math.degrees(x[2]):.1f} "
+          f"{type(d).__name__}: band {band.mean():.3%}, status counts {np.bincount(ref.status, minlength=4)}")
