@@ -782,3 +782,29 @@ def test_seeded_random_configurations_other_metrics(ensemble, seed):
     p, ic, ref, gps, band = check_parity(cfg, f"random configuration (other metrics) {seed}", max_band=0.01)
     print(f"random configuration (other metrics) {seed}: {type(m).__name__} {tuple(round(v, 3) for v in m.params()[:6])} r_obs {x[1]:.0f} theta {math.degrees(x[2]):.1f} "
           f"{type(d).__name__}: band {band.mean():.3%}, status counts {np.bincount(ref.status, minlength=4)}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(4))
+def test_seeded_random_line_profiles(ensemble, seed):
+    """PolarPlane + hemisphere callback + fused binned line profile at random spin, inclination, emissivity index, radial
+    range and bin grid: L1(flux) against the oracle at the north-star tolerance."""
+    rng = np.random.default_rng(7700 + seed)
+    m = gb.KerrMetric(1.0, float(rng.uniform(-0.9, 0.998))) if seed % 2 == 0 else gb.JohannsenPsaltisMetric(1.0, float(rng.uniform(0.0, 0.8)), float(rng.uniform(0.0, 0.8)))
+    x = [0.0, 1000.0, math.radians(float(rng.uniform(10.0, 80.0))), 0.0]
+    max_re = float(rng.uniform(20.0, 80.0))
+    d = gb.ThinDisc(0.0, 400.0)
+    grid = (gb.GeometricGrid(), gb.LinearGrid(), gb.InverseGrid())[seed % 3]
+    plane = gb.PolarPlane(grid, Nr=96, Ntheta=96, r_min=1.0, r_max=5.0 * max_re)
+    nb = int(rng.integers(60, 300))
+    bins = np.linspace(0.05, 1.6, nb)
+    index = float(rng.uniform(2.0, 4.0))
+    cfg = tracing_configuration(m, x, plane, d, (0.0, 2000.0), callback=gb.domain_upper_hemisphere(), ensemble=ensemble)
+    p, ic = cfg.to_c()
+    _, flux = gb.lineprofile(bins, gb.PowerLawEmissivity(index), m, x, d, gb.BinningMethod(), plane=plane, lambda_max=2000.0, max_re=max_re, ensemble=ensemble)
+    emis = cabi.Emissivity(cabi.EMISSIVITY_POWERLAW, 0, index, None, None)
+    want = oracle.lineprofile(p, ic, emis, bins, cabi.LineProfileOpts(gb.isco(m), max_re, 1, 0))
+    l1 = np.abs(flux - want).sum()
+    print(f"random line profile {seed}: {type(m).__name__} {tuple(round(v, 3) for v in m.params()[:3])} theta {math.degrees(x[2]):.1f} index {index:.2f} max_re {max_re:.1f} {nb} bins "
+          f"{type(grid).__name__}: L1 = {l1:.2e}")
+    assert flux.sum() == pytest.approx(1.0, abs=1e-12) and l1 < 1e-4
