@@ -339,13 +339,35 @@ GB_HD inline bool gen_scan_needed(const GbParams& P, double r0, double cprev, do
     return true;
 }
 
+// Stage input u + dt sum_l a_{S+1,l+1} k_l with the stage number as a template parameter: the coefficients are immediates
+// and the k rows are read at constant offsets (the run-time loop over l cost a fifth of the forward-mode kernel's
+// instructions in index arithmetic, compares and branches).  Same order of operations as the run-time loop.
+GB_HD constexpr double gen_a(int s, int l) {
+    return s == 1 ? GB_A21_V
+         : s == 2 ? (l == 0 ? GB_A31_V : GB_A32_V)
+         : s == 3 ? (l == 0 ? GB_A41_V : l == 1 ? GB_A42_V : GB_A43_V)
+         : s == 4 ? (l == 0 ? GB_A51_V : l == 1 ? GB_A52_V : l == 2 ? GB_A53_V : GB_A54_V)
+         : s == 5 ? (l == 0 ? GB_A61_V : l == 1 ? GB_A62_V : l == 2 ? GB_A63_V : l == 3 ? GB_A64_V : GB_A65_V)
+                  : (l == 0 ? GB_A71_V : l == 1 ? GB_A72_V : l == 2 ? GB_A73_V : l == 3 ? GB_A74_V : l == 4 ? GB_A75_V : GB_A76_V);
+}
+template <int N, int S>
+GB_HD inline void gen_stage_input(const GD<N> u[8], double dt, const GD<N> k[7][8], GD<N> tmp[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (S == 1) tmp[i] = u[i] + (dt * gen_a(1, 0)) * k[0][i];
+        else {
+            GD<N> acc = gen_a(S, 0) * k[0][i];
+#pragma unroll
+            for (int l = 1; l < S; ++l) acc = acc + gen_a(S, l) * k[l][i];
+            tmp[i] = u[i] + dt * acc;
+        }
+    }
+}
+
 // REC: callable (double lambda, const GD<N> u[8]) invoked with the initial state and after every accepted step
 template <int N, int MK = -1, class REC>
 GB_HD inline void gen_trace_ray(const GbParams& P, const GD<N> u_init[8], double hgt, bool norm_partials, GenResult<N>& res, REC&& rec) {
     typedef GD<N> S;
-    const double A[7][6] = {{0, 0, 0, 0, 0, 0}, {GB_A21_V, 0, 0, 0, 0, 0}, {GB_A31_V, GB_A32_V, 0, 0, 0, 0}, {GB_A41_V, GB_A42_V, GB_A43_V, 0, 0, 0},
-                            {GB_A51_V, GB_A52_V, GB_A53_V, GB_A54_V, 0, 0}, {GB_A61_V, GB_A62_V, GB_A63_V, GB_A64_V, GB_A65_V, 0},
-                            {GB_A71_V, GB_A72_V, GB_A73_V, GB_A74_V, GB_A75_V, GB_A76_V}};
     const double BT[7] = {GB_BT1_V, GB_BT2_V, GB_BT3_V, GB_BT4_V, GB_BT5_V, GB_BT6_V, GB_BT7_V};
     const double abstol = P.abstol, reltol = P.reltol, dtmax = P.dtmax, dtmin = 2.220446049250313e-16, tstop = P.lam1;
     const double beta1 = 7.0 / 50.0, beta2 = 2.0 / 25.0, gamma = 9.0 / 10.0, qmin = 1.0 / 5.0, qmax = 10.0, qoldinit = 1e-4;
@@ -391,10 +413,13 @@ GB_HD inline void gen_trace_ray(const GbParams& P, const GD<N> u_init[8], double
 #pragma unroll 1 /* one copy of the right-hand side in the step loop: the loop body then stays inside the instruction cache */
 #endif
         for (int s = 1; s < 7; ++s) {
-            for (int i = 0; i < 8; ++i) {
-                S acc = (s == 1) ? S(0.0) : A[s][0] * k[0][i];
-                for (int l = 1; l < s; ++l) acc = acc + A[s][l] * k[l][i];
-                tmp[i] = (s == 1) ? u[i] + (dt * A[1][0]) * k[0][i] : u[i] + dt * acc;
+            switch (s) {
+            case 1: gen_stage_input<N, 1>(u, dt, k, tmp); break;
+            case 2: gen_stage_input<N, 2>(u, dt, k, tmp); break;
+            case 3: gen_stage_input<N, 3>(u, dt, k, tmp); break;
+            case 4: gen_stage_input<N, 4>(u, dt, k, tmp); break;
+            case 5: gen_stage_input<N, 5>(u, dt, k, tmp); break;
+            default: gen_stage_input<N, 6>(u, dt, k, tmp); break;
             }
             if (s == 6) for (int i = 0; i < 8; ++i) un[i] = tmp[i];
             rhs_g<N, MK>(P, tmp, k[s], s_, c_);
