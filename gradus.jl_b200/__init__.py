@@ -36,6 +36,7 @@ from .api import (  # noqa: F401
     StatusCodes,
     TabulatedEmissivity,
     ThickDisc,
+    PolishDoughnut,
     ThinDisc,
     TracingConfiguration,
     EndpointCache,

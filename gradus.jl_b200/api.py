@@ -226,6 +226,66 @@ class ThickDisc:
         cabi.check(cabi.load().gb200_set_cross_section(ctx, cabi.dptr(self.rho), cabi.dptr(self.height), len(self.rho)), ctx)
 
 
+class PolishDoughnut(ThickDisc):
+    """`PolishDoughnut(m; rₖ = 12, n = 0.21, init_r = 5)` (src/geometry/discs/polish-doughnut.jl): a pressure-supported torus
+    (Fuerst & Wu 2004; Younsi et al. 2012) whose surface is an isobar through the innermost radius.  As in the reference the
+    set-up runs on the host -- innermost radius = the root of dE/dr of the sub-Keplerian orbital energy, the isobar as a
+    2-D ODE in (r, θ) integrated with Tsit5 (dtmax = 5e-2, OrdinaryDiffEq's default tolerances, every step saved) -- and the
+    cross-section is the linear interpolation of height over the saved radii; that table is what the device receives
+    (GB200_GEOMETRY_THICK_TABLE), so it interpolates the same nodes the reference does.  Kerr only, as in the reference."""
+
+    def __init__(self, m, rk=12.0, n=0.21, init_r=5.0, lambda_max=40.0, dtmax=5e-2):
+        from . import hostmath
+        if not isinstance(m, KerrMetric):
+            raise ValueError("PolishDoughnut: the isobar differential is defined for KerrMetric only (polish-doughnut.jl:39)")
+        M, a = m.M, m.a
+
+        def omega(r, th):  # Ω of the circular orbit at the cylindrical radius, scaled by (rₖ / r sinθ)^n (:17-21)
+            rs = r * np.sin(th)
+            kep = math.sqrt(M) / (rs**1.5 + a * math.sqrt(M))  # CircularOrbits.Ω of Kerr in closed form (prograde)
+            return kep * (rk / rs) ** n
+
+        def energy(r):  # orbital_energy at θ = π/2 (:23-31); complex r for the complex-step derivative
+            g = hostmath.metric_components(m, r, math.pi / 2)
+            w = omega(r, math.pi / 2)
+            return -(g[0] + g[4] * w) / np.sqrt(-g[0] - 2 * g[4] * w - g[3] * w * w)
+
+        dE = lambda r: float(np.imag(energy(r + 1e-30j)) / 1e-30)  # noqa: E731
+        r0 = float(init_r)
+        for _ in range(100):  # Newton on dE/dr with a central second difference (Roots.find_zero((df, d2f), init_r))
+            h = 1e-5 * max(1.0, abs(r0))
+            step = dE(r0) / ((dE(r0 + h) - dE(r0 - h)) / (2 * h))
+            r0 -= step
+            if abs(step) < 1e-14 * max(1.0, abs(r0)):
+                break
+        self.rk, self.n = float(rk), float(n)
+
+        def rhs(u):  # isobar_differential (:39-52), Younsi et al. (2012) eqs. (30), (31)
+            r, th = u
+            inv_w = 1.0 / float(omega(r, th))
+            s, c = math.sin(th), math.cos(th)
+            sig, dlt = r * r + a * a * c * c, r * r - 2 * M * r + a * a
+            p1 = M * ((sig - 2 * r * r) / sig**2) * (inv_w - a * s) ** 2 + r * s * s
+            p2 = math.sin(2 * th) * ((M * r / sig**2) * (a * inv_w - (r * r + a * a)) ** 2 + dlt / 2)
+            d = 1.0 / (math.sqrt(dlt * p1 * p1 + p2 * p2) * math.sqrt(1.0 / (dlt / sig)))
+            return np.array([p2 * d, -p1 * d])
+
+        sol = hostmath.tsit5_solve(rhs, [r0, math.pi / 2], float(lambda_max), dtmax=float(dtmax), terminate=lambda u: u[0] * math.cos(u[1]) < 0)
+        r = np.array([u[0] for u in sol])
+        z = np.array([math.cos(u[1]) * u[0] for u in sol])
+        keep = z > 0
+        self.rho, self.height = np.ascontiguousarray(r[keep]), np.ascontiguousarray(z[keep])
+        if np.any(np.diff(self.rho) <= 0):
+            raise ValueError("PolishDoughnut: the isobar does not run monotonically outwards for these parameters")
+        self.inner_radius, self.outer_radius = r0, float(r.max())
+        self.f = self.cross_section
+
+    def cross_section(self, rho):
+        """`cross_section(d, ρ)` (:123-129): the interpolated height inside [inner_radius, outer_radius], zero outside."""
+        rho = np.asarray(rho, np.float64)
+        return np.where((rho >= self.inner_radius) & (rho <= self.rho[-1]), np.interp(rho, self.rho, self.height), 0.0)
+
+
 _SUPPORTED_GEOMETRY = (ThinDisc, ShakuraSunyaev, DatumPlane, ThickDisc)
 
 

@@ -12,6 +12,8 @@ All functions accept numpy arrays for r (complex allowed: the radial metric deri
 which is exact to rounding for these rational metrics)."""
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 from . import api
@@ -221,3 +223,58 @@ def proper_area(m, r, theta):
     """`_proper_area`, corona/emissivity.jl:170-174: 2π √(g_rr g_φφ)"""
     g = metric_components(m, r, theta)
     return 2 * np.pi * np.sqrt(g[1] * g[3])
+
+
+# --------------------------------------------------------------------------- a small host-side Tsit5 (set-up ODEs)
+_TS_A = [[], [0.161], [-0.008480655492356989, 0.335480655492357], [2.8971530571054935, -6.359448489975075, 4.3622954328695815],
+         [5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525],
+         [5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383],
+         [0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774]]
+_TS_BT = [-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629, 0.5823571654525552,
+          -0.45808210592918697, 0.015151515151515152]
+
+
+def tsit5_solve(f, u0, t_end, *, dtmax, abstol=1e-6, reltol=1e-3, terminate=None, maxiters=100000):
+    """`solve(ODEProblem(f, u0, (0, t_end)), Tsit5(); dtmax, callback = DiscreteCallback(terminate, terminate!))` with
+    OrdinaryDiffEq's defaults (abstol 1e-6, reltol 1e-3, PI controller, Hairer-Wanner initial step), every accepted step
+    saved: the set-up ODEs of the reference that run on the host (the isobar of `PolishDoughnut`,
+    src/geometry/discs/polish-doughnut.jl:66-100).  Returns the list of saved states (initial state first)."""
+    u = np.asarray(u0, np.float64)
+    norm = lambda x: math.sqrt(float(np.mean(x * x)))  # noqa: E731  (ODE_DEFAULT_NORM)
+    t, f0 = 0.0, np.asarray(f(u), np.float64)
+    sk = abstol + np.abs(u) * reltol
+    d0, d1 = norm(u / sk), norm(f0 / sk)
+    dt0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+    dt0 = min(dt0, dtmax)
+    f1 = np.asarray(f(u + dt0 * f0), np.float64)
+    d2 = norm((f1 - f0) / sk) / dt0
+    md = max(d1, d2)
+    dt1 = max(1e-6, dt0 * 1e-3) if md <= 1e-15 else 10.0 ** (-(2.0 + math.log10(md)) / 5.0)
+    dt = min(100.0 * dt0, dt1, dtmax)
+    beta1, beta2, gamma, qmin, qmax, qold = 7.0 / 50.0, 2.0 / 25.0, 0.9, 0.2, 10.0, 1e-4
+    out, k1 = [u.copy()], f0
+    for _ in range(maxiters):
+        dt = min(dt, t_end - t)
+        ks = [k1]
+        for s in range(1, 7):
+            acc = sum(a * kk for a, kk in zip(_TS_A[s], ks))
+            ks.append(np.asarray(f(u + dt * acc), np.float64))
+        unew = u + dt * sum(a * kk for a, kk in zip(_TS_A[6], ks[:6]))
+        err = dt * sum(b * kk for b, kk in zip(_TS_BT, ks))
+        eest = norm(err / (abstol + np.maximum(np.abs(u), np.abs(unew)) * reltol))
+        if eest == 0.0:
+            q = 1.0 / qmax
+        else:
+            q11 = eest**beta1
+            q = max(1.0 / qmax, min(1.0 / qmin, q11 / qold**beta2 / gamma))
+        if eest > 1.0:
+            dt = dt / min(1.0 / qmin, q11 / gamma)
+            continue
+        qold = max(eest, 1e-4)
+        t += dt
+        u, k1 = unew, ks[6]
+        out.append(u.copy())
+        if (terminate is not None and terminate(u)) or t >= t_end:
+            break
+        dt = min(dt / q, dtmax)
+    return out

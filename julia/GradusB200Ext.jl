@@ -114,7 +114,35 @@ _geometry(::Nothing) = (Int32(0), (0.0, 0.0, 0.0, 0.0))
 _geometry(d::ThinDisc) = (Int32(1), (Float64(d.inner_radius), Float64(d.outer_radius), 0.0, 0.0))
 _geometry(d::ShakuraSunyaev) = (Int32(2), (Float64(d.Ṁ_Ṁedd), Float64(d.inv_η), Float64(d.inner_radius), 0.0))
 _geometry(d::DatumPlane) = (Int32(3), (Float64(d.height), 0.0, 0.0, 0.0))
+# thick discs whose height is a closure (`ThickDisc(f)`, `PolishDoughnut`: src/geometry/discs/thick-disc.jl:32-63,
+# polish-doughnut.jl:102-129) cross the ABI as a table (GB200_GEOMETRY_THICK_TABLE); `_install_geometry` uploads it
+_geometry(d::Gradus.AbstractThickAccretionDisc) = begin
+    ρ, h = _cross_section_table(d)
+    (Int32(4), (maximum(h), first(ρ), last(ρ), 0.0))
+end
 _geometry(d) = throw(ArgumentError("geometry $(typeof(d)) is outside the EnsembleB200 scope"))
+
+const _THICK_TABLES = IdDict{Any,Tuple{Vector{Float64},Vector{Float64}}}()
+function _cross_section_table(d::Gradus.AbstractThickAccretionDisc; n = 4097)
+    get!(_THICK_TABLES, d) do
+        if d isa Gradus.PolishDoughnut        # `d.f` is a linear interpolation already: its own nodes
+            return (collect(Float64, d.f.t), collect(Float64, d.f.u))
+        end
+        lo, hi = Float64(d.inner_radius), Float64(d.outer_radius)
+        (isfinite(lo) && isfinite(hi) && hi > lo) ||
+            throw(ArgumentError("EnsembleB200 tabulates cross_section(d, ρ) over [inner_radius, outer_radius]: give the disc finite radii"))
+        # Chebyshev nodes crowd towards the ends as 1/n^2, which resolves the square-root edges of tori
+        ρ = [0.5 * (lo + hi) - 0.5 * (hi - lo) * cospi((k - 1) / (n - 1)) for k = 1:n]
+        ρ[1], ρ[end] = lo, hi
+        (ρ, Float64[Gradus.cross_section(d, r) for r in ρ])
+    end
+end
+_install_geometry(ctx, d) = nothing
+function _install_geometry(ctx, d::Gradus.AbstractThickAccretionDisc)
+    d isa ShakuraSunyaev && return nothing
+    ρ, h = _cross_section_table(d)
+    _check(ccall((:gb200_set_cross_section, libgradus_b200), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32), ctx, ρ, h, length(ρ)), ctx)
+end
 
 # Julia names a closure type "#name#NN": recognise the reference's closures by the stem of that name.
 _closure_is(f, stem::AbstractString) = startswith(string(nameof(typeof(f))), "#" * stem)
@@ -285,6 +313,7 @@ function Gradus.ensemble_solve_tracing_problem(
     end
     GC.@preserve keep outs begin
         _foreach_device(ensemble, ranges) do d, ctx, r
+            _install_geometry(ctx, config.geometry)
             o = outs[d]
             ep = CEndpoints(pointer(o.status), pointer(o.λ), Tuple(pointer.(o.x)), Tuple(pointer.(o.v)), Tuple(pointer.(o.x0)),
                             Tuple(pointer.(o.v0)), C_NULL, C_NULL, C_NULL)
@@ -344,6 +373,7 @@ function Gradus.render_into_image!(image, trace::AbstractTrace, config::_B200Con
     ranges = _ranges(ic, length(ensemble.devices))
     pfs = Int32[pf.kind]
     if length(ranges) == 1          # the whole image in ray order: write straight into `image`
+        _install_geometry(_context(ensemble, 1), config.geometry)
         GC.@preserve keep image pfs begin
             imgs = [pointer(image)]
             _check(ccall((:gb200_render, libgradus_b200), Cint,
@@ -354,6 +384,7 @@ function Gradus.render_into_image!(image, trace::AbstractTrace, config::_B200Con
         parts = [Vector{T}(undef, r.count) for r in ranges]
         GC.@preserve keep parts pfs begin
             _foreach_device(ensemble, ranges) do d, ctx, r
+                _install_geometry(ctx, config.geometry)
                 imgs = [pointer(parts[d])]
                 _check(ccall((:gb200_render, libgradus_b200), Cint,
                              (Ptr{Cvoid}, Ref{CProblem}, Ref{CIC}, Ref{CRange}, Ptr{Int32}, Int32, Ptr{Cvoid}, Ptr{Ptr{Float64}}),
@@ -396,6 +427,7 @@ function lineprofile_b200(bins, ε, m::Gradus.AbstractMetric{T}, u, d;
         opts = CLineProfileOpts(minrₑ, maxrₑ, 1, 0)
         if length(ensemble.devices) == 1
             ctx = _context(ensemble, 1)
+            _install_geometry(ctx, d)
             _check(ccall((:gb200_lineprofile, libgradus_b200), Cint,
                          (Ptr{Cvoid}, Ref{CProblem}, Ref{CIC}, Ref{CRange}, Ref{CEmissivity}, Ptr{Cvoid}, Ptr{Float64}, Int32, Ref{CLineProfileOpts}, Ptr{Float64}),
                          ctx, p, ic, CRange(0, ic.n, 1, 1), emis, C_NULL, binsv, length(binsv), opts, flux), ctx)
@@ -404,6 +436,9 @@ function lineprofile_b200(bins, ε, m::Gradus.AbstractMetric{T}, u, d;
             devs = Int32.(ensemble.devices)
             _check(ccall((:gb200_comm_init, libgradus_b200), Cint, (Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}), devs, length(devs), comm), C_NULL)
             try
+                for i = 0:length(devs)-1   # a thick disc's table goes to every context of the communicator
+                    _install_geometry(ccall((:gb200_comm_context, libgradus_b200), Ptr{Cvoid}, (Ptr{Cvoid}, Int32), comm[], i), d)
+                end
                 _check(ccall((:gb200_comm_lineprofile, libgradus_b200), Cint,
                              (Ptr{Cvoid}, Ref{CProblem}, Ref{CIC}, Ref{CEmissivity}, Ptr{Cvoid}, Ptr{Float64}, Int32, Ref{CLineProfileOpts}, Ptr{Float64}),
                              comm[], p, ic, emis, C_NULL, binsv, length(binsv), opts, flux), C_NULL)

@@ -319,3 +319,43 @@ def test_device_thick_disc_table(ensemble):
     rho = got.x[1, hit] * np.abs(np.sin(got.x[2, hit]))
     z = got.x[1, hit] * np.abs(np.cos(got.x[2, hit]))
     assert np.quantile(np.abs(z - d.cross_section(rho)), 0.99) < 1e-9
+
+
+# --------------------------------------------------------------------------- PolishDoughnut (src/geometry/discs/polish-doughnut.jl)
+def test_polish_doughnut_cross_section_fingerprint():
+    """test/discs/test-polish-doughnut.jl: the cross-section map of the default torus around Kerr a = 0.2 (atol 1e-5 there).
+    The host set-up restates the reference's (innermost radius by Newton on dE/dr, isobar by Tsit5 with dtmax = 5e-2 and
+    OrdinaryDiffEq's defaults, linear interpolation over the saved steps): the literal is reproduced to 1e-11."""
+    d = gb.PolishDoughnut(gb.KerrMetric(1.0, 0.2), rk=12.0, n=0.21)
+    h = d.cross_section(np.linspace(10.0, 15.0, 200))
+    assert h.sum() == pytest.approx(219.97440610254944, abs=1e-9)
+    assert d.inner_radius == pytest.approx(10.0875, abs=1e-4) and 14.7 < d.outer_radius < 14.71
+    assert np.all(np.diff(d.rho) > 0) and d.height[0] < 1e-12 and 1.5 < d.height.max() < 1.6
+    with pytest.raises(ValueError):
+        gb.PolishDoughnut(gb.JohannsenMetric())
+
+
+@pytest.mark.gpu
+def test_device_polish_doughnut(ensemble):
+    """The torus as a device geometry: its node table crosses the ABI (GB200_GEOMETRY_THICK_TABLE), so the device interpolates
+    the nodes the reference interpolates.  Main parity protocol against the oracle with the same table."""
+    m = gb.KerrMetric(1.0, 0.2)
+    d = gb.PolishDoughnut(m)
+    oracle.set_cross_section(d.rho, d.height)
+    x = [0.0, 1000.0, math.radians(75), 0.0]
+    cfg = render_config(m, x, d, 2000.0, 96, 96, (-22, 22), (-12, 12), ensemble=ensemble)
+    p, ic = cfg.to_c()
+    assert p.geometry_kind == cabi.GEOMETRY_THICK_TABLE
+    ref = oracle.trace(p, ic)
+    ref_l = oracle.trace(p, ic, precision=1)
+    band = oracle.band_ratio(p, ic)
+    graze = ((band > 0) & (band < 1.3)) | (ref.status != ref_l.status)
+    got = api.solve_tracing_problem(cfg)
+    ok = ~graze
+    assert graze.mean() < 0.02 and np.array_equal(np.asarray(got.status)[ok], ref.status[ok])
+    hit = ok & (ref.status == cabi.STATUS_INTERSECTED)
+    assert hit.sum() > 1000
+    assert np.max(np.abs(got.x[1:3, hit] - ref.x[1:3, hit]) / np.maximum(np.abs(ref.x[1:3, hit]), 1e-3)) < 1e-6
+    rho = got.x[1, hit] * np.abs(np.sin(got.x[2, hit]))
+    z = got.x[1, hit] * np.abs(np.cos(got.x[2, hit]))
+    assert np.quantile(np.abs(z - d.cross_section(rho)), 0.99) < 1e-8  # the hits sit on the torus surface
