@@ -155,3 +155,27 @@ def test_device_profile_equals_oracle_profile_and_batches_are_independent():
             assert np.max(np.abs(got.eps[inner] / want.eps[inner] - 1)) < 1e-4
             assert np.max(np.abs(got.t - want.t)) < 1e-5
         assert dev_table is None or dev_table is api._PLUNGING_CACHE.get(key)
+
+
+# --------------------------------------------------------------------------- test/disc-profiles/test-beamedpointsource.jl
+def _beamed_vs_lamp_post(solver=None):
+    m, d = gb.KerrMetric(1.0, 0.998), gb.ThinDisc(0.0, 100.0)
+    p0 = corona.emissivity_profile(m, d, corona.LampPostModel(h=10.0), n_samples=100, solver=solver)
+    p1 = corona.emissivity_profile(m, d, corona.BeamedPointSource(10.0, 0.0), n_samples=100, solver=solver)
+    radii = np.linspace(2.0, 100.0, 10)
+    return p0.emissivity_at(radii), p1.emissivity_at(radii)
+
+
+def test_beamed_point_source_at_rest_is_a_lamp_post_with_the_oracle_tracer(oracle_plunging_kerr):
+    """A `BeamedPointSource` with β = 0 at r = 10 (θ = 1e-4) against the lamp post at h = 10: the reference asserts rtol 1e-1
+    on ten radii (test/disc-profiles/test-beamedpointsource.jl:18-19)."""
+    e0, e1 = _beamed_vs_lamp_post(common.oracle_solver)
+    assert np.all(e0 > 0) and np.allclose(e0, e1, rtol=1e-1)
+
+
+@pytest.mark.gpu
+def test_beamed_point_source_at_rest_is_a_lamp_post_on_the_device():
+    e0, e1 = _beamed_vs_lamp_post()
+    assert np.all(e0 > 0) and np.allclose(e0, e1, rtol=1e-1)
+    o0, o1 = _beamed_vs_lamp_post(common.oracle_solver)
+    assert np.allclose(e0, o0, rtol=1e-3) and np.allclose(e1, o1, rtol=1e-3)  # interpolated profiles; grazing rays may differ in class
