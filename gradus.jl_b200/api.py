@@ -199,6 +199,26 @@ class ShakuraSunyaev:
         return np.where(rho < self.inner_radius, -0.0, h)
 
 
+def cartesian_tangent_vector(d, rho):
+    """`_cartesian_tangent_vector(d, ρ)` (src/geometry/discs/thick-disc.jl:65-72): the unit tangent of the disc surface
+    (ρ, 0, cross_section(ρ)) in the x-z plane; the derivative the reference takes by ForwardDiff is a complex step here for
+    the Shakura-Sunyaev height and a central difference for closures."""
+    rho = float(rho)
+    if isinstance(d, ShakuraSunyaev):
+        dh = 0.0 if rho < d.inner_radius else 3.0 * d.inv_eta * d.Mdot_Medd * 0.5 * math.sqrt(d.inner_radius / rho) / rho
+    else:
+        h = 1e-6 * max(1.0, abs(rho))
+        dh = float(d.cross_section(rho + h) - d.cross_section(rho - h)) / (2 * h)
+    v = np.array([1.0, 0.0, dh])
+    return v / np.linalg.norm(v)
+
+
+def cartesian_surface_normal(d, rho):
+    """`_cartesian_surface_normal(d, ρ)` (thick-disc.jl:74-78): the tangent rotated by 90° about φ̂."""
+    t = cartesian_tangent_vector(d, rho)
+    return np.array([-t[2], t[1], t[0]])
+
+
 class ThickDisc:
     """`ThickDisc(f; inner_radius, outer_radius)` (src/geometry/discs/thick-disc.jl:32-52): a disc whose height above the
     equatorial plane is the closure `f(ρ)` (non-positive where there is no disc).  A closure cannot cross the C ABI, so it is

@@ -359,3 +359,13 @@ def test_device_polish_doughnut(ensemble):
     rho = got.x[1, hit] * np.abs(np.sin(got.x[2, hit]))
     z = got.x[1, hit] * np.abs(np.cos(got.x[2, hit]))
     assert np.quantile(np.abs(z - d.cross_section(rho)), 0.99) < 1e-8  # the hits sit on the torus surface
+
+
+def test_shakura_sunyaev_surface_tangents():
+    """test/discs/test-geometry.jl: unit tangents of the Shakura-Sunyaev surface around Kerr a = 0.9 (atol 1e-5 there)."""
+    d = gb.ShakuraSunyaev(gb.KerrMetric(1.0, 0.9))
+    assert np.allclose(api.cartesian_tangent_vector(d, 2.6), [0.689693957000099, 0.0, 0.724100991352412], atol=1e-5)
+    assert np.allclose(api.cartesian_tangent_vector(d, 6.6), [0.9679192396299138, 0.0, 0.2512615083021063], atol=1e-5)
+    assert np.allclose(api.cartesian_tangent_vector(d, 1.0), [1.0, 0.0, 0.0], atol=1e-5)
+    n = api.cartesian_surface_normal(d, 6.6)
+    assert abs(np.dot(n, api.cartesian_tangent_vector(d, 6.6))) < 1e-15 and n[2] > 0
