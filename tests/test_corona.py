@@ -179,3 +179,18 @@ def test_beamed_point_source_at_rest_is_a_lamp_post_on_the_device():
     assert np.all(e0 > 0) and np.allclose(e0, e1, rtol=1e-1)
     o0, o1 = _beamed_vs_lamp_post(common.oracle_solver)
     assert np.allclose(e0, o0, rtol=1e-3) and np.allclose(e1, o1, rtol=1e-3)  # interpolated profiles; grazing rays may differ in class
+
+
+def test_lorentz_factor_and_proper_area_against_the_closed_forms():
+    """test/unit/flux-calculations.jl: Keplerian Lorentz factor (Dauser+13) and the proper area of an annulus
+    (Wilkins & Fabian 2012) on the reference's 100-point geometric grid, `≈` (rtol 1.5e-8) there."""
+    m = gb.KerrMetric(1.0, 0.998)
+    a = m.a
+    r = np.geomspace(api.isco(m), 1000.0, 100)
+    v = np.array([hostmath.circular_fourvelocity(m, ri) for ri in r]).T
+    gamma = hostmath.lorentz_factor(m, r, math.pi / 2, v)
+    A = np.sqrt(r**2 - 2 * r + a**2) * (r**1.5 + a)
+    B = np.sqrt(r * np.sqrt(r) + 2 * a - 3 * np.sqrt(r)) * np.sqrt(r**3 + a**2 * r + 2 * a**2) * r**0.25
+    assert np.allclose(gamma, A / B, rtol=1e-9)
+    area = 2 * np.pi * np.sqrt((r**4 + a**2 * r**2 + 2 * a**2 * r) / (r**2 - 2 * r + a**2))
+    assert np.allclose(hostmath.proper_area(m, r, math.pi / 2), area, rtol=1e-12)
