@@ -63,6 +63,15 @@ def sample_position_velocity(m, model):
     raise ValueError(f"corona model {type(model).__name__} has no position/velocity sampler here")
 
 
+def _radial_angles(generator, n_samples):
+    idx = np.arange(1, n_samples + 1, dtype=np.float64)
+    if generator == "golden":
+        return idx, math.pi * (1 + math.sqrt(5.0)) * idx
+    if generator == "even":
+        return idx / n_samples, 2 * math.pi * (idx / n_samples)
+    raise ValueError("generator must be 'golden' or 'even'")
+
+
 @dataclass(frozen=True)
 class EvenSampler:
     """`EvenSampler(domain, generator)` (samplers.jl:8-16): domain "lower" | "both", generator "golden" | "even".
@@ -72,21 +81,34 @@ class EvenSampler:
     generator: str = "golden"
 
     def angles(self, n_samples):
-        idx = np.arange(1, n_samples + 1, dtype=np.float64)
-        if self.generator == "golden":
-            i = idx
-            radial = math.pi * (1 + math.sqrt(5.0)) * i
-        elif self.generator == "even":
-            i = idx / n_samples
-            radial = 2 * math.pi * i
-        else:
-            raise ValueError("generator must be 'golden' or 'even'")
+        i, radial = _radial_angles(self.generator, n_samples)
         u = i / n_samples
         if self.domain == "both":
             elev = np.arccos(np.clip(1 - 2 * u, -1.0, 1.0))
         elif self.domain == "lower":
             elev = np.arccos(np.clip(1 - u, -1.0, 1.0))
         else:
+            raise ValueError("domain must be 'lower' or 'both'")
+        return elev, np.mod(radial, 2 * math.pi)
+
+
+@dataclass(frozen=True)
+class WeierstrassSampler:
+    """`WeierstrassSampler(res, domain, generator)` (samplers.jl:17-28, 42-54): elevations 2 atan(√(res / i)) -- the inverse
+    stereographic projection of a spiral in the plane --, alternating between the hemispheres for domain "both"."""
+
+    res: float = 100.0
+    domain: str = "lower"
+    generator: str = "golden"
+
+    def angles(self, n_samples):
+        i, radial = _radial_angles(self.generator, n_samples)
+        elev = 2.0 * np.arctan(np.sqrt(self.res / i))
+        if self.domain == "both":
+            # `iseven(i)` of the generator's index: the ray counter for the golden spiral, i / N (never an even integer) otherwise
+            even = (np.arange(1, n_samples + 1) % 2 == 0) if self.generator == "golden" else np.zeros(n_samples, bool)
+            elev = np.where(even, elev, math.pi - elev)
+        elif self.domain != "lower":
             raise ValueError("domain must be 'lower' or 'both'")
         return elev, np.mod(radial, 2 * math.pi)
 

@@ -194,3 +194,32 @@ def test_lorentz_factor_and_proper_area_against_the_closed_forms():
     assert np.allclose(gamma, A / B, rtol=1e-9)
     area = 2 * np.pi * np.sqrt((r**4 + a**2 * r**2 + 2 * a**2 * r) / (r**2 - 2 * r + a**2))
     assert np.allclose(hostmath.proper_area(m, r, math.pi / 2), area, rtol=1e-12)
+
+
+def test_weierstrass_sampler_follows_the_reference():
+    """samplers.jl:42-54: 2 atan(sqrt(res / i)); both hemispheres alternate with the parity of the generator's index."""
+    s = corona.WeierstrassSampler(res=100.0, domain="lower", generator="golden")
+    el, az = s.angles(5)
+    assert np.allclose(el, 2 * np.arctan(np.sqrt(100.0 / np.arange(1, 6))))
+    assert np.allclose(az, np.mod(math.pi * (1 + math.sqrt(5.0)) * np.arange(1, 6), 2 * math.pi))
+    el2, _ = corona.WeierstrassSampler(domain="both").angles(4)
+    assert np.allclose(el2, [math.pi - el[0], el[1], math.pi - el[2], el[3]])
+    e_even, a_even = corona.EvenSampler("lower", "even").angles(4)
+    assert np.allclose(e_even, np.arccos(1 - np.array([1, 2, 3, 4]) / 16.0)) and np.allclose(a_even, np.mod(2 * math.pi * np.array([1, 2, 3, 4]) / 4.0, 2 * math.pi))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sampler", [corona.EvenSampler("lower", "golden"), corona.EvenSampler("both", "even"), corona.WeierstrassSampler(domain="lower"),
+                                     corona.WeierstrassSampler(domain="both", generator="even")])
+def test_corona_models_trace_with_every_sampler(sampler):
+    """test/smoke-tests/tracegeodesics.jl:44-66 (corona-models): 32-ray fans of a lamp post for every sampler / generator /
+    hemisphere combination that has a deterministic counterpart here."""
+    m = gb.KerrMetric(1.0, 0.0)
+    d = gb.ThinDisc(gb.isco(m), 50.0)
+    cg = corona.tracecorona(m, d, corona.LampPostModel(h=10.0, theta=math.radians(0.001)), lambda_max=200.0, n_samples=32, sampler=sampler)
+    hits = cg.geodesic_points["x"]
+    # only the rays that reach the disc are kept; the 32 rays of the even generator (elevations acos(1 - 2 i / N^2), the
+    # reference's index quirk) and of the Weierstrass spiral at res = 100 (elevations beyond 90 degrees for i < res) miss it
+    assert hits.shape[0] == 4 and hits.shape[1] <= 32 and (hits.shape[1] > 0 or not (isinstance(sampler, corona.EvenSampler) and sampler.generator == "golden"))
+    rho = hits[1] * np.abs(np.sin(hits[2]))
+    assert np.all((rho >= gb.isco(m) * (1 - 1e-9)) & (rho <= 50.0 * (1 + 1e-9)))
