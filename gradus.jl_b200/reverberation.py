@@ -157,3 +157,24 @@ def continuum_time(m, x, model, **kwargs):
     _, _, gp, _ = api.optimize_for_target(pos[1:], m, x, **kwargs)
     return float(gp["x"][0])
 
+
+
+def lag_frequency(t, f, *, flo=5e-5, R=1.0):
+    """`lag_frequency(t, f::AbstractMatrix; flo)` (src/reverberation.jl:29-49): the impulse response ψ(t) = Σ_E f[E, t] (NaNs as
+    zeros) is padded with zeros out to 1 / flo on the same time step, Fourier transformed, and the phase
+    atan(Im ψ̂ / (1 + Re ψ̂)) of the positive frequencies becomes a time lag φ / (2π ν).  Returns (frequencies, −lag); the
+    zero-frequency entry is 0 / 0 as in the reference.  Host FFT of a ~20 000-point array."""
+    t = np.asarray(t, np.float64)
+    f = np.asarray(f, np.float64)
+    psi = np.nansum(f, axis=0) if f.ndim == 2 else np.where(np.isnan(f), 0.0, f)
+    dt = t[1] - t[0]
+    t_ext = np.arange(t.min(), 1.0 / flo + 0.5 * dt * 1e-9, dt)  # range(minimum(t), 1 / flo, step = Δt)
+    psi_ext = np.zeros(t_ext.size)
+    psi_ext[: psi.size] = psi
+    freq = np.fft.fftfreq(t_ext.size, dt)
+    F = R * np.fft.fft(psi_ext)
+    n = t_ext.size // 2
+    phase = np.arctan(F[:n].imag / (1.0 + F[:n].real))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lag = phase / (2.0 * np.pi * freq[:n])
+    return freq[:n], -lag

@@ -118,3 +118,46 @@ def test_device_bucket2d_equals_the_host_bucket_and_ignores_the_order(ensemble):
     tb2, eb2, td = rv.bin_transfer_function(t[ok], e[ok], f[ok], ensemble=ensemble)
     _, _, td_host = rv.bin_transfer_function(t[ok], e[ok], f[ok])
     assert np.array_equal(np.isnan(td), np.isnan(td_host)) and np.nanmax(np.abs(td - td_host)) < 1e-12 * np.nanmax(td_host)
+
+
+# --------------------------------------------------------------------------- test/smoke-tests/reverberation.jl
+REF_FREQ_SUM = 2449.8787687490535   # reverberation.jl:44, rtol 1e-2
+REF_TAU_132 = 9.322742661315855     # reverberation.jl:45, rtol 1e-2
+
+
+def run_lag_frequency_smoke(solver=None, prober_cls=None, tracer=None):
+    """The reference's lag-frequency smoke test end to end: lamp-post emissivity profile (500 rays), continuum time through
+    the target solver, ten Cunningham transfer functions on the inverse grid, time-resolved quadrature, FFT."""
+    m = gb.KerrMetric(1.0, 0.998)
+    x = [0.0, 10_000.0, math.radians(45), 0.0]
+    d = gb.ThinDisc(0.0, float("inf"))
+    model = corona.LampPostModel()
+    radii = ti.inverse_grid(gb.isco(m), 100.0, 10)
+    kw = {} if prober_cls is None else {"prober": prober_cls(m, x, d)}
+    itb = ti.transferfunctions(m, x, d, radii=radii, beta0=2.0, **kw)
+    prof = corona.emissivity_profile(m, d, model, n_samples=500, solver=solver)
+    tkw = {} if tracer is None else {"tracer": tracer, "grid": 17}
+    t0 = rv.continuum_time(m, x, model, **tkw)
+    bins, tbins = np.linspace(0.0, 1.5, 100), np.linspace(0.0, 100.0, 100)
+    flux = ti.integrate_lagtransfer(prof, itb, bins, tbins, t0=t0, n_radii=100, h=1e-8, rmin=radii.min(), rmax=radii.max())
+    flux[flux == 0] = np.nan
+    return t0, rv.lag_frequency(tbins, flux)
+
+
+def check_lag_frequency(t0, freq, tau):
+    assert freq.sum() == pytest.approx(REF_FREQ_SUM, rel=1e-2)
+    assert tau[131] == pytest.approx(REF_TAU_132, rel=1e-2)
+    # light travel time from h = 5 on the axis to an observer at r = 10^4, 45 degrees: flat-space distance + Shapiro delay
+    flat = math.sqrt(1e8 + 25.0 - 2 * 1e4 * 5.0 * math.cos(math.radians(45)))
+    assert flat < t0 < flat + 4.0 * math.log(1e4 / 5.0) + 5.0
+
+
+def test_lag_frequency_smoke_with_the_oracle_tracer(oracle_plunging_kerr):
+    t0, (freq, tau) = run_lag_frequency_smoke(common.oracle_solver, common.OracleProber, common.oracle_target_tracer)
+    check_lag_frequency(t0, freq, tau)
+
+
+@pytest.mark.gpu
+def test_lag_frequency_smoke_on_the_device():
+    t0, (freq, tau) = run_lag_frequency_smoke()
+    check_lag_frequency(t0, freq, tau)
