@@ -369,3 +369,17 @@ def test_shakura_sunyaev_surface_tangents():
     assert np.allclose(api.cartesian_tangent_vector(d, 1.0), [1.0, 0.0, 0.0], atol=1e-5)
     n = api.cartesian_surface_normal(d, 6.6)
     assert abs(np.dot(n, api.cartesian_tangent_vector(d, 6.6))) < 1e-15 and n[2] > 0
+
+
+def test_special_radii_and_circular_orbit_literals():
+    """test/smoke-tests/special-radii.jl:27-41 (Johannsen ISCOs, atol 1e-5 there) and test/smoke-tests/circular-orbits.jl:15-24
+    (sum of the circular-orbit v^phi over r = 6:0.5:10, atol 1e-6 there; the reference finds each v^phi by minimising the
+    radial excursion of a traced orbit -- the closed form of `CircularOrbits` lands on the same numbers)."""
+    assert api.isco(gb.JohannsenMetric(1.0, 0.998, alpha13=1.0)) == pytest.approx(2.8482863127671534, abs=1e-9)
+    assert api.isco(gb.JohannsenMetric(1.0, 0.998, alpha22=1.0)) == pytest.approx(1.1306596884484472, abs=1e-9)
+    assert api.isco(gb.KerrMetric(1.0, 0.0)) == 6.0 and api.isco(gb.KerrMetric(1.0, 1.0)) == pytest.approx(1.0, abs=1e-12)
+    rs = np.arange(6.0, 10.01, 0.5)
+    for m, literal in [(gb.KerrMetric(1.0, 0.0), 0.5432533297869712), (gb.KerrMetric(1.0, 1.0), 0.5016710246454921),
+                       (gb.KerrMetric(1.0, -1.0), 0.5993458160081419), (gb.JohannsenMetric(1.0, 1.0, alpha22=1.0), 0.4980454719932759)]:
+        total = sum(hostmath.circular_fourvelocity(m, r)[3] for r in rs)
+        assert total == pytest.approx(literal, abs=1e-6)  # measured 2e-10 ... 9.8e-7 (the optimiser's own tolerance)
