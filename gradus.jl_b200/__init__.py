@@ -24,6 +24,7 @@ from .api import (  # noqa: F401
     InverseGrid,
     BumblebeeMetric,
     MorrisThorneWormhole,
+    DilatonAxion,
     JohannsenMetric,
     JohannsenPsaltisMetric,
     KerrNewmanMetric,

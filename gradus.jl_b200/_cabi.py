@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libgradus_b200.so")
 OK = 0
 ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = -1, -2, -3, -4, -5
 STATUS_OUT_OF_DOMAIN, STATUS_WITHIN_INNER_BOUNDARY, STATUS_INTERSECTED, STATUS_NO_STATUS = 0, 1, 2, 3
-METRIC_KERR, METRIC_JP, METRIC_JOHANNSEN, METRIC_BUMBLEBEE, METRIC_KERR_NEWMAN, METRIC_MORRIS_THORNE = 0, 1, 2, 3, 4, 5
+METRIC_KERR, METRIC_JP, METRIC_JOHANNSEN, METRIC_BUMBLEBEE, METRIC_KERR_NEWMAN, METRIC_MORRIS_THORNE, METRIC_DILATON_AXION = 0, 1, 2, 3, 4, 5, 6
 GEOMETRY_NONE, GEOMETRY_THIN_DISC, GEOMETRY_SHAKURA_SUNYAEV, GEOMETRY_DATUM_PLANE, GEOMETRY_THICK_TABLE = 0, 1, 2, 3, 4
 GEOMETRY_TARGET_POINT = 5  # gb200_trace_target only
 CALLBACK_NONE, CALLBACK_UPPER_HEMISPHERE = 0, 1

@@ -119,11 +119,34 @@ class MorrisThorneWormhole:
         return _pad8(self.b)
 
 
+@dataclass(frozen=True)
+class DilatonAxion:
+    """src/metrics/dilaton-axion-ad.jl:48-72: Einstein-Maxwell-Dilaton-Axion metric (Garcia et al. 1995); `beta` is the
+    reference's β (dilaton coupling), `b` the axion coupling.  The ratios β/b, β/a, β/(a b) follow the reference's rule
+    (0 where β == 0, :24-26) and travel as parameters 4..6."""
+
+    M: float = 1.0
+    a: float = 0.5
+    beta: float = 0.0
+    b: float = 1.0
+    kind = cabi.METRIC_DILATON_AXION
+
+    def ratios(self):
+        if self.beta == 0.0:
+            return 0.0, 0.0, 0.0
+        if self.a == 0.0 or self.b == 0.0:
+            raise ValueError("DilatonAxion with β ≠ 0 needs a ≠ 0 and b ≠ 0")
+        return self.beta / self.b, self.beta / self.a, self.beta / (self.a * self.b)
+
+    def params(self):
+        return _pad8(self.M, self.a, self.beta, self.b, *self.ratios())
+
+
 def _pad8(*vals):
     return tuple(float(v) for v in vals) + (0.0,) * (8 - len(vals))
 
 
-_SUPPORTED_METRICS = (KerrMetric, JohannsenPsaltisMetric, JohannsenMetric, BumblebeeMetric, KerrNewmanMetric, MorrisThorneWormhole)
+_SUPPORTED_METRICS = (KerrMetric, JohannsenPsaltisMetric, JohannsenMetric, BumblebeeMetric, KerrNewmanMetric, MorrisThorneWormhole, DilatonAxion)
 
 
 def _check_metric(m):
@@ -137,6 +160,9 @@ def inner_radius(m) -> float:
     _check_metric(m)
     if isinstance(m, MorrisThorneWormhole):
         return 0.0  # morris-thorne-ad.jl:40
+    if isinstance(m, DilatonAxion):  # dilaton-axion-ad.jl:69-72
+        bb = m.ratios()[0]
+        return m.M + m.b + math.sqrt((m.M + m.b) ** 2 - m.a**2 + m.beta**2 - (m.M - 2 * m.b) * m.M * bb**2)
     q2 = m.Q**2 if isinstance(m, KerrNewmanMetric) else 0.0
     return m.M + math.sqrt(m.M**2 - m.a**2 - q2)
 

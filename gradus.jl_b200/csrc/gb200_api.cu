@@ -159,6 +159,8 @@ static int validate(gb200_ctx* ctx, const gb200_problem* p, const gb200_ic* ic) 
     } else if (!(M > 0) || !(std::fabs(a) <= M)) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "need M > 0 and |a| <= M (M=%g a=%g)", M, a);
     if (p->metric_kind == GB200_METRIC_BUMBLEBEE && (!(p->metric_params[2] > -1.0) || std::fabs(a) > 0.3))
         return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "Bumblebee metric needs l > -1 and |a| <= 0.3 (bumblebee-ad.jl:33-40)");
+    if (p->metric_kind == GB200_METRIC_DILATON_AXION && p->metric_params[2] != 0.0 && (a == 0.0 || p->metric_params[3] == 0.0))
+        return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "Dilaton-Axion metric with beta != 0 needs a != 0 and b != 0 (beta / a, beta / b; dilaton-axion-ad.jl:24-26)");
     if (p->metric_kind == GB200_METRIC_KERR_NEWMAN && a * a + p->metric_params[2] * p->metric_params[2] > M * M)
         return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "Kerr-Newman metric needs a^2 + Q^2 <= M^2 (kerr-newman-ad.jl:50-52)");
     if (p->geometry_kind < GB200_GEOMETRY_NONE || p->geometry_kind > GB200_GEOMETRY_THICK_TABLE)

@@ -465,6 +465,7 @@ GB_HD inline void metric_jacobian_kind(int kind, const double* mp, S r, S s, S c
     case GB200_METRIC_JOHANNSEN: johannsen_metric_jacobian<S>(mp, r, s, c, g, dr, dth); break;
     case GB200_METRIC_BUMBLEBEE: bumblebee_metric_jacobian<S>(mp, r, s, c, g, dr, dth); break;
     case GB200_METRIC_MORRIS_THORNE: morris_thorne_metric_jacobian<S>(mp, r, s, c, g, dr, dth); break;
+    case GB200_METRIC_DILATON_AXION: dilaton_axion_metric_jacobian<S>(mp, r, s, c, g, dr, dth); break;
     default: kerr_newman_metric_jacobian<S>(mp, r, s, c, g, dr, dth); break;
     }
 }

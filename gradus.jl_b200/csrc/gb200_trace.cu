@@ -877,6 +877,7 @@ cudaError_t gb200_launch_trace(const GbParams& P, int sm_count, cudaStream_t str
     case GB200_METRIC_BUMBLEBEE: return launch_geom<GB200_METRIC_BUMBLEBEE>(P, sm_count, stream, blocks_out);
     case GB200_METRIC_KERR_NEWMAN: return launch_geom<GB200_METRIC_KERR_NEWMAN>(P, sm_count, stream, blocks_out);
     case GB200_METRIC_MORRIS_THORNE: return launch_geom<GB200_METRIC_MORRIS_THORNE>(P, sm_count, stream, blocks_out);
+    case GB200_METRIC_DILATON_AXION: return launch_geom<GB200_METRIC_DILATON_AXION>(P, sm_count, stream, blocks_out);
 #endif
     }
     return cudaErrorInvalidValue;
@@ -1056,6 +1057,7 @@ cudaError_t gb200_launch_debug_rhs(const GbParams& P, long long n, const double*
     case GB200_METRIC_JOHANNSEN: gb200_debug_rhs_kernel<GB200_METRIC_JOHANNSEN><<<grid, 128, 0, stream>>>(P, n, d_u, d_du); break;
     case GB200_METRIC_BUMBLEBEE: gb200_debug_rhs_kernel<GB200_METRIC_BUMBLEBEE><<<grid, 128, 0, stream>>>(P, n, d_u, d_du); break;
     case GB200_METRIC_MORRIS_THORNE: gb200_debug_rhs_kernel<GB200_METRIC_MORRIS_THORNE><<<grid, 128, 0, stream>>>(P, n, d_u, d_du); break;
+    case GB200_METRIC_DILATON_AXION: gb200_debug_rhs_kernel<GB200_METRIC_DILATON_AXION><<<grid, 128, 0, stream>>>(P, n, d_u, d_du); break;
     default: gb200_debug_rhs_kernel<GB200_METRIC_KERR_NEWMAN><<<grid, 128, 0, stream>>>(P, n, d_u, d_du); break;
     }
     return cudaGetLastError();

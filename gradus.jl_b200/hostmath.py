@@ -27,6 +27,19 @@ def metric_components(m, r, theta):
         b2l2 = m.b**2 + r * r
         zero = 0 * r + 0 * theta
         return np.stack(np.broadcast_arrays(zero - 1, zero + 1, b2l2 + zero, b2l2 * np.sin(theta), zero))
+    if isinstance(m, api.DilatonAxion):  # dilaton-axion-ad.jl:8-46
+        M, a, be, b = m.M, m.a, m.beta, m.b
+        bb, ba, bab = m.ratios()
+        cth, sth = np.cos(theta), np.sin(theta)
+        sigma = r * r + a * a * cth**2
+        delta = r * r + a * a - 2 * M * r
+        dhat = delta - (be**2 + 2 * b * r) - M * (M + 2 * b) * bb**2
+        shat = sigma - (be**2 + 2 * b * r) + M**2 * bb * (bb - 2 * a * cth)
+        dl = r * r - 2 * b * r + a * a
+        W = 1 + (bab * (2 * cth - bab) + ba**2) / sth**2
+        A = dl**2 - dhat * (W * a * sth) ** 2
+        return np.stack(np.broadcast_arrays(-(dhat - a * a * sth**2) / shat, dhat * 0 + shat / dhat, shat + 0 * r, A * sth**2 / shat,
+                                            -a * (dl - dhat * W) * sth**2 / shat))
     M, a = m.M, m.a
     c2 = np.cos(theta) ** 2
     s2 = np.sin(theta) ** 2

@@ -52,7 +52,9 @@ extern "C" {
                                             Lorentz force q/mu F v of geodesic_ode_problem(::KerrNewmanMetric), :66-102; 0 = neutral) */
 #define GB200_METRIC_MORRIS_THORNE 5     /* src/metrics/morris-thorne-ad.jl:4-15  params: b (throat size, metric_params[0]); r is the proper
                                             radial coordinate l, inner_radius = 0 (:40), no ISCO */
-#define GB200_METRIC_COUNT 6
+#define GB200_METRIC_DILATON_AXION 6     /* src/metrics/dilaton-axion-ad.jl:8-46  params: M, a, beta, b, beta/b, beta/a, beta/(a b) -- the three
+                                            ratios as the reference forms them (0 where beta == 0, :24-26) */
+#define GB200_METRIC_COUNT 7
 
 /* ---- accretion geometry: src/geometry/discs/ --------------------------- */
 #define GB200_GEOMETRY_NONE 0

@@ -105,6 +105,10 @@ _metric(m::JohannsenPsaltisMetric, qμ) = (Int32(1), _mp8(m.M, m.a, m.ϵ3))
 _metric(m::JohannsenMetric, qμ) = (Int32(2), _mp8(m.M, m.a, m.α13, m.α22, m.α52, m.ϵ3))
 _metric(m::BumblebeeMetric, qμ) = (Int32(3), _mp8(m.M, m.a, m.l))
 _metric(m::MorrisThorneWormhole, qμ) = (Int32(5), _mp8(m.b))
+_metric(m::Gradus.DilatonAxion, qμ) = begin   # the ratios as src/metrics/dilaton-axion-ad.jl:24-26 forms them
+    z = iszero(m.β)
+    (Int32(6), _mp8(m.M, m.a, m.β, m.b, z ? 0.0 : m.β / m.b, z ? 0.0 : m.β / m.a, z ? 0.0 : m.β / (m.a * m.b)))
+end
 # slot 4 (metric_params[3]) carries q for photons and q/μ otherwise (geodesic_ode_problem(::KerrNewmanMetric),
 # src/metrics/kerr-newman-ad.jl:74-78)
 _metric(m::KerrNewmanMetric, qμ) = (Int32(4), _mp8(m.M, m.a, m.Q, qμ))

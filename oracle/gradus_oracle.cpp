@@ -164,6 +164,21 @@ void metric_components(const Metric& m, const S& r, const S& th, S g[5]) {
         g[2] = sq(r);
         g[3] = sq(r) * sinth2;
         g[4] = -S(2.0) * M * a * sinth2 / r;
+    } else if (m.kind == GB200_METRIC_DILATON_AXION) { // src/metrics/dilaton-axion-ad.jl:8-46; p = (M, a, beta, b, beta/b, beta/a, beta/(a b))
+        S M = S(m.M), a = S(m.a), be = S(m.p[2]), b = S(m.p[3]), bb = S(m.p[4]), ba = S(m.p[5]), bab = S(m.p[6]);
+        S cth = rcos(th), sth = rsin(th);
+        S Sigma = sq(r) + sq(a) * sq(cth);
+        S Delta = sq(r) + sq(a) - S(2.0) * M * r;
+        S Dhat = Delta - (sq(be) + S(2.0) * b * r) - M * (M + S(2.0) * b) * sq(bb);
+        S Shat = Sigma - (sq(be) + S(2.0) * b * r) + sq(M) * bb * (bb - S(2.0) * a * cth);
+        S dl = sq(r) - S(2.0) * b * r + sq(a);
+        S W = S(1.0) + (bab * (S(2.0) * cth - bab) + sq(ba)) / sq(sth);
+        S A = sq(dl) - Dhat * sq(W * a * sth);
+        g[0] = -(Dhat - sq(a) * sq(sth)) / Shat;
+        g[1] = Shat / Dhat;
+        g[2] = Shat;
+        g[3] = A * sq(sth) / Shat;
+        g[4] = -a * (dl - Dhat * W) * sq(sth) / Shat;
     } else if (m.kind == GB200_METRIC_MORRIS_THORNE) { // src/metrics/morris-thorne-ad.jl:4-15 (b = m.p[0]; sin, not sin^2, :11)
         S b2l2 = S(m.p[0] * m.p[0]) + sq(r);
         g[0] = S(-1.0);
@@ -202,6 +217,10 @@ void metric_components(const Metric& m, const S& r, const S& th, S g[5]) {
 // src/metrics/kerr-metric.jl:72, johannsen-psaltis-ad.jl:50
 inline double inner_radius(const Metric& m) {
     if (m.kind == GB200_METRIC_MORRIS_THORNE) return 0.0; // morris-thorne-ad.jl:40
+    if (m.kind == GB200_METRIC_DILATON_AXION) { // dilaton-axion-ad.jl:69-72
+        const double b = m.p[3], bb = m.p[4];
+        return m.M + b + std::sqrt((m.M + b) * (m.M + b) - m.a * m.a + m.p[2] * m.p[2] - (m.M - 2.0 * b) * m.M * bb * bb);
+    }
     const double q2 = (m.kind == GB200_METRIC_KERR_NEWMAN) ? m.p[2] * m.p[2] : 0.0; // kerr-newman-ad.jl:65
     return m.M + std::sqrt(m.M * m.M - m.a * m.a - q2);
 }

@@ -33,6 +33,8 @@ NONTRIVIAL = [
     gb.KerrNewmanMetric(M=1.0, a=0.6, Q=0.5),
 ]
 IDS = ["johannsen", "bumblebee", "kerr_newman"]
+# Einstein-Maxwell-Dilaton-Axion (src/metrics/dilaton-axion-ad.jl): no entry in the smoke matrix; pinned on its ISCO literals
+DILATON = [gb.DilatonAxion(M=1.0, a=0.5, beta=0.0, b=0.3), gb.DilatonAxion(M=1.0, a=0.6, beta=0.2, b=0.5)]
 
 
 def _smoke_fixture(m, d):
@@ -50,7 +52,18 @@ def test_oracle_reproduces_the_smoke_matrix(m, shadow, thin, ss):
     assert np.nansum(oracle.render(p, ic, [cabi.PF_SHADOW])[0]) == pytest.approx(ss, rel=1e-9)
 
 
-@pytest.mark.parametrize("m", NONTRIVIAL, ids=IDS)
+def test_dilaton_axion_isco_literals():
+    """test/smoke-tests/special-radii.jl:20-22,34-36: 29.701502242023523 and 6.0 (atol 1e-5 there)."""
+    m = gb.DilatonAxion(M=1.0, a=0.6, beta=-0.5, b=0.1)
+    assert api.isco(m) == pytest.approx(29.701502242023523, abs=1e-9)
+    assert oracle.isco(m.kind, list(m.params())) == pytest.approx(29.701502242023523, abs=1e-9)
+    assert api.isco(gb.DilatonAxion(M=1.0, a=0.0, beta=0.0, b=0.0)) == pytest.approx(6.0, abs=1e-9)
+    assert api.inner_radius(gb.DilatonAxion(1.0, 0.5, 0.0, 1.0)) == pytest.approx(2.0 + math.sqrt(4.0 - 0.25))
+    with pytest.raises(ValueError):
+        gb.DilatonAxion(1.0, 0.0, 0.3, 1.0).params()  # β / a
+
+
+@pytest.mark.parametrize("m", NONTRIVIAL + DILATON, ids=IDS + ["dilaton_axion", "dilaton_axion_beta"])
 def test_host_and_oracle_metric_algebra_agree(m):
     mp = list(m.params())
     for r, th in [(3.0, 0.4), (9.0, 1.3), (250.0, 2.2)]:
@@ -162,7 +175,7 @@ def test_device_reproduces_the_smoke_matrix(m, shadow, thin, ss):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("m", NONTRIVIAL, ids=IDS)
+@pytest.mark.parametrize("m", NONTRIVIAL + DILATON, ids=IDS + ["dilaton_axion", "dilaton_axion_beta"])
 def test_device_matches_oracle_at_nontrivial_parameters(m):
     x = [0.0, 1000.0, math.radians(70), 0.0]
     d = gb.ThinDisc(api.isco(m), 40.0)
