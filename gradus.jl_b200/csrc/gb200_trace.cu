@@ -244,7 +244,10 @@ __device__ __noinline__ void gb_hist_add(const GbParams& P, unsigned long long* 
 #ifdef GB_MAXRREG /* tuning: explicit register cap instead of the occupancy target */
 #define GB_LAUNCH_BOUNDS __maxnreg__(GB_MAXRREG)
 #else
-#define GB_LAUNCH_BOUNDS __launch_bounds__(GB_BLOCK, GB_MIN_BLOCKS)
+#ifndef GB_MIN_BLOCKS_KERR
+#define GB_MIN_BLOCKS_KERR GB_MIN_BLOCKS /* the Kerr instantiations tolerate 16 warps per SM at 128 registers (tuning log) */
+#endif
+#define GB_LAUNCH_BOUNDS __launch_bounds__(GB_BLOCK, (METRIC == GB200_METRIC_KERR ? GB_MIN_BLOCKS_KERR : GB_MIN_BLOCKS))
 #endif
 template <int METRIC, int GEOM>
 __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbParams P) {
