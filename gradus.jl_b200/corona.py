@@ -38,6 +38,18 @@ class BeamedPointSource:
 
 
 @dataclass(frozen=True)
+class RingCorona:
+    """`RingCorona(vf, r, h)` (src/corona/models/extended.jl:56-80): a ring of radius r at height h above the disc; `vf` is
+    one of `SourceVelocities` ("co_rotating", "stationary").  Position and four-velocity of the source point are built here;
+    sky-sampled ray fans (`tracecorona`) run on the device like any other explicit-IC ensemble.  The reference's
+    time-dependent ring emissivity (its longitudinal-arm sampling, ring.jl) is not built."""
+
+    r: float = 5.0
+    h: float = 5.0
+    vf: str = "co_rotating"
+
+
+@dataclass(frozen=True)
 class PowerLawSpectrum:
     """`coronal_spectrum(spec, g) = g^-Γ`, src/corona/spectra.jl:11-25"""
 
@@ -60,6 +72,21 @@ def sample_position_velocity(m, model):
         # constrain_normalize(m, x, (1, drdt, 0, 0); μ = 1): scale to g(v, v) = −1
         v = np.array([1.0, drdt, 0.0, 0.0])
         return x, v / math.sqrt(-hostmath.dot(g, v, v))
+    if isinstance(model, RingCorona):
+        x = np.array([0.0, math.hypot(model.r, model.h), math.atan2(model.r, model.h), 0.0])
+        g = hostmath.metric_components(m, x[1], x[2])
+        if model.vf == "stationary":  # SourceVelocities.stationary (extended.jl:27-41)
+            return x, np.array([1.0 / math.sqrt(-g[0]), 0.0, 0.0, 0.0])
+        if model.vf != "co_rotating":
+            raise ValueError("RingCorona.vf must be 'co_rotating' or 'stationary'")
+        # SourceVelocities.co_rotating (extended.jl:13-25): the Keplerian four-velocity of the disc below, scaled by sin θ,
+        # normalised at x, then constrain_all for a unit-mass particle
+        s = math.sin(x[2])
+        v = np.asarray(hostmath.circular_fourvelocity(m, max(api.isco(m), x[1] * s)), np.float64) * s
+        v = v / math.sqrt(abs(hostmath.dot(g, v, v)))
+        disc = -g[0] * g[1] * v[1] ** 2 - g[0] * g[2] * v[2] ** 2 - g[0] - (g[0] * g[3] - g[4] ** 2) * v[3] ** 2
+        v[0] = -(g[4] * v[3] + math.sqrt(disc)) / g[0]
+        return x, v
     raise ValueError(f"corona model {type(model).__name__} has no position/velocity sampler here")
 
 

@@ -223,3 +223,30 @@ def test_corona_models_trace_with_every_sampler(sampler):
     assert hits.shape[0] == 4 and hits.shape[1] <= 32 and (hits.shape[1] > 0 or not (isinstance(sampler, corona.EvenSampler) and sampler.generator == "golden"))
     rho = hits[1] * np.abs(np.sin(hits[2]))
     assert np.all((rho >= gb.isco(m) * (1 - 1e-9)) & (rho <= 50.0 * (1 + 1e-9)))
+
+
+def test_beamed_source_tetrad_and_ring_corona_velocity():
+    """test/unit/coronal-beaming.jl: dr/dt of a beamed source against Gonzalez+17 eq. (8), the generic tetrad against their
+    analytic one (eq. 10, metric signature flipped), and the co-rotating velocity of a ring corona (rtol 1e-3 there)."""
+    m = gb.KerrMetric(1.0, 0.998)
+    x = np.array([0.0, 3.0, math.radians(0.01), 0.0])
+    g = hostmath.metric_components(m, x[1], x[2])
+    drdt = lambda beta: beta * math.sqrt(-g[0] / g[1])  # noqa: E731
+    assert drdt(1.0) == pytest.approx((x[1] ** 2 - 2 * x[1] + m.a**2) / (x[1] ** 2 + m.a**2), rel=1e-6)
+    v = drdt(0.25)
+    A = 1.0 / math.sqrt(-g[0] - v * v * g[1])
+    B = math.sqrt(-g[1] / g[0])
+    Cn = 1.0 / math.sqrt(-g[0] * (g[4] ** 2 - g[0] * g[3]))
+    analytic = np.array([A * np.array([1.0, v, 0.0, 0.0]), A * np.array([v * B, 1.0 / B, 0.0, 0.0]), [0.0, 0.0, math.sqrt(1.0 / g[2]), 0.0],
+                         Cn * np.array([g[4], 0.0, 0.0, -g[0]])])
+    G = hostmath.metric_matrix(g)
+    eta = np.diag([-1.0, 1.0, 1.0, 1.0])
+    assert np.allclose(analytic @ G @ analytic.T, eta, atol=1e-9)
+    generic = np.array(hostmath.tetradframe(G, np.array([1.0, v, 0.0, 0.0])))
+    assert np.allclose(generic @ G @ generic.T, eta, atol=1e-9)
+    assert np.allclose(generic, analytic, rtol=1e-8, atol=1e-10)
+    _, vel = corona.sample_position_velocity(m, corona.RingCorona(r=2.082, h=50.0))
+    lit = np.array([1.204, 0.0, 0.0, 0.300])  # quoted to four digits; Julia's `≈` on vectors compares norms
+    assert np.linalg.norm(vel - lit) <= 1e-3 * max(np.linalg.norm(vel), np.linalg.norm(lit))
+    pos, vel = corona.sample_position_velocity(m, corona.RingCorona(r=2.082, h=50.0, vf="stationary"))
+    assert hostmath.dot(hostmath.metric_components(m, pos[1], pos[2]), vel, vel) == pytest.approx(-1.0, abs=1e-12)
