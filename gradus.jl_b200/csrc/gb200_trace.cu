@@ -680,7 +680,7 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
             const bool accept = gb_le_one_pos(EEst2);
             const bool fast32 = (P.pow_mode == GB200_POW_FAST32);
 #if GB_OPT_LOGEXP
-            const double logE = 0.5 * gb_log_pos(EEst2);
+            const double logE = 0.5 * (GB_OPT_CTRL_LO ? gb_log_pos_lo(EEst2) : gb_log_pos(EEst2));
 #else
             const double logE = 0.5 * log(EEst2);
 #endif
@@ -709,7 +709,8 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
             } else {
                 const double arg = accept ? fma(beta1, logE, -qoldpow) : beta1 * logE; // qoldpow = beta2 * log(qold) in this mode
 #if GB_OPT_LOGEXP
-                Epow = gb_exp_small(gb_max(-8.0, gb_min(8.0, arg))); // q is clamped to [1/qmax, 1/qmin] = exp(-2.2 .. 1.7) afterwards
+                const double carg = gb_max(-8.0, gb_min(8.0, arg));
+                Epow = GB_OPT_CTRL_LO ? gb_exp_small_lo(carg) : gb_exp_small(carg); // q is clamped to [1/qmax, 1/qmin] = exp(-2.2 .. 1.7) afterwards
 #else
                 Epow = exp(arg);
 #endif

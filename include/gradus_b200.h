@@ -74,7 +74,9 @@ extern "C" {
 #define GB200_CALLBACK_UPPER_HEMISPHERE 1 /* r cos(theta) < delta -> OutOfDomain */
 
 /* ---- step-controller pow(): DiffEqBase.fastpow is version dependent ---- */
-#define GB200_POW_EXACT 0 /* IEEE double pow */
+#define GB200_POW_EXACT 0 /* x^y through double-precision log and exp.  In the throughput kernel the error estimate carries a relative
+                            2^-20 from its scale reciprocals and the pair is evaluated to 1e-7; the forward-mode
+                            kernel and the oracle evaluate it with libm */
 #define GB200_POW_FAST32 1 /* Float32 exp2(y*log2(x)) a la FastPower.jl */
 
 /* ---- integrator failure flags (SciML retcodes are invisible in GeodesicPoint) */
