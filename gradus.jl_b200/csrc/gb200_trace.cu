@@ -45,6 +45,9 @@
 #define GB_OPT_LOGEXP 1 /* branch-free log/exp with constant-bank coefficients in the step controller */
 #endif
 
+#ifndef GB_OPT_QRCP_LO
+#define GB_OPT_QRCP_LO 0
+#endif
 #ifndef GB_OPT_INVQ
 #define GB_OPT_INVQ 0 /* step-size update from 1/q = clamp(gamma exp(-arg)): no reciprocal, no division on the reject path */
 #endif
@@ -697,7 +700,8 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
                 Einv = gb_rcp(Epow);
             } else {
                 const double arg = accept ? fma(beta1, logE, -qoldpow) : beta1 * logE; // qoldpow = beta2 * log(qold) in this mode
-                Einv = gb_exp_small(gb_max(-8.0, gb_min(8.0, -arg))); // 1/q is clamped to [qmin, qmax] = exp(-1.7 .. 2.3) afterwards
+                const double narg = gb_max(-8.0, gb_min(8.0, -arg));
+                Einv = GB_OPT_CTRL_LO ? gb_exp_small_lo(narg) : gb_exp_small(narg); // 1/q is clamped to [qmin, qmax] = exp(-1.7 .. 2.3) afterwards
             }
             const double gEinv = gamma * Einv;
             const double dtnew = dt * gb_max_pos(qmin, gb_min_pos(qmax, gEinv));
@@ -719,7 +723,11 @@ __global__ void GB_LAUNCH_BOUNDS gb200_trace_kernel(const __grid_constant__ GbPa
             // ---- accept / reject, callbacks and the commit of the step.  Everything up to the commit is computed
             // unconditionally and committed with selects: the loop-carried state then lives in the same registers on
             // every path (the branchy form cost ~200 register moves per attempt where the paths merged).
+#if GB_OPT_QRCP_LO /* q is known to 1e-7: one Newton step on the reciprocal seed (2^-40) */
+            const double dtnew = dt * gb_rcp_lo(q);
+#else
             const double dtnew = dt * gb_rcp(q);
+#endif
 #endif
             const double ttmp = lam + dt;
             const double tnew = (fabs(ttmp - tstop) < 100.0 * (fabs(tstop) * 2.220446049250313e-16)) ? tstop : ttmp;
