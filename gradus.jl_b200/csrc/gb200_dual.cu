@@ -61,6 +61,7 @@ cudaError_t gb200_launch_dual(const GbParams& P, const GbDualIO& io, cudaStream_
 // ---------------------------------------------------------------- closest approach to a target point
 // The objective of optimize_for_target (src/tracing/precision-solvers.jl:452-546) over a set of rays: one ray per thread
 // through the generic integrator with the distance condition (disc_condition_g, GB200_GEOMETRY_TARGET_POINT).
+template <int MK>
 __global__ void __launch_bounds__(64) gb200_target_kernel(const __grid_constant__ GbParams P) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.count) return;
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(64) gb200_target_kernel(const __grid_constant_
     GD<0> u[8];
     for (int k = 0; k < 4; ++k) { u[k] = GD<0>(ri.x[k]); u[4 + k] = GD<0>(ri.v[k]); }
     GenResult<0> res;
-    gen_trace_ray<0, -1>(P, u, 0.0, false, res, GbNoRecord());
+    gen_trace_ray<0, MK>(P, u, 0.0, false, res, GbNoRecord());
     if (P.o_status) P.o_status[s] = res.status;
     if (P.o_lambda) P.o_lambda[s] = res.lambda;
     for (int k = 0; k < 4; ++k) {
@@ -86,7 +87,9 @@ __global__ void __launch_bounds__(64) gb200_target_kernel(const __grid_constant_
 
 cudaError_t gb200_launch_target(const GbParams& P, cudaStream_t stream) {
     if (P.count <= 0) return cudaSuccess;
-    gb200_target_kernel<<<(unsigned)((P.count + 63) / 64), 64, 0, stream>>>(P);
+    const unsigned grid = (unsigned)((P.count + 63) / 64);
+    if (P.metric_kind == GB200_METRIC_KERR) gb200_target_kernel<GB200_METRIC_KERR><<<grid, 64, 0, stream>>>(P);
+    else gb200_target_kernel<-1><<<grid, 64, 0, stream>>>(P);
     return cudaGetLastError();
 }
 
