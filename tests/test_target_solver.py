@@ -117,3 +117,24 @@ def test_continuum_time_with_the_oracle():
     t = gb.reverberation.continuum_time(m, x, model, tracer=oracle_target_tracer, grid=17)
     flat = math.sqrt(1000.0**2 + 10.0**2 - 2 * 1000.0 * 10.0 * math.cos(math.radians(60)))
     assert flat < t < flat + 2.0 * 2.0 * math.log(1000.0 / 10.0) + 5.0
+
+
+@pytest.mark.gpu
+def test_target_entry_point_validates_its_arguments():
+    import ctypes as C
+    cfg = api.tracing_configuration(M, X0, api.ImpactParameters(np.array([0.0]), np.array([11.0])), gb.ThinDisc(0.0, 50.0), 2000.0, trajectories=1)
+    with pytest.raises(gb.GradusB200Error):  # the distance callback takes the geometry's place
+        api.trace_target(cfg, (10.0, 0.5, 0.0), 1e-2)
+    cfg = api.tracing_configuration(M, X0, api.ImpactParameters(np.array([0.0]), np.array([11.0])), 2000.0, trajectories=1)
+    with pytest.raises(gb.GradusB200Error):
+        api.trace_target(cfg, (10.0, 0.5, 0.0), 0.0)
+    with pytest.raises(ValueError):
+        api.trace_target(cfg, (10.0, 0.5), 1e-2)
+    # an empty range is not an error
+    p, ic = cfg.to_c()
+    ens = cfg.ensemble
+    ctx = ens.ctx(ens.devices[0])
+    tgt = np.array([10.0, 0.5, 0.0])
+    closest = np.zeros(1)
+    rc = cabi.load().gb200_trace_target(ctx, C.byref(p), C.byref(ic), C.byref(cabi.Range(0, 0, 1)), cabi.dptr(tgt), 1e-2, None, cabi.dptr(closest))
+    assert rc == cabi.OK
