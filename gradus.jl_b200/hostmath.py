@@ -247,11 +247,12 @@ _TS_BT = [-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995,
           -0.45808210592918697, 0.015151515151515152]
 
 
-def tsit5_solve(f, u0, t_end, *, dtmax, abstol=1e-6, reltol=1e-3, terminate=None, maxiters=100000):
+def tsit5_solve(f, u0, t_end, *, dtmax, abstol=1e-6, reltol=1e-3, terminate=None, maxiters=100000, return_times=False):
     """`solve(ODEProblem(f, u0, (0, t_end)), Tsit5(); dtmax, callback = DiscreteCallback(terminate, terminate!))` with
     OrdinaryDiffEq's defaults (abstol 1e-6, reltol 1e-3, PI controller, Hairer-Wanner initial step), every accepted step
     saved: the set-up ODEs of the reference that run on the host (the isobar of `PolishDoughnut`,
-    src/geometry/discs/polish-doughnut.jl:66-100).  Returns the list of saved states (initial state first)."""
+    src/geometry/discs/polish-doughnut.jl:66-100).  Returns the list of saved states (initial state first), with their times
+    when `return_times` is set."""
     u = np.asarray(u0, np.float64)
     norm = lambda x: math.sqrt(float(np.mean(x * x)))  # noqa: E731  (ODE_DEFAULT_NORM)
     t, f0 = 0.0, np.asarray(f(u), np.float64)
@@ -265,7 +266,7 @@ def tsit5_solve(f, u0, t_end, *, dtmax, abstol=1e-6, reltol=1e-3, terminate=None
     dt1 = max(1e-6, dt0 * 1e-3) if md <= 1e-15 else 10.0 ** (-(2.0 + math.log10(md)) / 5.0)
     dt = min(100.0 * dt0, dt1, dtmax)
     beta1, beta2, gamma, qmin, qmax, qold = 7.0 / 50.0, 2.0 / 25.0, 0.9, 0.2, 10.0, 1e-4
-    out, k1 = [u.copy()], f0
+    out, times, k1 = [u.copy()], [0.0], f0
     for _ in range(maxiters):
         dt = min(dt, t_end - t)
         ks = [k1]
@@ -287,7 +288,8 @@ def tsit5_solve(f, u0, t_end, *, dtmax, abstol=1e-6, reltol=1e-3, terminate=None
         t += dt
         u, k1 = unew, ks[6]
         out.append(u.copy())
+        times.append(t)
         if (terminate is not None and terminate(u)) or t >= t_end:
             break
         dt = min(dt / q, dtmax)
-    return out
+    return (times, out) if return_times else out

@@ -396,3 +396,16 @@ def test_special_radii_and_circular_orbit_literals():
                        (gb.KerrMetric(1.0, -1.0), 0.5993458160081419), (gb.JohannsenMetric(1.0, 1.0, alpha22=1.0), 0.4980454719932759)]:
         total = sum(hostmath.circular_fourvelocity(m, r)[3] for r in rs)
         assert total == pytest.approx(literal, abs=1e-6)  # measured 2e-10 ... 9.8e-7 (the optimiser's own tolerance)
+
+
+def test_host_tsit5_on_known_solutions():
+    """`hostmath.tsit5_solve` (the set-up integrator behind `PolishDoughnut`): exponential decay and a harmonic oscillator with a
+    discrete termination, at OrdinaryDiffEq's default tolerances; dtmax is honoured and every accepted step is saved."""
+    sol = hostmath.tsit5_solve(lambda u: -u, [1.0], 2.0, dtmax=0.5)
+    assert sol[-1][0] == pytest.approx(math.exp(-2.0), rel=2e-4) and len(sol) >= 5
+    ts, sol = hostmath.tsit5_solve(lambda u: np.array([u[1], -u[0]]), [0.0, 1.0], 10.0, dtmax=0.05, terminate=lambda u: u[0] < 0.0,
+                                   return_times=True)
+    ts, x = np.array(ts), np.array([u[0] for u in sol])
+    assert np.all(x[:-1] >= 0.0) and x[-1] < 0.0                  # stops at the first step that ends below zero ...
+    assert math.pi < ts[-1] < math.pi + 0.05 + 1e-12              # ... i.e. within one dtmax after t = pi
+    assert np.max(np.diff(ts)) <= 0.05 + 1e-15 and np.max(np.abs(x - np.sin(ts))) < 1e-6
