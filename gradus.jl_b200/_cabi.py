@@ -107,7 +107,7 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = (
     "gb200_version", "gb200_init", "gb200_destroy", "gb200_last_error", "gb200_get_stats", "gb200_validate",
     "gb200_isco", "gb200_radiative_efficiency", "gb200_trace", "gb200_trace_batch", "gb200_trace_path", "gb200_build_plunging_table", "gb200_render", "gb200_lineprofile",
-    "gb200_render_batch", "gb200_render_device", "gb200_lineprofile_device", "gb200_fp64_peak", "gb200_fp64_issue_probe", "gb200_debug_rhs", "gb200_debug_math",
+    "gb200_render_batch", "gb200_render_device", "gb200_lineprofile_device", "gb200_fp64_peak", "gb200_fp64_issue_probe", "gb200_debug_rhs", "gb200_debug_math", "gb200_debug_math_lo",
     "gb200_trace_dual", "gb200_trace_dual_batch", "gb200_trace_target",
     "gb200_set_cross_section", "gb200_bucket2d", "gb200_comm_init", "gb200_comm_destroy", "gb200_comm_size", "gb200_comm_context", "gb200_comm_lineprofile", "gb200_comm_render",
 )
@@ -244,6 +244,7 @@ def load():
     lib.gb200_fp64_issue_probe.argtypes = [vp, C.c_int32, _dp]
     lib.gb200_debug_rhs.argtypes = [vp, C.c_int32, _dp, C.c_int64, _dp, _dp]
     lib.gb200_debug_math.argtypes = [vp, C.c_int64, _dp, _dp]
+    lib.gb200_debug_math_lo.argtypes = [vp, C.c_int64, _dp, _dp]
     lib.gb200_trace_dual.argtypes = [vp, C.POINTER(Problem), C.POINTER(DualIC), C.c_int32, C.POINTER(PlungingTable), C.POINTER(DualOut)]
     lib.gb200_trace_dual_batch.argtypes = [vp, C.c_int32, C.POINTER(Problem), C.POINTER(DualIC), C.c_int32,
                                            C.POINTER(C.POINTER(PlungingTable)), C.POINTER(DualOut)]

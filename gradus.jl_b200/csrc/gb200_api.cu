@@ -1627,6 +1627,19 @@ int gb200_debug_math(gb200_ctx* ctx, int64_t n, const double* x, double* out5) {
     return GB200_OK;
 }
 
+int gb200_debug_math_lo(gb200_ctx* ctx, int64_t n, const double* x, double* out2) {
+    if (!ctx || !x || !out2 || n < 1) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "bad arguments");
+    { int rc_ = begin_call(ctx, ctx->stream); if (rc_) return rc_; }
+    void *d_x, *d_o;
+    int rc = pool_get(ctx, SL_X0, sizeof(double) * (size_t)n, &d_x); if (rc) return rc;
+    rc = pool_get(ctx, SL_V0, sizeof(double) * 2 * (size_t)n, &d_o); if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(d_x, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, gb200_launch_debug_math_lo(n, (const double*)d_x, (double*)d_o, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(out2, d_o, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB200_OK;
+}
+
 int gb200_fp64_peak(gb200_ctx* ctx, double* tflops_out) {
     if (!ctx || !tflops_out) return fail(ctx, GB200_ERR_INVALID_ARGUMENT, "null argument");
     { int rc_ = begin_call(ctx, ctx->stream); if (rc_) return rc_; }

@@ -14,6 +14,7 @@ cudaError_t gb200_launch_dfma_mix(double* d_out, int blocks, int iters, int mix,
 cudaError_t gb200_launch_path(const GbParams& P, const double* d_u0, int cap, double* d_lambda, double* d_u, int* d_meta, cudaStream_t stream);
 cudaError_t gb200_launch_debug_rhs(const GbParams& P, long long n, const double* d_u, double* d_du, cudaStream_t stream);
 cudaError_t gb200_launch_debug_math(long long n, const double* d_x, double* d_out5, cudaStream_t stream);
+cudaError_t gb200_launch_debug_math_lo(long long n, const double* d_x, double* d_out2, cudaStream_t stream);
 
 // forward-mode (dual-number) traces and the single-ray path recorder: gb200_dual.cu
 struct GbDualIO {

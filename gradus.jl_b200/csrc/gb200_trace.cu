@@ -1061,6 +1061,16 @@ __global__ void gb200_debug_math_kernel(long long n, const double* __restrict__ 
     out5[5 * i + 3] = gb_log_pos(fabs(x[i]));
     out5[5 * i + 4] = gb_exp_small(fmax(-8.0, fmin(8.0, x[i])));
 }
+__global__ void gb200_debug_math_lo_kernel(long long n, const double* __restrict__ x, double* __restrict__ out2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out2[2 * i] = gb_log_pos_lo(fabs(x[i]));
+    out2[2 * i + 1] = gb_exp_small_lo(fmax(-8.0, fmin(8.0, x[i])));
+}
+cudaError_t gb200_launch_debug_math_lo(long long n, const double* d_x, double* d_out2, cudaStream_t stream) {
+    gb200_debug_math_lo_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, d_x, d_out2);
+    return cudaGetLastError();
+}
 cudaError_t gb200_launch_debug_rhs(const GbParams& P, long long n, const double* d_u, double* d_du, cudaStream_t stream) {
     const unsigned grid = (unsigned)((n + 127) / 128);
     switch (P.metric_kind) {

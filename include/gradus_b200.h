@@ -422,6 +422,9 @@ int gb200_comm_render(gb200_comm* comm, const gb200_problem* p, const gb200_ic* 
    oracle's AD-based RHS and libm directly. */
 int gb200_debug_rhs(gb200_ctx* ctx, int32_t metric_kind, const double* metric_params, int64_t n, const double* u, double* du);
 int gb200_debug_math(gb200_ctx* ctx, int64_t n, const double* x, double* out5);
+/* The step controller's own log and exp (evaluated to 1e-7, the accuracy of the error estimate they act on):
+   out2 = n x 2: log|x|, exp(clamp(x, -8, 8)). */
+int gb200_debug_math_lo(gb200_ctx* ctx, int64_t n, const double* x, double* out2);
 
 /* Dependent-free DFMA micro-benchmark: measured FP64 FMA throughput of the
    device in TFLOP/s (2 flop per FMA); the roofline denominator. */
