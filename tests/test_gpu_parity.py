@@ -813,3 +813,35 @@ def test_seeded_random_line_profiles(ensemble, seed):
     print(f"random line profile {seed}: {type(m).__name__} {tuple(round(v, 3) for v in m.params()[:3])} theta {math.degrees(x[2]):.1f} index {index:.2f} max_re {max_re:.1f} {nb} bins "
           f"{type(grid).__name__}: L1 = {l1:.2e}")
     assert flux.sum() == pytest.approx(1.0, abs=1e-12) and l1 < 1e-4
+
+
+def _random_config_planes_and_fans(seed, ensemble):
+    """Image planes (polar / Cartesian, every grid kind) with the hemisphere callback, and explicit-IC fans from an off-axis
+    source with random directions: the remaining initial-condition kinds under the main protocol."""
+    rng = np.random.default_rng(5300 + seed)
+    m = gb.KerrMetric(1.0, float(rng.uniform(-0.9, 0.998)))
+    d = gb.ThinDisc(0.0 if seed % 2 else gb.isco(m), float(rng.uniform(30.0, 120.0)))
+    grid = (gb.LinearGrid(), gb.GeometricGrid(), gb.InverseGrid())[seed % 3]
+    x = [0.0, 1000.0, math.radians(float(rng.uniform(20.0, 80.0))), 0.0]
+    if seed < 3:
+        plane = gb.PolarPlane(grid, Nr=48, Ntheta=64, r_min=1.0, r_max=float(rng.uniform(60.0, 150.0)))
+        return tracing_configuration(m, x, plane, d, (0.0, 2200.0), callback=gb.domain_upper_hemisphere(), ensemble=ensemble)
+    if seed < 6:
+        plane = gb.CartesianPlane(grid, x_min=0.1, y_min=0.1, x_max=float(rng.uniform(40.0, 100.0)), y_max=float(rng.uniform(30.0, 80.0)), Nx=40, Ny=40)
+        return tracing_configuration(m, x, plane, d, (0.0, 2200.0), callback=gb.domain_upper_hemisphere(), ensemble=ensemble)
+    # a source off the axis, rays in random directions (unnormalised: the library constrains v^t like constrain_all)
+    n = 2000
+    src = [0.0, float(rng.uniform(4.0, 30.0)), float(rng.uniform(0.2, 1.2)), float(rng.uniform(0.0, 6.0))]
+    dirs = rng.normal(size=(n, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    vs = np.stack([np.zeros(n), dirs[:, 0], dirs[:, 1] / src[1], dirs[:, 2] / (src[1] * math.sin(src[2]))], axis=1)
+    return tracing_configuration(m, src, vs, d, 5000.0, callback=gb.domain_upper_hemisphere(), ensemble=ensemble)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(9))
+def test_seeded_random_planes_and_fans(ensemble, seed):
+    cfg = _random_config_planes_and_fans(seed, ensemble)
+    p, ic, ref, gps, band = check_parity(cfg, f"random plane / fan {seed}", max_band=0.01)
+    print(f"random plane / fan {seed}: ic kind {ic.kind}, {ic.n} rays, band {band.mean():.3%}, status counts {np.bincount(ref.status, minlength=4)}")
+    assert (ref.status == cabi.STATUS_INTERSECTED).sum() > 50
