@@ -398,6 +398,15 @@ def run_callers(ens):
     dt = time.perf_counter() - t0
     out["emissivity_profiles"] = {"workload": "lamp post, 10 spins x 10 heights, 1000 rays each, one gb200_trace_batch",
                                   "seconds": dt, "profiles_per_s": len(grid) / dt, "rays": 1000 * len(grid)}
+    # the target solver (optimize_for_target through gb200_trace_target): the reference's own test target
+    from gradus_b200 import api
+    mt, xt, target = gb.KerrMetric(1.0, 1.0), [0.0, 1000.0, math.pi / 2, 0.0], (10.0, math.radians(40), -math.pi / 4)
+    api.optimize_for_target(target, mt, xt, ensemble=ens)
+    t0 = time.perf_counter()
+    a_, b_, _, acc = api.optimize_for_target(target, mt, xt, ensemble=ens)
+    out["target_solver"] = {"workload": "optimize_for_target, Kerr a=1, observer r=1000 at 90deg, target (10, 40deg, -45deg), d_tol=1e-2: "
+                                        "33 x 33 impact parameters per launch, re-centred and shrunk until the best ray is within d_tol",
+                            "seconds": time.perf_counter() - t0, "alpha": a_, "beta": b_, "closest_approach": acc}
     return out
 
 
